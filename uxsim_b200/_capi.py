@@ -1,0 +1,306 @@
+"""ctypes binding of the C-ABI declared in ``include/uxsim_b200.h``.
+
+This is the only place the package touches native code.  ``load_product()`` loads
+``uxsim_b200/libuxsim_b200.so`` (hand-written sm_100a CUDA + C++ host driver, built by
+``__graft_entry__.build()``) and raises if it is missing: there is no CPU fallback.
+
+The binding class is generic over the symbol prefix so that the test-suite can drive the two
+test-infrastructure libraries that export the same ABI (``oracle/liboracle.so`` with prefix ``uxo_`` and
+``oracle/_ref/libuxsim_ref.so`` with prefix ``uxr_``) through identical code; the package itself never
+loads those.
+
+Reference counterpart: the nanobind module ``uxsim_cpp`` (uxsim/trafficpp/bindings.cpp) as used by
+uxsim/uxsim_cpp_wrapper.py:26-37.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "libuxsim_b200.so")
+
+# ---- constants mirrored from include/uxsim_b200.h -------------------------------------------------
+UX_OK = 0
+UX_ERR_RUNTIME, UX_ERR_INVALID, UX_ERR_OUT_OF_RANGE, UX_ERR_CUDA, UX_ERR_CAPACITY = -1, -2, -3, -4, -5
+VS_HOME, VS_WAIT, VS_RUN, VS_END, VS_ABORT = 0, 1, 2, 3, 4
+
+LINK_VMAX, LINK_KAPPA, LINK_CAPACITY_OUT, LINK_CAPACITY_IN = 1, 2, 3, 4
+LINK_CAPACITY_OUT_REMAIN, LINK_CAPACITY_IN_REMAIN, LINK_MERGE_PRIORITY, LINK_ROUTE_CHOICE_PENALTY = 5, 6, 7, 8
+
+I_NUM_NODES, I_NUM_LINKS, I_NUM_VEHICLES, I_TIMESTEP, I_TOTAL_TIMESTEPS, I_NUM_REPLICAS = 1, 2, 3, 4, 5, 6
+I_ROUTE_UPDATE_STEPS, I_PLATOON_UPDATES, I_TRIPS_COMPLETED, I_LOG_ENTRIES, I_KERNEL_LAUNCHES = 7, 8, 9, 10, 11
+I_NUM_ACTIVE_DESTS, I_TRANSFER_LEVELS, I_LINK_EVENTS = 12, 13, 14
+D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT = 1, 2, 3, 4, 5
+
+A_CUM_ARRIVAL, A_CUM_DEPARTURE, A_TRAVELTIME_INSTANT, A_TRAVELTIME_ACTUAL = 1, 2, 3, 4
+A_VEH_STATE, A_VEH_ARRIVAL_TS, A_VEH_DEPART_TS, A_VEH_TRAVEL_TIME, A_VEH_DISTANCE = 10, 11, 12, 13, 14
+A_VEH_ORIG, A_VEH_DEST, A_VEH_LINK, A_VEH_X, A_VEH_V, A_VEH_LANE = 15, 16, 17, 18, 19, 20
+A_SIGNAL_LOG, A_NODE_SIGNAL_PHASE, A_NODE_SIGNAL_T = 30, 31, 32
+A_LINK_NUM_VEHICLES, A_LINK_CAPACITY_IN_REMAIN, A_LINK_CAPACITY_OUT_REMAIN = 40, 41, 42
+A_LINK_STAT_COUNT, A_LINK_TRIPS_COMPLETED, A_LINK_AVE_V_SUM = 43, 44, 45
+A_ROUTE_PREF, A_ROUTE_DIST, A_ROUTE_NEXT = 50, 51, 52
+A_LOG_OFFSETS, A_LOG_T, A_LOG_X, A_LOG_V, A_LOG_STATE, A_LOG_S, A_LOG_LANE, A_LOG_LINK = 60, 61, 62, 63, 64, 65, 66, 67
+A_LOG_N_MISSING, A_LTL_OFFSETS, A_LTL_T, A_LTL_ID = 68, 69, 70, 71
+A_ENTER_LINK, A_ENTER_TIME, A_ENTER_VEH = 80, 81, 82
+
+DT_F64, DT_I32, DT_I64 = 1, 2, 3
+_NP_DTYPE = {DT_F64: np.float64, DT_I32: np.int32, DT_I64: np.int64}
+
+_EXC = {
+    UX_ERR_RUNTIME: RuntimeError,
+    UX_ERR_INVALID: ValueError,
+    UX_ERR_OUT_OF_RANGE: IndexError,
+    UX_ERR_CUDA: RuntimeError,
+    UX_ERR_CAPACITY: RuntimeError,
+}
+
+#: every symbol include/uxsim_b200.h declares (without prefix); tests check each library exports all of them
+ABI_SYMBOLS = (
+    "create_world", "destroy_world", "add_node", "add_link", "add_demand", "add_vehicles", "set_vehicle_links",
+    "batch_enforce_routes_csr", "set_t_max", "set_toll_timeseries", "initialize_adj_matrix", "main_loop",
+    "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
+    "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
+    "ensemble_link_stats", "last_error",
+)
+
+
+class WorldParams(C.Structure):
+    """``ux_world_params`` (include/uxsim_b200.h)."""
+
+    _fields_ = [
+        ("t_max", C.c_double),
+        ("delta_n", C.c_double),
+        ("tau", C.c_double),
+        ("duo_update_time", C.c_double),
+        ("duo_update_weight", C.c_double),
+        ("route_choice_uncertainty", C.c_double),
+        ("random_seed", C.c_int64),
+        ("print_mode", C.c_int32),
+        ("vehicle_log_mode", C.c_int32),
+        ("hard_deterministic_mode", C.c_int32),
+        ("route_choice_update_gradual", C.c_int32),
+        ("no_cyclic_routing", C.c_int32),
+        ("adjust_node_capacity", C.c_int32),
+        ("instantaneous_TT_timestep_interval", C.c_int32),
+        ("num_replicas", C.c_int32),
+        ("device", C.c_int32),
+        ("num_threads", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+
+def _as_i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class CApi:
+    """Typed access to one shared library exporting the uxsim_b200 C-ABI under ``prefix``."""
+
+    def __init__(self, lib_path: str, prefix: str = "ux_"):
+        if not os.path.exists(lib_path):
+            raise ImportError(
+                f"native library not found: {lib_path}. Build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (needs nvcc). There is no CPU fallback."
+            )
+        self.path = lib_path
+        self.prefix = prefix
+        self.lib = C.CDLL(lib_path)
+        p = C.c_void_p
+        i32p, f64p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int64)
+
+        def fn(name, restype, argtypes):
+            f = getattr(self.lib, prefix + name)
+            f.restype = restype
+            f.argtypes = argtypes
+            return f
+
+        self.create_world = fn("create_world", p, [C.POINTER(WorldParams)])
+        self.destroy_world = fn("destroy_world", None, [p])
+        self.add_node = fn("add_node", C.c_int, [p, C.c_double, C.c_double, f64p, C.c_int, C.c_double, C.c_double, C.c_int])
+        self.add_link = fn("add_link", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                  C.c_double, C.c_double, C.c_double, i32p, C.c_int])
+        self.add_demand = fn("add_demand", C.c_int64, [p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i32p, C.c_int])
+        self.add_vehicles = fn("add_vehicles", C.c_int64, [p, C.c_int64, i32p, i32p, i32p])
+        self.set_vehicle_links = fn("set_vehicle_links", C.c_int, [p, C.c_int64, C.c_int, i32p, C.c_int])
+        self.batch_enforce_routes_csr = fn("batch_enforce_routes_csr", C.c_int, [p, i32p, i64p, C.c_int64])
+        self.set_t_max = fn("set_t_max", C.c_int, [p, C.c_double])
+        self.set_toll_timeseries = fn("set_toll_timeseries", C.c_int, [p, C.c_int, f64p, C.c_int])
+        self.initialize_adj_matrix = fn("initialize_adj_matrix", C.c_int, [p])
+        self.main_loop = fn("main_loop", C.c_int, [p, C.c_double, C.c_double])
+        self.check_simulation_ongoing = fn("check_simulation_ongoing", C.c_int, [p])
+        self.set_link_param = fn("set_link_param", C.c_int, [p, C.c_int, C.c_int, C.c_double])
+        self.set_link_signal_group = fn("set_link_signal_group", C.c_int, [p, C.c_int, i32p, C.c_int])
+        self.set_node_signal = fn("set_node_signal", C.c_int, [p, C.c_int, f64p, C.c_int, C.c_int, C.c_double])
+        self.get_int = fn("get_int", C.c_int64, [p, C.c_int])
+        self.get_double = fn("get_double", C.c_double, [p, C.c_int])
+        self.array_size = fn("array_size", C.c_int64, [p, C.c_int, C.POINTER(C.c_int)])
+        self.get_array = fn("get_array", C.c_int64, [p, C.c_int, C.c_int, C.c_void_p, C.c_int64])
+        self.get_device_array = fn("get_device_array", C.c_int64, [p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)])
+        self.ensemble_link_stats_device = fn("ensemble_link_stats_device", C.c_int64, [p, C.POINTER(C.c_void_p)])
+        self.ensemble_link_stats = fn("ensemble_link_stats", C.c_int64, [p, f64p, C.c_int64])
+        self.last_error = fn("last_error", C.c_char_p, [p])
+
+    def exported(self, name: str) -> bool:
+        return hasattr(self.lib, self.prefix + name)
+
+
+_product: Optional[CApi] = None
+
+
+def load_product() -> CApi:
+    """Load the CUDA backend.  Raises ImportError if it has not been built -- by design there is no fallback."""
+    global _product
+    if _product is None:
+        _product = CApi(PRODUCT_LIB, "ux_")
+    return _product
+
+
+class EngineWorld:
+    """A native world handle plus numpy-typed helpers.  Thin: one method per C-ABI entry point."""
+
+    def __init__(self, api: CApi, *, t_max: float, delta_n: float, tau: float = 1.0, duo_update_time: float = 600.0,
+                 duo_update_weight: float = 0.5, route_choice_uncertainty: float = 0.01, random_seed: int = 0,
+                 vehicle_log_mode: bool = False, hard_deterministic_mode: bool = False,
+                 route_choice_update_gradual: bool = False, no_cyclic_routing: bool = False,
+                 adjust_node_capacity: bool = False, instantaneous_TT_timestep_interval: int = 5,
+                 num_replicas: int = 1, device: int = -1, num_threads: int = 1):
+        self.api = api
+        delta_t = tau * delta_n
+        route_ts = max(1, int(duo_update_time / delta_t))
+        # uxsim.py:1806-1808: the TT interval is clamped to the route-update interval
+        itt = min(int(instantaneous_TT_timestep_interval), route_ts)
+        self.params = WorldParams(
+            t_max=float(t_max), delta_n=float(delta_n), tau=float(tau), duo_update_time=float(duo_update_time),
+            duo_update_weight=float(duo_update_weight), route_choice_uncertainty=float(route_choice_uncertainty),
+            random_seed=int(random_seed), print_mode=0, vehicle_log_mode=int(bool(vehicle_log_mode)),
+            hard_deterministic_mode=int(bool(hard_deterministic_mode)),
+            route_choice_update_gradual=int(bool(route_choice_update_gradual)),
+            no_cyclic_routing=int(bool(no_cyclic_routing)), adjust_node_capacity=int(bool(adjust_node_capacity)),
+            instantaneous_TT_timestep_interval=itt, num_replicas=int(num_replicas), device=int(device),
+            num_threads=int(num_threads), reserved0=0)
+        self.h = api.create_world(C.byref(self.params))
+        if not self.h:
+            raise RuntimeError("create_world failed: " + (api.last_error(None) or b"").decode())
+        self.delta_t = delta_t
+
+    # -- error handling ---------------------------------------------------------------------------
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            msg = (self.api.last_error(self.h) or b"").decode(errors="replace")
+            raise _EXC.get(int(rc), RuntimeError)(msg)
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api.destroy_world(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scenario ------------------------------------------------------------------------------------
+    def add_node(self, x=0.0, y=0.0, signal=(0.0,), signal_offset=0.0, flow_capacity=-1.0, number_of_lanes=0) -> int:
+        s = _as_f64(list(signal))
+        return self._check(self.api.add_node(self.h, float(x), float(y), s.ctypes.data_as(C.POINTER(C.c_double)), len(s),
+                                             float(signal_offset), float(flow_capacity), int(number_of_lanes)))
+
+    def add_link(self, start, end, vmax, kappa, length, lanes=1, merge_priority=1.0, capacity_out=-1.0, capacity_in=-1.0,
+                 signal_group=(0,)) -> int:
+        g = _as_i32(list(signal_group))
+        return self._check(self.api.add_link(self.h, int(start), int(end), float(vmax), float(kappa), float(length), int(lanes),
+                                             float(merge_priority), float(capacity_out), float(capacity_in),
+                                             g.ctypes.data_as(C.POINTER(C.c_int32)), len(g)))
+
+    def add_demand(self, orig, dest, start_t, end_t, flow, links_preferred: Sequence[int] = ()) -> int:
+        g = _as_i32(list(links_preferred))
+        return self._check(self.api.add_demand(self.h, int(orig), int(dest), float(start_t), float(end_t), float(flow),
+                                               g.ctypes.data_as(C.POINTER(C.c_int32)), len(g)))
+
+    def add_vehicles(self, orig, dest, depart_ts) -> int:
+        o, d, t = _as_i32(orig), _as_i32(dest), _as_i32(depart_ts)
+        ip = C.POINTER(C.c_int32)
+        return self._check(self.api.add_vehicles(self.h, len(o), o.ctypes.data_as(ip), d.ctypes.data_as(ip), t.ctypes.data_as(ip)))
+
+    def set_vehicle_links(self, vehicle: int, kind: int, links: Sequence[int]):
+        g = _as_i32(list(links))
+        self._check(self.api.set_vehicle_links(self.h, int(vehicle), int(kind), g.ctypes.data_as(C.POINTER(C.c_int32)), len(g)))
+
+    def batch_enforce_routes_csr(self, link_ids, offsets):
+        ids, off = _as_i32(link_ids), np.ascontiguousarray(offsets, dtype=np.int64)
+        self._check(self.api.batch_enforce_routes_csr(self.h, ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                      off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1))
+
+    def set_t_max(self, t_max: float):
+        self._check(self.api.set_t_max(self.h, float(t_max)))
+
+    def set_toll_timeseries(self, link: int, toll):
+        t = _as_f64(toll)
+        self._check(self.api.set_toll_timeseries(self.h, int(link), t.ctypes.data_as(C.POINTER(C.c_double)), len(t)))
+
+    def initialize_adj_matrix(self):
+        self._check(self.api.initialize_adj_matrix(self.h))
+
+    # -- hot path -------------------------------------------------------------------------------------
+    def main_loop(self, duration_t: float = -1.0, until_t: float = -1.0):
+        self._check(self.api.main_loop(self.h, float(duration_t), float(until_t)))
+
+    def check_simulation_ongoing(self) -> bool:
+        return bool(self.api.check_simulation_ongoing(self.h))
+
+    # -- interventions --------------------------------------------------------------------------------
+    def set_link_param(self, link: int, field: int, value: float):
+        self._check(self.api.set_link_param(self.h, int(link), int(field), float(value)))
+
+    def set_link_signal_group(self, link: int, group: Sequence[int]):
+        g = _as_i32(list(group))
+        self._check(self.api.set_link_signal_group(self.h, int(link), g.ctypes.data_as(C.POINTER(C.c_int32)), len(g)))
+
+    def set_node_signal(self, node: int, signal=None, phase: int = -1, signal_t: float = -1.0):
+        if signal is None:
+            self._check(self.api.set_node_signal(self.h, int(node), None, 0, int(phase), float(signal_t)))
+        else:
+            s = _as_f64(list(signal))
+            self._check(self.api.set_node_signal(self.h, int(node), s.ctypes.data_as(C.POINTER(C.c_double)), len(s), int(phase), float(signal_t)))
+
+    # -- results --------------------------------------------------------------------------------------
+    def get_int(self, what: int) -> int:
+        return int(self._check(self.api.get_int(self.h, int(what))))
+
+    def get_double(self, what: int) -> float:
+        return float(self.api.get_double(self.h, int(what)))
+
+    def get_array(self, what: int, replica: int = 0) -> np.ndarray:
+        dt = C.c_int(0)
+        n = self._check(self.api.array_size(self.h, int(what), C.byref(dt)))
+        out = np.empty(int(n), dtype=_NP_DTYPE[dt.value])
+        if n > 0:
+            self._check(self.api.get_array(self.h, int(what), int(replica), out.ctypes.data_as(C.c_void_p), int(n)))
+        return out
+
+    def get_device_array(self, what: int, replica: int = 0):
+        """Borrowed device pointer as (ptr, n_elements, numpy dtype).  CUDA backend only."""
+        ptr, dt = C.c_void_p(0), C.c_int(0)
+        n = self._check(self.api.get_device_array(self.h, int(what), int(replica), C.byref(ptr), C.byref(dt)))
+        return ptr.value, int(n), _NP_DTYPE[dt.value]
+
+    def ensemble_link_stats(self) -> np.ndarray:
+        L = self.get_int(I_NUM_LINKS)
+        out = np.empty(L * 4, dtype=np.float64)
+        self._check(self.api.ensemble_link_stats(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out.reshape(L, 4)
+
+    # convenient shaped views
+    def link_series(self, what: int, replica: int = 0) -> np.ndarray:
+        L, T = self.get_int(I_NUM_LINKS), self.get_int(I_TOTAL_TIMESTEPS)
+        return self.get_array(what, replica).reshape(L, T)

@@ -1,0 +1,119 @@
+"""GPU parity tests proper: the CUDA engine, called through the C-ABI, must be bit-identical to the oracle.
+
+Bar (BASELINE.json north_star): bit-exact integer cumulative counts and arrival timesteps on deterministic
+scenarios.  Because the oracle and the kernels draw from the same counter-based Philox stream, the same
+bit-exactness is demanded here on STOCHASTIC networks too, for every result array (FP64 included)."""
+import numpy as np
+import pytest
+
+from uxsim_b200 import _capi as C
+from uxsim_b200 import scenario as S
+
+from parity import compare_engines, run_pair, summary_stats
+
+pytestmark = pytest.mark.gpu
+
+DETERMINISTIC = [
+    S.straight_1link, S.straight_2link_bottleneck_capacity_out, S.straight_2link_bottleneck_speed,
+    S.straight_3link_spillback, S.straight_2link_signal, S.straight_node_capacity, S.lane_drop_2to1,
+    S.multilane_3lane, S.merge_y, S.diverge_2route, S.dead_end, S.short_links_chain,
+]
+
+
+@pytest.mark.parametrize("builder", DETERMINISTIC, ids=lambda f: f.__name__)
+def test_deterministic_bit_exact(builder, cuda_api, oracle_api):
+    Eg, Eo = run_pair(builder(), cuda_api, oracle_api)
+    assert compare_engines(Eg, Eo) == []
+    assert Eg.get_int(C.I_PLATOON_UPDATES) == Eo.get_int(C.I_PLATOON_UPDATES)
+
+
+def test_short_links_order_matters(cuda_api, oracle_api):
+    """Serial id-ordered Node.transfer visibility: node ids decreasing downstream on links
+    shorter than one platoon spacing; needs >1 dependency level and must still be exact."""
+    Eg, Eo = run_pair(S.short_links_chain(reverse_ids=True), cuda_api, oracle_api)
+    assert Eg.get_int(C.I_TRANSFER_LEVELS) > 1
+    assert compare_engines(Eg, Eo) == []
+
+
+STOCHASTIC = [
+    ("merge_stochastic", lambda: S.merge_y(hard_deterministic_mode=False, random_seed=3)),
+    ("siouxfalls", lambda: S.sioux_falls(seed=1)),
+    ("grid5", lambda: S.grid(n=5, seed=2, tmax=3000, demand_t=1000)),
+    ("grid6_signals", lambda: S.grid(n=6, seed=5, tmax=3000, demand_t=1200, signals=True)),
+    ("grid11", lambda: S.grid(seed=2)),
+    ("dta_grid9", lambda: S.dta_grid9(seed=1)),
+    ("chicago_dn30", lambda: S.chicago_sketch(seed=0)),
+    ("gradual_duo", lambda: S.grid(n=5, seed=4, tmax=3000, demand_t=1000, route_choice_update_gradual=True)),
+]
+
+
+@pytest.mark.parametrize("name,mk", STOCHASTIC, ids=[n for n, _ in STOCHASTIC])
+def test_stochastic_bit_exact(name, mk, cuda_api, oracle_api):
+    Eg, Eo = run_pair(mk(), cuda_api, oracle_api)
+    assert compare_engines(Eg, Eo) == []
+    assert Eg.get_int(C.I_PLATOON_UPDATES) == Eo.get_int(C.I_PLATOON_UPDATES)
+    assert Eg.get_int(C.I_TRIPS_COMPLETED) == Eo.get_int(C.I_TRIPS_COMPLETED)
+
+
+def test_chunked_execution_equals_single_run(cuda_api, oracle_api):
+    """exec_simulation(until_t=...) in chunks (test_verification_straight_road.py:940-1113) == one run."""
+    sc = S.grid(n=5, seed=9, tmax=3000, demand_t=1000)
+    Ea, Eo = run_pair(sc, cuda_api, oracle_api, until=[300, 305, 1234, 2000, 3000])
+    assert compare_engines(Ea, Eo) == []
+    Eb = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)
+    Eb.main_loop()
+    assert compare_engines(Ea, Eb) == []
+
+
+def test_replicas_match_independent_seeds(cuda_api, oracle_api):
+    """R replicas in one world == R single-seed oracle runs with seeds seed + r."""
+    sc = S.grid(n=5, seed=11, tmax=3000, demand_t=1000)
+    R = 4
+    Eg = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1, num_replicas=R)
+    Eg.main_loop()
+    for r in range(R):
+        Eo = sc.to_engine(oracle_api, vehicle_logging_timestep_interval=-1, random_seed=11 + r)
+        Eo.main_loop()
+        assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"
+    ens = Eg.ensemble_link_stats()
+    vol = sum(summary_stats(Eg, r)[2] for r in range(R))
+    assert np.array_equal(ens[:, 0], vol)
+
+
+def test_run_to_run_determinism(cuda_api):
+    sc = S.sioux_falls(seed=5)
+    Ea = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)
+    Eb = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)
+    Ea.main_loop(), Eb.main_loop()
+    assert compare_engines(Ea, Eb) == []
+
+
+def test_conservation_at_full_size(cuda_api):
+    """Size-independent properties at a BASELINE size (Chicago sketch, deltan=5, ~1M vehicles): flow conservation
+    per link, monotone curves, arrivals bounded by departures upstream, every finished trip has a valid step."""
+    sc = S.chicago_sketch(deltan=5, seed=0)
+    E = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)
+    E.main_loop()
+    L, T = E.get_int(C.I_NUM_LINKS), E.get_int(C.I_TOTAL_TIMESTEPS)
+    arr = E.get_array(C.A_CUM_ARRIVAL).reshape(L, T)
+    dep = E.get_array(C.A_CUM_DEPARTURE).reshape(L, T)
+    nveh = E.get_array(C.A_LINK_NUM_VEHICLES)
+    assert (np.diff(arr, axis=1) >= 0).all() and (np.diff(dep, axis=1) >= 0).all()
+    assert (arr >= dep).all()
+    assert np.array_equal(arr[:, -1] - dep[:, -1], nveh * 5.0)
+    st = E.get_array(C.A_VEH_STATE)
+    ats = E.get_array(C.A_VEH_ARRIVAL_TS)
+    dts = E.get_array(C.A_VEH_DEPART_TS)
+    done = st == C.VS_END
+    assert done.sum() > 0.8 * len(st)
+    assert (ats[done] > dts[done]).all() and (ats[~done] == -1).all()
+    assert E.get_int(C.I_TRIPS_COMPLETED) == int(done.sum() + (st == C.VS_ABORT).sum())
+    assert int(dep[:, -1].sum() / 5.0) == E.get_int(C.I_LINK_EVENTS)
+
+
+def test_error_codes(cuda_api):
+    E = S.straight_1link().to_engine(cuda_api)
+    with pytest.raises(RuntimeError):
+        E.main_loop(duration_t=10, until_t=10)
+    with pytest.raises(IndexError):
+        E.set_link_param(99, C.LINK_VMAX, 10.0)

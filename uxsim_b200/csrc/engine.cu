@@ -1,0 +1,1533 @@
+// engine.cu -- B200-native engine for UXsim's per-timestep simulation loop (World.exec_simulation).
+//
+// One translation unit: sm_100a CUDA kernels + the C++ host driver + the C-ABI of include/uxsim_b200.h.
+// Reference behaviour: toruseo/UXsim uxsim/trafficpp/traffi.cpp (C++ engine) == uxsim/uxsim.py (Python
+// engine); each kernel cites the reference functions it implements.  Design notes: DESIGN.md.
+//
+// Data layout (all FP64 where the reference is FP64; FMA contraction disabled with -fmad=false so every
+// compare that decides an integer outcome sees the reference's values):
+//   * every link owns a ring of `cap` slots inside one big SoA arena: X[2][C] (positions, double-buffered by
+//     timestep parity: X[t&1] = position at the start of step t, X[(t+1)&1] = position before the last move,
+//     i.e. the reference's x_old), V[C], VID[C], LANE[C].  A platoon's leader is the slot `lanes` positions
+//     ahead in the same ring (traffi.cpp:175-181), so car-following is a coalesced read of X[p] and X[p-lanes].
+//   * per-link queue = (head[2], tail) monotone counters; head is double-buffered like X because the update
+//     kernel both reads it (all slots) and advances it (trip ends).
+//   * time series are time-major [T][L] so one step writes one contiguous row.
+//   * R replicas (seeds) = R DevWorld structs sharing the static network arrays; blockIdx.y = replica.
+//
+// Timestep = 3 kernels (+ route update every DELTAT_ROUTE steps), replayed from CUDA graphs:
+//   k_pre      warp per node : Link::update of the node's out-links, Node::generate, signal, node capacity
+//   k_transfer warp per node : Node::transfer, one launch per dependency level (see DESIGN.md "transfer order")
+//   k_update   thread per ring slot : car_follow_newell + Vehicle::update; one thread per link also handles the
+//              link head (trip end, abort, next-link choice)
+//   k_edge_cost / k_sssp / k_duo(+finish) : update_adj_time_matrix, route_search_all, route_choice_duo
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+
+#include "../../include/uxsim_b200.h"
+#include "../../include/ux_rng.h"
+
+#ifdef UX_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define UX_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// limits
+// ---------------------------------------------------------------------------------------------------
+#define UX_MAXDEG 32   // max out-/in-degree of a node
+#define UX_MAXC 160    // max transfer candidates / out-link slots of one node (sum of lanes)
+#define UX_SEG 32      // ring slots per update-kernel work item (one warp)
+
+enum { LF_SEES_POPS = 1, LF_END_LT_START = 2 };            // link flags
+enum { VF_WAIT_END = 1, VF_ABORT = 2, VF_CAND = 4 };       // vehicle flags
+enum { DERR_NONE = 0, DERR_RING_FULL = 1, DERR_ROUTE_EXHAUSTED = 2, DERR_ROUTE_INCONSISTENT = 3, DERR_AVOID_ALL = 4 };
+
+// ---------------------------------------------------------------------------------------------------
+// device world
+// ---------------------------------------------------------------------------------------------------
+struct DevWorld {
+    int N, L, T, D, vis_words;
+    long long P, C;
+    int nseg;
+    double dn, dt, duo_w, duo_time, noise;
+    int itt, route_ts, hard_det, gradual, no_cyclic, log_mode;
+    long long seed;
+    // static network (shared by all replicas)
+    const int *l_start, *l_end, *l_lanes, *l_rcap, *l_flags, *l_sg_off, *l_sg, *l_pair_first, *l_pair_off, *l_pair_list;
+    const long long *l_roff;
+    const double *l_length, *l_vmax, *l_dpl_dn, *l_udt, *l_cap_out, *l_cap_in, *l_mp, *l_penalty, *l_toll;
+    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes;
+    const double *n_sig, *n_fc;
+    const int *v_orig, *v_dest, *v_depart_ts, *gen_off, *gen_list, *dest_row, *row_dest;
+    const int *vl_off[3], *vl_list[3];  // per-vehicle CSR: 0 specified_route, 1 links_preferred, 2 links_avoid
+    const int *seg_link, *seg_start;
+    const int *e_from, *e_to, *e_link;  // node-pair edges (leading link of each pair)
+    int n_edges;
+    // dynamic (per replica)
+    int *head, *tail, *tail_k1, *pop_k2, *hcount, *trips, *ev_cnt;
+    long long *stat_count;
+    double *cap_out_rem, *cap_in_rem;
+    double *X, *V;
+    int *VID, *LANE;
+    int *sig_phase, *gen_head, *gen_avail;
+    double *sig_t, *fc_rem;
+    int *v_state, *v_next, *v_link, *v_arr_ts, *v_trav;
+    double *v_mr, *v_atl, *v_tt, *v_dist, *v_entry_x;
+    unsigned char *v_flags;
+    unsigned *v_visited;
+    double *cum_arr, *cum_dep, *tt_inst, *ev_tt;
+    int *ev_ord, *sig_log;
+    double *pref, *rdist, *pair_cost;
+    int *pref_active, *has_path, *rnext;
+    int *err;     // [0] code, [1] info
+    int *t_base;  // timestep at the start of the running graph
+};
+
+#define UX_DEV __device__ __forceinline__
+
+UX_DEV void dev_error(const DevWorld &W, int code, int info) {
+    if (atomicCAS(&W.err[0], 0, code) == 0) W.err[1] = info;
+}
+
+UX_DEV int ring_slot(int head, int pos, int cap) {  // physical slot of queue position `pos`
+    unsigned s = ((unsigned)head % (unsigned)cap) + (unsigned)pos;
+    return (int)(s >= (unsigned)cap ? s - (unsigned)cap : s);
+}
+
+// random_choice (utils.h:62-87) with a supplied uniform u in [0,1)
+UX_DEV int weighted_pick(const double *wts, int n, double u) {
+    double wsum = 0.0;
+    for (int i = 0; i < n; i++) wsum += wts[i];
+    if (wsum <= 0.0) { int k = (int)(u * (double)n); return k >= n ? n - 1 : k; }
+    double r = u * wsum, accum = 0.0;
+    for (int i = 0; i < n; i++) { accum += wts[i]; if (r <= accum) return i; }
+    return n - 1;
+}
+
+UX_DEV bool is_inf(double c) { return c > 1.0e300; }
+
+UX_DEV bool list_has(const int *a, int n, int v) {
+    for (int i = 0; i < n; i++) if (a[i] == v) return true;
+    return false;
+}
+
+// Vehicle::route_next_link_choice (traffi.cpp:934-1033).  Returns the chosen link id or -1.
+UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned entity, unsigned purpose, unsigned draw) {
+    int o0 = W.n_out_off[node], nset = W.n_out_off[node + 1] - o0;
+    if (nset == 0) return -1;
+    const int *linkset = W.n_out + o0;
+    if (W.vl_off[0]) {  // specified_route
+        int r0 = W.vl_off[0][vid], len = W.vl_off[0][vid + 1] - r0;
+        if (len > 0) {
+            int traveled = W.v_trav[vid];
+            if (traveled >= len) { dev_error(W, DERR_ROUTE_EXHAUSTED, vid); return -1; }
+            int forced = W.vl_list[0][r0 + traveled];
+            if (!list_has(linkset, nset, forced)) { dev_error(W, DERR_ROUTE_INCONSISTENT, vid); return -1; }
+            return forced;
+        }
+    }
+    int bufa[UX_MAXDEG], bufb[UX_MAXDEG];
+    int *out = bufa, *tmp = bufb, n = 0;
+    for (int i = 0; i < nset; i++) out[n++] = linkset[i];
+    if (W.vl_off[1]) {  // links_preferred: intersection if non-empty
+        int r0 = W.vl_off[1][vid], len = W.vl_off[1][vid + 1] - r0;
+        if (len > 0) {
+            int m = 0;
+            for (int i = 0; i < n; i++) if (list_has(W.vl_list[1] + r0, len, out[i])) tmp[m++] = out[i];
+            if (m > 0) { int *s = out; out = tmp; tmp = s; n = m; }
+        }
+    }
+    if (W.vl_off[2]) {  // links_avoid: subtraction, error if nothing is left
+        int r0 = W.vl_off[2][vid], len = W.vl_off[2][vid + 1] - r0;
+        if (len > 0) {
+            int m = 0;
+            for (int i = 0; i < n; i++) if (!list_has(W.vl_list[2] + r0, len, out[i])) tmp[m++] = out[i];
+            if (m != n) { int *s = out; out = tmp; tmp = s; n = m; }
+            if (n == 0) { dev_error(W, DERR_AVOID_ALL, vid); return -1; }
+        }
+    }
+    if (W.no_cyclic) {
+        const unsigned *vis = W.v_visited + (size_t)vid * W.vis_words;
+        int m = 0;
+        for (int i = 0; i < n; i++) { int e = W.l_end[out[i]]; if (!((vis[e >> 5] >> (e & 31)) & 1u)) tmp[m++] = out[i]; }
+        if (m > 0) { int *s = out; out = tmp; tmp = s; n = m; }
+    }
+    if (n == 0) return -1;
+    double pw[UX_MAXDEG];
+    int row = W.dest_row[W.v_dest[vid]];
+    for (int i = 0; i < n; i++) pw[i] = row >= 0 ? W.pref[(size_t)row * W.L + out[i]] : 0.0;
+    if (W.hard_det) {
+        int best = 0;
+        for (int i = 1; i < n; i++) if (pw[i] > pw[best]) best = i;
+        return out[best];
+    }
+    double u = ux_rng_uniform(W.seed, (uint32_t)t, entity, purpose, draw);
+    return out[weighted_pick(pw, n, u)];
+}
+
+// acceptance test of an out-link seen with effective head `hd` (traffi.cpp:130-142, 285-297)
+UX_DEV bool can_accept(const DevWorld &W, int l, int hd, int cur) {
+    int sz = W.tail[l] - hd, lanes = W.l_lanes[l];
+    bool ok = false;
+    if (sz < lanes) ok = true;
+    else {
+        int slot = ring_slot(hd, sz - lanes, W.l_rcap[l]);
+        if (W.X[(size_t)cur * W.C + W.l_roff[l] + slot] > W.l_dpl_dn[l]) ok = true;
+    }
+    if (W.cap_in_rem[l] < W.dn) ok = false;
+    return ok;
+}
+
+// push a platoon at the tail of link l (lane + leader rule traffi.cpp:168-183 / 385-398).  Returns the slot.
+UX_DEV int ring_push(const DevWorld &W, int l, int hd, int cur, double x, double x_old, double v, int vid) {
+    int cap = W.l_rcap[l], tl = W.tail[l], sz = tl - hd, lanes = W.l_lanes[l];
+    if (sz >= cap) { dev_error(W, DERR_RING_FULL, l); return -1; }
+    long long o = W.l_roff[l];
+    int lane = 0;
+    if (sz > 0) lane = (W.LANE[o + ring_slot(tl - 1, 0, cap)] + 1) % lanes;
+    int slot = ring_slot(tl, 0, cap);
+    W.X[(size_t)cur * W.C + o + slot] = x;
+    W.X[(size_t)(cur ^ 1) * W.C + o + slot] = x_old;
+    W.V[o + slot] = v;
+    W.VID[o + slot] = vid;
+    W.LANE[o + slot] = lane;
+    W.tail[l] = tl + 1;
+    return slot;
+}
+
+UX_DEV void mark_entered(const DevWorld &W, int vid, int l) {  // traffi.cpp:160-166, 372-378
+    if (W.no_cyclic) { int s = W.l_start[l]; W.v_visited[(size_t)vid * W.vis_words + (s >> 5)] |= 1u << (s & 31); }
+    W.v_trav[vid] += 1;
+    W.v_link[vid] = l;
+}
+
+// record a link-exit travel time (traffi.cpp:357-362, 893-898) into the "last event per entry step" table
+UX_DEV void record_tt_event(const DevWorld &W, int l, double atl, double tt) {
+    int s = (int)(atl / W.dt);
+    if (s < 0) s = 0;
+    if (s >= W.T) s = W.T - 1;
+    int ord = W.ev_cnt[l] + 1;
+    W.ev_cnt[l] = ord;
+    W.ev_ord[(size_t)s * W.L + l] = ord;
+    W.ev_tt[(size_t)s * W.L + l] = tt;
+}
+
+// Vehicle::end_trip (traffi.cpp:886-927) for the front platoon `vid` of link l, currently at position x
+UX_DEV void end_trip(const DevWorld &W, int vid, int l, int t, double x) {
+    W.trips[l] += 1;
+    W.cum_dep[(size_t)t * W.L + l] += W.dn;
+    double atl = W.v_atl[vid];
+    record_tt_event(W, l, atl, ((double)t + 1.0) * W.dt - atl);
+    W.v_atl[vid] = (double)t * W.dt;
+    W.v_dist[vid] += x - W.v_entry_x[vid];
+    W.v_link[vid] = -1;
+    if (W.v_flags[vid] & VF_ABORT) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+    else {
+        W.v_state[vid] = UX_VS_END;
+        W.v_arr_ts[vid] = t;
+        W.v_tt[vid] = (double)t * W.dt - (double)W.v_depart_ts[vid] * W.dt;
+    }
+    W.v_flags[vid] = 0;
+}
+
+// Sum of V over the queue of link l in the fixed order "32 interleaved partial sums + butterfly" (oracle R3).
+UX_DEV double warp_queue_vsum(const DevWorld &W, int l, int hd, int n, int lane) {
+    int cap = W.l_rcap[l];
+    const double *V = W.V + W.l_roff[l];
+#ifdef UX_EMU
+    double part[32];
+    for (int k = 0; k < 32; k++) { double s = 0.0; for (int i = k; i < n; i += 32) s += V[ring_slot(hd, i, cap)]; part[k] = s; }
+    for (int off = 16; off >= 1; off >>= 1) { double nx[32]; for (int k = 0; k < 32; k++) nx[k] = part[k] + part[k ^ off]; for (int k = 0; k < 32; k++) part[k] = nx[k]; }
+    (void)lane;
+    return part[0];
+#else
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += V[ring_slot(hd, i, cap)];
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: Link::update (traffi.cpp:542-565, 599-622) for the node's out-links, then Node::generate (105-189),
+//     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_off) {
+    const DevWorld &W = worlds[blockIdx.y];
+    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+    if (warp >= W.N) return;
+    int n = warp, t = *W.t_base + step_off, cur = t & 1, L = W.L;
+    int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
+    // ---- link update of out-links
+    for (int k = 0; k < nout; k++) {
+        int l = W.n_out[o0 + k];
+        int hd = W.head[cur * L + l], nq = W.tail[l] - hd;
+        double tt;
+        bool fresh = (t % W.itt) == 0;
+        if (fresh) {
+            if (nq > 0) {
+                double vs = warp_queue_vsum(W, l, hd, nq, lane);
+                double avg = vs / (double)nq;
+                tt = avg > 0.0 ? W.l_length[l] / avg : W.l_length[l] / (W.l_vmax[l] / 100.0);
+            } else tt = W.l_length[l] / W.l_vmax[l];
+        }
+        if (lane == 0) {
+            size_t row = (size_t)t * L + l;
+            if (fresh) W.tt_inst[row] = tt;
+            else if (t > 0) W.tt_inst[row] = W.tt_inst[row - L];
+            if (t != 0) { W.cum_arr[row] = W.cum_arr[row - L]; W.cum_dep[row] = W.cum_dep[row - L]; }
+            int lanes = W.l_lanes[l];
+            double co = W.l_cap_out[l], ci = W.l_cap_in[l];
+            if (co < 10e9) { if (W.cap_out_rem[l] < W.dn * lanes) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
+            if (ci < 10e9) { if (W.cap_in_rem[l] < W.dn * lanes) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+            W.pop_k2[l] = 0;
+        }
+    }
+    if (lane != 0) return;
+    // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841)
+    {
+        int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
+        while (av < glen && W.v_depart_ts[W.gen_list[g0 + av]] <= t - 1) av++;
+        W.gen_avail[n] = av;
+        // ---- generate
+        int gh = W.gen_head[n];
+        if (gh < av && nout > 0) {
+            int total_lanes = W.n_out_lanes[n];
+            for (int i = 0; i < total_lanes; i++) {
+                if (gh >= av) break;
+                int vid = W.gen_list[g0 + gh];
+                int ol = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i);
+                W.v_next[vid] = ol;
+                if (ol < 0) break;
+                int hd = W.head[cur * L + ol];
+                if (!can_accept(W, ol, hd, cur)) break;
+                gh++;
+                if (ring_push(W, ol, hd, cur, 0.0, 0.0, W.l_vmax[ol], vid) < 0) break;
+                W.v_state[vid] = UX_VS_RUN;
+                W.v_atl[vid] = (double)t * W.dt;
+                W.v_entry_x[vid] = 0.0;
+                mark_entered(W, vid, ol);
+                W.cum_arr[(size_t)t * L + ol] += W.dn;
+                W.cap_in_rem[ol] -= W.dn;
+            }
+            W.gen_head[n] = gh;
+        }
+    }
+    for (int k = 0; k < nout; k++) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; }
+    // ---- signal
+    int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
+    int ph = W.sig_phase[n];
+    if (nsig > 1) {
+        double st = W.sig_t[n];
+        if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
+        st += W.dt;
+        W.sig_t[n] = st; W.sig_phase[n] = ph;
+    }
+    W.sig_log[(size_t)t * W.N + n] = ph;
+    // ---- node flow capacity
+    double fc = W.n_fc[n];
+    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
+    else W.fc_rem[n] = 10e10;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: Node::transfer (traffi.cpp:239-445).  One warp per node of dependency level `level`.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_transfer(const DevWorld *worlds, int step_off, int level) {
+    const DevWorld &W = worlds[blockIdx.y];
+    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+    int lo = W.lvl_off[level], cnt = W.lvl_off[level + 1] - lo;
+    if (warp >= cnt || lane != 0) return;
+    int n = W.lvl_nodes[lo + warp], t = *W.t_base + step_off, cur = t & 1, L = W.L;
+    size_t C = (size_t)W.C;
+    int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
+    if (nin == 0) return;
+    int popped[UX_MAXDEG];
+    int c_vid[UX_MAXC], c_next[UX_MAXC];
+    short c_in[UX_MAXC], c_pos[UX_MAXC];
+    int nc = 0;
+    bool any_wait = false;
+    for (int ii = 0; ii < nin; ii++) {
+        int il = W.n_in[i0 + ii], hd = W.head[cur * L + il], hc = W.hcount[il], cap = W.l_rcap[il];
+        popped[ii] = 0;
+        for (int j = 0; j < hc; j++) {
+            int vid = W.VID[W.l_roff[il] + ring_slot(hd, j, cap)];
+            unsigned char f = W.v_flags[vid];
+            if (f & VF_WAIT_END) any_wait = true;
+            if ((f & VF_CAND) && nc < UX_MAXC) {  // insertion sort by vehicle id (traffi.cpp:250-253)
+                int k = nc++;
+                while (k > 0 && c_vid[k - 1] > vid) { c_vid[k] = c_vid[k - 1]; c_next[k] = c_next[k - 1]; c_in[k] = c_in[k - 1]; c_pos[k] = c_pos[k - 1]; k--; }
+                c_vid[k] = vid; c_next[k] = W.v_next[vid]; c_in[k] = (short)ii; c_pos[k] = (short)j;
+            }
+        }
+    }
+    if (nc == 0 && !any_wait) return;
+    // out-link slots: each requested out-link repeated `lanes` times (traffi.cpp:260-273)
+    int expd[UX_MAXC], nexp = 0;
+    for (int k = 0; k < nc; k++) {
+        int nl = c_next[k];
+        if (nl < 0) continue;
+        bool seen = false;
+        for (int q = 0; q < k; q++) if (c_next[q] == nl) { seen = true; break; }
+        if (seen) continue;
+        int ln = W.l_lanes[nl];
+        for (int q = 0; q < ln && nexp < UX_MAXC; q++) expd[nexp++] = nl;
+    }
+    unsigned draw = 0;
+    if (!W.hard_det) {  // Fisher-Yates (traffi.cpp:276-282)
+        for (int i = nexp - 1; i > 0; i--) {
+            int j = ux_rng_below(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, draw++, i + 1);
+            int tmp = expd[i]; expd[i] = expd[j]; expd[j] = tmp;
+        }
+    }
+    int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = W.sig_phase[n];
+    double fc = W.n_fc[n];
+    for (int s = 0; s < nexp; s++) {
+        int ol = expd[s];
+        int hd_ol = W.head[cur * L + ol] + ((W.l_flags[ol] & LF_SEES_POPS) ? W.pop_k2[ol] : 0);
+        bool ok = can_accept(W, ol, hd_ol, cur);
+        if (W.fc_rem[n] < W.dn) ok = false;
+        if (!ok) continue;
+        int mv[UX_MAXC]; double mp[UX_MAXC]; int nm = 0;
+        for (int k = 0; k < nc; k++) {
+            if (c_vid[k] < 0 || c_next[k] != ol) continue;
+            int ii = c_in[k], il = W.n_in[i0 + ii];
+            if (c_pos[k] != popped[ii]) continue;             // must be the front of its in-link
+            if (W.cap_out_rem[il] < W.dn) continue;
+            if (nsig > 1) {                                   // signal (traffi.cpp:314)
+                int g0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - g0;
+                if (!list_has(W.l_sg + g0, gl, phase)) continue;
+            }
+            mv[nm] = k; mp[nm] = W.l_mp[il]; nm++;
+        }
+        if (nm == 0) continue;
+        int pick;
+        if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
+        else pick = weighted_pick(mp, nm, ux_rng_uniform(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, draw++));
+        int k = mv[pick], vid = c_vid[k], ii = c_in[k], il = W.n_in[i0 + ii];
+        int hd_il = W.head[cur * L + il], cap_il = W.l_rcap[il];
+        long long o_il = W.l_roff[il];
+        int islot = ring_slot(hd_il, c_pos[k], cap_il);
+        double x_il = W.X[(size_t)cur * C + o_il + islot], xold_il = W.X[(size_t)(cur ^ 1) * C + o_il + islot], v_il = W.V[o_il + islot];
+        W.cap_out_rem[il] -= W.dn; W.cap_in_rem[ol] -= W.dn;
+        if (fc >= 0.0) W.fc_rem[n] -= W.dn;
+        W.cum_dep[(size_t)t * L + il] += W.dn; W.cum_arr[(size_t)t * L + ol] += W.dn;
+        double atl = W.v_atl[vid];
+        record_tt_event(W, il, atl, (double)t * W.dt - atl);
+        W.v_atl[vid] = (double)t * W.dt;
+        W.v_dist[vid] += x_il - W.v_entry_x[vid];
+        popped[ii] += 1;
+        W.pop_k2[il] = popped[ii];
+        mark_entered(W, vid, ol);
+        W.v_flags[vid] = 0;
+        // carry the residual move onto the new link (traffi.cpp:400-419)
+        int sz = W.tail[ol] - hd_ol, lanes_ol = W.l_lanes[ol];
+        double x_next = W.v_mr[vid] * W.l_vmax[ol] / W.l_vmax[il];
+        if (sz >= lanes_ol) {
+            int lslot = ring_slot(hd_ol, sz - lanes_ol, W.l_rcap[ol]);
+            double x_cong = W.X[(size_t)(cur ^ 1) * C + W.l_roff[ol] + lslot] - W.l_dpl_dn[ol];
+            if (x_cong < 0.0) x_cong = 0.0;
+            if (x_next > x_cong) x_next = x_cong;
+        }
+        if (x_next >= W.l_length[ol]) x_next = W.l_length[ol];
+        if (x_next < 0.0) x_next = 0.0;
+        ring_push(W, ol, hd_ol, cur, x_next, xold_il, v_il + x_next / W.dt, vid);
+        W.v_entry_x[vid] = x_next;
+        W.v_mr[vid] = 0.0;
+        c_vid[k] = -1;  // remove from incoming
+        // the new front of the in-link may be waiting for its trip end (traffi.cpp:421-424)
+        if (popped[ii] < W.hcount[il]) {
+            int fslot = ring_slot(hd_il, popped[ii], cap_il);
+            int fv = W.VID[o_il + fslot];
+            if (W.v_flags[fv] & VF_WAIT_END) {
+                end_trip(W, fv, il, t, W.X[(size_t)cur * C + o_il + fslot]);
+                popped[ii] += 1; W.pop_k2[il] = popped[ii];
+            }
+        }
+    }
+    // flush trip-end-waiting fronts (traffi.cpp:432-441)
+    for (int ii = 0; ii < nin; ii++) {
+        int il = W.n_in[i0 + ii], hd_il = W.head[cur * L + il], cap_il = W.l_rcap[il], hc = W.hcount[il], lanes = W.l_lanes[il];
+        long long o_il = W.l_roff[il];
+        for (int q = 0; q < lanes; q++) {
+            if (popped[ii] >= hc) break;
+            int fslot = ring_slot(hd_il, popped[ii], cap_il);
+            int fv = W.VID[o_il + fslot];
+            if (!(W.v_flags[fv] & VF_WAIT_END)) break;
+            end_trip(W, fv, il, t, W.X[(size_t)cur * C + o_il + fslot]);
+            popped[ii] += 1; W.pop_k2[il] = popped[ii];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: Vehicle::car_follow_newell (traffi.cpp:798-823) + Vehicle::update RUN branch (844-878) for every
+//     occupied ring slot; the first thread of each link's first segment additionally handles the link head.
+// ---------------------------------------------------------------------------------------------------
+UX_DEV void link_head_update(const DevWorld &W, int l, int t, int cur) {
+    int L = W.L, lanes = W.l_lanes[l], cap = W.l_rcap[l];
+    long long o = W.l_roff[l];
+    size_t C = (size_t)W.C;
+    int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], hd = hd0 + pk2, tl = W.tail[l], n = tl - hd;
+    // lane relabel when the end node (smaller id) emptied the link before this step's pushes (DESIGN.md iii)
+    if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
+        int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+        if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
+    }
+    W.stat_count[l] += n;
+    int hc = n < lanes ? n : lanes, k = 0;
+    int end_node = W.l_end[l];
+    double len = W.l_length[l], udt = W.l_udt[l];
+    for (int j = 0; j < hc; j++) {
+        int slot = ring_slot(hd, j, cap);
+        int vid = W.VID[o + slot];
+        double x = W.X[(size_t)cur * C + o + slot];
+        double xn = x + udt;  // positions < lanes have no leader
+        if (xn < x) xn = x;
+        if (xn > len) { W.v_mr[vid] = xn - len; xn = len; }
+        unsigned char f = 0;
+        if (fabs(xn - len) < 1e-9) {
+            if (end_node == W.v_dest[vid]) {
+                f = VF_WAIT_END;
+                W.v_flags[vid] = f;
+                if (k == j) { end_trip(W, vid, l, t, xn); k++; continue; }
+            } else if (W.n_out_off[end_node + 1] == W.n_out_off[end_node]) {  // dead end: abort (traffi.cpp:864-871)
+                f = VF_WAIT_END | VF_ABORT;
+                W.v_next[vid] = -1;
+                W.v_flags[vid] = f;
+                if (k == j) { end_trip(W, vid, l, t, xn); k++; continue; }
+            } else {
+                W.v_next[vid] = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u);
+                f = VF_CAND;
+            }
+        }
+        W.v_flags[vid] = f;
+    }
+    W.head[(cur ^ 1) * L + l] = hd + k;
+    int rem = n - k;
+    W.hcount[l] = rem < lanes ? rem : lanes;
+}
+
+__global__ void __launch_bounds__(256) k_update(const DevWorld *worlds, int step_off) {
+    const DevWorld &W = worlds[blockIdx.y];
+    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+    if (gw >= W.nseg) return;
+    int l = W.seg_link[gw], s0 = W.seg_start[gw], p = s0 + lane, cap = W.l_rcap[l];
+    int t = *W.t_base + step_off, cur = t & 1;
+    if (p < cap) {
+        int hd = W.head[cur * W.L + l] + W.pop_k2[l], n = W.tail[l] - hd;
+        int hp = (int)((unsigned)hd % (unsigned)cap);
+        int pos = p - hp; if (pos < 0) pos += cap;
+        if (pos < n) {
+            size_t C = (size_t)W.C;
+            long long o = W.l_roff[l];
+            const double *Xc = W.X + (size_t)cur * C + o;
+            double x = Xc[p];
+            double xn = x + W.l_udt[l];
+            int lanes = W.l_lanes[l];
+            if (pos >= lanes) {
+                int lp = p - lanes; if (lp < 0) lp += cap;
+                double gap = Xc[lp] - W.l_dpl_dn[l];
+                if (gap < x) gap = x;
+                if (xn > gap) xn = gap;
+            }
+            if (xn < x) xn = x;
+            double len = W.l_length[l];
+            if (xn > len) xn = len;
+            W.X[(size_t)(cur ^ 1) * C + o + p] = xn;
+            W.V[o + p] = (xn - x) / W.dt;
+        }
+    }
+    if (s0 == 0 && lane == 0) link_head_update(W, l, t, cur);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Route choice: update_adj_time_matrix (traffi.cpp:1267-1306), route_search_all (1317-1385, as the
+// per-destination fixed point of oracle R2), route_choice_duo (1486-1553).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int step_off) {
+    const DevWorld &W = worlds[blockIdx.y];
+    int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (e >= W.n_edges) return;
+    int g = W.e_link[e], t = *W.t_base + step_off;
+    double cost = 0.0;
+    int m0 = W.l_pair_off[g], m1 = W.l_pair_off[g + 1], cntr = 0;
+    for (int m = m0; m < m1; m++) {  // members of the node pair in link-id order, running average
+        int l = W.l_pair_list[m];
+        double tt = W.tt_inst[(size_t)t * W.L + l];
+        if (tt <= 0.0) tt = W.l_length[l] / W.l_vmax[l];
+        double pen = W.l_toll ? W.l_toll[(size_t)t * W.L + l] : W.l_penalty[l];
+        double c;
+        if (W.hard_det) c = tt + pen;
+        else c = tt * (1.0 + W.noise * ux_rng_uniform(W.seed, (uint32_t)t, (uint32_t)l, UX_RNG_LINKNOISE, 0u)) + pen;
+        double nn = (double)cntr;
+        cost = cost * nn / (nn + 1.0) + c / (nn + 1.0);
+        cntr++;
+        if (W.l_cap_in[l] == 0.0) cost = INFINITY;
+    }
+    W.pair_cost[e] = cost;
+}
+
+// One block per active destination: label-correcting relaxation to the fixed point dist[i] = min_j c_ij + dist[j].
+__global__ void __launch_bounds__(256) k_sssp(const DevWorld *worlds) {
+    const DevWorld &W = worlds[blockIdx.y];
+    int row = (int)blockIdx.x;
+    if (row >= W.D) return;
+    int N = W.N, k = W.row_dest[row];
+    double *dist = W.rdist + (size_t)row * N;
+    int *next = W.rnext + (size_t)row * N;
+    unsigned long long *du = (unsigned long long *)dist;
+#ifdef UX_EMU
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < N; i++) { dist[i] = INFINITY; next[i] = 0x7fffffff; }
+    dist[k] = 0.0;
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (int e = 0; e < W.n_edges; e++) {
+            double c = W.pair_cost[e];
+            if (!(c > 0.0) || is_inf(c)) continue;
+            double nd = c + dist[W.e_to[e]];
+            if (nd < dist[W.e_from[e]]) { dist[W.e_from[e]] = nd; changed = true; }
+        }
+    }
+    int tid = 0, nth = 1;
+#else
+    int tid = (int)threadIdx.x, nth = (int)blockDim.x;
+    for (int i = tid; i < N; i += nth) { dist[i] = (i == k) ? 0.0 : INFINITY; next[i] = 0x7fffffff; }
+    __syncthreads();
+    while (true) {
+        int changed = 0;
+        for (int e = tid; e < W.n_edges; e += nth) {
+            double c = W.pair_cost[e];
+            if (!(c > 0.0) || is_inf(c)) continue;
+            double dj = __longlong_as_double((long long)du[W.e_to[e]]);
+            double nd = c + dj;
+            int i = W.e_from[e];
+            if (nd < __longlong_as_double((long long)du[i])) {  // non-negative doubles order like their bit patterns
+                atomicMin(&du[i], (unsigned long long)__double_as_longlong(nd));
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+#endif
+    // next hop: smallest node j with c_ij + dist[j] == dist[i]
+    int any = 0;
+    for (int e = tid; e < W.n_edges; e += nth) {
+        double c = W.pair_cost[e];
+        if (!(c > 0.0) || is_inf(c)) continue;
+        int i = W.e_from[e], j = W.e_to[e];
+        if (i == k) continue;
+        double dj = dist[j];
+        if (is_inf(dj)) continue;
+        if (c + dj == dist[i]) { atomicMin(&next[i], j); any = 1; }
+    }
+#ifndef UX_EMU
+    any = __syncthreads_or(any);
+#endif
+    for (int i = tid; i < N; i += nth) { if (i == k) next[i] = k; else if (next[i] == 0x7fffffff) next[i] = -1; }
+    if (tid == 0) W.has_path[row] = any ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_duo(const DevWorld *worlds, int gradual_step) {
+    const DevWorld &W = worlds[blockIdx.y];
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)W.D * W.L;
+    if (idx >= total) return;
+    int r = (int)(idx / W.L), l = (int)(idx % W.L);
+    double wt = gradual_step ? W.duo_w * (W.dt / W.duo_time) : W.duo_w;
+    if (!W.pref_active[r]) wt = 1.0;
+    double p = W.pref[idx];
+    if (W.rnext[(size_t)r * W.N + W.l_start[l]] == W.l_end[l]) p = (1.0 - wt) * p + wt;
+    else p = (1.0 - wt) * p;
+    W.pref[idx] = p;
+}
+
+__global__ void k_duo_finish(const DevWorld *worlds) {
+    const DevWorld &W = worlds[blockIdx.y];
+    int r = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (r < W.D && W.has_path[r]) W.pref_active[r] = 1;
+}
+
+__global__ void k_advance(const DevWorld *worlds, int nsteps) {
+    const DevWorld &W = worlds[blockIdx.y];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *W.t_base += nsteps;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// result kernels (off the hot path)
+// ---------------------------------------------------------------------------------------------------
+// [T][L] -> [L][T]
+template <typename T>
+__global__ void k_transpose(const T *src, T *dst, int rows, int cols) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * cols) return;
+    int r = (int)(idx / cols), c = (int)(idx % cols);
+    dst[(size_t)c * rows + r] = src[idx];
+}
+
+// Link::ensure_traveltime_real (traffi.cpp:631-648): position i takes the value of the latest event whose entry step <= i.
+__global__ void k_tt_actual(const DevWorld *worlds, int replica, double *out) {
+    const DevWorld &W = worlds[replica];
+    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (l >= W.L) return;
+    double cur = W.l_length[l] / W.l_vmax[l];
+    int best = 0;
+    for (int i = 0; i < W.T; i++) {
+        int ord = W.ev_ord[(size_t)i * W.L + l];
+        if (ord > best) { best = ord; cur = W.ev_tt[(size_t)i * W.L + l]; }
+        out[(size_t)l * W.T + i] = cur;
+    }
+}
+
+// scatter ring state to per-vehicle arrays (x, v, lane)
+__global__ void k_veh_snapshot(const DevWorld *worlds, int replica, double *vx, double *vv, int *vlane) {
+    const DevWorld &W = worlds[replica];
+    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+    if (gw >= W.nseg) return;
+    int l = W.seg_link[gw], p = W.seg_start[gw] + lane, cap = W.l_rcap[l];
+    if (p >= cap) return;
+    int cur = *W.t_base & 1;
+    int hd = W.head[cur * W.L + l], n = W.tail[l] - hd;
+    int pos = p - (int)((unsigned)hd % (unsigned)cap); if (pos < 0) pos += cap;
+    if (pos >= n) return;
+    long long o = W.l_roff[l];
+    int vid = W.VID[o + p];
+    vx[vid] = W.X[(size_t)cur * W.C + o + p]; vv[vid] = W.V[o + p]; vlane[vid] = W.LANE[o + p];
+}
+
+// per-link ensemble statistics over this world's replicas: {volume, sum tt_actual, sum tt_actual^2, platoons on link}
+__global__ void k_ensemble_stats(const DevWorld *worlds, int R, double *out) {
+    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (l >= worlds[0].L) return;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int r = 0; r < R; r++) {  // fixed replica order: deterministic sums
+        const DevWorld &W = worlds[r];
+        int T = W.T, L = W.L;
+        double cur = W.l_length[l] / W.l_vmax[l], s1 = 0, s2 = 0;
+        int best = 0;
+        for (int i = 0; i < T; i++) {
+            int ord = W.ev_ord[(size_t)i * L + l];
+            if (ord > best) { best = ord; cur = W.ev_tt[(size_t)i * L + l]; }
+            s1 += cur; s2 += cur * cur;
+        }
+        a0 += T > 0 ? W.cum_arr[(size_t)(T - 1) * L + l] : 0.0;
+        a1 += s1; a2 += s2;
+        a3 += (double)(W.tail[l] - W.head[(*W.t_base & 1) * L + l]);
+    }
+    out[l * 4 + 0] = a0; out[l * 4 + 1] = a1; out[l * 4 + 2] = a2; out[l * 4 + 3] = a3;
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct HNode {
+    double x, y, sig_offset, fc; std::vector<double> sig; int lanes;
+    int sig_phase0; double sig_t0, fc_rem0;
+    std::vector<int> in, out;
+};
+struct HLink {
+    int start, end, lanes; double length, vmax, kappa, delta, dpl, tau, w, capacity, mp, cap_out, cap_in, cap_out_rem0, cap_in_rem0, penalty;
+    std::vector<int> sg; std::vector<double> toll;
+};
+struct HVeh { int orig, dest, ts; };
+
+struct ux_world {
+    ux_world_params p;
+    double dt; int total_ts, route_ts, timestep; int R;
+    std::vector<HNode> nodes; std::vector<HLink> links; std::vector<HVeh> vehs;
+    std::map<long long, std::vector<int>> vlinks[3];
+    bool initialized = false, uploaded = false, net_dirty = false;
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    std::vector<DevWorld> hw;  // host copies of the per-replica device worlds
+    DevWorld *dworlds = nullptr;
+    int n_levels = 1, n_active = 0;
+    long long launches = 0, C = 0; int nseg = 0, n_edges = 0;
+    std::vector<int> dest_row, row_dest;
+    long long P_uploaded = 0;
+#ifndef UX_EMU
+    std::map<long long, std::pair<cudaGraphExec_t, long long>> graphs;  // key -> (executable graph, kernels per launch)
+#endif
+    // device pointers of updatable static arrays
+    double *d_vmax = nullptr, *d_dpl_dn = nullptr, *d_udt = nullptr, *d_cap_out = nullptr, *d_cap_in = nullptr, *d_mp = nullptr, *d_penalty = nullptr, *d_toll = nullptr, *d_n_sig = nullptr;
+    int *d_l_flags = nullptr, *d_lvl_off = nullptr, *d_lvl_nodes = nullptr, *d_sg_off = nullptr, *d_sg = nullptr, *d_n_sig_off = nullptr;
+    double *d_scratch = nullptr; size_t scratch_bytes = 0;
+    double *d_ens = nullptr;
+};
+
+static std::string g_err;
+
+static int fail(ux_world *w, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    (w ? w->err : g_err) = buf;
+    return code;
+}
+
+#define CUDA_OK(call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(w, UX_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static T *dalloc(ux_world *w, size_t n, bool zero = true) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    if (zero) cudaMemset(p, 0, (n ? n : 1) * sizeof(T));
+    w->allocs.push_back(p);
+    return (T *)p;
+}
+template <typename T>
+static T *dupload(ux_world *w, const std::vector<T> &v) {
+    T *p = dalloc<T>(w, v.size(), false);
+    if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return p;
+}
+
+extern "C" {
+
+// create_world (bindings.cpp:150-181; World::World traffi.cpp:1165-1216)
+UX_API ux_world *ux_create_world(const ux_world_params *params) {
+    if (!params || params->delta_n <= 0 || params->tau <= 0) { fail(nullptr, UX_ERR_INVALID, "bad world params"); return nullptr; }
+#ifndef UX_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fail(nullptr, UX_ERR_CUDA, "no CUDA device: the uxsim_b200 engine has no CPU fallback"); return nullptr; }
+#endif
+    ux_world *w = new ux_world();
+    w->p = *params;
+    w->dt = params->tau * params->delta_n;
+    w->total_ts = (int)(params->t_max / (params->tau * params->delta_n));
+    w->route_ts = (int)(params->duo_update_time / (params->tau * params->delta_n));
+    if (w->route_ts == 0) w->route_ts = 1;
+    if (w->p.instantaneous_TT_timestep_interval <= 0) w->p.instantaneous_TT_timestep_interval = 5;
+    w->R = params->num_replicas > 0 ? params->num_replicas : 1;
+    w->timestep = 0;
+    if (params->device >= 0) { w->device = params->device; cudaSetDevice(w->device); } else cudaGetDevice(&w->device);
+    return w;
+}
+
+UX_API void ux_destroy_world(ux_world *w) {
+    if (!w) return;
+#ifndef UX_EMU
+    cudaSetDevice(w->device);
+    for (auto &g : w->graphs) cudaGraphExecDestroy(g.second.first);
+#endif
+    for (void *p : w->allocs) cudaFree(p);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+// add_node (bindings.cpp:186-190; Node::Node traffi.cpp:47-100)
+UX_API int ux_add_node(ux_world *w, double x, double y, const double *sig, int nsig, double sig_offset, double flow_capacity, int number_of_lanes) {
+    if (w->initialized) return fail(w, UX_ERR_RUNTIME, "add_node after initialize_adj_matrix");
+    HNode n;
+    n.x = x; n.y = y; n.sig_offset = sig_offset;
+    if (nsig <= 0) n.sig = {0.0}; else n.sig.assign(sig, sig + nsig);
+    n.sig_phase0 = 0; n.sig_t0 = 0;
+    double cycle = 0; for (double s : n.sig) cycle += s;
+    if (n.sig.size() > 1 || (n.sig.size() == 1 && n.sig[0] != 0)) {
+        double offset = cycle - sig_offset; int i = 0, guard = 0;
+        while (true) {
+            if (offset < n.sig[i]) { n.sig_phase0 = i; n.sig_t0 = offset; break; }
+            offset -= n.sig[i]; i++; if (i >= (int)n.sig.size()) i = 0;
+            if (++guard > 1000000) return fail(w, UX_ERR_INVALID, "signal offset walk does not terminate");
+        }
+    }
+    if (flow_capacity >= 0.0) { n.fc = flow_capacity; n.fc_rem0 = flow_capacity * w->p.tau * w->p.delta_n; n.lanes = number_of_lanes > 0 ? number_of_lanes : (int)std::ceil(flow_capacity / 0.8); }
+    else { n.fc = -1.0; n.fc_rem0 = 10e10; n.lanes = number_of_lanes; }
+    w->nodes.push_back(n);
+    return (int)w->nodes.size() - 1;
+}
+
+static void link_derive(ux_world *w, HLink &l) {  // Link::Link traffi.cpp:491-511
+    l.delta = 1.0 / l.kappa;
+    l.dpl = l.delta * l.lanes;
+    l.tau = w->p.tau / l.lanes;
+    l.w = 1 / l.tau / l.kappa;
+    l.capacity = l.vmax * l.w * l.kappa / (l.vmax + l.w);
+}
+
+// add_link (bindings.cpp:192-207; Link::Link traffi.cpp:465-537)
+UX_API int ux_add_link(ux_world *w, int start, int end, double vmax, double kappa, double length, int lanes, double merge_priority,
+                       double cap_out, double cap_in, const int *sg, int nsg) {
+    if (w->initialized) return fail(w, UX_ERR_RUNTIME, "add_link after initialize_adj_matrix");
+    int N = (int)w->nodes.size();
+    if (start < 0 || start >= N || end < 0 || end >= N) return fail(w, UX_ERR_OUT_OF_RANGE, "add_link: node id out of range");
+    if (lanes < 1) return fail(w, UX_ERR_INVALID, "add_link: number_of_lanes must be >= 1");
+    HLink l;
+    l.start = start; l.end = end; l.lanes = lanes; l.length = length; l.vmax = vmax; l.kappa = kappa <= 0.0 ? 0.2 : kappa; l.mp = merge_priority; l.penalty = 0.0;
+    link_derive(w, l);
+    l.cap_out = cap_out < 0.0 ? l.capacity * 2 : cap_out;
+    l.cap_out_rem0 = l.cap_out * w->dt;
+    if (cap_in < 0.0) { l.cap_in = l.capacity * 2; l.cap_in_rem0 = l.capacity * 2; } else { l.cap_in = cap_in; l.cap_in_rem0 = cap_in * w->dt; }
+    if (nsg <= 0) l.sg = {0}; else l.sg.assign(sg, sg + nsg);
+    int id = (int)w->links.size();
+    w->nodes[start].out.push_back(id); w->nodes[end].in.push_back(id);
+    w->links.push_back(l);
+    return id;
+}
+
+// add_demand (bindings.cpp:209-216; traffi.cpp:1910-1941)
+UX_API int64_t ux_add_demand(ux_world *w, int orig, int dest, double start_t, double end_t, double flow, const int *links_pref, int npref) {
+    int N = (int)w->nodes.size();
+    if (orig < 0 || orig >= N || dest < 0 || dest >= N) return fail(w, UX_ERR_OUT_OF_RANGE, "add_demand: node id out of range");
+    int ts_start = (int)(start_t / w->dt), ts_end = (int)(end_t / w->dt);
+    double demand = 0.0; int64_t made = 0;
+    for (int ts = ts_start; ts < ts_end; ts++) {
+        demand += flow * w->dt;
+        while (demand >= (double)w->p.delta_n) {
+            if (npref > 0) w->vlinks[1][(long long)w->vehs.size()] = std::vector<int>(links_pref, links_pref + npref);
+            w->vehs.push_back({orig, dest, ts});
+            demand -= (double)w->p.delta_n; made++;
+        }
+    }
+    return made;
+}
+
+UX_API int64_t ux_add_vehicles(ux_world *w, int64_t n, const int *orig, const int *dest, const int *ts) {
+    int N = (int)w->nodes.size();
+    for (int64_t i = 0; i < n; i++) if (orig[i] < 0 || orig[i] >= N || dest[i] < 0 || dest[i] >= N) return fail(w, UX_ERR_OUT_OF_RANGE, "add_vehicles: node id out of range");
+    w->vehs.reserve(w->vehs.size() + (size_t)n);
+    for (int64_t i = 0; i < n; i++) w->vehs.push_back({orig[i], dest[i], ts[i]});
+    return n;
+}
+
+UX_API int ux_set_vehicle_links(ux_world *w, int64_t vid, int kind, const int *links, int n) {
+    if (vid < 0 || vid >= (int64_t)w->vehs.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "vehicle index out of range");
+    if (kind < 0 || kind > 2) return fail(w, UX_ERR_INVALID, "bad kind");
+    if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "set_vehicle_links after the simulation started is not supported");
+    for (int i = 0; i < n; i++) if (links[i] < 0 || links[i] >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    std::vector<int> v(links, links + (n > 0 ? n : 0));
+    if (n > 0) w->vlinks[kind][vid] = v; else w->vlinks[kind].erase(vid);
+    if (kind == 0) { if (n > 0) w->vlinks[1][vid] = v; else w->vlinks[1].erase(vid); }  // traffi.cpp:1035-1039
+    return 0;
+}
+
+UX_API int ux_batch_enforce_routes_csr(ux_world *w, const int *ids, const int64_t *off, int64_t nveh) {
+    if (nveh > (int64_t)w->vehs.size()) nveh = (int64_t)w->vehs.size();
+    for (int64_t i = 0; i < nveh; i++) if (off[i + 1] > off[i]) { int rc = ux_set_vehicle_links(w, i, 0, ids + off[i], (int)(off[i + 1] - off[i])); if (rc) return rc; }
+    return 0;
+}
+
+UX_API int ux_set_t_max(ux_world *w, double t_max) {
+    if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "set_t_max after the simulation started is not supported");
+    w->p.t_max = t_max;
+    w->total_ts = (int)(t_max / w->dt);
+    return 0;
+}
+
+UX_API int ux_set_toll_timeseries(ux_world *w, int link, const double *toll, int n) {
+    if (link < 0 || link >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "set_toll_timeseries after the simulation started is not supported");
+    w->links[link].toll.assign(toll, toll + n);
+    return 0;
+}
+
+// World::initialize_adj_matrix (traffi.cpp:1245-1265): freeze the network.
+UX_API int ux_initialize_adj_matrix(ux_world *w) {
+    if (w->initialized) return 0;
+    if (w->p.adjust_node_capacity) {  // Node::adjust_node_capacity traffi.cpp:212-224
+        for (auto &n : w->nodes) {
+            if (n.fc < 0.0 && !n.in.empty() && !n.out.empty()) {
+                double ci = w->links[n.in[0]].capacity, co = w->links[n.out[0]].capacity;
+                for (int l : n.in) ci = std::max(ci, w->links[l].capacity);
+                for (int l : n.out) co = std::max(co, w->links[l].capacity);
+                n.fc = (ci + co) / 2.0; n.fc_rem0 = n.fc * w->dt;
+                if (n.lanes <= 0) n.lanes = (int)std::ceil(n.fc / 0.8);
+            }
+        }
+    }
+    for (size_t i = 0; i < w->nodes.size(); i++) {
+        auto &n = w->nodes[i];
+        if (n.in.size() > UX_MAXDEG || n.out.size() > UX_MAXDEG) return fail(w, UX_ERR_INVALID, "node %d: degree > %d not supported", (int)i, UX_MAXDEG);
+        int li = 0, lo = 0;
+        for (int l : n.in) li += w->links[l].lanes;
+        for (int l : n.out) lo += w->links[l].lanes;
+        if (li > UX_MAXC || lo > UX_MAXC) return fail(w, UX_ERR_INVALID, "node %d: more than %d lanes in or out not supported", (int)i, UX_MAXC);
+    }
+    w->initialized = true;
+    return 0;
+}
+
+// ---- transfer dependency levels (DESIGN.md "transfer order") --------------------------------------------
+static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<int> &lvl_off, std::vector<int> &lvl_nodes) {
+    int N = (int)w->nodes.size(), L = (int)w->links.size();
+    lflags.assign(L, 0);
+    std::vector<int> level(N, 0);
+    for (int a = 0; a < N; a++) {  // ascending id: dependencies (smaller ids) are final
+        int lv = 0;
+        for (int l : w->nodes[a].out) {
+            const HLink &k = w->links[l];
+            if (k.end < a) {
+                lflags[l] |= LF_END_LT_START;
+                double bound = 2.0 * k.vmax * w->dt + k.dpl * w->p.delta_n;  // SURVEY 7.3 #1 effects (i) and (ii)
+                if (k.length < bound) { lflags[l] |= LF_SEES_POPS; lv = std::max(lv, level[k.end] + 1); }
+            }
+        }
+        level[a] = lv;
+    }
+    int nl = 0; for (int a = 0; a < N; a++) nl = std::max(nl, level[a] + 1);
+    if (N == 0) nl = 1;
+    lvl_off.assign(nl + 1, 0);
+    for (int a = 0; a < N; a++) lvl_off[level[a] + 1]++;
+    for (int i = 0; i < nl; i++) lvl_off[i + 1] += lvl_off[i];
+    lvl_nodes.assign(N, 0);
+    std::vector<int> fill(nl, 0);
+    for (int a = 0; a < N; a++) lvl_nodes[lvl_off[level[a]] + fill[level[a]]++] = a;
+    w->n_levels = nl;
+}
+
+static int upload_link_params(ux_world *w) {
+    int L = (int)w->links.size();
+    std::vector<double> vmax(L), dpl_dn(L), udt(L), co(L), ci(L), mp(L), pen(L);
+    for (int i = 0; i < L; i++) {
+        const HLink &l = w->links[i];
+        vmax[i] = l.vmax; dpl_dn[i] = l.dpl * w->p.delta_n; udt[i] = l.vmax * w->dt; co[i] = l.cap_out; ci[i] = l.cap_in; mp[i] = l.mp; pen[i] = l.penalty;
+    }
+    size_t b = sizeof(double) * L;
+    CUDA_OK(cudaMemcpy(w->d_vmax, vmax.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_dpl_dn, dpl_dn.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_udt, udt.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_cap_out, co.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_cap_in, ci.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_mp, mp.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_penalty, pen.data(), b, cudaMemcpyHostToDevice));
+    std::vector<int> lflags, lvl_off, lvl_nodes;
+    compute_levels(w, lflags, lvl_off, lvl_nodes);
+    lvl_off.resize(w->nodes.size() + 2, lvl_off.back());
+    CUDA_OK(cudaMemcpy(w->d_l_flags, lflags.data(), sizeof(int) * L, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_lvl_off, lvl_off.data(), sizeof(int) * lvl_off.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_lvl_nodes, lvl_nodes.data(), sizeof(int) * lvl_nodes.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Build all device state.  Called lazily by the first main_loop (so that vehicles added after
+// initialize_adj_matrix but before the run are included, like the reference).
+static int upload(ux_world *w) {
+    cudaSetDevice(w->device);
+    CUDA_OK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    int N = (int)w->nodes.size(), L = (int)w->links.size(), T = w->total_ts;
+    long long P = (long long)w->vehs.size();
+    DevWorld base;
+    memset(&base, 0, sizeof(base));
+    base.N = N; base.L = L; base.T = T; base.P = P;
+    base.dn = w->p.delta_n; base.dt = w->dt; base.duo_w = w->p.duo_update_weight; base.duo_time = w->p.duo_update_time; base.noise = w->p.route_choice_uncertainty;
+    base.itt = w->p.instantaneous_TT_timestep_interval; base.route_ts = w->route_ts; base.hard_det = w->p.hard_deterministic_mode;
+    base.gradual = w->p.route_choice_update_gradual; base.no_cyclic = w->p.no_cyclic_routing; base.log_mode = w->p.vehicle_log_mode;
+    base.vis_words = (N + 31) / 32;
+    // ---- links
+    std::vector<int> l_start(L), l_end(L), l_lanes(L), l_rcap(L), sg_off(L + 1, 0), sg;
+    std::vector<long long> l_roff(L);
+    std::vector<double> l_length(L);
+    long long C = 0;
+    std::vector<int> seg_link, seg_start;
+    bool any_toll = false;
+    for (int i = 0; i < L; i++) {
+        const HLink &l = w->links[i];
+        l_start[i] = l.start; l_end[i] = l.end; l_lanes[i] = l.lanes; l_length[i] = l.length;
+        // jam storage of the link in platoons + entry slack (a platoon is accepted once the one `lanes` ahead has
+        // moved one spacing, so at most length/(delta_per_lane*dn) per lane + the ones at x <= spacing)
+        double per_lane = l.length / (l.dpl * w->p.delta_n);
+        long long cap = ((long long)std::floor(per_lane) + 3) * l.lanes + 2;
+        if (cap > 0x3fffffff) return fail(w, UX_ERR_INVALID, "link %d: ring too large", i);
+        l_rcap[i] = (int)cap; l_roff[i] = C; C += cap;
+        for (int s = 0; s < (int)cap; s += UX_SEG) { seg_link.push_back(i); seg_start.push_back(s); }
+        sg_off[i + 1] = sg_off[i] + (int)l.sg.size();
+        sg.insert(sg.end(), l.sg.begin(), l.sg.end());
+        if (!l.toll.empty()) any_toll = true;
+    }
+    w->C = C; w->nseg = (int)seg_link.size();
+    base.C = C; base.nseg = w->nseg;
+    base.l_start = dupload(w, l_start); base.l_end = dupload(w, l_end); base.l_lanes = dupload(w, l_lanes); base.l_rcap = dupload(w, l_rcap);
+    base.l_roff = dupload(w, l_roff); base.l_length = dupload(w, l_length);
+    w->d_sg_off = dupload(w, sg_off); w->d_sg = dupload(w, sg);
+    base.l_sg_off = w->d_sg_off; base.l_sg = w->d_sg;
+    base.seg_link = dupload(w, seg_link); base.seg_start = dupload(w, seg_start);
+    w->d_vmax = dalloc<double>(w, L); w->d_dpl_dn = dalloc<double>(w, L); w->d_udt = dalloc<double>(w, L); w->d_cap_out = dalloc<double>(w, L);
+    w->d_cap_in = dalloc<double>(w, L); w->d_mp = dalloc<double>(w, L); w->d_penalty = dalloc<double>(w, L);
+    w->d_l_flags = dalloc<int>(w, L); w->d_lvl_off = dalloc<int>(w, N + 2); w->d_lvl_nodes = dalloc<int>(w, N);
+    base.l_vmax = w->d_vmax; base.l_dpl_dn = w->d_dpl_dn; base.l_udt = w->d_udt; base.l_cap_out = w->d_cap_out; base.l_cap_in = w->d_cap_in;
+    base.l_mp = w->d_mp; base.l_penalty = w->d_penalty; base.l_flags = w->d_l_flags; base.lvl_off = w->d_lvl_off; base.lvl_nodes = w->d_lvl_nodes;
+    { int rc = upload_link_params(w); if (rc) return rc; }
+    if (any_toll) {  // [T][L]; links without a series use their static penalty (traffi.cpp:1285-1289)
+        std::vector<double> toll((size_t)T * L);
+        for (int t = 0; t < T; t++) for (int i = 0; i < L; i++) { const HLink &l = w->links[i]; toll[(size_t)t * L + i] = (!l.toll.empty() && t < (int)l.toll.size()) ? l.toll[t] : l.penalty; }
+        w->d_toll = dupload(w, toll); base.l_toll = w->d_toll;
+    }
+    // node pairs: links sharing (start, end) are averaged (traffi.cpp:1297-1300)
+    std::vector<int> pair_first(L), pair_off(L + 1, 0), pair_list, e_from, e_to, e_link;
+    {
+        std::map<std::pair<int, int>, int> first;
+        std::vector<std::vector<int>> members(L);
+        for (int i = 0; i < L; i++) {
+            auto key = std::make_pair(w->links[i].start, w->links[i].end);
+            auto it = first.find(key);
+            if (it == first.end()) { first[key] = i; pair_first[i] = i; } else pair_first[i] = it->second;
+            members[pair_first[i]].push_back(i);
+        }
+        // edges are indexed by e; pair_off/pair_list are indexed by the LEADING LINK id g = e_link[e]
+        for (int i = 0; i < L; i++) { pair_off[i + 1] = pair_off[i] + (int)members[i].size(); pair_list.insert(pair_list.end(), members[i].begin(), members[i].end()); }
+        for (int i = 0; i < L; i++) if (pair_first[i] == i) { e_from.push_back(w->links[i].start); e_to.push_back(w->links[i].end); e_link.push_back(i); }
+    }
+    w->n_edges = (int)e_link.size(); base.n_edges = w->n_edges;
+    base.l_pair_first = dupload(w, pair_first); base.l_pair_off = dupload(w, pair_off); base.l_pair_list = dupload(w, pair_list);
+    base.e_from = dupload(w, e_from); base.e_to = dupload(w, e_to); base.e_link = dupload(w, e_link);
+    // ---- nodes
+    std::vector<int> out_off(N + 1, 0), in_off(N + 1, 0), out, in, sig_off(N + 1, 0), n_lanes(N), n_out_lanes(N);
+    std::vector<double> n_sig, n_fc(N);
+    for (int i = 0; i < N; i++) {
+        const HNode &n = w->nodes[i];
+        out_off[i + 1] = out_off[i] + (int)n.out.size(); in_off[i + 1] = in_off[i] + (int)n.in.size();
+        out.insert(out.end(), n.out.begin(), n.out.end()); in.insert(in.end(), n.in.begin(), n.in.end());
+        sig_off[i + 1] = sig_off[i] + (int)n.sig.size(); n_sig.insert(n_sig.end(), n.sig.begin(), n.sig.end());
+        n_fc[i] = n.fc; n_lanes[i] = n.lanes;
+        int tl = 0; for (int l : n.out) tl += w->links[l].lanes; n_out_lanes[i] = tl;
+    }
+    base.n_out_off = dupload(w, out_off); base.n_out = dupload(w, out); base.n_in_off = dupload(w, in_off); base.n_in = dupload(w, in);
+    w->d_n_sig_off = dupload(w, sig_off); w->d_n_sig = dupload(w, n_sig);
+    base.n_sig_off = w->d_n_sig_off; base.n_sig = w->d_n_sig; base.n_fc = dupload(w, n_fc); base.n_lanes = dupload(w, n_lanes); base.n_out_lanes = dupload(w, n_out_lanes);
+    // ---- vehicles
+    std::vector<int> v_orig(P), v_dest(P), v_ts(P), gen_off(N + 1, 0), gen_list(P);
+    w->dest_row.assign(N, -1); w->row_dest.clear();
+    for (long long i = 0; i < P; i++) { v_orig[i] = w->vehs[i].orig; v_dest[i] = w->vehs[i].dest; v_ts[i] = w->vehs[i].ts; gen_off[v_orig[i] + 1]++; }
+    for (int i = 0; i < N; i++) gen_off[i + 1] += gen_off[i];
+    {   // per-origin FIFO order = (departure step, creation order): traffi.cpp:1663-1676 + 1804-1808
+        std::vector<long long> order(P);
+        for (long long i = 0; i < P; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](long long a, long long b) { return v_ts[a] < v_ts[b]; });
+        std::vector<int> fill(N, 0);
+        for (long long q = 0; q < P; q++) { long long i = order[q]; gen_list[gen_off[v_orig[i]] + fill[v_orig[i]]++] = (int)i; }
+    }
+    for (long long i = 0; i < P; i++) if (w->dest_row[v_dest[i]] < 0) w->dest_row[v_dest[i]] = 0;
+    for (int i = 0; i < N; i++) if (w->dest_row[i] == 0) { w->dest_row[i] = (int)w->row_dest.size(); w->row_dest.push_back(i); }
+    int D = (int)w->row_dest.size(); w->n_active = D; base.D = D;
+    base.v_orig = dupload(w, v_orig); base.v_dest = dupload(w, v_dest); base.v_depart_ts = dupload(w, v_ts);
+    base.gen_off = dupload(w, gen_off); base.gen_list = dupload(w, gen_list);
+    base.dest_row = dupload(w, w->dest_row); base.row_dest = dupload(w, w->row_dest);
+    for (int kind = 0; kind < 3; kind++) {
+        if (w->vlinks[kind].empty()) continue;
+        std::vector<int> off(P + 1, 0), list;
+        for (long long i = 0; i < P; i++) {
+            auto it = w->vlinks[kind].find(i);
+            if (it != w->vlinks[kind].end()) list.insert(list.end(), it->second.begin(), it->second.end());
+            off[i + 1] = (int)list.size();
+        }
+        base.vl_off[kind] = dupload(w, off); base.vl_list[kind] = dupload(w, list);
+    }
+    w->P_uploaded = P;
+    // ---- per-replica dynamic state
+    std::vector<double> co_rem(L), ci_rem(L), sig_t(N), fc_rem(N);
+    std::vector<int> sig_ph(N);
+    for (int i = 0; i < L; i++) { co_rem[i] = w->links[i].cap_out_rem0; ci_rem[i] = w->links[i].cap_in_rem0; }
+    for (int i = 0; i < N; i++) { sig_t[i] = w->nodes[i].sig_t0; sig_ph[i] = w->nodes[i].sig_phase0; fc_rem[i] = w->nodes[i].fc_rem0; }
+    std::vector<int> tb(1, w->timestep);
+    w->hw.assign(w->R, base);
+    size_t TL = (size_t)T * L;
+    for (int r = 0; r < w->R; r++) {
+        DevWorld &d = w->hw[r];
+        d.seed = w->p.random_seed + r;
+        d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L);
+        d.trips = dalloc<int>(w, L); d.ev_cnt = dalloc<int>(w, L); d.stat_count = dalloc<long long>(w, L);
+        d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem);
+        d.X = dalloc<double>(w, 2 * (size_t)C); d.V = dalloc<double>(w, C); d.VID = dalloc<int>(w, C); d.LANE = dalloc<int>(w, C);
+        d.sig_phase = dupload(w, sig_ph); d.sig_t = dupload(w, sig_t); d.fc_rem = dupload(w, fc_rem);
+        d.gen_head = dalloc<int>(w, N); d.gen_avail = dalloc<int>(w, N);
+        d.v_state = dalloc<int>(w, P); d.v_next = dalloc<int>(w, P); d.v_link = dalloc<int>(w, P, false); d.v_arr_ts = dalloc<int>(w, P, false); d.v_trav = dalloc<int>(w, P);
+        if (d.v_link) cudaMemset(d.v_link, 0xff, sizeof(int) * (P ? P : 1));
+        if (d.v_arr_ts) cudaMemset(d.v_arr_ts, 0xff, sizeof(int) * (P ? P : 1));
+        d.v_mr = dalloc<double>(w, P); d.v_atl = dalloc<double>(w, P); d.v_dist = dalloc<double>(w, P); d.v_entry_x = dalloc<double>(w, P);
+        { std::vector<double> m1(P, -1.0); d.v_tt = dupload(w, m1); }
+        d.v_flags = dalloc<unsigned char>(w, P);
+        d.v_visited = base.no_cyclic ? dalloc<unsigned>(w, (size_t)P * base.vis_words) : nullptr;
+        d.cum_arr = dalloc<double>(w, TL); d.cum_dep = dalloc<double>(w, TL); d.tt_inst = dalloc<double>(w, TL); d.ev_tt = dalloc<double>(w, TL);
+        d.ev_ord = dalloc<int>(w, TL); d.sig_log = dalloc<int>(w, (size_t)T * N);
+        d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
+        d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
+        if (d.rnext) cudaMemset(d.rnext, 0xff, sizeof(int) * std::max<size_t>((size_t)D * N, 1));
+        d.err = dalloc<int>(w, 2); d.t_base = dupload(w, tb);
+        if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
+            return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
+    }
+    w->dworlds = dalloc<DevWorld>(w, w->R, false);
+    if (!w->dworlds) return fail(w, UX_ERR_CUDA, "device allocation failed");
+    CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaDeviceSynchronize());
+    w->uploaded = true;
+    return 0;
+}
+
+// enqueue the kernels of `nsteps` timesteps starting at phase (t mod route_ts) = `phase` on the stream
+static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
+    int N = (int)w->nodes.size(), R = w->R;
+    cudaStream_t st = w->stream;
+    dim3 g_nodes((N * 32 + 127) / 128, R), g_update((w->nseg * 32 + 255) / 256, R);
+    long long lc = 0;
+    for (int s = 0; s < nsteps; s++) {
+        if (N > 0) { UX_LAUNCH(k_pre, g_nodes, dim3(128), st, w->dworlds, s); lc++; }
+        if (N > 0) for (int lv = 0; lv < w->n_levels; lv++) { UX_LAUNCH(k_transfer, g_nodes, dim3(128), st, w->dworlds, s, lv); lc++; }
+        if (w->nseg > 0) { UX_LAUNCH(k_update, g_update, dim3(256), st, w->dworlds, s); lc++; }
+        bool route = ((phase + s) % w->route_ts) == 0;
+        if (w->n_active > 0 && w->n_edges > 0) {
+            if (route) {
+                UX_LAUNCH(k_edge_cost, dim3((w->n_edges + 127) / 128, R), dim3(128), st, w->dworlds, s); lc++;
+                UX_LAUNCH(k_sssp, dim3(w->n_active, R), dim3(256), st, w->dworlds); lc++;
+            }
+            if (route || w->p.route_choice_update_gradual) {
+                long long tot = (long long)w->n_active * (long long)w->links.size();
+                UX_LAUNCH(k_duo, dim3((unsigned)((tot + 255) / 256), R), dim3(256), st, w->dworlds, w->p.route_choice_update_gradual ? 1 : 0); lc++;
+                UX_LAUNCH(k_duo_finish, dim3((w->n_active + 127) / 128, R), dim3(128), st, w->dworlds); lc++;
+            }
+        }
+    }
+    UX_LAUNCH(k_advance, dim3(1, R), dim3(32), st, w->dworlds, nsteps); lc++;
+    *launch_count = lc;
+}
+
+static const char *derr_text(int code) {
+    switch (code) {
+    case DERR_RING_FULL: return "link ring buffer overflow (link %d)";
+    case DERR_ROUTE_EXHAUSTED: return "Vehicle %d: specified route has no more links";
+    case DERR_ROUTE_INCONSISTENT: return "Vehicle %d: specified route is inconsistent; the forced link is not an outgoing link of the current node";
+    case DERR_AVOID_ALL: return "Vehicle %d: links_avoid excludes all outgoing links of the current node";
+    default: return "device error (info %d)";
+    }
+}
+
+// World::main_loop (traffi.cpp:1642-1866)
+UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
+    if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; }
+    int start_ts = w->timestep, end_ts;
+    double time_now = w->timestep * w->dt;
+    if (duration_t < 0 && until_t < 0) end_ts = w->total_ts;
+    else if (duration_t >= 0 && until_t < 0) end_ts = (int)std::floor((duration_t + time_now) / w->dt) + 1;
+    else if (duration_t < 0 && until_t >= 0) end_ts = (int)std::floor(until_t / w->dt) + 1;
+    else return fail(w, UX_ERR_RUNTIME, "Cannot specify both `duration_t` and `until_t` parameters for `World.main_loop`");
+    if (end_ts > w->total_ts) end_ts = w->total_ts;
+    if (end_ts <= start_ts) return 0;
+    cudaSetDevice(w->device);
+    if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
+    if ((long long)w->vehs.size() != w->P_uploaded) return fail(w, UX_ERR_RUNTIME, "adding vehicles after the simulation started is not supported yet by the CUDA engine");
+    if (w->net_dirty) { int rc = upload_link_params(w); if (rc) return rc; w->net_dirty = false; }
+    int t = start_ts;
+    while (t < end_ts) {
+        int phase = t % w->route_ts;
+        int nsteps = std::min(end_ts - t, w->route_ts - phase);
+        if (nsteps > 512) nsteps = 512;
+        long long lc = 0;
+#ifdef UX_EMU
+        enqueue_steps(w, nsteps, phase, &lc);
+#else
+        long long key = ((long long)nsteps << 32) | (unsigned)phase | ((long long)w->n_levels << 48);
+        auto it = w->graphs.find(key);
+        if (it == w->graphs.end()) {
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            CUDA_OK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_steps(w, nsteps, phase, &lc);
+            CUDA_OK(cudaStreamEndCapture(w->stream, &graph));
+            CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            it = w->graphs.emplace(key, std::make_pair(exec, lc)).first;
+        }
+        lc = it->second.second;
+        CUDA_OK(cudaGraphLaunch(it->second.first, w->stream));
+#endif
+        w->launches += lc;
+        t += nsteps;
+    }
+    CUDA_OK(cudaStreamSynchronize(w->stream));
+    CUDA_OK(cudaGetLastError());
+    for (int r = 0; r < w->R; r++) {
+        int e[2] = {0, 0};
+        CUDA_OK(cudaMemcpy(e, w->hw[r].err, sizeof(e), cudaMemcpyDeviceToHost));
+        if (e[0]) {
+            int code = e[0] == DERR_RING_FULL ? UX_ERR_CAPACITY : e[0] == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
+            w->timestep = end_ts;
+            return fail(w, code, derr_text(e[0]), e[1]);
+        }
+    }
+    w->timestep = end_ts;
+    return 0;
+}
+
+UX_API int ux_check_simulation_ongoing(ux_world *w) { return w->timestep < w->total_ts; }
+
+// ---- interventions ---------------------------------------------------------------------------------------
+UX_API int ux_set_link_param(ux_world *w, int link, int field, double value) {
+    if (link < 0 || link >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    HLink &l = w->links[link];
+    double *rem = nullptr; double rv = 0;
+    switch (field) {
+    case UX_LINK_VMAX: if (value >= 0) { l.vmax = value; l.w = 1.0 / l.tau / l.kappa; l.capacity = l.vmax * l.w * l.kappa / (l.vmax + l.w); l.delta = 1.0 / l.kappa; } break;
+    case UX_LINK_KAPPA: if (value >= 0) { l.kappa = value; l.w = 1.0 / l.tau / l.kappa; l.capacity = l.vmax * l.w * l.kappa / (l.vmax + l.w); l.delta = 1.0 / l.kappa; l.dpl = l.delta * l.lanes; } break;
+    case UX_LINK_CAPACITY_OUT: l.cap_out = value; break;
+    case UX_LINK_CAPACITY_IN: l.cap_in = value; break;
+    case UX_LINK_CAPACITY_OUT_REMAIN: l.cap_out_rem0 = value; rem = &l.cap_out_rem0; rv = value; break;
+    case UX_LINK_CAPACITY_IN_REMAIN: l.cap_in_rem0 = value; rem = &l.cap_in_rem0; rv = value; break;
+    case UX_LINK_MERGE_PRIORITY: l.mp = value; break;
+    case UX_LINK_ROUTE_CHOICE_PENALTY: l.penalty = value; break;
+    default: return fail(w, UX_ERR_INVALID, "unknown link field %d", field);
+    }
+    if (w->uploaded) {
+        cudaSetDevice(w->device);
+        if (rem) for (int r = 0; r < w->R; r++) CUDA_OK(cudaMemcpy((field == UX_LINK_CAPACITY_OUT_REMAIN ? w->hw[r].cap_out_rem : w->hw[r].cap_in_rem) + link, &rv, sizeof(double), cudaMemcpyHostToDevice));
+        else w->net_dirty = true;
+    }
+    return 0;
+}
+
+UX_API int ux_set_link_signal_group(ux_world *w, int link, const int *sg, int n) {
+    if (link < 0 || link >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    if (w->uploaded && n != (int)w->links[link].sg.size()) return fail(w, UX_ERR_RUNTIME, "changing the size of a signal group after the simulation started is not supported");
+    w->links[link].sg.assign(sg, sg + n);
+    if (w->uploaded) {
+        cudaSetDevice(w->device);
+        int off = 0; for (int i = 0; i < link; i++) off += (int)w->links[i].sg.size();
+        CUDA_OK(cudaMemcpy(w->d_sg + off, sg, sizeof(int) * n, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+UX_API int ux_set_node_signal(ux_world *w, int node, const double *sig, int nsig, int phase, double sig_t) {
+    if (node < 0 || node >= (int)w->nodes.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "node id out of range");
+    HNode &n = w->nodes[node];
+    bool reset = false;
+    if (sig && nsig > 0) {
+        if (w->uploaded && nsig != (int)n.sig.size()) return fail(w, UX_ERR_RUNTIME, "changing the number of signal phases after the simulation started is not supported");
+        n.sig.assign(sig, sig + nsig);
+    }
+    if (!w->uploaded) {
+        if (sig && nsig > 0 && n.sig_phase0 >= nsig) { n.sig_phase0 = 0; n.sig_t0 = 0; }
+        if (phase >= 0) n.sig_phase0 = phase;
+        if (sig_t >= 0) n.sig_t0 = sig_t;
+        return 0;
+    }
+    (void)reset;
+    cudaSetDevice(w->device);
+    if (sig && nsig > 0) { int off = 0; for (int i = 0; i < node; i++) off += (int)w->nodes[i].sig.size(); CUDA_OK(cudaMemcpy(w->d_n_sig + off, sig, sizeof(double) * nsig, cudaMemcpyHostToDevice)); }
+    for (int r = 0; r < w->R; r++) {
+        if (phase >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_phase + node, &phase, sizeof(int), cudaMemcpyHostToDevice));
+        if (sig_t >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_t + node, &sig_t, sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ---- results ---------------------------------------------------------------------------------------------
+static long long dsum_ll(ux_world *w, const long long *d, int n) {
+    std::vector<long long> h(n); if (n) cudaMemcpy(h.data(), d, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+    long long s = 0; for (auto v : h) s += v; return s;
+}
+static long long dsum_i(ux_world *w, const int *d, int n) {
+    std::vector<int> h(n); if (n) cudaMemcpy(h.data(), d, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    long long s = 0; for (auto v : h) s += v; return s;
+}
+
+UX_API int64_t ux_get_int(ux_world *w, int what) {
+    switch (what) {
+    case UX_I_NUM_NODES: return (int64_t)w->nodes.size();
+    case UX_I_NUM_LINKS: return (int64_t)w->links.size();
+    case UX_I_NUM_VEHICLES: return (int64_t)w->vehs.size();
+    case UX_I_TIMESTEP: return w->timestep;
+    case UX_I_TOTAL_TIMESTEPS: return w->total_ts;
+    case UX_I_NUM_REPLICAS: return w->R;
+    case UX_I_ROUTE_UPDATE_STEPS: return w->route_ts;
+    case UX_I_PLATOON_UPDATES: return w->uploaded ? dsum_ll(w, w->hw[0].stat_count, (int)w->links.size()) : 0;
+    case UX_I_TRIPS_COMPLETED: return w->uploaded ? dsum_i(w, w->hw[0].trips, (int)w->links.size()) : 0;
+    case UX_I_LOG_ENTRIES: return 0;
+    case UX_I_KERNEL_LAUNCHES: return w->launches;
+    case UX_I_NUM_ACTIVE_DESTS: return w->n_active;
+    case UX_I_TRANSFER_LEVELS: return w->n_levels;
+    case UX_I_LINK_EVENTS: return w->uploaded ? dsum_i(w, w->hw[0].ev_cnt, (int)w->links.size()) : 0;
+    default: return fail(w, UX_ERR_INVALID, "unknown int query %d", what);
+    }
+}
+
+UX_API double ux_get_double(ux_world *w, int what) {
+    switch (what) {
+    case UX_D_DELTA_T: return w->dt;
+    case UX_D_TIME: return w->timestep * w->dt;
+    case UX_D_T_MAX: return w->p.t_max;
+    default: return NAN;
+    }
+}
+
+UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
+    int64_t N = (int64_t)w->nodes.size(), L = (int64_t)w->links.size(), T = w->total_ts, P = (int64_t)w->vehs.size();
+    int dt = UX_DT_F64; int64_t n = -1;
+    switch (what) {
+    case UX_A_CUM_ARRIVAL: case UX_A_CUM_DEPARTURE: case UX_A_TRAVELTIME_INSTANT: case UX_A_TRAVELTIME_ACTUAL: n = L * T; break;
+    case UX_A_VEH_STATE: case UX_A_VEH_ARRIVAL_TS: case UX_A_VEH_DEPART_TS: case UX_A_VEH_ORIG: case UX_A_VEH_DEST: case UX_A_VEH_LINK: case UX_A_VEH_LANE: n = P; dt = UX_DT_I32; break;
+    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
+    case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
+    case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
+    case UX_A_NODE_SIGNAL_T: n = N; break;
+    case UX_A_LINK_NUM_VEHICLES: n = L; dt = UX_DT_I32; break;
+    case UX_A_LINK_CAPACITY_IN_REMAIN: case UX_A_LINK_CAPACITY_OUT_REMAIN: case UX_A_LINK_STAT_COUNT: case UX_A_LINK_TRIPS_COMPLETED: n = L; break;
+    case UX_A_ROUTE_PREF: n = N * L; break;
+    case UX_A_ROUTE_DIST: n = N * N; break;
+    case UX_A_ROUTE_NEXT: n = N * N; dt = UX_DT_I32; break;
+    default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
+    }
+    if (dtype) *dtype = dt;
+    return n;
+}
+
+static int ensure_scratch(ux_world *w, size_t bytes) {
+    if (bytes <= w->scratch_bytes) return 0;
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    w->allocs.push_back(p);
+    w->d_scratch = (double *)p; w->scratch_bytes = bytes;
+    return 0;
+}
+
+// Produce the array `what` of `replica` in DEVICE memory in its ABI layout; *dptr is either state memory or scratch.
+static int64_t device_array(ux_world *w, int what, int replica, void **dptr, int *dtype) {
+    int dt; int64_t n = ux_array_size(w, what, &dt);
+    if (n < 0) return n;
+    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; }
+    cudaSetDevice(w->device);
+    if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
+    const DevWorld &d = w->hw[replica];
+    int N = d.N, L = d.L, T = d.T; long long P = d.P;
+    cudaStream_t st = w->stream;
+    if (dtype) *dtype = dt;
+    auto transpose_d = [&](const double *src, int rows, int cols) -> int {
+        int rc = ensure_scratch(w, sizeof(double) * (size_t)rows * cols + 16); if (rc) return rc;
+        long long tot = (long long)rows * cols;
+        if (tot > 0) UX_LAUNCH(k_transpose<double>, dim3((unsigned)((tot + 255) / 256)), dim3(256), st, src, w->d_scratch, rows, cols);
+        *dptr = w->d_scratch; return 0; };
+    auto transpose_i = [&](const int *src, int rows, int cols) -> int {
+        int rc = ensure_scratch(w, sizeof(int) * (size_t)rows * cols + 16); if (rc) return rc;
+        long long tot = (long long)rows * cols;
+        if (tot > 0) UX_LAUNCH(k_transpose<int>, dim3((unsigned)((tot + 255) / 256)), dim3(256), st, src, (int *)w->d_scratch, rows, cols);
+        *dptr = w->d_scratch; return 0; };
+    int rc = 0;
+    switch (what) {
+    case UX_A_CUM_ARRIVAL: rc = transpose_d(d.cum_arr, T, L); break;
+    case UX_A_CUM_DEPARTURE: rc = transpose_d(d.cum_dep, T, L); break;
+    case UX_A_TRAVELTIME_INSTANT: rc = transpose_d(d.tt_inst, T, L); break;
+    case UX_A_TRAVELTIME_ACTUAL:
+        rc = ensure_scratch(w, sizeof(double) * (size_t)T * L + 16); if (rc) break;
+        if (L > 0) UX_LAUNCH(k_tt_actual, dim3((L + 127) / 128), dim3(128), st, w->dworlds, replica, w->d_scratch);
+        *dptr = w->d_scratch; break;
+    case UX_A_SIGNAL_LOG: rc = transpose_i(d.sig_log, T, N); break;
+    case UX_A_VEH_ARRIVAL_TS: *dptr = d.v_arr_ts; break;
+    case UX_A_VEH_DEPART_TS: *dptr = (void *)d.v_depart_ts; break;
+    case UX_A_VEH_TRAVEL_TIME: *dptr = d.v_tt; break;
+    case UX_A_VEH_ORIG: *dptr = (void *)d.v_orig; break;
+    case UX_A_VEH_DEST: *dptr = (void *)d.v_dest; break;
+    case UX_A_VEH_LINK: *dptr = d.v_link; break;
+    case UX_A_NODE_SIGNAL_PHASE: *dptr = d.sig_phase; break;
+    case UX_A_NODE_SIGNAL_T: *dptr = d.sig_t; break;
+    case UX_A_LINK_CAPACITY_IN_REMAIN: *dptr = d.cap_in_rem; break;
+    case UX_A_LINK_CAPACITY_OUT_REMAIN: *dptr = d.cap_out_rem; break;
+    case UX_A_VEH_X: case UX_A_VEH_V: case UX_A_VEH_LANE: {
+        rc = ensure_scratch(w, (sizeof(double) * 2 + sizeof(int)) * (size_t)(P ? P : 1) + 64); if (rc) break;
+        double *vx = w->d_scratch, *vv = vx + P; int *vl = (int *)(vv + P);
+        CUDA_OK(cudaMemsetAsync(vx, 0, sizeof(double) * 2 * P + sizeof(int) * P, st));
+        if (w->nseg > 0) UX_LAUNCH(k_veh_snapshot, dim3((w->nseg * 32 + 255) / 256), dim3(256), st, w->dworlds, replica, vx, vv, vl);
+        *dptr = what == UX_A_VEH_X ? (void *)vx : what == UX_A_VEH_V ? (void *)vv : (void *)vl; break; }
+    default: *dptr = nullptr; break;  // assembled on the host
+    }
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    return n;
+}
+
+UX_API int64_t ux_get_device_array(ux_world *w, int what, int replica, void **dptr, int *dtype) {
+    int64_t n = device_array(w, what, replica, dptr, dtype);
+    if (n >= 0 && *dptr == nullptr) return fail(w, UX_ERR_INVALID, "array %d has no device form; use get_array", what);
+    return n;
+}
+
+UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    void *dptr = nullptr; int dt = 0;
+    int64_t n = device_array(w, what, replica, &dptr, &dt);
+    if (n < 0) return n;
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    size_t es = dt == UX_DT_F64 ? 8 : dt == UX_DT_I32 ? 4 : 8;
+    if (dptr) { if (n > 0) CUDA_OK(cudaMemcpy(dst, dptr, es * (size_t)n, cudaMemcpyDeviceToHost)); return n; }
+    const DevWorld &d = w->hw[replica];
+    int N = d.N, L = d.L; long long P = d.P;
+    double *o = (double *)dst; int *oi = (int *)dst;
+    switch (what) {
+    case UX_A_VEH_STATE: {  // HOME/WAIT are derived from the departure step (traffi.cpp:836-841)
+        std::vector<int> st(P); if (P) CUDA_OK(cudaMemcpy(st.data(), d.v_state, sizeof(int) * P, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < P; i++) {
+            int s = st[i];
+            if (s == UX_VS_HOME && w->vehs[i].ts <= w->timestep - 1) s = UX_VS_WAIT;
+            oi[i] = s;
+        }
+        break; }
+    case UX_A_VEH_DISTANCE: {
+        std::vector<double> dist(P), ex(P), vx(P); std::vector<int> st(P);
+        void *px = nullptr; int64_t m = device_array(w, UX_A_VEH_X, replica, &px, nullptr); if (m < 0) return m;
+        if (P) { CUDA_OK(cudaMemcpy(vx.data(), px, sizeof(double) * P, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(dist.data(), d.v_dist, sizeof(double) * P, cudaMemcpyDeviceToHost));
+                 CUDA_OK(cudaMemcpy(ex.data(), d.v_entry_x, sizeof(double) * P, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(st.data(), d.v_state, sizeof(int) * P, cudaMemcpyDeviceToHost)); }
+        for (long long i = 0; i < P; i++) o[i] = dist[i] + (st[i] == UX_VS_RUN ? vx[i] - ex[i] : 0.0);
+        break; }
+    case UX_A_LINK_NUM_VEHICLES: {
+        std::vector<int> hd(2 * (size_t)L), tl(L);
+        if (L) { CUDA_OK(cudaMemcpy(hd.data(), d.head, sizeof(int) * 2 * L, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(tl.data(), d.tail, sizeof(int) * L, cudaMemcpyDeviceToHost)); }
+        int cur = w->timestep & 1;
+        for (int l = 0; l < L; l++) oi[l] = tl[l] - hd[(size_t)cur * L + l];
+        break; }
+    case UX_A_LINK_STAT_COUNT: { std::vector<long long> h(L); if (L) CUDA_OK(cudaMemcpy(h.data(), d.stat_count, sizeof(long long) * L, cudaMemcpyDeviceToHost)); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
+    case UX_A_LINK_TRIPS_COMPLETED: { std::vector<int> h(L); if (L) CUDA_OK(cudaMemcpy(h.data(), d.trips, sizeof(int) * L, cudaMemcpyDeviceToHost)); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
+    case UX_A_ROUTE_PREF: {
+        std::vector<double> h((size_t)d.D * L); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.pref, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < N; k++) { int r = w->dest_row[k]; for (int l = 0; l < L; l++) o[(size_t)k * L + l] = r >= 0 ? h[(size_t)r * L + l] : 0.0; }
+        break; }
+    case UX_A_ROUTE_DIST: {
+        std::vector<double> h((size_t)d.D * N); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.rdist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        bool searched = w->timestep > 0;
+        for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = w->dest_row[k]; o[(size_t)i * N + k] = (r >= 0 && searched) ? h[(size_t)r * N + i] : INFINITY; }
+        break; }
+    case UX_A_ROUTE_NEXT: {
+        std::vector<int> h((size_t)d.D * N); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.rnext, sizeof(int) * h.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = w->dest_row[k]; oi[(size_t)i * N + k] = r >= 0 ? h[(size_t)r * N + i] : -1; }
+        break; }
+    default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
+    }
+    return n;
+}
+
+UX_API int64_t ux_ensemble_link_stats_device(ux_world *w, void **dptr) {
+    if (!w->uploaded) return fail(w, UX_ERR_RUNTIME, "ensemble_link_stats before the simulation ran");
+    cudaSetDevice(w->device);
+    int L = (int)w->links.size();
+    if (!w->d_ens) w->d_ens = dalloc<double>(w, (size_t)L * 4);
+    if (L > 0) UX_LAUNCH(k_ensemble_stats, dim3((L + 127) / 128), dim3(128), w->stream, w->dworlds, w->R, w->d_ens);
+    CUDA_OK(cudaStreamSynchronize(w->stream));
+    *dptr = w->d_ens;
+    return (int64_t)L * 4;
+}
+
+UX_API int64_t ux_ensemble_link_stats(ux_world *w, double *dst, int64_t capacity) {
+    void *d = nullptr;
+    int64_t n = ux_ensemble_link_stats_device(w, &d);
+    if (n < 0) return n;
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "capacity too small");
+    if (n > 0) CUDA_OK(cudaMemcpy(dst, d, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+UX_API const char *ux_last_error(ux_world *w) { return w ? w->err.c_str() : g_err.c_str(); }
+
+}  // extern "C"

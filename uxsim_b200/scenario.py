@@ -407,9 +407,10 @@ def _load_npz(name: str):
 
 def from_tables(name: str, world: Dict[str, Any], z) -> Scenario:
     s = Scenario(name, world)
+    z = {k: z[k] for k in z.files}  # NpzFile decompresses on every access: load each table once
     for nm, x, y in zip(z["node_name"], z["node_x"], z["node_y"]):
         s.addNode(str(nm), float(x), float(y))
-    has = lambda k: k in z.files
+    has = lambda k: k in z
     L = len(z["link_name"])
     for i in range(L):
         s.addLink(str(z["link_name"][i]), str(z["link_start"][i]), str(z["link_end"][i]), length=float(z["link_length"][i]),

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- platoon-updates/sec of the simulation loop (World.exec_simulation) on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload chicago|chicago_dn5|grid11|siouxfalls]
+                    [--replicas R] [--impl ours|reference]
+
+A "step" = one full run of the workload's simulation loop (all T timesteps) for a batch of R seeded replicas per
+GPU.  `value` = RUN platoon-updates of all replicas on all GPUs / device time of main_loop (inputs resident in
+HBM, CUDA events on the engine's launch stream, max over ranks).  `e2e` = the same metric through the C-ABI from
+HOST arrays: create world + vectorised ingest + upload (H2D) + main_loop + read-back (D2H) inside the timed
+region.  `--impl reference` times the reference's own C++ engine (oracle/_ref, built from the reference sources;
+else the oracle port) on the host cores for the same workload / metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (builder kwargs, description)
+    "chicago": ("chicago_sketch", dict(deltan=30, tmax=10000), "Chicago sketch, deltan=30, tmax=10000 (example_23en): 546 nodes, 2176 links, 32284 platoons = 968520 veh, 333 steps"),
+    "chicago_dn5": ("chicago_sketch", dict(deltan=5, tmax=10000), "Chicago sketch, deltan=5: 211782 platoons = 1058910 veh, 2000 steps"),
+    "grid11": ("grid", dict(n=11, deltan=5, tmax=7200), "11x11 grid (example_04en): 121 nodes, 440 links, 12100 platoons = 60500 veh, 1440 steps"),
+    "siouxfalls": ("sioux_falls", dict(deltan=5, tmax=7200), "Sioux Falls: 24 nodes, 76 links, 6938 platoons, 1440 steps"),
+}
+ALG_BYTES = {  # algorithmic bytes (SURVEY.md 8d / DESIGN.md)
+    "per_platoon_update": 32, "per_link_step": 40, "per_node_step": 20, "per_transfer": 160,
+}
+
+
+def make_scenario(workload, seed):
+    from uxsim_b200 import scenario as S
+
+    fn, kw, _ = WORKLOADS[workload]
+    return getattr(S, fn)(seed=seed, **kw)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def load_reference_lib():
+    from uxsim_b200._capi import CApi
+
+    ref = os.path.join(ROOT, "oracle", "_ref", "libuxsim_ref.so")
+    if os.path.exists(ref):
+        return CApi(ref, "uxr_"), "reference"
+    ora = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(ora):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True, capture_output=True)
+    return CApi(ora, "uxo_"), "port"
+
+
+def time_reference(workload, seeds, threads):
+    """Run the reference C++ engine (or the oracle port) on the host cores; returns (updates, seconds)."""
+    from uxsim_b200 import _capi as C
+
+    api, kind = load_reference_lib()
+    upd, secs = 0, 0.0
+    for s in seeds:
+        sc = make_scenario(workload, s)
+        E = sc.engine_from_tables(api, sc.tables(), vehicle_logging_timestep_interval=-1, threads=threads)
+        t0 = time.perf_counter()
+        E.main_loop()
+        secs += time.perf_counter() - t0
+        upd += E.get_int(C.I_PLATOON_UPDATES)
+        E.close()
+    return upd, secs, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = -1 if cores > 1 else 1
+    sample_seeds = 2 if args.workload == "chicago" else 1
+    ms, upd_total, t_total = [], 0, 0.0
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        seeds = [1000 + i * sample_seeds + k for k in range(sample_seeds)]
+        upd, secs, kind = time_reference(args.workload, seeds, threads)
+        if i >= args.warmup:
+            ms.append(secs * 1e3)
+            upd_total += upd
+            t_total += secs
+    value = upd_total / t_total
+    line = {
+        "impl": "reference", "metric": "platoon_updates_per_sec", "value": value, "unit": "platoon-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "fixture+synthetic-seeds",
+        "config": {"workload": WORKLOADS[args.workload][2], "replicas_per_step": sample_seeds,
+                   "engine": "reference trafficpp C++ (traffi.cpp via oracle/ref_harness.cpp, OpenMP)" if kind == "reference" else "oracle port (plain C, 1 thread)"},
+        "cpu_baseline": {"value": value, "unit": "platoon-updates/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+                         "sample": f"{sample_seeds} seed(s) of the workload per step, vehicle logging off, timing around main_loop only"},
+        "e2e": {"value": value, "unit": "platoon-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="chicago", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=32, help="seeded replicas per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from uxsim_b200 import _capi as C
+    from uxsim_b200.ensemble import _CudaArrayView
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    api = C.load_product()  # raises without the CUDA library: no fallback
+    R = args.replicas
+    sc = make_scenario(args.workload, 0)
+    tab = sc.tables()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def build(step, **over):
+        seed = 100000 * step + rank * R  # distinct seeds per step, rank, replica
+        return sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, device=local_rank, random_seed=seed, **over)
+
+    def reduce_stats(E):
+        """The path's only exchange step: all-reduce of per-link ensemble statistics [L,4] (NCCL, N>1 only)."""
+        ptr = C.C.c_void_p(0)
+        n = E._check(api.ensemble_link_stats_device(E.h, C.C.byref(ptr)))
+        t = torch.as_tensor(_CudaArrayView(ptr.value, int(n), np.float64, E), device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def updates_of(E):
+        return sum(int(E.get_array(C.A_LINK_STAT_COUNT, r).sum()) for r in range(R))
+
+    # ------------------------------------------------------------------ value: device-timed, inputs resident
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    step_ms, upd_total, launches = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        E = build(i)
+        E.get_array(C.A_LINK_NUM_VEHICLES)  # forces allocation + upload: inputs are resident before timing
+        flush_buf.zero_()
+        barrier()
+        if i == args.warmup and sampler:
+            sampler.start()
+        l0 = E.get_int(C.I_KERNEL_LAUNCHES)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        E.main_loop()  # CUDA graphs on the engine's stream; returns after the stream is drained
+        ms = E.get_double(C.D_LAST_LOOP_MS)  # CUDA events on the launching stream, recorded inside the engine
+        if world > 1:
+            reduce_stats(E)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            ms = max(ms, ev0.elapsed_time(ev1))  # includes the all-reduce
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        if i >= args.warmup:
+            step_ms.append(ms)
+            upd = updates_of(E)
+            launches += E.get_int(C.I_KERNEL_LAUNCHES) - l0
+            if world > 1:
+                t = torch.tensor([upd], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t)
+                upd = int(t.item())
+            upd_total += upd
+        E.close()
+    clocks = sampler.stop() if sampler else None
+    value = upd_total / (sum(step_ms) / 1e3)
+
+    # ------------------------------------------------------------------ e2e: host arrays -> C-ABI -> host results
+    e2e_s, e2e_upd, h2d, d2h = 0.0, 0, 0, 0
+    pinned = {}
+    for i in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        E = build(1000 + i)
+        E.main_loop()
+        stats = reduce_stats(E)
+        host_stats = stats.cpu()
+        res = [(E.get_array(C.A_VEH_ARRIVAL_TS, r), E.get_array(C.A_VEH_TRAVEL_TIME, r), E.get_array(C.A_LINK_STAT_COUNT, r)) for r in range(R)]
+        curves = (E.get_array(C.A_CUM_ARRIVAL, 0), E.get_array(C.A_CUM_DEPARTURE, 0))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        if i >= args.warmup:
+            upd = sum(int(x[2].sum()) for x in res)
+            if world > 1:
+                t = torch.tensor([upd], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t)
+                upd = int(t.item())
+            e2e_s += dt
+            e2e_upd += upd
+            h2d = E.get_int(C.I_H2D_BYTES)
+            d2h = E.get_int(C.I_D2H_BYTES) + host_stats.numel() * 8
+        del curves, res
+        E.close()
+    e2e_value = e2e_upd / e2e_s
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (rank 0)
+    roofline, kernels, cpu_baseline, single = None, None, None, None
+    if rank == 0:
+        E = build(5000)
+        E.set_option(C.OPT_KERNEL_TIMING, 1)  # eager launches with a CUDA-event pair around each kernel
+        E.main_loop()
+        T, L, N = E.get_int(C.I_TOTAL_TIMESTEPS), E.get_int(C.I_NUM_LINKS), E.get_int(C.I_NUM_NODES)
+        upd = updates_of(E)
+        transfers = sum(int(E.get_array(C.A_LINK_TRIPS_COMPLETED, r).sum()) for r in range(R))
+        events = E.get_int(C.I_LINK_EVENTS) * R
+        kms = {C.K_NAMES[k]: E.get_double(C.D_KERNEL_MS_OF + k) for k in range(len(C.K_NAMES))}
+        kl = {C.K_NAMES[k]: E.get_int(C.I_KERNEL_LAUNCHES_OF + k) for k in range(len(C.K_NAMES))}
+        tot_ms = sum(kms.values())
+        alg = {
+            "k_update": ALG_BYTES["per_platoon_update"] * upd,
+            "k_pre": (ALG_BYTES["per_link_step"] * L + ALG_BYTES["per_node_step"] * N) * T * R,
+            "k_transfer": ALG_BYTES["per_transfer"] * events,
+        }
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kernels = {}
+        for k in kms:
+            if kl[k] == 0:
+                continue
+            avg_us = kms[k] / kl[k] * 1e3
+            kernels[k] = {"share": kms[k] / tot_ms, "launches": kl[k], "avg_us": avg_us}
+            if k in alg:
+                per_launch = alg[k] / kl[k]
+                kernels[k]["alg_bytes_per_launch"] = per_launch
+                kernels[k]["GBps"] = per_launch / (avg_us * 1e-6) / 1e9
+        dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["share"])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["GBps"] / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                    "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"], "avg_launch_us": kernels[dom]["avg_us"],
+                    "note": "every kernel of this path is latency/launch-bound at this size (no tensor cores); see DESIGN.md"}
+        E.close()
+        # single-scenario latency (the "Chicago-sketch sim wall time" half of the metric)
+        lat = []
+        for i in range(3):
+            E1 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=1, device=local_rank, random_seed=42)
+            E1.get_array(C.A_LINK_NUM_VEHICLES)
+            E1.main_loop()
+            lat.append(E1.get_double(C.D_LAST_LOOP_MS))
+            u1 = int(E1.get_array(C.A_LINK_STAT_COUNT, 0).sum())
+            E1.close()
+        single = {"scenario_wall_ms": float(np.median(lat)), "platoon_updates": u1, "updates_per_sec": u1 / (np.median(lat) / 1e3)}
+        # CPU baseline on this box's host cores: bounded sample of the same workload
+        if world == 1:
+            cores = os.cpu_count() or 1
+            t_cpu, u_cpu, n_seed, kind = 0.0, 0, 0, "reference"
+            while t_cpu < args.cpu_seconds and n_seed < 64:
+                u, s_, kind = time_reference(args.workload, [2000 + n_seed], -1 if cores > 1 else 1)
+                u_cpu += u
+                t_cpu += s_
+                n_seed += 1
+            cpu_baseline = {"value": u_cpu / t_cpu, "unit": "platoon-updates/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+                            "sample": f"{n_seed} seeds of the workload, one scenario at a time, {t_cpu:.1f} s of main_loop, vehicle logging off",
+                            "scenario_wall_ms": 1e3 * t_cpu / n_seed}
+
+    if rank == 0:
+        line = {
+            "metric": "platoon_updates_per_sec", "value": value, "unit": "platoon-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "fixture network+demand (converted from the reference's dat/), synthetic seeds",
+            "config": {"workload": WORKLOADS[args.workload][2], "replicas_per_gpu": R, "global_replicas": R * world,
+                       "l2_flush": "256 MiB write between timed steps; every step runs on freshly allocated state",
+                       "timing": "CUDA events on the engine's launch stream around all graph launches of main_loop; max over ranks",
+                       "e2e_readback": "per replica: arrival step + travel time per platoon, per-link RUN counts; ensemble link stats [L,4]; cumulative curves of replica 0",
+                       "parallelism": f"replicas x{R} per GPU (blockIdx.y), ranks x{world}, NCCL all-reduce of link stats only"},
+            "e2e": {"value": e2e_value, "unit": "platoon-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "single_scenario": single,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

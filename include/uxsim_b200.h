@@ -112,6 +112,20 @@ UX_API int64_t UX_FN(add_demand)(ux_world *w, int orig, int dest, double start_t
  * platoon): n platoons with departure timestep depart_ts[i] (time = depart_ts * delta_t). */
 UX_API int64_t UX_FN(add_vehicles)(ux_world *w, int64_t n, const int *orig, const int *dest, const int *depart_ts);
 
+/* Vectorised scenario ingest: the same three calls over arrays, so that a whole scenario crosses
+ * the FFI in three calls instead of one call per node / link / OD row (uxsim_cpp_wrapper.py pays one nanobind
+ * call each).  Semantics are exactly add_node / add_link / add_demand applied in index order; CSR offsets have
+ * n+1 entries.  Return the number of entities (platoons for add_demands) created, or an error code. */
+UX_API int64_t UX_FN(add_nodes)(ux_world *w, int64_t n, const double *x, const double *y, const int *signal_off,
+                                const double *signal_intervals, const double *signal_offset, const double *flow_capacity,
+                                const int *number_of_lanes);
+UX_API int64_t UX_FN(add_links)(ux_world *w, int64_t n, const int *start_node, const int *end_node, const double *vmax,
+                                const double *kappa, const double *length, const int *number_of_lanes,
+                                const double *merge_priority, const double *capacity_out, const double *capacity_in,
+                                const int *signal_group_off, const int *signal_group);
+UX_API int64_t UX_FN(add_demands)(ux_world *w, int64_t n, const int *orig, const int *dest, const double *start_t,
+                                  const double *end_t, const double *flow);
+
 /* Vehicle.enforce_route / links_preferred / links_avoid (bindings.cpp Vehicle class; traffi.cpp:1035-1039).
  * kind: 0 = specified_route (also sets links_preferred, as enforce_route does), 1 = links_preferred,
  * 2 = links_avoid.  n == 0 clears. */
@@ -176,11 +190,26 @@ enum {
     UX_I_KERNEL_LAUNCHES = 11, /* CUDA kernels launched so far (product only; 0 elsewhere) */
     UX_I_NUM_ACTIVE_DESTS = 12,
     UX_I_TRANSFER_LEVELS = 13, /* number of dependency levels of the node-transfer stage */
-    UX_I_LINK_EVENTS = 14      /* link-exit events recorded (replica 0) */
+    UX_I_LINK_EVENTS = 14,     /* link-exit events recorded (replica 0) */
+    UX_I_H2D_BYTES = 15,       /* bytes copied host->device so far (product only) */
+    UX_I_D2H_BYTES = 16,       /* bytes copied device->host so far (product only) */
+    UX_I_RING_SLOTS = 17,      /* total ring-buffer slots per replica */
+    UX_I_KERNEL_LAUNCHES_OF = 100 /* + kernel id (UX_K_*): launches of that kernel in timing mode */
 };
+/* kernel ids for the timing mode */
+enum { UX_K_PRE = 0, UX_K_TRANSFER = 1, UX_K_UPDATE = 2, UX_K_EDGE_COST = 3, UX_K_SSSP = 4, UX_K_DUO = 5, UX_K_MISC = 6, UX_K_COUNT = 7 };
 UX_API int64_t UX_FN(get_int)(ux_world *w, int what);
 UX_API double UX_FN(get_double)(ux_world *w, int what);
-enum { UX_D_DELTA_T = 1, UX_D_TIME = 2, UX_D_T_MAX = 3, UX_D_AVE_V_SUM = 4, UX_D_STAT_SAMPLE_COUNT = 5 };
+enum {
+    UX_D_DELTA_T = 1, UX_D_TIME = 2, UX_D_T_MAX = 3, UX_D_AVE_V_SUM = 4, UX_D_STAT_SAMPLE_COUNT = 5,
+    UX_D_LAST_LOOP_MS = 6,      /* device time of the last main_loop, CUDA events on the launching stream (product only) */
+    UX_D_KERNEL_MS_OF = 100     /* + kernel id: summed device time of that kernel in timing mode [ms] */
+};
+/* engine options (product only; the test libraries accept and ignore them) */
+enum {
+    UX_OPT_KERNEL_TIMING = 1    /* 1: launch kernels eagerly with a CUDA-event pair around each (for roofline numbers) */
+};
+UX_API int UX_FN(set_option)(ux_world *w, int option, double value);
 
 /* array results; layouts are row-major.  T = total_timesteps, L = links, N = nodes, P = vehicles. */
 enum {

@@ -1120,4 +1120,23 @@ UX_API int64_t uxo_ensemble_link_stats(ux_world *w, double *dst, int64_t capacit
 }
 UX_API int64_t uxo_ensemble_link_stats_device(ux_world *w, void **dptr) { (void)dptr; return fail(w, UX_ERR_RUNTIME, "the oracle has no device arrays"); }
 
+#define PFX(n) uxo_##n
+/* vectorised ingest: add_node / add_link / add_demand in index order (include/uxsim_b200.h) */
+UX_API int64_t PFX(add_nodes)(ux_world *w, int64_t n, const double *x, const double *y, const int *so, const double *sig,
+                              const double *sig_offset, const double *fc, const int *lanes) {
+    for (int64_t i = 0; i < n; i++) { int rc = PFX(add_node)(w, x[i], y[i], sig + so[i], so[i + 1] - so[i], sig_offset[i], fc[i], lanes[i]); if (rc < 0) return rc; }
+    return n;
+}
+UX_API int64_t PFX(add_links)(ux_world *w, int64_t n, const int *a, const int *b, const double *vmax, const double *kappa, const double *len,
+                              const int *lanes, const double *mp, const double *co, const double *ci, const int *go, const int *sg) {
+    for (int64_t i = 0; i < n; i++) { int rc = PFX(add_link)(w, a[i], b[i], vmax[i], kappa[i], len[i], lanes[i], mp[i], co[i], ci[i], sg + go[i], go[i + 1] - go[i]); if (rc < 0) return rc; }
+    return n;
+}
+UX_API int64_t PFX(add_demands)(ux_world *w, int64_t n, const int *o, const int *d, const double *t0, const double *t1, const double *flow) {
+    int64_t made = 0;
+    for (int64_t i = 0; i < n; i++) { int64_t m = PFX(add_demand)(w, o[i], d[i], t0[i], t1[i], flow[i], 0, 0); if (m < 0) return m; made += m; }
+    return made;
+}
+UX_API int PFX(set_option)(ux_world *w, int option, double value) { (void)w; (void)option; (void)value; return 0; }
+
 UX_API const char *uxo_last_error(ux_world *w) { return w ? w->err : g_err; }

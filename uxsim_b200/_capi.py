@@ -34,7 +34,10 @@ LINK_CAPACITY_OUT_REMAIN, LINK_CAPACITY_IN_REMAIN, LINK_MERGE_PRIORITY, LINK_ROU
 I_NUM_NODES, I_NUM_LINKS, I_NUM_VEHICLES, I_TIMESTEP, I_TOTAL_TIMESTEPS, I_NUM_REPLICAS = 1, 2, 3, 4, 5, 6
 I_ROUTE_UPDATE_STEPS, I_PLATOON_UPDATES, I_TRIPS_COMPLETED, I_LOG_ENTRIES, I_KERNEL_LAUNCHES = 7, 8, 9, 10, 11
 I_NUM_ACTIVE_DESTS, I_TRANSFER_LEVELS, I_LINK_EVENTS = 12, 13, 14
-D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT = 1, 2, 3, 4, 5
+I_H2D_BYTES, I_D2H_BYTES, I_RING_SLOTS, I_KERNEL_LAUNCHES_OF = 15, 16, 17, 100
+K_NAMES = ("k_pre", "k_transfer", "k_update", "k_edge_cost", "k_sssp", "k_duo", "misc")
+OPT_KERNEL_TIMING = 1
+D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT, D_LAST_LOOP_MS, D_KERNEL_MS_OF = 1, 2, 3, 4, 5, 6, 100
 
 A_CUM_ARRIVAL, A_CUM_DEPARTURE, A_TRAVELTIME_INSTANT, A_TRAVELTIME_ACTUAL = 1, 2, 3, 4
 A_VEH_STATE, A_VEH_ARRIVAL_TS, A_VEH_DEPART_TS, A_VEH_TRAVEL_TIME, A_VEH_DISTANCE = 10, 11, 12, 13, 14
@@ -60,7 +63,8 @@ _EXC = {
 
 #: every symbol include/uxsim_b200.h declares (without prefix); tests check each library exports all of them
 ABI_SYMBOLS = (
-    "create_world", "destroy_world", "add_node", "add_link", "add_demand", "add_vehicles", "set_vehicle_links",
+    "create_world", "destroy_world", "add_node", "add_link", "add_demand", "add_nodes", "add_links", "add_demands",
+    "add_vehicles", "set_vehicle_links", "set_option",
     "batch_enforce_routes_csr", "set_t_max", "set_toll_timeseries", "initialize_adj_matrix", "main_loop",
     "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
     "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
@@ -128,6 +132,10 @@ class CApi:
         self.add_link = fn("add_link", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                                   C.c_double, C.c_double, C.c_double, i32p, C.c_int])
         self.add_demand = fn("add_demand", C.c_int64, [p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i32p, C.c_int])
+        self.add_nodes = fn("add_nodes", C.c_int64, [p, C.c_int64, f64p, f64p, i32p, f64p, f64p, f64p, i32p])
+        self.add_links = fn("add_links", C.c_int64, [p, C.c_int64, i32p, i32p, f64p, f64p, f64p, i32p, f64p, f64p, f64p, i32p, i32p])
+        self.add_demands = fn("add_demands", C.c_int64, [p, C.c_int64, i32p, i32p, f64p, f64p, f64p])
+        self.set_option = fn("set_option", C.c_int, [p, C.c_int, C.c_double])
         self.add_vehicles = fn("add_vehicles", C.c_int64, [p, C.c_int64, i32p, i32p, i32p])
         self.set_vehicle_links = fn("set_vehicle_links", C.c_int, [p, C.c_int64, C.c_int, i32p, C.c_int])
         self.batch_enforce_routes_csr = fn("batch_enforce_routes_csr", C.c_int, [p, i32p, i64p, C.c_int64])
@@ -226,6 +234,29 @@ class EngineWorld:
         g = _as_i32(list(links_preferred))
         return self._check(self.api.add_demand(self.h, int(orig), int(dest), float(start_t), float(end_t), float(flow),
                                                g.ctypes.data_as(C.POINTER(C.c_int32)), len(g)))
+
+    def add_nodes(self, x, y, signal_off, signal, signal_offset, flow_capacity, number_of_lanes) -> int:
+        x, y, sig, so, fc = _as_f64(x), _as_f64(y), _as_f64(signal), _as_f64(signal_offset), _as_f64(flow_capacity)
+        off, nl = _as_i32(signal_off), _as_i32(number_of_lanes)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        return self._check(self.api.add_nodes(self.h, len(x), x.ctypes.data_as(dp), y.ctypes.data_as(dp), off.ctypes.data_as(ip),
+                                              sig.ctypes.data_as(dp), so.ctypes.data_as(dp), fc.ctypes.data_as(dp), nl.ctypes.data_as(ip)))
+
+    def add_links(self, start, end, vmax, kappa, length, lanes, merge_priority, capacity_out, capacity_in, sg_off, sg) -> int:
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        a = [_as_i32(start), _as_i32(end), _as_f64(vmax), _as_f64(kappa), _as_f64(length), _as_i32(lanes), _as_f64(merge_priority),
+             _as_f64(capacity_out), _as_f64(capacity_in), _as_i32(sg_off), _as_i32(sg)]
+        ptrs = [v.ctypes.data_as(ip if v.dtype == np.int32 else dp) for v in a]
+        return self._check(self.api.add_links(self.h, len(a[0]), *ptrs))
+
+    def add_demands(self, orig, dest, t0, t1, flow) -> int:
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        o, d, a, b, f = _as_i32(orig), _as_i32(dest), _as_f64(t0), _as_f64(t1), _as_f64(flow)
+        return self._check(self.api.add_demands(self.h, len(o), o.ctypes.data_as(ip), d.ctypes.data_as(ip), a.ctypes.data_as(dp),
+                                                b.ctypes.data_as(dp), f.ctypes.data_as(dp)))
+
+    def set_option(self, option: int, value: float):
+        self._check(self.api.set_option(self.h, int(option), float(value)))
 
     def add_vehicles(self, orig, dest, depart_ts) -> int:
         o, d, t = _as_i32(orig), _as_i32(dest), _as_i32(depart_ts)

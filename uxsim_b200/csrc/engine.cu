@@ -766,6 +766,17 @@ struct ux_world {
     int *d_l_flags = nullptr, *d_lvl_off = nullptr, *d_lvl_nodes = nullptr, *d_sg_off = nullptr, *d_sg = nullptr, *d_n_sig_off = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     double *d_ens = nullptr;
+    // measurement
+    long long h2d_bytes = 0, d2h_bytes = 0;
+    double last_loop_ms = 0.0;
+    bool ktiming = false;
+    double k_ms[UX_K_COUNT] = {0};
+    long long k_launches[UX_K_COUNT] = {0};
+#ifndef UX_EMU
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> kt_events;  // pairs (start, stop)
+    std::vector<int> kt_ids;
+#endif
 };
 
 static std::string g_err;
@@ -794,7 +805,7 @@ static T *dalloc(ux_world *w, size_t n, bool zero = true) {
 template <typename T>
 static T *dupload(ux_world *w, const std::vector<T> &v) {
     T *p = dalloc<T>(w, v.size(), false);
-    if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (p && !v.empty()) { cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice); w->h2d_bytes += (long long)(v.size() * sizeof(T)); }
     return p;
 }
 
@@ -896,6 +907,29 @@ UX_API int64_t ux_add_demand(ux_world *w, int orig, int dest, double start_t, do
         }
     }
     return made;
+}
+
+// vectorised ingest (include/uxsim_b200.h): add_node / add_link / add_demand applied in index order
+UX_API int64_t ux_add_nodes(ux_world *w, int64_t n, const double *x, const double *y, const int *so, const double *sig, const double *sig_offset,
+                            const double *fc, const int *lanes) {
+    w->nodes.reserve(w->nodes.size() + (size_t)n);
+    for (int64_t i = 0; i < n; i++) { int rc = ux_add_node(w, x[i], y[i], sig + so[i], so[i + 1] - so[i], sig_offset[i], fc[i], lanes[i]); if (rc < 0) return rc; }
+    return n;
+}
+UX_API int64_t ux_add_links(ux_world *w, int64_t n, const int *a, const int *b, const double *vmax, const double *kappa, const double *len, const int *lanes,
+                            const double *mp, const double *co, const double *ci, const int *go, const int *sg) {
+    w->links.reserve(w->links.size() + (size_t)n);
+    for (int64_t i = 0; i < n; i++) { int rc = ux_add_link(w, a[i], b[i], vmax[i], kappa[i], len[i], lanes[i], mp[i], co[i], ci[i], sg + go[i], go[i + 1] - go[i]); if (rc < 0) return rc; }
+    return n;
+}
+UX_API int64_t ux_add_demands(ux_world *w, int64_t n, const int *o, const int *d, const double *t0, const double *t1, const double *flow) {
+    int64_t made = 0;
+    for (int64_t i = 0; i < n; i++) { int64_t m = ux_add_demand(w, o[i], d[i], t0[i], t1[i], flow[i], nullptr, 0); if (m < 0) return m; made += m; }
+    return made;
+}
+UX_API int ux_set_option(ux_world *w, int option, double value) {
+    if (option == UX_OPT_KERNEL_TIMING) { w->ktiming = value != 0.0; return 0; }
+    return fail(w, UX_ERR_INVALID, "unknown option %d", option);
 }
 
 UX_API int64_t ux_add_vehicles(ux_world *w, int64_t n, const int *orig, const int *dest, const int *ts) {
@@ -1170,6 +1204,15 @@ static int upload(ux_world *w) {
     return 0;
 }
 
+#ifdef UX_EMU
+#define KT_BEGIN(kid)
+#define KT_END(kid)
+#else
+#define KT_BEGIN(kid)                                                                    \
+    if (w->ktiming) { cudaEvent_t a_, b_; cudaEventCreate(&a_); cudaEventCreate(&b_);     \
+        w->kt_events.push_back(a_); w->kt_events.push_back(b_); w->kt_ids.push_back(kid); cudaEventRecord(a_, st); }
+#define KT_END(kid) if (w->ktiming) cudaEventRecord(w->kt_events.back(), st);
+#endif
 // enqueue the kernels of `nsteps` timesteps starting at phase (t mod route_ts) = `phase` on the stream
 static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
     int N = (int)w->nodes.size(), R = w->R;
@@ -1177,23 +1220,23 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
     dim3 g_nodes((N * 32 + 127) / 128, R), g_update((w->nseg * 32 + 255) / 256, R);
     long long lc = 0;
     for (int s = 0; s < nsteps; s++) {
-        if (N > 0) { UX_LAUNCH(k_pre, g_nodes, dim3(128), st, w->dworlds, s); lc++; }
-        if (N > 0) for (int lv = 0; lv < w->n_levels; lv++) { UX_LAUNCH(k_transfer, g_nodes, dim3(128), st, w->dworlds, s, lv); lc++; }
-        if (w->nseg > 0) { UX_LAUNCH(k_update, g_update, dim3(256), st, w->dworlds, s); lc++; }
+        if (N > 0) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_pre, g_nodes, dim3(128), st, w->dworlds, s); KT_END(UX_K_PRE) lc++; }
+        if (N > 0) for (int lv = 0; lv < w->n_levels; lv++) { KT_BEGIN(UX_K_TRANSFER) UX_LAUNCH(k_transfer, g_nodes, dim3(128), st, w->dworlds, s, lv); KT_END(UX_K_TRANSFER) lc++; }
+        if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(256), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
         bool route = ((phase + s) % w->route_ts) == 0;
         if (w->n_active > 0 && w->n_edges > 0) {
             if (route) {
-                UX_LAUNCH(k_edge_cost, dim3((w->n_edges + 127) / 128, R), dim3(128), st, w->dworlds, s); lc++;
-                UX_LAUNCH(k_sssp, dim3(w->n_active, R), dim3(256), st, w->dworlds); lc++;
+                KT_BEGIN(UX_K_EDGE_COST) UX_LAUNCH(k_edge_cost, dim3((w->n_edges + 127) / 128, R), dim3(128), st, w->dworlds, s); KT_END(UX_K_EDGE_COST) lc++;
+                KT_BEGIN(UX_K_SSSP) UX_LAUNCH(k_sssp, dim3(w->n_active, R), dim3(256), st, w->dworlds); KT_END(UX_K_SSSP) lc++;
             }
             if (route || w->p.route_choice_update_gradual) {
                 long long tot = (long long)w->n_active * (long long)w->links.size();
-                UX_LAUNCH(k_duo, dim3((unsigned)((tot + 255) / 256), R), dim3(256), st, w->dworlds, w->p.route_choice_update_gradual ? 1 : 0); lc++;
-                UX_LAUNCH(k_duo_finish, dim3((w->n_active + 127) / 128, R), dim3(128), st, w->dworlds); lc++;
+                KT_BEGIN(UX_K_DUO) UX_LAUNCH(k_duo, dim3((unsigned)((tot + 255) / 256), R), dim3(256), st, w->dworlds, w->p.route_choice_update_gradual ? 1 : 0); KT_END(UX_K_DUO) lc++;
+                KT_BEGIN(UX_K_MISC) UX_LAUNCH(k_duo_finish, dim3((w->n_active + 127) / 128, R), dim3(128), st, w->dworlds); KT_END(UX_K_MISC) lc++;
             }
         }
     }
-    UX_LAUNCH(k_advance, dim3(1, R), dim3(32), st, w->dworlds, nsteps); lc++;
+    KT_BEGIN(UX_K_MISC) UX_LAUNCH(k_advance, dim3(1, R), dim3(32), st, w->dworlds, nsteps); KT_END(UX_K_MISC) lc++;
     *launch_count = lc;
 }
 
@@ -1222,6 +1265,10 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
     if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
     if ((long long)w->vehs.size() != w->P_uploaded) return fail(w, UX_ERR_RUNTIME, "adding vehicles after the simulation started is not supported yet by the CUDA engine");
     if (w->net_dirty) { int rc = upload_link_params(w); if (rc) return rc; w->net_dirty = false; }
+#ifndef UX_EMU
+    if (!w->ev_begin) { CUDA_OK(cudaEventCreate(&w->ev_begin)); CUDA_OK(cudaEventCreate(&w->ev_end)); }
+    CUDA_OK(cudaEventRecord(w->ev_begin, w->stream));
+#endif
     int t = start_ts;
     while (t < end_ts) {
         int phase = t % w->route_ts;
@@ -1231,6 +1278,7 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
 #ifdef UX_EMU
         enqueue_steps(w, nsteps, phase, &lc);
 #else
+        if (w->ktiming) { enqueue_steps(w, nsteps, phase, &lc); w->launches += lc; t += nsteps; continue; }
         long long key = ((long long)nsteps << 32) | (unsigned)phase | ((long long)w->n_levels << 48);
         auto it = w->graphs.find(key);
         if (it == w->graphs.end()) {
@@ -1248,8 +1296,20 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
         w->launches += lc;
         t += nsteps;
     }
+#ifndef UX_EMU
+    CUDA_OK(cudaEventRecord(w->ev_end, w->stream));
+#endif
     CUDA_OK(cudaStreamSynchronize(w->stream));
     CUDA_OK(cudaGetLastError());
+#ifndef UX_EMU
+    { float ms = 0.f; cudaEventElapsedTime(&ms, w->ev_begin, w->ev_end); w->last_loop_ms = ms; }
+    for (size_t i = 0; i < w->kt_ids.size(); i++) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, w->kt_events[2 * i], w->kt_events[2 * i + 1]);
+        w->k_ms[w->kt_ids[i]] += ms; w->k_launches[w->kt_ids[i]] += 1;
+        cudaEventDestroy(w->kt_events[2 * i]); cudaEventDestroy(w->kt_events[2 * i + 1]);
+    }
+    w->kt_events.clear(); w->kt_ids.clear();
+#endif
     for (int r = 0; r < w->R; r++) {
         int e[2] = {0, 0};
         CUDA_OK(cudaMemcpy(e, w->hw[r].err, sizeof(e), cudaMemcpyDeviceToHost));
@@ -1351,7 +1411,12 @@ UX_API int64_t ux_get_int(ux_world *w, int what) {
     case UX_I_NUM_ACTIVE_DESTS: return w->n_active;
     case UX_I_TRANSFER_LEVELS: return w->n_levels;
     case UX_I_LINK_EVENTS: return w->uploaded ? dsum_i(w, w->hw[0].ev_cnt, (int)w->links.size()) : 0;
-    default: return fail(w, UX_ERR_INVALID, "unknown int query %d", what);
+    case UX_I_H2D_BYTES: return w->h2d_bytes;
+    case UX_I_D2H_BYTES: return w->d2h_bytes;
+    case UX_I_RING_SLOTS: return w->C;
+    default:
+        if (what >= UX_I_KERNEL_LAUNCHES_OF && what < UX_I_KERNEL_LAUNCHES_OF + UX_K_COUNT) return w->k_launches[what - UX_I_KERNEL_LAUNCHES_OF];
+        return fail(w, UX_ERR_INVALID, "unknown int query %d", what);
     }
 }
 
@@ -1360,7 +1425,10 @@ UX_API double ux_get_double(ux_world *w, int what) {
     case UX_D_DELTA_T: return w->dt;
     case UX_D_TIME: return w->timestep * w->dt;
     case UX_D_T_MAX: return w->p.t_max;
-    default: return NAN;
+    case UX_D_LAST_LOOP_MS: return w->last_loop_ms;
+    default:
+        if (what >= UX_D_KERNEL_MS_OF && what < UX_D_KERNEL_MS_OF + UX_K_COUNT) return w->k_ms[what - UX_D_KERNEL_MS_OF];
+        return NAN;
     }
 }
 
@@ -1462,7 +1530,7 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
     if (n < 0) return n;
     if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
     size_t es = dt == UX_DT_F64 ? 8 : dt == UX_DT_I32 ? 4 : 8;
-    if (dptr) { if (n > 0) CUDA_OK(cudaMemcpy(dst, dptr, es * (size_t)n, cudaMemcpyDeviceToHost)); return n; }
+    if (dptr) { if (n > 0) CUDA_OK(cudaMemcpy(dst, dptr, es * (size_t)n, cudaMemcpyDeviceToHost)); w->d2h_bytes += (long long)(es * (size_t)n); return n; }
     const DevWorld &d = w->hw[replica];
     int N = d.N, L = d.L; long long P = d.P;
     double *o = (double *)dst; int *oi = (int *)dst;

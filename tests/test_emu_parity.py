@@ -1,0 +1,37 @@
+"""CPU-side check of the kernel LOGIC: uxsim_b200/csrc/engine.cu compiled with g++ against tests/emu/cuda_emu.h
+(kernels run as loops over blocks/threads) must be bit-identical to the oracle.  This is a debugging aid for the
+GPU-less container; the GPU parity tests proper are tests/test_gpu_parity.py.  The emulation library is test
+infrastructure and is never loaded by the package."""
+import pytest
+
+from uxsim_b200 import _capi as C
+from uxsim_b200 import scenario as S
+
+from parity import compare_engines, run_pair
+
+CASES = [
+    ("1link", S.straight_1link, None), ("spillback", S.straight_3link_spillback, None), ("signal", S.straight_2link_signal, None),
+    ("lane_drop", S.lane_drop_2to1, None), ("3lane", S.multilane_3lane, None), ("merge", S.merge_y, None),
+    ("dead_end", S.dead_end, None), ("short_chain", S.short_links_chain, None),
+    ("merge_stochastic", lambda: S.merge_y(hard_deterministic_mode=False, random_seed=3), None),
+    ("grid5", lambda: S.grid(n=5, seed=2, tmax=3000, demand_t=1000), None),
+    ("grid5_chunked", lambda: S.grid(n=5, seed=9, tmax=3000, demand_t=1000), [300, 305, 1234, 3000]),
+    ("grid6_signals", lambda: S.grid(n=6, seed=5, tmax=3000, demand_t=1200, signals=True), None),
+    ("siouxfalls", lambda: S.sioux_falls(seed=1), None),
+    ("dta_grid9", lambda: S.dta_grid9(seed=1), None),
+    ("gradual", lambda: S.grid(n=5, seed=4, tmax=3000, demand_t=1000, route_choice_update_gradual=True), None),
+]
+
+
+@pytest.mark.parametrize("name,mk,until", CASES, ids=[c[0] for c in CASES])
+def test_emulated_kernels_match_oracle(name, mk, until, emu_api, oracle_api):
+    Ee, Eo = run_pair(mk(), emu_api, oracle_api, until=until)
+    assert compare_engines(Ee, Eo) == []
+    assert Ee.get_int(C.I_PLATOON_UPDATES) == Eo.get_int(C.I_PLATOON_UPDATES)
+
+
+def test_emulated_chicago_levels(emu_api, oracle_api):
+    """Chicago sketch (deltan=30) needs 4 transfer dependency levels; first 1500 s."""
+    Ee, Eo = run_pair(S.chicago_sketch(seed=0), emu_api, oracle_api, until=[1500])
+    assert Ee.get_int(C.I_TRANSFER_LEVELS) == 4
+    assert compare_engines(Ee, Eo) == []

@@ -44,8 +44,8 @@
 // ---------------------------------------------------------------------------------------------------
 // limits
 // ---------------------------------------------------------------------------------------------------
-#define UX_MAXDEG 32   // max out-/in-degree of a node
-#define UX_MAXC 160    // max transfer candidates / out-link slots of one node (sum of lanes)
+#define UX_MAXDEG 16   // max out-/in-degree of a node
+#define UX_MAXC 64     // max sum of lanes over the in-links (or the out-links) of one node
 #define UX_SEG 32      // ring slots per update-kernel work item (one warp)
 
 enum { LF_SEES_POPS = 1, LF_END_LT_START = 2 };            // link flags
@@ -66,9 +66,10 @@ struct DevWorld {
     const int *l_start, *l_end, *l_lanes, *l_rcap, *l_flags, *l_sg_off, *l_sg, *l_pair_first, *l_pair_off, *l_pair_list;
     const long long *l_roff;
     const double *l_length, *l_vmax, *l_dpl_dn, *l_udt, *l_cap_out, *l_cap_in, *l_mp, *l_penalty, *l_toll;
-    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes;
+    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes, *lvl_level;
+    int n_levels;
     const double *n_sig, *n_fc;
-    const int *v_orig, *v_dest, *v_depart_ts, *gen_off, *gen_list, *dest_row, *row_dest;
+    const int *v_orig, *v_dest, *v_depart_ts, *gen_off, *gen_list, *gen_ts, *dest_row, *row_dest;
     const int *vl_off[3], *vl_list[3];  // per-vehicle CSR: 0 specified_route, 1 links_preferred, 2 links_avoid
     const int *seg_link, *seg_start;
     const int *e_from, *e_to, *e_link;  // node-pair edges (leading link of each pair)
@@ -89,19 +90,54 @@ struct DevWorld {
     int *ev_ord, *sig_log;
     double *pref, *rdist, *pair_cost;
     int *pref_active, *has_path, *rnext;
+    int *lvl_done;  // per dependency level: transfer warps finished in the current step
     int *err;     // [0] code, [1] info
     int *t_base;  // timestep at the start of the running graph
 };
 
 #define UX_DEV __device__ __forceinline__
 
+// The per-replica DevWorld lives in global memory; reading its ~90 pointers through a reference there would make
+// every `W.x[...]` a dependent pointer load that must be repeated after each global store (possible aliasing).
+// Each block therefore copies its replica's struct into shared memory once; shared memory cannot alias global
+// stores, so the pointers stay in registers / LDS and the kernels' dependent-load chains halve.
+#ifdef UX_EMU
+#define LOAD_WORLD(W, worlds) static DevWorld W##_sh; W##_sh = (worlds)[blockIdx.y]; const DevWorld &W = W##_sh;
+#else
+#define LOAD_WORLD(W, worlds)                                                                            \
+    __shared__ DevWorld W##_sh;                                                                          \
+    {                                                                                                    \
+        const int *src_ = reinterpret_cast<const int *>(&(worlds)[blockIdx.y]);                          \
+        int *dst_ = reinterpret_cast<int *>(&W##_sh);                                                    \
+        _Pragma("unroll") for (int k_ = 0; k_ < (int)((sizeof(DevWorld) / 4 + 63) / 64); k_++) {           \
+            int i_ = (int)threadIdx.x + k_ * 64;  /* every block has >= 64 threads; extra threads repeat */ \
+            if (threadIdx.x < 64 && i_ < (int)(sizeof(DevWorld) / 4)) dst_[i_] = src_[i_];                \
+        }                                                                                                \
+    }                                                                                                    \
+    __syncthreads();                                                                                     \
+    const DevWorld &W = W##_sh;
+#endif
+
+// Warp-cooperative kernels are written as phases.  On the GPU WARP_FOR runs its body once with `lane` = the lane
+// id and WARP_SYNC is __syncwarp (execution + shared-memory ordering); in the host emulation build one thread per
+// warp runs every phase as a loop over the 32 lanes, which is equivalent because no phase depends on the order
+// in which its lanes execute.
+#ifdef UX_EMU
+#define WARP_BEGIN if (threadIdx.x & 31) return;
+#define WARP_FOR(lane) for (int lane = 0; lane < 32; lane++)
+#define WARP_SYNC()
+#else
+#define WARP_BEGIN
+#define WARP_FOR(lane) for (int lane = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
+#define WARP_SYNC() __syncwarp()
+#endif
+
 UX_DEV void dev_error(const DevWorld &W, int code, int info) {
     if (atomicCAS(&W.err[0], 0, code) == 0) W.err[1] = info;
 }
 
-UX_DEV int ring_slot(int head, int pos, int cap) {  // physical slot of queue position `pos`
-    unsigned s = ((unsigned)head % (unsigned)cap) + (unsigned)pos;
-    return (int)(s >= (unsigned)cap ? s - (unsigned)cap : s);
+UX_DEV int ring_slot(int head, int pos, int cap) {  // physical slot of queue position `pos` (cap is a power of two)
+    return (int)(((unsigned)head + (unsigned)pos) & (unsigned)(cap - 1));
 }
 
 // random_choice (utils.h:62-87) with a supplied uniform u in [0,1)
@@ -114,6 +150,14 @@ UX_DEV int weighted_pick(const double *wts, int n, double u) {
     return n - 1;
 }
 
+UX_DEV int ld_cg(const int *p) {
+#ifdef UX_EMU
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+
 UX_DEV bool is_inf(double c) { return c > 1.0e300; }
 
 UX_DEV bool list_has(const int *a, int n, int v) {
@@ -122,7 +166,7 @@ UX_DEV bool list_has(const int *a, int n, int v) {
 }
 
 // Vehicle::route_next_link_choice (traffi.cpp:934-1033).  Returns the chosen link id or -1.
-UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned entity, unsigned purpose, unsigned draw) {
+UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned entity, unsigned purpose, unsigned draw, int *deferred_err = nullptr) {
     int o0 = W.n_out_off[node], nset = W.n_out_off[node + 1] - o0;
     if (nset == 0) return -1;
     const int *linkset = W.n_out + o0;
@@ -130,9 +174,9 @@ UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned en
         int r0 = W.vl_off[0][vid], len = W.vl_off[0][vid + 1] - r0;
         if (len > 0) {
             int traveled = W.v_trav[vid];
-            if (traveled >= len) { dev_error(W, DERR_ROUTE_EXHAUSTED, vid); return -1; }
+            if (traveled >= len) { if (deferred_err) *deferred_err = DERR_ROUTE_EXHAUSTED; else dev_error(W, DERR_ROUTE_EXHAUSTED, vid); return -1; }
             int forced = W.vl_list[0][r0 + traveled];
-            if (!list_has(linkset, nset, forced)) { dev_error(W, DERR_ROUTE_INCONSISTENT, vid); return -1; }
+            if (!list_has(linkset, nset, forced)) { if (deferred_err) *deferred_err = DERR_ROUTE_INCONSISTENT; else dev_error(W, DERR_ROUTE_INCONSISTENT, vid); return -1; }
             return forced;
         }
     }
@@ -153,7 +197,7 @@ UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned en
             int m = 0;
             for (int i = 0; i < n; i++) if (!list_has(W.vl_list[2] + r0, len, out[i])) tmp[m++] = out[i];
             if (m != n) { int *s = out; out = tmp; tmp = s; n = m; }
-            if (n == 0) { dev_error(W, DERR_AVOID_ALL, vid); return -1; }
+            if (n == 0) { if (deferred_err) *deferred_err = DERR_AVOID_ALL; else dev_error(W, DERR_AVOID_ALL, vid); return -1; }
         }
     }
     if (W.no_cyclic) {
@@ -262,28 +306,46 @@ UX_DEV double warp_queue_vsum(const DevWorld &W, int l, int hd, int n, int lane)
 // K1: Link::update (traffi.cpp:542-565, 599-622) for the node's out-links, then Node::generate (105-189),
 //     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
 // ---------------------------------------------------------------------------------------------------
+struct PreSmem {
+    int choice[UX_MAXC], g_vid[UX_MAXC], g_err[UX_MAXC];
+    int o_hd[UX_MAXDEG], o_tail[UX_MAXDEG], o_lanes[UX_MAXDEG], o_cap[UX_MAXDEG], o_lastlane[UX_MAXDEG], o_win_off[UX_MAXDEG + 1], o_win_n[UX_MAXDEG];
+    long long o_roff[UX_MAXDEG];
+    double o_ci[UX_MAXDEG], o_dpl[UX_MAXDEG], o_vmax[UX_MAXDEG], o_cumarr[UX_MAXDEG];
+    double w_x[UX_MAXC];
+};
+
 __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_off) {
-    const DevWorld &W = worlds[blockIdx.y];
+    LOAD_WORLD(W, worlds)
+    WARP_BEGIN
+    __shared__ double tt_all[4][UX_MAXDEG];
+    __shared__ PreSmem ps_all[4];
     int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
     if (warp >= W.N) return;
+    double *tt_s = tt_all[(threadIdx.x >> 5) & 3];
     int n = warp, t = *W.t_base + step_off, cur = t & 1, L = W.L;
     int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
-    // ---- link update of out-links
-    for (int k = 0; k < nout; k++) {
-        int l = W.n_out[o0 + k];
-        int hd = W.head[cur * L + l], nq = W.tail[l] - hd;
-        double tt;
-        bool fresh = (t % W.itt) == 0;
-        if (fresh) {
+    bool fresh = (t % W.itt) == 0;
+    // ---- instantaneous travel time of the out-links (whole warp per link, only every `itt` steps)
+    if (fresh) {
+        for (int k = 0; k < nout; k++) {
+            int l = W.n_out[o0 + k];
+            int hd = W.head[cur * L + l], nq = W.tail[l] - hd;
+            double tt;
             if (nq > 0) {
                 double vs = warp_queue_vsum(W, l, hd, nq, lane);
                 double avg = vs / (double)nq;
                 tt = avg > 0.0 ? W.l_length[l] / avg : W.l_length[l] / (W.l_vmax[l] / 100.0);
             } else tt = W.l_length[l] / W.l_vmax[l];
+            if (lane == 0) tt_s[k] = tt;
         }
-        if (lane == 0) {
+        WARP_SYNC();
+    }
+    // ---- scalar link update, one lane per out-link
+    WARP_FOR(ln) {
+        for (int k = ln; k < nout; k += 32) {
+            int l = W.n_out[o0 + k];
             size_t row = (size_t)t * L + l;
-            if (fresh) W.tt_inst[row] = tt;
+            if (fresh) W.tt_inst[row] = tt_s[k];
             else if (t > 0) W.tt_inst[row] = W.tt_inst[row - L];
             if (t != 0) { W.cum_arr[row] = W.cum_arr[row - L]; W.cum_dep[row] = W.cum_dep[row - L]; }
             int lanes = W.l_lanes[l];
@@ -293,36 +355,116 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
             W.pop_k2[l] = 0;
         }
     }
-    if (lane != 0) return;
-    // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841)
-    {
-        int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
-        while (av < glen && W.v_depart_ts[W.gen_list[g0 + av]] <= t - 1) av++;
-        W.gen_avail[n] = av;
-        // ---- generate
-        int gh = W.gen_head[n];
-        if (gh < av && nout > 0) {
-            int total_lanes = W.n_out_lanes[n];
-            for (int i = 0; i < total_lanes; i++) {
-                if (gh >= av) break;
-                int vid = W.gen_list[g0 + gh];
-                int ol = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i);
+    WARP_SYNC();
+#ifndef UX_EMU
+    __threadfence_block();
+#endif
+    // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
+    //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
+    __shared__ int rel_all[4];
+    int *rel = &rel_all[(threadIdx.x >> 5) & 3];
+    int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
+    while (av < glen) {
+        WARP_FOR(ln) if (ln == 0) *rel = 0;
+        WARP_SYNC();
+        WARP_FOR(ln) { int idx = av + ln; if (idx < glen && W.gen_ts[g0 + idx] <= t - 1) atomicAdd(rel, 1); }
+        WARP_SYNC();
+        int c = *rel;
+        WARP_SYNC();
+        av += c;
+        if (c < 32) break;
+    }
+    // ---- generate (traffi.cpp:105-189).  The route draws of the first `natt` waiting platoons and the tail state of the
+    //      out-links are fetched in parallel; lane 0 then walks the attempts on shared memory and stops at the first refusal.
+    PreSmem &G = ps_all[(threadIdx.x >> 5) & 3];
+    int gh = W.gen_head[n];
+    int natt = av - gh;
+    { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > UX_MAXC) natt = UX_MAXC; }
+    if (nout == 0) natt = 0;
+    if (natt > 0) {
+        WARP_FOR(ln) {
+            for (int i = ln; i < natt; i += 32) {
+                int vid = W.gen_list[g0 + gh + i], e = 0;
+                G.g_vid[i] = vid;
+                G.choice[i] = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
+                G.g_err[i] = e;
+            }
+            for (int q = ln; q < nout; q += 32) {
+                int ol = W.n_out[o0 + q];
+                int hd = W.head[cur * L + ol], tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+                long long o = W.l_roff[ol];
+                double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[(size_t)t * L + ol];
+                int sz = tl - hd;
+                int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
+                G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
+                G.o_ci[q] = ci_; G.o_dpl[q] = dpl_; G.o_vmax[q] = vm_; G.o_cumarr[q] = ca_; G.o_lastlane[q] = ll_;
+                G.o_win_n[q] = sz < lanes ? sz : lanes;
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(ln) if (ln == 0) { int acc = 0; for (int q = 0; q < nout; q++) { G.o_win_off[q] = acc; acc += G.o_lanes[q]; } G.o_win_off[nout] = acc; }
+        WARP_SYNC();
+        WARP_FOR(ln) {
+            int tot = G.o_win_off[nout];
+            for (int e = ln; e < tot && e < UX_MAXC; e += 32) {
+                int q = 0;
+                while (G.o_win_off[q + 1] <= e) q++;
+                int k = e - G.o_win_off[q];
+                if (k < G.o_win_n[q]) {
+                    int sz = G.o_tail[q] - G.o_hd[q];
+                    G.w_x[e] = W.X[(size_t)cur * W.C + G.o_roff[q] + ring_slot(G.o_hd[q], sz - G.o_win_n[q] + k, G.o_cap[q])];
+                }
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(ln) if (ln == 0) {
+            for (int i = 0; i < natt; i++) {
+                int vid = G.g_vid[i], ol = G.choice[i];
+                if (G.g_err[i]) { dev_error(W, G.g_err[i], vid); break; }
                 W.v_next[vid] = ol;
                 if (ol < 0) break;
-                int hd = W.head[cur * L + ol];
-                if (!can_accept(W, ol, hd, cur)) break;
+                int q = 0;
+                while (q < nout && W.n_out[o0 + q] != ol) q++;
+                int lanes = G.o_lanes[q], sz = G.o_tail[q] - G.o_hd[q], w0 = G.o_win_off[q];
+                bool ok = false;  // traffi.cpp:130-142
+                if (sz < lanes) ok = true;
+                else if (G.w_x[w0] > G.o_dpl[q]) ok = true;
+                if (G.o_ci[q] < W.dn) ok = false;
+                if (!ok) break;
+                if (sz >= G.o_cap[q]) { dev_error(W, DERR_RING_FULL, ol); break; }
                 gh++;
-                if (ring_push(W, ol, hd, cur, 0.0, 0.0, W.l_vmax[ol], vid) < 0) break;
+                int lane_new = sz > 0 ? (G.o_lastlane[q] + 1) % lanes : 0;
+                int slot = ring_slot(G.o_tail[q], 0, G.o_cap[q]);
+                long long o = G.o_roff[q];
+                W.X[(size_t)cur * W.C + o + slot] = 0.0;
+                W.X[(size_t)(cur ^ 1) * W.C + o + slot] = 0.0;
+                W.V[o + slot] = G.o_vmax[q];
+                W.VID[o + slot] = vid;
+                W.LANE[o + slot] = lane_new;
+                G.o_tail[q] += 1; G.o_lastlane[q] = lane_new;
+                if (G.o_win_n[q] < lanes) { G.w_x[w0 + G.o_win_n[q]] = 0.0; G.o_win_n[q] += 1; }
+                else { for (int e = w0; e < w0 + lanes - 1; e++) G.w_x[e] = G.w_x[e + 1]; G.w_x[w0 + lanes - 1] = 0.0; }
                 W.v_state[vid] = UX_VS_RUN;
                 W.v_atl[vid] = (double)t * W.dt;
                 W.v_entry_x[vid] = 0.0;
                 mark_entered(W, vid, ol);
-                W.cum_arr[(size_t)t * L + ol] += W.dn;
-                W.cap_in_rem[ol] -= W.dn;
+                G.o_cumarr[q] += W.dn;
+                G.o_ci[q] -= W.dn;
             }
             W.gen_head[n] = gh;
         }
+        WARP_SYNC();
+        WARP_FOR(ln) {
+            for (int q = ln; q < nout; q += 32) {
+                int ol = W.n_out[o0 + q];
+                W.cap_in_rem[ol] = G.o_ci[q]; W.cum_arr[(size_t)t * L + ol] = G.o_cumarr[q]; W.tail[ol] = G.o_tail[q];
+            }
+        }
+        WARP_SYNC();
     }
+    if (lane != 0) return;
+    if (n == 0) for (int lv = 0; lv < W.n_levels; lv++) W.lvl_done[lv] = 0;
+    W.gen_avail[n] = av;
     for (int k = 0; k < nout; k++) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; }
     // ---- signal
     int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
@@ -342,213 +484,527 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
 
 // ---------------------------------------------------------------------------------------------------
 // K2: Node::transfer (traffi.cpp:239-445).  One warp per node of dependency level `level`.
+//
+// The reference algorithm is inherently serial inside a node (slots are tried one after another and every move
+// changes the queues the next slot sees), but everything it READS can be known up front.  So the warp first
+// gathers the node's whole neighbourhood into shared memory in parallel (in-link heads, the candidate platoons at
+// those heads, and for every requested out-link its tail state plus the window of its last `lanes` platoons),
+// lane 0 then runs the serial slot loop purely on shared memory (global stores only, no dependent global loads),
+// and the lanes write the per-link accumulators back in parallel.  A dependent chain of a few hundred global
+// loads becomes five.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_transfer(const DevWorld *worlds, int step_off, int level) {
-    const DevWorld &W = worlds[blockIdx.y];
-    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
-    int lo = W.lvl_off[level], cnt = W.lvl_off[level + 1] - lo;
-    if (warp >= cnt || lane != 0) return;
-    int n = W.lvl_nodes[lo + warp], t = *W.t_base + step_off, cur = t & 1, L = W.L;
+struct XferSmem {
+    // in-links
+    int il[UX_MAXDEG], hd[UX_MAXDEG], hc[UX_MAXDEG], cap[UX_MAXDEG], popped[UX_MAXDEG], pos_off[UX_MAXDEG + 1], evc[UX_MAXDEG], trips[UX_MAXDEG];
+    long long roff[UX_MAXDEG];
+    double co_rem[UX_MAXDEG], mp[UX_MAXDEG], vmax[UX_MAXDEG], cumdep[UX_MAXDEG];
+    unsigned char sig_ok[UX_MAXDEG];
+    // head positions of the in-links
+    int p_vid[UX_MAXC], p_next[UX_MAXC], p_dts[UX_MAXC];
+    short p_in[UX_MAXC], p_j[UX_MAXC], c_idx[UX_MAXC], expd[UX_MAXC];
+    unsigned char p_flag[UX_MAXC];
+    double p_x[UX_MAXC], p_xold[UX_MAXC], p_v[UX_MAXC], p_mr[UX_MAXC], p_atl[UX_MAXC], p_ex[UX_MAXC], p_dist[UX_MAXC];
+    int nc, npos, nol, any_wait, nexp, first, cur_slot, n_picks;
+    int omask[UX_MAXDEG][2];          // per requested out-link: candidates currently eligible to move onto it
+    unsigned char ogood[UX_MAXDEG];   // per requested out-link: acceptance test result
+    unsigned char c_first[UX_MAXC], c_q[UX_MAXC];
+    double fc_rem;
+    short shuf_j[UX_MAXC];
+    double u_merge[UX_MAXC];
+    // requested out-links
+    int ol[UX_MAXDEG], o_hd[UX_MAXDEG], o_tail[UX_MAXDEG], o_lanes[UX_MAXDEG], o_cap[UX_MAXDEG], o_lastlane[UX_MAXDEG], o_win_off[UX_MAXDEG + 1], o_win_n[UX_MAXDEG];
+    long long o_roff[UX_MAXDEG];
+    double o_ci[UX_MAXDEG], o_dpl[UX_MAXDEG], o_len[UX_MAXDEG], o_vmax[UX_MAXDEG], o_cumarr[UX_MAXDEG];
+    double w_x[UX_MAXC], w_xold[UX_MAXC];  // window of the last `lanes` platoons of each out-link (oldest first)
+};
+
+UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem &S, int p, int t) {  // Vehicle::end_trip traffi.cpp:886-927
+    int ii = S.p_in[p], il = S.il[ii], vid = S.p_vid[p];
+    S.trips[ii] += 1;
+    S.cumdep[ii] += W.dn;
+    double atl = S.p_atl[p];
+    {   // record_tt_event
+        int s = (int)(atl / W.dt);
+        if (s < 0) s = 0;
+        if (s >= W.T) s = W.T - 1;
+        int ord = ++S.evc[ii];
+        W.ev_ord[(size_t)s * W.L + il] = ord;
+        W.ev_tt[(size_t)s * W.L + il] = ((double)t + 1.0) * W.dt - atl;
+    }
+    W.v_atl[vid] = (double)t * W.dt;
+    W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
+    W.v_link[vid] = -1;
+    if (S.p_flag[p] & VF_ABORT) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+    else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)S.p_dts[p] * W.dt; }
+    W.v_flags[vid] = 0;
+    S.popped[ii] += 1;
+}
+
+#define XFER_WARPS 4
+UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
+    int cur = t & 1, L = W.L;
     size_t C = (size_t)W.C;
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     if (nin == 0) return;
-    int popped[UX_MAXDEG];
-    int c_vid[UX_MAXC], c_next[UX_MAXC];
-    short c_in[UX_MAXC], c_pos[UX_MAXC];
-    int nc = 0;
-    bool any_wait = false;
-    for (int ii = 0; ii < nin; ii++) {
-        int il = W.n_in[i0 + ii], hd = W.head[cur * L + il], hc = W.hcount[il], cap = W.l_rcap[il];
-        popped[ii] = 0;
-        for (int j = 0; j < hc; j++) {
-            int vid = W.VID[W.l_roff[il] + ring_slot(hd, j, cap)];
-            unsigned char f = W.v_flags[vid];
-            if (f & VF_WAIT_END) any_wait = true;
-            if ((f & VF_CAND) && nc < UX_MAXC) {  // insertion sort by vehicle id (traffi.cpp:250-253)
-                int k = nc++;
-                while (k > 0 && c_vid[k - 1] > vid) { c_vid[k] = c_vid[k - 1]; c_next[k] = c_next[k - 1]; c_in[k] = c_in[k - 1]; c_pos[k] = c_pos[k - 1]; k--; }
-                c_vid[k] = vid; c_next[k] = W.v_next[vid]; c_in[k] = (short)ii; c_pos[k] = (short)j;
-            }
-        }
-    }
-    if (nc == 0 && !any_wait) return;
-    // out-link slots: each requested out-link repeated `lanes` times (traffi.cpp:260-273)
-    int expd[UX_MAXC], nexp = 0;
-    for (int k = 0; k < nc; k++) {
-        int nl = c_next[k];
-        if (nl < 0) continue;
-        bool seen = false;
-        for (int q = 0; q < k; q++) if (c_next[q] == nl) { seen = true; break; }
-        if (seen) continue;
-        int ln = W.l_lanes[nl];
-        for (int q = 0; q < ln && nexp < UX_MAXC; q++) expd[nexp++] = nl;
-    }
-    unsigned draw = 0;
-    if (!W.hard_det) {  // Fisher-Yates (traffi.cpp:276-282)
-        for (int i = nexp - 1; i > 0; i--) {
-            int j = ux_rng_below(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, draw++, i + 1);
-            int tmp = expd[i]; expd[i] = expd[j]; expd[j] = tmp;
-        }
-    }
     int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = W.sig_phase[n];
-    double fc = W.n_fc[n];
-    for (int s = 0; s < nexp; s++) {
-        int ol = expd[s];
-        int hd_ol = W.head[cur * L + ol] + ((W.l_flags[ol] & LF_SEES_POPS) ? W.pop_k2[ol] : 0);
-        bool ok = can_accept(W, ol, hd_ol, cur);
-        if (W.fc_rem[n] < W.dn) ok = false;
-        if (!ok) continue;
-        int mv[UX_MAXC]; double mp[UX_MAXC]; int nm = 0;
-        for (int k = 0; k < nc; k++) {
-            if (c_vid[k] < 0 || c_next[k] != ol) continue;
-            int ii = c_in[k], il = W.n_in[i0 + ii];
-            if (c_pos[k] != popped[ii]) continue;             // must be the front of its in-link
-            if (W.cap_out_rem[il] < W.dn) continue;
-            if (nsig > 1) {                                   // signal (traffi.cpp:314)
-                int g0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - g0;
-                if (!list_has(W.l_sg + g0, gl, phase)) continue;
+    // ---- A1: in-link state
+    WARP_FOR(lane) {
+        for (int ii = lane; ii < nin; ii += 32) {
+            // loads first, shared stores afterwards: the pointers are generic, so a shared store between two loads
+            // would serialise them (the compiler must assume the load may target shared memory)
+            int il = W.n_in[i0 + ii];
+            int hd_ = W.head[cur * L + il], hc_ = W.hcount[il], cap_ = W.l_rcap[il], evc_ = W.ev_cnt[il], trips_ = W.trips[il];
+            long long roff_ = W.l_roff[il];
+            double co_ = W.cap_out_rem[il], mp_ = W.l_mp[il], vm_ = W.l_vmax[il], cd_ = W.cum_dep[(size_t)t * L + il];
+            bool ok = true;
+            if (nsig > 1) { int g0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - g0; ok = list_has(W.l_sg + g0, gl, phase); }
+            S.il[ii] = il; S.hd[ii] = hd_; S.hc[ii] = hc_; S.cap[ii] = cap_; S.roff[ii] = roff_;
+            S.popped[ii] = 0; S.evc[ii] = evc_; S.trips[ii] = trips_;
+            S.co_rem[ii] = co_; S.mp[ii] = mp_; S.vmax[ii] = vm_; S.cumdep[ii] = cd_;
+            S.sig_ok[ii] = ok ? 1 : 0;
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        int acc = 0;
+        for (int ii = 0; ii < nin; ii++) { S.pos_off[ii] = acc; acc += S.hc[ii]; }
+        S.pos_off[nin] = acc; S.npos = acc < UX_MAXC ? acc : UX_MAXC;
+    }
+    WARP_SYNC();
+    int npos = S.npos;
+    if (npos == 0) return;
+    // ---- A2: the platoons at the in-link heads
+    WARP_FOR(lane) {
+        for (int p = lane; p < npos; p += 32) {
+            int ii = 0;
+            while (S.pos_off[ii + 1] <= p) ii++;
+            int j = p - S.pos_off[ii];
+            long long o = S.roff[ii];
+            int slot = ring_slot(S.hd[ii], j, S.cap[ii]);
+            int vid = W.VID[o + slot];
+            unsigned char f = W.v_flags[vid];
+            int nx = W.v_next[vid];
+            double x_ = 0, xo_ = 0, v_ = 0, mr_ = 0, atl_ = 0, ex_ = 0, di_ = 0; int dts_ = 0;
+            if (f & (VF_CAND | VF_WAIT_END)) {
+                x_ = W.X[(size_t)cur * C + o + slot]; xo_ = W.X[(size_t)(cur ^ 1) * C + o + slot]; v_ = W.V[o + slot];
+                mr_ = W.v_mr[vid]; atl_ = W.v_atl[vid]; ex_ = W.v_entry_x[vid]; di_ = W.v_dist[vid]; dts_ = W.v_depart_ts[vid];
             }
-            mv[nm] = k; mp[nm] = W.l_mp[il]; nm++;
+            S.p_vid[p] = vid; S.p_in[p] = (short)ii; S.p_j[p] = (short)j; S.p_flag[p] = f; S.p_next[p] = nx;
+            S.p_x[p] = x_; S.p_xold[p] = xo_; S.p_v[p] = v_; S.p_mr[p] = mr_; S.p_atl[p] = atl_; S.p_ex[p] = ex_; S.p_dist[p] = di_; S.p_dts[p] = dts_;
         }
-        if (nm == 0) continue;
-        int pick;
-        if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
-        else pick = weighted_pick(mp, nm, ux_rng_uniform(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, draw++));
-        int k = mv[pick], vid = c_vid[k], ii = c_in[k], il = W.n_in[i0 + ii];
-        int hd_il = W.head[cur * L + il], cap_il = W.l_rcap[il];
-        long long o_il = W.l_roff[il];
-        int islot = ring_slot(hd_il, c_pos[k], cap_il);
-        double x_il = W.X[(size_t)cur * C + o_il + islot], xold_il = W.X[(size_t)(cur ^ 1) * C + o_il + islot], v_il = W.V[o_il + islot];
-        W.cap_out_rem[il] -= W.dn; W.cap_in_rem[ol] -= W.dn;
-        if (fc >= 0.0) W.fc_rem[n] -= W.dn;
-        W.cum_dep[(size_t)t * L + il] += W.dn; W.cum_arr[(size_t)t * L + ol] += W.dn;
-        double atl = W.v_atl[vid];
-        record_tt_event(W, il, atl, (double)t * W.dt - atl);
-        W.v_atl[vid] = (double)t * W.dt;
-        W.v_dist[vid] += x_il - W.v_entry_x[vid];
-        popped[ii] += 1;
-        W.pop_k2[il] = popped[ii];
-        mark_entered(W, vid, ol);
-        W.v_flags[vid] = 0;
-        // carry the residual move onto the new link (traffi.cpp:400-419)
-        int sz = W.tail[ol] - hd_ol, lanes_ol = W.l_lanes[ol];
-        double x_next = W.v_mr[vid] * W.l_vmax[ol] / W.l_vmax[il];
-        if (sz >= lanes_ol) {
-            int lslot = ring_slot(hd_ol, sz - lanes_ol, W.l_rcap[ol]);
-            double x_cong = W.X[(size_t)(cur ^ 1) * C + W.l_roff[ol] + lslot] - W.l_dpl_dn[ol];
-            if (x_cong < 0.0) x_cong = 0.0;
-            if (x_next > x_cong) x_next = x_cong;
-        }
-        if (x_next >= W.l_length[ol]) x_next = W.l_length[ol];
-        if (x_next < 0.0) x_next = 0.0;
-        ring_push(W, ol, hd_ol, cur, x_next, xold_il, v_il + x_next / W.dt, vid);
-        W.v_entry_x[vid] = x_next;
-        W.v_mr[vid] = 0.0;
-        c_vid[k] = -1;  // remove from incoming
-        // the new front of the in-link may be waiting for its trip end (traffi.cpp:421-424)
-        if (popped[ii] < W.hcount[il]) {
-            int fslot = ring_slot(hd_il, popped[ii], cap_il);
-            int fv = W.VID[o_il + fslot];
-            if (W.v_flags[fv] & VF_WAIT_END) {
-                end_trip(W, fv, il, t, W.X[(size_t)cur * C + o_il + fslot]);
-                popped[ii] += 1; W.pop_k2[il] = popped[ii];
+    }
+    WARP_SYNC();
+    // ---- A3: candidates sorted by vehicle id (traffi.cpp:250-253; rank sort, one lane per head position) and the
+    //          distinct requested out-links in order of first appearance (traffi.cpp:260-273)
+    WARP_FOR(lane) if (lane == 0) { S.nc = 0; S.any_wait = 0; }
+    WARP_SYNC();
+    WARP_FOR(lane) {
+        for (int p = lane; p < npos; p += 32) {
+            unsigned char f = S.p_flag[p];
+            if (f & VF_WAIT_END) atomicOr(&S.any_wait, 1);
+            if (f & VF_CAND) {
+                int vid = S.p_vid[p], rank = 0;
+                for (int q = 0; q < npos; q++) if ((S.p_flag[q] & VF_CAND) && S.p_vid[q] < vid) rank++;
+                S.c_idx[rank] = (short)p;
+                atomicAdd(&S.nc, 1);
             }
         }
     }
-    // flush trip-end-waiting fronts (traffi.cpp:432-441)
-    for (int ii = 0; ii < nin; ii++) {
-        int il = W.n_in[i0 + ii], hd_il = W.head[cur * L + il], cap_il = W.l_rcap[il], hc = W.hcount[il], lanes = W.l_lanes[il];
-        long long o_il = W.l_roff[il];
-        for (int q = 0; q < lanes; q++) {
-            if (popped[ii] >= hc) break;
-            int fslot = ring_slot(hd_il, popped[ii], cap_il);
-            int fv = W.VID[o_il + fslot];
-            if (!(W.v_flags[fv] & VF_WAIT_END)) break;
-            end_trip(W, fv, il, t, W.X[(size_t)cur * C + o_il + fslot]);
-            popped[ii] += 1; W.pop_k2[il] = popped[ii];
+    WARP_SYNC();
+    WARP_FOR(lane) {
+        int ncl = S.nc;
+        for (int k = lane; k < ncl; k += 32) {
+            int nl = S.p_next[S.c_idx[k]];
+            bool first = nl >= 0;
+            for (int q = 0; q < k && first; q++) if (S.p_next[S.c_idx[q]] == nl) first = false;
+            S.c_first[k] = first ? 1 : 0;
         }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        int nol = 0;
+        for (int k = 0; k < S.nc; k++) if (S.c_first[k] && nol < UX_MAXDEG) S.ol[nol++] = S.p_next[S.c_idx[k]];
+        S.nol = nol;
+    }
+    WARP_SYNC();
+    int nc = S.nc, nol = S.nol;
+    if (nc == 0 && !S.any_wait) return;
+    WARP_FOR(lane) {
+        for (int k = lane; k < nc; k += 32) {
+            int nl = S.p_next[S.c_idx[k]], q = 255;
+            for (int r = 0; r < nol; r++) if (S.ol[r] == nl) { q = r; break; }
+            S.c_q[k] = (unsigned char)q;
+        }
+    }
+    // ---- A4: out-link tail state
+    WARP_FOR(lane) {
+        for (int q = lane; q < nol; q += 32) {
+            int ol = S.ol[q];
+            int hd = W.head[cur * L + ol], fl_ = W.l_flags[ol], pk_ = ld_cg(W.pop_k2 + ol);  // written by a lower level in this launch
+            int tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+            long long o = W.l_roff[ol];
+            double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[(size_t)t * L + ol];
+            if (fl_ & LF_SEES_POPS) hd += pk_;
+            int sz = tl - hd;
+            int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
+            S.o_hd[q] = hd; S.o_tail[q] = tl; S.o_lanes[q] = lanes; S.o_cap[q] = cap; S.o_roff[q] = o;
+            S.o_ci[q] = ci_; S.o_dpl[q] = dpl_; S.o_len[q] = len_; S.o_vmax[q] = vm_; S.o_cumarr[q] = ca_;
+            S.o_lastlane[q] = ll_;
+            S.o_win_n[q] = sz < lanes ? sz : lanes;
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        int acc = 0;
+        for (int q = 0; q < nol; q++) { S.o_win_off[q] = acc; acc += S.o_lanes[q]; }
+        S.o_win_off[nol] = acc;
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) {
+        int tot = S.o_win_off[nol];
+        for (int e = lane; e < tot && e < UX_MAXC; e += 32) {
+            int q = 0;
+            while (S.o_win_off[q + 1] <= e) q++;
+            int k = e - S.o_win_off[q];
+            if (k < S.o_win_n[q]) {
+                int sz = S.o_tail[q] - S.o_hd[q];
+                int slot = ring_slot(S.o_hd[q], sz - S.o_win_n[q] + k, S.o_cap[q]);
+                S.w_x[e] = W.X[(size_t)cur * C + S.o_roff[q] + slot];
+                S.w_xold[e] = W.X[(size_t)(cur ^ 1) * C + S.o_roff[q] + slot];
+            }
+        }
+    }
+    WARP_SYNC();
+    // ---- B: the slot loop.  Slots are inherently sequential (each move changes what the next slot sees), but inside
+    //          a slot the eligibility scan over the candidates runs one lane per candidate, and all random numbers of
+    //          the node (shuffle indices, merge-lottery uniforms) are drawn up front in parallel: Philox is stateless.
+    WARP_FOR(lane) if (lane == 0) {
+        int nexp = 0;
+        for (int q = 0; q < nol; q++) for (int r = 0; r < S.o_lanes[q] && nexp < UX_MAXC; r++) S.expd[nexp++] = (short)q;
+        S.nexp = nexp;
+    }
+    WARP_SYNC();
+    int nexp = S.nexp;
+    int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
+    if (!W.hard_det) {
+        WARP_FOR(lane) {
+            for (int i = 1 + lane; i < nexp; i += 32)  // Fisher-Yates step i uses draw number (nexp-1-i) (traffi.cpp:276-282)
+                S.shuf_j[i] = (short)ux_rng_below(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nexp - 1 - i), i + 1);
+            for (int d = lane; d < nexp; d += 32)
+                S.u_merge[d] = ux_rng_uniform(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + d));
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) {
+            for (int i = nexp - 1; i > 0; i--) { int j = S.shuf_j[i]; short tmp = S.expd[i]; S.expd[i] = S.expd[j]; S.expd[j] = tmp; }
+        }
+        WARP_SYNC();
+    }
+    // Rounds instead of slots: a slot whose out-link cannot accept or has no eligible candidate changes nothing (and
+    // draws nothing), so each round evaluates every out-link / candidate in parallel against the current state, jumps
+    // to the first slot (in shuffled order) that moves a platoon, applies that one move on lane 0, and repeats.
+    double fc = W.n_fc[n];
+    WARP_FOR(lane) if (lane == 0) { S.cur_slot = 0; S.n_picks = 0; S.fc_rem = W.fc_rem[n]; }
+    WARP_SYNC();
+    while (true) {
+        WARP_FOR(lane) {
+            if (lane == 0) S.first = 0x7fffffff;
+            for (int q = lane; q < nol; q += 32) {
+                S.omask[q][0] = 0; S.omask[q][1] = 0;
+                int lanes_ol = S.o_lanes[q], sz = S.o_tail[q] - S.o_hd[q];
+                bool ok = false;  // acceptance (traffi.cpp:285-300)
+                if (sz < lanes_ol) ok = true;
+                else if (S.w_x[S.o_win_off[q]] > S.o_dpl[q]) ok = true;
+                if (S.o_ci[q] < W.dn) ok = false;
+                if (S.fc_rem < W.dn) ok = false;
+                S.ogood[q] = ok ? 1 : 0;
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) {
+            for (int k = lane; k < nc; k += 32) {
+                int p = S.c_idx[k], q = S.c_q[k];
+                if (p < 0 || q == 255) continue;
+                int ii = S.p_in[p];
+                if (S.p_j[p] != S.popped[ii]) continue;  // front of its in-link
+                if (S.co_rem[ii] < W.dn) continue;
+                if (!S.sig_ok[ii]) continue;
+                atomicOr(&S.omask[q][k >> 5], (int)(1u << (k & 31)));
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) {
+            for (int s = S.cur_slot + lane; s < nexp; s += 32) {
+                int q = S.expd[s];
+                if (S.ogood[q] && (S.omask[q][0] | S.omask[q][1])) { atomicMin(&S.first, s); break; }
+            }
+        }
+        WARP_SYNC();
+        int s = S.first;
+        if (s == 0x7fffffff) break;
+        WARP_FOR(lane) if (lane == 0) {
+            int q = S.expd[s], ol = S.ol[q];
+            unsigned m0 = (unsigned)S.omask[q][0], m1 = (unsigned)S.omask[q][1];
+            int lanes_ol = S.o_lanes[q];
+            int sz = S.o_tail[q] - S.o_hd[q], w0 = S.o_win_off[q];
+            double fc_rem = S.fc_rem;
+            int n_picks = S.n_picks;
+            short mv[UX_MAXC]; double mp[UX_MAXC]; int nm = 0;
+            for (int wd = 0; wd < 2; wd++) {  // eligible candidates in ascending vehicle id
+                unsigned m = wd ? m1 : m0;
+                while (m) {
+                    int bit = 0; while (!((m >> bit) & 1u)) bit++;
+                    m &= m - 1;
+                    int k = wd * 32 + bit;
+                    mv[nm] = (short)k; mp[nm] = S.mp[S.p_in[S.c_idx[k]]]; nm++;
+                }
+            }
+            int pick;
+            if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
+            else pick = weighted_pick(mp, nm, S.u_merge[n_picks++]);
+            int k = mv[pick], p = S.c_idx[k], vid = S.p_vid[p], ii = S.p_in[p], il = S.il[ii];
+            S.co_rem[ii] -= W.dn; S.o_ci[q] -= W.dn;
+            if (fc >= 0.0) fc_rem -= W.dn;
+            S.cumdep[ii] += W.dn; S.o_cumarr[q] += W.dn;
+            double atl = S.p_atl[p];
+            {   // record_tt_event (traffi.cpp:357-362)
+                int es = (int)(atl / W.dt);
+                if (es < 0) es = 0;
+                if (es >= W.T) es = W.T - 1;
+                int ord = ++S.evc[ii];
+                W.ev_ord[(size_t)es * L + il] = ord;
+                W.ev_tt[(size_t)es * L + il] = (double)t * W.dt - atl;
+            }
+            W.v_atl[vid] = (double)t * W.dt;
+            W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
+            S.popped[ii] += 1;
+            if (W.no_cyclic) { int sn = W.l_start[ol]; W.v_visited[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
+            W.v_trav[vid] += 1;
+            W.v_link[vid] = ol;
+            W.v_flags[vid] = 0;
+            // carry the residual move onto the new link (traffi.cpp:400-419)
+            double x_next = S.p_mr[p] * S.o_vmax[q] / S.vmax[ii];
+            if (sz >= lanes_ol) {
+                double x_cong = S.w_xold[w0] - S.o_dpl[q];
+                if (x_cong < 0.0) x_cong = 0.0;
+                if (x_next > x_cong) x_next = x_cong;
+            }
+            if (x_next >= S.o_len[q]) x_next = S.o_len[q];
+            if (x_next < 0.0) x_next = 0.0;
+            if (sz >= S.o_cap[q]) dev_error(W, DERR_RING_FULL, ol);
+            else {  // push (lane rule traffi.cpp:385-390)
+                int lane_new = sz > 0 ? (S.o_lastlane[q] + 1) % lanes_ol : 0;
+                int slot = ring_slot(S.o_tail[q], 0, S.o_cap[q]);
+                long long o = S.o_roff[q];
+                W.X[(size_t)cur * C + o + slot] = x_next;
+                W.X[(size_t)(cur ^ 1) * C + o + slot] = S.p_xold[p];
+                W.V[o + slot] = S.p_v[p] + x_next / W.dt;
+                W.VID[o + slot] = vid;
+                W.LANE[o + slot] = lane_new;
+                S.o_tail[q] += 1; S.o_lastlane[q] = lane_new;
+                if (S.o_win_n[q] < lanes_ol) { int e = w0 + S.o_win_n[q]; S.w_x[e] = x_next; S.w_xold[e] = S.p_xold[p]; S.o_win_n[q] += 1; }
+                else {
+                    for (int e = w0; e < w0 + lanes_ol - 1; e++) { S.w_x[e] = S.w_x[e + 1]; S.w_xold[e] = S.w_xold[e + 1]; }
+                    S.w_x[w0 + lanes_ol - 1] = x_next; S.w_xold[w0 + lanes_ol - 1] = S.p_xold[p];
+                }
+            }
+            W.v_entry_x[vid] = x_next;
+            W.v_mr[vid] = 0.0;
+            S.c_idx[k] = -1;  // remove from incoming
+            // the new front of the in-link may be waiting for its trip end (traffi.cpp:421-424)
+            if (S.popped[ii] < S.hc[ii]) {
+                int fp = S.pos_off[ii] + S.popped[ii];
+                if (fp < npos && (S.p_flag[fp] & VF_WAIT_END)) xfer_end_trip(W, S, fp, t);
+            }
+            S.fc_rem = fc_rem; S.n_picks = n_picks; S.cur_slot = s + 1;
+        }
+        WARP_SYNC();
+    }
+    WARP_FOR(lane) if (lane == 0) {
+        // flush trip-end-waiting fronts (traffi.cpp:432-441)
+        for (int ii = 0; ii < nin; ii++) {
+            int lanes = S.hc[ii];  // hcount = min(lanes, queue length): positions beyond it cannot be waiting
+            for (int r = 0; r < lanes; r++) {
+                if (S.popped[ii] >= S.hc[ii]) break;
+                int fp = S.pos_off[ii] + S.popped[ii];
+                if (fp >= npos || !(S.p_flag[fp] & VF_WAIT_END)) break;
+                xfer_end_trip(W, S, fp, t);
+            }
+        }
+        W.fc_rem[n] = S.fc_rem;
+    }
+    WARP_SYNC();
+    // ---- C: write the per-link accumulators back
+    WARP_FOR(lane) {
+        for (int ii = lane; ii < nin; ii += 32) {
+            int il = S.il[ii];
+            W.cap_out_rem[il] = S.co_rem[ii]; W.cum_dep[(size_t)t * L + il] = S.cumdep[ii];
+            W.pop_k2[il] = S.popped[ii]; W.ev_cnt[il] = S.evc[ii]; W.trips[il] = S.trips[ii];
+        }
+        for (int q = lane; q < nol; q += 32) {
+            int ol = S.ol[q];
+            W.cap_in_rem[ol] = S.o_ci[q]; W.cum_arr[(size_t)t * L + ol] = S.o_cumarr[q]; W.tail[ol] = S.o_tail[q];
+        }
+    }
+}
+
+// All dependency levels run in ONE launch: warps are ordered by (level, node id), and a warp of level k > 0 waits
+// until every warp of level k-1 has finished this step (they are dispatched earlier -- the same forward-progress
+// assumption as decoupled look-back scans).  Levels exist only for links short enough that the serial id-ordered
+// visibility of Node.transfer matters (DESIGN.md "transfer order"); most networks have a single level and never wait.
+__global__ void __launch_bounds__(32 * XFER_WARPS) k_transfer(const DevWorld *worlds, int step_off) {
+    LOAD_WORLD(W, worlds)
+    WARP_BEGIN
+    __shared__ XferSmem sm_all[XFER_WARPS];
+    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (warp >= W.N) return;
+    XferSmem &S = sm_all[(threadIdx.x >> 5) % XFER_WARPS];
+    int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
+    int lvl = W.n_levels > 1 ? W.lvl_level[warp] : 0;
+    if (lvl > 0) {
+        int need = W.lvl_off[lvl] - W.lvl_off[lvl - 1];
+        WARP_FOR(lane) if (lane == 0) {
+            volatile int *done = W.lvl_done + (lvl - 1);
+#ifdef UX_EMU
+            if (*done < need) { dev_error(W, DERR_RING_FULL, -1); }
+#else
+            while (*done < need) __nanosleep(64);
+            __threadfence();
+#endif
+        }
+        WARP_SYNC();
+    }
+    xfer_node(W, S, n, t);
+    if (W.n_levels > 1) {
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) { __threadfence(); atomicAdd(W.lvl_done + lvl, 1); }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K3: Vehicle::car_follow_newell (traffi.cpp:798-823) + Vehicle::update RUN branch (844-878) for every
-//     occupied ring slot; the first thread of each link's first segment additionally handles the link head.
+//     occupied ring slot.  The warp owning a link's first segment additionally handles the link head: the
+//     platoons that can be at the link end are exactly the first `lanes` queue positions (anything further back
+//     has a leader on the same link), so their trip end / abort / next-link choice is evaluated by one lane per
+//     position in parallel and only the "is it the front" prefix (traffi.cpp:861, 869) is resolved serially.
 // ---------------------------------------------------------------------------------------------------
-UX_DEV void link_head_update(const DevWorld &W, int l, int t, int cur) {
-    int L = W.L, lanes = W.l_lanes[l], cap = W.l_rcap[l];
-    long long o = W.l_roff[l];
-    size_t C = (size_t)W.C;
-    int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], hd = hd0 + pk2, tl = W.tail[l], n = tl - hd;
-    // lane relabel when the end node (smaller id) emptied the link before this step's pushes (DESIGN.md iii)
-    if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
-        int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
-        if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
-    }
-    W.stat_count[l] += n;
-    int hc = n < lanes ? n : lanes, k = 0;
-    int end_node = W.l_end[l];
-    double len = W.l_length[l], udt = W.l_udt[l];
-    for (int j = 0; j < hc; j++) {
-        int slot = ring_slot(hd, j, cap);
-        int vid = W.VID[o + slot];
-        double x = W.X[(size_t)cur * C + o + slot];
-        double xn = x + udt;  // positions < lanes have no leader
-        if (xn < x) xn = x;
-        if (xn > len) { W.v_mr[vid] = xn - len; xn = len; }
-        unsigned char f = 0;
-        if (fabs(xn - len) < 1e-9) {
-            if (end_node == W.v_dest[vid]) {
-                f = VF_WAIT_END;
-                W.v_flags[vid] = f;
-                if (k == j) { end_trip(W, vid, l, t, xn); k++; continue; }
-            } else if (W.n_out_off[end_node + 1] == W.n_out_off[end_node]) {  // dead end: abort (traffi.cpp:864-871)
-                f = VF_WAIT_END | VF_ABORT;
-                W.v_next[vid] = -1;
-                W.v_flags[vid] = f;
-                if (k == j) { end_trip(W, vid, l, t, xn); k++; continue; }
-            } else {
-                W.v_next[vid] = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u);
-                f = VF_CAND;
-            }
-        }
-        W.v_flags[vid] = f;
-    }
-    W.head[(cur ^ 1) * L + l] = hd + k;
-    int rem = n - k;
-    W.hcount[l] = rem < lanes ? rem : lanes;
-}
+#define UX_MAXLANE 64
+#define UPD_WARPS 8
+struct HeadSmem {
+    int vid[UX_MAXLANE], next[UX_MAXLANE], dts[UX_MAXLANE];
+    unsigned char kind[UX_MAXLANE];  // 0 not at end, 1 trip end, 2 abort, 3 transfer candidate
+    double xn[UX_MAXLANE], atl[UX_MAXLANE], ex[UX_MAXLANE], dist[UX_MAXLANE];
+};
 
-__global__ void __launch_bounds__(256) k_update(const DevWorld *worlds, int step_off) {
-    const DevWorld &W = worlds[blockIdx.y];
-    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+__global__ void __launch_bounds__(32 * UPD_WARPS) k_update(const DevWorld *worlds, int step_off) {
+    LOAD_WORLD(W, worlds)
+    WARP_BEGIN
+    __shared__ HeadSmem hs_all[UPD_WARPS];
+    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (gw >= W.nseg) return;
-    int l = W.seg_link[gw], s0 = W.seg_start[gw], p = s0 + lane, cap = W.l_rcap[l];
+    // work item = (link, part): the warp sweeps the 32-position windows part, part+nparts, ... of the link's queue, so the
+    // work is proportional to the platoons present, and long queues are shared by several warps
+    int l = W.seg_link[gw], part = W.seg_start[gw] & 0xffff, nparts = W.seg_start[gw] >> 16, L = W.L;
     int t = *W.t_base + step_off, cur = t & 1;
-    if (p < cap) {
-        int hd = W.head[cur * W.L + l] + W.pop_k2[l], n = W.tail[l] - hd;
-        int hp = (int)((unsigned)hd % (unsigned)cap);
-        int pos = p - hp; if (pos < 0) pos += cap;
-        if (pos < n) {
-            size_t C = (size_t)W.C;
-            long long o = W.l_roff[l];
-            const double *Xc = W.X + (size_t)cur * C + o;
+    size_t C = (size_t)W.C;
+    int cap = W.l_rcap[l];
+    long long o = W.l_roff[l];
+    int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], tl = W.tail[l];
+    int lanes = W.l_lanes[l];
+    double len = W.l_length[l], udt = W.l_udt[l], dpl = W.l_dpl_dn[l];
+    int hd = hd0 + pk2, n = tl - hd;
+    int s0 = part;
+    const double *Xc = W.X + (size_t)cur * C + o;
+    WARP_FOR(lane) {
+        for (int pos = part * 32 + lane; pos < n; pos += nparts * 32) {
+            int p = ring_slot(hd, pos, cap);
             double x = Xc[p];
-            double xn = x + W.l_udt[l];
-            int lanes = W.l_lanes[l];
+            double xn = x + udt;
             if (pos >= lanes) {
-                int lp = p - lanes; if (lp < 0) lp += cap;
-                double gap = Xc[lp] - W.l_dpl_dn[l];
+                double gap = Xc[ring_slot(hd, pos - lanes, cap)] - dpl;
                 if (gap < x) gap = x;
                 if (xn > gap) xn = gap;
             }
             if (xn < x) xn = x;
-            double len = W.l_length[l];
             if (xn > len) xn = len;
             W.X[(size_t)(cur ^ 1) * C + o + p] = xn;
             W.V[o + p] = (xn - x) / W.dt;
         }
     }
-    if (s0 == 0 && lane == 0) link_head_update(W, l, t, cur);
+    if (s0 != 0) return;
+    // ---- link head
+    HeadSmem &H = hs_all[(threadIdx.x >> 5) % UPD_WARPS];
+    int hc = n < lanes ? n : lanes;
+    if (hc > UX_MAXLANE) hc = UX_MAXLANE;
+    int end_node = W.l_end[l];
+    bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
+    WARP_FOR(lane) {
+        for (int j = lane; j < hc; j += 32) {
+            int slot = ring_slot(hd, j, cap);
+            int vid = W.VID[o + slot];
+            double x = Xc[slot];
+            int dest_ = W.v_dest[vid];
+            double atl_ = W.v_atl[vid], ex_ = W.v_entry_x[vid], di_ = W.v_dist[vid]; int dts_ = W.v_depart_ts[vid];
+            double xn = x + udt;  // positions < lanes have no leader
+            if (xn < x) xn = x;
+            bool over = xn > len;
+            double mr_ = xn - len;
+            if (over) xn = len;
+            unsigned char kind = 0;
+            int nx = -1;
+            if (fabs(xn - len) < 1e-9) {
+                if (end_node == dest_) kind = 1;
+                else if (dead_end) kind = 2;  // traffi.cpp:864-871 (trip_abort is always 1 in this engine)
+                else { kind = 3; nx = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u); }
+            }
+            if (over) W.v_mr[vid] = mr_;
+            H.vid[j] = vid; H.kind[j] = kind; H.xn[j] = xn; H.next[j] = nx;
+            H.atl[j] = atl_; H.ex[j] = ex_; H.dist[j] = di_; H.dts[j] = dts_;
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        // lane relabel when the end node (smaller id) emptied the link before this step's pushes
+        if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
+            int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+            if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
+        }
+        W.stat_count[l] += n;
+        int k = 0, evc = 0, trips = 0;
+        double cumdep = 0.0;
+        bool touched = false;
+        for (int j = 0; j < hc; j++) {
+            int vid = H.vid[j];
+            unsigned char kind = H.kind[j], f = 0;
+            if (kind == 3) { W.v_next[vid] = H.next[j]; f = VF_CAND; }
+            else if (kind == 1 || kind == 2) {
+                f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
+                if (kind == 2) W.v_next[vid] = -1;
+                if (k == j) {  // it is the front (everything ahead ended in this pass): end_trip, traffi.cpp:886-927
+                    if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[(size_t)t * L + l]; touched = true; }
+                    trips += 1; cumdep += W.dn;
+                    double atl = H.atl[j];
+                    int es = (int)(atl / W.dt);
+                    if (es < 0) es = 0;
+                    if (es >= W.T) es = W.T - 1;
+                    evc += 1;
+                    W.ev_ord[(size_t)es * L + l] = evc;
+                    W.ev_tt[(size_t)es * L + l] = ((double)t + 1.0) * W.dt - atl;
+                    W.v_atl[vid] = (double)t * W.dt;
+                    W.v_dist[vid] = H.dist[j] + (H.xn[j] - H.ex[j]);
+                    W.v_link[vid] = -1;
+                    if (kind == 2) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+                    else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)H.dts[j] * W.dt; }
+                    f = 0;
+                    k++;
+                }
+            }
+            W.v_flags[vid] = f;
+        }
+        if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[(size_t)t * L + l] = cumdep; }
+        W.head[(cur ^ 1) * L + l] = hd + k;
+        int rem = n - k;
+        W.hcount[l] = rem < lanes ? rem : lanes;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -556,7 +1012,7 @@ __global__ void __launch_bounds__(256) k_update(const DevWorld *worlds, int step
 // per-destination fixed point of oracle R2), route_choice_duo (1486-1553).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int step_off) {
-    const DevWorld &W = worlds[blockIdx.y];
+    LOAD_WORLD(W, worlds)
     int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (e >= W.n_edges) return;
     int g = W.e_link[e], t = *W.t_base + step_off;
@@ -580,7 +1036,7 @@ __global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int s
 
 // One block per active destination: label-correcting relaxation to the fixed point dist[i] = min_j c_ij + dist[j].
 __global__ void __launch_bounds__(256) k_sssp(const DevWorld *worlds) {
-    const DevWorld &W = worlds[blockIdx.y];
+    LOAD_WORLD(W, worlds)
     int row = (int)blockIdx.x;
     if (row >= W.D) return;
     int N = W.N, k = W.row_dest[row];
@@ -640,7 +1096,7 @@ __global__ void __launch_bounds__(256) k_sssp(const DevWorld *worlds) {
 }
 
 __global__ void __launch_bounds__(256) k_duo(const DevWorld *worlds, int gradual_step) {
-    const DevWorld &W = worlds[blockIdx.y];
+    LOAD_WORLD(W, worlds)
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)W.D * W.L;
     if (idx >= total) return;
@@ -695,15 +1151,15 @@ __global__ void k_veh_snapshot(const DevWorld *worlds, int replica, double *vx, 
     const DevWorld &W = worlds[replica];
     int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
     if (gw >= W.nseg) return;
-    int l = W.seg_link[gw], p = W.seg_start[gw] + lane, cap = W.l_rcap[l];
-    if (p >= cap) return;
+    int l = W.seg_link[gw], part = W.seg_start[gw] & 0xffff, nparts = W.seg_start[gw] >> 16, cap = W.l_rcap[l];
     int cur = *W.t_base & 1;
     int hd = W.head[cur * W.L + l], n = W.tail[l] - hd;
-    int pos = p - (int)((unsigned)hd % (unsigned)cap); if (pos < 0) pos += cap;
-    if (pos >= n) return;
     long long o = W.l_roff[l];
-    int vid = W.VID[o + p];
-    vx[vid] = W.X[(size_t)cur * W.C + o + p]; vv[vid] = W.V[o + p]; vlane[vid] = W.LANE[o + p];
+    for (int pos = part * 32 + lane; pos < n; pos += nparts * 32) {
+        int p = ring_slot(hd, pos, cap);
+        int vid = W.VID[o + p];
+        vx[vid] = W.X[(size_t)cur * W.C + o + p]; vv[vid] = W.V[o + p]; vlane[vid] = W.LANE[o + p];
+    }
 }
 
 // per-link ensemble statistics over this world's replicas: {volume, sum tt_actual, sum tt_actual^2, platoons on link}
@@ -763,7 +1219,7 @@ struct ux_world {
 #endif
     // device pointers of updatable static arrays
     double *d_vmax = nullptr, *d_dpl_dn = nullptr, *d_udt = nullptr, *d_cap_out = nullptr, *d_cap_in = nullptr, *d_mp = nullptr, *d_penalty = nullptr, *d_toll = nullptr, *d_n_sig = nullptr;
-    int *d_l_flags = nullptr, *d_lvl_off = nullptr, *d_lvl_nodes = nullptr, *d_sg_off = nullptr, *d_sg = nullptr, *d_n_sig_off = nullptr;
+    int *d_l_flags = nullptr, *d_lvl_off = nullptr, *d_lvl_nodes = nullptr, *d_lvl_level = nullptr, *d_sg_off = nullptr, *d_sg = nullptr, *d_n_sig_off = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     double *d_ens = nullptr;
     // measurement
@@ -992,13 +1448,17 @@ UX_API int ux_initialize_adj_matrix(ux_world *w) {
         for (int l : n.in) li += w->links[l].lanes;
         for (int l : n.out) lo += w->links[l].lanes;
         if (li > UX_MAXC || lo > UX_MAXC) return fail(w, UX_ERR_INVALID, "node %d: more than %d lanes in or out not supported", (int)i, UX_MAXC);
+        for (int l : n.out) {
+            if (w->links[l].lanes > UX_MAXLANE) return fail(w, UX_ERR_INVALID, "link %d: more than %d lanes not supported", l, UX_MAXLANE);
+            if (w->links[l].end == (int)i) return fail(w, UX_ERR_INVALID, "link %d: self-loops are not supported", l);
+        }
     }
     w->initialized = true;
     return 0;
 }
 
 // ---- transfer dependency levels (DESIGN.md "transfer order") --------------------------------------------
-static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<int> &lvl_off, std::vector<int> &lvl_nodes) {
+static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<int> &lvl_off, std::vector<int> &lvl_nodes, std::vector<int> &lvl_level) {
     int N = (int)w->nodes.size(), L = (int)w->links.size();
     lflags.assign(L, 0);
     std::vector<int> level(N, 0);
@@ -1022,6 +1482,8 @@ static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<in
     lvl_nodes.assign(N, 0);
     std::vector<int> fill(nl, 0);
     for (int a = 0; a < N; a++) lvl_nodes[lvl_off[level[a]] + fill[level[a]]++] = a;
+    lvl_level.assign(N, 0);
+    for (int q = 0; q < N; q++) lvl_level[q] = level[lvl_nodes[q]];
     w->n_levels = nl;
 }
 
@@ -1040,8 +1502,11 @@ static int upload_link_params(ux_world *w) {
     CUDA_OK(cudaMemcpy(w->d_cap_in, ci.data(), b, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(w->d_mp, mp.data(), b, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(w->d_penalty, pen.data(), b, cudaMemcpyHostToDevice));
-    std::vector<int> lflags, lvl_off, lvl_nodes;
-    compute_levels(w, lflags, lvl_off, lvl_nodes);
+    std::vector<int> lflags, lvl_off, lvl_nodes, lvl_level;
+    compute_levels(w, lflags, lvl_off, lvl_nodes, lvl_level);
+    CUDA_OK(cudaMemcpy(w->d_lvl_level, lvl_level.data(), sizeof(int) * lvl_level.size(), cudaMemcpyHostToDevice));
+    for (auto &d : w->hw) d.n_levels = w->n_levels;
+    if (w->dworlds) CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->hw.size(), cudaMemcpyHostToDevice));
     lvl_off.resize(w->nodes.size() + 2, lvl_off.back());
     CUDA_OK(cudaMemcpy(w->d_l_flags, lflags.data(), sizeof(int) * L, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(w->d_lvl_off, lvl_off.data(), sizeof(int) * lvl_off.size(), cudaMemcpyHostToDevice));
@@ -1076,10 +1541,14 @@ static int upload(ux_world *w) {
         // jam storage of the link in platoons + entry slack (a platoon is accepted once the one `lanes` ahead has
         // moved one spacing, so at most length/(delta_per_lane*dn) per lane + the ones at x <= spacing)
         double per_lane = l.length / (l.dpl * w->p.delta_n);
-        long long cap = ((long long)std::floor(per_lane) + 3) * l.lanes + 2;
-        if (cap > 0x3fffffff) return fail(w, UX_ERR_INVALID, "link %d: ring too large", i);
+        long long need = ((long long)std::floor(per_lane) + 3) * l.lanes + 2, cap = 4;
+        while (cap < need) cap <<= 1;  // power of two: slot = position & (cap - 1)
+        if (cap > 0x20000000) return fail(w, UX_ERR_INVALID, "link %d: ring too large", i);
         l_rcap[i] = (int)cap; l_roff[i] = C; C += cap;
-        for (int s = 0; s < (int)cap; s += UX_SEG) { seg_link.push_back(i); seg_start.push_back(s); }
+        {   // work items of the update kernel: one warp per 512 ring slots, at least one per link
+            int nparts = (int)((cap + 511) / 512);
+            for (int part = 0; part < nparts; part++) { seg_link.push_back(i); seg_start.push_back(part | (nparts << 16)); }
+        }
         sg_off[i + 1] = sg_off[i] + (int)l.sg.size();
         sg.insert(sg.end(), l.sg.begin(), l.sg.end());
         if (!l.toll.empty()) any_toll = true;
@@ -1093,9 +1562,9 @@ static int upload(ux_world *w) {
     base.seg_link = dupload(w, seg_link); base.seg_start = dupload(w, seg_start);
     w->d_vmax = dalloc<double>(w, L); w->d_dpl_dn = dalloc<double>(w, L); w->d_udt = dalloc<double>(w, L); w->d_cap_out = dalloc<double>(w, L);
     w->d_cap_in = dalloc<double>(w, L); w->d_mp = dalloc<double>(w, L); w->d_penalty = dalloc<double>(w, L);
-    w->d_l_flags = dalloc<int>(w, L); w->d_lvl_off = dalloc<int>(w, N + 2); w->d_lvl_nodes = dalloc<int>(w, N);
+    w->d_l_flags = dalloc<int>(w, L); w->d_lvl_off = dalloc<int>(w, N + 2); w->d_lvl_nodes = dalloc<int>(w, N); w->d_lvl_level = dalloc<int>(w, N);
     base.l_vmax = w->d_vmax; base.l_dpl_dn = w->d_dpl_dn; base.l_udt = w->d_udt; base.l_cap_out = w->d_cap_out; base.l_cap_in = w->d_cap_in;
-    base.l_mp = w->d_mp; base.l_penalty = w->d_penalty; base.l_flags = w->d_l_flags; base.lvl_off = w->d_lvl_off; base.lvl_nodes = w->d_lvl_nodes;
+    base.l_mp = w->d_mp; base.l_penalty = w->d_penalty; base.l_flags = w->d_l_flags; base.lvl_off = w->d_lvl_off; base.lvl_nodes = w->d_lvl_nodes; base.lvl_level = w->d_lvl_level;
     { int rc = upload_link_params(w); if (rc) return rc; }
     if (any_toll) {  // [T][L]; links without a series use their static penalty (traffi.cpp:1285-1289)
         std::vector<double> toll((size_t)T * L);
@@ -1151,6 +1620,7 @@ static int upload(ux_world *w) {
     int D = (int)w->row_dest.size(); w->n_active = D; base.D = D;
     base.v_orig = dupload(w, v_orig); base.v_dest = dupload(w, v_dest); base.v_depart_ts = dupload(w, v_ts);
     base.gen_off = dupload(w, gen_off); base.gen_list = dupload(w, gen_list);
+    { std::vector<int> gen_ts(P); for (long long q = 0; q < P; q++) gen_ts[q] = v_ts[gen_list[q]]; base.gen_ts = dupload(w, gen_ts); }
     base.dest_row = dupload(w, w->dest_row); base.row_dest = dupload(w, w->row_dest);
     for (int kind = 0; kind < 3; kind++) {
         if (w->vlinks[kind].empty()) continue;
@@ -1192,7 +1662,7 @@ static int upload(ux_world *w) {
         d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
         d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
         if (d.rnext) cudaMemset(d.rnext, 0xff, sizeof(int) * std::max<size_t>((size_t)D * N, 1));
-        d.err = dalloc<int>(w, 2); d.t_base = dupload(w, tb);
+        d.err = dalloc<int>(w, 2); d.t_base = dupload(w, tb); d.lvl_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
         if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
             return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
     }
@@ -1221,7 +1691,7 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
     long long lc = 0;
     for (int s = 0; s < nsteps; s++) {
         if (N > 0) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_pre, g_nodes, dim3(128), st, w->dworlds, s); KT_END(UX_K_PRE) lc++; }
-        if (N > 0) for (int lv = 0; lv < w->n_levels; lv++) { KT_BEGIN(UX_K_TRANSFER) UX_LAUNCH(k_transfer, g_nodes, dim3(128), st, w->dworlds, s, lv); KT_END(UX_K_TRANSFER) lc++; }
+        if (N > 0) { KT_BEGIN(UX_K_TRANSFER) UX_LAUNCH(k_transfer, g_nodes, dim3(128), st, w->dworlds, s); KT_END(UX_K_TRANSFER) lc++; }
         if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(256), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
         bool route = ((phase + s) % w->route_ts) == 0;
         if (w->n_active > 0 && w->n_edges > 0) {

@@ -194,6 +194,7 @@ enum {
     UX_I_H2D_BYTES = 15,       /* bytes copied host->device so far (product only) */
     UX_I_D2H_BYTES = 16,       /* bytes copied device->host so far (product only) */
     UX_I_RING_SLOTS = 17,      /* total ring-buffer slots per replica */
+    UX_I_MAX_DEPART_TS = 18,   /* largest departure timestep over all platoons (for the automatic TMAX, uxsim.py:2325-2333) */
     UX_I_KERNEL_LAUNCHES_OF = 100 /* + kernel id (UX_K_*): launches of that kernel in timing mode */
 };
 /* kernel ids for the timing mode */

@@ -248,6 +248,7 @@ UX_API int64_t uxr_get_int(ux_world *w, int what) {
     case UX_I_NUM_ACTIVE_DESTS: return W->node_id;
     case UX_I_TRANSFER_LEVELS: return W->node_id;
     case UX_I_LINK_EVENTS: { int64_t s = 0; for (auto *l : W->links) s += (int64_t)l->traveltime_real_events.size(); return s; }
+    case UX_I_MAX_DEPART_TS: { int m = 0; for (auto *v : W->vehicles) m = std::max(m, (int)(v->departure_time / W->delta_t)); return m; }
     default: return fail(w, UX_ERR_INVALID, "unknown int query");
     }
 }

@@ -941,6 +941,7 @@ UX_API int64_t uxo_get_int(ux_world *w, int what) {
     case UX_I_NUM_ACTIVE_DESTS: { int s = 0; if (w->dest_active) for (int i = 0; i < w->nn; i++) s += w->dest_active[i]; return s; }
     case UX_I_TRANSFER_LEVELS: return 1;
     case UX_I_LINK_EVENTS: { int64_t s = 0; for (int i = 0; i < w->nl; i++) s += w->links[i].nev; return s; }
+    case UX_I_MAX_DEPART_TS: { int m = 0; for (int64_t i = 0; i < w->nv; i++) if (w->vehs[i].depart_ts > m) m = w->vehs[i].depart_ts; return m; }
     default: return fail(w, UX_ERR_INVALID, "unknown int query %d", what);
     }
 }

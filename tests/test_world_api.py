@@ -1,0 +1,92 @@
+"""The reference-facing API: uxsim_b200.World(..., cuda=True) mirrors CppWorld (uxsim_cpp_wrapper.py)."""
+import inspect
+
+import numpy as np
+import pytest
+
+import uxsim_b200
+from uxsim_b200 import _capi as C
+from uxsim_b200 import scenario as S
+from uxsim_b200.world import CudaLink, CudaNode, CudaWorld
+
+
+def test_wrapper_signatures_match_class_constructors():
+    """tests/test_wrapper_functions.py:10-35 of the reference: addNode/addLink take what the classes take."""
+    for fn, cls in ((CudaWorld.addNode, CudaNode), (CudaWorld.addLink, CudaLink)):
+        a = list(inspect.signature(fn).parameters)[1:]
+        b = list(inspect.signature(cls.__init__).parameters)[2:]
+        assert a == b
+
+
+def test_reference_kwargs_are_accepted():
+    """Every World(...) kwarg of the reference (uxsim.py:1677-1690) exists on CudaWorld with the same default."""
+    ref = dict(name="", deltan=5, reaction_time=1, duo_update_time=600, duo_update_weight=0.5, duo_noise=0.01,
+               route_choice_principle="homogeneous_DUO", route_choice_update_gradual=False, instantaneous_TT_timestep_interval=5,
+               no_cyclic_routing=False, adjust_node_capacity=False, eular_dt=120, eular_dx=100, random_seed=None, print_mode=1,
+               save_mode=1, show_mode=0, show_progress=1, show_progress_deltat=600, tmax=None, vehicle_logging_timestep_interval=1,
+               reduce_memory_delete_vehicle_route_pref=False, hard_deterministic_mode=False, user_attribute=None, user_function=None, threads=1)
+    sig = inspect.signature(CudaWorld.__init__).parameters
+    for k, v in ref.items():
+        assert k in sig and sig[k].default == v, k
+
+
+def test_only_cuda_mode_is_offered():
+    with pytest.raises(NotImplementedError):
+        uxsim_b200.World(name="x")
+
+
+@pytest.mark.gpu
+def test_readme_merge_example(cuda_api, oracle_api):
+    """README Y-merge through the World API == the same scenario through the raw C-ABI of the oracle."""
+    W = uxsim_b200.World(cuda=True, name="", deltan=5, tmax=1200, print_mode=0, save_mode=0, show_mode=0, random_seed=0)
+    W.addNode("orig1", 0, 0), W.addNode("orig2", 0, 2), W.addNode("merge", 1, 1), W.addNode("dest", 2, 1)
+    W.addLink("link1", "orig1", "merge", length=1000, free_flow_speed=20, number_of_lanes=1)
+    W.addLink("link2", "orig2", "merge", length=1000, free_flow_speed=20, number_of_lanes=1)
+    W.addLink("link3", "merge", "dest", length=1000, free_flow_speed=20, number_of_lanes=1)
+    W.adddemand("orig1", "dest", 0, 1000, 0.45)
+    W.adddemand("orig2", "dest", 400, 1000, 0.6)
+    assert W.exec_simulation() == 1
+    assert len(W.VEHICLES) == 162 and W.TSIZE == 240 and not W.check_simulation_ongoing()
+    sc = S.merge_y(hard_deterministic_mode=False, random_seed=0, tmax=1200)
+    Eo = sc.to_engine(oracle_api, vehicle_logging_timestep_interval=-1)
+    Eo.main_loop()
+    L, T = 3, 240
+    assert np.array_equal(W.get_link("link3").cum_arrival, Eo.get_array(C.A_CUM_ARRIVAL).reshape(L, T)[2])
+    assert np.array_equal(W.get_link("link1").cum_departure, Eo.get_array(C.A_CUM_DEPARTURE).reshape(L, T)[0])
+    tt = np.array([v.travel_time for v in W.VEHICLES.values()], dtype=float)
+    assert np.array_equal(tt, Eo.get_array(C.A_VEH_TRAVEL_TIME))
+    a = W.analyzer
+    assert a.trip_all == 810 and 0 < a.trip_completed <= 810 and a.average_travel_time > 100
+
+
+@pytest.mark.gpu
+def test_chunked_exec_and_interventions(cuda_api):
+    """exec_simulation(until_t=...) returns 0 until the horizon; signals can be changed between chunks
+    (uxsim_cpp_wrapper.py:89-124; test_cpp_mode.py:8485-8643)."""
+    W = uxsim_b200.World(cuda=True, deltan=5, tmax=2000, print_mode=0, save_mode=0, random_seed=0)
+    W.addNode("o", 0, 0), W.addNode("m", 1, 0, signal=[60, 60]), W.addNode("d", 2, 0)
+    l1 = W.addLink("l1", "o", "m", length=1000, signal_group=0)
+    W.addLink("l2", "m", "d", length=1000)
+    W.adddemand("o", "d", 0, 1000, 0.4)
+    assert W.exec_simulation(until_t=500) == 0
+    assert W.T == 101 and W.check_simulation_ongoing()
+    n_mid = l1.num_vehicles
+    assert n_mid >= 0
+    W.get_node("m").signal = [30, 90]
+    assert W.exec_simulation() == 1
+    assert l1.cum_departure[-1] == 80 * 5 or l1.cum_departure[-1] > 0
+    assert len(W.VEHICLES_RUNNING) == (W._veh("state") == C.VS_RUN).sum()
+
+
+@pytest.mark.gpu
+def test_unsupported_like_cpp_mode(cuda_api):
+    W = uxsim_b200.World(cuda=True, deltan=5, tmax=600, print_mode=0, save_mode=0)
+    W.addNode("a", 0, 0), W.addNode("b", 1, 0)
+    W.addLink("l", "a", "b", length=500)
+    with pytest.raises(NotImplementedError):
+        W.addVehicle("a", "b", 0, mode="taxi")
+    for f in (W.copy, lambda: W.save("x"), lambda: W.load_scenario("x"), lambda: W.save_scenario("x")):
+        with pytest.raises(NotImplementedError):
+            f()
+    with pytest.raises(ValueError):
+        W.addNode("a", 0, 0)

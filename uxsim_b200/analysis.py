@@ -1,0 +1,86 @@
+"""Summary statistics of a finished run, computed from the arrays the engine hands back.
+
+Used as ``W.analyzer`` when the reference package (and with it ``uxsim/analyzer.py``) is not installed -- e.g. on the
+GPU box.  It restates the numbers of ``Analyzer.basic_analysis`` / ``od_analysis`` / ``print_simple_stats``
+(analyzer.py:98-181, 1166-1190) with vectorised numpy instead of per-vehicle Python loops; plotting, pandas
+export and Edie states stay with the reference's analyzer.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi as C
+
+
+def free_flow_times(W) -> np.ndarray:
+    """All-pairs free-flow travel time (analyzer.py:147-163 uses scipy floyd_warshall on length/u)."""
+    n = len(W.NODES)
+    adj = np.full((n, n), np.inf)
+    for l in W.LINKS:
+        if l.capacity_in != 0:
+            adj[l.start_node.id, l.end_node.id] = min(adj[l.start_node.id, l.end_node.id], l.length / l.u)
+    try:
+        from scipy.sparse.csgraph import floyd_warshall
+
+        a = np.where(np.isinf(adj), 0.0, adj)
+        return floyd_warshall(a, directed=True)
+    except Exception:
+        d = adj.copy()
+        np.fill_diagonal(d, 0.0)
+        for k in range(n):
+            d = np.minimum(d, d[:, k:k + 1] + d[k:k + 1, :])
+        return d
+
+
+class BasicAnalyzer:
+    def __init__(self, W):
+        self.W = W
+        self.average_speed = 0.0
+        self.average_speed_count = 0
+        self.trip_all = self.trip_completed = 0
+        self.total_travel_time = self.average_travel_time = self.total_delay = self.average_delay = -1
+        self.total_distance_traveled = 0.0
+
+    def basic_analysis(self):
+        W = self.W
+        dn = W.DELTAN
+        st, tt = W._veh("state"), W._veh("travel_time")
+        dist = W._veh("distance")
+        o = W._E.get_array(C.A_VEH_ORIG)
+        d = W._E.get_array(C.A_VEH_DEST)
+        done = tt >= 0
+        self.trip_all = len(st) * dn
+        self.trip_completed = int(done.sum()) * dn
+        self.total_distance_traveled = float(dist.sum()) * dn
+        if done.any():
+            ff = free_flow_times(W)
+            self.total_travel_time = float(tt[done].sum()) * dn
+            self.average_travel_time = self.total_travel_time / self.trip_completed
+            self.total_delay = float((tt[done] - ff[o[done], d[done]]).sum()) * dn
+            self.average_delay = self.total_delay / self.trip_completed
+        else:
+            self.total_travel_time = self.average_travel_time = self.total_delay = self.average_delay = -1
+        upd = W._E.get_array(C.A_LINK_STAT_COUNT).sum()
+        self.average_speed_count = int(upd)
+
+    def print_simple_stats(self, force_print=False):
+        W = self.W
+        p = print if force_print else W.print
+        p("results:")
+        p(f" number of completed trips:\t {self.trip_completed} / {self.trip_all}")
+        if self.trip_completed > 0:
+            p(f" total travel time:\t\t {self.total_travel_time:.1f} s")
+            p(f" average travel time of trips:\t {self.average_travel_time:.1f} s")
+            p(f" average delay of trips:\t {self.average_delay:.1f} s")
+            p(f" delay ratio:\t\t\t {self.average_delay / self.average_travel_time:.3f}")
+            p(f" total distance traveled:\t {self.total_distance_traveled:.1f} m")
+
+    def link_summary(self):
+        """traffic_volume / vehicles_remain / free and average travel time per link (link_analysis_coarse, analyzer.py:183-203)."""
+        W = self.W
+        arr, dep, tta = W._series("cum_arrival"), W._series("cum_departure"), W._series("traveltime_actual")
+        vol = dep[:, -1]
+        pos = np.where(tta > 0, tta, np.nan)
+        return dict(traffic_volume=vol, vehicles_remain=arr[:, -1] - dep[:, -1],
+                    free_travel_time=np.array([l.length / l.u for l in W.LINKS]),
+                    average_travel_time=np.where(vol > 0, np.nanmean(pos, axis=1), -1.0))

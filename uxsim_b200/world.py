@@ -1,0 +1,804 @@
+"""``World(..., cuda=True)``: the reference's scenario API in front of the CUDA engine.
+
+Mirrors ``uxsim/uxsim_cpp_wrapper.py`` (``CppWorld`` 800-1533, ``CppNode`` 40-181, ``CppLink`` 184-482,
+``CppVehicle`` 486-725): same constructor kwargs, same ``addNode / addLink / addVehicle / adddemand* /
+finalize_scenario / exec_simulation / check_simulation_ongoing / get_node / get_link / defRoute`` methods, same
+attributes for ``analyzer.py`` (``W.VEHICLES / LINKS / NODES``, per-link ``cum_arrival / cum_departure /
+traveltime_actual / traveltime_instant``, per-vehicle ``travel_time / arrival_time / distance_traveled / state``),
+same unsupported set (taxi mode, ``save / copy / load_scenario`` raise ``NotImplementedError`` exactly like cpp
+mode, uxsim_cpp_wrapper.py:929-931, 1468-1472, 1529-1533).  ``user_function`` callbacks are stored, never called
+(as in cpp mode).
+
+Selection works like ``cpp=True`` (uxsim.py:1671-1675): ``uxsim_b200.World(..., cuda=True)`` returns a
+:class:`CudaWorld`.  Simulation logic lives in ``csrc/engine.cu`` only; this file forwards parameters, keeps the
+name<->id maps, and hands results back.  Results are fetched lazily and cached as numpy arrays; with
+``as_tensor=True`` helpers the same buffers are exposed as zero-copy torch CUDA tensors
+(:func:`uxsim_b200.ensemble.device_tensor`).
+
+If the reference package ``uxsim`` is importable, its unmodified ``Analyzer`` is attached as ``W.analyzer``;
+otherwise :class:`uxsim_b200.analysis.BasicAnalyzer` provides the ``basic_analysis`` / ``print_simple_stats``
+numbers from the same attributes.
+"""
+from __future__ import annotations
+
+import csv
+import math
+import string
+import time
+import warnings
+from collections import OrderedDict, deque
+from collections import defaultdict as ddict
+
+import numpy as np
+
+from . import _capi as C
+
+_STATE_NAMES = ["home", "wait", "run", "end", "abort"]
+
+
+class CudaNode:
+    """uxsim_cpp_wrapper.py:40-181 (CppNode)."""
+
+    def __init__(self, W, name, x, y, signal=[0], signal_offset=0, signal_offset_old=None, flow_capacity=None,
+                 number_of_lanes=None, auto_rename=False, attribute=None, user_attribute=None, user_function=None):
+        self.W = W
+        self.attribute, self.user_attribute, self.user_function = attribute, user_attribute, user_function
+        if signal_offset_old is not None:
+            signal_offset = sum(signal) - signal_offset_old
+        self.inlinks, self.outlinks = dict(), dict()
+        self.id = len(W.NODES)
+        self.name = name
+        if self.name in W.NODES_NAME_DICT:
+            if auto_rename:
+                self.name = self.name + "_renamed" + "".join(W.rng.choice(list(string.ascii_letters + string.digits), size=8))
+            else:
+                raise ValueError(f"Node name {self.name} already used by another node.")
+        W.NODES.append(self)
+        W.NODES_NAME_DICT[self.name] = self
+        self.x, self.y = float(x), float(y)
+        self._signal = [float(s) for s in signal]
+        self.signal_offset = float(signal_offset)
+        self.flow_capacity = flow_capacity
+        self.number_of_lanes = number_of_lanes
+        if flow_capacity is not None and number_of_lanes is None:
+            self.number_of_lanes = math.ceil(flow_capacity / 0.8)
+        self.flag_lanes_automatically_determined = flow_capacity is not None and number_of_lanes is None
+        eid = W._E.add_node(self.x, self.y, self._signal, self.signal_offset,
+                            -1.0 if flow_capacity is None else float(flow_capacity),
+                            -1 if number_of_lanes is None else int(number_of_lanes))
+        assert eid == self.id
+
+    def __repr__(self):
+        return f"<Node {self.name}>"
+
+    @property
+    def signal(self):
+        return list(self._signal)
+
+    @signal.setter
+    def signal(self, value):
+        self._signal = [float(v) for v in value]
+        self.W._E.set_node_signal(self.id, self._signal)
+
+    @property
+    def cycle_length(self):
+        return sum(self._signal)
+
+    @property
+    def signal_phase(self):
+        return int(self.W._E.get_array(C.A_NODE_SIGNAL_PHASE)[self.id])
+
+    @signal_phase.setter
+    def signal_phase(self, value):
+        self.W._E.set_node_signal(self.id, None, phase=int(value))
+
+    @property
+    def signal_t(self):
+        return float(self.W._E.get_array(C.A_NODE_SIGNAL_T)[self.id])
+
+    @signal_t.setter
+    def signal_t(self, value):
+        self.W._E.set_node_signal(self.id, None, signal_t=float(value))
+
+    @property
+    def signal_log(self):
+        return list(self.W._series("signal_log")[self.id][: self.W.T])
+
+
+class CudaLink:
+    """uxsim_cpp_wrapper.py:184-482 (CppLink)."""
+
+    def __init__(self, W, name, start_node, end_node, length, free_flow_speed=20, jam_density=0.2, jam_density_per_lane=None,
+                 number_of_lanes=1, merge_priority=1, signal_group=[0], capacity_out=None, capacity_in=None,
+                 congestion_pricing=None, eular_dx=None, attribute=None, user_attribute=None, user_function=None, auto_rename=False):
+        self.W = W
+        self.start_node, self.end_node = W.get_node(start_node), W.get_node(end_node)
+        self.number_of_lanes = int(number_of_lanes)
+        if self.number_of_lanes != number_of_lanes:
+            raise ValueError(f"number_of_lanes must be an integer. Got {number_of_lanes}.")
+        self.signal_group = [signal_group] if isinstance(signal_group, int) else list(signal_group)
+        self.id = len(W.LINKS)
+        self.name = name if name is not None else self.start_node.name + "-" + self.end_node.name
+        if self.name in W.LINKS_NAME_DICT:
+            if auto_rename:
+                self.name = self.name + "_renamed" + "".join(W.rng.choice(list(string.ascii_letters + string.digits), size=8))
+            else:
+                raise ValueError(f"Link name {self.name} already used by another link.")
+        W.LINKS.append(self)
+        W.LINKS_NAME_DICT[self.name] = self
+        self.start_node.outlinks[self.name] = self
+        self.end_node.inlinks[self.name] = self
+        self.attribute, self.user_attribute, self.user_function = attribute, user_attribute, user_function
+        kappa = jam_density if jam_density_per_lane is None else jam_density_per_lane * number_of_lanes
+        # derived FD parameters, uxsim.py:519-532
+        self.length = length
+        self.u = self.free_flow_speed = float(free_flow_speed)
+        self.kappa = self.jam_density = float(kappa)
+        self.jam_density_per_lane = jam_density_per_lane
+        self.tau = W.REACTION_TIME / self.number_of_lanes
+        self.w = 1 / self.tau / self.kappa
+        self.capacity = self.u * self.w * self.kappa / (self.u + self.w)
+        self.delta = 1 / self.kappa
+        self.delta_per_lane = self.delta * self.number_of_lanes
+        self.q_star, self.k_star = self.capacity, self.capacity / self.u
+        self.merge_priority = float(merge_priority)
+        self._capacity_out = self.capacity * 2 if capacity_out is None else float(capacity_out)
+        self._capacity_in = self.capacity * 2 if capacity_in is None else float(capacity_in)
+        self.congestion_pricing = congestion_pricing
+        self._route_choice_penalty = 0
+        self.vehicles, self.vehicles_enter_log = deque(), {}
+        self.tss, self.xss, self.cs, self.ls, self.names = [], [], [], [], []
+        self.eular_dx = eular_dx
+        self.edie_dx = max(self.length / 10, self.u * W.DELTAT) if eular_dx is None else eular_dx
+        eid = W._E.add_link(self.start_node.id, self.end_node.id, self.u, self.kappa, float(length), self.number_of_lanes,
+                            self.merge_priority, -1.0 if capacity_out is None else float(capacity_out),
+                            -1.0 if capacity_in is None else float(capacity_in), self.signal_group)
+        assert eid == self.id
+
+    def __repr__(self):
+        return f"<Link {self.name}>"
+
+    def init_after_tmax_fix(self):
+        self.edie_dt = self.W.EULAR_DT
+        shape = [int(self.W.TMAX / self.edie_dt) + 1, int(self.length / self.edie_dx)]
+        self.k_mat, self.q_mat, self.v_mat = np.zeros(shape), np.zeros(shape), np.zeros(shape)
+        self.tn_mat, self.dn_mat = np.zeros(shape), np.zeros(shape)
+        self.an = self.edie_dt * self.edie_dx
+
+    # time series handed back from the device (uxsim_cpp_wrapper.py:292-333)
+    @property
+    def cum_arrival(self):
+        return self.W._series("cum_arrival")[self.id]
+
+    @property
+    def cum_departure(self):
+        return self.W._series("cum_departure")[self.id]
+
+    @property
+    def traveltime_instant(self):
+        return self.W._series("traveltime_instant")[self.id]
+
+    @property
+    def traveltime_actual(self):
+        return self.W._series("traveltime_actual")[self.id]
+
+    @traveltime_actual.setter
+    def traveltime_actual(self, value):
+        pass
+
+    @property
+    def capacity_out(self):
+        return self._capacity_out
+
+    @capacity_out.setter
+    def capacity_out(self, v):
+        self._capacity_out = float(v)
+        self.W._E.set_link_param(self.id, C.LINK_CAPACITY_OUT, float(v))
+
+    @property
+    def capacity_in(self):
+        return self._capacity_in
+
+    @capacity_in.setter
+    def capacity_in(self, v):
+        self._capacity_in = float(v)
+        self.W._E.set_link_param(self.id, C.LINK_CAPACITY_IN, float(v))
+
+    @property
+    def capacity_in_remain(self):
+        return float(self.W._E.get_array(C.A_LINK_CAPACITY_IN_REMAIN)[self.id])
+
+    @capacity_in_remain.setter
+    def capacity_in_remain(self, v):
+        self.W._E.set_link_param(self.id, C.LINK_CAPACITY_IN_REMAIN, float(v))
+
+    @property
+    def capacity_out_remain(self):
+        return float(self.W._E.get_array(C.A_LINK_CAPACITY_OUT_REMAIN)[self.id])
+
+    @capacity_out_remain.setter
+    def capacity_out_remain(self, v):
+        self.W._E.set_link_param(self.id, C.LINK_CAPACITY_OUT_REMAIN, float(v))
+
+    @property
+    def route_choice_penalty(self):
+        return self._route_choice_penalty
+
+    @route_choice_penalty.setter
+    def route_choice_penalty(self, v):
+        self._route_choice_penalty = v
+        self.W._E.set_link_param(self.id, C.LINK_ROUTE_CHOICE_PENALTY, float(v))
+
+    def get_toll(self, t):
+        return self.congestion_pricing(t) if self.congestion_pricing else self.route_choice_penalty
+
+    # current state
+    @property
+    def num_vehicles(self):
+        return int(self.W._E.get_array(C.A_LINK_NUM_VEHICLES)[self.id]) * self.W.DELTAN
+
+    @property
+    def density(self):
+        return self.num_vehicles / self.length
+
+    @property
+    def speed(self):
+        on = (self.W._veh("link") == self.id) & (self.W._veh("state") == C.VS_RUN)
+        return float(self.W._veh("v")[on].mean()) if on.any() else self.u
+
+    @property
+    def flow(self):
+        return self.density * self.speed
+
+    def _idx(self, t):
+        n = self.W.TSIZE
+        return min(max(int(t / self.W.DELTAT), 0), n - 1)
+
+    def arrival_count(self, t):
+        return self.cum_arrival[self._idx(t)]
+
+    def departure_count(self, t):
+        return self.cum_departure[self._idx(t)]
+
+    def num_vehicles_t(self, t):
+        return self.arrival_count(t) - self.departure_count(t)
+
+    def instant_travel_time(self, t):
+        return self.traveltime_instant[self._idx(t)]
+
+    def actual_travel_time(self, t):
+        return self.traveltime_actual[self._idx(t)]
+
+    def average_speed(self, t):
+        tt = self.actual_travel_time(t)
+        return self.length / tt if tt > 0 else self.u
+
+    def change_free_flow_speed(self, new_value):
+        if new_value >= 0:
+            self.W._E.set_link_param(self.id, C.LINK_VMAX, float(new_value))
+            self.u = self.free_flow_speed = float(new_value)
+            self.w = 1 / self.tau / self.kappa
+            self.capacity = self.u * self.w * self.kappa / (self.u + self.w)
+            self.W._invalidate()
+
+    def change_jam_density(self, new_value):
+        if new_value >= 0:
+            self.W._E.set_link_param(self.id, C.LINK_KAPPA, float(new_value))
+            self.kappa = self.jam_density = float(new_value)
+            self.w = 1 / self.tau / self.kappa
+            self.capacity = self.u * self.w * self.kappa / (self.u + self.w)
+            self.delta = 1 / self.kappa
+            self.delta_per_lane = self.delta * self.number_of_lanes
+            self.W._invalidate()
+
+
+class CudaVehicle:
+    """Lazy proxy of one platoon (uxsim_cpp_wrapper.py:486-725).  All state is read from the world's cached arrays."""
+
+    __slots__ = ("W", "id", "name", "orig", "dest", "color", "attribute", "user_attribute", "user_function", "mode", "dest_list",
+                 "node_event", "route_pref", "links_prefer", "links_avoid", "specified_route", "route_choice_principle", "link_old")
+
+    def __repr__(self):
+        return f"<Vehicle {self.name}>"
+
+    @property
+    def state(self):
+        return _STATE_NAMES[int(self.W._veh("state")[self.id])]
+
+    @property
+    def departure_time(self):
+        return int(self.W._veh("depart_ts")[self.id])
+
+    @property
+    def departure_time_in_second(self):
+        return self.departure_time * self.W.DELTAT
+
+    @property
+    def arrival_time(self):
+        return int(self.W._veh("arrival_ts")[self.id])
+
+    @property
+    def travel_time(self):
+        tt = float(self.W._veh("travel_time")[self.id])
+        return -1 if tt < 0 else tt
+
+    @property
+    def distance_traveled(self):
+        return float(self.W._veh("distance")[self.id])
+
+    @property
+    def flag_trip_aborted(self):
+        return int(self.W._veh("state")[self.id] == C.VS_ABORT)
+
+    @property
+    def link(self):
+        l = int(self.W._veh("link")[self.id])
+        return self.W.LINKS[l] if l >= 0 else None
+
+    @property
+    def x(self):
+        return float(self.W._veh("x")[self.id])
+
+    @property
+    def v(self):
+        return float(self.W._veh("v")[self.id])
+
+    @property
+    def lane(self):
+        return int(self.W._veh("lane")[self.id])
+
+    def enforce_route(self, route, set_avoid=False):
+        links = [self.W.get_link(l) for l in route]
+        self.specified_route = links
+        self.links_prefer = list(links)
+        self.W._E.set_vehicle_links(self.id, 0, [l.id for l in links])
+
+    def get_xy_coords(self, t=-1):
+        l = self.link
+        if l is None:
+            return self.orig.x, self.orig.y
+        r = self.x / l.length if l.length > 0 else 0
+        return (l.start_node.x + r * (l.end_node.x - l.start_node.x), l.start_node.y + r * (l.end_node.y - l.start_node.y))
+
+    def _no_logs(self):
+        raise NotImplementedError("per-platoon logs (log_t, log_x, ...) are not handed back by the CUDA engine yet; "
+                                  "use vehicle_logging_timestep_interval=-1 and the link/vehicle summary arrays")
+
+    log_t = property(_no_logs)
+    log_x = property(_no_logs)
+    log_v = property(_no_logs)
+    log_s = property(_no_logs)
+    log_state = property(_no_logs)
+    log_link = property(_no_logs)
+    log_lane = property(_no_logs)
+    log_t_link = property(_no_logs)
+
+
+class CudaRoute:
+    """uxsim_cpp_wrapper.py:729-765 (CppRoute)."""
+
+    def __init__(self, W, links, name="", trust_input=False):
+        self.W, self.name = W, name
+        self.links = [W.get_link(l) for l in links]
+        if not trust_input:
+            for a, b in zip(self.links[:-1], self.links[1:]):
+                if a.end_node != b.start_node:
+                    raise ValueError(f"Route links not connected: {a.name} -> {b.name}")
+        self.links_name = [l.name for l in self.links]
+
+    def __repr__(self):
+        return f"<Route {self.name}: {self.links_name}>"
+
+    def __iter__(self):
+        return iter(self.links)
+
+    def __len__(self):
+        return len(self.links)
+
+    def __getitem__(self, i):
+        return self.links[i]
+
+    def __eq__(self, other):
+        return self.links_name == other.links_name if hasattr(other, "links_name") else NotImplemented
+
+    def actual_travel_time(self, t, return_details=False):
+        tt, ct, det = 0, t, []
+        for l in self.links:
+            x = l.actual_travel_time(ct)
+            tt += x
+            ct += x
+            det.append(x)
+        return (tt, det) if return_details else tt
+
+
+class CudaRouteChoice:
+    """uxsim_cpp_wrapper.py:768-797 (CppRouteChoice)."""
+
+    def __init__(self, W):
+        self.W = W
+
+    @property
+    def dist(self):
+        n = len(self.W.NODES)
+        return self.W._E.get_array(C.A_ROUTE_DIST).reshape(n, n)
+
+    @property
+    def next(self):
+        n = len(self.W.NODES)
+        return self.W._E.get_array(C.A_ROUTE_NEXT).reshape(n, n)
+
+    @property
+    def route_pref(self):
+        return self.W._E.get_array(C.A_ROUTE_PREF).reshape(len(self.W.NODES), len(self.W.LINKS))
+
+
+class CudaWorld:
+    """uxsim_cpp_wrapper.py:800-1533 (CppWorld), in front of libuxsim_b200.so."""
+
+    def __init__(self, name="", deltan=5, reaction_time=1, duo_update_time=600, duo_update_weight=0.5, duo_noise=0.01,
+                 route_choice_principle="homogeneous_DUO", route_choice_update_gradual=False, instantaneous_TT_timestep_interval=5,
+                 eular_dt=120, eular_dx=100, random_seed=None, print_mode=1, save_mode=1, show_mode=0, show_progress=1,
+                 show_progress_deltat=600, tmax=None, vehicle_logging_timestep_interval=1, reduce_memory_delete_vehicle_route_pref=False,
+                 hard_deterministic_mode=False, no_cyclic_routing=False, adjust_node_capacity=False, meta_data=None,
+                 user_attribute=None, user_function=None, threads=1, num_replicas=1, device=-1):
+        self.W = self
+        self.rng = np.random.default_rng(seed=random_seed)
+        self.random_seed = random_seed
+        self.TMAX, self.DELTAN, self.REACTION_TIME = tmax, deltan, reaction_time
+        self.DUO_UPDATE_TIME, self.DUO_UPDATE_WEIGHT, self.DUO_NOISE, self.EULAR_DT = duo_update_time, duo_update_weight, duo_noise, eular_dt
+        self.DELTAT = self.REACTION_TIME * self.DELTAN
+        self.DELTAT_ROUTE = max(1, int(self.DUO_UPDATE_TIME / self.DELTAT))
+        self.VEHICLES, self.VEHICLES_LIVING, self.VEHICLES_RUNNING = OrderedDict(), OrderedDict(), OrderedDict()
+        self.NODES, self.LINKS, self.NODES_NAME_DICT, self.LINKS_NAME_DICT = [], [], {}, {}
+        self.vehicle_logging_timestep_interval = vehicle_logging_timestep_interval
+        self.route_choice_principle = route_choice_principle
+        self.route_choice_update_gradual = route_choice_update_gradual
+        self.instantaneous_TT_timestep_interval = min(int(instantaneous_TT_timestep_interval), self.DELTAT_ROUTE)
+        self.show_progress = show_progress
+        self.show_progress_deltat_timestep = int(show_progress_deltat / self.DELTAT)
+        self.name = name
+        self.hard_deterministic_mode, self.no_cyclic_routing, self.adjust_node_capacity = hard_deterministic_mode, no_cyclic_routing, adjust_node_capacity
+        self.meta_data = meta_data if meta_data is not None else {}
+        self.network_info, self.demand_info = ddict(list), ddict(list)
+        self.finalized = 0
+        self.world_start_time = time.time()
+        self.print_mode, self.save_mode, self.show_mode = print_mode, save_mode, show_mode
+        self.print = print if print_mode else (lambda *a, **k: None)
+        self.user_attribute, self.user_function = user_attribute, user_function
+        self.num_threads = threads
+        seed = random_seed if random_seed is not None else int(np.random.default_rng().integers(0, 2**31 - 1))
+        # the horizon is fixed at finalize time (set_t_max), like CppWorld._ensure_cpp_world (878-898)
+        self._E = C.EngineWorld(
+            C.load_product(), t_max=float(tmax if tmax is not None else 7200), delta_n=float(deltan), tau=float(reaction_time),
+            duo_update_time=float(duo_update_time), duo_update_weight=float(duo_update_weight), route_choice_uncertainty=float(duo_noise),
+            random_seed=int(seed), vehicle_log_mode=False, hard_deterministic_mode=hard_deterministic_mode,
+            route_choice_update_gradual=route_choice_update_gradual, no_cyclic_routing=no_cyclic_routing,
+            adjust_node_capacity=adjust_node_capacity, instantaneous_TT_timestep_interval=int(instantaneous_TT_timestep_interval),
+            num_replicas=num_replicas, device=device)
+        self._cache = {}
+        self._veh_by_index = []
+        self._simulation_done = False
+        self.T, self.TIME = 0, 0
+
+    # ---- result cache ------------------------------------------------------------------------------------
+    def _invalidate(self):
+        self._cache = {}
+
+    _SERIES = {"cum_arrival": C.A_CUM_ARRIVAL, "cum_departure": C.A_CUM_DEPARTURE, "traveltime_instant": C.A_TRAVELTIME_INSTANT,
+               "traveltime_actual": C.A_TRAVELTIME_ACTUAL, "signal_log": C.A_SIGNAL_LOG}
+    _VEH = {"state": C.A_VEH_STATE, "arrival_ts": C.A_VEH_ARRIVAL_TS, "depart_ts": C.A_VEH_DEPART_TS, "travel_time": C.A_VEH_TRAVEL_TIME,
+            "distance": C.A_VEH_DISTANCE, "link": C.A_VEH_LINK, "x": C.A_VEH_X, "v": C.A_VEH_V, "lane": C.A_VEH_LANE}
+
+    def _series(self, key):
+        if key not in self._cache:
+            rows = len(self.NODES) if key == "signal_log" else len(self.LINKS)
+            self._cache[key] = self._E.get_array(self._SERIES[key]).reshape(rows, self.TSIZE)
+        return self._cache[key]
+
+    def _veh(self, key):
+        k = "veh_" + key
+        if k not in self._cache:
+            self._cache[k] = self._E.get_array(self._VEH[key])
+        return self._cache[k]
+
+    # ---- scenario definition -----------------------------------------------------------------------------
+    def addNode(self, name, x, y, signal=[0], signal_offset=0, signal_offset_old=None, flow_capacity=None, number_of_lanes=None,
+                auto_rename=False, attribute=None, user_attribute=None, user_function=None):
+        return CudaNode(self, name, x, y, signal=signal, signal_offset=signal_offset, signal_offset_old=signal_offset_old,
+                        flow_capacity=flow_capacity, number_of_lanes=number_of_lanes, auto_rename=auto_rename, attribute=attribute,
+                        user_attribute=user_attribute, user_function=user_function)
+
+    def addLink(self, name, start_node, end_node, length, free_flow_speed=20, jam_density=0.2, jam_density_per_lane=None,
+                number_of_lanes=1, merge_priority=1, signal_group=[0], capacity_out=None, capacity_in=None, congestion_pricing=None,
+                eular_dx=None, attribute=None, user_attribute=None, user_function=None, auto_rename=False):
+        return CudaLink(self, name, start_node, end_node, length, free_flow_speed=free_flow_speed, jam_density=jam_density,
+                        jam_density_per_lane=jam_density_per_lane, number_of_lanes=number_of_lanes, merge_priority=merge_priority,
+                        signal_group=signal_group, capacity_out=capacity_out, capacity_in=capacity_in, congestion_pricing=congestion_pricing,
+                        eular_dx=eular_dx, attribute=attribute, user_attribute=user_attribute, user_function=user_function, auto_rename=auto_rename)
+
+    def _register(self, n_new, orig, dest, attribute=None):
+        colors = self.rng.random(size=(n_new, 3))
+        rcp = self.route_choice_principle
+        for j in range(n_new):
+            v = CudaVehicle.__new__(CudaVehicle)
+            v.W, v.id = self, len(self._veh_by_index)
+            v.name = str(v.id)
+            v.orig, v.dest = orig, dest
+            v.color = (float(colors[j, 0]), float(colors[j, 1]), float(colors[j, 2]))
+            v.attribute, v.user_attribute, v.user_function = attribute, None, None
+            v.mode, v.dest_list, v.node_event, v.route_pref = "single_trip", [], {}, {}
+            v.links_prefer, v.links_avoid, v.specified_route, v.route_choice_principle, v.link_old = [], [], None, rcp, None
+            self.VEHICLES[v.name] = v
+            self.VEHICLES_LIVING[v.name] = v
+            self._veh_by_index.append(v)
+
+    def addVehicle(self, orig, dest, departure_time, name=None, route_pref=None, route_choice_principle=None, mode="single_trip",
+                   links_prefer=[], links_avoid=[], trip_abort=1, departure_time_is_time_step=0, attribute=None, user_attribute=None,
+                   user_function=None, auto_rename=False, direct_call=True):
+        if mode == "taxi":
+            raise NotImplementedError("taxi mode is not supported in CUDA mode")  # as cpp mode, uxsim_cpp_wrapper.py:929-931
+        o, d = self.get_node(orig), self.get_node(dest)
+        ts = int(departure_time) if departure_time_is_time_step else int(departure_time / self.DELTAT)
+        self._E.add_vehicles([o.id], [d.id], [ts])
+        self._register(1, o, d, attribute)
+        v = self._veh_by_index[-1]
+        if name is not None:
+            name = str(name)
+            if name in self.VEHICLES and name != v.name:
+                if not auto_rename:
+                    raise ValueError(f"Vehicle name {name} already used by another vehicle. Please specify a unique name.")
+                name = name + "_renamed" + "".join(self.rng.choice(list(string.ascii_letters + string.digits), size=8))
+            self.VEHICLES.pop(v.name), self.VEHICLES_LIVING.pop(v.name)
+            v.name = name
+            self.VEHICLES[name] = v
+            self.VEHICLES_LIVING[name] = v
+        if links_prefer:
+            v.links_prefer = [self.get_link(l) for l in links_prefer]
+            self._E.set_vehicle_links(v.id, 1, [l.id for l in v.links_prefer])
+        if links_avoid:
+            v.links_avoid = [self.get_link(l) for l in links_avoid]
+            self._E.set_vehicle_links(v.id, 2, [l.id for l in v.links_avoid])
+        v.user_attribute, v.user_function = user_attribute, user_function
+        self._invalidate()
+        return v
+
+    def adddemand(self, orig, dest, t_start, t_end, flow=-1, volume=-1, attribute=None, direct_call=True):
+        """uxsim.py:2021-2053; the FP64 accumulation happens in ux_add_demand (traffi.cpp:1910-1941)."""
+        if volume > 0:
+            flow = volume / (t_end - t_start)
+        o, d = self.get_node(orig), self.get_node(dest)
+        n = self._E.add_demand(o.id, d.id, float(t_start), float(t_end), float(flow))
+        self._register(n, o, d, attribute)
+        self.demand_info["adddemand"].append(dict(orig=o.name, dest=d.name, t_start=t_start, t_end=t_end, flow=flow, volume=volume))
+        self._invalidate()
+
+    def adddemand_point2point(self, x_orig, y_orig, x_dest, y_dest, t_start, t_end, flow=-1, volume=-1, attribute=None, direct_call=True):
+        self.adddemand(self.get_nearest_node(x_orig, y_orig), self.get_nearest_node(x_dest, y_dest), t_start, t_end, flow, volume, attribute)
+
+    def adddemand_area2area(self, x_orig, y_orig, radious_orig, x_dest, y_dest, radious_dest, t_start, t_end, flow=-1, volume=-1,
+                            attribute=None, direct_call=True):
+        warnings.warn("`adddemand_area2area()` is not recommended. Use `adddemand_area2area2()`.", FutureWarning)
+        origs = [o for o in self.get_nodes_in_area(x_orig, y_orig, radious_orig) if o.outlinks] or [self.get_nearest_node(x_orig, y_orig)]
+        dests = [d for d in self.get_nodes_in_area(x_dest, y_dest, radious_dest) if d.inlinks] or [self.get_nearest_node(x_dest, y_dest)]
+        self._nodes2nodes(origs, dests, t_start, t_end, flow, volume, attribute)
+
+    def adddemand_nodes2nodes(self, origs, dests, t_start, t_end, flow=-1, volume=-1, attribute=None, direct_call=True):
+        warnings.warn("`adddemand_nodes2nodes()` is not recommended. Use `adddemand_nodes2nodes2()`.", FutureWarning)
+        origs = [self.get_node(o) for o in origs if self.get_node(o).outlinks]
+        dests = [self.get_node(d) for d in dests if self.get_node(d).inlinks]
+        self._nodes2nodes(origs, dests, t_start, t_end, flow, volume, attribute)
+
+    def _nodes2nodes(self, origs, dests, t_start, t_end, flow, volume, attribute):
+        if flow != -1:
+            flow = flow / (len(origs) * len(dests))
+        if volume != -1:
+            volume = volume / (len(origs) * len(dests))
+        for o in origs:
+            for d in dests:
+                self.adddemand(o, d, t_start, t_end, flow, volume, attribute)
+
+    def adddemand_area2area2(self, x_orig, y_orig, radious_orig, x_dest, y_dest, radious_dest, t_start, t_end, flow=-1, volume=-1,
+                             attribute=None, direct_call=True):
+        origs = [o for o in self.get_nodes_in_area(x_orig, y_orig, radious_orig) if o.outlinks] or [self.get_nearest_node(x_orig, y_orig)]
+        dests = [d for d in self.get_nodes_in_area(x_dest, y_dest, radious_dest) if d.inlinks] or [self.get_nearest_node(x_dest, y_dest)]
+        self.adddemand_nodes2nodes2(origs, dests, t_start, t_end, flow, volume, attribute)
+
+    def adddemand_nodes2nodes2(self, origs, dests, t_start, t_end, flow=-1, volume=-1, attribute=None, direct_call=True):
+        """uxsim.py:2262-2310: random OD assignment, then one platoon per draw (bulk-registered)."""
+        origs = [self.get_node(o) for o in origs if self.get_node(o).outlinks]
+        dests = [self.get_node(d) for d in dests if self.get_node(d).inlinks]
+        if flow >= 0 and volume == -1:
+            volume = flow * (t_end - t_start)
+        size = int(volume / self.DELTAN)
+        ts = np.linspace(t_start, t_end, size)
+        os_ = self.rng.choice(origs, size=size)
+        ds_ = self.rng.choice(dests, size=size)
+        for t, o, d in zip(ts, os_, ds_):
+            d2 = d if o != d else self.rng.choice([dd for dd in dests if dd != d])
+            self.addVehicle(o, d2, t, attribute=attribute)
+
+    # ---- simulation ----------------------------------------------------------------------------------------
+    def finalize_scenario(self, tmax=None):
+        """uxsim_cpp_wrapper.py:1087-1121."""
+        if self.TMAX is None:
+            if tmax is None:
+                m = self._E.get_int(C.I_MAX_DEPART_TS) * self.DELTAT
+                self.TMAX = (m // 1800 + 2) * 1800
+            else:
+                self.TMAX = tmax
+        self._E.set_t_max(float(self.TMAX))
+        self.T, self.TIME = 0, 0
+        self.TSIZE = int(self.TMAX / self.DELTAT)
+        self.Q_AREA = ddict(lambda: np.zeros(int(self.TMAX / self.EULAR_DT)))
+        self.K_AREA = ddict(lambda: np.zeros(int(self.TMAX / self.EULAR_DT)))
+        for l in self.LINKS:
+            l.init_after_tmax_fix()
+            if l.congestion_pricing is not None:
+                self._E.set_toll_timeseries(l.id, [float(l.congestion_pricing(t * self.DELTAT)) for t in range(self.TSIZE)])
+        self.ADJ_MAT = np.zeros([len(self.NODES), len(self.NODES)])
+        self.ADJ_MAT_LINKS, self.NODE_PAIR_LINKS = dict(), dict()
+        for l in self.LINKS:
+            self.ADJ_MAT[l.start_node.id, l.end_node.id] = 1
+            self.ADJ_MAT_LINKS[l.start_node.id, l.end_node.id] = l
+            self.NODE_PAIR_LINKS[l.start_node.name, l.end_node.name] = l
+        self._E.initialize_adj_matrix()
+        self.ROUTECHOICE = CudaRouteChoice(self)
+        self.analyzer = _make_analyzer(self)
+        self.finalized = 1
+        self.sim_start_time = time.time()
+        self.print("simulating...")
+
+    def exec_simulation(self, until_t=None, duration_t=None, duration_t2=None):
+        """uxsim_cpp_wrapper.py:1165-1202 -- same end-step arithmetic, one FFI crossing."""
+        if not self.finalized:
+            self.finalize_scenario()
+        start_ts = self.T
+        if until_t is not None:
+            end_ts = int(until_t / self.DELTAT)
+        elif duration_t2 is not None:
+            end_ts = start_ts + int(duration_t2 / self.DELTAT) - 1
+        elif duration_t is not None:
+            end_ts = start_ts + int(duration_t / self.DELTAT)
+        else:
+            end_ts = self.TSIZE
+        end_ts = min(end_ts, self.TSIZE)
+        if start_ts == end_ts == self.TSIZE:
+            self.simulation_terminated()
+            return 1
+        if end_ts < start_ts:
+            raise Exception("exec_simulation error: Simulation duration is not positive. Check until_t or duration_t or duration_t2")
+        self._E.main_loop(-1.0, float(end_ts * self.DELTAT))
+        self._invalidate()
+        self.T = self._E.get_int(C.I_TIMESTEP)
+        self.TIME = self.T * self.DELTAT
+        self._sync_registries()
+        if self.T >= self.TSIZE:
+            self.simulation_terminated()
+            return 1
+        return 0
+
+    def _sync_registries(self):
+        st = self._veh("state")
+        self.VEHICLES_LIVING = OrderedDict((v.name, v) for v, s in zip(self._veh_by_index, st) if s < C.VS_END)
+        self.VEHICLES_RUNNING = OrderedDict((v.name, v) for v, s in zip(self._veh_by_index, st) if s == C.VS_RUN)
+
+    def simulation_terminated(self):
+        self.print(" simulation finished")
+        self._simulation_done = True
+        self.analyzer.basic_analysis()
+
+    def check_simulation_ongoing(self):
+        return True if not self.finalized else self.T <= self.TSIZE - 1
+
+    # ---- lookups ---------------------------------------------------------------------------------------------
+    def get_node(self, node):
+        if node is None or isinstance(node, CudaNode):
+            return node
+        if isinstance(node, (str, np.str_)):
+            return self.NODES_NAME_DICT.get(str(node))
+        if hasattr(node, "name"):
+            return self.NODES_NAME_DICT.get(node.name)
+        raise Exception(f"'{node}' is not Node in this World")
+
+    def get_link(self, link):
+        if link is None:
+            return None
+        if isinstance(link, CudaLink):
+            return link if link.W is self else self.LINKS_NAME_DICT.get(link.name)
+        if isinstance(link, (str, np.str_)):
+            return self.LINKS_NAME_DICT.get(str(link))
+        if hasattr(link, "name"):
+            return self.LINKS_NAME_DICT.get(link.name)
+        raise Exception(f"'{link}' is not Link in this World")
+
+    def get_nearest_node(self, x, y):
+        return min(self.NODES, key=lambda n: (n.x - x) ** 2 + (n.y - y) ** 2) if self.NODES else None
+
+    def get_nodes_in_area(self, x, y, r):
+        return [n for n in self.NODES if (n.x - x) ** 2 + (n.y - y) ** 2 < r ** 2]
+
+    def defRoute(self, links, name="", trust_input=False):
+        return CudaRoute(self, links, name=name, trust_input=trust_input)
+
+    # ---- I/O (uxsim_cpp_wrapper.py:1435-1472) ---------------------------------------------------------------
+    def load_scenario_from_csv(self, fname_node, fname_link, fname_demand, tmax=None):
+        self.generate_Nodes_from_csv(fname_node)
+        self.generate_Links_from_csv(fname_link)
+        self.generate_demand_from_csv(fname_demand)
+        if tmax is not None:
+            self.TMAX = tmax
+
+    def generate_Nodes_from_csv(self, fname):
+        with open(fname) as f:
+            for r in csv.reader(f):
+                if r[1] != "x":
+                    self.addNode(r[0], float(r[1]), float(r[2]))
+
+    def generate_Links_from_csv(self, fname):
+        with open(fname) as f:
+            for r in csv.reader(f):
+                if r[3] != "length":
+                    self.addLink(r[0], r[1], r[2], length=float(r[3]), free_flow_speed=float(r[4]), jam_density=float(r[5]), merge_priority=float(r[6]))
+
+    def generate_demand_from_csv(self, fname):
+        with open(fname) as f:
+            for r in csv.reader(f):
+                if r[2] != "start_t":
+                    if len(r) > 5 and r[5] != "":
+                        self.adddemand(r[0], r[1], float(r[2]), float(r[3]), float(r[4]), float(r[5]))
+                    else:
+                        self.adddemand(r[0], r[1], float(r[2]), float(r[3]), float(r[4]))
+
+    def save_scenario(self, fname, network=True, demand=True):
+        raise NotImplementedError("save_scenario is not supported in CUDA mode (as in C++ mode).")
+
+    def load_scenario(self, fname, network=True, demand=True):
+        raise NotImplementedError("load_scenario is not supported in CUDA mode (as in C++ mode).")
+
+    def copy(self):
+        raise NotImplementedError("copy() is not supported in CUDA mode (as in C++ mode)")
+
+    def save(self, fname):
+        raise NotImplementedError("save() is not supported in CUDA mode (as in C++ mode)")
+
+    def on_time(self, time_val):
+        return self.T == int(time_val / self.DELTAT)
+
+    def change_print_mode(self, print_mode):
+        self.print_mode = print_mode
+        self.print = print if print_mode else (lambda *a, **k: None)
+
+    def print_scenario_stats(self):
+        print("simulation setting:" if self.finalized else "simulation setting (not finalized):")
+        print(" scenario name:", self.name)
+        print(" simulation duration:\t", self.TMAX, "s")
+        print(" number of vehicles:\t", len(self.VEHICLES) * self.DELTAN, "veh")
+        print(" total road length:\t", sum(l.length for l in self.LINKS), "m")
+        print(" timestep size:\t", self.DELTAT, "s")
+        print(" platoon size:\t\t", self.DELTAN, "veh")
+        print(" number of platoons:\t", len(self.VEHICLES))
+        print(" number of links:\t", len(self.LINKS))
+        print(" number of nodes:\t", len(self.NODES))
+
+
+def _make_analyzer(W):
+    try:
+        from uxsim.analyzer import Analyzer  # the reference's own, unmodified, when it is installed
+
+        return Analyzer(W)
+    except Exception:
+        from .analysis import BasicAnalyzer
+
+        return BasicAnalyzer(W)
+
+
+class World:
+    """Factory with the reference's selection idiom: ``World(..., cuda=True)`` -> :class:`CudaWorld`
+    (uxsim.py:1671-1675 does the same for ``cpp=True``).  Without ``cuda=True`` this package has nothing to offer:
+    it is a backend, not a second CPU engine."""
+
+    def __new__(cls, *args, cuda=False, cpp=False, **kwargs):
+        if cuda:
+            return CudaWorld(*args, **kwargs)
+        raise NotImplementedError("uxsim_b200 only provides the CUDA engine: use World(..., cuda=True), or the reference package "
+                                  "`uxsim` for its Python / C++ engines.")

@@ -56,3 +56,16 @@ def summary_stats(E, replica=0):
     L, T = E.get_int(C.I_NUM_LINKS), E.get_int(C.I_TOTAL_TIMESTEPS)
     flow = E.get_array(C.A_CUM_ARRIVAL, replica).reshape(L, T)[:, -1]
     return int(done.sum()), float(tt[done].mean()) if done.any() else 0.0, flow
+
+
+LOG_FIELDS = [(k[2:].lower(), getattr(C, k)) for k in dir(C) if k.startswith(("A_LOG_", "A_LTL_", "A_ENTER_"))]
+
+
+def compare_logs(Ea, Eb, replica_a=0, replica_b=0):
+    """Per-platoon logs in the reference's compact flat layout; returns the names of differing arrays."""
+    bad = []
+    for name, what in LOG_FIELDS:
+        x, y = Ea.get_array(what, replica_a), Eb.get_array(what, replica_b)
+        if x.shape != y.shape or not np.array_equal(x, y):
+            bad.append(name)
+    return bad

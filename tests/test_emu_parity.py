@@ -7,7 +7,7 @@ import pytest
 from uxsim_b200 import _capi as C
 from uxsim_b200 import scenario as S
 
-from parity import compare_engines, run_pair
+from parity import compare_engines, compare_logs, run_pair
 
 CASES = [
     ("1link", S.straight_1link, None), ("spillback", S.straight_3link_spillback, None), ("signal", S.straight_2link_signal, None),
@@ -35,3 +35,18 @@ def test_emulated_chicago_levels(emu_api, oracle_api):
     Ee, Eo = run_pair(S.chicago_sketch(seed=0), emu_api, oracle_api, until=[1500])
     assert Ee.get_int(C.I_TRANSFER_LEVELS) == 4
     assert compare_engines(Ee, Eo) == []
+
+
+LOG_CASES = [("spillback", S.straight_3link_spillback), ("3lane", S.multilane_3lane), ("lane_drop", S.lane_drop_2to1), ("dead_end", S.dead_end),
+             ("merge_stochastic", lambda: S.merge_y(hard_deterministic_mode=False, random_seed=3)),
+             ("grid6_signals", lambda: S.grid(n=6, seed=5, tmax=3000, demand_t=1200, signals=True))]
+
+
+@pytest.mark.parametrize("name,mk", LOG_CASES, ids=[c[0] for c in LOG_CASES])
+def test_emulated_vehicle_logs_match_oracle(name, mk, emu_api, oracle_api):
+    """Full per-platoon logs (log_t/x/v/s/lane/link/state, log_t_link, enter log), mid-run and at the end."""
+    sc = mk()
+    Ee, Eo = run_pair(sc, emu_api, oracle_api, until=[0.4 * sc.tmax()], vehicle_logging_timestep_interval=1)
+    assert compare_logs(Ee, Eo) == []
+    Ee.main_loop(), Eo.main_loop()
+    assert compare_logs(Ee, Eo) == [] and compare_engines(Ee, Eo) == []

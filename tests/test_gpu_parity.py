@@ -9,7 +9,7 @@ import pytest
 from uxsim_b200 import _capi as C
 from uxsim_b200 import scenario as S
 
-from parity import compare_engines, run_pair, summary_stats
+from parity import compare_engines, compare_logs, run_pair, summary_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -117,3 +117,21 @@ def test_error_codes(cuda_api):
         E.main_loop(duration_t=10, until_t=10)
     with pytest.raises(IndexError):
         E.set_link_param(99, C.LINK_VMAX, 10.0)
+
+
+LOG_CASES = [("spillback", S.straight_3link_spillback), ("3lane", S.multilane_3lane), ("lane_drop", S.lane_drop_2to1), ("dead_end", S.dead_end),
+             ("short_chain", S.short_links_chain), ("merge_stochastic", lambda: S.merge_y(hard_deterministic_mode=False, random_seed=3)),
+             ("grid6_signals", lambda: S.grid(n=6, seed=5, tmax=3000, demand_t=1200, signals=True)), ("siouxfalls", lambda: S.sioux_falls(seed=1)),
+             ("chicago_dn30", lambda: S.chicago_sketch(seed=0))]
+
+
+@pytest.mark.parametrize("name,mk", LOG_CASES, ids=[c[0] for c in LOG_CASES])
+def test_vehicle_logs_bit_exact(name, mk, cuda_api, oracle_api):
+    """vehicle_logging_timestep_interval=1 (the API default): every per-platoon log array in the reference's compact flat
+    layout (traffi.cpp:1990-2081), log_t_link and the enter log, mid-run and at the end."""
+    sc = mk()
+    Eg, Eo = run_pair(sc, cuda_api, oracle_api, until=[0.4 * sc.tmax()], vehicle_logging_timestep_interval=1)
+    assert compare_logs(Eg, Eo) == []
+    Eg.main_loop(), Eo.main_loop()
+    assert compare_logs(Eg, Eo) == [] and compare_engines(Eg, Eo) == []
+    assert Eg.get_int(C.I_LOG_ENTRIES) == Eo.get_int(C.I_LOG_ENTRIES)

@@ -90,3 +90,23 @@ def test_unsupported_like_cpp_mode(cuda_api):
             f()
     with pytest.raises(ValueError):
         W.addNode("a", 0, 0)
+
+
+@pytest.mark.gpu
+def test_vehicle_log_properties(cuda_api):
+    """CudaVehicle.log_* mirror CppVehicle (uxsim_cpp_wrapper.py:575-664); the chunked-exec known answer of
+    test_verification_straight_road.py:940-989: after 1000 s a platoon logged x=1600 at t=995 and sits at x=1800... here: free flow."""
+    W = uxsim_b200.World(cuda=True, deltan=5, tmax=1200, print_mode=0, save_mode=0, random_seed=0)
+    W.addNode("o", 0, 0), W.addNode("d", 1, 0)
+    link = W.addLink("l", "o", "d", length=2000, free_flow_speed=20)
+    veh = W.addVehicle("o", "d", 100)
+    W.exec_simulation()
+    assert veh.state == "end" and veh.travel_time == 100.0
+    assert len(veh.log_t) == len(veh.log_x) == len(veh.log_state) == len(veh.log_link)
+    run = [i for i, s in enumerate(veh.log_state) if s == "run"]
+    assert veh.log_x[run[0]] == 0 and all(veh.log_v[i] == 20.0 for i in run)
+    assert veh.log_link[run[0]] is link and veh.log_state[-1] == "end" and veh.log_state[0] == "home"
+    assert [x[1] for x in veh.log_t_link] == ["home", link, "end"]
+    route, ts = veh.traveled_route()
+    assert route.links == [link] and len(ts) == 2
+    assert list(link.vehicles_enter_log.values()) == [veh]

@@ -50,7 +50,7 @@
 
 enum { LF_SEES_POPS = 1, LF_END_LT_START = 2 };            // link flags
 enum { VF_WAIT_END = 1, VF_ABORT = 2, VF_CAND = 4 };       // vehicle flags
-enum { DERR_NONE = 0, DERR_RING_FULL = 1, DERR_ROUTE_EXHAUSTED = 2, DERR_ROUTE_INCONSISTENT = 3, DERR_AVOID_ALL = 4 };
+enum { DERR_NONE = 0, DERR_RING_FULL = 1, DERR_ROUTE_EXHAUSTED = 2, DERR_ROUTE_INCONSISTENT = 3, DERR_AVOID_ALL = 4, DERR_LOG_FULL = 5 };
 
 // ---------------------------------------------------------------------------------------------------
 // device world
@@ -66,7 +66,7 @@ struct DevWorld {
     const int *l_start, *l_end, *l_lanes, *l_rcap, *l_flags, *l_sg_off, *l_sg, *l_pair_first, *l_pair_off, *l_pair_list;
     const long long *l_roff;
     const double *l_length, *l_vmax, *l_dpl_dn, *l_udt, *l_cap_out, *l_cap_in, *l_mp, *l_penalty, *l_toll;
-    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes, *lvl_level;
+    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes, *lvl_level, *dep_off, *dep_list;
     int n_levels;
     const double *n_sig, *n_fc;
     const int *v_orig, *v_dest, *v_depart_ts, *gen_off, *gen_list, *gen_ts, *dest_row, *row_dest;
@@ -85,12 +85,16 @@ struct DevWorld {
     int *v_state, *v_next, *v_link, *v_arr_ts, *v_trav;
     double *v_mr, *v_atl, *v_tt, *v_dist, *v_entry_x;
     unsigned char *v_flags;
+    // per-platoon per-step RUN records (Vehicle::log_data, traffi.cpp:1060-1110), appended in arrival order
+    int *v_gen_ts, *v_end_ts; unsigned char *v_end_kind;  // step of generation / of trip end, 1 = ended in update, 2 = in transfer
+    int *lg_vid, *lg_t, *lg_link, *lg_lane; double *lg_x, *lg_v, *lg_s;
+    unsigned long long *lg_count; long long lg_cap;
     unsigned *v_visited;
     double *cum_arr, *cum_dep, *tt_inst, *ev_tt;
     int *ev_ord, *sig_log;
     double *pref, *rdist, *pair_cost;
     int *pref_active, *has_path, *rnext;
-    int *lvl_done;  // per dependency level: transfer warps finished in the current step
+    int *node_done;  // per node: (timestep + 1) of the last finished transfer -- monotone, so it never needs a reset
     int *err;     // [0] code, [1] info
     int *t_base;  // timestep at the start of the running graph
 };
@@ -445,6 +449,7 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
                 if (G.o_win_n[q] < lanes) { G.w_x[w0 + G.o_win_n[q]] = 0.0; G.o_win_n[q] += 1; }
                 else { for (int e = w0; e < w0 + lanes - 1; e++) G.w_x[e] = G.w_x[e + 1]; G.w_x[w0 + lanes - 1] = 0.0; }
                 W.v_state[vid] = UX_VS_RUN;
+                if (W.log_mode) W.v_gen_ts[vid] = t;
                 W.v_atl[vid] = (double)t * W.dt;
                 W.v_entry_x[vid] = 0.0;
                 mark_entered(W, vid, ol);
@@ -463,7 +468,6 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
         WARP_SYNC();
     }
     if (lane != 0) return;
-    if (n == 0) for (int lv = 0; lv < W.n_levels; lv++) W.lvl_done[lv] = 0;
     W.gen_avail[n] = av;
     for (int k = 0; k < nout; k++) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; }
     // ---- signal
@@ -536,6 +540,7 @@ UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem &S, int p, int t) {  // Ve
     W.v_link[vid] = -1;
     if (S.p_flag[p] & VF_ABORT) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
     else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)S.p_dts[p] * W.dt; }
+    if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 2; }
     W.v_flags[vid] = 0;
     S.popped[ii] += 1;
 }
@@ -848,8 +853,8 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
 }
 
 // All dependency levels run in ONE launch: warps are ordered by (level, node id), and a warp of level k > 0 waits
-// until every warp of level k-1 has finished this step (they are dispatched earlier -- the same forward-progress
-// assumption as decoupled look-back scans).  Levels exist only for links short enough that the serial id-ordered
+// until the specific lower-level nodes it depends on have finished this step (they are dispatched earlier -- the
+// same forward-progress assumption as decoupled look-back scans).  Levels exist only for links short enough that the serial id-ordered
 // visibility of Node.transfer matters (DESIGN.md "transfer order"); most networks have a single level and never wait.
 __global__ void __launch_bounds__(32 * XFER_WARPS) k_transfer(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
@@ -860,23 +865,26 @@ __global__ void __launch_bounds__(32 * XFER_WARPS) k_transfer(const DevWorld *wo
     XferSmem &S = sm_all[(threadIdx.x >> 5) % XFER_WARPS];
     int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
     int lvl = W.n_levels > 1 ? W.lvl_level[warp] : 0;
-    if (lvl > 0) {
-        int need = W.lvl_off[lvl] - W.lvl_off[lvl - 1];
-        WARP_FOR(lane) if (lane == 0) {
-            volatile int *done = W.lvl_done + (lvl - 1);
+    if (lvl > 0) {  // wait for exactly the nodes whose pops this node must see (end nodes of its SEES_POPS out-links)
+        WARP_FOR(lane) {
+            for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
+                volatile int *done = W.node_done + W.dep_list[q];
 #ifdef UX_EMU
-            if (*done < need) { dev_error(W, DERR_RING_FULL, -1); }
+                if (*done < t + 1) dev_error(W, DERR_RING_FULL, -1);
 #else
-            while (*done < need) __nanosleep(64);
-            __threadfence();
+                while (*done < t + 1) __nanosleep(32);
 #endif
+            }
         }
+#ifndef UX_EMU
+        __threadfence();
+#endif
         WARP_SYNC();
     }
     xfer_node(W, S, n, t);
     if (W.n_levels > 1) {
         WARP_SYNC();
-        WARP_FOR(lane) if (lane == 0) { __threadfence(); atomicAdd(W.lvl_done + lvl, 1); }
+        WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)(W.node_done + n)) = t + 1; }
     }
 }
 
@@ -887,12 +895,44 @@ __global__ void __launch_bounds__(32 * XFER_WARPS) k_transfer(const DevWorld *wo
 //     has a leader on the same link), so their trip end / abort / next-link choice is evaluated by one lane per
 //     position in parallel and only the "is it the front" prefix (traffi.cpp:861, 869) is resolved serially.
 // ---------------------------------------------------------------------------------------------------
+// One RUN log record (Vehicle::log_data traffi.cpp:1060-1110) for the platoon at queue position `pos` of link l, taken
+// BEFORE this step's move.  The spacing follows the reference's id-ordered emulation (1081-1095): a lower-id leader is
+// seen after its move (or not at all if it just ended its trip), a higher-id leader before its move.
+UX_DEV void log_run_record(const DevWorld &W, int l, int t, int cur, int hd, int n, int pos, int cap, long long o, int lanes,
+                           double len, double udt, double dpl, int n_ended, int relabel_pushes) {
+    size_t C = (size_t)W.C;
+    const double *Xc = W.X + (size_t)cur * C + o;
+    int p = ring_slot(hd, pos, cap);
+    int vid = W.VID[o + p];
+    double x = Xc[p], v = W.V[o + p];
+    int lane = pos < relabel_pushes ? pos % lanes : W.LANE[o + p];
+    double s = -1.0;
+    if (pos >= lanes) {
+        int pl = pos - lanes, lp = ring_slot(hd, pl, cap);
+        int lvid = W.VID[o + lp];
+        double xl = Xc[lp];
+        if (lvid < vid) {
+            if (pl >= n_ended) {  // leader still on the link after its own update: its post-move position
+                double xn = xl + udt;
+                if (pl >= lanes) { double gap = Xc[ring_slot(hd, pl - lanes, cap)] - dpl; if (gap < xl) gap = xl; if (xn > gap) xn = gap; }
+                if (xn < xl) xn = xl;
+                if (xn > len) xn = len;
+                s = xn - x;
+            }
+        } else s = xl - x;
+    }
+    unsigned long long idx = atomicAdd(W.lg_count, 1ull);
+    if ((long long)idx >= W.lg_cap) { dev_error(W, DERR_LOG_FULL, l); return; }
+    W.lg_vid[idx] = vid; W.lg_t[idx] = t; W.lg_link[idx] = l; W.lg_lane[idx] = lane; W.lg_x[idx] = x; W.lg_v[idx] = v; W.lg_s[idx] = s;
+}
+
 #define UX_MAXLANE 64
 #define UPD_WARPS 8
 struct HeadSmem {
     int vid[UX_MAXLANE], next[UX_MAXLANE], dts[UX_MAXLANE];
     unsigned char kind[UX_MAXLANE];  // 0 not at end, 1 trip end, 2 abort, 3 transfer candidate
     double xn[UX_MAXLANE], atl[UX_MAXLANE], ex[UX_MAXLANE], dist[UX_MAXLANE];
+    int k_ended;
 };
 
 __global__ void __launch_bounds__(32 * UPD_WARPS) k_update(const DevWorld *worlds, int step_off) {
@@ -914,9 +954,95 @@ __global__ void __launch_bounds__(32 * UPD_WARPS) k_update(const DevWorld *world
     int hd = hd0 + pk2, n = tl - hd;
     int s0 = part;
     const double *Xc = W.X + (size_t)cur * C + o;
+    if (s0 == 0) {
+        // ---- link head
+        HeadSmem &H = hs_all[(threadIdx.x >> 5) % UPD_WARPS];
+        int hc = n < lanes ? n : lanes;
+        if (hc > UX_MAXLANE) hc = UX_MAXLANE;
+        int end_node = W.l_end[l];
+        bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
+        WARP_FOR(lane) {
+            for (int j = lane; j < hc; j += 32) {
+                int slot = ring_slot(hd, j, cap);
+                int vid = W.VID[o + slot];
+                double x = Xc[slot];
+                int dest_ = W.v_dest[vid];
+                double atl_ = W.v_atl[vid], ex_ = W.v_entry_x[vid], di_ = W.v_dist[vid]; int dts_ = W.v_depart_ts[vid];
+                double xn = x + udt;  // positions < lanes have no leader
+                if (xn < x) xn = x;
+                bool over = xn > len;
+                double mr_ = xn - len;
+                if (over) xn = len;
+                unsigned char kind = 0;
+                int nx = -1;
+                if (fabs(xn - len) < 1e-9) {
+                    if (end_node == dest_) kind = 1;
+                    else if (dead_end) kind = 2;  // traffi.cpp:864-871 (trip_abort is always 1 in this engine)
+                    else { kind = 3; nx = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u); }
+                }
+                if (over) W.v_mr[vid] = mr_;
+                H.vid[j] = vid; H.kind[j] = kind; H.xn[j] = xn; H.next[j] = nx;
+                H.atl[j] = atl_; H.ex[j] = ex_; H.dist[j] = di_; H.dts[j] = dts_;
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) {
+            // lane relabel when the end node (smaller id) emptied the link before this step's pushes
+            if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
+                int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+                if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
+            }
+            W.stat_count[l] += n;
+            int k = 0, evc = 0, trips = 0;
+            double cumdep = 0.0;
+            bool touched = false;
+            for (int j = 0; j < hc; j++) {
+                int vid = H.vid[j];
+                unsigned char kind = H.kind[j], f = 0;
+                if (kind == 3) { W.v_next[vid] = H.next[j]; f = VF_CAND; }
+                else if (kind == 1 || kind == 2) {
+                    f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
+                    if (kind == 2) W.v_next[vid] = -1;
+                    if (k == j) {  // it is the front (everything ahead ended in this pass): end_trip, traffi.cpp:886-927
+                        if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[(size_t)t * L + l]; touched = true; }
+                        trips += 1; cumdep += W.dn;
+                        double atl = H.atl[j];
+                        int es = (int)(atl / W.dt);
+                        if (es < 0) es = 0;
+                        if (es >= W.T) es = W.T - 1;
+                        evc += 1;
+                        W.ev_ord[(size_t)es * L + l] = evc;
+                        W.ev_tt[(size_t)es * L + l] = ((double)t + 1.0) * W.dt - atl;
+                        W.v_atl[vid] = (double)t * W.dt;
+                        W.v_dist[vid] = H.dist[j] + (H.xn[j] - H.ex[j]);
+                        W.v_link[vid] = -1;
+                        if (kind == 2) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+                        else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)H.dts[j] * W.dt; }
+                        if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 1; }
+                        f = 0;
+                        k++;
+                    }
+                }
+                W.v_flags[vid] = f;
+            }
+            if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[(size_t)t * L + l] = cumdep; }
+            W.head[(cur ^ 1) * L + l] = hd + k;
+            int rem = n - k;
+            W.hcount[l] = rem < lanes ? rem : lanes;
+            H.k_ended = k;
+        }
+
+        if (W.log_mode) {  // positions that may have a just-ended leader are logged here, once the ended count is known
+            WARP_SYNC();
+            int nlog = n < 2 * lanes ? n : 2 * lanes, k_ended = H.k_ended;
+            WARP_FOR(lane) { for (int pos = lane; pos < nlog; pos += 32) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, k_ended, 0); }
+            WARP_SYNC();
+        }
+    }
     WARP_FOR(lane) {
         for (int pos = part * 32 + lane; pos < n; pos += nparts * 32) {
             int p = ring_slot(hd, pos, cap);
+            if (W.log_mode && pos >= 2 * lanes) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, 0, 0);
             double x = Xc[p];
             double xn = x + udt;
             if (pos >= lanes) {
@@ -929,81 +1055,6 @@ __global__ void __launch_bounds__(32 * UPD_WARPS) k_update(const DevWorld *world
             W.X[(size_t)(cur ^ 1) * C + o + p] = xn;
             W.V[o + p] = (xn - x) / W.dt;
         }
-    }
-    if (s0 != 0) return;
-    // ---- link head
-    HeadSmem &H = hs_all[(threadIdx.x >> 5) % UPD_WARPS];
-    int hc = n < lanes ? n : lanes;
-    if (hc > UX_MAXLANE) hc = UX_MAXLANE;
-    int end_node = W.l_end[l];
-    bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
-    WARP_FOR(lane) {
-        for (int j = lane; j < hc; j += 32) {
-            int slot = ring_slot(hd, j, cap);
-            int vid = W.VID[o + slot];
-            double x = Xc[slot];
-            int dest_ = W.v_dest[vid];
-            double atl_ = W.v_atl[vid], ex_ = W.v_entry_x[vid], di_ = W.v_dist[vid]; int dts_ = W.v_depart_ts[vid];
-            double xn = x + udt;  // positions < lanes have no leader
-            if (xn < x) xn = x;
-            bool over = xn > len;
-            double mr_ = xn - len;
-            if (over) xn = len;
-            unsigned char kind = 0;
-            int nx = -1;
-            if (fabs(xn - len) < 1e-9) {
-                if (end_node == dest_) kind = 1;
-                else if (dead_end) kind = 2;  // traffi.cpp:864-871 (trip_abort is always 1 in this engine)
-                else { kind = 3; nx = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u); }
-            }
-            if (over) W.v_mr[vid] = mr_;
-            H.vid[j] = vid; H.kind[j] = kind; H.xn[j] = xn; H.next[j] = nx;
-            H.atl[j] = atl_; H.ex[j] = ex_; H.dist[j] = di_; H.dts[j] = dts_;
-        }
-    }
-    WARP_SYNC();
-    WARP_FOR(lane) if (lane == 0) {
-        // lane relabel when the end node (smaller id) emptied the link before this step's pushes
-        if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
-            int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
-            if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
-        }
-        W.stat_count[l] += n;
-        int k = 0, evc = 0, trips = 0;
-        double cumdep = 0.0;
-        bool touched = false;
-        for (int j = 0; j < hc; j++) {
-            int vid = H.vid[j];
-            unsigned char kind = H.kind[j], f = 0;
-            if (kind == 3) { W.v_next[vid] = H.next[j]; f = VF_CAND; }
-            else if (kind == 1 || kind == 2) {
-                f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
-                if (kind == 2) W.v_next[vid] = -1;
-                if (k == j) {  // it is the front (everything ahead ended in this pass): end_trip, traffi.cpp:886-927
-                    if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[(size_t)t * L + l]; touched = true; }
-                    trips += 1; cumdep += W.dn;
-                    double atl = H.atl[j];
-                    int es = (int)(atl / W.dt);
-                    if (es < 0) es = 0;
-                    if (es >= W.T) es = W.T - 1;
-                    evc += 1;
-                    W.ev_ord[(size_t)es * L + l] = evc;
-                    W.ev_tt[(size_t)es * L + l] = ((double)t + 1.0) * W.dt - atl;
-                    W.v_atl[vid] = (double)t * W.dt;
-                    W.v_dist[vid] = H.dist[j] + (H.xn[j] - H.ex[j]);
-                    W.v_link[vid] = -1;
-                    if (kind == 2) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
-                    else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)H.dts[j] * W.dt; }
-                    f = 0;
-                    k++;
-                }
-            }
-            W.v_flags[vid] = f;
-        }
-        if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[(size_t)t * L + l] = cumdep; }
-        W.head[(cur ^ 1) * L + l] = hd + k;
-        int rem = n - k;
-        W.hcount[l] = rem < lanes ? rem : lanes;
     }
 }
 
@@ -1034,55 +1085,87 @@ __global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int s
     W.pair_cost[e] = cost;
 }
 
-// One block per active destination: label-correcting relaxation to the fixed point dist[i] = min_j c_ij + dist[j].
-__global__ void __launch_bounds__(256) k_sssp(const DevWorld *worlds) {
+// One block per active destination: label-correcting relaxation to the fixed point dist[i] = min_j c_ij + dist[j]
+// (oracle R2).  The destination's dist / next rows live in shared memory for the whole search (12 B per node, up to
+// ~19k nodes in 227 KB; larger graphs fall back to the rows in global memory), so a sweep over the edges costs
+// shared-memory atomics only; the fixed point does not depend on the relaxation order, so the result is deterministic.
+#define SSSP_KE 8
+#define SSSP_THREADS 256
+template <bool USE_SMEM>
+__global__ void __launch_bounds__(SSSP_THREADS) k_sssp(const DevWorld *worlds) {
     LOAD_WORLD(W, worlds)
     int row = (int)blockIdx.x;
     if (row >= W.D) return;
-    int N = W.N, k = W.row_dest[row];
-    double *dist = W.rdist + (size_t)row * N;
-    int *next = W.rnext + (size_t)row * N;
-    unsigned long long *du = (unsigned long long *)dist;
+    int N = W.N, k = W.row_dest[row], E = W.n_edges;
+    double *gdist = W.rdist + (size_t)row * N;
+    int *gnext = W.rnext + (size_t)row * N;
+    const double *cost = W.pair_cost;
+    const int *e_from = W.e_from, *e_to = W.e_to;
 #ifdef UX_EMU
     if (threadIdx.x != 0) return;
+    double *dist = gdist; int *next = gnext;
     for (int i = 0; i < N; i++) { dist[i] = INFINITY; next[i] = 0x7fffffff; }
     dist[k] = 0.0;
     for (bool changed = true; changed;) {
         changed = false;
-        for (int e = 0; e < W.n_edges; e++) {
-            double c = W.pair_cost[e];
+        for (int e = 0; e < E; e++) {
+            double c = cost[e];
             if (!(c > 0.0) || is_inf(c)) continue;
-            double nd = c + dist[W.e_to[e]];
-            if (nd < dist[W.e_from[e]]) { dist[W.e_from[e]] = nd; changed = true; }
+            double nd = c + dist[e_to[e]];
+            if (nd < dist[e_from[e]]) { dist[e_from[e]] = nd; changed = true; }
         }
     }
     int tid = 0, nth = 1;
 #else
+    extern __shared__ unsigned long long sssp_smem[];
+    // compile-time address space: with a run-time select the loads / atomics below become generic and crawl
+    double *dist; int *next; unsigned long long *du;
+    if (USE_SMEM) { du = sssp_smem; dist = reinterpret_cast<double *>(sssp_smem); next = reinterpret_cast<int *>(sssp_smem + N); }
+    else { dist = gdist; next = gnext; du = reinterpret_cast<unsigned long long *>(gdist); }
     int tid = (int)threadIdx.x, nth = (int)blockDim.x;
     for (int i = tid; i < N; i += nth) { dist[i] = (i == k) ? 0.0 : INFINITY; next[i] = 0x7fffffff; }
+    // the first SSSP_KE edges of every thread stay in registers for all sweeps; only larger graphs re-read the rest
+    double rc[SSSP_KE]; int rf[SSSP_KE], rt[SSSP_KE];
+#pragma unroll
+    for (int q = 0; q < SSSP_KE; q++) {
+        int e = tid + q * nth;
+        double c = e < E ? __ldg(cost + e) : INFINITY;
+        if (!(c > 0.0)) c = INFINITY;  // adj > 0 filter (traffi.cpp:1331): such edges never relax anything
+        rc[q] = c; rf[q] = e < E ? __ldg(e_from + e) : 0; rt[q] = e < E ? __ldg(e_to + e) : 0;
+    }
     __syncthreads();
     while (true) {
         int changed = 0;
-        for (int e = tid; e < W.n_edges; e += nth) {
-            double c = W.pair_cost[e];
+        // two relaxation passes per barrier: the fixed point does not depend on the order or staleness of the reads
+        for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+        for (int q = 0; q < SSSP_KE; q++) {
+            double nd = rc[q] + __longlong_as_double((long long)du[rt[q]]);  // inf + x = inf: never smaller
+            if (nd < __longlong_as_double((long long)du[rf[q]])) {  // non-negative doubles order like their bit patterns
+                atomicMin(&du[rf[q]], (unsigned long long)__double_as_longlong(nd));
+                changed = 1;
+            }
+        }
+        for (int e = tid + SSSP_KE * nth; e < E; e += nth) {
+            double c = __ldg(cost + e);
             if (!(c > 0.0) || is_inf(c)) continue;
-            double dj = __longlong_as_double((long long)du[W.e_to[e]]);
-            double nd = c + dj;
-            int i = W.e_from[e];
-            if (nd < __longlong_as_double((long long)du[i])) {  // non-negative doubles order like their bit patterns
+            double nd = c + __longlong_as_double((long long)du[__ldg(e_to + e)]);
+            int i = __ldg(e_from + e);
+            if (nd < __longlong_as_double((long long)du[i])) {
                 atomicMin(&du[i], (unsigned long long)__double_as_longlong(nd));
                 changed = 1;
             }
+        }
         }
         if (!__syncthreads_or(changed)) break;
     }
 #endif
     // next hop: smallest node j with c_ij + dist[j] == dist[i]
     int any = 0;
-    for (int e = tid; e < W.n_edges; e += nth) {
-        double c = W.pair_cost[e];
+    for (int e = tid; e < E; e += nth) {
+        double c = cost[e];
         if (!(c > 0.0) || is_inf(c)) continue;
-        int i = W.e_from[e], j = W.e_to[e];
+        int i = e_from[e], j = e_to[e];
         if (i == k) continue;
         double dj = dist[j];
         if (is_inf(dj)) continue;
@@ -1091,7 +1174,12 @@ __global__ void __launch_bounds__(256) k_sssp(const DevWorld *worlds) {
 #ifndef UX_EMU
     any = __syncthreads_or(any);
 #endif
-    for (int i = tid; i < N; i += nth) { if (i == k) next[i] = k; else if (next[i] == 0x7fffffff) next[i] = -1; }
+    for (int i = tid; i < N; i += nth) {
+        int nx = next[i];
+        if (i == k) nx = k; else if (nx == 0x7fffffff) nx = -1;
+        gnext[i] = nx;
+        gdist[i] = dist[i];
+    }
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
 }
 
@@ -1144,6 +1232,17 @@ __global__ void k_tt_actual(const DevWorld *worlds, int replica, double *out) {
         if (ord > best) { best = ord; cur = W.ev_tt[(size_t)i * W.L + l]; }
         out[(size_t)l * W.T + i] = cur;
     }
+}
+
+// order the RUN records per platoon and by time: record (vid, t) goes to off[vid] + (t - gen_ts[vid])
+__global__ void k_log_scatter(const DevWorld *worlds, int replica, long long n, const long long *off, int *o_t, int *o_link, int *o_lane,
+                              double *o_x, double *o_v, double *o_s) {
+    const DevWorld &W = worlds[replica];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int vid = W.lg_vid[i], t = W.lg_t[i];
+    long long d = off[vid] + (t - W.v_gen_ts[vid]);
+    o_t[d] = t; o_link[d] = W.lg_link[i]; o_lane[d] = W.lg_lane[i]; o_x[d] = W.lg_x[i]; o_v[d] = W.lg_v[i]; o_s[d] = W.lg_s[i];
 }
 
 // scatter ring state to per-vehicle arrays (x, v, lane)
@@ -1219,9 +1318,16 @@ struct ux_world {
 #endif
     // device pointers of updatable static arrays
     double *d_vmax = nullptr, *d_dpl_dn = nullptr, *d_udt = nullptr, *d_cap_out = nullptr, *d_cap_in = nullptr, *d_mp = nullptr, *d_penalty = nullptr, *d_toll = nullptr, *d_n_sig = nullptr;
-    int *d_l_flags = nullptr, *d_lvl_off = nullptr, *d_lvl_nodes = nullptr, *d_lvl_level = nullptr, *d_sg_off = nullptr, *d_sg = nullptr, *d_n_sig_off = nullptr;
+    int *d_l_flags = nullptr, *d_lvl_off = nullptr, *d_lvl_nodes = nullptr, *d_lvl_level = nullptr, *d_dep_off = nullptr, *d_dep_list = nullptr, *d_sg_off = nullptr, *d_sg = nullptr, *d_n_sig_off = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     double *d_ens = nullptr;
+    // assembled per-platoon logs of one replica (World::build_all_vehicle_logs_flat_compact layout), built on demand
+    struct LogCache {
+        int replica = -1, timestep = -1;
+        std::vector<long long> offsets, ltl_offsets;
+        std::vector<double> t, x, v, s, ltl_t, enter_t;
+        std::vector<int> state, lane, link, n_missing, ltl_id, enter_link, enter_veh;
+    } logs;
     // measurement
     long long h2d_bytes = 0, d2h_bytes = 0;
     double last_loop_ms = 0.0;
@@ -1458,7 +1564,8 @@ UX_API int ux_initialize_adj_matrix(ux_world *w) {
 }
 
 // ---- transfer dependency levels (DESIGN.md "transfer order") --------------------------------------------
-static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<int> &lvl_off, std::vector<int> &lvl_nodes, std::vector<int> &lvl_level) {
+static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<int> &lvl_off, std::vector<int> &lvl_nodes, std::vector<int> &lvl_level,
+                           std::vector<int> &dep_off, std::vector<int> &dep_list) {
     int N = (int)w->nodes.size(), L = (int)w->links.size();
     lflags.assign(L, 0);
     std::vector<int> level(N, 0);
@@ -1484,6 +1591,11 @@ static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<in
     for (int a = 0; a < N; a++) lvl_nodes[lvl_off[level[a]] + fill[level[a]]++] = a;
     lvl_level.assign(N, 0);
     for (int q = 0; q < N; q++) lvl_level[q] = level[lvl_nodes[q]];
+    dep_off.assign(N + 1, 0); dep_list.clear();
+    for (int a = 0; a < N; a++) {
+        for (int l : w->nodes[a].out) if (lflags[l] & LF_SEES_POPS) { int b = w->links[l].end; if (std::find(dep_list.begin() + dep_off[a], dep_list.end(), b) == dep_list.end()) dep_list.push_back(b); }
+        dep_off[a + 1] = (int)dep_list.size();
+    }
     w->n_levels = nl;
 }
 
@@ -1502,8 +1614,11 @@ static int upload_link_params(ux_world *w) {
     CUDA_OK(cudaMemcpy(w->d_cap_in, ci.data(), b, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(w->d_mp, mp.data(), b, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(w->d_penalty, pen.data(), b, cudaMemcpyHostToDevice));
-    std::vector<int> lflags, lvl_off, lvl_nodes, lvl_level;
-    compute_levels(w, lflags, lvl_off, lvl_nodes, lvl_level);
+    std::vector<int> lflags, lvl_off, lvl_nodes, lvl_level, dep_off, dep_list;
+    compute_levels(w, lflags, lvl_off, lvl_nodes, lvl_level, dep_off, dep_list);
+    dep_list.resize(w->links.size() + 1, 0);
+    CUDA_OK(cudaMemcpy(w->d_dep_off, dep_off.data(), sizeof(int) * dep_off.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w->d_dep_list, dep_list.data(), sizeof(int) * dep_list.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(w->d_lvl_level, lvl_level.data(), sizeof(int) * lvl_level.size(), cudaMemcpyHostToDevice));
     for (auto &d : w->hw) d.n_levels = w->n_levels;
     if (w->dworlds) CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->hw.size(), cudaMemcpyHostToDevice));
@@ -1562,9 +1677,9 @@ static int upload(ux_world *w) {
     base.seg_link = dupload(w, seg_link); base.seg_start = dupload(w, seg_start);
     w->d_vmax = dalloc<double>(w, L); w->d_dpl_dn = dalloc<double>(w, L); w->d_udt = dalloc<double>(w, L); w->d_cap_out = dalloc<double>(w, L);
     w->d_cap_in = dalloc<double>(w, L); w->d_mp = dalloc<double>(w, L); w->d_penalty = dalloc<double>(w, L);
-    w->d_l_flags = dalloc<int>(w, L); w->d_lvl_off = dalloc<int>(w, N + 2); w->d_lvl_nodes = dalloc<int>(w, N); w->d_lvl_level = dalloc<int>(w, N);
+    w->d_l_flags = dalloc<int>(w, L); w->d_lvl_off = dalloc<int>(w, N + 2); w->d_lvl_nodes = dalloc<int>(w, N); w->d_lvl_level = dalloc<int>(w, N); w->d_dep_off = dalloc<int>(w, N + 1); w->d_dep_list = dalloc<int>(w, L + 1);
     base.l_vmax = w->d_vmax; base.l_dpl_dn = w->d_dpl_dn; base.l_udt = w->d_udt; base.l_cap_out = w->d_cap_out; base.l_cap_in = w->d_cap_in;
-    base.l_mp = w->d_mp; base.l_penalty = w->d_penalty; base.l_flags = w->d_l_flags; base.lvl_off = w->d_lvl_off; base.lvl_nodes = w->d_lvl_nodes; base.lvl_level = w->d_lvl_level;
+    base.l_mp = w->d_mp; base.l_penalty = w->d_penalty; base.l_flags = w->d_l_flags; base.lvl_off = w->d_lvl_off; base.lvl_nodes = w->d_lvl_nodes; base.lvl_level = w->d_lvl_level; base.dep_off = w->d_dep_off; base.dep_list = w->d_dep_list;
     { int rc = upload_link_params(w); if (rc) return rc; }
     if (any_toll) {  // [T][L]; links without a series use their static penalty (traffi.cpp:1285-1289)
         std::vector<double> toll((size_t)T * L);
@@ -1656,13 +1771,25 @@ static int upload(ux_world *w) {
         d.v_mr = dalloc<double>(w, P); d.v_atl = dalloc<double>(w, P); d.v_dist = dalloc<double>(w, P); d.v_entry_x = dalloc<double>(w, P);
         { std::vector<double> m1(P, -1.0); d.v_tt = dupload(w, m1); }
         d.v_flags = dalloc<unsigned char>(w, P);
+        if (base.log_mode) {
+            long long cap = 0;
+            for (long long i = 0; i < P; i++) cap += std::max(0, T - w->vehs[i].ts - 1);  // a platoon can be RUN from ts+1 to T-1
+            d.lg_cap = cap;
+            d.v_gen_ts = dalloc<int>(w, P, false); d.v_end_ts = dalloc<int>(w, P, false); d.v_end_kind = dalloc<unsigned char>(w, P);
+            if (d.v_gen_ts) cudaMemset(d.v_gen_ts, 0xff, sizeof(int) * (P ? P : 1));
+            if (d.v_end_ts) cudaMemset(d.v_end_ts, 0xff, sizeof(int) * (P ? P : 1));
+            d.lg_vid = dalloc<int>(w, cap, false); d.lg_t = dalloc<int>(w, cap, false); d.lg_link = dalloc<int>(w, cap, false); d.lg_lane = dalloc<int>(w, cap, false);
+            d.lg_x = dalloc<double>(w, cap, false); d.lg_v = dalloc<double>(w, cap, false); d.lg_s = dalloc<double>(w, cap, false);
+            d.lg_count = dalloc<unsigned long long>(w, 1);
+            if (!d.lg_vid || !d.lg_s || !d.lg_count || !d.v_gen_ts) return fail(w, UX_ERR_CUDA, "device allocation of the vehicle logs failed (%lld records)", cap);
+        }
         d.v_visited = base.no_cyclic ? dalloc<unsigned>(w, (size_t)P * base.vis_words) : nullptr;
         d.cum_arr = dalloc<double>(w, TL); d.cum_dep = dalloc<double>(w, TL); d.tt_inst = dalloc<double>(w, TL); d.ev_tt = dalloc<double>(w, TL);
         d.ev_ord = dalloc<int>(w, TL); d.sig_log = dalloc<int>(w, (size_t)T * N);
         d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
         d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
         if (d.rnext) cudaMemset(d.rnext, 0xff, sizeof(int) * std::max<size_t>((size_t)D * N, 1));
-        d.err = dalloc<int>(w, 2); d.t_base = dupload(w, tb); d.lvl_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
+        d.err = dalloc<int>(w, 2); d.t_base = dupload(w, tb); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
         if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
             return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
     }
@@ -1672,6 +1799,19 @@ static int upload(ux_world *w) {
     CUDA_OK(cudaDeviceSynchronize());
     w->uploaded = true;
     return 0;
+}
+
+static void launch_sssp(ux_world *w, cudaStream_t st) {
+    int N = (int)w->nodes.size();
+#ifdef UX_EMU
+    UX_LAUNCH(k_sssp<false>, dim3(w->n_active, w->R), dim3(SSSP_THREADS), st, w->dworlds);
+#else
+    size_t bytes = (size_t)N * 12 + 16;
+    int use_smem = bytes <= 200 * 1024;
+    if (use_smem && bytes > 48 * 1024) cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (use_smem) k_sssp<true><<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), bytes, st>>>(w->dworlds);
+    else k_sssp<false><<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), 0, st>>>(w->dworlds);
+#endif
 }
 
 #ifdef UX_EMU
@@ -1697,7 +1837,7 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
         if (w->n_active > 0 && w->n_edges > 0) {
             if (route) {
                 KT_BEGIN(UX_K_EDGE_COST) UX_LAUNCH(k_edge_cost, dim3((w->n_edges + 127) / 128, R), dim3(128), st, w->dworlds, s); KT_END(UX_K_EDGE_COST) lc++;
-                KT_BEGIN(UX_K_SSSP) UX_LAUNCH(k_sssp, dim3(w->n_active, R), dim3(256), st, w->dworlds); KT_END(UX_K_SSSP) lc++;
+                KT_BEGIN(UX_K_SSSP) launch_sssp(w, st); KT_END(UX_K_SSSP) lc++;
             }
             if (route || w->p.route_choice_update_gradual) {
                 long long tot = (long long)w->n_active * (long long)w->links.size();
@@ -1716,6 +1856,7 @@ static const char *derr_text(int code) {
     case DERR_ROUTE_EXHAUSTED: return "Vehicle %d: specified route has no more links";
     case DERR_ROUTE_INCONSISTENT: return "Vehicle %d: specified route is inconsistent; the forced link is not an outgoing link of the current node";
     case DERR_AVOID_ALL: return "Vehicle %d: links_avoid excludes all outgoing links of the current node";
+    case DERR_LOG_FULL: return "vehicle log buffer overflow (link %d)";
     default: return "device error (info %d)";
     }
 }
@@ -1784,7 +1925,7 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
         int e[2] = {0, 0};
         CUDA_OK(cudaMemcpy(e, w->hw[r].err, sizeof(e), cudaMemcpyDeviceToHost));
         if (e[0]) {
-            int code = e[0] == DERR_RING_FULL ? UX_ERR_CAPACITY : e[0] == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
+            int code = (e[0] == DERR_RING_FULL || e[0] == DERR_LOG_FULL) ? UX_ERR_CAPACITY : e[0] == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
             w->timestep = end_ts;
             return fail(w, code, derr_text(e[0]), e[1]);
         }
@@ -1856,6 +1997,7 @@ UX_API int ux_set_node_signal(ux_world *w, int node, const double *sig, int nsig
 }
 
 // ---- results ---------------------------------------------------------------------------------------------
+static int64_t get_log_array(ux_world *w, int what, int replica, void *dst, int64_t capacity, int *dtype, bool size_only);
 static long long dsum_ll(ux_world *w, const long long *d, int n) {
     std::vector<long long> h(n); if (n) cudaMemcpy(h.data(), d, sizeof(long long) * n, cudaMemcpyDeviceToHost);
     long long s = 0; for (auto v : h) s += v; return s;
@@ -1876,7 +2018,7 @@ UX_API int64_t ux_get_int(ux_world *w, int what) {
     case UX_I_ROUTE_UPDATE_STEPS: return w->route_ts;
     case UX_I_PLATOON_UPDATES: return w->uploaded ? dsum_ll(w, w->hw[0].stat_count, (int)w->links.size()) : 0;
     case UX_I_TRIPS_COMPLETED: return w->uploaded ? dsum_i(w, w->hw[0].trips, (int)w->links.size()) : 0;
-    case UX_I_LOG_ENTRIES: return 0;
+    case UX_I_LOG_ENTRIES: { if (!w->uploaded || !w->p.vehicle_log_mode) return 0; int dt_; return get_log_array(w, UX_A_LOG_T, 0, nullptr, 0, &dt_, true); }
     case UX_I_KERNEL_LAUNCHES: return w->launches;
     case UX_I_NUM_ACTIVE_DESTS: return w->n_active;
     case UX_I_TRANSFER_LEVELS: return w->n_levels;
@@ -1903,9 +2045,126 @@ UX_API double ux_get_double(ux_world *w, int what) {
     }
 }
 
+// ---- per-platoon logs: World::build_all_vehicle_logs_flat_compact (traffi.cpp:1990-2081) + build_enter_log_data (1965-1983) ----
+// The device holds only the RUN records; HOME / WAIT / END entries are implied by the departure, generation and end
+// steps (the reference reconstructs log_t / log_state from the same counters, traffi.cpp:1117-1133).
+static int build_logs(ux_world *w, int replica) {
+    auto &G = w->logs;
+    if (G.replica == replica && G.timestep == w->timestep) return 0;
+    const DevWorld &d = w->hw[replica];
+    long long P = d.P; int Tnow = w->timestep; double dt = w->dt;
+    std::vector<int> gen(P), endt(P), st(P), arr(P); std::vector<unsigned char> kind(P);
+    unsigned long long nrec = 0;
+    if (P) {
+        CUDA_OK(cudaMemcpy(gen.data(), d.v_gen_ts, sizeof(int) * P, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(endt.data(), d.v_end_ts, sizeof(int) * P, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(kind.data(), d.v_end_kind, P, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(st.data(), d.v_state, sizeof(int) * P, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(arr.data(), d.v_arr_ts, sizeof(int) * P, cudaMemcpyDeviceToHost));
+    }
+    CUDA_OK(cudaMemcpy(&nrec, d.lg_count, sizeof(nrec), cudaMemcpyDeviceToHost));
+    // RUN entries per platoon and their offsets in the time-ordered record array
+    std::vector<long long> roff(P + 1, 0);
+    for (long long i = 0; i < P; i++) {
+        long long r = 0;
+        if (gen[i] >= 0) { int last = kind[i] == 1 ? endt[i] : kind[i] == 2 ? endt[i] - 1 : Tnow - 1; r = last - gen[i] + 1; if (r < 0) r = 0; }
+        roff[i + 1] = roff[i] + r;
+    }
+    if ((unsigned long long)roff[P] != nrec) return fail(w, UX_ERR_RUNTIME, "vehicle log bookkeeping mismatch: %lld expected, %llu recorded", roff[P], nrec);
+    std::vector<int> r_t(nrec), r_link(nrec), r_lane(nrec); std::vector<double> r_x(nrec), r_v(nrec), r_s(nrec);
+    if (nrec) {
+        size_t need = sizeof(long long) * (P + 1) + nrec * (3 * sizeof(int) + 3 * sizeof(double)) + 256;
+        int rc = 0;
+        void *tmp = nullptr;
+        CUDA_OK(cudaMalloc(&tmp, need));
+        char *b = (char *)tmp;
+        long long *d_off = (long long *)b; b += sizeof(long long) * (P + 1);
+        double *ox = (double *)b; b += nrec * 8; double *ov = (double *)b; b += nrec * 8; double *os = (double *)b; b += nrec * 8;
+        int *ot = (int *)b; b += nrec * 4; int *ol = (int *)b; b += nrec * 4; int *oa = (int *)b;
+        cudaMemcpy(d_off, roff.data(), sizeof(long long) * (P + 1), cudaMemcpyHostToDevice);
+        UX_LAUNCH(k_log_scatter, dim3((unsigned)((nrec + 255) / 256)), dim3(256), w->stream, w->dworlds, replica, (long long)nrec, d_off, ot, ol, oa, ox, ov, os);
+        cudaStreamSynchronize(w->stream);
+        cudaMemcpy(r_t.data(), ot, nrec * 4, cudaMemcpyDeviceToHost); cudaMemcpy(r_link.data(), ol, nrec * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(r_lane.data(), oa, nrec * 4, cudaMemcpyDeviceToHost); cudaMemcpy(r_x.data(), ox, nrec * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(r_v.data(), ov, nrec * 8, cudaMemcpyDeviceToHost); cudaMemcpy(r_s.data(), os, nrec * 8, cudaMemcpyDeviceToHost);
+        w->d2h_bytes += (long long)(nrec * 36);
+        cudaFree(tmp);
+        (void)rc;
+    }
+    G.offsets.assign(P + 1, 0); G.ltl_offsets.assign(P + 1, 0); G.n_missing.assign(P, 0);
+    G.t.clear(); G.x.clear(); G.v.clear(); G.s.clear(); G.state.clear(); G.lane.clear(); G.link.clear();
+    G.ltl_t.clear(); G.ltl_id.clear(); G.enter_t.clear(); G.enter_link.clear(); G.enter_veh.clear();
+    for (long long i = 0; i < P; i++) {
+        G.offsets[i] = (long long)G.t.size(); G.ltl_offsets[i] = (long long)G.ltl_t.size();
+        int ts0 = w->vehs[i].ts;
+        G.ltl_t.push_back((double)ts0 * dt); G.ltl_id.push_back(-1);  // home entry (traffi.cpp:2059-2061)
+        if (ts0 < Tnow) {
+            G.n_missing[i] = ((double)ts0 * dt > 0) ? (int)(((double)ts0 * dt) / dt) : 0;
+            auto push = [&](int tstep, int state, double x, double v, double s_, int lane, int link) {
+                G.t.push_back((double)tstep * dt); G.state.push_back(state); G.x.push_back(x); G.v.push_back(v); G.s.push_back(s_); G.lane.push_back(lane); G.link.push_back(link);
+            };
+            push(ts0, UX_VS_HOME, -1, -1, -1.0, -1, -1);
+            int wait_end = gen[i] >= 0 ? gen[i] : Tnow;
+            for (int tt = ts0 + 1; tt < wait_end; tt++) push(tt, UX_VS_WAIT, -1, -1, -1.0, -1, -1);
+            int prev = -999;
+            for (long long q = roff[i]; q < roff[i + 1]; q++) {
+                push(r_t[q], UX_VS_RUN, r_x[q], r_v[q], r_s[q], r_lane[q], r_link[q]);
+                if (r_link[q] >= 0 && r_link[q] != prev) {
+                    G.ltl_t.push_back((double)r_t[q] * dt); G.ltl_id.push_back(r_link[q]);
+                    G.enter_link.push_back(r_link[q]); G.enter_t.push_back((double)r_t[q] * dt); G.enter_veh.push_back((int)i);
+                    prev = r_link[q];
+                }
+            }
+            if (kind[i]) push(endt[i], st[i], -1, -1, -1.0, -1, -1);
+        }
+        if (st[i] == UX_VS_END) { G.ltl_t.push_back(arr[i] >= 0 ? (double)arr[i] * dt : -1.0); G.ltl_id.push_back(-2); }
+    }
+    G.offsets[P] = (long long)G.t.size(); G.ltl_offsets[P] = (long long)G.ltl_t.size();
+    G.replica = replica; G.timestep = w->timestep;
+    return 0;
+}
+
+static bool is_log_array(int what) { return (what >= UX_A_LOG_OFFSETS && what <= UX_A_LTL_ID) || (what >= UX_A_ENTER_LINK && what <= UX_A_ENTER_VEH); }
+
+// copy one assembled log array out; returns elements or an error code
+static int64_t get_log_array(ux_world *w, int what, int replica, void *dst, int64_t capacity, int *dtype, bool size_only) {
+    if (!w->p.vehicle_log_mode) return fail(w, UX_ERR_RUNTIME, "vehicle logs are off (vehicle_log_mode = 0)");
+    if (!w->uploaded) { if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; } cudaSetDevice(w->device); int rc = upload(w); if (rc) return rc; }
+    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    cudaSetDevice(w->device);
+    int rc = build_logs(w, replica); if (rc) return rc;
+    auto &G = w->logs;
+    const void *src = nullptr; int64_t n = 0; int dt = UX_DT_F64;
+    switch (what) {
+    case UX_A_LOG_OFFSETS: src = G.offsets.data(); n = (int64_t)G.offsets.size(); dt = UX_DT_I64; break;
+    case UX_A_LTL_OFFSETS: src = G.ltl_offsets.data(); n = (int64_t)G.ltl_offsets.size(); dt = UX_DT_I64; break;
+    case UX_A_LOG_T: src = G.t.data(); n = (int64_t)G.t.size(); break;
+    case UX_A_LOG_X: src = G.x.data(); n = (int64_t)G.x.size(); break;
+    case UX_A_LOG_V: src = G.v.data(); n = (int64_t)G.v.size(); break;
+    case UX_A_LOG_S: src = G.s.data(); n = (int64_t)G.s.size(); break;
+    case UX_A_LOG_STATE: src = G.state.data(); n = (int64_t)G.state.size(); dt = UX_DT_I32; break;
+    case UX_A_LOG_LANE: src = G.lane.data(); n = (int64_t)G.lane.size(); dt = UX_DT_I32; break;
+    case UX_A_LOG_LINK: src = G.link.data(); n = (int64_t)G.link.size(); dt = UX_DT_I32; break;
+    case UX_A_LOG_N_MISSING: src = G.n_missing.data(); n = (int64_t)G.n_missing.size(); dt = UX_DT_I32; break;
+    case UX_A_LTL_T: src = G.ltl_t.data(); n = (int64_t)G.ltl_t.size(); break;
+    case UX_A_LTL_ID: src = G.ltl_id.data(); n = (int64_t)G.ltl_id.size(); dt = UX_DT_I32; break;
+    case UX_A_ENTER_LINK: src = G.enter_link.data(); n = (int64_t)G.enter_link.size(); dt = UX_DT_I32; break;
+    case UX_A_ENTER_TIME: src = G.enter_t.data(); n = (int64_t)G.enter_t.size(); break;
+    case UX_A_ENTER_VEH: src = G.enter_veh.data(); n = (int64_t)G.enter_veh.size(); dt = UX_DT_I32; break;
+    default: return fail(w, UX_ERR_INVALID, "not a log array");
+    }
+    if (dtype) *dtype = dt;
+    if (size_only) return n;
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    size_t es = dt == UX_DT_I32 ? 4 : 8;
+    if (n) memcpy(dst, src, es * (size_t)n);
+    return n;
+}
+
 UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     int64_t N = (int64_t)w->nodes.size(), L = (int64_t)w->links.size(), T = w->total_ts, P = (int64_t)w->vehs.size();
     int dt = UX_DT_F64; int64_t n = -1;
+    if (is_log_array(what)) return get_log_array(w, what, 0, nullptr, 0, dtype, true);
     switch (what) {
     case UX_A_CUM_ARRIVAL: case UX_A_CUM_DEPARTURE: case UX_A_TRAVELTIME_INSTANT: case UX_A_TRAVELTIME_ACTUAL: n = L * T; break;
     case UX_A_VEH_STATE: case UX_A_VEH_ARRIVAL_TS: case UX_A_VEH_DEPART_TS: case UX_A_VEH_ORIG: case UX_A_VEH_DEST: case UX_A_VEH_LINK: case UX_A_VEH_LANE: n = P; dt = UX_DT_I32; break;
@@ -1996,6 +2255,7 @@ UX_API int64_t ux_get_device_array(ux_world *w, int what, int replica, void **dp
 }
 
 UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    if (is_log_array(what)) return get_log_array(w, what, replica, dst, capacity, nullptr, false);
     void *dptr = nullptr; int dt = 0;
     int64_t n = device_array(w, what, replica, &dptr, &dt);
     if (n < 0) return n;

@@ -360,18 +360,62 @@ class CudaVehicle:
         r = self.x / l.length if l.length > 0 else 0
         return (l.start_node.x + r * (l.end_node.x - l.start_node.x), l.start_node.y + r * (l.end_node.y - l.start_node.y))
 
-    def _no_logs(self):
-        raise NotImplementedError("per-platoon logs (log_t, log_x, ...) are not handed back by the CUDA engine yet; "
-                                  "use vehicle_logging_timestep_interval=-1 and the link/vehicle summary arrays")
+    # ---- per-step logs (uxsim_cpp_wrapper.py:575-664): slices of the world's flat arrays, home steps prepended ----
+    def _log(self, key):
+        return self.W._vehicle_log(self.id)[key]
 
-    log_t = property(_no_logs)
-    log_x = property(_no_logs)
-    log_v = property(_no_logs)
-    log_s = property(_no_logs)
-    log_state = property(_no_logs)
-    log_link = property(_no_logs)
-    log_lane = property(_no_logs)
-    log_t_link = property(_no_logs)
+    @property
+    def log_t(self):
+        return self._log("log_t")
+
+    @property
+    def log_x(self):
+        return self._log("log_x")
+
+    @property
+    def log_v(self):
+        return self._log("log_v")
+
+    @property
+    def log_s(self):
+        return self._log("log_s")
+
+    @property
+    def log_lane(self):
+        return self._log("log_lane")
+
+    @property
+    def log_state(self):
+        return [_STATE_NAMES[s] if 0 <= s < 5 else "end" for s in self._log("log_state")]
+
+    @property
+    def log_link(self):
+        links = self.W.LINKS
+        return [links[i] if 0 <= i < len(links) else -1 for i in self._log("log_link")]
+
+    @property
+    def log_t_link(self):
+        links = self.W.LINKS
+        out = []
+        for t, lid in zip(self._log("log_t_link_t"), self._log("log_t_link_id")):
+            lid = int(lid)
+            out.append([t, "home" if lid == -1 else "end" if lid == -2 else links[lid] if 0 <= lid < len(links) else -1])
+        return out
+
+    def traveled_route(self, include_arrival_time=True, include_departure_time=False):
+        """uxsim_cpp_wrapper.py:666-681."""
+        links, ts = [], []
+        ltl = self.log_t_link
+        for t, l in ltl:
+            if l == "home" and include_departure_time:
+                ts.append(t)
+            if isinstance(l, CudaLink):
+                ts.append(t)
+                links.append(l)
+        if ltl and include_arrival_time:
+            t, l = ltl[-1]
+            ts.append(t if l == "end" else -1)
+        return CudaRoute(self.W, links, trust_input=True), ts
 
 
 class CudaRoute:
@@ -471,7 +515,7 @@ class CudaWorld:
         self._E = C.EngineWorld(
             C.load_product(), t_max=float(tmax if tmax is not None else 7200), delta_n=float(deltan), tau=float(reaction_time),
             duo_update_time=float(duo_update_time), duo_update_weight=float(duo_update_weight), route_choice_uncertainty=float(duo_noise),
-            random_seed=int(seed), vehicle_log_mode=False, hard_deterministic_mode=hard_deterministic_mode,
+            random_seed=int(seed), vehicle_log_mode=vehicle_logging_timestep_interval > 0, hard_deterministic_mode=hard_deterministic_mode,
             route_choice_update_gradual=route_choice_update_gradual, no_cyclic_routing=no_cyclic_routing,
             adjust_node_capacity=adjust_node_capacity, instantaneous_TT_timestep_interval=int(instantaneous_TT_timestep_interval),
             num_replicas=num_replicas, device=device)
@@ -494,6 +538,44 @@ class CudaWorld:
             rows = len(self.NODES) if key == "signal_log" else len(self.LINKS)
             self._cache[key] = self._E.get_array(self._SERIES[key]).reshape(rows, self.TSIZE)
         return self._cache[key]
+
+    def _vehicle_log(self, vid):
+        """Per-platoon view of the flat SoA logs (uxsim_cpp_wrapper.py:1309-1367), fetched once per state of the run."""
+        if self.vehicle_logging_timestep_interval <= 0:
+            raise RuntimeError("vehicle logging is off (vehicle_logging_timestep_interval=-1)")
+        if "logs" not in self._cache:
+            E = self._E
+            flat = {k: E.get_array(getattr(C, "A_" + k.upper())) for k in
+                    ("log_offsets", "log_t", "log_x", "log_v", "log_state", "log_s", "log_lane", "log_link", "log_n_missing", "ltl_offsets", "ltl_t", "ltl_id")}
+            if isinstance(self.DELTAT, (int, np.integer)):
+                flat["log_t"] = flat["log_t"].astype(np.int64)
+            self._cache["logs"] = flat
+            self._cache["logs_per_vehicle"] = {}
+        per = self._cache["logs_per_vehicle"]
+        if vid not in per:
+            f = self._cache["logs"]
+            s, e = int(f["log_offsets"][vid]), int(f["log_offsets"][vid + 1])
+            ls, le = int(f["ltl_offsets"][vid]), int(f["ltl_offsets"][vid + 1])
+            nm = int(f["log_n_missing"][vid])
+            d = dict(log_t=f["log_t"][s:e], log_x=f["log_x"][s:e], log_v=f["log_v"][s:e], log_s=f["log_s"][s:e], log_state=f["log_state"][s:e],
+                     log_lane=f["log_lane"][s:e], log_link=f["log_link"][s:e], log_t_link_t=f["ltl_t"][ls:le], log_t_link_id=f["ltl_id"][ls:le])
+            if nm > 0:  # home steps before the first recorded entry
+                d["log_t"] = np.concatenate([np.arange(nm, dtype=d["log_t"].dtype) * self.DELTAT, d["log_t"]])
+                for k in ("log_x", "log_v", "log_s"):
+                    d[k] = np.concatenate([np.full(nm, -1.0), d[k]])
+                d["log_state"] = np.concatenate([np.zeros(nm, np.int32), d["log_state"]])
+                for k in ("log_lane", "log_link"):
+                    d[k] = np.concatenate([np.full(nm, -1, np.int32), d[k]])
+            per[vid] = d
+        return per[vid]
+
+    def _build_vehicles_enter_log(self):
+        """uxsim_cpp_wrapper.py:1377-1398."""
+        for l in self.LINKS:
+            l.vehicles_enter_log = {}
+        E = self._E
+        for lid, t, vi in zip(E.get_array(C.A_ENTER_LINK), E.get_array(C.A_ENTER_TIME), E.get_array(C.A_ENTER_VEH)):
+            self.LINKS[int(lid)].vehicles_enter_log[float(t)] = self._veh_by_index[int(vi)]
 
     def _veh(self, key):
         k = "veh_" + key
@@ -685,6 +767,8 @@ class CudaWorld:
     def simulation_terminated(self):
         self.print(" simulation finished")
         self._simulation_done = True
+        if self.vehicle_logging_timestep_interval > 0:
+            self._build_vehicles_enter_log()
         self.analyzer.basic_analysis()
 
     def check_simulation_ongoing(self):

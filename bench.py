@@ -30,6 +30,7 @@ WORKLOADS = {
     "chicago_dn5": ("chicago_sketch", dict(deltan=5, tmax=10000), "Chicago sketch, deltan=5: 211782 platoons = 1058910 veh, 2000 steps"),
     "grid11": ("grid", dict(n=11, deltan=5, tmax=7200), "11x11 grid (example_04en): 121 nodes, 440 links, 12100 platoons = 60500 veh, 1440 steps"),
     "siouxfalls": ("sioux_falls", dict(deltan=5, tmax=7200), "Sioux Falls: 24 nodes, 76 links, 6938 platoons, 1440 steps"),
+    "grid100": ("grid_random_od", dict(n=100, n_platoons=1_000_000, deltan=5, tmax=7200), "100x100 grid, signals at every node, random OD: 10000 nodes, 39600 links, 1M platoons = 5M veh, 1440 steps"),
 }
 ALG_BYTES = {  # algorithmic bytes (SURVEY.md 8d / DESIGN.md)
     "per_platoon_update": 32, "per_link_step": 40, "per_node_step": 20, "per_transfer": 160,

@@ -135,3 +135,27 @@ def test_vehicle_logs_bit_exact(name, mk, cuda_api, oracle_api):
     Eg.main_loop(), Eo.main_loop()
     assert compare_logs(Eg, Eo) == [] and compare_engines(Eg, Eo) == []
     assert Eg.get_int(C.I_LOG_ENTRIES) == Eo.get_int(C.I_LOG_ENTRIES)
+
+
+def test_grid_random_od_with_signals(cuda_api, oracle_api):
+    """Small variant of BASELINE config C4 (grid, signal at every node, random OD, addVehicle departures)."""
+    sc = S.grid_random_od(n=12, n_platoons=20000, tmax=4000, demand_t=1500, seed=3)
+    Eg, Eo = run_pair(sc, cuda_api, oracle_api)
+    assert compare_engines(Eg, Eo) == []
+
+
+def test_c4_full_size_properties(cuda_api):
+    """BASELINE config C4 at full size (100x100 grid, 1M platoons = 5M vehicles, 1440 steps): conservation properties."""
+    sc = S.grid_random_od(n=100, n_platoons=1_000_000, seed=0)
+    E = sc.engine_from_tables(cuda_api, sc.tables(), vehicle_logging_timestep_interval=-1)
+    E.main_loop()
+    L, T = E.get_int(C.I_NUM_LINKS), E.get_int(C.I_TOTAL_TIMESTEPS)
+    arr = E.get_array(C.A_CUM_ARRIVAL).reshape(L, T)
+    dep = E.get_array(C.A_CUM_DEPARTURE).reshape(L, T)
+    assert (np.diff(arr, axis=1) >= 0).all() and (arr >= dep).all()
+    assert np.array_equal(arr[:, -1] - dep[:, -1], E.get_array(C.A_LINK_NUM_VEHICLES) * 5.0)
+    st = E.get_array(C.A_VEH_STATE)  # (the scenario is far over capacity by design: most platoons are still queued at the end)
+    assert (st == C.VS_END).sum() + (st == C.VS_RUN).sum() + (st == C.VS_WAIT).sum() == len(st)
+    assert (st == C.VS_END).sum() > 0
+    assert E.get_int(C.I_TRIPS_COMPLETED) == int((st == C.VS_END).sum())
+    assert int(arr[:, -1].sum() / 5.0) - int(dep[:, -1].sum() / 5.0) == int((st == C.VS_RUN).sum())

@@ -73,6 +73,7 @@ struct DevWorld {
     const int *vl_off[3], *vl_list[3];  // per-vehicle CSR: 0 specified_route, 1 links_preferred, 2 links_avoid
     const int *seg_link, *seg_start;
     const int *e_from, *e_to, *e_link;  // node-pair edges (leading link of each pair)
+    const int *ein_off, *ein_from, *ein_eid;  // the same edges grouped by their END node (CSR), for the frontier search
     int n_edges;
     // dynamic (per replica)
     int *head, *tail, *tail_k1, *pop_k2, *hcount, *trips, *ev_cnt;
@@ -1183,6 +1184,83 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp(const DevWorld *worlds) {
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
 }
 
+// Frontier (label-correcting worklist) variant for graphs whose rows fit in shared memory: only the in-edges of nodes
+// whose distance just improved are relaxed, so the work is ~E per destination instead of (sweeps x E).  Same fixed
+// point, hence the same dist / next as k_sssp and the oracle.  Shared memory: dist 8N + next 4N + queued flag N +
+// two uint16 worklists 4N = 17N bytes (N < 65536).
+__global__ void __launch_bounds__(SSSP_THREADS) k_sssp_frontier(const DevWorld *worlds) {
+#ifndef UX_EMU
+    LOAD_WORLD(W, worlds)
+    int row = (int)blockIdx.x;
+    if (row >= W.D) return;
+    int N = W.N, k = W.row_dest[row], E = W.n_edges;
+    extern __shared__ unsigned long long sssp_smem[];
+    unsigned long long *du = sssp_smem;
+    double *dist = reinterpret_cast<double *>(sssp_smem);
+    int *next = reinterpret_cast<int *>(sssp_smem + N);
+    unsigned short *fa = reinterpret_cast<unsigned short *>(next + N), *fb = fa + N;
+    unsigned char *inq = reinterpret_cast<unsigned char *>(fb + N);
+    __shared__ int nf_s[2];
+    const double *cost = W.pair_cost;
+    int tid = (int)threadIdx.x, nth = (int)blockDim.x;
+    for (int i = tid; i < N; i += nth) { dist[i] = (i == k) ? 0.0 : INFINITY; next[i] = 0x7fffffff; inq[i] = 0; }
+    if (tid == 0) { fa[0] = (unsigned short)k; nf_s[0] = 1; nf_s[1] = 0; }
+    __syncthreads();
+    int cur = 0;
+    while (true) {
+        int nf = nf_s[cur];
+        if (nf == 0) break;
+        unsigned short *F = cur ? fb : fa, *G = cur ? fa : fb;
+        for (int base = 0; base < nf; base += nth) {
+            int idx = base + tid, j = -1;
+            double dj = 0.0;
+            if (idx < nf) { j = F[idx]; dj = dist[j]; inq[j] = 0; }
+            __syncthreads();  // every queued flag of this chunk is cleared before anyone can re-queue
+            if (j >= 0) {
+                for (int q = __ldg(W.ein_off + j); q < __ldg(W.ein_off + j + 1); q++) {
+                    double c = __ldg(cost + __ldg(W.ein_eid + q));
+                    if (!(c > 0.0) || is_inf(c)) continue;
+                    int i = __ldg(W.ein_from + q);
+                    double nd = c + dj;
+                    if (nd < __longlong_as_double((long long)du[i])) {
+                        unsigned long long old = atomicMin(&du[i], (unsigned long long)__double_as_longlong(nd));
+                        if ((unsigned long long)__double_as_longlong(nd) < old) {
+                            unsigned int *w32 = reinterpret_cast<unsigned int *>(inq + (i & ~3));
+                            unsigned int bit = 1u << ((i & 3) * 8);
+                            if (!(atomicOr(w32, bit) & bit)) G[atomicAdd(&nf_s[cur ^ 1], 1)] = (unsigned short)i;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) nf_s[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+    int any = 0;
+    for (int e = tid; e < E; e += nth) {  // next hop: smallest node j with c_ij + dist[j] == dist[i]
+        double c = __ldg(cost + e);
+        if (!(c > 0.0) || is_inf(c)) continue;
+        int i = __ldg(W.e_from + e), j = __ldg(W.e_to + e);
+        if (i == k) continue;
+        double dj = dist[j];
+        if (is_inf(dj)) continue;
+        if (c + dj == dist[i]) { atomicMin(&next[i], j); any = 1; }
+    }
+    any = __syncthreads_or(any);
+    double *gdist = W.rdist + (size_t)row * N;
+    int *gnext = W.rnext + (size_t)row * N;
+    for (int i = tid; i < N; i += nth) {
+        int nx = next[i];
+        if (i == k) nx = k; else if (nx == 0x7fffffff) nx = -1;
+        gnext[i] = nx;
+        gdist[i] = dist[i];
+    }
+    if (tid == 0) W.has_path[row] = any ? 1 : 0;
+#endif
+}
+
 __global__ void __launch_bounds__(256) k_duo(const DevWorld *worlds, int gradual_step) {
     LOAD_WORLD(W, worlds)
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1704,6 +1782,14 @@ static int upload(ux_world *w) {
     w->n_edges = (int)e_link.size(); base.n_edges = w->n_edges;
     base.l_pair_first = dupload(w, pair_first); base.l_pair_off = dupload(w, pair_off); base.l_pair_list = dupload(w, pair_list);
     base.e_from = dupload(w, e_from); base.e_to = dupload(w, e_to); base.e_link = dupload(w, e_link);
+    {
+        int Ep = (int)e_link.size();
+        std::vector<int> ein_off(N + 1, 0), ein_from(Ep), ein_eid(Ep), fill(N, 0);
+        for (int e = 0; e < Ep; e++) ein_off[e_to[e] + 1]++;
+        for (int i = 0; i < N; i++) ein_off[i + 1] += ein_off[i];
+        for (int e = 0; e < Ep; e++) { int j = e_to[e], q = ein_off[j] + fill[j]++; ein_from[q] = e_from[e]; ein_eid[q] = e; }
+        base.ein_off = dupload(w, ein_off); base.ein_from = dupload(w, ein_from); base.ein_eid = dupload(w, ein_eid);
+    }
     // ---- nodes
     std::vector<int> out_off(N + 1, 0), in_off(N + 1, 0), out, in, sig_off(N + 1, 0), n_lanes(N), n_out_lanes(N);
     std::vector<double> n_sig, n_fc(N);
@@ -1806,8 +1892,15 @@ static void launch_sssp(ux_world *w, cudaStream_t st) {
 #ifdef UX_EMU
     UX_LAUNCH(k_sssp<false>, dim3(w->n_active, w->R), dim3(SSSP_THREADS), st, w->dworlds);
 #else
-    size_t bytes = (size_t)N * 12 + 16;
+    size_t bytes = (size_t)N * 12 + 16, fbytes = (size_t)((N + 3) & ~3) * 17 + 64;
     int use_smem = bytes <= 200 * 1024;
+    // small graphs converge in a few dozen whole-edge sweeps (cheaper than one barrier per wavefront); large sparse graphs
+    // are dominated by sweeps x E and switch to the worklist kernel
+    if (N >= 2048 && N < 65536 && fbytes <= 220 * 1024) {
+        if (fbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fbytes);
+        k_sssp_frontier<<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), fbytes, st>>>(w->dworlds);
+        return;
+    }
     if (use_smem && bytes > 48 * 1024) cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (use_smem) k_sssp<true><<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), bytes, st>>>(w->dworlds);
     else k_sssp<false><<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), 0, st>>>(w->dworlds);

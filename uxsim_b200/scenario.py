@@ -30,6 +30,7 @@ class Scenario:
     nodes: List[Dict[str, Any]] = field(default_factory=list)  # kwargs of addNode
     links: List[Dict[str, Any]] = field(default_factory=list)  # kwargs of addLink
     demands: List[Tuple] = field(default_factory=list)          # ("demand", o, d, t0, t1, flow, volume) | ("vehicle", o, d, t)
+    bulk_vehicles: Optional[Tuple] = None                       # (orig ids, dest ids, departure steps) appended after `demands`
 
     # ---- construction helpers (reference argument names) ------------------------------------------
     def addNode(self, name, x, y, signal=(0,), signal_offset=0, flow_capacity=None, number_of_lanes=None):
@@ -150,6 +151,8 @@ class Scenario:
                     flow = volume / (t1 - t0)
                 E.add_demand(nidx[o], nidx[dd], t0, t1, flow)
         flush()
+        if self.bulk_vehicles is not None:
+            E.add_vehicles(*self.bulk_vehicles)
         E.initialize_adj_matrix()
         return E
 
@@ -189,8 +192,9 @@ class Scenario:
             sg_off=sg_off, sg=np.array(sg, np.int32),
             d_orig=np.array([nidx[d[1]] for d in dem], np.int32), d_dest=np.array([nidx[d[2]] for d in dem], np.int32),
             d_t0=np.array([d[3] for d in dem], np.float64), d_t1=np.array([d[4] for d in dem], np.float64), d_flow=flow,
-            v_orig=np.array([nidx[d[1]] for d in veh], np.int32), v_dest=np.array([nidx[d[2]] for d in veh], np.int32),
-            v_ts=np.array([int(d[3] / dt) for d in veh], np.int32),
+            v_orig=np.concatenate([np.array([nidx[d[1]] for d in veh], np.int32)] + ([self.bulk_vehicles[0]] if self.bulk_vehicles else [])),
+            v_dest=np.concatenate([np.array([nidx[d[2]] for d in veh], np.int32)] + ([self.bulk_vehicles[1]] if self.bulk_vehicles else [])),
+            v_ts=np.concatenate([np.array([int(d[3] / dt) for d in veh], np.int32)] + ([self.bulk_vehicles[2]] if self.bulk_vehicles else [])),
         )
 
     def engine_from_tables(self, api, tab: Dict[str, np.ndarray], **over):
@@ -447,9 +451,7 @@ def grid_random_od(n=100, n_platoons=1_000_000, deltan=5, tmax=7200, demand_t=36
         d[same] = rng.integers(0, n * n, int(same.sum()))
         same = o == d
     t = rng.uniform(0, demand_t, n_platoons)
-    s._bulk_vehicles = (o.astype(np.int32), d.astype(np.int32), t)
-    for k in range(n_platoons):
-        s.demands.append(("vehicle", str(int(o[k])), str(int(d[k])), float(t[k])))
+    s.bulk_vehicles = (o.astype(np.int32), d.astype(np.int32), (t / s.delta_t).astype(np.int32))  # addVehicle: step = int(t/dt), uxsim.py:1045-1048
     return s
 
 

@@ -208,7 +208,10 @@ enum {
 };
 /* engine options (product only; the test libraries accept and ignore them) */
 enum {
-    UX_OPT_KERNEL_TIMING = 1    /* 1: launch kernels eagerly with a CUDA-event pair around each (for roofline numbers) */
+    UX_OPT_KERNEL_TIMING = 1,   /* 1: launch kernels eagerly with a CUDA-event pair around each (for roofline numbers) */
+    UX_OPT_ALL_DESTINATIONS = 2 /* 1 (before the first main_loop): keep route preferences for every node, as the reference does,
+                                   instead of only for the destinations present in the demand.  Needed only if demand towards
+                                   NEW destinations will be added between main_loop calls. */
 };
 UX_API int UX_FN(set_option)(ux_world *w, int option, double value);
 

@@ -159,3 +159,61 @@ def test_c4_full_size_properties(cuda_api):
     assert (st == C.VS_END).sum() > 0
     assert E.get_int(C.I_TRIPS_COMPLETED) == int((st == C.VS_END).sum())
     assert int(arr[:, -1].sum() / 5.0) - int(dep[:, -1].sum() / 5.0) == int((st == C.VS_RUN).sum())
+
+
+@pytest.mark.parametrize("log", [-1, 1])
+def test_demand_added_between_chunks(log, cuda_api, oracle_api):
+    """adddemand / addVehicle after the simulation started (the reference rebuilds its departure buckets on every
+    main_loop and clamps past-due departures to the chunk start, traffi.cpp:1663-1676)."""
+    sc = S.grid(n=5, seed=9, tmax=3000, demand_t=1000)
+    nidx = sc.node_index()
+    Es = [sc.to_engine(api, vehicle_logging_timestep_interval=log) for api in (cuda_api, oracle_api)]
+    for E in Es:
+        E.main_loop(until_t=700)
+        E.add_demand(nidx["n(0, 0)"], nidx["n(4, 4)"], 300, 1500, 0.3)
+        E.add_vehicles([nidx["n(4, 0)"], nidx["n(0, 2)"]], [nidx["n(0, 4)"], nidx["n(4, 2)"]], [10, 400])
+        E.main_loop(until_t=1400)
+        E.add_demand(nidx["n(2, 0)"], nidx["n(2, 4)"], 1500, 2000, 0.2)
+        E.main_loop()
+    assert compare_engines(Es[0], Es[1]) == []
+    if log > 0:
+        assert compare_logs(Es[0], Es[1]) == []
+
+
+def test_new_destination_midrun_needs_all_destinations(cuda_api, oracle_api):
+    sc = S.straight_3link_spillback()
+    E = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)
+    E.main_loop(until_t=300)
+    E.add_vehicles([0], [1], [100])  # node 1 was never a destination
+    with pytest.raises(RuntimeError):
+        E.main_loop()
+    kw = sc.engine_kwargs(vehicle_logging_timestep_interval=-1)
+    Es = []
+    for api in (cuda_api, oracle_api):
+        E = sc.to_engine(api, vehicle_logging_timestep_interval=-1)
+        Es.append(E)
+    # with the option the same sequence is exact
+    E2 = C.EngineWorld(cuda_api, **kw)
+    E2.set_option(C.OPT_ALL_DESTINATIONS, 1)
+    for n in sc.nodes:
+        E2.add_node(n["x"], n["y"], n["signal"], n["signal_offset"])
+    nidx = sc.node_index()
+    for l in sc.links:
+        E2.add_link(nidx[l["start_node"]], nidx[l["end_node"]], l["free_flow_speed"], l["jam_density"], l["length"], l["number_of_lanes"],
+                    l["merge_priority"], -1.0 if l["capacity_out"] is None else l["capacity_out"], -1.0 if l["capacity_in"] is None else l["capacity_in"])
+    for d in sc.demands:
+        E2.add_demand(nidx[d[1]], nidx[d[2]], d[3], d[4], d[5])
+    E2.initialize_adj_matrix()
+    Eo = Es[1]
+    for E in (E2, Eo):
+        E.main_loop(until_t=300)
+        E.add_vehicles([0], [1], [100])
+        E.main_loop()
+    assert compare_engines(E2, Eo, fields=[f for f in __import__("parity").EXACT_FIELDS if f[0] not in ("route_pref", "route_next")]) == []
+
+
+def test_large_graph_worklist_shortest_paths(cuda_api, oracle_api):
+    """N >= 2048 nodes switches route search to the frontier (worklist) kernel: same fixed point, same results."""
+    sc = S.grid_random_od(n=46, n_platoons=6000, tmax=2400, demand_t=900, seed=5)
+    Eg, Eo = run_pair(sc, cuda_api, oracle_api)
+    assert compare_engines(Eg, Eo) == []

@@ -1391,6 +1391,8 @@ struct ux_world {
     long long launches = 0, C = 0; int nseg = 0, n_edges = 0;
     std::vector<int> dest_row, row_dest;
     long long P_uploaded = 0;
+    bool all_dests = false;
+    std::vector<int> h_gen_off, h_gen_list, eff_ts;  // host copies of the per-origin FIFO lists; effective departure step per platoon
 #ifndef UX_EMU
     std::map<long long, std::pair<cudaGraphExec_t, long long>> graphs;  // key -> (executable graph, kernels per launch)
 #endif
@@ -1569,6 +1571,10 @@ UX_API int64_t ux_add_demands(ux_world *w, int64_t n, const int *o, const int *d
 }
 UX_API int ux_set_option(ux_world *w, int option, double value) {
     if (option == UX_OPT_KERNEL_TIMING) { w->ktiming = value != 0.0; return 0; }
+    if (option == UX_OPT_ALL_DESTINATIONS) {
+        if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "UX_OPT_ALL_DESTINATIONS must be set before the first main_loop");
+        w->all_dests = value != 0.0; return 0;
+    }
     return fail(w, UX_ERR_INVALID, "unknown option %d", option);
 }
 
@@ -1817,6 +1823,8 @@ static int upload(ux_world *w) {
         for (long long q = 0; q < P; q++) { long long i = order[q]; gen_list[gen_off[v_orig[i]] + fill[v_orig[i]]++] = (int)i; }
     }
     for (long long i = 0; i < P; i++) if (w->dest_row[v_dest[i]] < 0) w->dest_row[v_dest[i]] = 0;
+    if (w->all_dests) for (int i = 0; i < N; i++) w->dest_row[i] = 0;
+    w->h_gen_off = gen_off; w->h_gen_list = gen_list; w->eff_ts = v_ts;
     for (int i = 0; i < N; i++) if (w->dest_row[i] == 0) { w->dest_row[i] = (int)w->row_dest.size(); w->row_dest.push_back(i); }
     int D = (int)w->row_dest.size(); w->n_active = D; base.D = D;
     base.v_orig = dupload(w, v_orig); base.v_dest = dupload(w, v_dest); base.v_depart_ts = dupload(w, v_ts);
@@ -1916,6 +1924,87 @@ static void launch_sssp(ux_world *w, cudaStream_t st) {
         w->kt_events.push_back(a_); w->kt_events.push_back(b_); w->kt_ids.push_back(kid); cudaEventRecord(a_, st); }
 #define KT_END(kid) if (w->ktiming) cudaEventRecord(w->kt_events.back(), st);
 #endif
+// Vehicles added between main_loop calls (adddemand after the start; traffi.cpp:1663-1676 rebuilds the departure
+// buckets on every call and clamps past-due departures to the first step of the chunk).  All per-platoon device arrays
+// grow (old contents copied), the per-origin FIFO lists are rebuilt behind their already-released prefix, and the
+// cached graphs are dropped.  Destinations must already have a route-preference row (see UX_OPT_ALL_DESTINATIONS).
+}  // extern "C" (templates need C++ linkage)
+template <typename T>
+static T *dgrow(ux_world *w, T *old, size_t oldn, size_t newn, int fill_byte) {
+    T *p = dalloc<T>(w, newn, false);
+    if (!p) return nullptr;
+    cudaMemset(p, fill_byte, (newn ? newn : 1) * sizeof(T));
+    if (old && oldn) cudaMemcpy(p, old, oldn * sizeof(T), cudaMemcpyDeviceToDevice);
+    return p;
+}
+extern "C" {
+
+static int extend_vehicles(ux_world *w) {
+    cudaSetDevice(w->device);
+    int N = (int)w->nodes.size(), T = w->total_ts, start_ts = w->timestep;
+    long long P0 = w->P_uploaded, P = (long long)w->vehs.size();
+    for (long long i = P0; i < P; i++) if (w->dest_row[w->vehs[i].dest] < 0)
+        return fail(w, UX_ERR_RUNTIME, "vehicle %lld added after the start has destination node %d, which had no demand before: set UX_OPT_ALL_DESTINATIONS "
+                    "(World(..., all_destinations=True)) before the first exec_simulation", i, w->vehs[i].dest);
+    w->eff_ts.resize(P);
+    for (long long i = P0; i < P; i++) w->eff_ts[i] = std::max(w->vehs[i].ts, start_ts);  // traffi.cpp:1673
+    // per-origin lists: keep the released prefix, merge the rest with the new platoons by (effective step, id)
+    std::vector<std::vector<int>> lists(N);
+    for (int o = 0; o < N; o++) lists[o].assign(w->h_gen_list.begin() + w->h_gen_off[o], w->h_gen_list.begin() + w->h_gen_off[o + 1]);
+    std::vector<size_t> released(N, 0);
+    for (int o = 0; o < N; o++) { size_t r = 0; while (r < lists[o].size() && w->eff_ts[lists[o][r]] <= start_ts - 1) r++; released[o] = r; }
+    for (long long i = P0; i < P; i++) lists[w->vehs[i].orig].push_back((int)i);
+    for (int o = 0; o < N; o++)
+        std::stable_sort(lists[o].begin() + released[o], lists[o].end(), [&](int a, int b) { return w->eff_ts[a] < w->eff_ts[b]; });
+    std::vector<int> gen_off(N + 1, 0), gen_list, gen_ts, v_orig(P), v_dest(P), v_ts(P);
+    for (int o = 0; o < N; o++) { gen_off[o + 1] = gen_off[o] + (int)lists[o].size(); gen_list.insert(gen_list.end(), lists[o].begin(), lists[o].end()); }
+    gen_ts.resize(gen_list.size());
+    for (size_t q = 0; q < gen_list.size(); q++) gen_ts[q] = w->eff_ts[gen_list[q]];
+    for (long long i = 0; i < P; i++) { v_orig[i] = w->vehs[i].orig; v_dest[i] = w->vehs[i].dest; v_ts[i] = w->vehs[i].ts; }
+    w->h_gen_off = gen_off; w->h_gen_list = gen_list;
+    const int *d_orig = dupload(w, v_orig), *d_dest = dupload(w, v_dest), *d_ts = dupload(w, v_ts);
+    const int *d_goff = dupload(w, gen_off), *d_glist = dupload(w, gen_list), *d_gts = dupload(w, gen_ts);
+    const int *vl_off[3] = {nullptr, nullptr, nullptr}, *vl_list[3] = {nullptr, nullptr, nullptr};
+    for (int kind = 0; kind < 3; kind++) {
+        if (w->vlinks[kind].empty()) continue;
+        std::vector<int> off(P + 1, 0), list;
+        for (long long i = 0; i < P; i++) {
+            auto it = w->vlinks[kind].find(i);
+            if (it != w->vlinks[kind].end()) list.insert(list.end(), it->second.begin(), it->second.end());
+            off[i + 1] = (int)list.size();
+        }
+        vl_off[kind] = dupload(w, off); vl_list[kind] = dupload(w, list);
+    }
+    long long extra_log = 0;
+    for (long long i = P0; i < P; i++) extra_log += std::max(0, T - w->eff_ts[i] - 1);
+    for (int r = 0; r < w->R; r++) {
+        DevWorld &d = w->hw[r];
+        d.P = P; d.v_orig = d_orig; d.v_dest = d_dest; d.v_depart_ts = d_ts; d.gen_off = d_goff; d.gen_list = d_glist; d.gen_ts = d_gts;
+        for (int kind = 0; kind < 3; kind++) { d.vl_off[kind] = vl_off[kind]; d.vl_list[kind] = vl_list[kind]; }
+        d.v_state = dgrow(w, d.v_state, P0, P, 0); d.v_next = dgrow(w, d.v_next, P0, P, 0); d.v_link = dgrow(w, d.v_link, P0, P, 0xff);
+        d.v_arr_ts = dgrow(w, d.v_arr_ts, P0, P, 0xff); d.v_trav = dgrow(w, d.v_trav, P0, P, 0);
+        d.v_mr = dgrow(w, d.v_mr, P0, P, 0); d.v_atl = dgrow(w, d.v_atl, P0, P, 0); d.v_dist = dgrow(w, d.v_dist, P0, P, 0); d.v_entry_x = dgrow(w, d.v_entry_x, P0, P, 0);
+        d.v_flags = dgrow(w, d.v_flags, P0, P, 0);
+        { double *tt = dgrow(w, d.v_tt, P0, P, 0); std::vector<double> m1(P - P0, -1.0); if (tt) cudaMemcpy(tt + P0, m1.data(), sizeof(double) * (P - P0), cudaMemcpyHostToDevice); d.v_tt = tt; }
+        if (d.no_cyclic) d.v_visited = dgrow(w, d.v_visited, (size_t)P0 * d.vis_words, (size_t)P * d.vis_words, 0);
+        if (d.log_mode) {
+            d.v_gen_ts = dgrow(w, d.v_gen_ts, P0, P, 0xff); d.v_end_ts = dgrow(w, d.v_end_ts, P0, P, 0xff); d.v_end_kind = dgrow(w, d.v_end_kind, P0, P, 0);
+            unsigned long long cnt = 0; cudaMemcpy(&cnt, d.lg_count, sizeof(cnt), cudaMemcpyDeviceToHost);
+            long long ncap = d.lg_cap + extra_log;
+            d.lg_vid = dgrow(w, d.lg_vid, cnt, ncap, 0); d.lg_t = dgrow(w, d.lg_t, cnt, ncap, 0); d.lg_link = dgrow(w, d.lg_link, cnt, ncap, 0); d.lg_lane = dgrow(w, d.lg_lane, cnt, ncap, 0);
+            d.lg_x = dgrow(w, d.lg_x, cnt, ncap, 0); d.lg_v = dgrow(w, d.lg_v, cnt, ncap, 0); d.lg_s = dgrow(w, d.lg_s, cnt, ncap, 0);
+            d.lg_cap = ncap;
+            if (!d.lg_vid || !d.lg_s) return fail(w, UX_ERR_CUDA, "device allocation failed while growing the vehicle logs");
+        }
+        if (!d.v_state || !d.v_tt || !d.v_flags || !d.v_entry_x) return fail(w, UX_ERR_CUDA, "device allocation failed while adding vehicles");
+    }
+    CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaDeviceSynchronize());
+    w->P_uploaded = P;
+    w->logs.replica = -1;
+    return 0;
+}
+
 // enqueue the kernels of `nsteps` timesteps starting at phase (t mod route_ts) = `phase` on the stream
 static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
     int N = (int)w->nodes.size(), R = w->R;
@@ -1967,7 +2056,7 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
     if (end_ts <= start_ts) return 0;
     cudaSetDevice(w->device);
     if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
-    if ((long long)w->vehs.size() != w->P_uploaded) return fail(w, UX_ERR_RUNTIME, "adding vehicles after the simulation started is not supported yet by the CUDA engine");
+    if ((long long)w->vehs.size() != w->P_uploaded) { int rc = extend_vehicles(w); if (rc) return rc; }
     if (w->net_dirty) { int rc = upload_link_params(w); if (rc) return rc; w->net_dirty = false; }
 #ifndef UX_EMU
     if (!w->ev_begin) { CUDA_OK(cudaEventCreate(&w->ev_begin)); CUDA_OK(cudaEventCreate(&w->ev_end)); }
@@ -2189,8 +2278,8 @@ static int build_logs(ux_world *w, int replica) {
     G.ltl_t.clear(); G.ltl_id.clear(); G.enter_t.clear(); G.enter_link.clear(); G.enter_veh.clear();
     for (long long i = 0; i < P; i++) {
         G.offsets[i] = (long long)G.t.size(); G.ltl_offsets[i] = (long long)G.ltl_t.size();
-        int ts0 = w->vehs[i].ts;
-        G.ltl_t.push_back((double)ts0 * dt); G.ltl_id.push_back(-1);  // home entry (traffi.cpp:2059-2061)
+        int ts0 = w->eff_ts[i];
+        G.ltl_t.push_back((double)w->vehs[i].ts * dt); G.ltl_id.push_back(-1);  // home entry (traffi.cpp:2059-2061)
         if (ts0 < Tnow) {
             G.n_missing[i] = ((double)ts0 * dt > 0) ? (int)(((double)ts0 * dt) / dt) : 0;
             auto push = [&](int tstep, int state, double x, double v, double s_, int lane, int link) {
@@ -2363,7 +2452,7 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         std::vector<int> st(P); if (P) CUDA_OK(cudaMemcpy(st.data(), d.v_state, sizeof(int) * P, cudaMemcpyDeviceToHost));
         for (long long i = 0; i < P; i++) {
             int s = st[i];
-            if (s == UX_VS_HOME && w->vehs[i].ts <= w->timestep - 1) s = UX_VS_WAIT;
+            if (s == UX_VS_HOME && w->eff_ts[i] <= w->timestep - 1) s = UX_VS_WAIT;
             oi[i] = s;
         }
         break; }

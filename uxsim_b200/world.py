@@ -484,7 +484,7 @@ class CudaWorld:
                  eular_dt=120, eular_dx=100, random_seed=None, print_mode=1, save_mode=1, show_mode=0, show_progress=1,
                  show_progress_deltat=600, tmax=None, vehicle_logging_timestep_interval=1, reduce_memory_delete_vehicle_route_pref=False,
                  hard_deterministic_mode=False, no_cyclic_routing=False, adjust_node_capacity=False, meta_data=None,
-                 user_attribute=None, user_function=None, threads=1, num_replicas=1, device=-1):
+                 user_attribute=None, user_function=None, threads=1, num_replicas=1, device=-1, all_destinations=False):
         self.W = self
         self.rng = np.random.default_rng(seed=random_seed)
         self.random_seed = random_seed
@@ -519,6 +519,8 @@ class CudaWorld:
             route_choice_update_gradual=route_choice_update_gradual, no_cyclic_routing=no_cyclic_routing,
             adjust_node_capacity=adjust_node_capacity, instantaneous_TT_timestep_interval=int(instantaneous_TT_timestep_interval),
             num_replicas=num_replicas, device=device)
+        if all_destinations:  # keep route preferences for every node (needed to add demand to NEW destinations mid-run)
+            self._E.set_option(C.OPT_ALL_DESTINATIONS, 1)
         self._cache = {}
         self._veh_by_index = []
         self._simulation_done = False

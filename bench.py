@@ -280,8 +280,7 @@ def main():
         tot_ms = sum(kms.values())
         alg = {
             "k_update": ALG_BYTES["per_platoon_update"] * upd,
-            "k_pre": (ALG_BYTES["per_link_step"] * L + ALG_BYTES["per_node_step"] * N) * T * R,
-            "k_transfer": ALG_BYTES["per_transfer"] * events,
+            "k_node": (ALG_BYTES["per_link_step"] * L + ALG_BYTES["per_node_step"] * N) * T * R + ALG_BYTES["per_transfer"] * events,
         }
         peaks = {}
         try:

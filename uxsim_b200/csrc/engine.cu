@@ -15,11 +15,11 @@
 //   * time series are time-major [T][L] so one step writes one contiguous row.
 //   * R replicas (seeds) = R DevWorld structs sharing the static network arrays; blockIdx.y = replica.
 //
-// Timestep = 3 kernels (+ route update every DELTAT_ROUTE steps), replayed from CUDA graphs:
-//   k_pre      warp per node : Link::update of the node's out-links, Node::generate, signal, node capacity
-//   k_transfer warp per node : Node::transfer, one launch per dependency level (see DESIGN.md "transfer order")
-//   k_update   thread per ring slot : car_follow_newell + Vehicle::update; one thread per link also handles the
-//              link head (trip end, abort, next-link choice)
+// Timestep = 2 kernels (+ route update every DELTAT_ROUTE steps), replayed from CUDA graphs:
+//   k_node     warp per node : Link::update of the link sides the node owns, Node::generate, signal, node capacity,
+//              then Node::transfer; all dependency levels in one launch (see DESIGN.md "transfer order")
+//   k_update   warp per (link, part) : car_follow_newell + Vehicle::update for the occupied positions; the part-0
+//              warp also handles the link head (trip end, abort, next-link choice) and the per-step log records
 //   k_edge_cost / k_sssp / k_duo(+finish) : update_adj_time_matrix, route_search_all, route_choice_duo
 #include <cstdint>
 #include <cstdio>
@@ -311,24 +311,20 @@ UX_DEV double warp_queue_vsum(const DevWorld &W, int l, int hd, int n, int lane)
 // K1: Link::update (traffi.cpp:542-565, 599-622) for the node's out-links, then Node::generate (105-189),
 //     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
 // ---------------------------------------------------------------------------------------------------
+template <int MC, int MD>
 struct PreSmem {
-    int choice[UX_MAXC], g_vid[UX_MAXC], g_err[UX_MAXC];
-    int o_hd[UX_MAXDEG], o_tail[UX_MAXDEG], o_lanes[UX_MAXDEG], o_cap[UX_MAXDEG], o_lastlane[UX_MAXDEG], o_win_off[UX_MAXDEG + 1], o_win_n[UX_MAXDEG];
-    long long o_roff[UX_MAXDEG];
-    double o_ci[UX_MAXDEG], o_dpl[UX_MAXDEG], o_vmax[UX_MAXDEG], o_cumarr[UX_MAXDEG];
-    double w_x[UX_MAXC];
+    int choice[MC], g_vid[MC], g_err[MC];
+    int o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD];
+    long long o_roff[MD];
+    double o_ci[MD], o_dpl[MD], o_vmax[MD], o_cumarr[MD];
+    double w_x[MC];
 };
 
-__global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_off) {
-    LOAD_WORLD(W, worlds)
-    WARP_BEGIN
-    __shared__ double tt_all[4][UX_MAXDEG];
-    __shared__ PreSmem ps_all[4];
-    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
-    if (warp >= W.N) return;
-    double *tt_s = tt_all[(threadIdx.x >> 5) & 3];
-    int n = warp, t = *W.t_base + step_off, cur = t & 1, L = W.L;
+template <int MC, int MD>
+UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *rel, int n, int t, int lane) {
+    int cur = t & 1, L = W.L;
     int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
+    int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     bool fresh = (t % W.itt) == 0;
     // ---- instantaneous travel time of the out-links (whole warp per link, only every `itt` steps)
     if (fresh) {
@@ -345,29 +341,32 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
         }
         WARP_SYNC();
     }
-    // ---- scalar link update, one lane per out-link
+    // ---- scalar link update (Link::update traffi.cpp:542-565).  A link's inflow side (arrival curve, capacity_in
+    //      tokens, instantaneous travel time) belongs to its START node, its outflow side (departure curve, capacity_out
+    //      tokens, pops of this step) to its END node -- the same ownership the transfer uses, so that this node's whole
+    //      timestep (update, generate, signal, transfer) needs nothing from other nodes except the dependency wait.
     WARP_FOR(ln) {
         for (int k = ln; k < nout; k += 32) {
             int l = W.n_out[o0 + k];
             size_t row = (size_t)t * L + l;
             if (fresh) W.tt_inst[row] = tt_s[k];
             else if (t > 0) W.tt_inst[row] = W.tt_inst[row - L];
-            if (t != 0) { W.cum_arr[row] = W.cum_arr[row - L]; W.cum_dep[row] = W.cum_dep[row - L]; }
-            int lanes = W.l_lanes[l];
-            double co = W.l_cap_out[l], ci = W.l_cap_in[l];
-            if (co < 10e9) { if (W.cap_out_rem[l] < W.dn * lanes) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
-            if (ci < 10e9) { if (W.cap_in_rem[l] < W.dn * lanes) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+            if (t != 0) W.cum_arr[row] = W.cum_arr[row - L];
+            double ci = W.l_cap_in[l];
+            if (ci < 10e9) { if (W.cap_in_rem[l] < W.dn * W.l_lanes[l]) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+        }
+        for (int k = ln; k < nin; k += 32) {
+            int l = W.n_in[i0 + k];
+            size_t row = (size_t)t * L + l;
+            if (t != 0) W.cum_dep[row] = W.cum_dep[row - L];
+            double co = W.l_cap_out[l];
+            if (co < 10e9) { if (W.cap_out_rem[l] < W.dn * W.l_lanes[l]) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
             W.pop_k2[l] = 0;
         }
     }
     WARP_SYNC();
-#ifndef UX_EMU
-    __threadfence_block();
-#endif
     // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
     //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
-    __shared__ int rel_all[4];
-    int *rel = &rel_all[(threadIdx.x >> 5) & 3];
     int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
     while (av < glen) {
         WARP_FOR(ln) if (ln == 0) *rel = 0;
@@ -381,10 +380,9 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
     }
     // ---- generate (traffi.cpp:105-189).  The route draws of the first `natt` waiting platoons and the tail state of the
     //      out-links are fetched in parallel; lane 0 then walks the attempts on shared memory and stops at the first refusal.
-    PreSmem &G = ps_all[(threadIdx.x >> 5) & 3];
     int gh = W.gen_head[n];
     int natt = av - gh;
-    { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > UX_MAXC) natt = UX_MAXC; }
+    { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > MC) natt = MC; }
     if (nout == 0) natt = 0;
     if (natt > 0) {
         WARP_FOR(ln) {
@@ -411,7 +409,7 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
         WARP_SYNC();
         WARP_FOR(ln) {
             int tot = G.o_win_off[nout];
-            for (int e = ln; e < tot && e < UX_MAXC; e += 32) {
+            for (int e = ln; e < tot && e < MC; e += 32) {
                 int q = 0;
                 while (G.o_win_off[q + 1] <= e) q++;
                 int k = e - G.o_win_off[q];
@@ -468,23 +466,25 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
         }
         WARP_SYNC();
     }
-    if (lane != 0) return;
-    W.gen_avail[n] = av;
-    for (int k = 0; k < nout; k++) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; }
-    // ---- signal
-    int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
-    int ph = W.sig_phase[n];
-    if (nsig > 1) {
-        double st = W.sig_t[n];
-        if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
-        st += W.dt;
-        W.sig_t[n] = st; W.sig_phase[n] = ph;
+    WARP_FOR(ln) if (ln == 0) {
+        W.gen_avail[n] = av;
+        for (int k = 0; k < nout; k++) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; }
+        // ---- signal (Node::signal_update traffi.cpp:194-207)
+        int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
+        int ph = W.sig_phase[n];
+        if (nsig > 1) {
+            double st = W.sig_t[n];
+            if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
+            st += W.dt;
+            W.sig_t[n] = st; W.sig_phase[n] = ph;
+        }
+        W.sig_log[(size_t)t * W.N + n] = ph;
+        // ---- node flow capacity (Node::flow_capacity_update traffi.cpp:226-234)
+        double fc = W.n_fc[n];
+        if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
+        else W.fc_rem[n] = 10e10;
     }
-    W.sig_log[(size_t)t * W.N + n] = ph;
-    // ---- node flow capacity
-    double fc = W.n_fc[n];
-    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
-    else W.fc_rem[n] = 10e10;
+    WARP_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -498,32 +498,34 @@ __global__ void __launch_bounds__(128) k_pre(const DevWorld *worlds, int step_of
 // and the lanes write the per-link accumulators back in parallel.  A dependent chain of a few hundred global
 // loads becomes five.
 // ---------------------------------------------------------------------------------------------------
+template <int MC, int MD>
 struct XferSmem {
     // in-links
-    int il[UX_MAXDEG], hd[UX_MAXDEG], hc[UX_MAXDEG], cap[UX_MAXDEG], popped[UX_MAXDEG], pos_off[UX_MAXDEG + 1], evc[UX_MAXDEG], trips[UX_MAXDEG];
-    long long roff[UX_MAXDEG];
-    double co_rem[UX_MAXDEG], mp[UX_MAXDEG], vmax[UX_MAXDEG], cumdep[UX_MAXDEG];
-    unsigned char sig_ok[UX_MAXDEG];
+    int il[MD], hd[MD], hc[MD], cap[MD], popped[MD], pos_off[MD + 1], evc[MD], trips[MD];
+    long long roff[MD];
+    double co_rem[MD], mp[MD], vmax[MD], cumdep[MD];
+    unsigned char sig_ok[MD];
     // head positions of the in-links
-    int p_vid[UX_MAXC], p_next[UX_MAXC], p_dts[UX_MAXC];
-    short p_in[UX_MAXC], p_j[UX_MAXC], c_idx[UX_MAXC], expd[UX_MAXC];
-    unsigned char p_flag[UX_MAXC];
-    double p_x[UX_MAXC], p_xold[UX_MAXC], p_v[UX_MAXC], p_mr[UX_MAXC], p_atl[UX_MAXC], p_ex[UX_MAXC], p_dist[UX_MAXC];
+    int p_vid[MC], p_next[MC], p_dts[MC];
+    short p_in[MC], p_j[MC], c_idx[MC], expd[MC];
+    unsigned char p_flag[MC];
+    double p_x[MC], p_xold[MC], p_v[MC], p_mr[MC], p_atl[MC], p_ex[MC], p_dist[MC];
     int nc, npos, nol, any_wait, nexp, first, cur_slot, n_picks;
-    int omask[UX_MAXDEG][2];          // per requested out-link: candidates currently eligible to move onto it
-    unsigned char ogood[UX_MAXDEG];   // per requested out-link: acceptance test result
-    unsigned char c_first[UX_MAXC], c_q[UX_MAXC];
+    int omask[MD][2];          // per requested out-link: candidates currently eligible to move onto it
+    unsigned char ogood[MD];   // per requested out-link: acceptance test result
+    unsigned char c_first[MC], c_q[MC];
     double fc_rem;
-    short shuf_j[UX_MAXC];
-    double u_merge[UX_MAXC];
+    short shuf_j[MC];
+    double u_merge[MC];
     // requested out-links
-    int ol[UX_MAXDEG], o_hd[UX_MAXDEG], o_tail[UX_MAXDEG], o_lanes[UX_MAXDEG], o_cap[UX_MAXDEG], o_lastlane[UX_MAXDEG], o_win_off[UX_MAXDEG + 1], o_win_n[UX_MAXDEG];
-    long long o_roff[UX_MAXDEG];
-    double o_ci[UX_MAXDEG], o_dpl[UX_MAXDEG], o_len[UX_MAXDEG], o_vmax[UX_MAXDEG], o_cumarr[UX_MAXDEG];
-    double w_x[UX_MAXC], w_xold[UX_MAXC];  // window of the last `lanes` platoons of each out-link (oldest first)
+    int ol[MD], o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD];
+    long long o_roff[MD];
+    double o_ci[MD], o_dpl[MD], o_len[MD], o_vmax[MD], o_cumarr[MD];
+    double w_x[MC], w_xold[MC];  // window of the last `lanes` platoons of each out-link (oldest first)
 };
 
-UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem &S, int p, int t) {  // Vehicle::end_trip traffi.cpp:886-927
+template <int MC, int MD>
+UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem<MC, MD> &S, int p, int t) {  // Vehicle::end_trip traffi.cpp:886-927
     int ii = S.p_in[p], il = S.il[ii], vid = S.p_vid[p];
     S.trips[ii] += 1;
     S.cumdep[ii] += W.dn;
@@ -547,7 +549,8 @@ UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem &S, int p, int t) {  // Ve
 }
 
 #define XFER_WARPS 4
-UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
+template <int MC, int MD>
+UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
     int cur = t & 1, L = W.L;
     size_t C = (size_t)W.C;
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
@@ -574,7 +577,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
     WARP_FOR(lane) if (lane == 0) {
         int acc = 0;
         for (int ii = 0; ii < nin; ii++) { S.pos_off[ii] = acc; acc += S.hc[ii]; }
-        S.pos_off[nin] = acc; S.npos = acc < UX_MAXC ? acc : UX_MAXC;
+        S.pos_off[nin] = acc; S.npos = acc < MC ? acc : MC;
     }
     WARP_SYNC();
     int npos = S.npos;
@@ -629,7 +632,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
     WARP_SYNC();
     WARP_FOR(lane) if (lane == 0) {
         int nol = 0;
-        for (int k = 0; k < S.nc; k++) if (S.c_first[k] && nol < UX_MAXDEG) S.ol[nol++] = S.p_next[S.c_idx[k]];
+        for (int k = 0; k < S.nc; k++) if (S.c_first[k] && nol < MD) S.ol[nol++] = S.p_next[S.c_idx[k]];
         S.nol = nol;
     }
     WARP_SYNC();
@@ -641,6 +644,24 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
             for (int r = 0; r < nol; r++) if (S.ol[r] == nl) { q = r; break; }
             S.c_q[k] = (unsigned char)q;
         }
+    }
+    // ---- dependency wait (only nodes with SEES_POPS out-links): everything above -- in-link heads, candidate sort -- is
+    //      independent of the lower-level nodes, so it overlaps their work; only the out-link tail state needs their pops.
+    if (has_deps) {
+        WARP_FOR(lane) {
+            for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
+                volatile int *done = W.node_done + W.dep_list[q];
+#ifdef UX_EMU
+                if (*done < t + 1) dev_error(W, DERR_RING_FULL, -1);
+#else
+                while (*done < t + 1) __nanosleep(32);
+#endif
+            }
+        }
+#ifndef UX_EMU
+        __threadfence();
+#endif
+        WARP_SYNC();
     }
     // ---- A4: out-link tail state
     WARP_FOR(lane) {
@@ -668,7 +689,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
     WARP_SYNC();
     WARP_FOR(lane) {
         int tot = S.o_win_off[nol];
-        for (int e = lane; e < tot && e < UX_MAXC; e += 32) {
+        for (int e = lane; e < tot && e < MC; e += 32) {
             int q = 0;
             while (S.o_win_off[q + 1] <= e) q++;
             int k = e - S.o_win_off[q];
@@ -686,7 +707,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
     //          the node (shuffle indices, merge-lottery uniforms) are drawn up front in parallel: Philox is stateless.
     WARP_FOR(lane) if (lane == 0) {
         int nexp = 0;
-        for (int q = 0; q < nol; q++) for (int r = 0; r < S.o_lanes[q] && nexp < UX_MAXC; r++) S.expd[nexp++] = (short)q;
+        for (int q = 0; q < nol; q++) for (int r = 0; r < S.o_lanes[q] && nexp < MC; r++) S.expd[nexp++] = (short)q;
         S.nexp = nexp;
     }
     WARP_SYNC();
@@ -754,7 +775,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
             int sz = S.o_tail[q] - S.o_hd[q], w0 = S.o_win_off[q];
             double fc_rem = S.fc_rem;
             int n_picks = S.n_picks;
-            short mv[UX_MAXC]; double mp[UX_MAXC]; int nm = 0;
+            short mv[MC]; double mp[MC]; int nm = 0;
             for (int wd = 0; wd < 2; wd++) {  // eligible candidates in ascending vehicle id
                 unsigned m = wd ? m1 : m0;
                 while (m) {
@@ -853,36 +874,37 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem &S, int n, int t) {
     }
 }
 
+// k_node: one warp runs a node's whole timestep -- Link::update of the sides it owns, Node::generate, signal, node
+// capacity (pre_node) and Node::transfer (xfer_node).
 // All dependency levels run in ONE launch: warps are ordered by (level, node id), and a warp of level k > 0 waits
 // until the specific lower-level nodes it depends on have finished this step (they are dispatched earlier -- the
 // same forward-progress assumption as decoupled look-back scans).  Levels exist only for links short enough that the serial id-ordered
 // visibility of Node.transfer matters (DESIGN.md "transfer order"); most networks have a single level and never wait.
-__global__ void __launch_bounds__(32 * XFER_WARPS) k_transfer(const DevWorld *worlds, int step_off) {
+template <int MC, int MD>
+union NodeSmem {  // the two halves of a node's timestep use shared memory one after the other
+    PreSmem<MC, MD> pre;
+    XferSmem<MC, MD> xf;
+};
+
+// MC / MD bound the sum of lanes and the degree of a node; the launcher picks the smallest instantiation the network fits
+// in, because the shared-memory footprint per warp decides how many node warps are resident.
+template <int MC, int MD>
+__global__ void __launch_bounds__(32 * XFER_WARPS) k_node(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
     WARP_BEGIN
-    __shared__ XferSmem sm_all[XFER_WARPS];
-    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ NodeSmem<MC, MD> sm_all[XFER_WARPS];
+    __shared__ double tt_all[XFER_WARPS][MD];
+    __shared__ int rel_all[XFER_WARPS];
+    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), wib = (int)((threadIdx.x >> 5) % XFER_WARPS);
     if (warp >= W.N) return;
-    XferSmem &S = sm_all[(threadIdx.x >> 5) % XFER_WARPS];
     int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
     int lvl = W.n_levels > 1 ? W.lvl_level[warp] : 0;
-    if (lvl > 0) {  // wait for exactly the nodes whose pops this node must see (end nodes of its SEES_POPS out-links)
-        WARP_FOR(lane) {
-            for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
-                volatile int *done = W.node_done + W.dep_list[q];
-#ifdef UX_EMU
-                if (*done < t + 1) dev_error(W, DERR_RING_FULL, -1);
-#else
-                while (*done < t + 1) __nanosleep(32);
-#endif
-            }
-        }
+    pre_node(W, sm_all[wib].pre, tt_all[wib], &rel_all[wib], n, t, (int)(threadIdx.x & 31));
 #ifndef UX_EMU
-        __threadfence();
+    __threadfence_block();
 #endif
-        WARP_SYNC();
-    }
-    xfer_node(W, S, n, t);
+    XferSmem<MC, MD> &S = sm_all[wib].xf;
+    xfer_node(W, S, n, t, lvl > 0);
     if (W.n_levels > 1) {
         WARP_SYNC();
         WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)(W.node_done + n)) = t + 1; }
@@ -1392,6 +1414,7 @@ struct ux_world {
     std::vector<int> dest_row, row_dest;
     long long P_uploaded = 0;
     bool all_dests = false;
+    int max_node_lanes = 0, max_node_deg = 0;
     std::vector<int> h_gen_off, h_gen_list, eff_ts;  // host copies of the per-origin FIFO lists; effective departure step per platoon
 #ifndef UX_EMU
     std::map<long long, std::pair<cudaGraphExec_t, long long>> graphs;  // key -> (executable graph, kernels per launch)
@@ -1637,6 +1660,8 @@ UX_API int ux_initialize_adj_matrix(ux_world *w) {
         int li = 0, lo = 0;
         for (int l : n.in) li += w->links[l].lanes;
         for (int l : n.out) lo += w->links[l].lanes;
+        w->max_node_lanes = std::max(w->max_node_lanes, std::max(li, lo));
+        w->max_node_deg = std::max(w->max_node_deg, (int)std::max(n.in.size(), n.out.size()));
         if (li > UX_MAXC || lo > UX_MAXC) return fail(w, UX_ERR_INVALID, "node %d: more than %d lanes in or out not supported", (int)i, UX_MAXC);
         for (int l : n.out) {
             if (w->links[l].lanes > UX_MAXLANE) return fail(w, UX_ERR_INVALID, "link %d: more than %d lanes not supported", l, UX_MAXLANE);
@@ -2012,8 +2037,13 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
     dim3 g_nodes((N * 32 + 127) / 128, R), g_update((w->nseg * 32 + 255) / 256, R);
     long long lc = 0;
     for (int s = 0; s < nsteps; s++) {
-        if (N > 0) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_pre, g_nodes, dim3(128), st, w->dworlds, s); KT_END(UX_K_PRE) lc++; }
-        if (N > 0) { KT_BEGIN(UX_K_TRANSFER) UX_LAUNCH(k_transfer, g_nodes, dim3(128), st, w->dworlds, s); KT_END(UX_K_TRANSFER) lc++; }
+        if (N > 0) {
+            KT_BEGIN(UX_K_TRANSFER)
+            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(128), st, w->dworlds, s);
+            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node<32, 16>), g_nodes, dim3(128), st, w->dworlds, s);
+            else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(128), st, w->dworlds, s);
+            KT_END(UX_K_TRANSFER) lc++;
+        }
         if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(256), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
         bool route = ((phase + s) % w->route_ts) == 0;
         if (w->n_active > 0 && w->n_edges > 0) {

@@ -5,7 +5,7 @@ import numpy as np
 import bench
 from uxsim_b200 import _capi as C
 
-api = C.load_product()
+api = C.CApi(os.environ["UX_LIB"], "ux_") if os.environ.get("UX_LIB") else C.load_product()  # UX_LIB: probe a variant build
 def probe(wl, R):
     sc = bench.make_scenario(wl, 0); tab = sc.tables()
     E = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R)

@@ -889,7 +889,7 @@ union NodeSmem {  // the two halves of a node's timestep use shared memory one a
 // MC / MD bound the sum of lanes and the degree of a node; the launcher picks the smallest instantiation the network fits
 // in, because the shared-memory footprint per warp decides how many node warps are resident.
 template <int MC, int MD>
-__global__ void __launch_bounds__(32 * XFER_WARPS) k_node(const DevWorld *worlds, int step_off) {
+__global__ void __launch_bounds__(32 * XFER_WARPS, 8) k_node(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
     WARP_BEGIN
     __shared__ NodeSmem<MC, MD> sm_all[XFER_WARPS];
@@ -950,7 +950,7 @@ UX_DEV void log_run_record(const DevWorld &W, int l, int t, int cur, int hd, int
 }
 
 #define UX_MAXLANE 64
-#define UPD_WARPS 8
+#define UPD_WARPS 4
 struct HeadSmem {
     int vid[UX_MAXLANE], next[UX_MAXLANE], dts[UX_MAXLANE];
     unsigned char kind[UX_MAXLANE];  // 0 not at end, 1 trip end, 2 abort, 3 transfer candidate
@@ -958,7 +958,9 @@ struct HeadSmem {
     int k_ended;
 };
 
-__global__ void __launch_bounds__(32 * UPD_WARPS) k_update(const DevWorld *worlds, int step_off) {
+// 4 warps per block and <= 48 registers (10 blocks per SM): the kernel is a swarm of tiny, latency-bound warps -- measured
+// best among {8x4, 8x5, 4x10, 4x12} blocks-per-SM variants at 32 replicas.
+__global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
     WARP_BEGIN
     __shared__ HeadSmem hs_all[UPD_WARPS];
@@ -2034,7 +2036,7 @@ static int extend_vehicles(ux_world *w) {
 static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
     int N = (int)w->nodes.size(), R = w->R;
     cudaStream_t st = w->stream;
-    dim3 g_nodes((N * 32 + 127) / 128, R), g_update((w->nseg * 32 + 255) / 256, R);
+    dim3 g_nodes((N * 32 + 127) / 128, R), g_update((w->nseg + UPD_WARPS - 1) / UPD_WARPS, R);
     long long lc = 0;
     for (int s = 0; s < nsteps; s++) {
         if (N > 0) {
@@ -2044,7 +2046,7 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
             else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(128), st, w->dworlds, s);
             KT_END(UX_K_TRANSFER) lc++;
         }
-        if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(256), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
+        if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
         bool route = ((phase + s) % w->route_ts) == 0;
         if (w->n_active > 0 && w->n_edges > 0) {
             if (route) {

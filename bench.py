@@ -334,7 +334,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "fixture network+demand (converted from the reference's dat/), synthetic seeds",
             "config": {"workload": WORKLOADS[args.workload][2], "replicas_per_gpu": R, "global_replicas": R * world,
-                       "l2_flush": "256 MiB write between timed steps; every step runs on freshly allocated state",
+                       "l2_flush": "256 MiB write between timed steps; every step builds a new world (state re-initialised; device slabs recycled through the engine's cache)",
                        "timing": "CUDA events on the engine's launch stream around all graph launches of main_loop; max over ranks",
                        "e2e_readback": "per replica: arrival step + travel time per platoon, per-link RUN counts; ensemble link stats [L,4]; cumulative curves of replica 0",
                        "parallelism": f"replicas x{R} per GPU (blockIdx.y), ranks x{world}, NCCL all-reduce of link stats only"},

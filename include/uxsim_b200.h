@@ -204,6 +204,9 @@ UX_API double UX_FN(get_double)(ux_world *w, int what);
 enum {
     UX_D_DELTA_T = 1, UX_D_TIME = 2, UX_D_T_MAX = 3, UX_D_AVE_V_SUM = 4, UX_D_STAT_SAMPLE_COUNT = 5,
     UX_D_LAST_LOOP_MS = 6,      /* device time of the last main_loop, CUDA events on the launching stream (product only) */
+    UX_D_UPLOAD_MS = 7,         /* host wall time of building + uploading the device state [ms] (product only) */
+    UX_D_GRAPH_BUILD_MS = 8,    /* host wall time spent capturing/instantiating CUDA graphs in the last main_loop [ms] */
+    UX_D_LAST_LOOP_WALL_MS = 9, /* host wall time of the last main_loop call [ms] */
     UX_D_KERNEL_MS_OF = 100     /* + kernel id: summed device time of that kernel in timing mode [ms] */
 };
 /* engine options (product only; the test libraries accept and ignore them) */

@@ -38,6 +38,7 @@ I_H2D_BYTES, I_D2H_BYTES, I_RING_SLOTS, I_MAX_DEPART_TS, I_KERNEL_LAUNCHES_OF = 
 K_NAMES = ("k_pre(unused)", "k_node", "k_update", "k_edge_cost", "k_sssp", "k_duo", "misc")
 OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS = 1, 2
 D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT, D_LAST_LOOP_MS, D_KERNEL_MS_OF = 1, 2, 3, 4, 5, 6, 100
+D_UPLOAD_MS, D_GRAPH_BUILD_MS, D_LAST_LOOP_WALL_MS = 7, 8, 9
 
 A_CUM_ARRIVAL, A_CUM_DEPARTURE, A_TRAVELTIME_INSTANT, A_TRAVELTIME_ACTUAL = 1, 2, 3, 4
 A_VEH_STATE, A_VEH_ARRIVAL_TS, A_VEH_DEPART_TS, A_VEH_TRAVEL_TIME, A_VEH_DISTANCE = 10, 11, 12, 13, 14

@@ -29,6 +29,8 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <mutex>
+#include <chrono>
 #include <algorithm>
 
 #include "../../include/uxsim_b200.h"
@@ -1398,6 +1400,7 @@ struct HLink {
     std::vector<int> sg; std::vector<double> toll;
 };
 struct HVeh { int orig, dest, ts; };
+struct Slab { char *base; size_t size, used; };
 
 struct ux_world {
     ux_world_params p;
@@ -1408,7 +1411,8 @@ struct ux_world {
     std::string err;
     int device = 0;
     cudaStream_t stream = nullptr;
-    std::vector<void *> allocs;
+    std::vector<void *> allocs;  // cudaMalloc'ed scratch (freed with the world)
+    std::vector<Slab> slabs;     // state memory (returned to the slab cache)
     std::vector<DevWorld> hw;  // host copies of the per-replica device worlds
     DevWorld *dworlds = nullptr;
     int n_levels = 1, n_active = 0;
@@ -1435,7 +1439,8 @@ struct ux_world {
     } logs;
     // measurement
     long long h2d_bytes = 0, d2h_bytes = 0;
-    double last_loop_ms = 0.0;
+    double last_loop_ms = 0.0, upload_ms = 0.0, loop_wall_ms = 0.0, graph_build_ms = 0.0;
+    int *d_err_all = nullptr;
     bool ktiming = false;
     double k_ms[UX_K_COUNT] = {0};
     long long k_launches[UX_K_COUNT] = {0};
@@ -1461,18 +1466,75 @@ static int fail(ux_world *w, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(w, UX_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// ---- device memory.  A world bump-allocates its arrays from slabs; slabs come from (and return to) a per-device
+// cache that outlives the world, so building the ~45 state arrays of each replica costs a handful of driver calls and a
+// solver that builds a world per iteration (DTA days, ensemble batches) reuses the previous world's memory.  A slab is
+// zeroed once when a world acquires it (on the world's stream), which is the initial value of almost all state.
+static std::mutex g_slab_mu;
+static std::map<int, std::vector<Slab>> g_slab_cache;  // device -> free slabs
+static size_t g_slab_cached_bytes = 0;
+
+static size_t slab_cache_limit() {  // bytes kept across worlds (env UXSIM_B200_SLAB_CACHE_MB; default 32 GiB)
+    static size_t lim = [] { const char *e = getenv("UXSIM_B200_SLAB_CACHE_MB"); return e ? (size_t)atoll(e) << 20 : (size_t)32 << 30; }();
+    return lim;
+}
+static void slab_cache_drop(int device) {
+    std::lock_guard<std::mutex> g(g_slab_mu);
+    for (Slab &s : g_slab_cache[device]) { cudaFree(s.base); g_slab_cached_bytes -= s.size; }
+    g_slab_cache[device].clear();
+}
+static bool slab_acquire(ux_world *w, size_t need) {
+    const size_t MB = (size_t)1 << 20;
+    size_t next = w->slabs.empty() ? 4 * MB : std::min(w->slabs.back().size * 2, 512 * MB);
+    size_t want = std::max((need + 2 * MB - 1) / (2 * MB) * (2 * MB), next);
+    Slab got{nullptr, 0, 0};
+    {
+        std::lock_guard<std::mutex> g(g_slab_mu);
+        auto &fl = g_slab_cache[w->device];
+        int best = -1;
+        for (int i = 0; i < (int)fl.size(); i++)
+            if (fl[i].size >= need && fl[i].size <= 2 * want && (best < 0 || fl[i].size < fl[best].size)) best = i;
+        if (best >= 0) { got = fl[best]; fl.erase(fl.begin() + best); g_slab_cached_bytes -= got.size; }
+    }
+    if (!got.base) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            slab_cache_drop(w->device);  // memory pressure: give the cache back and retry once
+            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+        got.base = (char *)p; got.size = want;
+    }
+    got.used = 0;
+    cudaMemsetAsync(got.base, 0, got.size, w->stream);
+    w->slabs.push_back(got);
+    return true;
+}
+static void slabs_release(ux_world *w) {
+    std::lock_guard<std::mutex> g(g_slab_mu);
+    for (Slab &s : w->slabs) {
+        if (g_slab_cached_bytes + s.size <= slab_cache_limit()) { g_slab_cache[w->device].push_back(s); g_slab_cached_bytes += s.size; }
+        else cudaFree(s.base);
+    }
+    w->slabs.clear();
+}
+
 template <typename T>
-static T *dalloc(ux_world *w, size_t n, bool zero = true) {
-    void *p = nullptr;
-    if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
-    if (zero) cudaMemset(p, 0, (n ? n : 1) * sizeof(T));
-    w->allocs.push_back(p);
-    return (T *)p;
+static T *dalloc(ux_world *w, size_t n, bool zero = true) {  // slab memory is already zero; `zero` documents who relies on it
+    (void)zero;
+    size_t bytes = ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (w->slabs.empty() || w->slabs.back().size - w->slabs.back().used < bytes)
+        if (!slab_acquire(w, bytes)) return nullptr;
+    Slab &s = w->slabs.back();
+    T *p = (T *)(s.base + s.used);
+    s.used += bytes;
+    return p;
 }
 template <typename T>
 static T *dupload(ux_world *w, const std::vector<T> &v) {
     T *p = dalloc<T>(w, v.size(), false);
-    if (p && !v.empty()) { cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice); w->h2d_bytes += (long long)(v.size() * sizeof(T)); }
+    // pageable source: the call returns once the data is staged, so `v` may die right after
+    if (p && !v.empty()) { cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, w->stream); w->h2d_bytes += (long long)(v.size() * sizeof(T)); }
     return p;
 }
 
@@ -1504,7 +1566,9 @@ UX_API void ux_destroy_world(ux_world *w) {
     cudaSetDevice(w->device);
     for (auto &g : w->graphs) cudaGraphExecDestroy(g.second.first);
 #endif
+    if (w->stream) cudaStreamSynchronize(w->stream);
     for (void *p : w->allocs) cudaFree(p);
+    slabs_release(w);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
 }
@@ -1718,31 +1782,32 @@ static int upload_link_params(ux_world *w) {
         vmax[i] = l.vmax; dpl_dn[i] = l.dpl * w->p.delta_n; udt[i] = l.vmax * w->dt; co[i] = l.cap_out; ci[i] = l.cap_in; mp[i] = l.mp; pen[i] = l.penalty;
     }
     size_t b = sizeof(double) * L;
-    CUDA_OK(cudaMemcpy(w->d_vmax, vmax.data(), b, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_dpl_dn, dpl_dn.data(), b, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_udt, udt.data(), b, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_cap_out, co.data(), b, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_cap_in, ci.data(), b, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_mp, mp.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(w->d_vmax, vmax.data(), b, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_dpl_dn, dpl_dn.data(), b, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_udt, udt.data(), b, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_cap_out, co.data(), b, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_cap_in, ci.data(), b, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_mp, mp.data(), b, cudaMemcpyHostToDevice, w->stream));
     CUDA_OK(cudaMemcpy(w->d_penalty, pen.data(), b, cudaMemcpyHostToDevice));
     std::vector<int> lflags, lvl_off, lvl_nodes, lvl_level, dep_off, dep_list;
     compute_levels(w, lflags, lvl_off, lvl_nodes, lvl_level, dep_off, dep_list);
     dep_list.resize(w->links.size() + 1, 0);
-    CUDA_OK(cudaMemcpy(w->d_dep_off, dep_off.data(), sizeof(int) * dep_off.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_dep_list, dep_list.data(), sizeof(int) * dep_list.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_lvl_level, lvl_level.data(), sizeof(int) * lvl_level.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(w->d_dep_off, dep_off.data(), sizeof(int) * dep_off.size(), cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_dep_list, dep_list.data(), sizeof(int) * dep_list.size(), cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_lvl_level, lvl_level.data(), sizeof(int) * lvl_level.size(), cudaMemcpyHostToDevice, w->stream));
     for (auto &d : w->hw) d.n_levels = w->n_levels;
-    if (w->dworlds) CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->hw.size(), cudaMemcpyHostToDevice));
+    if (w->dworlds) CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->hw.size(), cudaMemcpyHostToDevice, w->stream));
     lvl_off.resize(w->nodes.size() + 2, lvl_off.back());
-    CUDA_OK(cudaMemcpy(w->d_l_flags, lflags.data(), sizeof(int) * L, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_lvl_off, lvl_off.data(), sizeof(int) * lvl_off.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(w->d_lvl_nodes, lvl_nodes.data(), sizeof(int) * lvl_nodes.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(w->d_l_flags, lflags.data(), sizeof(int) * L, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_lvl_off, lvl_off.data(), sizeof(int) * lvl_off.size(), cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaMemcpyAsync(w->d_lvl_nodes, lvl_nodes.data(), sizeof(int) * lvl_nodes.size(), cudaMemcpyHostToDevice, w->stream));
     return 0;
 }
 
 // Build all device state.  Called lazily by the first main_loop (so that vehicles added after
 // initialize_adj_matrix but before the run are included, like the reference).
 static int upload(ux_world *w) {
+    auto t_begin = std::chrono::steady_clock::now();
     cudaSetDevice(w->device);
     CUDA_OK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     int N = (int)w->nodes.size(), L = (int)w->links.size(), T = w->total_ts;
@@ -1876,6 +1941,8 @@ static int upload(ux_world *w) {
     for (int i = 0; i < N; i++) { sig_t[i] = w->nodes[i].sig_t0; sig_ph[i] = w->nodes[i].sig_phase0; fc_rem[i] = w->nodes[i].fc_rem0; }
     std::vector<int> tb(1, w->timestep);
     w->hw.assign(w->R, base);
+    w->d_err_all = dalloc<int>(w, 2 * (size_t)w->R);
+    if (!w->d_err_all) return fail(w, UX_ERR_CUDA, "device allocation failed");
     size_t TL = (size_t)T * L;
     for (int r = 0; r < w->R; r++) {
         DevWorld &d = w->hw[r];
@@ -1887,8 +1954,8 @@ static int upload(ux_world *w) {
         d.sig_phase = dupload(w, sig_ph); d.sig_t = dupload(w, sig_t); d.fc_rem = dupload(w, fc_rem);
         d.gen_head = dalloc<int>(w, N); d.gen_avail = dalloc<int>(w, N);
         d.v_state = dalloc<int>(w, P); d.v_next = dalloc<int>(w, P); d.v_link = dalloc<int>(w, P, false); d.v_arr_ts = dalloc<int>(w, P, false); d.v_trav = dalloc<int>(w, P);
-        if (d.v_link) cudaMemset(d.v_link, 0xff, sizeof(int) * (P ? P : 1));
-        if (d.v_arr_ts) cudaMemset(d.v_arr_ts, 0xff, sizeof(int) * (P ? P : 1));
+        if (d.v_link) cudaMemsetAsync(d.v_link, 0xff, sizeof(int) * (P ? P : 1), w->stream);
+        if (d.v_arr_ts) cudaMemsetAsync(d.v_arr_ts, 0xff, sizeof(int) * (P ? P : 1), w->stream);
         d.v_mr = dalloc<double>(w, P); d.v_atl = dalloc<double>(w, P); d.v_dist = dalloc<double>(w, P); d.v_entry_x = dalloc<double>(w, P);
         { std::vector<double> m1(P, -1.0); d.v_tt = dupload(w, m1); }
         d.v_flags = dalloc<unsigned char>(w, P);
@@ -1897,8 +1964,8 @@ static int upload(ux_world *w) {
             for (long long i = 0; i < P; i++) cap += std::max(0, T - w->vehs[i].ts - 1);  // a platoon can be RUN from ts+1 to T-1
             d.lg_cap = cap;
             d.v_gen_ts = dalloc<int>(w, P, false); d.v_end_ts = dalloc<int>(w, P, false); d.v_end_kind = dalloc<unsigned char>(w, P);
-            if (d.v_gen_ts) cudaMemset(d.v_gen_ts, 0xff, sizeof(int) * (P ? P : 1));
-            if (d.v_end_ts) cudaMemset(d.v_end_ts, 0xff, sizeof(int) * (P ? P : 1));
+            if (d.v_gen_ts) cudaMemsetAsync(d.v_gen_ts, 0xff, sizeof(int) * (P ? P : 1), w->stream);
+            if (d.v_end_ts) cudaMemsetAsync(d.v_end_ts, 0xff, sizeof(int) * (P ? P : 1), w->stream);
             d.lg_vid = dalloc<int>(w, cap, false); d.lg_t = dalloc<int>(w, cap, false); d.lg_link = dalloc<int>(w, cap, false); d.lg_lane = dalloc<int>(w, cap, false);
             d.lg_x = dalloc<double>(w, cap, false); d.lg_v = dalloc<double>(w, cap, false); d.lg_s = dalloc<double>(w, cap, false);
             d.lg_count = dalloc<unsigned long long>(w, 1);
@@ -1909,16 +1976,17 @@ static int upload(ux_world *w) {
         d.ev_ord = dalloc<int>(w, TL); d.sig_log = dalloc<int>(w, (size_t)T * N);
         d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
         d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
-        if (d.rnext) cudaMemset(d.rnext, 0xff, sizeof(int) * std::max<size_t>((size_t)D * N, 1));
-        d.err = dalloc<int>(w, 2); d.t_base = dupload(w, tb); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
+        if (d.rnext) cudaMemsetAsync(d.rnext, 0xff, sizeof(int) * std::max<size_t>((size_t)D * N, 1), w->stream);
+        d.err = w->d_err_all + 2 * r; d.t_base = dupload(w, tb); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
         if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
             return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
     }
     w->dworlds = dalloc<DevWorld>(w, w->R, false);
     if (!w->dworlds) return fail(w, UX_ERR_CUDA, "device allocation failed");
-    CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaStreamSynchronize(w->stream));
     w->uploaded = true;
+    w->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return 0;
 }
 
@@ -1960,8 +2028,8 @@ template <typename T>
 static T *dgrow(ux_world *w, T *old, size_t oldn, size_t newn, int fill_byte) {
     T *p = dalloc<T>(w, newn, false);
     if (!p) return nullptr;
-    cudaMemset(p, fill_byte, (newn ? newn : 1) * sizeof(T));
-    if (old && oldn) cudaMemcpy(p, old, oldn * sizeof(T), cudaMemcpyDeviceToDevice);
+    if (fill_byte) cudaMemsetAsync(p, fill_byte, (newn ? newn : 1) * sizeof(T), w->stream);
+    if (old && oldn) cudaMemcpyAsync(p, old, oldn * sizeof(T), cudaMemcpyDeviceToDevice, w->stream);
     return p;
 }
 extern "C" {
@@ -2012,7 +2080,7 @@ static int extend_vehicles(ux_world *w) {
         d.v_arr_ts = dgrow(w, d.v_arr_ts, P0, P, 0xff); d.v_trav = dgrow(w, d.v_trav, P0, P, 0);
         d.v_mr = dgrow(w, d.v_mr, P0, P, 0); d.v_atl = dgrow(w, d.v_atl, P0, P, 0); d.v_dist = dgrow(w, d.v_dist, P0, P, 0); d.v_entry_x = dgrow(w, d.v_entry_x, P0, P, 0);
         d.v_flags = dgrow(w, d.v_flags, P0, P, 0);
-        { double *tt = dgrow(w, d.v_tt, P0, P, 0); std::vector<double> m1(P - P0, -1.0); if (tt) cudaMemcpy(tt + P0, m1.data(), sizeof(double) * (P - P0), cudaMemcpyHostToDevice); d.v_tt = tt; }
+        { double *tt = dgrow(w, d.v_tt, P0, P, 0); std::vector<double> m1(P - P0, -1.0); if (tt) cudaMemcpyAsync(tt + P0, m1.data(), sizeof(double) * (P - P0), cudaMemcpyHostToDevice, w->stream); d.v_tt = tt; }
         if (d.no_cyclic) d.v_visited = dgrow(w, d.v_visited, (size_t)P0 * d.vis_words, (size_t)P * d.vis_words, 0);
         if (d.log_mode) {
             d.v_gen_ts = dgrow(w, d.v_gen_ts, P0, P, 0xff); d.v_end_ts = dgrow(w, d.v_end_ts, P0, P, 0xff); d.v_end_kind = dgrow(w, d.v_end_kind, P0, P, 0);
@@ -2025,8 +2093,8 @@ static int extend_vehicles(ux_world *w) {
         }
         if (!d.v_state || !d.v_tt || !d.v_flags || !d.v_entry_x) return fail(w, UX_ERR_CUDA, "device allocation failed while adding vehicles");
     }
-    CUDA_OK(cudaMemcpy(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice, w->stream));
+    CUDA_OK(cudaStreamSynchronize(w->stream));
     w->P_uploaded = P;
     w->logs.replica = -1;
     return 0;
@@ -2090,36 +2158,46 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
     if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
     if ((long long)w->vehs.size() != w->P_uploaded) { int rc = extend_vehicles(w); if (rc) return rc; }
     if (w->net_dirty) { int rc = upload_link_params(w); if (rc) return rc; w->net_dirty = false; }
-#ifndef UX_EMU
-    if (!w->ev_begin) { CUDA_OK(cudaEventCreate(&w->ev_begin)); CUDA_OK(cudaEventCreate(&w->ev_end)); }
-    CUDA_OK(cudaEventRecord(w->ev_begin, w->stream));
-#endif
-    int t = start_ts;
-    while (t < end_ts) {
+    auto t_begin = std::chrono::steady_clock::now();
+    // chunks between route updates: (steps, phase); the executable graph of a chunk shape is built once and cached
+    std::vector<std::pair<int, int>> chunks;
+    for (int t = start_ts; t < end_ts;) {
         int phase = t % w->route_ts;
-        int nsteps = std::min(end_ts - t, w->route_ts - phase);
-        if (nsteps > 512) nsteps = 512;
-        long long lc = 0;
-#ifdef UX_EMU
-        enqueue_steps(w, nsteps, phase, &lc);
-#else
-        if (w->ktiming) { enqueue_steps(w, nsteps, phase, &lc); w->launches += lc; t += nsteps; continue; }
-        long long key = ((long long)nsteps << 32) | (unsigned)phase | ((long long)w->n_levels << 48);
-        auto it = w->graphs.find(key);
-        if (it == w->graphs.end()) {
+        int nsteps = std::min(std::min(end_ts - t, w->route_ts - phase), 512);
+        chunks.push_back({nsteps, phase});
+        t += nsteps;
+    }
+#ifndef UX_EMU
+    auto graph_key = [&](int nsteps, int phase) { return ((long long)nsteps << 32) | (unsigned)phase | ((long long)w->n_levels << 48); };
+    if (!w->ktiming)
+        for (auto &c : chunks) {
+            long long key = graph_key(c.first, c.second), lc = 0;
+            if (w->graphs.count(key)) continue;
             cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
             CUDA_OK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
-            enqueue_steps(w, nsteps, phase, &lc);
+            enqueue_steps(w, c.first, c.second, &lc);
             CUDA_OK(cudaStreamEndCapture(w->stream, &graph));
             CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
             cudaGraphDestroy(graph);
-            it = w->graphs.emplace(key, std::make_pair(exec, lc)).first;
+            w->graphs.emplace(key, std::make_pair(exec, lc));
         }
-        lc = it->second.second;
-        CUDA_OK(cudaGraphLaunch(it->second.first, w->stream));
+    w->graph_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (!w->ev_begin) { CUDA_OK(cudaEventCreate(&w->ev_begin)); CUDA_OK(cudaEventCreate(&w->ev_end)); }
+    CUDA_OK(cudaEventRecord(w->ev_begin, w->stream));
+#endif
+    for (auto &c : chunks) {
+        long long lc = 0;
+#ifdef UX_EMU
+        enqueue_steps(w, c.first, c.second, &lc);
+#else
+        if (w->ktiming) enqueue_steps(w, c.first, c.second, &lc);
+        else {
+            auto &g = w->graphs[graph_key(c.first, c.second)];
+            lc = g.second;
+            CUDA_OK(cudaGraphLaunch(g.first, w->stream));
+        }
 #endif
         w->launches += lc;
-        t += nsteps;
     }
 #ifndef UX_EMU
     CUDA_OK(cudaEventRecord(w->ev_end, w->stream));
@@ -2135,15 +2213,17 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
     }
     w->kt_events.clear(); w->kt_ids.clear();
 #endif
-    for (int r = 0; r < w->R; r++) {
-        int e[2] = {0, 0};
-        CUDA_OK(cudaMemcpy(e, w->hw[r].err, sizeof(e), cudaMemcpyDeviceToHost));
-        if (e[0]) {
-            int code = (e[0] == DERR_RING_FULL || e[0] == DERR_LOG_FULL) ? UX_ERR_CAPACITY : e[0] == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
-            w->timestep = end_ts;
-            return fail(w, code, derr_text(e[0]), e[1]);
+    w->timestep = end_ts;
+    {   // device-side error words of all replicas (one block, one copy)
+        std::vector<int> e(2 * (size_t)w->R, 0);
+        CUDA_OK(cudaMemcpy(e.data(), w->d_err_all, sizeof(int) * e.size(), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < w->R; r++) if (e[2 * r]) {
+            int c0 = e[2 * r];
+            int code = (c0 == DERR_RING_FULL || c0 == DERR_LOG_FULL) ? UX_ERR_CAPACITY : c0 == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
+            return fail(w, code, derr_text(c0), e[2 * r + 1]);
         }
     }
+    w->loop_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     w->timestep = end_ts;
     return 0;
 }
@@ -2253,6 +2333,9 @@ UX_API double ux_get_double(ux_world *w, int what) {
     case UX_D_TIME: return w->timestep * w->dt;
     case UX_D_T_MAX: return w->p.t_max;
     case UX_D_LAST_LOOP_MS: return w->last_loop_ms;
+    case UX_D_UPLOAD_MS: return w->upload_ms;
+    case UX_D_GRAPH_BUILD_MS: return w->graph_build_ms;
+    case UX_D_LAST_LOOP_WALL_MS: return w->loop_wall_ms;
     default:
         if (what >= UX_D_KERNEL_MS_OF && what < UX_D_KERNEL_MS_OF + UX_K_COUNT) return w->k_ms[what - UX_D_KERNEL_MS_OF];
         return NAN;

@@ -299,8 +299,15 @@ def main():
                 kernels[k]["alg_bytes_per_launch"] = per_launch
                 kernels[k]["GBps"] = per_launch / (avg_us * 1e-6) / 1e9
         dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["share"])
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch from the committed ncu capture of this workload / replica count, if there is one
+            ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{R}")
+            if ent and dom in ent:
+                traffic, traffic_src = ent[dom], ent.get("source")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["GBps"] / peak, "traffic": None,
+                    "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                     "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"], "avg_launch_us": kernels[dom]["avg_us"],
                     "note": "every kernel of this path is latency/launch-bound at this size (no tensor cores); see DESIGN.md"}

@@ -110,19 +110,21 @@ struct DevWorld {
 // stores, so the pointers stay in registers / LDS and the kernels' dependent-load chains halve.
 #ifdef UX_EMU
 #define LOAD_WORLD(W, worlds) static DevWorld W##_sh; W##_sh = (worlds)[blockIdx.y]; const DevWorld &W = W##_sh;
+#define LOAD_WORLD_N(W, worlds, NT, REPLICA) static DevWorld W##_sh; W##_sh = (worlds)[REPLICA]; const DevWorld &W = W##_sh;
 #else
-#define LOAD_WORLD(W, worlds)                                                                            \
+#define LOAD_WORLD_N(W, worlds, NT, REPLICA)  /* the first NT threads of the block copy (every block has >= NT threads) */ \
     __shared__ DevWorld W##_sh;                                                                          \
     {                                                                                                    \
-        const int *src_ = reinterpret_cast<const int *>(&(worlds)[blockIdx.y]);                          \
+        const int *src_ = reinterpret_cast<const int *>(&(worlds)[REPLICA]);                          \
         int *dst_ = reinterpret_cast<int *>(&W##_sh);                                                    \
-        _Pragma("unroll") for (int k_ = 0; k_ < (int)((sizeof(DevWorld) / 4 + 63) / 64); k_++) {           \
-            int i_ = (int)threadIdx.x + k_ * 64;  /* every block has >= 64 threads; extra threads repeat */ \
-            if (threadIdx.x < 64 && i_ < (int)(sizeof(DevWorld) / 4)) dst_[i_] = src_[i_];                \
+        _Pragma("unroll") for (int k_ = 0; k_ < (int)((sizeof(DevWorld) / 4 + (NT) - 1) / (NT)); k_++) {   \
+            int i_ = (int)threadIdx.x + k_ * (NT);                                                       \
+            if (threadIdx.x < (NT) && i_ < (int)(sizeof(DevWorld) / 4)) dst_[i_] = src_[i_];              \
         }                                                                                                \
     }                                                                                                    \
     __syncthreads();                                                                                     \
     const DevWorld &W = W##_sh;
+#define LOAD_WORLD(W, worlds) LOAD_WORLD_N(W, worlds, 64, blockIdx.y)
 #endif
 
 // Warp-cooperative kernels are written as phases.  On the GPU WARP_FOR runs its body once with `lane` = the lane
@@ -550,7 +552,9 @@ UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem<MC, MD> &S, int p, int t) 
     S.popped[ii] += 1;
 }
 
+#ifndef XFER_WARPS
 #define XFER_WARPS 4
+#endif
 template <int MC, int MD>
 UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
     int cur = t & 1, L = W.L;
@@ -891,13 +895,15 @@ union NodeSmem {  // the two halves of a node's timestep use shared memory one a
 // MC / MD bound the sum of lanes and the degree of a node; the launcher picks the smallest instantiation the network fits
 // in, because the shared-memory footprint per warp decides how many node warps are resident.
 template <int MC, int MD>
-__global__ void __launch_bounds__(32 * XFER_WARPS, 8) k_node(const DevWorld *worlds, int step_off) {
-    LOAD_WORLD(W, worlds)
+__global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const DevWorld *worlds, int step_off) {
+    // replica = blockIdx.x (fastest in launch order): the blocks resident together are the same nodes of different replicas
+    // -- same code path, same static tables -- and every replica's dependency chains start in the first wave
+    LOAD_WORLD_N(W, worlds, (XFER_WARPS > 1 ? 64 : 32), blockIdx.x)
     WARP_BEGIN
     __shared__ NodeSmem<MC, MD> sm_all[XFER_WARPS];
     __shared__ double tt_all[XFER_WARPS][MD];
     __shared__ int rel_all[XFER_WARPS];
-    int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), wib = (int)((threadIdx.x >> 5) % XFER_WARPS);
+    int warp = (int)((blockIdx.y * blockDim.x + threadIdx.x) >> 5), wib = (int)((threadIdx.x >> 5) % XFER_WARPS);
     if (warp >= W.N) return;
     int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
     int lvl = W.n_levels > 1 ? W.lvl_level[warp] : 0;
@@ -1764,6 +1770,23 @@ static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<in
     lvl_nodes.assign(N, 0);
     std::vector<int> fill(nl, 0);
     for (int a = 0; a < N; a++) lvl_nodes[lvl_off[level[a]] + fill[level[a]]++] = a;
+    {   // Launch order of the node warps.  A node may only wait for warps with a smaller linear index, so dependencies
+        // must come first; beyond that the order is free.  Critical-path order: a node's height = length of the longest
+        // chain of dependents hanging off it; sort by (height desc, weight desc), so the chains of waiting nodes start
+        // at the very beginning of the launch and the independent bulk fills the machine behind them, heaviest first.
+        std::vector<int> weight(N, 0), height(N, 0);
+        for (int a = 0; a < N; a++) {
+            int wt = 0;
+            for (int l : w->nodes[a].in) wt += 2 * w->links[l].lanes + 1;
+            for (int l : w->nodes[a].out) wt += w->links[l].lanes + 1;
+            weight[a] = wt * (1 + (int)w->nodes[a].out.size());
+        }
+        for (int a = N - 1; a >= 0; a--)  // a dependency always has the smaller id, so height[a] is final here
+            for (int l : w->nodes[a].out) if (lflags[l] & LF_SEES_POPS) { int b = w->links[l].end; height[b] = std::max(height[b], height[a] + 1); }
+        std::stable_sort(lvl_nodes.begin(), lvl_nodes.end(), [&](int a, int b) {
+            if (height[a] != height[b]) return height[a] > height[b];
+            return weight[a] > weight[b]; });
+    }
     lvl_level.assign(N, 0);
     for (int q = 0; q < N; q++) lvl_level[q] = level[lvl_nodes[q]];
     dep_off.assign(N + 1, 0); dep_list.clear();
@@ -1788,7 +1811,7 @@ static int upload_link_params(ux_world *w) {
     CUDA_OK(cudaMemcpyAsync(w->d_cap_out, co.data(), b, cudaMemcpyHostToDevice, w->stream));
     CUDA_OK(cudaMemcpyAsync(w->d_cap_in, ci.data(), b, cudaMemcpyHostToDevice, w->stream));
     CUDA_OK(cudaMemcpyAsync(w->d_mp, mp.data(), b, cudaMemcpyHostToDevice, w->stream));
-    CUDA_OK(cudaMemcpy(w->d_penalty, pen.data(), b, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(w->d_penalty, pen.data(), b, cudaMemcpyHostToDevice, w->stream));
     std::vector<int> lflags, lvl_off, lvl_nodes, lvl_level, dep_off, dep_list;
     compute_levels(w, lflags, lvl_off, lvl_nodes, lvl_level, dep_off, dep_list);
     dep_list.resize(w->links.size() + 1, 0);
@@ -2104,14 +2127,14 @@ static int extend_vehicles(ux_world *w) {
 static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
     int N = (int)w->nodes.size(), R = w->R;
     cudaStream_t st = w->stream;
-    dim3 g_nodes((N * 32 + 127) / 128, R), g_update((w->nseg + UPD_WARPS - 1) / UPD_WARPS, R);
+    dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_WARPS - 1) / UPD_WARPS, R);
     long long lc = 0;
     for (int s = 0; s < nsteps; s++) {
         if (N > 0) {
             KT_BEGIN(UX_K_TRANSFER)
-            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(128), st, w->dworlds, s);
-            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node<32, 16>), g_nodes, dim3(128), st, w->dworlds, s);
-            else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(128), st, w->dworlds, s);
+            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
+            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node<32, 16>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
+            else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
             KT_END(UX_K_TRANSFER) lc++;
         }
         if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }

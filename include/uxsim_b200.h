@@ -207,11 +207,18 @@ enum {
     UX_D_UPLOAD_MS = 7,         /* host wall time of building + uploading the device state [ms] (product only) */
     UX_D_GRAPH_BUILD_MS = 8,    /* host wall time spent capturing/instantiating CUDA graphs in the last main_loop [ms] */
     UX_D_LAST_LOOP_WALL_MS = 9, /* host wall time of the last main_loop call [ms] */
+    UX_D_DTA_N_SWAP = 10,       /* RouteSwapResult::n_swap of the last dta_route_swap */
+    UX_D_DTA_POTENTIAL_N_SWAP = 11,
+    UX_D_DTA_TOTAL_T_GAP = 12,
+    UX_D_DTA_SWAP_MS = 13,      /* device time of the last dta_route_swap's kernels (product only) */
     UX_D_KERNEL_MS_OF = 100     /* + kernel id: summed device time of that kernel in timing mode [ms] */
 };
 /* engine options (product only; the test libraries accept and ignore them) */
 enum {
     UX_OPT_KERNEL_TIMING = 1,   /* 1: launch kernels eagerly with a CUDA-event pair around each (for roofline numbers) */
+    UX_OPT_RECORD_TRAVERSALS = 3, /* 1 (before the first main_loop): record every link entry (platoon, link, step) on the device so that
+                                   dta_route_swap can read the traversed routes without the per-step vehicle logs (CUDA build; the CPU
+                                   engines read their logs, as dta_get_traveled_route does, dta_solver.cpp:30-57) */
     UX_OPT_ALL_DESTINATIONS = 2 /* 1 (before the first main_loop): keep route preferences for every node, as the reference does,
                                    instead of only for the destinations present in the demand.  Needed only if demand towards
                                    NEW destinations will be added between main_loop calls. */
@@ -268,7 +275,23 @@ enum {
     /* World::build_enter_log_data (traffi.cpp:1965-1983) */
     UX_A_ENTER_LINK = 80,       /* i32 [E3] */
     UX_A_ENTER_TIME = 81,       /* f64 [E3] */
-    UX_A_ENTER_VEH = 82         /* i32 [E3] */
+    UX_A_ENTER_VEH = 82,        /* i32 [E3] */
+    /* DTA solver batch operations.  OD route-set store (ODRouteSetStore::to_csr, bindings.cpp), pairs
+     * sorted by (orig, dest): */
+    UX_A_DTA_OD_ORIG = 100,     /* i32 [n_od] */
+    UX_A_DTA_OD_DEST = 101,     /* i32 [n_od] */
+    UX_A_DTA_OD_OFFSETS = 102,  /* i64 [n_od+1]  routes of pair p = [off[p], off[p+1]) */
+    UX_A_DTA_ROUTE_OFFSETS = 103, /* i64 [n_routes+1] */
+    UX_A_DTA_ROUTE_LINKS = 104, /* i32 */
+    /* result of the last dta_route_swap (RouteSwapResult dta_solver.h:104-114, as the flat CSR of bindings.cpp:661-706) */
+    UX_A_DTA_RS_OFFSETS = 110,  /* i64 [P+1]  routes_specified: route to enforce in the next iteration (empty = none) */
+    UX_A_DTA_RS_LINKS = 111,    /* i32 */
+    UX_A_DTA_RA_OFFSETS = 112,  /* i64 [P+1]  route_actual: links traversed in this run */
+    UX_A_DTA_RA_LINKS = 113,    /* i32 */
+    UX_A_DTA_COST_ACTUAL = 114, /* f64 [P]    arrival_time - first link entry time */
+    UX_A_DTA_T_GAP = 115,       /* f64 [P]    per-platoon cost gap; total_t_gap is its sum in index order */
+    UX_A_DTA_CHOICE = 116,      /* i32 [P]    -2 nothing enforced (trip unfinished), -1 keeps the traversed route, r >= 0 = index into the store's routes */
+    UX_A_DTA_RA_ENTRY_T = 117   /* f64        entry time of each link of route_actual (TraveledRouteInfo::entry_times) */
 };
 enum { UX_DT_F64 = 1, UX_DT_I32 = 2, UX_DT_I64 = 3 };
 
@@ -286,6 +309,23 @@ UX_API int64_t UX_FN(get_device_array)(ux_world *w, int what, int replica, void 
  * written to DEVICE memory as f64 [L][4] ready for one ncclAllReduce(sum). */
 UX_API int64_t UX_FN(ensemble_link_stats_device)(ux_world *w, void **dptr_out);
 UX_API int64_t UX_FN(ensemble_link_stats)(ux_world *w, double *dst, int64_t capacity);
+
+/* ---- DTA solver batch operations (dta_solver.h, bindings.cpp:461-706) ------------------------ */
+
+/* World.enumerate_od_route_sets_ids_cpp(k, seed) (bindings.cpp:461-465; World::enumerate_k_random_routes_cpp
+ * traffi.cpp:1387-1481): up to k distinct shortest routes per connected node pair under free-flow, then randomly
+ * re-weighted (mt19937(seed), U(0,100)) link costs, until the mean number of routes per pair is stable for 11 rounds.
+ * The store is kept by the world (UX_A_DTA_OD_* / ROUTE_*).  Returns the number of routes or an error code. */
+UX_API int64_t UX_FN(dta_enumerate_route_sets)(ux_world *w, int k, unsigned int seed);
+/* World.make_od_route_set_store (bindings.cpp:467-489): an external store in CSR form. */
+UX_API int UX_FN(dta_set_route_sets)(ux_world *w, int64_t n_od, const int *orig, const int *dest, const int64_t *od_offsets,
+                                     const int64_t *route_offsets, const int *route_links);
+/* World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_route_swap_due / _dso dta_solver.cpp:130-373) on the
+ * finished run of `replica`.  mode 0 = DUE (travel time + tolls), 1 = DSO (travel time + congestion externality,
+ * Link::estimate_congestion_externality traffi.cpp:650-689); swap_num < 0 = probabilistic candidates (swap_prob),
+ * otherwise exactly swap_num candidates (DSO only).  Results: UX_A_DTA_RS_* .. UX_A_DTA_CHOICE, UX_D_DTA_*. */
+UX_API int UX_FN(dta_route_swap)(ux_world *w, int replica, int mode, double swap_prob, int swap_num,
+                                 int has_external_route_sets, unsigned int rng_seed);
 
 /* Message of the last failure on `w` (or of the last failed create_world when w == NULL). */
 UX_API const char *UX_FN(last_error)(ux_world *w);

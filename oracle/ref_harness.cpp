@@ -17,6 +17,7 @@
 #include <stdexcept>
 
 #include "traffi.cpp"      // resolved via -I/root/reference/uxsim/trafficpp (as bindings.cpp:18 does)
+#include "dta_solver.cpp"  // bindings.cpp:19
 
 #define UX_PREFIX uxr_
 #include "../include/uxsim_b200.h"
@@ -26,6 +27,12 @@ struct ux_world {
     ux_world_params p;
     std::string err;
     bool initialized = false;
+    // DTA solver state (bindings.cpp keeps these as Python-owned objects)
+    ODRouteSetStore store;
+    std::vector<std::pair<int, int>> od_keys;  // sorted (orig, dest)
+    RouteSwapResult swap;
+    std::vector<double> swap_entry_t;          // TraveledRouteInfo::entry_times, flat in route_actual order
+    bool has_swap = false;
 };
 
 static std::string g_err;
@@ -256,6 +263,9 @@ UX_API int64_t uxr_get_int(ux_world *w, int what) {
 UX_API double uxr_get_double(ux_world *w, int what) {
     World *W = w->W;
     switch (what) {
+    case UX_D_DTA_N_SWAP: return w->swap.n_swap;
+    case UX_D_DTA_POTENTIAL_N_SWAP: return w->swap.potential_n_swap;
+    case UX_D_DTA_TOTAL_T_GAP: return w->swap.total_t_gap;
     case UX_D_DELTA_T: return W->delta_t;
     case UX_D_TIME: return (double)W->timestep * W->delta_t;
     case UX_D_T_MAX: return W->t_max;
@@ -293,6 +303,15 @@ UX_API int64_t uxr_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_LOG_N_MISSING: n = P; dt = UX_DT_I32; break;
     case UX_A_LTL_T: case UX_A_LTL_ID: { auto fl = W->build_all_vehicle_logs_flat_compact(); n = (int64_t)fl.ltl_t.size(); dt = what == UX_A_LTL_T ? UX_DT_F64 : UX_DT_I32; break; }
     case UX_A_ENTER_LINK: case UX_A_ENTER_VEH: case UX_A_ENTER_TIME: { n = (int64_t)W->build_enter_log_data().size(); dt = what == UX_A_ENTER_TIME ? UX_DT_F64 : UX_DT_I32; break; }
+    case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = (int64_t)w->od_keys.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_OD_OFFSETS: n = (int64_t)w->od_keys.size() + 1; dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_OFFSETS: { n = 1; for (auto &k : w->od_keys) n += (int64_t)w->store.sets[k].size(); dt = UX_DT_I64; break; }
+    case UX_A_DTA_ROUTE_LINKS: { n = 0; for (auto &k : w->od_keys) for (auto &r : w->store.sets[k]) n += (int64_t)r.size(); dt = UX_DT_I32; break; }
+    case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
+    case UX_A_DTA_RS_LINKS: { n = 0; for (auto &r : w->swap.routes_specified) n += (int64_t)r.size(); dt = UX_DT_I32; break; }
+    case UX_A_DTA_RA_LINKS: { n = 0; for (auto &r : w->swap.route_actual) n += (int64_t)r.size(); dt = UX_DT_I32; break; }
+    case UX_A_DTA_RA_ENTRY_T: n = (int64_t)w->swap_entry_t.size(); break;
+    case UX_A_DTA_COST_ACTUAL: n = P; break;
     default: return fail(w, UX_ERR_INVALID, "unknown array");
     }
     if (dtype) *dtype = dt;
@@ -337,6 +356,20 @@ UX_API int64_t uxr_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_ROUTE_PREF: for (int64_t k = 0; k < N; k++) for (int64_t l = 0; l < L; l++) d[k * L + l] = k < (int64_t)W->route_preference.size() ? W->route_preference[k][l] : 0.0; break;
     case UX_A_ROUTE_DIST: for (int64_t i = 0; i < N; i++) for (int64_t k = 0; k < N; k++) d[i * N + k] = i < (int64_t)W->route_dist.size() ? W->route_dist[i][k] : 0.0; break;
     case UX_A_ROUTE_NEXT: for (int64_t i = 0; i < N; i++) for (int64_t k = 0; k < N; k++) ii[i * N + k] = i < (int64_t)W->route_next.size() ? W->route_next[i][k] : -1; break;
+    case UX_A_DTA_OD_ORIG: for (size_t i = 0; i < w->od_keys.size(); i++) ii[i] = w->od_keys[i].first; break;
+    case UX_A_DTA_OD_DEST: for (size_t i = 0; i < w->od_keys.size(); i++) ii[i] = w->od_keys[i].second; break;
+    case UX_A_DTA_OD_OFFSETS: { int64_t a = 0; ll[0] = 0; for (size_t i = 0; i < w->od_keys.size(); i++) { a += (int64_t)w->store.sets[w->od_keys[i]].size(); ll[i + 1] = a; } break; }
+    case UX_A_DTA_ROUTE_OFFSETS: { int64_t a = 0, q = 0; ll[q++] = 0; for (auto &k : w->od_keys) for (auto &r : w->store.sets[k]) { a += (int64_t)r.size(); ll[q++] = a; } break; }
+    case UX_A_DTA_ROUTE_LINKS: { int64_t q = 0; for (auto &k : w->od_keys) for (auto &r : w->store.sets[k]) for (int l : r) ii[q++] = l; break; }
+    case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: {
+        if (!w->has_swap) return fail(w, UX_ERR_RUNTIME, "no route swap result");
+        auto &rr = what == UX_A_DTA_RS_OFFSETS ? w->swap.routes_specified : w->swap.route_actual;
+        int64_t a = 0; ll[0] = 0; for (int64_t i = 0; i < P; i++) { a += (int64_t)rr[i].size(); ll[i + 1] = a; } break; }
+    case UX_A_DTA_RS_LINKS: case UX_A_DTA_RA_LINKS: {
+        auto &rr = what == UX_A_DTA_RS_LINKS ? w->swap.routes_specified : w->swap.route_actual;
+        int64_t q = 0; for (auto &r : rr) for (int l : r) ii[q++] = l; break; }
+    case UX_A_DTA_RA_ENTRY_T: memcpy(d, w->swap_entry_t.data(), sizeof(double) * w->swap_entry_t.size()); break;
+    case UX_A_DTA_COST_ACTUAL: if (!w->has_swap) return fail(w, UX_ERR_RUNTIME, "no route swap result"); memcpy(d, w->swap.cost_actual.data(), sizeof(double) * P); break;
     case UX_A_ENTER_LINK: case UX_A_ENTER_TIME: case UX_A_ENTER_VEH: {
         auto e = W->build_enter_log_data();
         for (size_t i = 0; i < e.size(); i++) { if (what == UX_A_ENTER_LINK) ii[i] = e[i].link_id; else if (what == UX_A_ENTER_TIME) d[i] = e[i].time; else ii[i] = e[i].vehicle_index; }
@@ -398,6 +431,48 @@ UX_API int64_t PFX(add_demands)(ux_world *w, int64_t n, const int *o, const int 
     return made;
 }
 UX_API int PFX(set_option)(ux_world *w, int option, double value) { (void)w; (void)option; (void)value; return 0; }
+
+// ---- DTA solver batch operations: forwarding calls into the reference's dta_solver.cpp
+static void index_store(ux_world *w) {
+    w->od_keys.clear();
+    for (auto &kv : w->store.sets) w->od_keys.push_back(kv.first);
+    std::sort(w->od_keys.begin(), w->od_keys.end());
+}
+// enumerate_od_route_sets_ids_cpp bindings.cpp:461-465
+UX_API int64_t uxr_dta_enumerate_route_sets(ux_world *w, int k, unsigned int seed) {
+    UXR_TRY
+    if (!w->initialized) { int rc = uxr_initialize_adj_matrix(w); if (rc) return rc; }
+    w->store = dta_enumerate_od_route_sets_ids(w->W, k, seed);
+    index_store(w);
+    int64_t n = 0; for (auto &kv : w->store.sets) n += (int64_t)kv.second.size();
+    return n;
+    UXR_CATCH(w)
+}
+// make_od_route_set_store bindings.cpp:467-489
+UX_API int uxr_dta_set_route_sets(ux_world *w, int64_t n_od, const int *orig, const int *dest, const int64_t *od_off, const int64_t *route_off, const int *links) {
+    UXR_TRY
+    w->store.sets.clear();
+    for (int64_t p = 0; p < n_od; p++) {
+        std::vector<std::vector<int>> routes;
+        for (int64_t r = od_off[p]; r < od_off[p + 1]; r++) routes.emplace_back(links + route_off[r], links + route_off[r + 1]);
+        w->store.sets[{orig[p], dest[p]}] = std::move(routes);
+    }
+    index_store(w);
+    return 0;
+    UXR_CATCH(w)
+}
+// route_swap_due / route_swap_dso bindings.cpp:661-706
+UX_API int uxr_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
+    UXR_TRY
+    if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "reference harness has a single replica");
+    if (mode == 0) w->swap = dta_route_swap_due(w->W, w->store, swap_prob, has_external != 0, rng_seed);
+    else w->swap = dta_route_swap_dso(w->W, w->store, swap_prob, swap_num, has_external != 0, rng_seed);
+    w->swap_entry_t.clear();
+    for (Vehicle *v : w->W->vehicles) { auto tr = dta_get_traveled_route(v); w->swap_entry_t.insert(w->swap_entry_t.end(), tr.entry_times.begin(), tr.entry_times.end()); }
+    w->has_swap = true;
+    return 0;
+    UXR_CATCH(w)
+}
 
 UX_API const char *uxr_last_error(ux_world *w) { return w ? w->err.c_str() : g_err.c_str(); }
 

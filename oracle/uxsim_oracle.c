@@ -100,6 +100,10 @@ struct ux_world {
     int *in_pair_list; int *in_pair_off; /* CSR: for node j, the pair-leading links ending at j */
     /* scratch */
     int *snapshot; int snapshot_cap;
+    /* DTA solver: OD route-set store (pairs sorted by (orig, dest)) and the last route-swap result */
+    int64_t dta_n_od; int *dta_o, *dta_d; int64_t *dta_od_off, *dta_route_off; int *dta_links;
+    int64_t *rs_off, *ra_off; int *rs_links, *ra_links; double *ra_entry_t, *cost_actual, *t_gap; int *choice;
+    double n_swap, potential_n_swap, total_t_gap; int has_swap;
     char err[512];
 };
 
@@ -169,6 +173,8 @@ UX_API void uxo_destroy_world(ux_world *w) {
     free(w->nodes); free(w->links); free(w->vehs);
     free(w->pref); free(w->pref_active); free(w->dest_active); free(w->rdist); free(w->rnext);
     free(w->pair_first); free(w->pair_cost); free(w->in_pair_list); free(w->in_pair_off); free(w->snapshot);
+    free(w->dta_o); free(w->dta_d); free(w->dta_od_off); free(w->dta_route_off); free(w->dta_links);
+    free(w->rs_off); free(w->ra_off); free(w->rs_links); free(w->ra_links); free(w->ra_entry_t); free(w->cost_actual); free(w->t_gap); free(w->choice);
     free(w);
 }
 
@@ -951,6 +957,9 @@ UX_API double uxo_get_double(ux_world *w, int what) {
     case UX_D_TIME: return w->timestep * w->delta_t;
     case UX_D_T_MAX: return w->p.t_max;
     case UX_D_AVE_V_SUM: { double s = 0; for (int i = 0; i < w->nl; i++) s += w->links[i].ave_v_sum; return s; }
+    case UX_D_DTA_N_SWAP: return w->n_swap;
+    case UX_D_DTA_POTENTIAL_N_SWAP: return w->potential_n_swap;
+    case UX_D_DTA_TOTAL_T_GAP: return w->total_t_gap;
     case UX_D_STAT_SAMPLE_COUNT: { double s = 0; for (int i = 0; i < w->nl; i++) s += w->links[i].stat_count; for (int i = 0; i < w->nn; i++) s += w->nodes[i].stat_count; return s; }
     default: return NAN;
     }
@@ -1017,6 +1026,16 @@ UX_API int64_t uxo_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_LOG_N_MISSING: n = P; dt = UX_DT_I32; break;
     case UX_A_LTL_T: case UX_A_LTL_ID: { n = 0; for (int64_t i = 0; i < P; i++) n += ltl_count(&w->vehs[i]); dt = what == UX_A_LTL_T ? UX_DT_F64 : UX_DT_I32; break; }
     case UX_A_ENTER_LINK: case UX_A_ENTER_VEH: case UX_A_ENTER_TIME: { n = 0; for (int64_t i = 0; i < P; i++) n += enter_count(&w->vehs[i]); dt = what == UX_A_ENTER_TIME ? UX_DT_F64 : UX_DT_I32; break; }
+    case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = w->dta_n_od; dt = UX_DT_I32; break;
+    case UX_A_DTA_OD_OFFSETS: n = w->dta_n_od + 1; dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_OFFSETS: n = (w->dta_od_off ? w->dta_od_off[w->dta_n_od] : 0) + 1; dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_LINKS: n = w->dta_od_off ? w->dta_route_off[w->dta_od_off[w->dta_n_od]] : 0; dt = UX_DT_I32; break;
+    case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
+    case UX_A_DTA_RS_LINKS: n = w->has_swap ? w->rs_off[P] : 0; dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_LINKS: n = w->has_swap ? w->ra_off[P] : 0; dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_ENTRY_T: n = w->has_swap ? w->ra_off[P] : 0; break;
+    case UX_A_DTA_COST_ACTUAL: case UX_A_DTA_T_GAP: n = P; break;
+    case UX_A_DTA_CHOICE: n = P; dt = UX_DT_I32; break;
     default: return fail(w, UX_ERR_INVALID, "unknown array %d", what);
     }
     if (dtype) *dtype = dt;
@@ -1098,6 +1117,19 @@ UX_API int64_t uxo_get_array(ux_world *w, int what, int replica, void *dst, int6
             for (int k = 0; k < v->log_size; k++) { int lid = v->log_link[k]; if (lid >= 0 && lid != prev) { if (what == UX_A_ENTER_LINK) ii[s] = lid; else if (what == UX_A_ENTER_TIME) d[s] = log_t_at(w, v, k); else ii[s] = (int)i; s++; prev = lid; } }
         }
         break; }
+    case UX_A_DTA_OD_ORIG: memcpy(dst, w->dta_o, sizeof(int) * n); break;
+    case UX_A_DTA_OD_DEST: memcpy(dst, w->dta_d, sizeof(int) * n); break;
+    case UX_A_DTA_OD_OFFSETS: if (w->dta_od_off) memcpy(dst, w->dta_od_off, sizeof(int64_t) * n); else ((int64_t *)dst)[0] = 0; break;
+    case UX_A_DTA_ROUTE_OFFSETS: if (w->dta_route_off) memcpy(dst, w->dta_route_off, sizeof(int64_t) * n); else ((int64_t *)dst)[0] = 0; break;
+    case UX_A_DTA_ROUTE_LINKS: memcpy(dst, w->dta_links, sizeof(int) * n); break;
+    case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: case UX_A_DTA_RS_LINKS: case UX_A_DTA_RA_LINKS: case UX_A_DTA_RA_ENTRY_T:
+    case UX_A_DTA_COST_ACTUAL: case UX_A_DTA_T_GAP: case UX_A_DTA_CHOICE: {
+        if (!w->has_swap) return fail(w, UX_ERR_RUNTIME, "no route swap result");
+        const void *src = what == UX_A_DTA_RS_OFFSETS ? (void *)w->rs_off : what == UX_A_DTA_RA_OFFSETS ? (void *)w->ra_off : what == UX_A_DTA_RS_LINKS ? (void *)w->rs_links
+            : what == UX_A_DTA_RA_LINKS ? (void *)w->ra_links : what == UX_A_DTA_RA_ENTRY_T ? (void *)w->ra_entry_t : what == UX_A_DTA_COST_ACTUAL ? (void *)w->cost_actual
+            : what == UX_A_DTA_T_GAP ? (void *)w->t_gap : (void *)w->choice;
+        memcpy(dst, src, (dt == UX_DT_I32 ? 4 : 8) * (size_t)n);
+        break; }
     default: return fail(w, UX_ERR_INVALID, "unknown array %d", what);
     }
     return n;
@@ -1120,6 +1152,305 @@ UX_API int64_t uxo_ensemble_link_stats(ux_world *w, double *dst, int64_t capacit
     return L * 4;
 }
 UX_API int64_t uxo_ensemble_link_stats_device(ux_world *w, void **dptr) { (void)dptr; return fail(w, UX_ERR_RUNTIME, "the oracle has no device arrays"); }
+
+
+/* ------------------------------------------------------------------------------------------------ */
+/* DTA solver batch operations: restatement of dta_solver.cpp + traffi.cpp:650-689,  */
+/* 1317-1481.  Random streams are the reference's own here (std::mt19937 seeded per call), so these   */
+/* functions are bit-exact against oracle/_ref for every output.                                      */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* std::mt19937 = MT19937 (Matsumoto & Nishimura 1998), default parameters */
+typedef struct { uint32_t s[624]; int idx; } mt19937;
+static void mt_seed(mt19937 *m, uint32_t seed) {
+    m->s[0] = seed;
+    for (int i = 1; i < 624; i++) m->s[i] = 1812433253u * (m->s[i - 1] ^ (m->s[i - 1] >> 30)) + (uint32_t)i;
+    m->idx = 624;
+}
+static uint32_t mt_next(mt19937 *m) {
+    if (m->idx >= 624) {
+        for (int i = 0; i < 624; i++) {
+            uint32_t y = (m->s[i] & 0x80000000u) | (m->s[(i + 1) % 624] & 0x7fffffffu);
+            m->s[i] = m->s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        m->idx = 0;
+    }
+    uint32_t y = m->s[m->idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+/* std::uniform_real_distribution<double>(a, b) over mt19937 as libstdc++ evaluates it: generate_canonical<double, 53>
+ * takes two 32-bit draws, sum = d0 + d1 * 2^32, divided by 2^64 (clamped below 1), then * (b - a) + a. */
+static double mt_uniform(mt19937 *m, double a, double b) {
+    double sum = 0.0, tmp = 1.0;
+    for (int k = 0; k < 2; k++) { sum += (double)mt_next(m) * tmp; tmp *= 4294967296.0; }
+    double r = sum / tmp;
+    if (r >= 1.0) r = nextafter(1.0, 0.0);
+    return r * (b - a) + a;
+}
+
+/* min-heap of (dist, node) pairs ordered like std::pair<double,int> under std::greater (traffi.cpp:1353) */
+typedef struct { double d; int n; } HeapItem;
+static int heap_less(HeapItem a, HeapItem b) { return a.d < b.d || (a.d == b.d && a.n < b.n); }
+static void heap_push(HeapItem **h, int *n, int *cap, HeapItem it) {
+    if (*n >= *cap) { *cap = *cap ? *cap * 2 : 64; *h = (HeapItem *)xrealloc(*h, sizeof(HeapItem) * (size_t)*cap); }
+    int i = (*n)++;
+    while (i > 0) { int p = (i - 1) / 2; if (!heap_less(it, (*h)[p])) break; (*h)[i] = (*h)[p]; i = p; }
+    (*h)[i] = it;
+}
+static HeapItem heap_pop(HeapItem *h, int *n) {
+    HeapItem top = h[0], last = h[--(*n)];
+    int i = 0;
+    while (1) {
+        int c = 2 * i + 1;
+        if (c >= *n) break;
+        if (c + 1 < *n && heap_less(h[c + 1], h[c])) c++;
+        if (!heap_less(h[c], last)) break;
+        h[i] = h[c]; i = c;
+    }
+    if (*n > 0) h[i] = last;
+    return top;
+}
+
+/* World::route_search_all(adj, 0) traffi.cpp:1317-1385: forward Dijkstra from every source over the cells adj > 0,
+ * neighbours in ascending node order, strict improvement, next hop inherited from the parent. */
+static void dta_route_search_all(int N, const double *adj, double *dist, int *next) {
+    int *nb_off = (int *)xrealloc(NULL, sizeof(int) * (size_t)(N + 1)), cnt = 0;
+    for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) if (adj[(size_t)i * N + j] > 0.0) cnt++;
+    int *nb = (int *)xrealloc(NULL, sizeof(int) * (size_t)(cnt + 1));
+    cnt = 0;
+    for (int i = 0; i < N; i++) { nb_off[i] = cnt; for (int j = 0; j < N; j++) if (adj[(size_t)i * N + j] > 0.0) nb[cnt++] = j; }
+    nb_off[N] = cnt;
+    unsigned char *visited = (unsigned char *)xrealloc(NULL, (size_t)N + 1);
+    HeapItem *heap = NULL; int hn = 0, hcap = 0;
+    for (int start = 0; start < N; start++) {
+        double *ds = dist + (size_t)start * N; int *nh = next + (size_t)start * N;
+        for (int i = 0; i < N; i++) { ds[i] = INFINITY; nh[i] = -1; visited[i] = 0; }
+        ds[start] = 0.0; nh[start] = start;
+        HeapItem it0 = {0.0, start}; heap_push(&heap, &hn, &hcap, it0);
+        while (hn > 0) {
+            HeapItem it = heap_pop(heap, &hn);
+            int cur = it.n;
+            if (visited[cur]) continue;
+            visited[cur] = 1;
+            double dcur = ds[cur];
+            for (int q = nb_off[cur]; q < nb_off[cur + 1]; q++) {
+                int nx = nb[q];
+                double nd = dcur + adj[(size_t)cur * N + nx];
+                if (nd < ds[nx]) { ds[nx] = nd; nh[nx] = (cur == start) ? nx : nh[cur]; HeapItem pi = {nd, nx}; heap_push(&heap, &hn, &hcap, pi); }
+            }
+        }
+    }
+    free(nb_off); free(nb); free(visited); free(heap);
+}
+
+typedef struct { int n; int **r; int *len; } RouteList;
+
+static void dta_store_free(ux_world *w) {
+    free(w->dta_o); free(w->dta_d); free(w->dta_od_off); free(w->dta_route_off); free(w->dta_links);
+    w->dta_o = w->dta_d = w->dta_links = NULL; w->dta_od_off = w->dta_route_off = NULL; w->dta_n_od = 0;
+}
+
+/* dta_enumerate_od_route_sets_ids dta_solver.cpp:16-24 = World::enumerate_k_random_routes_cpp traffi.cpp:1387-1481 */
+UX_API int64_t uxo_dta_enumerate_route_sets(ux_world *w, int k, unsigned int seed) {
+    if (!w->initialized) { int rc = uxo_initialize_adj_matrix(w); if (rc) return rc; }
+    int N = w->nn, L = w->nl;
+    int *pair_link = (int *)xrealloc(NULL, sizeof(int) * (size_t)N * N + 4);
+    for (size_t i = 0; i < (size_t)N * N; i++) pair_link[i] = -1;
+    for (int l = 0; l < L; l++) pair_link[(size_t)w->links[l].start * N + w->links[l].end] = l;  /* last link wins */
+    RouteList *rl = (RouteList *)calloc((size_t)N * N + 1, sizeof(RouteList));
+    unsigned char *present = (unsigned char *)calloc((size_t)N * N + 1, 1);
+    double *adj = (double *)calloc((size_t)N * N + 1, sizeof(double)), *dist = (double *)xrealloc(NULL, sizeof(double) * (size_t)N * N + 8);
+    int *next = (int *)xrealloc(NULL, sizeof(int) * (size_t)N * N + 4), *path = (int *)xrealloc(NULL, sizeof(int) * (size_t)(N + 1));
+    mt19937 rng; mt_seed(&rng, seed);
+    int counter = 0, iteration = 0; double avg_old = 0.0;
+    while (1) {
+        for (int l = 0; l < L; l++) {
+            const OLink *ln = &w->links[l];
+            double base = ln->length / ln->vmax;
+            adj[(size_t)ln->start * N + ln->end] = iteration == 0 ? base : base * mt_uniform(&rng, 0.0, 100.0);
+        }
+        dta_route_search_all(N, adj, dist, next);
+        long long total_routes = 0, total_pairs = 0;
+        for (int src = 0; src < N; src++) for (int dst = 0; dst < N; dst++) {
+            if (src == dst || next[(size_t)src * N + dst] == -1) continue;
+            RouteList *R = &rl[(size_t)src * N + dst];
+            present[(size_t)src * N + dst] = 1;
+            total_pairs++; total_routes += R->n;
+            if (R->n >= k) continue;
+            int len = 0, cur = src, valid = 1;
+            while (cur != dst) {
+                int nx = next[(size_t)cur * N + dst];
+                if (nx == -1 || nx == cur) { valid = 0; break; }
+                int lid = pair_link[(size_t)cur * N + nx];
+                if (lid == -1 || len >= N) { valid = 0; break; }
+                path[len++] = lid; cur = nx;
+            }
+            if (!valid || len == 0) continue;
+            int dup = 0;
+            for (int q = 0; q < R->n && !dup; q++) if (R->len[q] == len && memcmp(R->r[q], path, sizeof(int) * (size_t)len) == 0) dup = 1;
+            if (dup) continue;
+            R->r = (int **)xrealloc(R->r, sizeof(int *) * (size_t)(R->n + 1)); R->len = (int *)xrealloc(R->len, sizeof(int) * (size_t)(R->n + 1));
+            R->r[R->n] = (int *)xrealloc(NULL, sizeof(int) * (size_t)len); memcpy(R->r[R->n], path, sizeof(int) * (size_t)len); R->len[R->n] = len; R->n++;
+        }
+        double avg = total_pairs > 0 ? (double)total_routes / (double)total_pairs : 0.0;
+        if (avg == avg_old) counter++; else { counter = 0; avg_old = avg; }
+        iteration++;
+        if (counter > 10) break;
+    }
+    /* flatten: pairs in (orig, dest) order, including connected pairs that ended up with no route */
+    dta_store_free(w);
+    int64_t n_od = 0, n_routes = 0, n_links = 0;
+    for (size_t i = 0; i < (size_t)N * N; i++) if (present[i]) { n_od++; n_routes += rl[i].n; for (int q = 0; q < rl[i].n; q++) n_links += rl[i].len[q]; }
+    w->dta_n_od = n_od;
+    w->dta_o = (int *)xrealloc(NULL, sizeof(int) * (size_t)n_od); w->dta_d = (int *)xrealloc(NULL, sizeof(int) * (size_t)n_od);
+    w->dta_od_off = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (size_t)(n_od + 1)); w->dta_route_off = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (size_t)(n_routes + 1));
+    w->dta_links = (int *)xrealloc(NULL, sizeof(int) * (size_t)n_links);
+    int64_t p = 0, r = 0, e = 0;
+    w->dta_od_off[0] = 0; w->dta_route_off[0] = 0;
+    for (int src = 0; src < N; src++) for (int dst = 0; dst < N; dst++) {
+        size_t i = (size_t)src * N + dst;
+        if (!present[i]) continue;
+        w->dta_o[p] = src; w->dta_d[p] = dst;
+        for (int q = 0; q < rl[i].n; q++) { memcpy(w->dta_links + e, rl[i].r[q], sizeof(int) * (size_t)rl[i].len[q]); e += rl[i].len[q]; w->dta_route_off[++r] = e; free(rl[i].r[q]); }
+        free(rl[i].r); free(rl[i].len);
+        w->dta_od_off[++p] = r;
+    }
+    free(pair_link); free(rl); free(present); free(adj); free(dist); free(next); free(path);
+    return n_routes;
+}
+
+/* World.make_od_route_set_store bindings.cpp:467-489 */
+UX_API int uxo_dta_set_route_sets(ux_world *w, int64_t n_od, const int *orig, const int *dest, const int64_t *od_off, const int64_t *route_off, const int *links) {
+    for (int64_t p = 1; p < n_od; p++)
+        if (orig[p] < orig[p - 1] || (orig[p] == orig[p - 1] && dest[p] <= dest[p - 1])) return fail(w, UX_ERR_INVALID, "route sets must be sorted by (orig, dest) without duplicates");
+    dta_store_free(w);
+    int64_t n_routes = od_off[n_od], n_links = route_off[n_routes];
+    w->dta_n_od = n_od;
+    w->dta_o = (int *)xrealloc(NULL, sizeof(int) * (size_t)n_od); memcpy(w->dta_o, orig, sizeof(int) * (size_t)n_od);
+    w->dta_d = (int *)xrealloc(NULL, sizeof(int) * (size_t)n_od); memcpy(w->dta_d, dest, sizeof(int) * (size_t)n_od);
+    w->dta_od_off = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (size_t)(n_od + 1)); memcpy(w->dta_od_off, od_off, sizeof(int64_t) * (size_t)(n_od + 1));
+    w->dta_route_off = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (size_t)(n_routes + 1)); memcpy(w->dta_route_off, route_off, sizeof(int64_t) * (size_t)(n_routes + 1));
+    w->dta_links = (int *)xrealloc(NULL, sizeof(int) * (size_t)n_links); memcpy(w->dta_links, links, sizeof(int) * (size_t)n_links);
+    return 0;
+}
+
+/* dta_get_toll / dta_get_actual_travel_time dta_solver.h:44-65 */
+static double dta_toll(const ux_world *w, const OLink *ln, double t) {
+    if (ln->ntoll > 0) { int ts = (int)(t / w->delta_t); if (ts < 0) ts = 0; if (ts >= ln->ntoll) ts = ln->ntoll - 1; return ln->toll[ts]; }
+    return ln->penalty;
+}
+static double dta_actual_tt(ux_world *w, OLink *ln, double t) {
+    ensure_traveltime_real(w, ln);
+    int n = w->total_ts;
+    if (n == 0) return ln->length / ln->vmax;
+    int idx = (int)(t / w->delta_t);
+    if (idx < 0) idx = 0;
+    if (idx >= n) idx = n - 1;
+    return ln->tt_real[idx];
+}
+/* Link::estimate_congestion_externality traffi.cpp:650-689 */
+static double dta_externality(ux_world *w, OLink *ln, int ts) {
+    ensure_traveltime_real(w, ln);
+    int n = w->total_ts; double dt = w->delta_t, fftt = ln->length / ln->vmax * 1.01;
+    int ts_end = ts;
+    for (int i = ts; i < n; i++) {
+        double tt_i = ln->tt_real[i];
+        int fut = i + (int)(tt_i / dt);
+        if (fut >= n) break;
+        if (tt_i > fftt && ln->arr[fut] - ln->dep[fut] > 0) ts_end = i; else break;
+    }
+    double veh_count = 0;
+    if (ts >= 0 && ts < n && ts_end >= 0 && ts_end < n) veh_count = ln->arr[ts_end] - ln->arr[ts];
+    int ts_out = 0;
+    if (ts >= 0 && ts < n) ts_out = (int)(ts + (int)(ln->tt_real[ts] / dt)) + 1;
+    if (ts_out >= n) ts_out = n - 1;
+    int ts_out_leader = ts_out;
+    for (int i = ts_out; i > 0; i--) if (i < n && ts_out < n && ln->dep[i] < ln->dep[ts_out]) { ts_out_leader = i; break; }
+    return (double)(ts_out - ts_out_leader) * dt * veh_count;
+}
+/* dta_compute_route_cost_due / _dso dta_solver.cpp:72-104 */
+static double dta_route_cost(ux_world *w, int mode, const int *links, int n, double departure_time) {
+    double tt_total = 0.0, extra = 0.0, t = departure_time;
+    for (int j = 0; j < n; j++) {
+        OLink *ln = &w->links[links[j]];
+        double ltt = dta_actual_tt(w, ln, t);
+        if (mode == 0) extra += dta_toll(w, ln, t); else extra += dta_externality(w, ln, (int)(t / w->delta_t));
+        tt_total += ltt; t += ltt;
+    }
+    return tt_total + extra;
+}
+
+/* dta_route_swap_due / dta_route_swap_dso dta_solver.cpp:130-373 */
+UX_API int uxo_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
+    if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "oracle has a single replica");
+    if (mode != 0 && swap_num >= 0) return fail(w, UX_ERR_INVALID, "swap_num >= 0 uses std::shuffle, which this restatement does not reproduce");
+    int64_t P = w->nv;
+    free(w->rs_off); free(w->ra_off); free(w->rs_links); free(w->ra_links); free(w->ra_entry_t); free(w->cost_actual); free(w->t_gap); free(w->choice);
+    w->rs_off = (int64_t *)calloc((size_t)P + 1, sizeof(int64_t)); w->ra_off = (int64_t *)calloc((size_t)P + 1, sizeof(int64_t));
+    w->cost_actual = (double *)calloc((size_t)P + 1, sizeof(double)); w->t_gap = (double *)calloc((size_t)P + 1, sizeof(double)); w->choice = (int *)calloc((size_t)P + 1, sizeof(int));
+    /* traveled routes (dta_get_traveled_route dta_solver.cpp:30-57) */
+    int64_t tot = 0;
+    for (int64_t i = 0; i < P; i++) { w->ra_off[i] = tot; tot += enter_count(&w->vehs[i]); }
+    w->ra_off[P] = tot;
+    w->ra_links = (int *)xrealloc(NULL, sizeof(int) * (size_t)tot + 4); w->ra_entry_t = (double *)xrealloc(NULL, sizeof(double) * (size_t)tot + 8);
+    for (int64_t i = 0; i < P; i++) {
+        const OVeh *v = &w->vehs[i]; int prev = -999; int64_t s = w->ra_off[i];
+        for (int k = 0; k < v->log_size; k++) { int lid = v->log_link[k]; if (lid >= 0 && lid != prev) { w->ra_links[s] = lid; w->ra_entry_t[s] = log_t_at(w, v, k); s++; prev = lid; } }
+    }
+    mt19937 rng; mt_seed(&rng, rng_seed);
+    unsigned char *cand = NULL;
+    if (mode != 0) { cand = (unsigned char *)calloc((size_t)P + 1, 1); for (int64_t i = 0; i < P; i++) cand[i] = mt_uniform(&rng, 0.0, 1.0) < swap_prob; }
+    w->n_swap = 0; w->potential_n_swap = 0; w->total_t_gap = 0;
+    for (int64_t vi = 0; vi < P; vi++) {
+        const OVeh *v = &w->vehs[vi];
+        const int *tr = w->ra_links + w->ra_off[vi]; const double *et = w->ra_entry_t + w->ra_off[vi]; int ntr = (int)(w->ra_off[vi + 1] - w->ra_off[vi]);
+        double arrival = (v->state == UX_VS_END && v->arrival_time >= 0) ? v->arrival_time : -1.0;
+        w->cost_actual[vi] = ntr > 0 ? arrival - et[0] : 0;
+        w->choice[vi] = -2;
+        if (v->state != UX_VS_END) continue;
+        w->choice[vi] = -1;
+        int64_t lo = 0, hi = w->dta_n_od, pair = -1;
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (w->dta_o[mid] < v->orig || (w->dta_o[mid] == v->orig && w->dta_d[mid] < v->dest)) lo = mid + 1; else hi = mid; }
+        if (lo < w->dta_n_od && w->dta_o[lo] == v->orig && w->dta_d[lo] == v->dest) pair = lo;
+        if (pair < 0) continue;
+        int64_t r0 = w->dta_od_off[pair], r1 = w->dta_od_off[pair + 1];
+        if (has_external) {
+            int found = 0;
+            for (int64_t r = r0; r < r1 && !found; r++) { int64_t len = w->dta_route_off[r + 1] - w->dta_route_off[r]; if (len == ntr && memcmp(w->dta_links + w->dta_route_off[r], tr, sizeof(int) * (size_t)ntr) == 0) found = 1; }
+            if (!found && r1 > r0) { w->choice[vi] = (int)r0; continue; }
+        }
+        int flag_swap = mode == 0 ? (mt_uniform(&rng, 0.0, 1.0) < swap_prob) : cand[vi];
+        double departure_t = ntr > 0 ? et[0] : v->departure_time, cost_current = 0.0;
+        if (mode == 0) {
+            double t = departure_t;
+            for (int j = 0; j < ntr; j++) { OLink *ln = &w->links[tr[j]]; double ltt = dta_actual_tt(w, ln, t); cost_current += dta_toll(w, ln, et[j]); cost_current += ltt; t += ltt; }
+        } else cost_current = dta_route_cost(w, 1, tr, ntr, departure_t);
+        int changed = 0, changed_idx = -1; double t_gap = 0.0, pot = 0.0;
+        for (int64_t r = r0; r < r1; r++) {
+            double cost_alt = dta_route_cost(w, mode, w->dta_links + w->dta_route_off[r], (int)(w->dta_route_off[r + 1] - w->dta_route_off[r]), departure_t);
+            if (cost_alt < cost_current) { t_gap = cost_current - cost_alt; pot = w->p.delta_n; if (flag_swap) { changed = 1; changed_idx = (int)r; cost_current = cost_alt; } }
+        }
+        w->potential_n_swap += pot; w->total_t_gap += t_gap; w->t_gap[vi] = t_gap;
+        if (changed && changed_idx >= 0) { w->choice[vi] = changed_idx; w->n_swap += w->p.delta_n; }
+    }
+    free(cand);
+    /* routes_specified */
+    tot = 0;
+    for (int64_t vi = 0; vi < P; vi++) {
+        w->rs_off[vi] = tot;
+        int c = w->choice[vi];
+        tot += c == -2 ? 0 : c == -1 ? w->ra_off[vi + 1] - w->ra_off[vi] : w->dta_route_off[c + 1] - w->dta_route_off[c];
+    }
+    w->rs_off[P] = tot;
+    w->rs_links = (int *)xrealloc(NULL, sizeof(int) * (size_t)tot + 4);
+    for (int64_t vi = 0; vi < P; vi++) {
+        int c = w->choice[vi]; int64_t n = w->rs_off[vi + 1] - w->rs_off[vi];
+        if (n > 0) memcpy(w->rs_links + w->rs_off[vi], c == -1 ? w->ra_links + w->ra_off[vi] : w->dta_links + w->dta_route_off[c], sizeof(int) * (size_t)n);
+    }
+    w->has_swap = 1;
+    return 0;
+}
 
 #define PFX(n) uxo_##n
 /* vectorised ingest: add_node / add_link / add_demand in index order (include/uxsim_b200.h) */

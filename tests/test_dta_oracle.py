@@ -1,0 +1,74 @@
+"""DTA solver batch operations: the oracle's restatement of dta_solver.cpp against the reference's own
+code (oracle/_ref, built from /root/reference in the dev container) -- bit-exact for every output, since these functions
+use the reference's own mt19937 streams."""
+import numpy as np
+import pytest
+
+from uxsim_b200 import _capi as C
+from uxsim_b200 import scenario as S
+
+SCENARIOS = {
+    "diverge": lambda: S.diverge_2route(),
+    "grid5": lambda: S.grid(5, seed=3),
+    "siouxfalls": lambda: S.sioux_falls(),
+    "dta_grid9": lambda: S.dta_grid9(),
+}
+
+
+def first_route_csr(E, pick=0):
+    """Per-vehicle CSR enforcing route number `pick` (mod the set size) of the vehicle's OD pair from the store."""
+    o, d, od_off, r_off, links = E.dta_route_sets_csr()
+    key = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(o, d))}
+    vo, vd = E.get_array(C.A_VEH_ORIG), E.get_array(C.A_VEH_DEST)
+    ids, off = [], [0]
+    for a, b in zip(vo, vd):
+        p = key.get((int(a), int(b)))
+        if p is not None and od_off[p + 1] > od_off[p]:
+            r = od_off[p] + pick % (od_off[p + 1] - od_off[p])
+            ids.extend(links[r_off[r]:r_off[r + 1]])
+        off.append(len(ids))
+    return np.asarray(ids, np.int32), np.asarray(off, np.int64)
+
+
+def run(api, name, seed=0, k=6, enum_seed=99, pick=0, **kw):
+    """A finished run in which every platoon follows an enforced route (as in DTA iterations >= 1), so that the oracle and
+    the reference hold the same state whatever their shortest-path tie-breaking is."""
+    sc = SCENARIOS[name]()
+    E = sc.to_engine(api, vehicle_logging_timestep_interval=1, random_seed=seed, **kw)
+    E.dta_enumerate_route_sets(k, enum_seed)
+    E.batch_enforce_routes_csr(*first_route_csr(E, pick))
+    E.main_loop()
+    return E
+
+
+def assert_swap_equal(a, b):
+    for k in ("rs_offsets", "rs_link_ids", "ra_offsets", "ra_link_ids"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["cost_actual"], b["cost_actual"])
+    for k in ("n_swap", "potential_n_swap", "total_t_gap"):
+        assert a[k] == b[k], (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("name", ["diverge", "grid5", "siouxfalls"])
+def test_enumerate_route_sets_matches_reference(oracle_api, ref_api, name):
+    sc = SCENARIOS[name]()
+    Eo, Er = sc.to_engine(oracle_api), sc.to_engine(ref_api)
+    for k, seed in ((3, 1), (10, 12345)):
+        no, nr = Eo.dta_enumerate_route_sets(k, seed), Er.dta_enumerate_route_sets(k, seed)
+        assert no == nr and no > 0
+        for x, y in zip(Eo.dta_route_sets_csr(), Er.dta_route_sets_csr()):
+            assert np.array_equal(x, y)
+    Eo.close(); Er.close()
+
+
+@pytest.mark.parametrize("name", ["diverge", "grid5", "siouxfalls", "dta_grid9"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_route_swap_matches_reference(oracle_api, ref_api, name, mode):
+    # deterministic simulation (hard_deterministic_mode) so that both engines hold the same finished run
+    Eo, Er = (run(api, name, hard_deterministic_mode=True) for api in (oracle_api, ref_api))
+    assert np.array_equal(Eo.get_array(C.A_VEH_ARRIVAL_TS), Er.get_array(C.A_VEH_ARRIVAL_TS))
+    for swap_prob, rng_seed in ((0.05, 7), (0.5, 8), (1.0, 9)):
+        a, b = Eo.dta_route_swap(mode, swap_prob, rng_seed), Er.dta_route_swap(mode, swap_prob, rng_seed)
+        assert_swap_equal(a, b)
+        assert np.array_equal(Eo.get_array(C.A_DTA_RA_ENTRY_T), Er.get_array(C.A_DTA_RA_ENTRY_T))
+    Eo.close(); Er.close()

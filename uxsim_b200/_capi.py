@@ -36,9 +36,10 @@ I_ROUTE_UPDATE_STEPS, I_PLATOON_UPDATES, I_TRIPS_COMPLETED, I_LOG_ENTRIES, I_KER
 I_NUM_ACTIVE_DESTS, I_TRANSFER_LEVELS, I_LINK_EVENTS = 12, 13, 14
 I_H2D_BYTES, I_D2H_BYTES, I_RING_SLOTS, I_MAX_DEPART_TS, I_KERNEL_LAUNCHES_OF = 15, 16, 17, 18, 100
 K_NAMES = ("k_pre(unused)", "k_node", "k_update", "k_edge_cost", "k_sssp", "k_duo", "misc")
-OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS = 1, 2
+OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS, OPT_RECORD_TRAVERSALS = 1, 2, 3
 D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT, D_LAST_LOOP_MS, D_KERNEL_MS_OF = 1, 2, 3, 4, 5, 6, 100
 D_UPLOAD_MS, D_GRAPH_BUILD_MS, D_LAST_LOOP_WALL_MS = 7, 8, 9
+D_DTA_N_SWAP, D_DTA_POTENTIAL_N_SWAP, D_DTA_TOTAL_T_GAP, D_DTA_SWAP_MS = 10, 11, 12, 13
 
 A_CUM_ARRIVAL, A_CUM_DEPARTURE, A_TRAVELTIME_INSTANT, A_TRAVELTIME_ACTUAL = 1, 2, 3, 4
 A_VEH_STATE, A_VEH_ARRIVAL_TS, A_VEH_DEPART_TS, A_VEH_TRAVEL_TIME, A_VEH_DISTANCE = 10, 11, 12, 13, 14
@@ -49,6 +50,8 @@ A_LINK_STAT_COUNT, A_LINK_TRIPS_COMPLETED, A_LINK_AVE_V_SUM = 43, 44, 45
 A_ROUTE_PREF, A_ROUTE_DIST, A_ROUTE_NEXT = 50, 51, 52
 A_LOG_OFFSETS, A_LOG_T, A_LOG_X, A_LOG_V, A_LOG_STATE, A_LOG_S, A_LOG_LANE, A_LOG_LINK = 60, 61, 62, 63, 64, 65, 66, 67
 A_LOG_N_MISSING, A_LTL_OFFSETS, A_LTL_T, A_LTL_ID = 68, 69, 70, 71
+A_DTA_OD_ORIG, A_DTA_OD_DEST, A_DTA_OD_OFFSETS, A_DTA_ROUTE_OFFSETS, A_DTA_ROUTE_LINKS = 100, 101, 102, 103, 104
+A_DTA_RS_OFFSETS, A_DTA_RS_LINKS, A_DTA_RA_OFFSETS, A_DTA_RA_LINKS, A_DTA_COST_ACTUAL, A_DTA_T_GAP, A_DTA_CHOICE, A_DTA_RA_ENTRY_T = 110, 111, 112, 113, 114, 115, 116, 117
 A_ENTER_LINK, A_ENTER_TIME, A_ENTER_VEH = 80, 81, 82
 
 DT_F64, DT_I32, DT_I64 = 1, 2, 3
@@ -69,7 +72,7 @@ ABI_SYMBOLS = (
     "batch_enforce_routes_csr", "set_t_max", "set_toll_timeseries", "initialize_adj_matrix", "main_loop",
     "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
     "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
-    "ensemble_link_stats", "last_error",
+    "ensemble_link_stats", "last_error", "dta_enumerate_route_sets", "dta_set_route_sets", "dta_route_swap",
 )
 
 
@@ -156,6 +159,10 @@ class CApi:
         self.ensemble_link_stats_device = fn("ensemble_link_stats_device", C.c_int64, [p, C.POINTER(C.c_void_p)])
         self.ensemble_link_stats = fn("ensemble_link_stats", C.c_int64, [p, f64p, C.c_int64])
         self.last_error = fn("last_error", C.c_char_p, [p])
+        # DTA solver batch operations
+        self.dta_enumerate_route_sets = fn("dta_enumerate_route_sets", C.c_int64, [p, C.c_int, C.c_uint])
+        self.dta_set_route_sets = fn("dta_set_route_sets", C.c_int, [p, C.c_int64, i32p, i32p, i64p, i64p, i32p])
+        self.dta_route_swap = fn("dta_route_swap", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint])
 
     def exported(self, name: str) -> bool:
         return hasattr(self.lib, self.prefix + name)
@@ -289,6 +296,33 @@ class EngineWorld:
 
     def check_simulation_ongoing(self) -> bool:
         return bool(self.api.check_simulation_ongoing(self.h))
+
+    # -- DTA solver batch operations --------------------------------------------------
+    def dta_enumerate_route_sets(self, k: int, seed: int) -> int:
+        """World.enumerate_od_route_sets_ids_cpp (bindings.cpp:461-465): returns the number of routes."""
+        return self._check(self.api.dta_enumerate_route_sets(self.h, int(k), int(seed) & 0xFFFFFFFF))
+
+    def dta_set_route_sets(self, orig, dest, od_offsets, route_offsets, route_links):
+        """World.make_od_route_set_store (bindings.cpp:467-489) from CSR arrays."""
+        o, d, rl = _as_i32(orig), _as_i32(dest), _as_i32(route_links)
+        oo, ro = np.ascontiguousarray(od_offsets, dtype=np.int64), np.ascontiguousarray(route_offsets, dtype=np.int64)
+        ip, lp = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        self._check(self.api.dta_set_route_sets(self.h, len(o), o.ctypes.data_as(ip), d.ctypes.data_as(ip), oo.ctypes.data_as(lp),
+                                                ro.ctypes.data_as(lp), rl.ctypes.data_as(ip)))
+
+    def dta_route_sets_csr(self):
+        """ODRouteSetStore.to_csr: (orig, dest, od_offsets, route_offsets, route_links), pairs sorted by (orig, dest)."""
+        return tuple(self.get_array(a) for a in (A_DTA_OD_ORIG, A_DTA_OD_DEST, A_DTA_OD_OFFSETS, A_DTA_ROUTE_OFFSETS, A_DTA_ROUTE_LINKS))
+
+    def dta_route_swap(self, mode: int, swap_prob: float, rng_seed: int, swap_num: int = -1, has_external_route_sets: bool = False,
+                       replica: int = 0) -> dict:
+        """World.route_swap_due (mode 0) / route_swap_dso (mode 1) (bindings.cpp:661-706): same keys as the nanobind dict."""
+        self._check(self.api.dta_route_swap(self.h, int(replica), int(mode), float(swap_prob), int(swap_num),
+                                            1 if has_external_route_sets else 0, int(rng_seed) & 0xFFFFFFFF))
+        g = lambda a: self.get_array(a, replica)
+        return {"rs_link_ids": g(A_DTA_RS_LINKS), "rs_offsets": g(A_DTA_RS_OFFSETS), "ra_link_ids": g(A_DTA_RA_LINKS),
+                "ra_offsets": g(A_DTA_RA_OFFSETS), "cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP),
+                "potential_n_swap": self.get_double(D_DTA_POTENTIAL_N_SWAP), "total_t_gap": self.get_double(D_DTA_TOTAL_T_GAP)}
 
     # -- interventions --------------------------------------------------------------------------------
     def set_link_param(self, link: int, field: int, value: float):

@@ -30,6 +30,8 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 static dim3 blockIdx, threadIdx, blockDim, gridDim;
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;

@@ -35,6 +35,7 @@ def run(api, name, seed=0, k=6, enum_seed=99, pick=0, **kw):
     the reference hold the same state whatever their shortest-path tie-breaking is."""
     sc = SCENARIOS[name]()
     E = sc.to_engine(api, vehicle_logging_timestep_interval=1, random_seed=seed, **kw)
+    E.set_option(C.OPT_RECORD_TRAVERSALS, 1)  # the CUDA engine records link entries instead of reading logs; a no-op elsewhere
     E.dta_enumerate_route_sets(k, enum_seed)
     E.batch_enforce_routes_csr(*first_route_csr(E, pick))
     E.main_loop()
@@ -72,3 +73,36 @@ def test_route_swap_matches_reference(oracle_api, ref_api, name, mode):
         assert_swap_equal(a, b)
         assert np.array_equal(Eo.get_array(C.A_DTA_RA_ENTRY_T), Er.get_array(C.A_DTA_RA_ENTRY_T))
     Eo.close(); Er.close()
+
+
+# ---- the product's kernels (host emulation build of engine.cu, CPU only) against the oracle ------------------------------
+@pytest.mark.parametrize("name", ["diverge", "grid5", "siouxfalls"])
+def test_emu_enumerate_matches_oracle(oracle_api, emu_api, name):
+    sc = SCENARIOS[name]()
+    Eo, Ee = sc.to_engine(oracle_api), sc.to_engine(emu_api)
+    assert Eo.dta_enumerate_route_sets(5, 4242) == Ee.dta_enumerate_route_sets(5, 4242)
+    for x, y in zip(Eo.dta_route_sets_csr(), Ee.dta_route_sets_csr()):
+        assert np.array_equal(x, y)
+    Eo.close(); Ee.close()
+
+
+def check_swap_against_oracle(oracle_api, api, name, mode, **kw):
+    Eo, Ee = (run(a, name, hard_deterministic_mode=True, **kw) for a in (oracle_api, api))
+    assert np.array_equal(Eo.get_array(C.A_VEH_ARRIVAL_TS), Ee.get_array(C.A_VEH_ARRIVAL_TS))
+    moved = 0
+    for swap_prob, rng_seed in ((0.05, 7), (0.5, 8), (1.0, 9)):
+        a, b = Eo.dta_route_swap(mode, swap_prob, rng_seed), Ee.dta_route_swap(mode, swap_prob, rng_seed)
+        assert_swap_equal(a, b)
+        for arr in (C.A_DTA_RA_ENTRY_T, C.A_DTA_T_GAP, C.A_DTA_CHOICE):
+            assert np.array_equal(Eo.get_array(arr), Ee.get_array(arr)), arr
+        moved += a["n_swap"]
+    Eo.close(); Ee.close()
+    return moved
+
+
+@pytest.mark.parametrize("name", ["diverge", "grid5", "siouxfalls", "dta_grid9"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_emu_route_swap_matches_oracle(oracle_api, emu_api, name, mode):
+    moved = check_swap_against_oracle(oracle_api, emu_api, name, mode)
+    if name in ("siouxfalls", "dta_grid9"):
+        assert moved > 0  # congested networks: some platoons do find a cheaper route

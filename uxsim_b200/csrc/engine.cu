@@ -32,6 +32,10 @@
 #include <mutex>
 #include <chrono>
 #include <algorithm>
+#include <random>
+#include <queue>
+#include <thread>
+#include <atomic>
 
 #include "../../include/uxsim_b200.h"
 #include "../../include/ux_rng.h"
@@ -97,6 +101,8 @@ struct DevWorld {
     int *ev_ord, *sig_log;
     double *pref, *rdist, *pair_cost;
     int *pref_active, *has_path, *rnext;
+    // link-entry events (platoon, ordinal of the link on its route, link, step) in arrival order; only with UX_OPT_RECORD_TRAVERSALS
+    int4 *tv_ev; unsigned long long *tv_count; long long tv_cap;
     int *node_done;  // per node: (timestep + 1) of the last finished transfer -- monotone, so it never needs a reset
     int *err;     // [0] code, [1] info
     int *t_base;  // timestep at the start of the running graph
@@ -258,10 +264,21 @@ UX_DEV int ring_push(const DevWorld &W, int l, int hd, int cur, double x, double
     return slot;
 }
 
-UX_DEV void mark_entered(const DevWorld &W, int vid, int l) {  // traffi.cpp:160-166, 372-378
+// One link-entry event for the DTA route swap (what dta_get_traveled_route reads back out of the per-step logs,
+// dta_solver.cpp:30-57: a platoon entering link l in step t has its first log record on l at time t*dt).
+UX_DEV void record_traversal(const DevWorld &W, int vid, int k, int l, int t) {
+    if (!W.tv_count) return;
+    unsigned long long idx = atomicAdd(W.tv_count, 1ull);
+    if ((long long)idx >= W.tv_cap) { dev_error(W, DERR_LOG_FULL, l); return; }
+    W.tv_ev[idx] = make_int4(vid, k, l, t);
+}
+
+UX_DEV void mark_entered(const DevWorld &W, int vid, int l, int t) {  // traffi.cpp:160-166, 372-378
     if (W.no_cyclic) { int s = W.l_start[l]; W.v_visited[(size_t)vid * W.vis_words + (s >> 5)] |= 1u << (s & 31); }
-    W.v_trav[vid] += 1;
+    int k = W.v_trav[vid];
+    W.v_trav[vid] = k + 1;
     W.v_link[vid] = l;
+    record_traversal(W, vid, k, l, t);
 }
 
 // record a link-exit travel time (traffi.cpp:357-362, 893-898) into the "last event per entry step" table
@@ -455,7 +472,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
                 if (W.log_mode) W.v_gen_ts[vid] = t;
                 W.v_atl[vid] = (double)t * W.dt;
                 W.v_entry_x[vid] = 0.0;
-                mark_entered(W, vid, ol);
+                mark_entered(W, vid, ol, t);
                 G.o_cumarr[q] += W.dn;
                 G.o_ci[q] -= W.dn;
             }
@@ -811,7 +828,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
             S.popped[ii] += 1;
             if (W.no_cyclic) { int sn = W.l_start[ol]; W.v_visited[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
-            W.v_trav[vid] += 1;
+            { int k = W.v_trav[vid]; W.v_trav[vid] = k + 1; record_traversal(W, vid, k, ol, t); }
             W.v_link[vid] = ol;
             W.v_flags[vid] = 0;
             // carry the residual move onto the new link (traffi.cpp:400-419)
@@ -1393,6 +1410,161 @@ __global__ void k_ensemble_stats(const DevWorld *worlds, int R, double *out) {
     out[l * 4 + 0] = a0; out[l * 4 + 1] = a1; out[l * 4 + 2] = a2; out[l * 4 + 3] = a3;
 }
 
+
+// =====================================================================================================
+// DTA solver batch operations: route swap of dta_solver.cpp:130-373 on the device.
+// Every platoon evaluates the cost of each route of its OD pair on the finished run's traveltime_actual table --
+// independent work per (platoon, route), serial only along a route (the clock advances link by link).
+// =====================================================================================================
+struct DtaDev {
+    const double *tt;   // [L][T] traveltime_actual (k_tt_actual)
+    const double *ext;  // [L][T] congestion externality (DSO) or nullptr
+    const int *od_o, *od_d, *route_links; const long long *od_off, *route_off; long long n_od;  // route-set store, pairs sorted
+    const long long *tr_off; int *tr_link, *tr_t;  // traversed routes (CSR per platoon): link, entry step
+    int mode, has_external;
+    const unsigned char *flag_swap;
+    int *pair; unsigned char *draws;       // k_dta_prepare -> host RNG -> k_dta_swap
+    double *cost_actual, *t_gap; int *choice; unsigned char *pot;
+};
+
+// link-entry events -> per-platoon CSR (position = offset + ordinal of the link on the platoon's route)
+__global__ void k_dta_scatter(const DevWorld *worlds, int replica, long long n, DtaDev D) {
+    const DevWorld &W = worlds[replica];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 e = W.tv_ev[i];
+    long long q = D.tr_off[e.x] + e.y;
+    D.tr_link[q] = e.z; D.tr_t[q] = e.w;
+}
+
+// Link::estimate_congestion_externality (traffi.cpp:650-689) for every (link, step): thread per cell, [L][T]
+__global__ void k_dta_externality(const DevWorld *worlds, int replica, const double *tt, double *ext) {
+    const DevWorld &W = worlds[replica];
+    int n = W.T, L = W.L;
+    long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= (long long)L * n) return;
+    int l = (int)(cell / n), ts = (int)(cell % n);
+    const double *ttl = tt + (size_t)l * n;
+    double dt = W.dt, fftt = W.l_length[l] / W.l_vmax[l] * 1.01;
+    int ts_end = ts;
+    for (int i = ts; i < n; i++) {  // congestion tail (forward scan)
+        double tt_i = ttl[i];
+        int fut = i + (int)(tt_i / dt);
+        if (fut >= n) break;
+        if (tt_i > fftt && W.cum_arr[(size_t)fut * L + l] - W.cum_dep[(size_t)fut * L + l] > 0) ts_end = i; else break;
+    }
+    double veh_count = W.cum_arr[(size_t)ts_end * L + l] - W.cum_arr[(size_t)ts * L + l];
+    int ts_out = (int)(ts + (int)(ttl[ts] / dt)) + 1;
+    if (ts_out >= n) ts_out = n - 1;
+    int ts_out_leader = ts_out;
+    double dep_out = W.cum_dep[(size_t)ts_out * L + l];
+    for (int i = ts_out; i > 0; i--) if (W.cum_dep[(size_t)i * L + l] < dep_out) { ts_out_leader = i; break; }  // leader headway (backward scan)
+    ext[cell] = (double)(ts_out - ts_out_leader) * dt * veh_count;
+}
+
+UX_DEV double dta_actual_tt(const DevWorld &W, const DtaDev &D, int l, double t) {  // dta_get_actual_travel_time dta_solver.h:56-65
+    int n = W.T;
+    if (n == 0) return W.l_length[l] / W.l_vmax[l];
+    int idx = (int)(t / W.dt);
+    if (idx < 0) idx = 0;
+    if (idx >= n) idx = n - 1;
+    return D.tt[(size_t)l * n + idx];
+}
+UX_DEV double dta_toll(const DevWorld &W, int l, double t) {  // dta_get_toll dta_solver.h:44-53 (series cover all T steps)
+    if (W.l_toll) { int ts = (int)(t / W.dt); if (ts < 0) ts = 0; if (ts >= W.T) ts = W.T - 1; return W.l_toll[(size_t)ts * W.L + l]; }
+    return W.l_penalty[l];
+}
+// dta_compute_route_cost_due / _dso (dta_solver.cpp:72-104)
+UX_DEV double dta_route_cost(const DevWorld &W, const DtaDev &D, const int *links, int n, double departure_time) {
+    double tt_total = 0.0, extra = 0.0, t = departure_time;
+    for (int j = 0; j < n; j++) {
+        int l = links[j];
+        double ltt = dta_actual_tt(W, D, l, t);
+        if (D.mode == 0) extra += dta_toll(W, l, t);
+        else { int ts = (int)(t / W.dt); extra += (ts >= 0 && ts < W.T) ? D.ext[(size_t)l * W.T + ts] : 0.0; }
+        tt_total += ltt; t += ltt;
+    }
+    return tt_total + extra;
+}
+
+// per platoon: travel cost, and whether it takes part in the swap (finished trip, OD pair in the store, traversed route in
+// an external set): the ones that do consume one uniform draw each, in platoon order (dta_solver.cpp:149-203)
+__global__ void k_dta_prepare(const DevWorld *worlds, int replica, DtaDev D) {
+    const DevWorld &W = worlds[replica];
+    long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= W.P) return;
+    long long a0 = D.tr_off[vi]; int ntr = (int)(D.tr_off[vi + 1] - a0);
+    int st = W.v_state[vi], arr = W.v_arr_ts[vi];
+    double arrival = (st == UX_VS_END && arr >= 0) ? (double)arr * W.dt : -1.0;
+    D.cost_actual[vi] = ntr > 0 ? arrival - (double)D.tr_t[a0] * W.dt : 0.0;
+    int choice = -2, pair = -1; unsigned char draws = 0;
+    if (st == UX_VS_END || st == UX_VS_ABORT) {
+        choice = -1;
+        int o = W.v_orig[vi], d = W.v_dest[vi];
+        long long lo = 0, hi = D.n_od;
+        while (lo < hi) { long long mid = (lo + hi) >> 1; int mo = D.od_o[mid]; if (mo < o || (mo == o && D.od_d[mid] < d)) lo = mid + 1; else hi = mid; }
+        if (lo < D.n_od && D.od_o[lo] == o && D.od_d[lo] == d) {
+            long long r0 = D.od_off[lo], r1 = D.od_off[lo + 1];
+            bool forced = false;
+            if (D.has_external) {
+                bool found = false;
+                for (long long r = r0; r < r1 && !found; r++) {
+                    long long b = D.route_off[r];
+                    if (D.route_off[r + 1] - b != ntr) continue;
+                    bool same = true;
+                    for (int j = 0; j < ntr && same; j++) same = D.route_links[b + j] == D.tr_link[a0 + j];
+                    found = same;
+                }
+                if (!found && r1 > r0) { choice = (int)r0; forced = true; }
+            }
+            if (!forced) { pair = (int)lo; draws = 1; }
+        }
+    }
+    D.choice[vi] = choice; D.pair[vi] = pair; D.draws[vi] = draws; D.t_gap[vi] = 0.0; D.pot[vi] = 0;
+}
+
+#define DTA_WARPS 4
+// warp per platoon: lanes evaluate the alternative routes, then the scan over routes in store order (dta_solver.cpp:228-241)
+__global__ void __launch_bounds__(32 * DTA_WARPS) k_dta_swap(const DevWorld *worlds, int replica, DtaDev D) {
+    LOAD_WORLD_N(W, worlds, 64, replica)
+    WARP_BEGIN
+    __shared__ double cost_s[DTA_WARPS][32];
+    long long vi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int wib = (int)((threadIdx.x >> 5) % DTA_WARPS);
+    if (vi >= W.P) return;
+    int pair = D.pair[vi];
+    if (pair < 0) return;
+    long long a0 = D.tr_off[vi]; int ntr = (int)(D.tr_off[vi + 1] - a0);
+    const int *tr = D.tr_link + a0;
+    double departure_t = ntr > 0 ? (double)D.tr_t[a0] * W.dt : (double)W.v_depart_ts[vi] * W.dt;
+    long long r0 = D.od_off[pair], r1 = D.od_off[pair + 1];
+    double cost_current = 0.0, t_gap = 0.0; int changed_idx = -1; bool pot = false;
+    bool flag_swap = D.flag_swap[vi] != 0;
+    for (long long base = r0 - 1; base < r1; base += 32) {  // slot r0-1 is the traversed route itself
+        WARP_FOR(lane) {
+            long long r = base + lane;
+            double c = 0.0;
+            if (r == r0 - 1) {
+                if (D.mode == 0) {  // DUE: tolls at the actual entry times (dta_solver.cpp:209-221)
+                    double t = departure_t;
+                    for (int j = 0; j < ntr; j++) { double ltt = dta_actual_tt(W, D, tr[j], t); c += dta_toll(W, tr[j], (double)D.tr_t[a0 + j] * W.dt); c += ltt; t += ltt; }
+                } else c = dta_route_cost(W, D, tr, ntr, departure_t);
+            } else if (r < r1) c = dta_route_cost(W, D, D.route_links + D.route_off[r], (int)(D.route_off[r + 1] - D.route_off[r]), departure_t);
+            cost_s[wib][lane] = c;
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) {
+            for (int q = 0; q < 32 && base + q < r1; q++) {
+                double c = cost_s[wib][q];
+                if (base + q == r0 - 1) { cost_current = c; continue; }
+                if (c < cost_current) { t_gap = cost_current - c; pot = true; if (flag_swap) { changed_idx = (int)(base + q); cost_current = c; } }
+            }
+        }
+        WARP_SYNC();
+    }
+    WARP_FOR(lane) if (lane == 0) { D.t_gap[vi] = t_gap; D.pot[vi] = pot ? 1 : 0; if (changed_idx >= 0) D.choice[vi] = changed_idx; }
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -1443,6 +1615,17 @@ struct ux_world {
         std::vector<double> t, x, v, s, ltl_t, enter_t;
         std::vector<int> state, lane, link, n_missing, ltl_id, enter_link, enter_veh;
     } logs;
+    // DTA solver: OD route-set store (pairs sorted by (orig, dest)), its device copy, and the last route-swap result
+    bool record_traversals = false;
+    struct DtaStore {
+        std::vector<int> o, d, links; std::vector<long long> od_off{0}, route_off{0};
+        int *d_o = nullptr, *d_d = nullptr, *d_links = nullptr; long long *d_od_off = nullptr, *d_route_off = nullptr; bool on_device = false;
+    } dta;
+    struct DtaResult {
+        bool valid = false; int replica = 0;
+        std::vector<long long> rs_off, ra_off; std::vector<int> rs_links, ra_links, choice; std::vector<double> ra_entry_t, cost_actual, t_gap;
+        double n_swap = 0, potential_n_swap = 0, total_t_gap = 0, ms = 0;
+    } swap;
     // measurement
     long long h2d_bytes = 0, d2h_bytes = 0;
     double last_loop_ms = 0.0, upload_ms = 0.0, loop_wall_ms = 0.0, graph_build_ms = 0.0;
@@ -1669,6 +1852,10 @@ UX_API int ux_set_option(ux_world *w, int option, double value) {
     if (option == UX_OPT_ALL_DESTINATIONS) {
         if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "UX_OPT_ALL_DESTINATIONS must be set before the first main_loop");
         w->all_dests = value != 0.0; return 0;
+    }
+    if (option == UX_OPT_RECORD_TRAVERSALS) {
+        if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "UX_OPT_RECORD_TRAVERSALS must be set before the first main_loop");
+        w->record_traversals = value != 0.0; return 0;
     }
     return fail(w, UX_ERR_INVALID, "unknown option %d", option);
 }
@@ -1993,6 +2180,13 @@ static int upload(ux_world *w) {
             d.lg_x = dalloc<double>(w, cap, false); d.lg_v = dalloc<double>(w, cap, false); d.lg_s = dalloc<double>(w, cap, false);
             d.lg_count = dalloc<unsigned long long>(w, 1);
             if (!d.lg_vid || !d.lg_s || !d.lg_count || !d.v_gen_ts) return fail(w, UX_ERR_CUDA, "device allocation of the vehicle logs failed (%lld records)", cap);
+        }
+        if (w->record_traversals) {  // at most one link entry per platoon and step; in practice a few dozen per trip
+            long long bound = 0;
+            for (long long i = 0; i < P; i++) bound += std::max(0, T - w->vehs[i].ts - 1);
+            d.tv_cap = std::min(bound, std::max(P * 48, (long long)1 << 20));
+            d.tv_ev = dalloc<int4>(w, (size_t)d.tv_cap, false); d.tv_count = dalloc<unsigned long long>(w, 1);
+            if (!d.tv_ev || !d.tv_count) return fail(w, UX_ERR_CUDA, "device allocation of the traversal log failed (%lld events)", d.tv_cap);
         }
         d.v_visited = base.no_cyclic ? dalloc<unsigned>(w, (size_t)P * base.vis_words) : nullptr;
         d.cum_arr = dalloc<double>(w, TL); d.cum_dep = dalloc<double>(w, TL); d.tt_inst = dalloc<double>(w, TL); d.ev_tt = dalloc<double>(w, TL);
@@ -2356,6 +2550,10 @@ UX_API double ux_get_double(ux_world *w, int what) {
     case UX_D_TIME: return w->timestep * w->dt;
     case UX_D_T_MAX: return w->p.t_max;
     case UX_D_LAST_LOOP_MS: return w->last_loop_ms;
+    case UX_D_DTA_N_SWAP: return w->swap.n_swap;
+    case UX_D_DTA_POTENTIAL_N_SWAP: return w->swap.potential_n_swap;
+    case UX_D_DTA_TOTAL_T_GAP: return w->swap.total_t_gap;
+    case UX_D_DTA_SWAP_MS: return w->swap.ms;
     case UX_D_UPLOAD_MS: return w->upload_ms;
     case UX_D_GRAPH_BUILD_MS: return w->graph_build_ms;
     case UX_D_LAST_LOOP_WALL_MS: return w->loop_wall_ms;
@@ -2497,6 +2695,16 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_ROUTE_PREF: n = N * L; break;
     case UX_A_ROUTE_DIST: n = N * N; break;
     case UX_A_ROUTE_NEXT: n = N * N; dt = UX_DT_I32; break;
+    case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = (int64_t)w->dta.o.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_OD_OFFSETS: n = (int64_t)w->dta.od_off.size(); dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta.route_off.size(); dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_LINKS: n = (int64_t)w->dta.links.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
+    case UX_A_DTA_RS_LINKS: n = (int64_t)w->swap.rs_links.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_LINKS: n = (int64_t)w->swap.ra_links.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_ENTRY_T: n = (int64_t)w->swap.ra_entry_t.size(); break;
+    case UX_A_DTA_COST_ACTUAL: case UX_A_DTA_T_GAP: n = P; break;
+    case UX_A_DTA_CHOICE: n = P; dt = UX_DT_I32; break;
     default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
     }
     if (dtype) *dtype = dt;
@@ -2574,8 +2782,283 @@ UX_API int64_t ux_get_device_array(ux_world *w, int what, int replica, void **dp
     return n;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// DTA solver batch operations
+// ---------------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+// Forward shortest-path tree from `start` with the reference's conventions (World::route_search_all traffi.cpp:1317-1385):
+// neighbours in ascending node order, strict improvement, ties between queue entries broken by the smaller node id, the
+// first hop inherited from the parent.  Only the first-hop row is kept.
+struct FirstHopSearch {
+    std::vector<double> dist; std::vector<char> done;
+    std::priority_queue<std::pair<double, int>, std::vector<std::pair<double, int>>, std::greater<std::pair<double, int>>> pq;
+    void run(int N, int start, const std::vector<int> &off, const std::vector<int> &to, const std::vector<double> &wgt, int *hop) {
+        dist.assign(N, INFINITY); done.assign(N, 0);
+        for (int i = 0; i < N; i++) hop[i] = -1;
+        dist[start] = 0.0; hop[start] = start;
+        pq.push({0.0, start});
+        while (!pq.empty()) {
+            int cur = pq.top().second; pq.pop();
+            if (done[cur]) continue;
+            done[cur] = 1;
+            double dcur = dist[cur];
+            for (int q = off[cur]; q < off[cur + 1]; q++) {
+                if (!(wgt[q] > 0.0)) continue;
+                int nx = to[q];
+                double nd = dcur + wgt[q];
+                if (nd < dist[nx]) { dist[nx] = nd; hop[nx] = cur == start ? nx : hop[cur]; pq.push({nd, nx}); }
+            }
+        }
+    }
+};
+template <typename F>
+void parallel_for(int n, F body) {  // body(thread index, item)
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (n < 64) nt = 1;
+    std::atomic<int> next{0};
+    auto work = [&](int tid) { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) body(tid, i); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+}
+}  // namespace
+extern "C" {
+
+static void dta_store_changed(ux_world *w) { w->dta.on_device = false; w->swap.valid = false; }
+
+// World.enumerate_od_route_sets_ids_cpp (bindings.cpp:461-465) = World::enumerate_k_random_routes_cpp (traffi.cpp:1387-1481).
+// Host side (it runs once per solve): one shortest-path tree per source and round, sources spread over host threads.
+UX_API int64_t ux_dta_enumerate_route_sets(ux_world *w, int k, unsigned int seed) {
+    if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; }
+    int N = (int)w->nodes.size(), L = (int)w->links.size();
+    if ((long long)N * N > (1ll << 31)) return fail(w, UX_ERR_CAPACITY, "route enumeration keeps an N x N first-hop table; %d nodes is too many", N);
+    // node pairs in (from, to) order; a pair's weight and link id are those of its LAST link (traffi.cpp:1392-1395, 1412-1421)
+    std::map<std::pair<int, int>, int> pair_id;
+    for (int l = 0; l < L; l++) pair_id[{w->links[l].start, w->links[l].end}] = 0;
+    std::vector<int> off(N + 1, 0), to, pair_link;
+    { int q = 0; for (auto &kv : pair_id) { kv.second = q++; off[kv.first.first + 1]++; to.push_back(kv.first.second); } }
+    for (int i = 0; i < N; i++) off[i + 1] += off[i];
+    pair_link.assign(to.size(), -1);
+    std::vector<int> link_pair(L);
+    for (int l = 0; l < L; l++) { link_pair[l] = pair_id[{w->links[l].start, w->links[l].end}]; pair_link[link_pair[l]] = l; }
+    std::vector<double> wgt(to.size(), 0.0);
+    std::vector<int> hop((size_t)N * N);
+    std::vector<std::vector<std::vector<int>>> routes((size_t)N * N);  // [src*N+dst] -> routes
+    std::vector<char> present((size_t)N * N, 0);
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<double> rdist(0.0, 100.0);
+    int nt = 32;
+    std::vector<FirstHopSearch> searchers(nt);
+    std::vector<std::vector<int>> paths(nt);
+    int counter = 0, iteration = 0; double avg_old = 0.0;
+    while (true) {
+        for (int l = 0; l < L; l++) {
+            double base = w->links[l].length / w->links[l].vmax;
+            wgt[link_pair[l]] = iteration == 0 ? base : base * rdist(rng);
+        }
+        parallel_for(N, [&](int tid, int src) { searchers[tid].run(N, src, off, to, wgt, hop.data() + (size_t)src * N); });
+        std::vector<long long> tot_routes(N, 0), tot_pairs(N, 0);
+        parallel_for(N, [&](int tid, int src) {
+            std::vector<int> &path = paths[tid];
+            for (int dst = 0; dst < N; dst++) {
+                if (src == dst || hop[(size_t)src * N + dst] == -1) continue;
+                auto &rs = routes[(size_t)src * N + dst];
+                present[(size_t)src * N + dst] = 1;
+                tot_pairs[src]++; tot_routes[src] += (long long)rs.size();
+                if ((int)rs.size() >= k) continue;
+                path.clear();
+                int cur = src; bool valid = true;
+                while (cur != dst) {  // chain the first hops of the trees rooted at the nodes passed
+                    int nx = hop[(size_t)cur * N + dst];
+                    if (nx == -1 || nx == cur || (int)path.size() > N) { valid = false; break; }
+                    auto it = pair_id.find({cur, nx});
+                    if (it == pair_id.end()) { valid = false; break; }
+                    path.push_back(pair_link[it->second]);
+                    cur = nx;
+                }
+                if (!valid || path.empty()) continue;
+                if (std::find(rs.begin(), rs.end(), path) == rs.end()) rs.push_back(path);
+            }
+        });
+        long long total_routes = 0, total_pairs = 0;
+        for (int i = 0; i < N; i++) { total_routes += tot_routes[i]; total_pairs += tot_pairs[i]; }
+        double avg = total_pairs > 0 ? (double)total_routes / (double)total_pairs : 0.0;
+        if (avg == avg_old) counter++; else { counter = 0; avg_old = avg; }
+        iteration++;
+        if (counter > 10) break;
+    }
+    auto &S = w->dta;
+    S.o.clear(); S.d.clear(); S.links.clear(); S.od_off.assign(1, 0); S.route_off.assign(1, 0);
+    for (int src = 0; src < N; src++) for (int dst = 0; dst < N; dst++) {
+        if (!present[(size_t)src * N + dst]) continue;
+        S.o.push_back(src); S.d.push_back(dst);
+        for (auto &r : routes[(size_t)src * N + dst]) { S.links.insert(S.links.end(), r.begin(), r.end()); S.route_off.push_back((long long)S.links.size()); }
+        S.od_off.push_back((long long)S.route_off.size() - 1);
+    }
+    dta_store_changed(w);
+    return (int64_t)S.route_off.size() - 1;
+}
+
+// World.make_od_route_set_store (bindings.cpp:467-489)
+UX_API int ux_dta_set_route_sets(ux_world *w, int64_t n_od, const int *orig, const int *dest, const int64_t *od_off, const int64_t *route_off, const int *links) {
+    int N = (int)w->nodes.size(), L = (int)w->links.size();
+    for (int64_t p = 0; p < n_od; p++) {
+        if (orig[p] < 0 || orig[p] >= N || dest[p] < 0 || dest[p] >= N) return fail(w, UX_ERR_OUT_OF_RANGE, "route sets: node id out of range");
+        if (p > 0 && (orig[p] < orig[p - 1] || (orig[p] == orig[p - 1] && dest[p] <= dest[p - 1]))) return fail(w, UX_ERR_INVALID, "route sets must be sorted by (orig, dest) without duplicates");
+    }
+    int64_t n_routes = od_off[n_od], n_links = route_off[n_routes];
+    for (int64_t e = 0; e < n_links; e++) if (links[e] < 0 || links[e] >= L) return fail(w, UX_ERR_OUT_OF_RANGE, "route sets: link id out of range");
+    auto &S = w->dta;
+    S.o.assign(orig, orig + n_od); S.d.assign(dest, dest + n_od); S.links.assign(links, links + n_links);
+    S.od_off.assign(od_off, od_off + n_od + 1); S.route_off.assign(route_off, route_off + n_routes + 1);
+    dta_store_changed(w);
+    return 0;
+}
+
+// World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_solver.cpp:130-373)
+UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
+    if (!w->uploaded || w->timestep == 0) return fail(w, UX_ERR_RUNTIME, "dta_route_swap needs a finished run");
+    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    if (!w->record_traversals) return fail(w, UX_ERR_RUNTIME, "dta_route_swap needs UX_OPT_RECORD_TRAVERSALS set before the run");
+    if (mode != 0 && mode != 1) return fail(w, UX_ERR_INVALID, "mode must be 0 (DUE) or 1 (DSO)");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    const DevWorld &hw = w->hw[replica];
+    long long P = hw.P; int L = hw.L, T = hw.T;
+    auto &S = w->dta; auto &R = w->swap;
+    R.valid = false;
+    if (!S.on_device) {  // the store goes to the device once per solve
+        S.d_o = dupload(w, S.o); S.d_d = dupload(w, S.d); S.d_links = dupload(w, S.links); S.d_od_off = dupload(w, S.od_off); S.d_route_off = dupload(w, S.route_off);
+        if (!S.d_o || !S.d_d || !S.d_links || !S.d_od_off || !S.d_route_off) return fail(w, UX_ERR_CUDA, "device allocation failed (route sets)");
+        S.on_device = true;
+    }
+    // traversed routes: counts -> offsets (host scan) -> scatter of the entry events
+    std::vector<int> trav(P);
+    unsigned long long n_ev = 0;
+    if (P) CUDA_OK(cudaMemcpy(trav.data(), hw.v_trav, sizeof(int) * P, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(&n_ev, hw.tv_count, sizeof(n_ev), cudaMemcpyDeviceToHost));
+    R.ra_off.assign(P + 1, 0);
+    for (long long i = 0; i < P; i++) R.ra_off[i + 1] = R.ra_off[i] + trav[i];
+    if ((unsigned long long)R.ra_off[P] != n_ev) return fail(w, UX_ERR_RUNTIME, "traversal log bookkeeping mismatch: %lld expected, %llu recorded", R.ra_off[P], n_ev);
+    size_t ne = (size_t)n_ev, TL = (size_t)T * L;
+    size_t bytes = 0;
+    auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
+    size_t o_tt = carve(8 * TL), o_ext = carve(mode == 1 ? 8 * TL : 0), o_troff = carve(8 * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(P), o_pair = carve(4 * P),
+           o_draw = carve(P), o_ca = carve(8 * P), o_tg = carve(8 * P), o_ch = carve(4 * P), o_pot = carve(P);
+    char *buf = nullptr;
+    CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
+    auto release = [&](int rc) { cudaFree(buf); return rc; };
+    DtaDev D;
+    memset(&D, 0, sizeof(D));
+    double *d_tt = (double *)(buf + o_tt), *d_ext = (double *)(buf + o_ext);
+    D.tt = d_tt; D.ext = mode == 1 ? d_ext : nullptr;
+    D.od_o = S.d_o; D.od_d = S.d_d; D.route_links = S.d_links; D.od_off = S.d_od_off; D.route_off = S.d_route_off; D.n_od = (long long)S.o.size();
+    D.tr_off = (const long long *)(buf + o_troff); D.tr_link = (int *)(buf + o_trl); D.tr_t = (int *)(buf + o_trt);
+    D.mode = mode; D.has_external = has_external ? 1 : 0;
+    D.flag_swap = (const unsigned char *)(buf + o_fs); D.pair = (int *)(buf + o_pair); D.draws = (unsigned char *)(buf + o_draw);
+    D.cost_actual = (double *)(buf + o_ca); D.t_gap = (double *)(buf + o_tg); D.choice = (int *)(buf + o_ch); D.pot = (unsigned char *)(buf + o_pot);
+#ifndef UX_EMU
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
+#endif
+    cudaMemcpyAsync(buf + o_troff, R.ra_off.data(), 8 * (P + 1), cudaMemcpyHostToDevice, st);
+    if (ne) UX_LAUNCH(k_dta_scatter, dim3((unsigned)((ne + 255) / 256)), dim3(256), st, w->dworlds, replica, (long long)ne, D);
+    if (L > 0) UX_LAUNCH(k_tt_actual, dim3((L + 127) / 128), dim3(128), st, w->dworlds, replica, d_tt);
+    if (mode == 1 && TL) UX_LAUNCH(k_dta_externality, dim3((unsigned)((TL + 127) / 128)), dim3(128), st, w->dworlds, replica, (const double *)d_tt, d_ext);
+    if (P) UX_LAUNCH(k_dta_prepare, dim3((unsigned)((P + 127) / 128)), dim3(128), st, w->dworlds, replica, D);
+    // swap candidates: the reference's own stream, std::mt19937(rng_seed) + uniform_real_distribution (dta_solver.cpp:148-149, 265-283)
+    std::vector<unsigned char> draws(P), flag(P, 0);
+    if (P) { cudaMemcpyAsync(draws.data(), buf + o_draw, P, cudaMemcpyDeviceToHost, st); }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route-swap preparation: %s", cudaGetErrorString(cudaGetLastError())));
+    {
+        std::mt19937 rng(rng_seed);
+        std::uniform_real_distribution<double> udist(0.0, 1.0);
+        if (mode == 1 && swap_num >= 0) {
+            std::vector<int> idx(P);
+            for (long long i = 0; i < P; i++) idx[i] = (int)i;
+            std::shuffle(idx.begin(), idx.end(), rng);
+            long long m = std::min<long long>(swap_num, P);
+            for (long long i = 0; i < m; i++) flag[idx[i]] = 1;
+        } else if (mode == 1) { for (long long i = 0; i < P; i++) flag[i] = udist(rng) < swap_prob; }
+        else { for (long long i = 0; i < P; i++) if (draws[i]) flag[i] = udist(rng) < swap_prob; }
+    }
+    if (P) {
+        cudaMemcpyAsync(buf + o_fs, flag.data(), P, cudaMemcpyHostToDevice, st);
+        UX_LAUNCH(k_dta_swap, dim3((unsigned)((P + DTA_WARPS - 1) / DTA_WARPS)), dim3(32 * DTA_WARPS), st, w->dworlds, replica, D);
+    }
+#ifndef UX_EMU
+    cudaEventRecord(e1, st);
+#endif
+    R.choice.assign(P, -2); R.cost_actual.assign(P, 0.0); R.t_gap.assign(P, 0.0);
+    std::vector<unsigned char> pot(P, 0);
+    std::vector<int> tr_t(ne);
+    R.ra_links.assign(ne, 0);
+    if (P) {
+        cudaMemcpyAsync(R.choice.data(), buf + o_ch, 4 * P, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(R.cost_actual.data(), buf + o_ca, 8 * P, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(R.t_gap.data(), buf + o_tg, 8 * P, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(pot.data(), buf + o_pot, P, cudaMemcpyDeviceToHost, st);
+    }
+    if (ne) { cudaMemcpyAsync(R.ra_links.data(), buf + o_trl, 4 * ne, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(tr_t.data(), buf + o_trt, 4 * ne, cudaMemcpyDeviceToHost, st); }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route swap: %s", cudaGetErrorString(cudaGetLastError())));
+#ifndef UX_EMU
+    { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); R.ms = ms; cudaEventDestroy(e0); cudaEventDestroy(e1); }
+#endif
+    w->d2h_bytes += (long long)(P * (4 + 8 + 8 + 1 + 1 + 4) + ne * 8);
+    w->h2d_bytes += (long long)(P * 9 + 8);
+    R.ra_entry_t.resize(ne);
+    for (size_t i = 0; i < ne; i++) R.ra_entry_t[i] = (double)tr_t[i] * w->dt;
+    // totals in platoon order (sequential sums of dta_solver.cpp:243-252) and the next iteration's routes
+    R.n_swap = 0; R.potential_n_swap = 0; R.total_t_gap = 0;
+    R.rs_off.assign(P + 1, 0);
+    for (long long i = 0; i < P; i++) {
+        int c = R.choice[i];
+        if (pot[i]) R.potential_n_swap += w->p.delta_n;
+        R.total_t_gap += R.t_gap[i];
+        if (c >= 0 && pot[i]) R.n_swap += w->p.delta_n;  // a forced external route has pot == 0
+        long long len = c == -2 ? 0 : c == -1 ? R.ra_off[i + 1] - R.ra_off[i] : S.route_off[c + 1] - S.route_off[c];
+        R.rs_off[i + 1] = R.rs_off[i] + len;
+    }
+    R.rs_links.resize((size_t)R.rs_off[P]);
+    for (long long i = 0; i < P; i++) {
+        int c = R.choice[i]; long long len = R.rs_off[i + 1] - R.rs_off[i];
+        if (len > 0) memcpy(R.rs_links.data() + R.rs_off[i], c == -1 ? R.ra_links.data() + R.ra_off[i] : S.links.data() + S.route_off[c], sizeof(int) * (size_t)len);
+    }
+    R.replica = replica; R.valid = true;
+    return release(0);
+}
+
+static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    int dt; int64_t n = ux_array_size(w, what, &dt);
+    if (n < 0) return n;
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    const void *src = nullptr;
+    if (what >= UX_A_DTA_RS_OFFSETS) {
+        if (!w->swap.valid || w->swap.replica != replica) return fail(w, UX_ERR_RUNTIME, "no route swap result for replica %d", replica);
+        auto &r = w->swap;
+        src = what == UX_A_DTA_RS_OFFSETS ? (const void *)r.rs_off.data() : what == UX_A_DTA_RA_OFFSETS ? (const void *)r.ra_off.data() : what == UX_A_DTA_RS_LINKS ? (const void *)r.rs_links.data()
+            : what == UX_A_DTA_RA_LINKS ? (const void *)r.ra_links.data() : what == UX_A_DTA_RA_ENTRY_T ? (const void *)r.ra_entry_t.data() : what == UX_A_DTA_COST_ACTUAL ? (const void *)r.cost_actual.data()
+            : what == UX_A_DTA_T_GAP ? (const void *)r.t_gap.data() : (const void *)r.choice.data();
+    } else {
+        auto &d = w->dta;
+        src = what == UX_A_DTA_OD_ORIG ? (const void *)d.o.data() : what == UX_A_DTA_OD_DEST ? (const void *)d.d.data() : what == UX_A_DTA_OD_OFFSETS ? (const void *)d.od_off.data()
+            : what == UX_A_DTA_ROUTE_OFFSETS ? (const void *)d.route_off.data() : (const void *)d.links.data();
+    }
+    if (n > 0) memcpy(dst, src, (dt == UX_DT_I32 ? 4 : 8) * (size_t)n);
+    return n;
+}
+
 UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
     if (is_log_array(what)) return get_log_array(w, what, replica, dst, capacity, nullptr, false);
+    if (what >= UX_A_DTA_OD_ORIG && what <= UX_A_DTA_RA_ENTRY_T) return get_dta_array(w, what, replica, dst, capacity);
+    if (what == UX_A_VEH_ORIG || what == UX_A_VEH_DEST || what == UX_A_VEH_DEPART_TS) {  // static: answered from the host copy (no upload forced)
+        int64_t P = (int64_t)w->vehs.size();
+        if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+        if (capacity < P) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)P);
+        int *oi = (int *)dst;
+        for (int64_t i = 0; i < P; i++) oi[i] = what == UX_A_VEH_ORIG ? w->vehs[i].orig : what == UX_A_VEH_DEST ? w->vehs[i].dest : w->vehs[i].ts;
+        return P;
+    }
     void *dptr = nullptr; int dt = 0;
     int64_t n = device_array(w, what, replica, &dptr, &dt);
     if (n < 0) return n;

@@ -1,0 +1,75 @@
+"""Day-to-day DUE / DSO solvers over the engine (uxsim_b200/dta.py; counterparts of CppSolverDUE / CppSolverDSO_D2D).
+
+The solver logic is exercised on CPU with the host-emulation build standing in for the GPU library (test-only
+monkeypatch), and on the GPU with the real library."""
+import random
+
+import numpy as np
+import pytest
+
+from uxsim_b200 import _capi as C
+from uxsim_b200 import scenario as S
+from uxsim_b200.dta import CudaSolverDSO_D2D, CudaSolverDUE, SolverDUE
+
+
+def _solve(cls, max_iter=6, **kw):
+    random.seed(1)
+    sol = cls(lambda: S.dta_grid9().to_world(print_mode=0, vehicle_logging_timestep_interval=-1))
+    W = sol.solve(max_iter=max_iter, n_routes_per_od=6, swap_prob=0.2, print_progress=False, **kw)
+    return sol, W
+
+
+def _check_due(sol, W):
+    assert len(sol.ttts) == len(sol.t_gaps) == len(sol.route_log) == 6
+    assert sol.t_gaps[-1] < 0.7 * sol.t_gaps[0]          # the route cost gap closes
+    assert all(n > 0 for n in sol.n_swaps) and all(p >= n for p, n in zip(sol.potential_swaps, sol.n_swaps))
+    assert W is sol.W_sol and W.analyzer.trip_completed == W.analyzer.trip_all
+    r = sol.route_log[-1]
+    name, links = next(iter(r.items()))
+    assert len(r) == len(W.VEHICLES) and all(l in W.LINKS_NAME_DICT for l in links)
+    assert (W.get_node("n(0, 3)").name, W.get_node("n(8, 3)").name) in W.dict_od_to_routes or len(W.dict_od_to_routes) > 0
+
+
+def _check_dso(sol, W):
+    assert min(sol.ttts) < 0.9 * sol.ttts[0]              # total travel time falls towards the system optimum
+    assert W is sol.W_sol and W.analyzer.total_travel_time == min(sol.ttts) or W.analyzer.trip_completed == W.analyzer.trip_all
+
+
+@pytest.fixture
+def emu_as_product(emu_api, monkeypatch):
+    monkeypatch.setattr(C, "_product", emu_api)
+    return emu_api
+
+
+def test_due_solver_emulated(emu_as_product):
+    _check_due(*_solve(CudaSolverDUE))
+
+
+def test_dso_solver_emulated(emu_as_product):
+    _check_dso(*_solve(CudaSolverDSO_D2D))
+
+
+def test_solver_with_external_route_sets_emulated(emu_as_product):
+    W0 = S.dta_grid9().to_world(print_mode=0, vehicle_logging_timestep_interval=-1)
+    W0.finalize_scenario()
+    W0._E.dta_enumerate_route_sets(3, 5)
+    o, d, od_off, r_off, links = W0._E.dta_route_sets_csr()
+    route_sets = {(W0.NODES[o[p]].name, W0.NODES[d[p]].name): [[W0.LINKS[i].name for i in links[r_off[r]:r_off[r + 1]]] for r in range(od_off[p], od_off[p + 1])]
+                  for p in range(len(o)) if od_off[p + 1] > od_off[p]}
+    sol, W = _solve(CudaSolverDUE, max_iter=3, route_sets=route_sets)
+    assert len(sol.ttts) == 3 and sol.potential_swaps[0] > 0
+
+
+def test_solver_rejects_foreign_worlds():
+    with pytest.raises(ValueError, match="cuda=True"):
+        SolverDUE(lambda: object()).solve(max_iter=1)
+
+
+@pytest.mark.gpu
+def test_due_solver_gpu(cuda_api):
+    _check_due(*_solve(CudaSolverDUE))
+
+
+@pytest.mark.gpu
+def test_dso_solver_gpu(cuda_api):
+    _check_dso(*_solve(CudaSolverDSO_D2D))

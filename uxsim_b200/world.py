@@ -769,7 +769,7 @@ class CudaWorld:
     def simulation_terminated(self):
         self.print(" simulation finished")
         self._simulation_done = True
-        if self.vehicle_logging_timestep_interval > 0:
+        if self.vehicle_logging_timestep_interval > 0 and not getattr(self, "_skip_log_on_terminate", False):
             self._build_vehicles_enter_log()
         self.analyzer.basic_analysis()
 

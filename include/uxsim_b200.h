@@ -320,6 +320,14 @@ UX_API int64_t UX_FN(dta_enumerate_route_sets)(ux_world *w, int k, unsigned int 
 /* World.make_od_route_set_store (bindings.cpp:467-489): an external store in CSR form. */
 UX_API int UX_FN(dta_set_route_sets)(ux_world *w, int64_t n_od, const int *orig, const int *dest, const int64_t *od_offsets,
                                      const int64_t *route_offsets, const int *route_links);
+/* The reference keeps ONE ODRouteSetStore object for a whole solve and hands it to every day's world
+ * (DTAsolvers_cpp_adapter.py:280-291, 330): share `from`'s store with `w` without copying it (in the CUDA build the device
+ * image is uploaded once per solve). */
+UX_API int UX_FN(dta_share_route_sets)(ux_world *w, ux_world *from);
+/* Enforced routes of ONE replica, CSR as in batch_enforce_routes_csr (the CPU engines have a single replica: replica must
+ * be 0 and the call is batch_enforce_routes_csr).  A replica-batched day-to-day solve runs one independent chain of
+ * route sets per replica.  Before the first main_loop. */
+UX_API int UX_FN(dta_enforce_routes)(ux_world *w, int replica, const int *link_ids, const int64_t *offsets, int64_t n_vehicles);
 /* World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_route_swap_due / _dso dta_solver.cpp:130-373) on the
  * finished run of `replica`.  mode 0 = DUE (travel time + tolls), 1 = DSO (travel time + congestion externality,
  * Link::estimate_congestion_externality traffi.cpp:650-689); swap_num < 0 = probabilistic candidates (swap_prob),

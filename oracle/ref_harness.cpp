@@ -461,6 +461,15 @@ UX_API int uxr_dta_set_route_sets(ux_world *w, int64_t n_od, const int *orig, co
     return 0;
     UXR_CATCH(w)
 }
+UX_API int uxr_dta_share_route_sets(ux_world *w, ux_world *from) {
+    if (!from) return fail(w, UX_ERR_INVALID, "dta_share_route_sets: no source world");
+    if (from != w) { w->store = from->store; w->od_keys = from->od_keys; }
+    return 0;
+}
+UX_API int uxr_dta_enforce_routes(ux_world *w, int replica, const int *ids, const int64_t *off, int64_t nveh) {
+    if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "reference harness has a single replica");
+    return uxr_batch_enforce_routes_csr(w, ids, off, nveh);
+}
 // route_swap_due / route_swap_dso bindings.cpp:661-706
 UX_API int uxr_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
     UXR_TRY

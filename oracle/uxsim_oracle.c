@@ -1335,6 +1335,17 @@ UX_API int uxo_dta_set_route_sets(ux_world *w, int64_t n_od, const int *orig, co
     return 0;
 }
 
+UX_API int uxo_dta_share_route_sets(ux_world *w, ux_world *from) {
+    if (!from) return fail(w, UX_ERR_INVALID, "dta_share_route_sets: no source world");
+    if (from == w) return 0;
+    if (!from->dta_od_off) { dta_store_free(w); return 0; }
+    return uxo_dta_set_route_sets(w, from->dta_n_od, from->dta_o, from->dta_d, from->dta_od_off, from->dta_route_off, from->dta_links);
+}
+UX_API int uxo_dta_enforce_routes(ux_world *w, int replica, const int *ids, const int64_t *off, int64_t nveh) {
+    if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "oracle has a single replica");
+    return uxo_batch_enforce_routes_csr(w, ids, off, nveh);
+}
+
 /* dta_get_toll / dta_get_actual_travel_time dta_solver.h:44-65 */
 static double dta_toll(const ux_world *w, const OLink *ln, double t) {
     if (ln->ntoll > 0) { int ts = (int)(t / w->delta_t); if (ts < 0) ts = 0; if (ts >= ln->ntoll) ts = ln->ntoll - 1; return ln->toll[ts]; }

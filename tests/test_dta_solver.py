@@ -65,6 +65,30 @@ def test_solver_rejects_foreign_worlds():
         SolverDUE(lambda: object()).solve(max_iter=1)
 
 
+def _check_ensemble(api):
+    from uxsim_b200.dta import DayToDayEnsemble
+
+    sc = S.dta_grid9()
+    ens = DayToDayEnsemble(sc, 3, mode="DUE", base_seed=10, api=api)
+    ens.solve(max_iter=4, n_routes_per_od=6, swap_prob=0.2)
+    assert ens.ttts.shape == (3, 4) and (ens.trips > 0).all()
+    assert (ens.t_gaps[:, -1] < ens.t_gaps[:, 0]).all()          # every chain closes its gap
+    assert len({tuple(ens.ttts[r]) for r in range(3)}) == 3       # chains are independent (different seeds, different routes)
+    # chain r of the ensemble == a single-replica solve with seed base_seed + r (same swap seeds)
+    solo = DayToDayEnsemble(sc, 1, mode="DUE", base_seed=10 + 1, api=api)
+    solo.solve(max_iter=2, n_routes_per_od=6, swap_prob=0.2)
+    assert solo.ttts[0, 0] == ens.ttts[1, 0] and solo.n_swaps[0, 0] != 0
+
+
+def test_day_to_day_ensemble_emulated(emu_api):
+    _check_ensemble(emu_api)
+
+
+@pytest.mark.gpu
+def test_day_to_day_ensemble_gpu(cuda_api):
+    _check_ensemble(cuda_api)
+
+
 @pytest.mark.gpu
 def test_due_solver_gpu(cuda_api):
     _check_due(*_solve(CudaSolverDUE))

@@ -72,7 +72,8 @@ ABI_SYMBOLS = (
     "batch_enforce_routes_csr", "set_t_max", "set_toll_timeseries", "initialize_adj_matrix", "main_loop",
     "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
     "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
-    "ensemble_link_stats", "last_error", "dta_enumerate_route_sets", "dta_set_route_sets", "dta_route_swap",
+    "ensemble_link_stats", "last_error", "dta_enumerate_route_sets", "dta_set_route_sets", "dta_share_route_sets",
+    "dta_enforce_routes", "dta_route_swap",
 )
 
 
@@ -162,6 +163,8 @@ class CApi:
         # DTA solver batch operations
         self.dta_enumerate_route_sets = fn("dta_enumerate_route_sets", C.c_int64, [p, C.c_int, C.c_uint])
         self.dta_set_route_sets = fn("dta_set_route_sets", C.c_int, [p, C.c_int64, i32p, i32p, i64p, i64p, i32p])
+        self.dta_share_route_sets = fn("dta_share_route_sets", C.c_int, [p, p])
+        self.dta_enforce_routes = fn("dta_enforce_routes", C.c_int, [p, C.c_int, i32p, i64p, C.c_int64])
         self.dta_route_swap = fn("dta_route_swap", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint])
 
     def exported(self, name: str) -> bool:
@@ -309,6 +312,15 @@ class EngineWorld:
         ip, lp = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         self._check(self.api.dta_set_route_sets(self.h, len(o), o.ctypes.data_as(ip), d.ctypes.data_as(ip), oo.ctypes.data_as(lp),
                                                 ro.ctypes.data_as(lp), rl.ctypes.data_as(ip)))
+
+    def dta_share_route_sets(self, other: "EngineWorld"):
+        """Use ``other``'s route-set store (one store per solve, as the reference's ODRouteSetStore object)."""
+        self._check(self.api.dta_share_route_sets(self.h, other.h))
+
+    def dta_enforce_routes(self, replica: int, link_ids, offsets):
+        ids, off = _as_i32(link_ids), np.ascontiguousarray(offsets, dtype=np.int64)
+        self._check(self.api.dta_enforce_routes(self.h, int(replica), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1))
 
     def dta_route_sets_csr(self):
         """ODRouteSetStore.to_csr: (orig, dest, od_offsets, route_offsets, route_links), pairs sorted by (orig, dest)."""

@@ -36,6 +36,7 @@
 #include <queue>
 #include <thread>
 #include <atomic>
+#include <memory>
 
 #include "../../include/uxsim_b200.h"
 #include "../../include/ux_rng.h"
@@ -1580,6 +1581,15 @@ struct HLink {
 struct HVeh { int orig, dest, ts; };
 struct Slab { char *base; size_t size, used; };
 
+// OD route-set store of the DTA solvers (pairs sorted by (orig, dest)) with its device copy.  One store serves every day of
+// a solve, so worlds share it by reference; the device copy lives as long as any world does.
+struct DtaStore {
+    std::vector<int> o, d, links; std::vector<long long> od_off{0}, route_off{0};
+    int device = -1; void *d_block = nullptr;
+    int *d_o = nullptr, *d_d = nullptr, *d_links = nullptr; long long *d_od_off = nullptr, *d_route_off = nullptr;
+    ~DtaStore() { if (d_block) { cudaSetDevice(device); cudaFree(d_block); } }
+};
+
 struct ux_world {
     ux_world_params p;
     double dt; int total_ts, route_ts, timestep; int R;
@@ -1617,10 +1627,8 @@ struct ux_world {
     } logs;
     // DTA solver: OD route-set store (pairs sorted by (orig, dest)), its device copy, and the last route-swap result
     bool record_traversals = false;
-    struct DtaStore {
-        std::vector<int> o, d, links; std::vector<long long> od_off{0}, route_off{0};
-        int *d_o = nullptr, *d_d = nullptr, *d_links = nullptr; long long *d_od_off = nullptr, *d_route_off = nullptr; bool on_device = false;
-    } dta;
+    std::map<int, std::pair<std::vector<int>, std::vector<int>>> rep_routes;  // replica -> (offsets [P+1], link ids): per-replica enforced routes
+    std::shared_ptr<DtaStore> dta_p = std::make_shared<DtaStore>();  // shared between the worlds of one solve (ux_dta_share_route_sets)
     struct DtaResult {
         bool valid = false; int replica = 0;
         std::vector<long long> rs_off, ra_off; std::vector<int> rs_links, ra_links, choice; std::vector<double> ra_entry_t, cost_actual, t_gap;
@@ -1882,6 +1890,23 @@ UX_API int ux_set_vehicle_links(ux_world *w, int64_t vid, int kind, const int *l
 UX_API int ux_batch_enforce_routes_csr(ux_world *w, const int *ids, const int64_t *off, int64_t nveh) {
     if (nveh > (int64_t)w->vehs.size()) nveh = (int64_t)w->vehs.size();
     for (int64_t i = 0; i < nveh; i++) if (off[i + 1] > off[i]) { int rc = ux_set_vehicle_links(w, i, 0, ids + off[i], (int)(off[i + 1] - off[i])); if (rc) return rc; }
+    return 0;
+}
+
+// Enforced routes of ONE replica (the day-to-day solvers run one independent chain per replica): same CSR as
+// batch_enforce_routes_csr; for that replica it replaces the world-wide specified_route / links_preferred lists.
+UX_API int ux_dta_enforce_routes(ux_world *w, int replica, const int *ids, const int64_t *off, int64_t nveh) {
+    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "dta_enforce_routes after the simulation started is not supported");
+    int64_t P = (int64_t)w->vehs.size();
+    if (nveh > P) nveh = P;
+    if (nveh > 0 && off[nveh] > 0x7fffffff) return fail(w, UX_ERR_CAPACITY, "dta_enforce_routes: more than 2^31 route entries");
+    for (int64_t e = 0; e < (nveh > 0 ? off[nveh] : 0); e++) if (ids[e] < 0 || ids[e] >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    auto &rr = w->rep_routes[replica];
+    rr.first.assign(P + 1, 0);
+    for (int64_t i = 0; i < nveh; i++) rr.first[i + 1] = (int)off[i + 1];
+    for (int64_t i = nveh; i < P; i++) rr.first[i + 1] = rr.first[nveh];
+    rr.second.assign(ids, ids + (nveh > 0 ? off[nveh] : 0));
     return 0;
 }
 
@@ -2157,6 +2182,10 @@ static int upload(ux_world *w) {
     for (int r = 0; r < w->R; r++) {
         DevWorld &d = w->hw[r];
         d.seed = w->p.random_seed + r;
+        {   // per-replica enforced routes (ux_dta_enforce_routes): specified_route and links_preferred of this replica
+            auto it = w->rep_routes.find(r);
+            if (it != w->rep_routes.end()) { const int *o_ = dupload(w, it->second.first), *l_ = dupload(w, it->second.second); d.vl_off[0] = d.vl_off[1] = o_; d.vl_list[0] = d.vl_list[1] = l_; }
+        }
         d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L);
         d.trips = dalloc<int>(w, L); d.ev_cnt = dalloc<int>(w, L); d.stat_count = dalloc<long long>(w, L);
         d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem);
@@ -2255,6 +2284,7 @@ static int extend_vehicles(ux_world *w) {
     cudaSetDevice(w->device);
     int N = (int)w->nodes.size(), T = w->total_ts, start_ts = w->timestep;
     long long P0 = w->P_uploaded, P = (long long)w->vehs.size();
+    if (!w->rep_routes.empty()) return fail(w, UX_ERR_RUNTIME, "adding vehicles to a world with per-replica routes is not supported");
     for (long long i = P0; i < P; i++) if (w->dest_row[w->vehs[i].dest] < 0)
         return fail(w, UX_ERR_RUNTIME, "vehicle %lld added after the start has destination node %d, which had no demand before: set UX_OPT_ALL_DESTINATIONS "
                     "(World(..., all_destinations=True)) before the first exec_simulation", i, w->vehs[i].dest);
@@ -2695,10 +2725,10 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_ROUTE_PREF: n = N * L; break;
     case UX_A_ROUTE_DIST: n = N * N; break;
     case UX_A_ROUTE_NEXT: n = N * N; dt = UX_DT_I32; break;
-    case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = (int64_t)w->dta.o.size(); dt = UX_DT_I32; break;
-    case UX_A_DTA_OD_OFFSETS: n = (int64_t)w->dta.od_off.size(); dt = UX_DT_I64; break;
-    case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta.route_off.size(); dt = UX_DT_I64; break;
-    case UX_A_DTA_ROUTE_LINKS: n = (int64_t)w->dta.links.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = (int64_t)w->dta_p->o.size(); dt = UX_DT_I32; break;
+    case UX_A_DTA_OD_OFFSETS: n = (int64_t)w->dta_p->od_off.size(); dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta_p->route_off.size(); dt = UX_DT_I64; break;
+    case UX_A_DTA_ROUTE_LINKS: n = (int64_t)w->dta_p->links.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
     case UX_A_DTA_RS_LINKS: n = (int64_t)w->swap.rs_links.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_RA_LINKS: n = (int64_t)w->swap.ra_links.size(); dt = UX_DT_I32; break;
@@ -2827,7 +2857,7 @@ void parallel_for(int n, F body) {  // body(thread index, item)
 }  // namespace
 extern "C" {
 
-static void dta_store_changed(ux_world *w) { w->dta.on_device = false; w->swap.valid = false; }
+static DtaStore &dta_new_store(ux_world *w) { w->dta_p = std::make_shared<DtaStore>(); w->swap.valid = false; return *w->dta_p; }
 
 // World.enumerate_od_route_sets_ids_cpp (bindings.cpp:461-465) = World::enumerate_k_random_routes_cpp (traffi.cpp:1387-1481).
 // Host side (it runs once per solve): one shortest-path tree per source and round, sources spread over host threads.
@@ -2890,15 +2920,13 @@ UX_API int64_t ux_dta_enumerate_route_sets(ux_world *w, int k, unsigned int seed
         iteration++;
         if (counter > 10) break;
     }
-    auto &S = w->dta;
-    S.o.clear(); S.d.clear(); S.links.clear(); S.od_off.assign(1, 0); S.route_off.assign(1, 0);
+    DtaStore &S = dta_new_store(w);
     for (int src = 0; src < N; src++) for (int dst = 0; dst < N; dst++) {
         if (!present[(size_t)src * N + dst]) continue;
         S.o.push_back(src); S.d.push_back(dst);
         for (auto &r : routes[(size_t)src * N + dst]) { S.links.insert(S.links.end(), r.begin(), r.end()); S.route_off.push_back((long long)S.links.size()); }
         S.od_off.push_back((long long)S.route_off.size() - 1);
     }
-    dta_store_changed(w);
     return (int64_t)S.route_off.size() - 1;
 }
 
@@ -2911,10 +2939,18 @@ UX_API int ux_dta_set_route_sets(ux_world *w, int64_t n_od, const int *orig, con
     }
     int64_t n_routes = od_off[n_od], n_links = route_off[n_routes];
     for (int64_t e = 0; e < n_links; e++) if (links[e] < 0 || links[e] >= L) return fail(w, UX_ERR_OUT_OF_RANGE, "route sets: link id out of range");
-    auto &S = w->dta;
+    DtaStore &S = dta_new_store(w);
     S.o.assign(orig, orig + n_od); S.d.assign(dest, dest + n_od); S.links.assign(links, links + n_links);
     S.od_off.assign(od_off, od_off + n_od + 1); S.route_off.assign(route_off, route_off + n_routes + 1);
-    dta_store_changed(w);
+    return 0;
+}
+
+// Share `from`'s store with `w` (no copy; the device image is uploaded once per solve, not once per day)
+UX_API int ux_dta_share_route_sets(ux_world *w, ux_world *from) {
+    if (!from) return fail(w, UX_ERR_INVALID, "dta_share_route_sets: no source world");
+    if (from->nodes.size() != w->nodes.size() || from->links.size() != w->links.size()) return fail(w, UX_ERR_INVALID, "dta_share_route_sets: the worlds have different networks");
+    w->dta_p = from->dta_p;
+    w->swap.valid = false;
     return 0;
 }
 
@@ -2928,12 +2964,22 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     cudaStream_t st = w->stream;
     const DevWorld &hw = w->hw[replica];
     long long P = hw.P; int L = hw.L, T = hw.T;
-    auto &S = w->dta; auto &R = w->swap;
+    DtaStore &S = *w->dta_p; auto &R = w->swap;
     R.valid = false;
-    if (!S.on_device) {  // the store goes to the device once per solve
-        S.d_o = dupload(w, S.o); S.d_d = dupload(w, S.d); S.d_links = dupload(w, S.links); S.d_od_off = dupload(w, S.od_off); S.d_route_off = dupload(w, S.route_off);
-        if (!S.d_o || !S.d_d || !S.d_links || !S.d_od_off || !S.d_route_off) return fail(w, UX_ERR_CUDA, "device allocation failed (route sets)");
-        S.on_device = true;
+    if (!S.d_block || S.device != w->device) {  // the store goes to the device once per solve
+        if (S.d_block) { cudaSetDevice(S.device); cudaFree(S.d_block); S.d_block = nullptr; cudaSetDevice(w->device); }
+        size_t b0 = (4 * S.o.size() + 255) & ~(size_t)255, b1 = (4 * S.links.size() + 255) & ~(size_t)255, b2 = (8 * S.od_off.size() + 255) & ~(size_t)255,
+               b3 = (8 * S.route_off.size() + 255) & ~(size_t)255;
+        CUDA_OK(cudaMalloc(&S.d_block, 2 * b0 + b1 + b2 + b3 + 256));
+        char *b = (char *)S.d_block;
+        S.device = w->device;
+        S.d_o = (int *)b; S.d_d = (int *)(b + b0); S.d_links = (int *)(b + 2 * b0); S.d_od_off = (long long *)(b + 2 * b0 + b1); S.d_route_off = (long long *)(b + 2 * b0 + b1 + b2);
+        cudaMemcpyAsync(S.d_o, S.o.data(), 4 * S.o.size(), cudaMemcpyHostToDevice, st); cudaMemcpyAsync(S.d_d, S.d.data(), 4 * S.d.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(S.d_links, S.links.data(), 4 * S.links.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(S.d_od_off, S.od_off.data(), 8 * S.od_off.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(S.d_route_off, S.route_off.data(), 8 * S.route_off.size(), cudaMemcpyHostToDevice, st);
+        CUDA_OK(cudaStreamSynchronize(st));
+        w->h2d_bytes += (long long)(8 * S.o.size() + 4 * S.links.size() + 8 * (S.od_off.size() + S.route_off.size()));
     }
     // traversed routes: counts -> offsets (host scan) -> scatter of the entry events
     std::vector<int> trav(P);
@@ -3040,7 +3086,7 @@ static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int6
             : what == UX_A_DTA_RA_LINKS ? (const void *)r.ra_links.data() : what == UX_A_DTA_RA_ENTRY_T ? (const void *)r.ra_entry_t.data() : what == UX_A_DTA_COST_ACTUAL ? (const void *)r.cost_actual.data()
             : what == UX_A_DTA_T_GAP ? (const void *)r.t_gap.data() : (const void *)r.choice.data();
     } else {
-        auto &d = w->dta;
+        DtaStore &d = *w->dta_p;
         src = what == UX_A_DTA_OD_ORIG ? (const void *)d.o.data() : what == UX_A_DTA_OD_DEST ? (const void *)d.d.data() : what == UX_A_DTA_OD_OFFSETS ? (const void *)d.od_off.data()
             : what == UX_A_DTA_ROUTE_OFFSETS ? (const void *)d.route_off.data() : (const void *)d.links.data();
     }

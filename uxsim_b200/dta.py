@@ -137,10 +137,10 @@ class _CudaSolverBase:
         # same global-RNG consumption order as the reference solvers (one draw for the enumeration, one per day)
         enum_seed = random.randint(0, 2**31 - 1)
         if route_sets is not None:
-            store = _route_sets_to_csr(W_orig, route_sets)
+            W_orig._E.dta_set_route_sets(*_route_sets_to_csr(W_orig, route_sets))
         else:
             W_orig._E.dta_enumerate_route_sets(n_routes_per_od, enum_seed)
-            store = W_orig._E.dta_route_sets_csr()
+        store = W_orig._E.dta_route_sets_csr()  # W_orig keeps the one store of this solve; every day's world shares it
         dict_od_to_routes = _LazyODRoutes(store, node_names, link_names)
         if print_progress:
             print(f"number of OD pairs: {len(store[0])}, number of routes: {len(store[3]) - 1}")
@@ -157,7 +157,7 @@ class _CudaSolverBase:
                 W.finalize_scenario()
             E = W._E
             E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
-            E.dta_set_route_sets(*store)
+            E.dta_share_route_sets(W_orig._E)
             if prev_rs is not None:
                 E.batch_enforce_routes_csr(*prev_rs)
             t0 = time.perf_counter()
@@ -247,3 +247,59 @@ def SolverDSO_D2D(func_World, cuda=True, **kwargs):
     if not cuda:
         raise NotImplementedError("uxsim_b200 only provides the CUDA solvers; use the reference package for the Python / C++ ones.")
     return CudaSolverDSO_D2D(func_World, **kwargs)
+
+
+class DayToDayEnsemble:
+    """R independent day-to-day chains advanced together (seeded replicas of a DUE / DSO solve).
+
+    Every day is ONE world with R replicas (replica r = seed ``base_seed + r`` with its own enforced routes): one
+    ``main_loop`` simulates all chains' day, then each chain swaps routes on its own finished run.  Works on the arrays of a
+    :class:`uxsim_b200.scenario.Scenario` (no per-vehicle Python objects).  Ranks of a ``torch.distributed`` job give each
+    rank its own block of chains (``uxsim_b200.ensemble.shard_seeds``); there is no exchange between chains.
+    """
+
+    def __init__(self, scenario, n_replicas, mode="DUE", base_seed=0, device=-1, api=None, **world_over):
+        self.scenario, self.R, self.mode = scenario, int(n_replicas), {"DUE": 0, "DSO": 1}[mode]
+        self.base_seed, self.device, self.api, self.world_over = int(base_seed), device, api or C.load_product(), world_over
+        self.ttts = self.n_swaps = self.potential_swaps = self.t_gaps = self.trips = None
+        self.day_seconds = []      # per day: (build + enforce, simulation, route swaps) wall seconds
+        self.routes = None         # per chain: (link ids, offsets) enforced on the next day
+
+    def solve(self, max_iter, n_routes_per_od=10, swap_prob=0.05, enum_seed=12345, swap_seed=0, keep_last_world=False):
+        sc, api, R = self.scenario, self.api, self.R
+        tab = sc.tables()
+        E0 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, device=self.device, **self.world_over)
+        E0.dta_enumerate_route_sets(n_routes_per_od, enum_seed)
+        dn = sc.deltan
+        shape = (R, max_iter)
+        self.ttts, self.n_swaps, self.potential_swaps, self.t_gaps, self.trips = (np.zeros(shape) for _ in range(5))
+        prev = [None] * R
+        E = None
+        for day in range(max_iter):
+            t0 = time.perf_counter()
+            E = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, device=self.device,
+                                      random_seed=self.base_seed, **self.world_over)
+            E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
+            E.dta_share_route_sets(E0)
+            for r in range(R):
+                if prev[r] is not None:
+                    E.dta_enforce_routes(r, *prev[r])
+            t1 = time.perf_counter()
+            E.main_loop()
+            t2 = time.perf_counter()
+            for r in range(R):
+                res = E.dta_route_swap(self.mode, swap_prob, (swap_seed * 1000003 + day * 65537 + r) & 0x7FFFFFFF, replica=r)
+                prev[r] = (res["rs_link_ids"], res["rs_offsets"])
+                tt = E.get_array(C.A_VEH_TRAVEL_TIME, r)
+                done = tt >= 0
+                self.ttts[r, day] = float(tt[done].sum()) * dn
+                self.trips[r, day] = int(done.sum()) * dn
+                self.n_swaps[r, day], self.potential_swaps[r, day] = res["n_swap"], res["potential_n_swap"]
+                self.t_gaps[r, day] = res["total_t_gap"] / max(1, len(tt))
+            t3 = time.perf_counter()
+            self.day_seconds.append((t1 - t0, t2 - t1, t3 - t2))
+            if day != max_iter - 1 or not keep_last_world:
+                E.close()
+        self.routes = prev
+        E0.close()
+        return E if keep_last_world else None

@@ -211,6 +211,7 @@ enum {
     UX_D_DTA_POTENTIAL_N_SWAP = 11,
     UX_D_DTA_TOTAL_T_GAP = 12,
     UX_D_DTA_SWAP_MS = 13,      /* device time of the last dta_route_swap's kernels (product only) */
+    UX_D_DTA_N_SWAP_OF = 1000,  /* + replica: n_swap of that replica after a batched dta_route_swap (replica == -1); +1000: potential_n_swap; +2000: total_t_gap */
     UX_D_KERNEL_MS_OF = 100     /* + kernel id: summed device time of that kernel in timing mode [ms] */
 };
 /* engine options (product only; the test libraries accept and ignore them) */
@@ -331,7 +332,9 @@ UX_API int UX_FN(dta_enforce_routes)(ux_world *w, int replica, const int *link_i
 /* World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_route_swap_due / _dso dta_solver.cpp:130-373) on the
  * finished run of `replica`.  mode 0 = DUE (travel time + tolls), 1 = DSO (travel time + congestion externality,
  * Link::estimate_congestion_externality traffi.cpp:650-689); swap_num < 0 = probabilistic candidates (swap_prob),
- * otherwise exactly swap_num candidates (DSO only).  Results: UX_A_DTA_RS_* .. UX_A_DTA_CHOICE, UX_D_DTA_*. */
+ * otherwise exactly swap_num candidates (DSO only).  Results: UX_A_DTA_RS_* .. UX_A_DTA_CHOICE, UX_D_DTA_*.
+ * replica == -1 (CUDA build): all replicas at once, replica r drawing its candidates from rng_seed + r; array_size of the
+ * variable-length results is then an upper bound over the replicas and get_array returns the replica's actual length. */
 UX_API int UX_FN(dta_route_swap)(ux_world *w, int replica, int mode, double swap_prob, int swap_num,
                                  int has_external_route_sets, unsigned int rng_seed);
 

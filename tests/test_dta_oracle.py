@@ -106,3 +106,24 @@ def test_emu_route_swap_matches_oracle(oracle_api, emu_api, name, mode):
     moved = check_swap_against_oracle(oracle_api, emu_api, name, mode)
     if name in ("siouxfalls", "dta_grid9"):
         assert moved > 0  # congested networks: some platoons do find a cheaper route
+
+
+def check_batched_swap_equals_per_replica(api, mode):
+    sc = SCENARIOS["dta_grid9"]()
+    E = sc.to_engine(api, vehicle_logging_timestep_interval=-1, random_seed=5, num_replicas=3)
+    E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
+    E.dta_enumerate_route_sets(5, 77)
+    E.main_loop()
+    single = [E.dta_route_swap(mode, 0.3, 100 + r, replica=r) for r in range(3)]
+    gaps = [E.get_array(C.A_DTA_T_GAP, r) for r in range(3)]
+    batched = E.dta_route_swap_all(mode, 0.3, 100)
+    for r in range(3):
+        assert_swap_equal(single[r], batched[r])
+        assert np.array_equal(gaps[r], E.get_array(C.A_DTA_T_GAP, r))
+    assert not np.array_equal(batched[0]["ra_link_ids"], batched[1]["ra_link_ids"])  # replicas are different runs
+    E.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_emu_batched_swap_equals_per_replica(emu_api, mode):
+    check_batched_swap_equals_per_replica(emu_api, mode)

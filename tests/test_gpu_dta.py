@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from uxsim_b200 import _capi as C
-from test_dta_oracle import SCENARIOS, check_swap_against_oracle, run
+from test_dta_oracle import SCENARIOS, check_batched_swap_equals_per_replica, check_swap_against_oracle, run
 
 pytestmark = pytest.mark.gpu
 
@@ -42,3 +42,8 @@ def test_gpu_route_swap_needs_recorded_traversals(cuda_api):
     with pytest.raises(RuntimeError, match="RECORD_TRAVERSALS"):
         E.dta_route_swap(0, 0.5, 1)
     E.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gpu_batched_swap_equals_per_replica(cuda_api, mode):
+    check_batched_swap_equals_per_replica(cuda_api, mode)

@@ -39,7 +39,7 @@ K_NAMES = ("k_pre(unused)", "k_node", "k_update", "k_edge_cost", "k_sssp", "k_du
 OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS, OPT_RECORD_TRAVERSALS = 1, 2, 3
 D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT, D_LAST_LOOP_MS, D_KERNEL_MS_OF = 1, 2, 3, 4, 5, 6, 100
 D_UPLOAD_MS, D_GRAPH_BUILD_MS, D_LAST_LOOP_WALL_MS = 7, 8, 9
-D_DTA_N_SWAP, D_DTA_POTENTIAL_N_SWAP, D_DTA_TOTAL_T_GAP, D_DTA_SWAP_MS = 10, 11, 12, 13
+D_DTA_N_SWAP, D_DTA_POTENTIAL_N_SWAP, D_DTA_TOTAL_T_GAP, D_DTA_SWAP_MS, D_DTA_N_SWAP_OF = 10, 11, 12, 13, 1000
 
 A_CUM_ARRIVAL, A_CUM_DEPARTURE, A_TRAVELTIME_INSTANT, A_TRAVELTIME_ACTUAL = 1, 2, 3, 4
 A_VEH_STATE, A_VEH_ARRIVAL_TS, A_VEH_DEPART_TS, A_VEH_TRAVEL_TIME, A_VEH_DISTANCE = 10, 11, 12, 13, 14
@@ -336,6 +336,18 @@ class EngineWorld:
                 "ra_offsets": g(A_DTA_RA_OFFSETS), "cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP),
                 "potential_n_swap": self.get_double(D_DTA_POTENTIAL_N_SWAP), "total_t_gap": self.get_double(D_DTA_TOTAL_T_GAP)}
 
+    def dta_route_swap_all(self, mode: int, swap_prob: float, rng_seed: int, swap_num: int = -1, has_external_route_sets: bool = False) -> list:
+        """Route swap of every replica in one call (replica r draws from ``rng_seed + r``): list of the per-replica dicts."""
+        self._check(self.api.dta_route_swap(self.h, -1, int(mode), float(swap_prob), int(swap_num), 1 if has_external_route_sets else 0,
+                                            int(rng_seed) & 0xFFFFFFFF))
+        out = []
+        for r in range(self.get_int(I_NUM_REPLICAS)):
+            g = lambda a: self.get_array(a, r)
+            out.append({"rs_link_ids": g(A_DTA_RS_LINKS), "rs_offsets": g(A_DTA_RS_OFFSETS), "ra_link_ids": g(A_DTA_RA_LINKS),
+                        "ra_offsets": g(A_DTA_RA_OFFSETS), "cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP_OF + r),
+                        "potential_n_swap": self.get_double(D_DTA_N_SWAP_OF + 1000 + r), "total_t_gap": self.get_double(D_DTA_N_SWAP_OF + 2000 + r)})
+        return out
+
     # -- interventions --------------------------------------------------------------------------------
     def set_link_param(self, link: int, field: int, value: float):
         self._check(self.api.set_link_param(self.h, int(link), int(field), float(value)))
@@ -363,7 +375,9 @@ class EngineWorld:
         n = self._check(self.api.array_size(self.h, int(what), C.byref(dt)))
         out = np.empty(int(n), dtype=_NP_DTYPE[dt.value])
         if n > 0:
-            self._check(self.api.get_array(self.h, int(what), int(replica), out.ctypes.data_as(C.c_void_p), int(n)))
+            m = self._check(self.api.get_array(self.h, int(what), int(replica), out.ctypes.data_as(C.c_void_p), int(n)))
+            if m < n:  # variable-length per-replica results: array_size is an upper bound
+                out = out[:m]
         return out
 
     def get_device_array(self, what: int, replica: int = 0):

@@ -1422,25 +1422,28 @@ struct DtaDev {
     const double *ext;  // [L][T] congestion externality (DSO) or nullptr
     const int *od_o, *od_d, *route_links; const long long *od_off, *route_off; long long n_od;  // route-set store, pairs sorted
     const long long *tr_off; int *tr_link, *tr_t;  // traversed routes (CSR per platoon): link, entry step
-    int mode, has_external;
+    int mode, has_external, replica;
     const unsigned char *flag_swap;
     int *pair; unsigned char *draws;       // k_dta_prepare -> host RNG -> k_dta_swap
     double *cost_actual, *t_gap; int *choice; unsigned char *pot;
 };
 
 // link-entry events -> per-platoon CSR (position = offset + ordinal of the link on the platoon's route)
-__global__ void k_dta_scatter(const DevWorld *worlds, int replica, long long n, DtaDev D) {
-    const DevWorld &W = worlds[replica];
+__global__ void k_dta_scatter(const DevWorld *worlds, const DtaDev *dd) {
+    const DtaDev &D = dd[blockIdx.y];
+    const DevWorld &W = worlds[D.replica];
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (long long)*W.tv_count) return;
     int4 e = W.tv_ev[i];
     long long q = D.tr_off[e.x] + e.y;
     D.tr_link[q] = e.z; D.tr_t[q] = e.w;
 }
 
 // Link::estimate_congestion_externality (traffi.cpp:650-689) for every (link, step): thread per cell, [L][T]
-__global__ void k_dta_externality(const DevWorld *worlds, int replica, const double *tt, double *ext) {
-    const DevWorld &W = worlds[replica];
+__global__ void k_dta_externality(const DevWorld *worlds, const DtaDev *dd) {
+    const DtaDev &D = dd[blockIdx.y];
+    const DevWorld &W = worlds[D.replica];
+    const double *tt = D.tt; double *ext = const_cast<double *>(D.ext);
     int n = W.T, L = W.L;
     long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= (long long)L * n) return;
@@ -1490,8 +1493,9 @@ UX_DEV double dta_route_cost(const DevWorld &W, const DtaDev &D, const int *link
 
 // per platoon: travel cost, and whether it takes part in the swap (finished trip, OD pair in the store, traversed route in
 // an external set): the ones that do consume one uniform draw each, in platoon order (dta_solver.cpp:149-203)
-__global__ void k_dta_prepare(const DevWorld *worlds, int replica, DtaDev D) {
-    const DevWorld &W = worlds[replica];
+__global__ void k_dta_prepare(const DevWorld *worlds, const DtaDev *dd) {
+    const DtaDev &D = dd[blockIdx.y];
+    const DevWorld &W = worlds[D.replica];
     long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (vi >= W.P) return;
     long long a0 = D.tr_off[vi]; int ntr = (int)(D.tr_off[vi + 1] - a0);
@@ -1526,8 +1530,9 @@ __global__ void k_dta_prepare(const DevWorld *worlds, int replica, DtaDev D) {
 
 #define DTA_WARPS 4
 // warp per platoon: lanes evaluate the alternative routes, then the scan over routes in store order (dta_solver.cpp:228-241)
-__global__ void __launch_bounds__(32 * DTA_WARPS) k_dta_swap(const DevWorld *worlds, int replica, DtaDev D) {
-    LOAD_WORLD_N(W, worlds, 64, replica)
+__global__ void __launch_bounds__(32 * DTA_WARPS) k_dta_swap(const DevWorld *worlds, const DtaDev *dd) {
+    const DtaDev &D = dd[blockIdx.y];
+    LOAD_WORLD_N(W, worlds, 64, D.replica)
     WARP_BEGIN
     __shared__ double cost_s[DTA_WARPS][32];
     long long vi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1632,8 +1637,11 @@ struct ux_world {
     struct DtaResult {
         bool valid = false; int replica = 0;
         std::vector<long long> rs_off, ra_off; std::vector<int> rs_links, ra_links, choice; std::vector<double> ra_entry_t, cost_actual, t_gap;
-        double n_swap = 0, potential_n_swap = 0, total_t_gap = 0, ms = 0;
-    } swap;
+        double n_swap = 0, potential_n_swap = 0, total_t_gap = 0;
+    };
+    std::vector<DtaResult> swaps;  // per replica
+    int swap_last = 0;             // replica of the most recent result (scalar queries without a replica index)
+    double swap_ms = 0;
     // measurement
     long long h2d_bytes = 0, d2h_bytes = 0;
     double last_loop_ms = 0.0, upload_ms = 0.0, loop_wall_ms = 0.0, graph_build_ms = 0.0;
@@ -2580,15 +2588,20 @@ UX_API double ux_get_double(ux_world *w, int what) {
     case UX_D_TIME: return w->timestep * w->dt;
     case UX_D_T_MAX: return w->p.t_max;
     case UX_D_LAST_LOOP_MS: return w->last_loop_ms;
-    case UX_D_DTA_N_SWAP: return w->swap.n_swap;
-    case UX_D_DTA_POTENTIAL_N_SWAP: return w->swap.potential_n_swap;
-    case UX_D_DTA_TOTAL_T_GAP: return w->swap.total_t_gap;
-    case UX_D_DTA_SWAP_MS: return w->swap.ms;
+    case UX_D_DTA_N_SWAP: return w->swaps.empty() ? 0.0 : w->swaps[w->swap_last].n_swap;
+    case UX_D_DTA_POTENTIAL_N_SWAP: return w->swaps.empty() ? 0.0 : w->swaps[w->swap_last].potential_n_swap;
+    case UX_D_DTA_TOTAL_T_GAP: return w->swaps.empty() ? 0.0 : w->swaps[w->swap_last].total_t_gap;
+    case UX_D_DTA_SWAP_MS: return w->swap_ms;
     case UX_D_UPLOAD_MS: return w->upload_ms;
     case UX_D_GRAPH_BUILD_MS: return w->graph_build_ms;
     case UX_D_LAST_LOOP_WALL_MS: return w->loop_wall_ms;
     default:
-        if (what >= UX_D_KERNEL_MS_OF && what < UX_D_KERNEL_MS_OF + UX_K_COUNT) return w->k_ms[what - UX_D_KERNEL_MS_OF];
+        if (what >= UX_D_DTA_N_SWAP_OF && what < UX_D_DTA_N_SWAP_OF + 3000) {  // per-replica scalars of a batched route swap
+        int kind = (what - UX_D_DTA_N_SWAP_OF) / 1000, r = (what - UX_D_DTA_N_SWAP_OF) % 1000;
+        if (r >= (int)w->swaps.size() || !w->swaps[r].valid) return NAN;
+        return kind == 0 ? w->swaps[r].n_swap : kind == 1 ? w->swaps[r].potential_n_swap : w->swaps[r].total_t_gap;
+    }
+    if (what >= UX_D_KERNEL_MS_OF && what < UX_D_KERNEL_MS_OF + UX_K_COUNT) return w->k_ms[what - UX_D_KERNEL_MS_OF];
         return NAN;
     }
 }
@@ -2730,9 +2743,9 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta_p->route_off.size(); dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_LINKS: n = (int64_t)w->dta_p->links.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
-    case UX_A_DTA_RS_LINKS: n = (int64_t)w->swap.rs_links.size(); dt = UX_DT_I32; break;
-    case UX_A_DTA_RA_LINKS: n = (int64_t)w->swap.ra_links.size(); dt = UX_DT_I32; break;
-    case UX_A_DTA_RA_ENTRY_T: n = (int64_t)w->swap.ra_entry_t.size(); break;
+    case UX_A_DTA_RS_LINKS: n = 0; for (auto &r : w->swaps) n = std::max(n, (int64_t)r.rs_links.size()); dt = UX_DT_I32; break;  // upper bound over the replicas
+    case UX_A_DTA_RA_LINKS: n = 0; for (auto &r : w->swaps) n = std::max(n, (int64_t)r.ra_links.size()); dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_ENTRY_T: n = 0; for (auto &r : w->swaps) n = std::max(n, (int64_t)r.ra_entry_t.size()); break;
     case UX_A_DTA_COST_ACTUAL: case UX_A_DTA_T_GAP: n = P; break;
     case UX_A_DTA_CHOICE: n = P; dt = UX_DT_I32; break;
     default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
@@ -2857,7 +2870,7 @@ void parallel_for(int n, F body) {  // body(thread index, item)
 }  // namespace
 extern "C" {
 
-static DtaStore &dta_new_store(ux_world *w) { w->dta_p = std::make_shared<DtaStore>(); w->swap.valid = false; return *w->dta_p; }
+static DtaStore &dta_new_store(ux_world *w) { w->dta_p = std::make_shared<DtaStore>(); w->swaps.clear(); return *w->dta_p; }
 
 // World.enumerate_od_route_sets_ids_cpp (bindings.cpp:461-465) = World::enumerate_k_random_routes_cpp (traffi.cpp:1387-1481).
 // Host side (it runs once per solve): one shortest-path tree per source and round, sources spread over host threads.
@@ -2950,22 +2963,26 @@ UX_API int ux_dta_share_route_sets(ux_world *w, ux_world *from) {
     if (!from) return fail(w, UX_ERR_INVALID, "dta_share_route_sets: no source world");
     if (from->nodes.size() != w->nodes.size() || from->links.size() != w->links.size()) return fail(w, UX_ERR_INVALID, "dta_share_route_sets: the worlds have different networks");
     w->dta_p = from->dta_p;
-    w->swap.valid = false;
+    w->swaps.clear();
     return 0;
 }
 
-// World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_solver.cpp:130-373)
+// World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_solver.cpp:130-373).  replica == -1: every replica of
+// the world in the same launches (replica r draws its candidates from mt19937(rng_seed + r)).
 UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
     if (!w->uploaded || w->timestep == 0) return fail(w, UX_ERR_RUNTIME, "dta_route_swap needs a finished run");
-    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    if (replica < -1 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
     if (!w->record_traversals) return fail(w, UX_ERR_RUNTIME, "dta_route_swap needs UX_OPT_RECORD_TRAVERSALS set before the run");
     if (mode != 0 && mode != 1) return fail(w, UX_ERR_INVALID, "mode must be 0 (DUE) or 1 (DSO)");
     cudaSetDevice(w->device);
     cudaStream_t st = w->stream;
-    const DevWorld &hw = w->hw[replica];
-    long long P = hw.P; int L = hw.L, T = hw.T;
-    DtaStore &S = *w->dta_p; auto &R = w->swap;
-    R.valid = false;
+    std::vector<int> reps;
+    if (replica >= 0) reps.push_back(replica); else for (int r = 0; r < w->R; r++) reps.push_back(r);
+    const int nr = (int)reps.size();
+    const long long P = w->hw[0].P; const int L = w->hw[0].L, T = w->hw[0].T;
+    DtaStore &S = *w->dta_p;
+    w->swaps.resize(w->R);
+    for (int r : reps) w->swaps[r].valid = false;
     if (!S.d_block || S.device != w->device) {  // the store goes to the device once per solve
         if (S.d_block) { cudaSetDevice(S.device); cudaFree(S.d_block); S.d_block = nullptr; cudaSetDevice(w->device); }
         size_t b0 = (4 * S.o.size() + 255) & ~(size_t)255, b1 = (4 * S.links.size() + 255) & ~(size_t)255, b2 = (8 * S.od_off.size() + 255) & ~(size_t)255,
@@ -2981,115 +2998,146 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
         CUDA_OK(cudaStreamSynchronize(st));
         w->h2d_bytes += (long long)(8 * S.o.size() + 4 * S.links.size() + 8 * (S.od_off.size() + S.route_off.size()));
     }
-    // traversed routes: counts -> offsets (host scan) -> scatter of the entry events
-    std::vector<int> trav(P);
-    unsigned long long n_ev = 0;
-    if (P) CUDA_OK(cudaMemcpy(trav.data(), hw.v_trav, sizeof(int) * P, cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(&n_ev, hw.tv_count, sizeof(n_ev), cudaMemcpyDeviceToHost));
-    R.ra_off.assign(P + 1, 0);
-    for (long long i = 0; i < P; i++) R.ra_off[i + 1] = R.ra_off[i] + trav[i];
-    if ((unsigned long long)R.ra_off[P] != n_ev) return fail(w, UX_ERR_RUNTIME, "traversal log bookkeeping mismatch: %lld expected, %llu recorded", R.ra_off[P], n_ev);
-    size_t ne = (size_t)n_ev, TL = (size_t)T * L;
+    // traversed routes: per-platoon counts -> offsets (host scan); the events are scattered on the device
+    std::vector<int> trav((size_t)nr * P);
+    std::vector<unsigned long long> n_ev(nr, 0);
+    std::vector<long long> tr_off((size_t)nr * (P + 1), 0), ev_base(nr + 1, 0);
+    for (int q = 0; q < nr; q++) {
+        const DevWorld &hw = w->hw[reps[q]];
+        if (P) cudaMemcpyAsync(trav.data() + (size_t)q * P, hw.v_trav, sizeof(int) * P, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&n_ev[q], hw.tv_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    unsigned long long max_ev = 0;
+    for (int q = 0; q < nr; q++) {
+        long long *off = tr_off.data() + (size_t)q * (P + 1);
+        for (long long i = 0; i < P; i++) off[i + 1] = off[i] + trav[(size_t)q * P + i];
+        if ((unsigned long long)off[P] != n_ev[q]) return fail(w, UX_ERR_RUNTIME, "traversal log bookkeeping mismatch (replica %d): %lld expected, %llu recorded", reps[q], off[P], n_ev[q]);
+        ev_base[q + 1] = ev_base[q] + off[P];
+        max_ev = std::max(max_ev, n_ev[q]);
+    }
+    const size_t ne = (size_t)ev_base[nr], TL = (size_t)T * L, nP = (size_t)nr * P;
     size_t bytes = 0;
     auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
-    size_t o_tt = carve(8 * TL), o_ext = carve(mode == 1 ? 8 * TL : 0), o_troff = carve(8 * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(P), o_pair = carve(4 * P),
-           o_draw = carve(P), o_ca = carve(8 * P), o_tg = carve(8 * P), o_ch = carve(4 * P), o_pot = carve(P);
+    const size_t o_tt = carve(8 * TL * nr), o_ext = carve(mode == 1 ? 8 * TL * nr : 0), o_troff = carve(8 * (size_t)nr * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(nP),
+                 o_pair = carve(4 * nP), o_draw = carve(nP), o_ca = carve(8 * nP), o_tg = carve(8 * nP), o_ch = carve(4 * nP), o_pot = carve(nP), o_dd = carve(sizeof(DtaDev) * nr);
     char *buf = nullptr;
     CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
     auto release = [&](int rc) { cudaFree(buf); return rc; };
-    DtaDev D;
-    memset(&D, 0, sizeof(D));
-    double *d_tt = (double *)(buf + o_tt), *d_ext = (double *)(buf + o_ext);
-    D.tt = d_tt; D.ext = mode == 1 ? d_ext : nullptr;
-    D.od_o = S.d_o; D.od_d = S.d_d; D.route_links = S.d_links; D.od_off = S.d_od_off; D.route_off = S.d_route_off; D.n_od = (long long)S.o.size();
-    D.tr_off = (const long long *)(buf + o_troff); D.tr_link = (int *)(buf + o_trl); D.tr_t = (int *)(buf + o_trt);
-    D.mode = mode; D.has_external = has_external ? 1 : 0;
-    D.flag_swap = (const unsigned char *)(buf + o_fs); D.pair = (int *)(buf + o_pair); D.draws = (unsigned char *)(buf + o_draw);
-    D.cost_actual = (double *)(buf + o_ca); D.t_gap = (double *)(buf + o_tg); D.choice = (int *)(buf + o_ch); D.pot = (unsigned char *)(buf + o_pot);
+    std::vector<DtaDev> hd(nr);
+    for (int q = 0; q < nr; q++) {
+        DtaDev &D = hd[q];
+        memset(&D, 0, sizeof(D));
+        D.tt = (double *)(buf + o_tt) + (size_t)q * TL; D.ext = mode == 1 ? (double *)(buf + o_ext) + (size_t)q * TL : nullptr;
+        D.od_o = S.d_o; D.od_d = S.d_d; D.route_links = S.d_links; D.od_off = S.d_od_off; D.route_off = S.d_route_off; D.n_od = (long long)S.o.size();
+        D.tr_off = (const long long *)(buf + o_troff) + (size_t)q * (P + 1); D.tr_link = (int *)(buf + o_trl) + ev_base[q]; D.tr_t = (int *)(buf + o_trt) + ev_base[q];
+        D.mode = mode; D.has_external = has_external ? 1 : 0; D.replica = reps[q];
+        D.flag_swap = (const unsigned char *)(buf + o_fs) + (size_t)q * P; D.pair = (int *)(buf + o_pair) + (size_t)q * P; D.draws = (unsigned char *)(buf + o_draw) + (size_t)q * P;
+        D.cost_actual = (double *)(buf + o_ca) + (size_t)q * P; D.t_gap = (double *)(buf + o_tg) + (size_t)q * P; D.choice = (int *)(buf + o_ch) + (size_t)q * P; D.pot = (unsigned char *)(buf + o_pot) + (size_t)q * P;
+    }
+    const DtaDev *d_dd = (const DtaDev *)(buf + o_dd);
 #ifndef UX_EMU
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
 #endif
-    cudaMemcpyAsync(buf + o_troff, R.ra_off.data(), 8 * (P + 1), cudaMemcpyHostToDevice, st);
-    if (ne) UX_LAUNCH(k_dta_scatter, dim3((unsigned)((ne + 255) / 256)), dim3(256), st, w->dworlds, replica, (long long)ne, D);
-    if (L > 0) UX_LAUNCH(k_tt_actual, dim3((L + 127) / 128), dim3(128), st, w->dworlds, replica, d_tt);
-    if (mode == 1 && TL) UX_LAUNCH(k_dta_externality, dim3((unsigned)((TL + 127) / 128)), dim3(128), st, w->dworlds, replica, (const double *)d_tt, d_ext);
-    if (P) UX_LAUNCH(k_dta_prepare, dim3((unsigned)((P + 127) / 128)), dim3(128), st, w->dworlds, replica, D);
+    cudaMemcpyAsync(buf + o_dd, hd.data(), sizeof(DtaDev) * nr, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + o_troff, tr_off.data(), 8 * tr_off.size(), cudaMemcpyHostToDevice, st);
+    if (max_ev) UX_LAUNCH(k_dta_scatter, dim3((unsigned)((max_ev + 255) / 256), nr), dim3(256), st, w->dworlds, d_dd);
+    if (L > 0) for (int q = 0; q < nr; q++) UX_LAUNCH(k_tt_actual, dim3((L + 127) / 128), dim3(128), st, w->dworlds, reps[q], const_cast<double *>(hd[q].tt));
+    if (mode == 1 && TL) UX_LAUNCH(k_dta_externality, dim3((unsigned)((TL + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd);
+    if (P) UX_LAUNCH(k_dta_prepare, dim3((unsigned)((P + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd);
     // swap candidates: the reference's own stream, std::mt19937(rng_seed) + uniform_real_distribution (dta_solver.cpp:148-149, 265-283)
-    std::vector<unsigned char> draws(P), flag(P, 0);
-    if (P) { cudaMemcpyAsync(draws.data(), buf + o_draw, P, cudaMemcpyDeviceToHost, st); }
+    std::vector<unsigned char> draws(nP), flag(nP, 0);
+    if (nP) cudaMemcpyAsync(draws.data(), buf + o_draw, nP, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route-swap preparation: %s", cudaGetErrorString(cudaGetLastError())));
-    {
-        std::mt19937 rng(rng_seed);
+    for (int q = 0; q < nr; q++) {
+        std::mt19937 rng(replica >= 0 ? rng_seed : rng_seed + (unsigned)reps[q]);
         std::uniform_real_distribution<double> udist(0.0, 1.0);
+        unsigned char *fl = flag.data() + (size_t)q * P; const unsigned char *dr = draws.data() + (size_t)q * P;
         if (mode == 1 && swap_num >= 0) {
             std::vector<int> idx(P);
             for (long long i = 0; i < P; i++) idx[i] = (int)i;
             std::shuffle(idx.begin(), idx.end(), rng);
             long long m = std::min<long long>(swap_num, P);
-            for (long long i = 0; i < m; i++) flag[idx[i]] = 1;
-        } else if (mode == 1) { for (long long i = 0; i < P; i++) flag[i] = udist(rng) < swap_prob; }
-        else { for (long long i = 0; i < P; i++) if (draws[i]) flag[i] = udist(rng) < swap_prob; }
+            for (long long i = 0; i < m; i++) fl[idx[i]] = 1;
+        } else if (mode == 1) { for (long long i = 0; i < P; i++) fl[i] = udist(rng) < swap_prob; }
+        else { for (long long i = 0; i < P; i++) if (dr[i]) fl[i] = udist(rng) < swap_prob; }
     }
-    if (P) {
-        cudaMemcpyAsync(buf + o_fs, flag.data(), P, cudaMemcpyHostToDevice, st);
-        UX_LAUNCH(k_dta_swap, dim3((unsigned)((P + DTA_WARPS - 1) / DTA_WARPS)), dim3(32 * DTA_WARPS), st, w->dworlds, replica, D);
+    if (nP) {
+        cudaMemcpyAsync(buf + o_fs, flag.data(), nP, cudaMemcpyHostToDevice, st);
+        UX_LAUNCH(k_dta_swap, dim3((unsigned)((P + DTA_WARPS - 1) / DTA_WARPS), nr), dim3(32 * DTA_WARPS), st, w->dworlds, d_dd);
     }
 #ifndef UX_EMU
     cudaEventRecord(e1, st);
 #endif
-    R.choice.assign(P, -2); R.cost_actual.assign(P, 0.0); R.t_gap.assign(P, 0.0);
-    std::vector<unsigned char> pot(P, 0);
-    std::vector<int> tr_t(ne);
-    R.ra_links.assign(ne, 0);
-    if (P) {
-        cudaMemcpyAsync(R.choice.data(), buf + o_ch, 4 * P, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(R.cost_actual.data(), buf + o_ca, 8 * P, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(R.t_gap.data(), buf + o_tg, 8 * P, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(pot.data(), buf + o_pot, P, cudaMemcpyDeviceToHost, st);
+    std::vector<int> choice(nP), tr_l(ne), tr_t(ne); std::vector<double> cost(nP), gap(nP); std::vector<unsigned char> pot(nP, 0);
+    if (nP) {
+        cudaMemcpyAsync(choice.data(), buf + o_ch, 4 * nP, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(cost.data(), buf + o_ca, 8 * nP, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(gap.data(), buf + o_tg, 8 * nP, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(pot.data(), buf + o_pot, nP, cudaMemcpyDeviceToHost, st);
     }
-    if (ne) { cudaMemcpyAsync(R.ra_links.data(), buf + o_trl, 4 * ne, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(tr_t.data(), buf + o_trt, 4 * ne, cudaMemcpyDeviceToHost, st); }
+    if (ne) { cudaMemcpyAsync(tr_l.data(), buf + o_trl, 4 * ne, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(tr_t.data(), buf + o_trt, 4 * ne, cudaMemcpyDeviceToHost, st); }
     if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route swap: %s", cudaGetErrorString(cudaGetLastError())));
 #ifndef UX_EMU
-    { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); R.ms = ms; cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); w->swap_ms = ms; cudaEventDestroy(e0); cudaEventDestroy(e1); }
 #endif
-    w->d2h_bytes += (long long)(P * (4 + 8 + 8 + 1 + 1 + 4) + ne * 8);
-    w->h2d_bytes += (long long)(P * 9 + 8);
-    R.ra_entry_t.resize(ne);
-    for (size_t i = 0; i < ne; i++) R.ra_entry_t[i] = (double)tr_t[i] * w->dt;
-    // totals in platoon order (sequential sums of dta_solver.cpp:243-252) and the next iteration's routes
-    R.n_swap = 0; R.potential_n_swap = 0; R.total_t_gap = 0;
-    R.rs_off.assign(P + 1, 0);
-    for (long long i = 0; i < P; i++) {
-        int c = R.choice[i];
-        if (pot[i]) R.potential_n_swap += w->p.delta_n;
-        R.total_t_gap += R.t_gap[i];
-        if (c >= 0 && pot[i]) R.n_swap += w->p.delta_n;  // a forced external route has pot == 0
-        long long len = c == -2 ? 0 : c == -1 ? R.ra_off[i + 1] - R.ra_off[i] : S.route_off[c + 1] - S.route_off[c];
-        R.rs_off[i + 1] = R.rs_off[i] + len;
+    w->d2h_bytes += (long long)(nP * (4 + 8 + 8 + 1 + 1 + 4) + ne * 8);
+    w->h2d_bytes += (long long)(nP * 9 + 8 * nr);
+    for (int q = 0; q < nr; q++) {
+        auto &R = w->swaps[reps[q]];
+        const long long *off = tr_off.data() + (size_t)q * (P + 1);
+        const size_t nq = (size_t)off[P];
+        R.ra_off.assign(off, off + P + 1);
+        R.ra_links.assign(tr_l.begin() + ev_base[q], tr_l.begin() + ev_base[q] + nq);
+        R.ra_entry_t.resize(nq);
+        for (size_t i = 0; i < nq; i++) R.ra_entry_t[i] = (double)tr_t[ev_base[q] + i] * w->dt;
+        R.choice.assign(choice.begin() + (size_t)q * P, choice.begin() + (size_t)(q + 1) * P);
+        R.cost_actual.assign(cost.begin() + (size_t)q * P, cost.begin() + (size_t)(q + 1) * P);
+        R.t_gap.assign(gap.begin() + (size_t)q * P, gap.begin() + (size_t)(q + 1) * P);
+        const unsigned char *pt = pot.data() + (size_t)q * P;
+        // totals in platoon order (sequential sums of dta_solver.cpp:243-252) and the next iteration's routes
+        R.n_swap = 0; R.potential_n_swap = 0; R.total_t_gap = 0;
+        R.rs_off.assign(P + 1, 0);
+        for (long long i = 0; i < P; i++) {
+            int c = R.choice[i];
+            if (pt[i]) R.potential_n_swap += w->p.delta_n;
+            R.total_t_gap += R.t_gap[i];
+            if (c >= 0 && pt[i]) R.n_swap += w->p.delta_n;  // a forced external route has pot == 0
+            long long len = c == -2 ? 0 : c == -1 ? R.ra_off[i + 1] - R.ra_off[i] : S.route_off[c + 1] - S.route_off[c];
+            R.rs_off[i + 1] = R.rs_off[i] + len;
+        }
+        R.rs_links.resize((size_t)R.rs_off[P]);
+        for (long long i = 0; i < P; i++) {
+            int c = R.choice[i]; long long len = R.rs_off[i + 1] - R.rs_off[i];
+            if (len > 0) memcpy(R.rs_links.data() + R.rs_off[i], c == -1 ? R.ra_links.data() + R.ra_off[i] : S.links.data() + S.route_off[c], sizeof(int) * (size_t)len);
+        }
+        R.replica = reps[q]; R.valid = true;
+        w->swap_last = reps[q];
     }
-    R.rs_links.resize((size_t)R.rs_off[P]);
-    for (long long i = 0; i < P; i++) {
-        int c = R.choice[i]; long long len = R.rs_off[i + 1] - R.rs_off[i];
-        if (len > 0) memcpy(R.rs_links.data() + R.rs_off[i], c == -1 ? R.ra_links.data() + R.ra_off[i] : S.links.data() + S.route_off[c], sizeof(int) * (size_t)len);
-    }
-    R.replica = replica; R.valid = true;
     return release(0);
 }
 
 static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
     int dt; int64_t n = ux_array_size(w, what, &dt);
     if (n < 0) return n;
-    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
     const void *src = nullptr;
     if (what >= UX_A_DTA_RS_OFFSETS) {
-        if (!w->swap.valid || w->swap.replica != replica) return fail(w, UX_ERR_RUNTIME, "no route swap result for replica %d", replica);
-        auto &r = w->swap;
-        src = what == UX_A_DTA_RS_OFFSETS ? (const void *)r.rs_off.data() : what == UX_A_DTA_RA_OFFSETS ? (const void *)r.ra_off.data() : what == UX_A_DTA_RS_LINKS ? (const void *)r.rs_links.data()
-            : what == UX_A_DTA_RA_LINKS ? (const void *)r.ra_links.data() : what == UX_A_DTA_RA_ENTRY_T ? (const void *)r.ra_entry_t.data() : what == UX_A_DTA_COST_ACTUAL ? (const void *)r.cost_actual.data()
-            : what == UX_A_DTA_T_GAP ? (const void *)r.t_gap.data() : (const void *)r.choice.data();
+        if (replica < 0 || replica >= (int)w->swaps.size() || !w->swaps[replica].valid) return fail(w, UX_ERR_RUNTIME, "no route swap result for replica %d", replica);
+        auto &r = w->swaps[replica];
+        switch (what) {
+        case UX_A_DTA_RS_OFFSETS: src = r.rs_off.data(); break;
+        case UX_A_DTA_RA_OFFSETS: src = r.ra_off.data(); break;
+        case UX_A_DTA_RS_LINKS: src = r.rs_links.data(); n = (int64_t)r.rs_links.size(); break;
+        case UX_A_DTA_RA_LINKS: src = r.ra_links.data(); n = (int64_t)r.ra_links.size(); break;
+        case UX_A_DTA_RA_ENTRY_T: src = r.ra_entry_t.data(); n = (int64_t)r.ra_entry_t.size(); break;
+        case UX_A_DTA_COST_ACTUAL: src = r.cost_actual.data(); break;
+        case UX_A_DTA_T_GAP: src = r.t_gap.data(); break;
+        default: src = r.choice.data(); break;
+        }
     } else {
         DtaStore &d = *w->dta_p;
         src = what == UX_A_DTA_OD_ORIG ? (const void *)d.o.data() : what == UX_A_DTA_OD_DEST ? (const void *)d.d.data() : what == UX_A_DTA_OD_OFFSETS ? (const void *)d.od_off.data()
             : what == UX_A_DTA_ROUTE_OFFSETS ? (const void *)d.route_off.data() : (const void *)d.links.data();
     }
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
     if (n > 0) memcpy(dst, src, (dt == UX_DT_I32 ? 4 : 8) * (size_t)n);
     return n;
 }

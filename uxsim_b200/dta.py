@@ -287,8 +287,9 @@ class DayToDayEnsemble:
             t1 = time.perf_counter()
             E.main_loop()
             t2 = time.perf_counter()
-            for r in range(R):
-                res = E.dta_route_swap(self.mode, swap_prob, (swap_seed * 1000003 + day * 65537 + r) & 0x7FFFFFFF, replica=r)
+            day_seed = (swap_seed * 1000003 + day * 65537) & 0x3FFFFFFF   # chain r draws its swap candidates from day_seed + r
+            results = E.dta_route_swap_all(self.mode, swap_prob, day_seed)   # every chain's swap in the same launches
+            for r, res in enumerate(results):
                 prev[r] = (res["rs_link_ids"], res["rs_offsets"])
                 tt = E.get_array(C.A_VEH_TRAVEL_TIME, r)
                 done = tt >= 0

@@ -338,6 +338,12 @@ UX_API int UX_FN(dta_enforce_routes)(ux_world *w, int replica, const int *link_i
 UX_API int UX_FN(dta_route_swap)(ux_world *w, int replica, int mode, double swap_prob, int swap_num,
                                  int has_external_route_sets, unsigned int rng_seed);
 
+/* Rewind a finished world to t = 0 for the next day of a day-to-day solve (CUDA build): dynamic state re-initialised in
+ * place, each replica's routes_specified of the last dta_route_swap enforced straight from device memory, network / platoon
+ * tables / captured graphs kept.  Same results as: new world + batch_enforce_routes_csr(rs) + main_loop.  The reference
+ * builds a new World per day (DTAsolvers_cpp_adapter.py:318-330), so the CPU engines answer UX_ERR_RUNTIME. */
+UX_API int UX_FN(dta_next_day)(ux_world *w);
+
 /* Message of the last failure on `w` (or of the last failed create_world when w == NULL). */
 UX_API const char *UX_FN(last_error)(ux_world *w);
 

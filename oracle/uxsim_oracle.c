@@ -1341,6 +1341,7 @@ UX_API int uxo_dta_share_route_sets(ux_world *w, ux_world *from) {
     if (!from->dta_od_off) { dta_store_free(w); return 0; }
     return uxo_dta_set_route_sets(w, from->dta_n_od, from->dta_o, from->dta_d, from->dta_od_off, from->dta_route_off, from->dta_links);
 }
+UX_API int uxo_dta_next_day(ux_world *w) { return fail(w, UX_ERR_RUNTIME, "the oracle builds a new world per day (as the reference does)"); }
 UX_API int uxo_dta_enforce_routes(ux_world *w, int replica, const int *ids, const int64_t *off, int64_t nveh) {
     if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "oracle has a single replica");
     return uxo_batch_enforce_routes_csr(w, ids, off, nveh);

@@ -80,6 +80,48 @@ def _check_ensemble(api):
     assert solo.ttts[0, 0] == ens.ttts[1, 0] and solo.n_swaps[0, 0] != 0
 
 
+def _check_rewind_equals_rebuild(api):
+    """dta_next_day (rewind in place, routes handed over on the device) == a new world per day with the routes enforced
+    through the host, which is what the reference does (and what the oracle-parity tests cover)."""
+    from uxsim_b200.dta import DayToDayEnsemble
+
+    sc, R, days = S.dta_grid9(), 3, 3
+    ens = DayToDayEnsemble(sc, R, mode="DUE", base_seed=3, api=api)
+    ens.solve(max_iter=days, n_routes_per_od=5, swap_prob=0.3, enum_seed=9, swap_seed=2)
+    tab = sc.tables()
+    E0 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1)
+    E0.dta_enumerate_route_sets(5, 9)
+    prev = [None] * R
+    for day in range(days):
+        E = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, random_seed=3)
+        E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
+        E.dta_share_route_sets(E0)
+        for r in range(R):
+            if prev[r] is not None:
+                E.dta_enforce_routes(r, *prev[r])
+        E.main_loop()
+        res = E.dta_route_swap_all(0, 0.3, (2 * 1000003 + day * 65537) & 0x3FFFFFFF)
+        for r in range(R):
+            prev[r] = (res[r]["rs_link_ids"], res[r]["rs_offsets"])
+            tt = E.get_array(C.A_VEH_TRAVEL_TIME, r)
+            assert float(tt[tt >= 0].sum()) * sc.deltan == ens.ttts[r, day]
+            assert res[r]["n_swap"] == ens.n_swaps[r, day] and res[r]["potential_n_swap"] == ens.potential_swaps[r, day]
+            assert res[r]["total_t_gap"] / len(tt) == ens.t_gaps[r, day]
+        E.close()
+    for r in range(R):
+        assert np.array_equal(prev[r][0], ens.routes[r][0]) and np.array_equal(prev[r][1], ens.routes[r][1])
+    E0.close()
+
+
+def test_rewind_equals_rebuild_emulated(emu_api):
+    _check_rewind_equals_rebuild(emu_api)
+
+
+@pytest.mark.gpu
+def test_rewind_equals_rebuild_gpu(cuda_api):
+    _check_rewind_equals_rebuild(cuda_api)
+
+
 def test_day_to_day_ensemble_emulated(emu_api):
     _check_ensemble(emu_api)
 

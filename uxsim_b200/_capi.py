@@ -73,7 +73,7 @@ ABI_SYMBOLS = (
     "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
     "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
     "ensemble_link_stats", "last_error", "dta_enumerate_route_sets", "dta_set_route_sets", "dta_share_route_sets",
-    "dta_enforce_routes", "dta_route_swap",
+    "dta_enforce_routes", "dta_route_swap", "dta_next_day",
 )
 
 
@@ -165,6 +165,7 @@ class CApi:
         self.dta_set_route_sets = fn("dta_set_route_sets", C.c_int, [p, C.c_int64, i32p, i32p, i64p, i64p, i32p])
         self.dta_share_route_sets = fn("dta_share_route_sets", C.c_int, [p, p])
         self.dta_enforce_routes = fn("dta_enforce_routes", C.c_int, [p, C.c_int, i32p, i64p, C.c_int64])
+        self.dta_next_day = fn("dta_next_day", C.c_int, [p])
         self.dta_route_swap = fn("dta_route_swap", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint])
 
     def exported(self, name: str) -> bool:
@@ -322,6 +323,10 @@ class EngineWorld:
         self._check(self.api.dta_enforce_routes(self.h, int(replica), ids.ctypes.data_as(C.POINTER(C.c_int32)),
                                                 off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1))
 
+    def dta_next_day(self):
+        """Rewind the finished world to t = 0 with the last route swap's routes enforced (CUDA engine only)."""
+        self._check(self.api.dta_next_day(self.h))
+
     def dta_route_sets_csr(self):
         """ODRouteSetStore.to_csr: (orig, dest, od_offsets, route_offsets, route_links), pairs sorted by (orig, dest)."""
         return tuple(self.get_array(a) for a in (A_DTA_OD_ORIG, A_DTA_OD_DEST, A_DTA_OD_OFFSETS, A_DTA_ROUTE_OFFSETS, A_DTA_ROUTE_LINKS))
@@ -336,13 +341,19 @@ class EngineWorld:
                 "ra_offsets": g(A_DTA_RA_OFFSETS), "cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP),
                 "potential_n_swap": self.get_double(D_DTA_POTENTIAL_N_SWAP), "total_t_gap": self.get_double(D_DTA_TOTAL_T_GAP)}
 
-    def dta_route_swap_all(self, mode: int, swap_prob: float, rng_seed: int, swap_num: int = -1, has_external_route_sets: bool = False) -> list:
-        """Route swap of every replica in one call (replica r draws from ``rng_seed + r``): list of the per-replica dicts."""
+    def dta_route_swap_all(self, mode: int, swap_prob: float, rng_seed: int, swap_num: int = -1, has_external_route_sets: bool = False,
+                           routes: bool = True) -> list:
+        """Route swap of every replica in one call (replica r draws from ``rng_seed + r``): list of the per-replica dicts.
+        ``routes=False`` leaves the link lists on the device (``dta_next_day`` consumes them there)."""
         self._check(self.api.dta_route_swap(self.h, -1, int(mode), float(swap_prob), int(swap_num), 1 if has_external_route_sets else 0,
                                             int(rng_seed) & 0xFFFFFFFF))
         out = []
         for r in range(self.get_int(I_NUM_REPLICAS)):
             g = lambda a: self.get_array(a, r)
+            if not routes:
+                out.append({"cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP_OF + r),
+                            "potential_n_swap": self.get_double(D_DTA_N_SWAP_OF + 1000 + r), "total_t_gap": self.get_double(D_DTA_N_SWAP_OF + 2000 + r)})
+                continue
             out.append({"rs_link_ids": g(A_DTA_RS_LINKS), "rs_offsets": g(A_DTA_RS_OFFSETS), "ra_link_ids": g(A_DTA_RA_LINKS),
                         "ra_offsets": g(A_DTA_RA_OFFSETS), "cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP_OF + r),
                         "potential_n_swap": self.get_double(D_DTA_N_SWAP_OF + 1000 + r), "total_t_gap": self.get_double(D_DTA_N_SWAP_OF + 2000 + r)})

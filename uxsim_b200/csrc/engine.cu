@@ -1528,6 +1528,36 @@ __global__ void k_dta_prepare(const DevWorld *worlds, const DtaDev *dd) {
     D.choice[vi] = choice; D.pair[vi] = pair; D.draws[vi] = draws; D.t_gap[vi] = 0.0; D.pot[vi] = 0;
 }
 
+__global__ void k_fill_f64(double *p, long long n, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// routes_specified of one replica as a device CSR: length per platoon, then (after the host's scan) the link lists
+__global__ void k_dta_rs_len(const DevWorld *worlds, const DtaDev *dd, int *len_out) {
+    const DtaDev &D = dd[blockIdx.y];
+    const DevWorld &W = worlds[D.replica];
+    long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= W.P) return;
+    int c = D.choice[vi];
+    long long len = c == -2 ? 0 : c == -1 ? D.tr_off[vi + 1] - D.tr_off[vi] : D.route_off[c + 1] - D.route_off[c];
+    len_out[(size_t)blockIdx.y * W.P + vi] = (int)len;
+}
+struct DtaGather { const int *off; int *links; };
+__global__ void k_dta_rs_gather(const DevWorld *worlds, const DtaDev *dd, const DtaGather *gg) {
+    const DtaDev &D = dd[blockIdx.y];
+    const DtaGather &G = gg[blockIdx.y];
+    const DevWorld &W = worlds[D.replica];
+    long long vi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // 8 threads per platoon
+    int sub = (int)(threadIdx.x & 7);
+    if (vi >= W.P) return;
+    int c = D.choice[vi];
+    if (c == -2) return;
+    const int *src = c == -1 ? D.tr_link + D.tr_off[vi] : D.route_links + D.route_off[c];
+    int o = G.off[vi], len = G.off[vi + 1] - o;
+    for (int j = sub; j < len; j += 8) G.links[o + j] = src[j];
+}
+
 #define DTA_WARPS 4
 // warp per platoon: lanes evaluate the alternative routes, then the scan over routes in store order (dta_solver.cpp:228-241)
 __global__ void __launch_bounds__(32 * DTA_WARPS) k_dta_swap(const DevWorld *worlds, const DtaDev *dd) {
@@ -1637,9 +1667,19 @@ struct ux_world {
     struct DtaResult {
         bool valid = false; int replica = 0;
         std::vector<long long> rs_off, ra_off; std::vector<int> rs_links, ra_links, choice; std::vector<double> ra_entry_t, cost_actual, t_gap;
+        bool rs_fetched = false, ra_fetched = false;  // the link lists are copied back from the device on first request
+        const int *d_tr_link = nullptr, *d_tr_t = nullptr;
         double n_swap = 0, potential_n_swap = 0, total_t_gap = 0;
     };
     std::vector<DtaResult> swaps;  // per replica
+    char *swap_buf = nullptr;      // device scratch of the last route swap (traversed routes stay there for lazy hand-back)
+    struct NextRoutes { int *off = nullptr, *links = nullptr; size_t cap = 0; bool ready = false; };
+    std::vector<NextRoutes> next_routes;  // per replica: routes_specified of the last swap as a device CSR (next day's enforced routes)
+    // re-initialisation recipe of the per-replica dynamic state (ux_dta_next_day rewinds the world instead of rebuilding it)
+    struct ReInit { void *dst; size_t bytes; int kind; std::shared_ptr<std::vector<char>> src; };  // 0: bytes of 0xff, 1: doubles of -1.0, 2: copy of src
+    std::vector<ReInit> reinit;
+    size_t dyn_slab0 = 0, dyn_used0 = 0, dyn_slab1 = 0, dyn_used1 = 0;
+    bool rewindable = false;
     int swap_last = 0;             // replica of the most recent result (scalar queries without a replica index)
     double swap_ms = 0;
     // measurement
@@ -1773,6 +1813,8 @@ UX_API void ux_destroy_world(ux_world *w) {
 #endif
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (void *p : w->allocs) cudaFree(p);
+    if (w->swap_buf) cudaFree(w->swap_buf);
+    for (auto &nr_ : w->next_routes) { if (nr_.off) cudaFree(nr_.off); if (nr_.links) cudaFree(nr_.links); }
     slabs_release(w);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
@@ -2184,35 +2226,47 @@ static int upload(ux_world *w) {
     for (int i = 0; i < N; i++) { sig_t[i] = w->nodes[i].sig_t0; sig_ph[i] = w->nodes[i].sig_phase0; fc_rem[i] = w->nodes[i].fc_rem0; }
     std::vector<int> tb(1, w->timestep);
     w->hw.assign(w->R, base);
+    for (auto &kv : w->rep_routes) {  // per-replica enforced routes (ux_dta_enforce_routes): specified_route and links_preferred of that replica
+        DevWorld &d = w->hw[kv.first];
+        const int *o_ = dupload(w, kv.second.first), *l_ = dupload(w, kv.second.second);
+        d.vl_off[0] = d.vl_off[1] = o_; d.vl_list[0] = d.vl_list[1] = l_;
+    }
+    // Everything allocated from here to the end of the replica loop is per-replica DYNAMIC state: zero, except what the
+    // ReInit list records.  ux_dta_next_day rewinds a finished world by zeroing these slab ranges and replaying the list.
+    dalloc<char>(w, 1);  // make sure the marks below sit inside a slab
+    w->dyn_slab0 = w->slabs.size() - 1; w->dyn_used0 = w->slabs.back().used;
+    w->reinit.clear();
+    auto share = [](const void *p_, size_t b) { auto v = std::make_shared<std::vector<char>>(b); if (b) memcpy(v->data(), p_, b); return v; };
+    auto h_co = share(co_rem.data(), 8 * co_rem.size()), h_ci = share(ci_rem.data(), 8 * ci_rem.size()), h_sp = share(sig_ph.data(), 4 * sig_ph.size()),
+         h_st = share(sig_t.data(), 8 * sig_t.size()), h_fc = share(fc_rem.data(), 8 * fc_rem.size());
+    auto reg_ff = [&](void *q, size_t b) { if (q) { cudaMemsetAsync(q, 0xff, b ? b : 1, w->stream); w->reinit.push_back({q, b ? b : 1, 0, nullptr}); } };
+    auto reg_copy = [&](void *q, const std::shared_ptr<std::vector<char>> &src) { if (q && !src->empty()) w->reinit.push_back({q, src->size(), 2, src}); };
     w->d_err_all = dalloc<int>(w, 2 * (size_t)w->R);
     if (!w->d_err_all) return fail(w, UX_ERR_CUDA, "device allocation failed");
     size_t TL = (size_t)T * L;
     for (int r = 0; r < w->R; r++) {
         DevWorld &d = w->hw[r];
         d.seed = w->p.random_seed + r;
-        {   // per-replica enforced routes (ux_dta_enforce_routes): specified_route and links_preferred of this replica
-            auto it = w->rep_routes.find(r);
-            if (it != w->rep_routes.end()) { const int *o_ = dupload(w, it->second.first), *l_ = dupload(w, it->second.second); d.vl_off[0] = d.vl_off[1] = o_; d.vl_list[0] = d.vl_list[1] = l_; }
-        }
         d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L);
         d.trips = dalloc<int>(w, L); d.ev_cnt = dalloc<int>(w, L); d.stat_count = dalloc<long long>(w, L);
         d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem);
+        reg_copy(d.cap_out_rem, h_co); reg_copy(d.cap_in_rem, h_ci);
         d.X = dalloc<double>(w, 2 * (size_t)C); d.V = dalloc<double>(w, C); d.VID = dalloc<int>(w, C); d.LANE = dalloc<int>(w, C);
         d.sig_phase = dupload(w, sig_ph); d.sig_t = dupload(w, sig_t); d.fc_rem = dupload(w, fc_rem);
+        reg_copy(d.sig_phase, h_sp); reg_copy(d.sig_t, h_st); reg_copy(d.fc_rem, h_fc);
         d.gen_head = dalloc<int>(w, N); d.gen_avail = dalloc<int>(w, N);
         d.v_state = dalloc<int>(w, P); d.v_next = dalloc<int>(w, P); d.v_link = dalloc<int>(w, P, false); d.v_arr_ts = dalloc<int>(w, P, false); d.v_trav = dalloc<int>(w, P);
-        if (d.v_link) cudaMemsetAsync(d.v_link, 0xff, sizeof(int) * (P ? P : 1), w->stream);
-        if (d.v_arr_ts) cudaMemsetAsync(d.v_arr_ts, 0xff, sizeof(int) * (P ? P : 1), w->stream);
+        reg_ff(d.v_link, sizeof(int) * P); reg_ff(d.v_arr_ts, sizeof(int) * P);
         d.v_mr = dalloc<double>(w, P); d.v_atl = dalloc<double>(w, P); d.v_dist = dalloc<double>(w, P); d.v_entry_x = dalloc<double>(w, P);
-        { std::vector<double> m1(P, -1.0); d.v_tt = dupload(w, m1); }
+        d.v_tt = dalloc<double>(w, P);
+        if (d.v_tt && P) { UX_LAUNCH(k_fill_f64, dim3((unsigned)((P + 255) / 256)), dim3(256), w->stream, d.v_tt, (long long)P, -1.0); w->reinit.push_back({d.v_tt, (size_t)P * 8, 1, nullptr}); }
         d.v_flags = dalloc<unsigned char>(w, P);
         if (base.log_mode) {
             long long cap = 0;
             for (long long i = 0; i < P; i++) cap += std::max(0, T - w->vehs[i].ts - 1);  // a platoon can be RUN from ts+1 to T-1
             d.lg_cap = cap;
             d.v_gen_ts = dalloc<int>(w, P, false); d.v_end_ts = dalloc<int>(w, P, false); d.v_end_kind = dalloc<unsigned char>(w, P);
-            if (d.v_gen_ts) cudaMemsetAsync(d.v_gen_ts, 0xff, sizeof(int) * (P ? P : 1), w->stream);
-            if (d.v_end_ts) cudaMemsetAsync(d.v_end_ts, 0xff, sizeof(int) * (P ? P : 1), w->stream);
+            reg_ff(d.v_gen_ts, sizeof(int) * P); reg_ff(d.v_end_ts, sizeof(int) * P);
             d.lg_vid = dalloc<int>(w, cap, false); d.lg_t = dalloc<int>(w, cap, false); d.lg_link = dalloc<int>(w, cap, false); d.lg_lane = dalloc<int>(w, cap, false);
             d.lg_x = dalloc<double>(w, cap, false); d.lg_v = dalloc<double>(w, cap, false); d.lg_s = dalloc<double>(w, cap, false);
             d.lg_count = dalloc<unsigned long long>(w, 1);
@@ -2230,11 +2284,13 @@ static int upload(ux_world *w) {
         d.ev_ord = dalloc<int>(w, TL); d.sig_log = dalloc<int>(w, (size_t)T * N);
         d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
         d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
-        if (d.rnext) cudaMemsetAsync(d.rnext, 0xff, sizeof(int) * std::max<size_t>((size_t)D * N, 1), w->stream);
+        reg_ff(d.rnext, sizeof(int) * (size_t)D * N);
         d.err = w->d_err_all + 2 * r; d.t_base = dupload(w, tb); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
         if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
             return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
     }
+    w->dyn_slab1 = w->slabs.size() - 1; w->dyn_used1 = w->slabs.back().used;
+    w->rewindable = w->timestep == 0;
     w->dworlds = dalloc<DevWorld>(w, w->R, false);
     if (!w->dworlds) return fail(w, UX_ERR_CUDA, "device allocation failed");
     CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice, w->stream));
@@ -2293,6 +2349,7 @@ static int extend_vehicles(ux_world *w) {
     int N = (int)w->nodes.size(), T = w->total_ts, start_ts = w->timestep;
     long long P0 = w->P_uploaded, P = (long long)w->vehs.size();
     if (!w->rep_routes.empty()) return fail(w, UX_ERR_RUNTIME, "adding vehicles to a world with per-replica routes is not supported");
+    w->rewindable = false;  // the per-platoon arrays move out of the recorded dynamic region
     for (long long i = P0; i < P; i++) if (w->dest_row[w->vehs[i].dest] < 0)
         return fail(w, UX_ERR_RUNTIME, "vehicle %lld added after the start has destination node %d, which had no demand before: set UX_OPT_ALL_DESTINATIONS "
                     "(World(..., all_destinations=True)) before the first exec_simulation", i, w->vehs[i].dest);
@@ -2743,9 +2800,9 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta_p->route_off.size(); dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_LINKS: n = (int64_t)w->dta_p->links.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
-    case UX_A_DTA_RS_LINKS: n = 0; for (auto &r : w->swaps) n = std::max(n, (int64_t)r.rs_links.size()); dt = UX_DT_I32; break;  // upper bound over the replicas
-    case UX_A_DTA_RA_LINKS: n = 0; for (auto &r : w->swaps) n = std::max(n, (int64_t)r.ra_links.size()); dt = UX_DT_I32; break;
-    case UX_A_DTA_RA_ENTRY_T: n = 0; for (auto &r : w->swaps) n = std::max(n, (int64_t)r.ra_entry_t.size()); break;
+    case UX_A_DTA_RS_LINKS: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.rs_off.back()); dt = UX_DT_I32; break;  // upper bound over the replicas
+    case UX_A_DTA_RA_LINKS: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.ra_off.back()); dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_ENTRY_T: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.ra_off.back()); break;
     case UX_A_DTA_COST_ACTUAL: case UX_A_DTA_T_GAP: n = P; break;
     case UX_A_DTA_CHOICE: n = P; dt = UX_DT_I32; break;
     default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
@@ -2967,6 +3024,27 @@ UX_API int ux_dta_share_route_sets(ux_world *w, ux_world *from) {
     return 0;
 }
 
+// The link lists of a swap result stay on the device until somebody asks for them (a replica-batched solve never does).
+static int dta_fetch(ux_world *w, int r, bool want_rs, bool want_ra) {
+    auto &R = w->swaps[r];
+    long long P = (long long)R.ra_off.size() - 1;
+    if (want_rs && !R.rs_fetched) {
+        size_t n = (size_t)R.rs_off[P];
+        R.rs_links.resize(n);
+        if (n) CUDA_OK(cudaMemcpy(R.rs_links.data(), w->next_routes[r].links, 4 * n, cudaMemcpyDeviceToHost));
+        R.rs_fetched = true; w->d2h_bytes += (long long)(4 * n);
+    }
+    if (want_ra && !R.ra_fetched) {
+        size_t n = (size_t)R.ra_off[P];
+        std::vector<int> tt(n);
+        R.ra_links.resize(n); R.ra_entry_t.resize(n);
+        if (n) { CUDA_OK(cudaMemcpy(R.ra_links.data(), R.d_tr_link, 4 * n, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(tt.data(), R.d_tr_t, 4 * n, cudaMemcpyDeviceToHost)); }
+        for (size_t i = 0; i < n; i++) R.ra_entry_t[i] = (double)tt[i] * w->dt;
+        R.ra_fetched = true; w->d2h_bytes += (long long)(8 * n);
+    }
+    return 0;
+}
+
 // World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_solver.cpp:130-373).  replica == -1: every replica of
 // the world in the same launches (replica r draws its candidates from mt19937(rng_seed + r)).
 UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
@@ -2981,8 +3059,10 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     const int nr = (int)reps.size();
     const long long P = w->hw[0].P; const int L = w->hw[0].L, T = w->hw[0].T;
     DtaStore &S = *w->dta_p;
-    w->swaps.resize(w->R);
+    w->swaps.resize(w->R); w->next_routes.resize(w->R);
+    for (int r = 0; r < w->R; r++) if (w->swaps[r].valid) { int rc = dta_fetch(w, r, true, true); if (rc) return rc; }  // results about to lose their device backing
     for (int r : reps) w->swaps[r].valid = false;
+    if (w->swap_buf) { cudaFree(w->swap_buf); w->swap_buf = nullptr; }
     if (!S.d_block || S.device != w->device) {  // the store goes to the device once per solve
         if (S.d_block) { cudaSetDevice(S.device); cudaFree(S.d_block); S.d_block = nullptr; cudaSetDevice(w->device); }
         size_t b0 = (4 * S.o.size() + 255) & ~(size_t)255, b1 = (4 * S.links.size() + 255) & ~(size_t)255, b2 = (8 * S.od_off.size() + 255) & ~(size_t)255,
@@ -3020,10 +3100,12 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     size_t bytes = 0;
     auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
     const size_t o_tt = carve(8 * TL * nr), o_ext = carve(mode == 1 ? 8 * TL * nr : 0), o_troff = carve(8 * (size_t)nr * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(nP),
-                 o_pair = carve(4 * nP), o_draw = carve(nP), o_ca = carve(8 * nP), o_tg = carve(8 * nP), o_ch = carve(4 * nP), o_pot = carve(nP), o_dd = carve(sizeof(DtaDev) * nr);
+                 o_pair = carve(4 * nP), o_draw = carve(nP), o_ca = carve(8 * nP), o_tg = carve(8 * nP), o_ch = carve(4 * nP), o_pot = carve(nP), o_dd = carve(sizeof(DtaDev) * nr),
+                 o_len = carve(4 * nP), o_gg = carve(sizeof(DtaGather) * nr);
     char *buf = nullptr;
     CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
-    auto release = [&](int rc) { cudaFree(buf); return rc; };
+    w->swap_buf = buf;
+    auto release = [&](int rc) { if (rc) { cudaFree(buf); w->swap_buf = nullptr; } return rc; };
     std::vector<DtaDev> hd(nr);
     for (int q = 0; q < nr; q++) {
         DtaDev &D = hd[q];
@@ -3065,54 +3147,103 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     if (nP) {
         cudaMemcpyAsync(buf + o_fs, flag.data(), nP, cudaMemcpyHostToDevice, st);
         UX_LAUNCH(k_dta_swap, dim3((unsigned)((P + DTA_WARPS - 1) / DTA_WARPS), nr), dim3(32 * DTA_WARPS), st, w->dworlds, d_dd);
+        UX_LAUNCH(k_dta_rs_len, dim3((unsigned)((P + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd, (int *)(buf + o_len));
     }
 #ifndef UX_EMU
     cudaEventRecord(e1, st);
 #endif
-    std::vector<int> choice(nP), tr_l(ne), tr_t(ne); std::vector<double> cost(nP), gap(nP); std::vector<unsigned char> pot(nP, 0);
+    std::vector<int> choice(nP), lens(nP); std::vector<double> cost(nP), gap(nP); std::vector<unsigned char> pot(nP, 0);
     if (nP) {
         cudaMemcpyAsync(choice.data(), buf + o_ch, 4 * nP, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(cost.data(), buf + o_ca, 8 * nP, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(gap.data(), buf + o_tg, 8 * nP, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(pot.data(), buf + o_pot, nP, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(lens.data(), buf + o_len, 4 * nP, cudaMemcpyDeviceToHost, st);
     }
-    if (ne) { cudaMemcpyAsync(tr_l.data(), buf + o_trl, 4 * ne, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(tr_t.data(), buf + o_trt, 4 * ne, cudaMemcpyDeviceToHost, st); }
     if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route swap: %s", cudaGetErrorString(cudaGetLastError())));
 #ifndef UX_EMU
     { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); w->swap_ms = ms; cudaEventDestroy(e0); cudaEventDestroy(e1); }
 #endif
-    w->d2h_bytes += (long long)(nP * (4 + 8 + 8 + 1 + 1 + 4) + ne * 8);
+    w->d2h_bytes += (long long)(nP * (4 + 8 + 8 + 1 + 1 + 4 + 4));
     w->h2d_bytes += (long long)(nP * 9 + 8 * nr);
+    std::vector<DtaGather> hg(nr);
+    std::vector<int> off32((size_t)nr * (P + 1), 0);
     for (int q = 0; q < nr; q++) {
         auto &R = w->swaps[reps[q]];
         const long long *off = tr_off.data() + (size_t)q * (P + 1);
-        const size_t nq = (size_t)off[P];
         R.ra_off.assign(off, off + P + 1);
-        R.ra_links.assign(tr_l.begin() + ev_base[q], tr_l.begin() + ev_base[q] + nq);
-        R.ra_entry_t.resize(nq);
-        for (size_t i = 0; i < nq; i++) R.ra_entry_t[i] = (double)tr_t[ev_base[q] + i] * w->dt;
+        R.d_tr_link = (const int *)(buf + o_trl) + ev_base[q]; R.d_tr_t = (const int *)(buf + o_trt) + ev_base[q];
+        R.ra_links.clear(); R.ra_entry_t.clear(); R.rs_links.clear(); R.rs_fetched = R.ra_fetched = false;
         R.choice.assign(choice.begin() + (size_t)q * P, choice.begin() + (size_t)(q + 1) * P);
         R.cost_actual.assign(cost.begin() + (size_t)q * P, cost.begin() + (size_t)(q + 1) * P);
         R.t_gap.assign(gap.begin() + (size_t)q * P, gap.begin() + (size_t)(q + 1) * P);
         const unsigned char *pt = pot.data() + (size_t)q * P;
-        // totals in platoon order (sequential sums of dta_solver.cpp:243-252) and the next iteration's routes
+        const int *ln = lens.data() + (size_t)q * P;
+        int *o32 = off32.data() + (size_t)q * (P + 1);
+        // totals in platoon order (sequential sums of dta_solver.cpp:243-252) and the offsets of the next iteration's routes
         R.n_swap = 0; R.potential_n_swap = 0; R.total_t_gap = 0;
         R.rs_off.assign(P + 1, 0);
         for (long long i = 0; i < P; i++) {
-            int c = R.choice[i];
             if (pt[i]) R.potential_n_swap += w->p.delta_n;
             R.total_t_gap += R.t_gap[i];
-            if (c >= 0 && pt[i]) R.n_swap += w->p.delta_n;  // a forced external route has pot == 0
-            long long len = c == -2 ? 0 : c == -1 ? R.ra_off[i + 1] - R.ra_off[i] : S.route_off[c + 1] - S.route_off[c];
-            R.rs_off[i + 1] = R.rs_off[i] + len;
+            if (R.choice[i] >= 0 && pt[i]) R.n_swap += w->p.delta_n;  // a forced external route has pot == 0
+            R.rs_off[i + 1] = R.rs_off[i] + ln[i];
+            o32[i + 1] = (int)R.rs_off[i + 1];
         }
-        R.rs_links.resize((size_t)R.rs_off[P]);
-        for (long long i = 0; i < P; i++) {
-            int c = R.choice[i]; long long len = R.rs_off[i + 1] - R.rs_off[i];
-            if (len > 0) memcpy(R.rs_links.data() + R.rs_off[i], c == -1 ? R.ra_links.data() + R.ra_off[i] : S.links.data() + S.route_off[c], sizeof(int) * (size_t)len);
+        if (R.rs_off[P] > 0x7fffffff) return release(fail(w, UX_ERR_CAPACITY, "more than 2^31 route entries (replica %d)", reps[q]));
+        auto &NR = w->next_routes[reps[q]];
+        NR.ready = false;
+        if (!NR.off) { if (cudaMalloc((void **)&NR.off, 4 * (size_t)(P + 1)) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "device allocation failed (next-day routes)")); }
+        size_t need = (size_t)R.rs_off[P] + 1;
+        if (need > NR.cap) {
+            if (NR.links) cudaFree(NR.links);
+            NR.cap = need + need / 4; NR.links = nullptr;
+            if (cudaMalloc((void **)&NR.links, 4 * NR.cap) != cudaSuccess) { NR.cap = 0; return release(fail(w, UX_ERR_CUDA, "device allocation failed (next-day routes)")); }
         }
+        cudaMemcpyAsync(NR.off, o32, 4 * (size_t)(P + 1), cudaMemcpyHostToDevice, st);
+        hg[q].off = NR.off; hg[q].links = NR.links;
         R.replica = reps[q]; R.valid = true;
         w->swap_last = reps[q];
     }
+    if (nP) {  // the next day's enforced routes, assembled on the device
+        cudaMemcpyAsync(buf + o_gg, hg.data(), sizeof(DtaGather) * nr, cudaMemcpyHostToDevice, st);
+        UX_LAUNCH(k_dta_rs_gather, dim3((unsigned)((P * 8 + 255) / 256), nr), dim3(256), st, w->dworlds, d_dd, (const DtaGather *)(buf + o_gg));
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error assembling the next-day routes: %s", cudaGetErrorString(cudaGetLastError())));
+    for (int q = 0; q < nr; q++) w->next_routes[reps[q]].ready = true;
+    w->h2d_bytes += (long long)(4 * off32.size());
     return release(0);
+}
+
+
+// Rewind a finished world to t = 0 for the next day of a day-to-day solve: the per-replica dynamic state is re-initialised in
+// place (zero + the recorded non-zero initial values), every replica that has a route-swap result gets its routes_specified
+// as enforced routes straight from device memory, and the static network, the platoon tables and the captured graphs stay.
+// Equivalent to building a new world, enforcing the routes and running it -- without the rebuild.
+UX_API int ux_dta_next_day(ux_world *w) {
+    if (!w->uploaded) return fail(w, UX_ERR_RUNTIME, "dta_next_day needs a finished run");
+    if (!w->rewindable) return fail(w, UX_ERR_RUNTIME, "this world cannot be rewound (vehicles were added after the start)");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (size_t i = w->dyn_slab0; i <= w->dyn_slab1 && i < w->slabs.size(); i++) {
+        size_t a0 = i == w->dyn_slab0 ? w->dyn_used0 : 0, a1 = i == w->dyn_slab1 ? w->dyn_used1 : w->slabs[i].used;
+        if (a1 > a0) CUDA_OK(cudaMemsetAsync(w->slabs[i].base + a0, 0, a1 - a0, st));
+    }
+    for (auto &ri : w->reinit) {
+        if (ri.kind == 0) cudaMemsetAsync(ri.dst, 0xff, ri.bytes, st);
+        else if (ri.kind == 1) { long long n = (long long)(ri.bytes / 8); UX_LAUNCH(k_fill_f64, dim3((unsigned)((n + 255) / 256)), dim3(256), st, (double *)ri.dst, n, -1.0); }
+        else cudaMemcpyAsync(ri.dst, ri.src->data(), ri.bytes, cudaMemcpyHostToDevice, st);
+    }
+    for (int r = 0; r < w->R && r < (int)w->next_routes.size(); r++) {
+        auto &NR = w->next_routes[r];
+        if (!NR.ready) continue;
+        DevWorld &d = w->hw[r];
+        d.vl_off[0] = d.vl_off[1] = NR.off; d.vl_list[0] = d.vl_list[1] = NR.links;
+    }
+    CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    w->timestep = 0;
+    w->logs.replica = -1;
+    return 0;
 }
 
 static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
@@ -3122,6 +3253,7 @@ static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int6
     if (what >= UX_A_DTA_RS_OFFSETS) {
         if (replica < 0 || replica >= (int)w->swaps.size() || !w->swaps[replica].valid) return fail(w, UX_ERR_RUNTIME, "no route swap result for replica %d", replica);
         auto &r = w->swaps[replica];
+        { int rc = dta_fetch(w, replica, what == UX_A_DTA_RS_LINKS, what == UX_A_DTA_RA_LINKS || what == UX_A_DTA_RA_ENTRY_T); if (rc) return rc; }
         switch (what) {
         case UX_A_DTA_RS_OFFSETS: src = r.rs_off.data(); break;
         case UX_A_DTA_RA_OFFSETS: src = r.ra_off.data(); break;

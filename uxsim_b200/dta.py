@@ -273,24 +273,23 @@ class DayToDayEnsemble:
         dn = sc.deltan
         shape = (R, max_iter)
         self.ttts, self.n_swaps, self.potential_swaps, self.t_gaps, self.trips = (np.zeros(shape) for _ in range(5))
-        prev = [None] * R
         E = None
         for day in range(max_iter):
             t0 = time.perf_counter()
-            E = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, device=self.device,
-                                      random_seed=self.base_seed, **self.world_over)
-            E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
-            E.dta_share_route_sets(E0)
-            for r in range(R):
-                if prev[r] is not None:
-                    E.dta_enforce_routes(r, *prev[r])
+            if E is None:   # day 0: build the world once; later days rewind it in place (routes stay on the device)
+                E = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, device=self.device,
+                                          random_seed=self.base_seed, **self.world_over)
+                E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
+                E.dta_share_route_sets(E0)
+            else:
+                E.dta_next_day()
             t1 = time.perf_counter()
             E.main_loop()
             t2 = time.perf_counter()
             day_seed = (swap_seed * 1000003 + day * 65537) & 0x3FFFFFFF   # chain r draws its swap candidates from day_seed + r
-            results = E.dta_route_swap_all(self.mode, swap_prob, day_seed)   # every chain's swap in the same launches
+            last = day == max_iter - 1
+            results = E.dta_route_swap_all(self.mode, swap_prob, day_seed, routes=last)   # every chain's swap in the same launches
             for r, res in enumerate(results):
-                prev[r] = (res["rs_link_ids"], res["rs_offsets"])
                 tt = E.get_array(C.A_VEH_TRAVEL_TIME, r)
                 done = tt >= 0
                 self.ttts[r, day] = float(tt[done].sum()) * dn
@@ -299,8 +298,9 @@ class DayToDayEnsemble:
                 self.t_gaps[r, day] = res["total_t_gap"] / max(1, len(tt))
             t3 = time.perf_counter()
             self.day_seconds.append((t1 - t0, t2 - t1, t3 - t2))
-            if day != max_iter - 1 or not keep_last_world:
-                E.close()
-        self.routes = prev
+        self.routes = [(res["rs_link_ids"], res["rs_offsets"]) for res in results]
+        if not keep_last_world:
+            E.close()
+            E = None
         E0.close()
         return E if keep_last_world else None

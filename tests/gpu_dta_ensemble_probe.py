@@ -18,6 +18,6 @@ tot = time.perf_counter() - t0
 ds = np.array(ens.day_seconds)
 print(json.dumps({"workload": wl, "chains": R, "days": days, "k": k, "total_s": tot,
                   "day_ms_build_enforce": ds[1:, 0].mean() * 1e3, "day_ms_simulation": ds[1:, 1].mean() * 1e3, "day_ms_route_swaps": ds[1:, 2].mean() * 1e3,
-                  "chain_days_per_s": R / ds[1:].sum(axis=1).mean(),
+                  "chain_days_per_s": R / ds[1:].sum(axis=1).mean(), "swap_device_ms_last": ens.swap_device_ms[-1],
                   "mean_ttt_by_day": ens.ttts.mean(axis=0).tolist(), "mean_gap_by_day": ens.t_gaps.mean(axis=0).tolist(),
                   "trips_last_day_mean": ens.trips[:, -1].mean()}))

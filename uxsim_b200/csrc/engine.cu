@@ -1349,17 +1349,21 @@ __global__ void k_transpose(const T *src, T *dst, int rows, int cols) {
 }
 
 // Link::ensure_traveltime_real (traffi.cpp:631-648): position i takes the value of the latest event whose entry step <= i.
+UX_DEV void tt_actual_link(const DevWorld &W, int l, double *out) {
+    double cur = W.l_length[l] / W.l_vmax[l];
+    int best = 0;
+#pragma unroll 8
+    for (int i = 0; i < W.T; i++) {  // the loads do not depend on the running arg-max, so they pipeline
+        int ord = W.ev_ord[(size_t)i * W.L + l];
+        double v = W.ev_tt[(size_t)i * W.L + l];
+        if (ord > best) { best = ord; cur = v; }
+        out[(size_t)l * W.T + i] = cur;
+    }
+}
 __global__ void k_tt_actual(const DevWorld *worlds, int replica, double *out) {
     const DevWorld &W = worlds[replica];
     int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (l >= W.L) return;
-    double cur = W.l_length[l] / W.l_vmax[l];
-    int best = 0;
-    for (int i = 0; i < W.T; i++) {
-        int ord = W.ev_ord[(size_t)i * W.L + l];
-        if (ord > best) { best = ord; cur = W.ev_tt[(size_t)i * W.L + l]; }
-        out[(size_t)l * W.T + i] = cur;
-    }
+    if (l < W.L) tt_actual_link(W, l, out);
 }
 
 // order the RUN records per platoon and by time: record (vid, t) goes to off[vid] + (t - gen_ts[vid])
@@ -1427,6 +1431,14 @@ struct DtaDev {
     int *pair; unsigned char *draws;       // k_dta_prepare -> host RNG -> k_dta_swap
     double *cost_actual, *t_gap; int *choice; unsigned char *pot;
 };
+
+// traveltime_actual tables of several replicas in one launch (blockIdx.y = entry of dd)
+__global__ void k_dta_tt_actual(const DevWorld *worlds, const DtaDev *dd) {
+    const DtaDev &D = dd[blockIdx.y];
+    const DevWorld &W = worlds[D.replica];
+    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (l < W.L) tt_actual_link(W, l, const_cast<double *>(D.tt));
+}
 
 // link-entry events -> per-platoon CSR (position = offset + ordinal of the link on the platoon's route)
 __global__ void k_dta_scatter(const DevWorld *worlds, const DtaDev *dd) {
@@ -3060,8 +3072,8 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     const long long P = w->hw[0].P; const int L = w->hw[0].L, T = w->hw[0].T;
     DtaStore &S = *w->dta_p;
     w->swaps.resize(w->R); w->next_routes.resize(w->R);
-    for (int r = 0; r < w->R; r++) if (w->swaps[r].valid) { int rc = dta_fetch(w, r, true, true); if (rc) return rc; }  // results about to lose their device backing
     for (int r : reps) w->swaps[r].valid = false;
+    for (int r = 0; r < w->R; r++) if (w->swaps[r].valid) { int rc = dta_fetch(w, r, false, true); if (rc) return rc; }  // other replicas' results lose their device backing
     if (w->swap_buf) { cudaFree(w->swap_buf); w->swap_buf = nullptr; }
     if (!S.d_block || S.device != w->device) {  // the store goes to the device once per solve
         if (S.d_block) { cudaSetDevice(S.device); cudaFree(S.d_block); S.d_block = nullptr; cudaSetDevice(w->device); }
@@ -3124,7 +3136,7 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     cudaMemcpyAsync(buf + o_dd, hd.data(), sizeof(DtaDev) * nr, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(buf + o_troff, tr_off.data(), 8 * tr_off.size(), cudaMemcpyHostToDevice, st);
     if (max_ev) UX_LAUNCH(k_dta_scatter, dim3((unsigned)((max_ev + 255) / 256), nr), dim3(256), st, w->dworlds, d_dd);
-    if (L > 0) for (int q = 0; q < nr; q++) UX_LAUNCH(k_tt_actual, dim3((L + 127) / 128), dim3(128), st, w->dworlds, reps[q], const_cast<double *>(hd[q].tt));
+    if (L > 0) UX_LAUNCH(k_dta_tt_actual, dim3((L + 63) / 64, nr), dim3(64), st, w->dworlds, d_dd);
     if (mode == 1 && TL) UX_LAUNCH(k_dta_externality, dim3((unsigned)((TL + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd);
     if (P) UX_LAUNCH(k_dta_prepare, dim3((unsigned)((P + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd);
     // swap candidates: the reference's own stream, std::mt19937(rng_seed) + uniform_real_distribution (dta_solver.cpp:148-149, 265-283)

@@ -262,7 +262,8 @@ class DayToDayEnsemble:
         self.scenario, self.R, self.mode = scenario, int(n_replicas), {"DUE": 0, "DSO": 1}[mode]
         self.base_seed, self.device, self.api, self.world_over = int(base_seed), device, api or C.load_product(), world_over
         self.ttts = self.n_swaps = self.potential_swaps = self.t_gaps = self.trips = None
-        self.day_seconds = []      # per day: (build + enforce, simulation, route swaps) wall seconds
+        self.day_seconds = []      # per day: (build or rewind, simulation, route swaps) wall seconds
+        self.swap_device_ms = []   # per day: device time of the batched route-swap kernels
         self.routes = None         # per chain: (link ids, offsets) enforced on the next day
 
     def solve(self, max_iter, n_routes_per_od=10, swap_prob=0.05, enum_seed=12345, swap_seed=0, keep_last_world=False):
@@ -298,6 +299,7 @@ class DayToDayEnsemble:
                 self.t_gaps[r, day] = res["total_t_gap"] / max(1, len(tt))
             t3 = time.perf_counter()
             self.day_seconds.append((t1 - t0, t2 - t1, t3 - t2))
+            self.swap_device_ms.append(E.get_double(C.D_DTA_SWAP_MS))
         self.routes = [(res["rs_link_ids"], res["rs_offsets"]) for res in results]
         if not keep_last_world:
             E.close()

@@ -278,7 +278,7 @@ def main():
         E.main_loop()
         stats = reduce_stats(E)
         host_stats = stats.cpu()
-        res = [(E.get_array(C.A_VEH_ARRIVAL_TS, r), E.get_array(C.A_VEH_TRAVEL_TIME, r), E.get_array(C.A_LINK_STAT_COUNT, r)) for r in range(R)]
+        res = (E.get_array_all(C.A_VEH_ARRIVAL_TS), E.get_array_all(C.A_VEH_TRAVEL_TIME), E.get_array_all(C.A_LINK_STAT_COUNT))  # [R, n] each, one transfer each
         curves = (E.get_array(C.A_CUM_ARRIVAL, 0), E.get_array(C.A_CUM_DEPARTURE, 0))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -287,7 +287,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         if i >= args.warmup:
-            upd = sum(int(x[2].sum()) for x in res)
+            upd = int(res[2].sum())
             if world > 1:
                 t = torch.tensor([upd], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t)

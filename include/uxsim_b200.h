@@ -301,6 +301,8 @@ UX_API int64_t UX_FN(array_size)(ux_world *w, int what, int *dtype_out);
 /* Copy an array result of `replica` into host memory (the reference's "owned numpy copy" getters,
  * bindings.cpp:26-42).  `capacity` in elements.  Returns elements written or an error code. */
 UX_API int64_t UX_FN(get_array)(ux_world *w, int what, int replica, void *dst, int64_t capacity);
+/* CUDA build: replica == -1 copies the per-replica state arrays UX_A_VEH_ARRIVAL_TS / VEH_TRAVEL_TIME / VEH_LINK /
+ * LINK_STAT_COUNT / NODE_SIGNAL_* / LINK_CAPACITY_*_REMAIN of ALL replicas, replica-major [R][n], in one transfer. */
 /* Borrowed DEVICE pointer to an array result (CUDA build only; used to wrap results as torch tensors
  * without a host copy).  Returns elements or an error code. */
 UX_API int64_t UX_FN(get_device_array)(ux_world *w, int what, int replica, void **dptr_out, int *dtype_out);

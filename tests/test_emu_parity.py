@@ -2,6 +2,7 @@
 (kernels run as loops over blocks/threads) must be bit-identical to the oracle.  This is a debugging aid for the
 GPU-less container; the GPU parity tests proper are tests/test_gpu_parity.py.  The emulation library is test
 infrastructure and is never loaded by the package."""
+import numpy as np
 import pytest
 
 from uxsim_b200 import _capi as C
@@ -50,3 +51,18 @@ def test_emulated_vehicle_logs_match_oracle(name, mk, emu_api, oracle_api):
     assert compare_logs(Ee, Eo) == []
     Ee.main_loop(), Eo.main_loop()
     assert compare_logs(Ee, Eo) == [] and compare_engines(Ee, Eo) == []
+
+
+def test_all_replica_getter_matches_per_replica(emu_api):
+    """get_array(replica=-1): [R, n] in one transfer == the per-replica getters."""
+    from uxsim_b200 import _capi as C
+    from uxsim_b200 import scenario as S
+
+    E = S.grid(4, seed=1).to_engine(emu_api, vehicle_logging_timestep_interval=-1, num_replicas=3, random_seed=7)
+    E.main_loop()
+    for what in (C.A_VEH_ARRIVAL_TS, C.A_VEH_TRAVEL_TIME, C.A_LINK_STAT_COUNT, C.A_VEH_LINK, C.A_LINK_CAPACITY_IN_REMAIN):
+        allr = E.get_array_all(what)
+        assert allr.shape[0] == 3
+        for r in range(3):
+            assert np.array_equal(allr[r], E.get_array(what, r)), what
+    E.close()

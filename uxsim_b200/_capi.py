@@ -381,6 +381,16 @@ class EngineWorld:
     def get_double(self, what: int) -> float:
         return float(self.api.get_double(self.h, int(what)))
 
+    def get_array_all(self, what: int) -> np.ndarray:
+        """A per-replica state array of EVERY replica, shape ``[R, n]``, in one device->host transfer (CUDA engine)."""
+        dt = C.c_int(0)
+        n = self._check(self.api.array_size(self.h, int(what), C.byref(dt)))
+        R = self.get_int(I_NUM_REPLICAS)
+        out = np.empty((R, int(n)), dtype=_NP_DTYPE[dt.value])
+        if out.size:
+            self._check(self.api.get_array(self.h, int(what), -1, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
     def get_array(self, what: int, replica: int = 0) -> np.ndarray:
         dt = C.c_int(0)
         n = self._check(self.api.array_size(self.h, int(what), C.byref(dt)))

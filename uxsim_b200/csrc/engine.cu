@@ -3297,6 +3297,47 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         for (int64_t i = 0; i < P; i++) oi[i] = what == UX_A_VEH_ORIG ? w->vehs[i].orig : what == UX_A_VEH_DEST ? w->vehs[i].dest : w->vehs[i].ts;
         return P;
     }
+    if (replica == -1) {  // every replica's copy of a per-replica state array, replica-major, in ONE device->host transfer
+        const int R = w->R;
+        int dt0; int64_t n0 = ux_array_size(w, what, &dt0);
+        if (n0 < 0) return n0;
+        if (capacity < n0 * R) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)(n0 * R));
+        if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; }
+        cudaSetDevice(w->device);
+        if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
+        size_t es0 = dt0 == UX_DT_I32 ? 4 : 8, row = es0 * (size_t)n0;
+        std::vector<const void *> src(R, nullptr);
+        for (int r = 0; r < R; r++) {
+            const DevWorld &d = w->hw[r];
+            switch (what) {
+            case UX_A_VEH_ARRIVAL_TS: src[r] = d.v_arr_ts; break;
+            case UX_A_VEH_TRAVEL_TIME: src[r] = d.v_tt; break;
+            case UX_A_VEH_LINK: src[r] = d.v_link; break;
+            case UX_A_NODE_SIGNAL_PHASE: src[r] = d.sig_phase; break;
+            case UX_A_NODE_SIGNAL_T: src[r] = d.sig_t; break;
+            case UX_A_LINK_CAPACITY_IN_REMAIN: src[r] = d.cap_in_rem; break;
+            case UX_A_LINK_CAPACITY_OUT_REMAIN: src[r] = d.cap_out_rem; break;
+            default: break;
+            }
+        }
+        if (what == UX_A_LINK_STAT_COUNT) {  // i64 on the device, f64 in the ABI
+            int rc = ensure_scratch(w, 8 * (size_t)n0 * R + 16); if (rc) return rc;
+            for (int r = 0; r < R; r++) cudaMemcpyAsync((char *)w->d_scratch + row * r, w->hw[r].stat_count, row, cudaMemcpyDeviceToDevice, w->stream);
+            std::vector<long long> h((size_t)n0 * R);
+            if (n0 * R) CUDA_OK(cudaMemcpyAsync(h.data(), w->d_scratch, row * R, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_OK(cudaStreamSynchronize(w->stream));
+            double *o = (double *)dst;
+            for (size_t i = 0; i < h.size(); i++) o[i] = (double)h[i];
+        } else {
+            if (!src[0]) return fail(w, UX_ERR_INVALID, "array %d cannot be fetched for all replicas at once", what);
+            int rc = ensure_scratch(w, row * R + 16); if (rc) return rc;
+            for (int r = 0; r < R; r++) cudaMemcpyAsync((char *)w->d_scratch + row * r, src[r], row, cudaMemcpyDeviceToDevice, w->stream);
+            if (n0 * R) CUDA_OK(cudaMemcpyAsync(dst, w->d_scratch, row * R, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_OK(cudaStreamSynchronize(w->stream));
+        }
+        w->d2h_bytes += (long long)(row * R);
+        return n0 * R;
+    }
     void *dptr = nullptr; int dt = 0;
     int64_t n = device_array(w, what, replica, &dptr, &dt);
     if (n < 0) return n;

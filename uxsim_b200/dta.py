@@ -290,8 +290,9 @@ class DayToDayEnsemble:
             day_seed = (swap_seed * 1000003 + day * 65537) & 0x3FFFFFFF   # chain r draws its swap candidates from day_seed + r
             last = day == max_iter - 1
             results = E.dta_route_swap_all(self.mode, swap_prob, day_seed, routes=last)   # every chain's swap in the same launches
+            tt_all = E.get_array_all(C.A_VEH_TRAVEL_TIME)
             for r, res in enumerate(results):
-                tt = E.get_array(C.A_VEH_TRAVEL_TIME, r)
+                tt = tt_all[r]
                 done = tt >= 0
                 self.ttts[r, day] = float(tt[done].sum()) * dn
                 self.trips[r, day] = int(done.sum()) * dn

@@ -14,8 +14,9 @@ for it in range(4):
     E = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, random_seed=it); t.append(time.perf_counter())
     E.get_array(C.A_LINK_NUM_VEHICLES); t.append(time.perf_counter())
     E.main_loop(); t.append(time.perf_counter())
-    res = [(E.get_array(C.A_VEH_ARRIVAL_TS, r), E.get_array(C.A_VEH_TRAVEL_TIME, r), E.get_array(C.A_LINK_STAT_COUNT, r)) for r in range(R)]; t.append(time.perf_counter())
+    st = E.ensemble_link_stats(); t.append(time.perf_counter())
+    res = (E.get_array_all(C.A_VEH_ARRIVAL_TS), E.get_array_all(C.A_VEH_TRAVEL_TIME), E.get_array_all(C.A_LINK_STAT_COUNT)); t.append(time.perf_counter())
     curves = (E.get_array(C.A_CUM_ARRIVAL, 0), E.get_array(C.A_CUM_DEPARTURE, 0)); t.append(time.perf_counter())
     eng = "upload %.1f graph-build %.1f loop-wall %.1f loop-device %.1f" % tuple(E.get_double(k) for k in (C.D_UPLOAD_MS, C.D_GRAPH_BUILD_MS, C.D_LAST_LOOP_WALL_MS, C.D_LAST_LOOP_MS))
     E.close(); t.append(time.perf_counter())
-    print(f"{wl} R={R} total {(t[-1]-t[0])*1e3:.1f} ms | ingest, upload, main_loop, readback, curves, close = " + " ".join(f"{(b-a)*1e3:.1f}" for a, b in zip(t, t[1:])) + " | engine: " + eng, flush=True)
+    print(f"{wl} R={R} total {(t[-1]-t[0])*1e3:.1f} ms | ingest, upload, main_loop, link stats, readback, curves, close = " + " ".join(f"{(b-a)*1e3:.1f}" for a, b in zip(t, t[1:])) + " | engine: " + eng, flush=True)

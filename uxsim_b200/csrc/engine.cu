@@ -1393,28 +1393,35 @@ __global__ void k_veh_snapshot(const DevWorld *worlds, int replica, double *vx, 
     }
 }
 
-// per-link ensemble statistics over this world's replicas: {volume, sum tt_actual, sum tt_actual^2, platoons on link}
-__global__ void k_ensemble_stats(const DevWorld *worlds, int R, double *out) {
+// per-link ensemble statistics over this world's replicas: {volume, sum tt_actual, sum tt_actual^2, platoons on link}.
+// Stage 1: thread per (link, replica) walks that replica's travel-time event table; stage 2: thread per link adds the
+// replicas in index order (deterministic sums).
+__global__ void k_ensemble_partial(const DevWorld *worlds, double *part) {
+    const DevWorld &W = worlds[blockIdx.y];
     int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (l >= worlds[0].L) return;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int r = 0; r < R; r++) {  // fixed replica order: deterministic sums
-        const DevWorld &W = worlds[r];
-        int T = W.T, L = W.L;
-        double cur = W.l_length[l] / W.l_vmax[l], s1 = 0, s2 = 0;
-        int best = 0;
-        for (int i = 0; i < T; i++) {
-            int ord = W.ev_ord[(size_t)i * L + l];
-            if (ord > best) { best = ord; cur = W.ev_tt[(size_t)i * L + l]; }
-            s1 += cur; s2 += cur * cur;
-        }
-        a0 += T > 0 ? W.cum_arr[(size_t)(T - 1) * L + l] : 0.0;
-        a1 += s1; a2 += s2;
-        a3 += (double)(W.tail[l] - W.head[(*W.t_base & 1) * L + l]);
+    int T = W.T, L = W.L;
+    if (l >= L) return;
+    double cur = W.l_length[l] / W.l_vmax[l], s1 = 0, s2 = 0;
+    int best = 0;
+#pragma unroll 8
+    for (int i = 0; i < T; i++) {
+        int ord = W.ev_ord[(size_t)i * L + l];
+        double v = W.ev_tt[(size_t)i * L + l];
+        if (ord > best) { best = ord; cur = v; }
+        s1 += cur; s2 += cur * cur;
     }
-    out[l * 4 + 0] = a0; out[l * 4 + 1] = a1; out[l * 4 + 2] = a2; out[l * 4 + 3] = a3;
+    double *o = part + ((size_t)blockIdx.y * L + l) * 4;
+    o[0] = T > 0 ? W.cum_arr[(size_t)(T - 1) * L + l] : 0.0; o[1] = s1; o[2] = s2;
+    o[3] = (double)(W.tail[l] - W.head[(*W.t_base & 1) * L + l]);
 }
-
+__global__ void k_ensemble_stats(const DevWorld *worlds, int R, const double *part, double *out) {
+    int L = worlds[0].L;
+    int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= L * 4) return;
+    double a = 0;
+    for (int r = 0; r < R; r++) a += part[(size_t)r * L * 4 + i];  // fixed replica order
+    out[i] = a;
+}
 
 // =====================================================================================================
 // DTA solver batch operations: route swap of dta_solver.cpp:130-373 on the device.
@@ -3394,7 +3401,11 @@ UX_API int64_t ux_ensemble_link_stats_device(ux_world *w, void **dptr) {
     cudaSetDevice(w->device);
     int L = (int)w->links.size();
     if (!w->d_ens) w->d_ens = dalloc<double>(w, (size_t)L * 4);
-    if (L > 0) UX_LAUNCH(k_ensemble_stats, dim3((L + 127) / 128), dim3(128), w->stream, w->dworlds, w->R, w->d_ens);
+    if (L > 0) {
+        int rc = ensure_scratch(w, 8 * (size_t)L * 4 * w->R + 16); if (rc) return rc;
+        UX_LAUNCH(k_ensemble_partial, dim3((L + 63) / 64, w->R), dim3(64), w->stream, w->dworlds, w->d_scratch);
+        UX_LAUNCH(k_ensemble_stats, dim3((L * 4 + 127) / 128), dim3(128), w->stream, w->dworlds, w->R, (const double *)w->d_scratch, w->d_ens);
+    }
     CUDA_OK(cudaStreamSynchronize(w->stream));
     *dptr = w->d_ens;
     return (int64_t)L * 4;

@@ -69,3 +69,42 @@ def test_two_rank_allreduce_equals_serial(tmp_path, oracle_api):
         st = E.ensemble_link_stats()
         ref = st if ref is None else ref + st
     assert np.array_equal(got.reshape(ref.shape), ref)
+
+
+DTA_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch.distributed as dist
+    from uxsim_b200 import _capi as C, scenario as S
+    from uxsim_b200.dta import DayToDayEnsemble
+    dist.init_process_group("gloo")
+    api = C.CApi(os.path.join({root!r}, "tests", "emu", "_build", "libuxsim_emu.so"), "ux_")   # host emulation of the CUDA engine
+    ens = DayToDayEnsemble(S.dta_grid9(), 4, mode="DUE", base_seed=20, api=api)
+    assert len(ens.local) == 2
+    ens.solve(max_iter=3, n_routes_per_od=5, swap_prob=0.2)
+    ttts, gaps = ens.gather_traces()
+    if dist.get_rank() == 0:
+        np.savez(sys.argv[1], ttts=ttts, gaps=gaps, stats=ens.link_stats_sum)
+    dist.barrier()
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_day_to_day_ensemble_equals_single_process(tmp_path, emu_api):
+    """4 DUE chains over 2 ranks (2 replicas each) == the same 4 chains in one process: chains are independent, seeds and
+    swap seeds follow the global chain index, and the link statistics are all-reduced once at the end."""
+    from uxsim_b200.dta import DayToDayEnsemble
+
+    script = tmp_path / "dta_worker.py"
+    script.write_text(DTA_WORKER.format(root=ROOT))
+    out = tmp_path / "dta.npz"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                    "--master-port", str(port), str(script), str(out)], check=True, timeout=600, capture_output=True)
+    got = np.load(out)
+    ens = DayToDayEnsemble(S.dta_grid9(), 4, mode="DUE", base_seed=20, api=emu_api)
+    ens.solve(max_iter=3, n_routes_per_od=5, swap_prob=0.2)
+    assert np.array_equal(got["ttts"], ens.ttts) and np.array_equal(got["gaps"], ens.t_gaps)
+    assert np.allclose(got["stats"], ens.link_stats_sum, rtol=1e-12)   # sum over ranks re-associates the replica sum

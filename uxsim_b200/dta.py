@@ -259,8 +259,23 @@ class DayToDayEnsemble:
     """
 
     def __init__(self, scenario, n_replicas, mode="DUE", base_seed=0, device=-1, api=None, **world_over):
-        self.scenario, self.R, self.mode = scenario, int(n_replicas), {"DUE": 0, "DSO": 1}[mode]
-        self.base_seed, self.device, self.api, self.world_over = int(base_seed), device, api or C.load_product(), world_over
+        from .ensemble import shard_seeds
+
+        self.n_global = int(n_replicas)
+        self.rank, self.world_size = 0, 1
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        self.local = shard_seeds(self.n_global, self.rank, self.world_size)   # this rank's block of chains
+        if len(self.local) == 0:
+            raise ValueError(f"rank {self.rank} of {self.world_size} has no chain: use at least as many chains as ranks")
+        self.scenario, self.R, self.mode = scenario, len(self.local), {"DUE": 0, "DSO": 1}[mode]
+        self.base_seed, self.device, self.api, self.world_over = int(base_seed) + self.local.start, device, api or C.load_product(), world_over
+        self.link_stats_sum = None  # [L, 4] summed over the chains of ALL ranks after the last day (one all-reduce)
         self.ttts = self.n_swaps = self.potential_swaps = self.t_gaps = self.trips = None
         self.day_seconds = []      # per day: (build or rewind, simulation, route swaps) wall seconds
         self.swap_device_ms = []   # per day: device time of the batched route-swap kernels
@@ -287,7 +302,7 @@ class DayToDayEnsemble:
             t1 = time.perf_counter()
             E.main_loop()
             t2 = time.perf_counter()
-            day_seed = (swap_seed * 1000003 + day * 65537) & 0x3FFFFFFF   # chain r draws its swap candidates from day_seed + r
+            day_seed = ((swap_seed * 1000003 + day * 65537) & 0x3FFFFFFF) + self.local.start   # chain c draws its swap candidates from seed + c
             last = day == max_iter - 1
             results = E.dta_route_swap_all(self.mode, swap_prob, day_seed, routes=last)   # every chain's swap in the same launches
             tt_all = E.get_array_all(C.A_VEH_TRAVEL_TIME)
@@ -302,8 +317,35 @@ class DayToDayEnsemble:
             self.day_seconds.append((t1 - t0, t2 - t1, t3 - t2))
             self.swap_device_ms.append(E.get_double(C.D_DTA_SWAP_MS))
         self.routes = [(res["rs_link_ids"], res["rs_offsets"]) for res in results]
+        self.link_stats_sum = self._reduce_link_stats(E)
         if not keep_last_world:
             E.close()
             E = None
         E0.close()
         return E if keep_last_world else None
+
+    def _reduce_link_stats(self, E):
+        """Per-link {volume, sum tt, sum tt^2, platoons left} of the last day, summed over every chain of every rank: the
+        path's only exchange (NCCL all-reduce on the device buffer; gloo / no process group: host tensor)."""
+        import torch
+
+        from .ensemble import _CudaArrayView, allreduce_link_stats
+
+        L = E.get_int(C.I_NUM_LINKS)
+        if self.api.prefix == "ux_" and torch.cuda.is_available():
+            ptr = C.C.c_void_p(0)
+            n = E._check(self.api.ensemble_link_stats_device(E.h, C.C.byref(ptr)))
+            t = torch.as_tensor(_CudaArrayView(ptr.value, int(n), np.float64, E), device="cuda").clone()
+        else:
+            t = torch.from_numpy(E.ensemble_link_stats().reshape(-1).copy())
+        return allreduce_link_stats(t).cpu().numpy().reshape(L, 4)
+
+    def gather_traces(self):
+        """Total-travel-time and gap traces of all chains of all ranks, ``[n_global, days]`` (rank order = chain order)."""
+        if self.world_size == 1:
+            return self.ttts, self.t_gaps
+        import torch.distributed as dist
+
+        parts = [None] * self.world_size
+        dist.all_gather_object(parts, (self.ttts, self.t_gaps))
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])

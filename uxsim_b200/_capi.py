@@ -350,8 +350,8 @@ class EngineWorld:
         out = []
         for r in range(self.get_int(I_NUM_REPLICAS)):
             g = lambda a: self.get_array(a, r)
-            if not routes:
-                out.append({"cost_actual": g(A_DTA_COST_ACTUAL), "n_swap": self.get_double(D_DTA_N_SWAP_OF + r),
+            if not routes:  # scalars only: nothing per-platoon crosses the bus
+                out.append({"n_swap": self.get_double(D_DTA_N_SWAP_OF + r),
                             "potential_n_swap": self.get_double(D_DTA_N_SWAP_OF + 1000 + r), "total_t_gap": self.get_double(D_DTA_N_SWAP_OF + 2000 + r)})
                 continue
             out.append({"rs_link_ids": g(A_DTA_RS_LINKS), "rs_offsets": g(A_DTA_RS_OFFSETS), "ra_link_ids": g(A_DTA_RA_LINKS),

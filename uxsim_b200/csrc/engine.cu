@@ -1577,6 +1577,60 @@ __global__ void k_dta_rs_gather(const DevWorld *worlds, const DtaDev *dd, const 
     for (int j = sub; j < len; j += 8) G.links[o + j] = src[j];
 }
 
+// exclusive scan of n ints (block per job): out[0] = 0 ... out[n] = total; used for the traversal counts and the route lengths
+struct DtaScanJob { const int *in; void *out; long long n; int out_is_i64; };
+__global__ void __launch_bounds__(1024) k_dta_scan(const DtaScanJob *jobs) {
+    const DtaScanJob J = jobs[blockIdx.x];
+    long long *o64 = (long long *)J.out; int *o32 = (int *)J.out;
+#ifdef UX_EMU
+    if (threadIdx.x) return;
+    long long acc = 0;
+    for (long long i = 0; i < J.n; i++) { if (J.out_is_i64) o64[i] = acc; else o32[i] = (int)acc; acc += J.in[i]; }
+    if (J.out_is_i64) o64[J.n] = acc; else o32[J.n] = (int)acc;
+#else
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry_s;
+    int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < J.n; base += 1024) {
+        long long i = base + tid;
+        long long v = i < J.n ? (long long)J.in[i] : 0, x = v;
+        for (int d = 1; d < 32; d <<= 1) { long long y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            long long t = warp_tot[lane], u = t;
+            for (int d = 1; d < 32; d <<= 1) { long long y = __shfl_up_sync(0xffffffffu, u, d); if (lane >= d) u += y; }
+            warp_tot[lane] = u - t;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        long long excl = carry_s + warp_tot[wid] + x - v;
+        if (i < J.n) { if (J.out_is_i64) o64[i] = excl; else o32[i] = (int)excl; }
+        __syncthreads();
+        if (tid == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) { if (J.out_is_i64) o64[J.n] = carry_s; else o32[J.n] = (int)carry_s; }
+#endif
+}
+
+// RouteSwapResult totals of one replica, accumulated in platoon order exactly as the reference's loop does
+// (dta_solver.cpp:243-252: total_t_gap is a sequential FP64 sum): one thread per replica.
+__global__ void k_dta_totals(const DevWorld *worlds, const DtaDev *dd, double *out) {
+    if (threadIdx.x) return;
+    const DtaDev &D = dd[blockIdx.x];
+    const DevWorld &W = worlds[D.replica];
+    double n_swap = 0, pot_n = 0, gap = 0;
+    for (long long i = 0; i < W.P; i++) {
+        bool pt = D.pot[i] != 0;
+        if (pt) pot_n += W.dn;
+        gap += D.t_gap[i];
+        if (D.choice[i] >= 0 && pt) n_swap += W.dn;  // a forced external route has pot == 0
+    }
+    out[blockIdx.x * 3 + 0] = n_swap; out[blockIdx.x * 3 + 1] = pot_n; out[blockIdx.x * 3 + 2] = gap;
+}
+
 #define DTA_WARPS 4
 // warp per platoon: lanes evaluate the alternative routes, then the scan over routes in store order (dta_solver.cpp:228-241)
 __global__ void __launch_bounds__(32 * DTA_WARPS) k_dta_swap(const DevWorld *worlds, const DtaDev *dd) {
@@ -1685,9 +1739,11 @@ struct ux_world {
     std::shared_ptr<DtaStore> dta_p = std::make_shared<DtaStore>();  // shared between the worlds of one solve (ux_dta_share_route_sets)
     struct DtaResult {
         bool valid = false; int replica = 0;
+        long long P = 0, rs_total = 0, ra_total = 0;
+        // host copies, filled from the device on first request (a replica-batched solve never asks)
         std::vector<long long> rs_off, ra_off; std::vector<int> rs_links, ra_links, choice; std::vector<double> ra_entry_t, cost_actual, t_gap;
-        bool rs_fetched = false, ra_fetched = false;  // the link lists are copied back from the device on first request
-        const int *d_tr_link = nullptr, *d_tr_t = nullptr;
+        bool rs_fetched = false, ra_fetched = false, meta_fetched = false;
+        const int *d_tr_link = nullptr, *d_tr_t = nullptr, *d_choice = nullptr; const long long *d_tr_off = nullptr; const double *d_cost = nullptr, *d_gap = nullptr;
         double n_swap = 0, potential_n_swap = 0, total_t_gap = 0;
     };
     std::vector<DtaResult> swaps;  // per replica
@@ -2819,9 +2875,9 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta_p->route_off.size(); dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_LINKS: n = (int64_t)w->dta_p->links.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_RS_OFFSETS: case UX_A_DTA_RA_OFFSETS: n = P + 1; dt = UX_DT_I64; break;
-    case UX_A_DTA_RS_LINKS: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.rs_off.back()); dt = UX_DT_I32; break;  // upper bound over the replicas
-    case UX_A_DTA_RA_LINKS: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.ra_off.back()); dt = UX_DT_I32; break;
-    case UX_A_DTA_RA_ENTRY_T: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.ra_off.back()); break;
+    case UX_A_DTA_RS_LINKS: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.rs_total); dt = UX_DT_I32; break;  // upper bound over the replicas
+    case UX_A_DTA_RA_LINKS: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.ra_total); dt = UX_DT_I32; break;
+    case UX_A_DTA_RA_ENTRY_T: n = 0; for (auto &r : w->swaps) if (r.valid) n = std::max(n, (int64_t)r.ra_total); break;
     case UX_A_DTA_COST_ACTUAL: case UX_A_DTA_T_GAP: n = P; break;
     case UX_A_DTA_CHOICE: n = P; dt = UX_DT_I32; break;
     default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
@@ -3043,18 +3099,29 @@ UX_API int ux_dta_share_route_sets(ux_world *w, ux_world *from) {
     return 0;
 }
 
-// The link lists of a swap result stay on the device until somebody asks for them (a replica-batched solve never does).
-static int dta_fetch(ux_world *w, int r, bool want_rs, bool want_ra) {
+// The per-platoon arrays and link lists of a swap result stay on the device until somebody asks for them (a replica-batched
+// solve never does: ux_dta_next_day consumes the routes where they are).
+static int dta_fetch(ux_world *w, int r, bool want_meta, bool want_rs, bool want_ra) {
     auto &R = w->swaps[r];
-    long long P = (long long)R.ra_off.size() - 1;
+    const long long P = R.P;
+    if (want_meta && !R.meta_fetched) {
+        R.choice.resize(P); R.cost_actual.resize(P); R.t_gap.resize(P); R.ra_off.resize(P + 1); R.rs_off.resize(P + 1);
+        std::vector<int> o32(P + 1);
+        if (P) { CUDA_OK(cudaMemcpy(R.choice.data(), R.d_choice, 4 * P, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(R.cost_actual.data(), R.d_cost, 8 * P, cudaMemcpyDeviceToHost));
+                 CUDA_OK(cudaMemcpy(R.t_gap.data(), R.d_gap, 8 * P, cudaMemcpyDeviceToHost)); }
+        CUDA_OK(cudaMemcpy(R.ra_off.data(), R.d_tr_off, 8 * (P + 1), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(o32.data(), w->next_routes[r].off, 4 * (P + 1), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i <= P; i++) R.rs_off[i] = o32[i];
+        R.meta_fetched = true; w->d2h_bytes += (long long)(P * 32 + 16);
+    }
     if (want_rs && !R.rs_fetched) {
-        size_t n = (size_t)R.rs_off[P];
+        size_t n = (size_t)R.rs_total;
         R.rs_links.resize(n);
         if (n) CUDA_OK(cudaMemcpy(R.rs_links.data(), w->next_routes[r].links, 4 * n, cudaMemcpyDeviceToHost));
         R.rs_fetched = true; w->d2h_bytes += (long long)(4 * n);
     }
     if (want_ra && !R.ra_fetched) {
-        size_t n = (size_t)R.ra_off[P];
+        size_t n = (size_t)R.ra_total;
         std::vector<int> tt(n);
         R.ra_links.resize(n); R.ra_entry_t.resize(n);
         if (n) { CUDA_OK(cudaMemcpy(R.ra_links.data(), R.d_tr_link, 4 * n, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(tt.data(), R.d_tr_t, 4 * n, cudaMemcpyDeviceToHost)); }
@@ -3065,7 +3132,10 @@ static int dta_fetch(ux_world *w, int r, bool want_rs, bool want_ra) {
 }
 
 // World.route_swap_due / route_swap_dso (bindings.cpp:661-706; dta_solver.cpp:130-373).  replica == -1: every replica of
-// the world in the same launches (replica r draws its candidates from mt19937(rng_seed + r)).
+// the world in the same launches (replica r draws its candidates from mt19937(rng_seed + r)).  Everything per-platoon stays
+// on the device: offsets are device scans, the totals a device reduction in platoon order; the host sees a few scalars per
+// replica plus, for DUE, one byte per platoon (who draws a random number) because the candidate stream is the reference's
+// sequential std::mt19937.
 UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_prob, int swap_num, int has_external, unsigned int rng_seed) {
     if (!w->uploaded || w->timestep == 0) return fail(w, UX_ERR_RUNTIME, "dta_route_swap needs a finished run");
     if (replica < -1 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
@@ -3080,7 +3150,7 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     DtaStore &S = *w->dta_p;
     w->swaps.resize(w->R); w->next_routes.resize(w->R);
     for (int r : reps) w->swaps[r].valid = false;
-    for (int r = 0; r < w->R; r++) if (w->swaps[r].valid) { int rc = dta_fetch(w, r, false, true); if (rc) return rc; }  // other replicas' results lose their device backing
+    for (int r = 0; r < w->R; r++) if (w->swaps[r].valid) { int rc = dta_fetch(w, r, true, false, true); if (rc) return rc; }  // other replicas' results lose their device backing
     if (w->swap_buf) { cudaFree(w->swap_buf); w->swap_buf = nullptr; }
     if (!S.d_block || S.device != w->device) {  // the store goes to the device once per solve
         if (S.d_block) { cudaSetDevice(S.device); cudaFree(S.d_block); S.d_block = nullptr; cudaSetDevice(w->device); }
@@ -3097,35 +3167,28 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
         CUDA_OK(cudaStreamSynchronize(st));
         w->h2d_bytes += (long long)(8 * S.o.size() + 4 * S.links.size() + 8 * (S.od_off.size() + S.route_off.size()));
     }
-    // traversed routes: per-platoon counts -> offsets (host scan); the events are scattered on the device
-    std::vector<int> trav((size_t)nr * P);
+    // number of link-entry events per replica (sizes the traversed-route arrays)
     std::vector<unsigned long long> n_ev(nr, 0);
-    std::vector<long long> tr_off((size_t)nr * (P + 1), 0), ev_base(nr + 1, 0);
-    for (int q = 0; q < nr; q++) {
-        const DevWorld &hw = w->hw[reps[q]];
-        if (P) cudaMemcpyAsync(trav.data() + (size_t)q * P, hw.v_trav, sizeof(int) * P, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(&n_ev[q], hw.tv_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-    }
+    std::vector<long long> ev_base(nr + 1, 0);
+    for (int q = 0; q < nr; q++) cudaMemcpyAsync(&n_ev[q], w->hw[reps[q]].tv_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CUDA_OK(cudaStreamSynchronize(st));
     unsigned long long max_ev = 0;
     for (int q = 0; q < nr; q++) {
-        long long *off = tr_off.data() + (size_t)q * (P + 1);
-        for (long long i = 0; i < P; i++) off[i + 1] = off[i] + trav[(size_t)q * P + i];
-        if ((unsigned long long)off[P] != n_ev[q]) return fail(w, UX_ERR_RUNTIME, "traversal log bookkeeping mismatch (replica %d): %lld expected, %llu recorded", reps[q], off[P], n_ev[q]);
-        ev_base[q + 1] = ev_base[q] + off[P];
-        max_ev = std::max(max_ev, n_ev[q]);
+        if ((long long)n_ev[q] > w->hw[reps[q]].tv_cap) return fail(w, UX_ERR_CAPACITY, "traversal log overflow (replica %d)", reps[q]);
+        ev_base[q + 1] = ev_base[q] + (long long)n_ev[q]; max_ev = std::max(max_ev, n_ev[q]);
     }
     const size_t ne = (size_t)ev_base[nr], TL = (size_t)T * L, nP = (size_t)nr * P;
     size_t bytes = 0;
     auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
     const size_t o_tt = carve(8 * TL * nr), o_ext = carve(mode == 1 ? 8 * TL * nr : 0), o_troff = carve(8 * (size_t)nr * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(nP),
                  o_pair = carve(4 * nP), o_draw = carve(nP), o_ca = carve(8 * nP), o_tg = carve(8 * nP), o_ch = carve(4 * nP), o_pot = carve(nP), o_dd = carve(sizeof(DtaDev) * nr),
-                 o_len = carve(4 * nP), o_gg = carve(sizeof(DtaGather) * nr);
+                 o_len = carve(4 * nP), o_gg = carve(sizeof(DtaGather) * nr), o_jobs = carve(sizeof(DtaScanJob) * 2 * nr), o_tot = carve(8 * 3 * (size_t)nr);
     char *buf = nullptr;
     CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
     w->swap_buf = buf;
     auto release = [&](int rc) { if (rc) { cudaFree(buf); w->swap_buf = nullptr; } return rc; };
     std::vector<DtaDev> hd(nr);
+    std::vector<DtaScanJob> jobs(2 * nr);
     for (int q = 0; q < nr; q++) {
         DtaDev &D = hd[q];
         memset(&D, 0, sizeof(D));
@@ -3135,25 +3198,34 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
         D.mode = mode; D.has_external = has_external ? 1 : 0; D.replica = reps[q];
         D.flag_swap = (const unsigned char *)(buf + o_fs) + (size_t)q * P; D.pair = (int *)(buf + o_pair) + (size_t)q * P; D.draws = (unsigned char *)(buf + o_draw) + (size_t)q * P;
         D.cost_actual = (double *)(buf + o_ca) + (size_t)q * P; D.t_gap = (double *)(buf + o_tg) + (size_t)q * P; D.choice = (int *)(buf + o_ch) + (size_t)q * P; D.pot = (unsigned char *)(buf + o_pot) + (size_t)q * P;
+        auto &NR = w->next_routes[reps[q]];
+        NR.ready = false;
+        if (!NR.off) { if (cudaMalloc((void **)&NR.off, 4 * (size_t)(P + 1)) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "device allocation failed (next-day routes)")); }
+        jobs[q] = {w->hw[reps[q]].v_trav, (void *)D.tr_off, P, 1};                               // traversal counts -> tr_off
+        jobs[nr + q] = {(const int *)(buf + o_len) + (size_t)q * P, (void *)NR.off, P, 0};       // route lengths -> next-day offsets
     }
     const DtaDev *d_dd = (const DtaDev *)(buf + o_dd);
+    const DtaScanJob *d_jobs = (const DtaScanJob *)(buf + o_jobs);
 #ifndef UX_EMU
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
 #endif
     cudaMemcpyAsync(buf + o_dd, hd.data(), sizeof(DtaDev) * nr, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(buf + o_troff, tr_off.data(), 8 * tr_off.size(), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + o_jobs, jobs.data(), sizeof(DtaScanJob) * 2 * nr, cudaMemcpyHostToDevice, st);
+    UX_LAUNCH(k_dta_scan, dim3(nr), dim3(1024), st, d_jobs);
     if (max_ev) UX_LAUNCH(k_dta_scatter, dim3((unsigned)((max_ev + 255) / 256), nr), dim3(256), st, w->dworlds, d_dd);
     if (L > 0) UX_LAUNCH(k_dta_tt_actual, dim3((L + 63) / 64, nr), dim3(64), st, w->dworlds, d_dd);
     if (mode == 1 && TL) UX_LAUNCH(k_dta_externality, dim3((unsigned)((TL + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd);
     if (P) UX_LAUNCH(k_dta_prepare, dim3((unsigned)((P + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd);
     // swap candidates: the reference's own stream, std::mt19937(rng_seed) + uniform_real_distribution (dta_solver.cpp:148-149, 265-283)
-    std::vector<unsigned char> draws(nP), flag(nP, 0);
-    if (nP) cudaMemcpyAsync(draws.data(), buf + o_draw, nP, cudaMemcpyDeviceToHost, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route-swap preparation: %s", cudaGetErrorString(cudaGetLastError())));
-    for (int q = 0; q < nr; q++) {
+    std::vector<unsigned char> draws(mode == 0 ? nP : 0), flag(nP, 0);
+    if (mode == 0 && nP) {
+        cudaMemcpyAsync(draws.data(), buf + o_draw, nP, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route-swap preparation: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    parallel_for(nr, [&](int, int q) {  // replicas draw independently
         std::mt19937 rng(replica >= 0 ? rng_seed : rng_seed + (unsigned)reps[q]);
         std::uniform_real_distribution<double> udist(0.0, 1.0);
-        unsigned char *fl = flag.data() + (size_t)q * P; const unsigned char *dr = draws.data() + (size_t)q * P;
+        unsigned char *fl = flag.data() + (size_t)q * P;
         if (mode == 1 && swap_num >= 0) {
             std::vector<int> idx(P);
             for (long long i = 0; i < P; i++) idx[i] = (int)i;
@@ -3161,64 +3233,36 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
             long long m = std::min<long long>(swap_num, P);
             for (long long i = 0; i < m; i++) fl[idx[i]] = 1;
         } else if (mode == 1) { for (long long i = 0; i < P; i++) fl[i] = udist(rng) < swap_prob; }
-        else { for (long long i = 0; i < P; i++) if (dr[i]) fl[i] = udist(rng) < swap_prob; }
-    }
+        else { const unsigned char *dr = draws.data() + (size_t)q * P; for (long long i = 0; i < P; i++) if (dr[i]) fl[i] = udist(rng) < swap_prob; }
+    });
+    std::vector<double> totals(3 * (size_t)nr, 0.0);
+    std::vector<int> rs_tot(nr, 0);
     if (nP) {
         cudaMemcpyAsync(buf + o_fs, flag.data(), nP, cudaMemcpyHostToDevice, st);
         UX_LAUNCH(k_dta_swap, dim3((unsigned)((P + DTA_WARPS - 1) / DTA_WARPS), nr), dim3(32 * DTA_WARPS), st, w->dworlds, d_dd);
         UX_LAUNCH(k_dta_rs_len, dim3((unsigned)((P + 127) / 128), nr), dim3(128), st, w->dworlds, d_dd, (int *)(buf + o_len));
     }
-#ifndef UX_EMU
-    cudaEventRecord(e1, st);
-#endif
-    std::vector<int> choice(nP), lens(nP); std::vector<double> cost(nP), gap(nP); std::vector<unsigned char> pot(nP, 0);
-    if (nP) {
-        cudaMemcpyAsync(choice.data(), buf + o_ch, 4 * nP, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(cost.data(), buf + o_ca, 8 * nP, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(gap.data(), buf + o_tg, 8 * nP, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(pot.data(), buf + o_pot, nP, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(lens.data(), buf + o_len, 4 * nP, cudaMemcpyDeviceToHost, st);
-    }
+    UX_LAUNCH(k_dta_scan, dim3(nr), dim3(1024), st, d_jobs + nr);
+    UX_LAUNCH(k_dta_totals, dim3(nr), dim3(32), st, w->dworlds, d_dd, (double *)(buf + o_tot));
+    cudaMemcpyAsync(totals.data(), buf + o_tot, 8 * 3 * (size_t)nr, cudaMemcpyDeviceToHost, st);
+    for (int q = 0; q < nr; q++) cudaMemcpyAsync(&rs_tot[q], w->next_routes[reps[q]].off + P, 4, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route swap: %s", cudaGetErrorString(cudaGetLastError())));
-#ifndef UX_EMU
-    { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); w->swap_ms = ms; cudaEventDestroy(e0); cudaEventDestroy(e1); }
-#endif
-    w->d2h_bytes += (long long)(nP * (4 + 8 + 8 + 1 + 1 + 4 + 4));
-    w->h2d_bytes += (long long)(nP * 9 + 8 * nr);
     std::vector<DtaGather> hg(nr);
-    std::vector<int> off32((size_t)nr * (P + 1), 0);
     for (int q = 0; q < nr; q++) {
         auto &R = w->swaps[reps[q]];
-        const long long *off = tr_off.data() + (size_t)q * (P + 1);
-        R.ra_off.assign(off, off + P + 1);
-        R.d_tr_link = (const int *)(buf + o_trl) + ev_base[q]; R.d_tr_t = (const int *)(buf + o_trt) + ev_base[q];
-        R.ra_links.clear(); R.ra_entry_t.clear(); R.rs_links.clear(); R.rs_fetched = R.ra_fetched = false;
-        R.choice.assign(choice.begin() + (size_t)q * P, choice.begin() + (size_t)(q + 1) * P);
-        R.cost_actual.assign(cost.begin() + (size_t)q * P, cost.begin() + (size_t)(q + 1) * P);
-        R.t_gap.assign(gap.begin() + (size_t)q * P, gap.begin() + (size_t)(q + 1) * P);
-        const unsigned char *pt = pot.data() + (size_t)q * P;
-        const int *ln = lens.data() + (size_t)q * P;
-        int *o32 = off32.data() + (size_t)q * (P + 1);
-        // totals in platoon order (sequential sums of dta_solver.cpp:243-252) and the offsets of the next iteration's routes
-        R.n_swap = 0; R.potential_n_swap = 0; R.total_t_gap = 0;
-        R.rs_off.assign(P + 1, 0);
-        for (long long i = 0; i < P; i++) {
-            if (pt[i]) R.potential_n_swap += w->p.delta_n;
-            R.total_t_gap += R.t_gap[i];
-            if (R.choice[i] >= 0 && pt[i]) R.n_swap += w->p.delta_n;  // a forced external route has pot == 0
-            R.rs_off[i + 1] = R.rs_off[i] + ln[i];
-            o32[i + 1] = (int)R.rs_off[i + 1];
-        }
-        if (R.rs_off[P] > 0x7fffffff) return release(fail(w, UX_ERR_CAPACITY, "more than 2^31 route entries (replica %d)", reps[q]));
         auto &NR = w->next_routes[reps[q]];
-        NR.ready = false;
-        if (!NR.off) { if (cudaMalloc((void **)&NR.off, 4 * (size_t)(P + 1)) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "device allocation failed (next-day routes)")); }
-        size_t need = (size_t)R.rs_off[P] + 1;
+        if (rs_tot[q] < 0) return release(fail(w, UX_ERR_CAPACITY, "more than 2^31 route entries (replica %d)", reps[q]));
+        size_t need = (size_t)rs_tot[q] + 1;
         if (need > NR.cap) {
             if (NR.links) cudaFree(NR.links);
             NR.cap = need + need / 4; NR.links = nullptr;
             if (cudaMalloc((void **)&NR.links, 4 * NR.cap) != cudaSuccess) { NR.cap = 0; return release(fail(w, UX_ERR_CUDA, "device allocation failed (next-day routes)")); }
         }
-        cudaMemcpyAsync(NR.off, o32, 4 * (size_t)(P + 1), cudaMemcpyHostToDevice, st);
         hg[q].off = NR.off; hg[q].links = NR.links;
+        R = ux_world::DtaResult();
+        R.P = P; R.rs_total = rs_tot[q]; R.ra_total = (long long)n_ev[q];
+        R.d_tr_link = hd[q].tr_link; R.d_tr_t = hd[q].tr_t; R.d_tr_off = hd[q].tr_off; R.d_choice = hd[q].choice; R.d_cost = hd[q].cost_actual; R.d_gap = hd[q].t_gap;
+        R.n_swap = totals[3 * q + 0]; R.potential_n_swap = totals[3 * q + 1]; R.total_t_gap = totals[3 * q + 2];
         R.replica = reps[q]; R.valid = true;
         w->swap_last = reps[q];
     }
@@ -3226,12 +3270,18 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
         cudaMemcpyAsync(buf + o_gg, hg.data(), sizeof(DtaGather) * nr, cudaMemcpyHostToDevice, st);
         UX_LAUNCH(k_dta_rs_gather, dim3((unsigned)((P * 8 + 255) / 256), nr), dim3(256), st, w->dworlds, d_dd, (const DtaGather *)(buf + o_gg));
     }
+#ifndef UX_EMU
+    cudaEventRecord(e1, st);
+#endif
     if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error assembling the next-day routes: %s", cudaGetErrorString(cudaGetLastError())));
+#ifndef UX_EMU
+    { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); w->swap_ms = ms; cudaEventDestroy(e0); cudaEventDestroy(e1); }
+#endif
     for (int q = 0; q < nr; q++) w->next_routes[reps[q]].ready = true;
-    w->h2d_bytes += (long long)(4 * off32.size());
+    w->d2h_bytes += (long long)((mode == 0 ? nP : 0) + 32 * (size_t)nr);
+    w->h2d_bytes += (long long)(nP + (sizeof(DtaDev) + 2 * sizeof(DtaScanJob) + sizeof(DtaGather)) * nr);
     return release(0);
 }
-
 
 // Rewind a finished world to t = 0 for the next day of a day-to-day solve: the per-replica dynamic state is re-initialised in
 // place (zero + the recorded non-zero initial values), every replica that has a route-swap result gets its routes_specified
@@ -3272,7 +3322,8 @@ static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int6
     if (what >= UX_A_DTA_RS_OFFSETS) {
         if (replica < 0 || replica >= (int)w->swaps.size() || !w->swaps[replica].valid) return fail(w, UX_ERR_RUNTIME, "no route swap result for replica %d", replica);
         auto &r = w->swaps[replica];
-        { int rc = dta_fetch(w, replica, what == UX_A_DTA_RS_LINKS, what == UX_A_DTA_RA_LINKS || what == UX_A_DTA_RA_ENTRY_T); if (rc) return rc; }
+        { int rc = dta_fetch(w, replica, what != UX_A_DTA_RS_LINKS && what != UX_A_DTA_RA_LINKS && what != UX_A_DTA_RA_ENTRY_T, what == UX_A_DTA_RS_LINKS,
+                             what == UX_A_DTA_RA_LINKS || what == UX_A_DTA_RA_ENTRY_T); if (rc) return rc; }
         switch (what) {
         case UX_A_DTA_RS_OFFSETS: src = r.rs_off.data(); break;
         case UX_A_DTA_RA_OFFSETS: src = r.ra_off.data(); break;

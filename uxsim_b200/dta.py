@@ -303,8 +303,7 @@ class DayToDayEnsemble:
             E.main_loop()
             t2 = time.perf_counter()
             day_seed = ((swap_seed * 1000003 + day * 65537) & 0x3FFFFFFF) + self.local.start   # chain c draws its swap candidates from seed + c
-            last = day == max_iter - 1
-            results = E.dta_route_swap_all(self.mode, swap_prob, day_seed, routes=last)   # every chain's swap in the same launches
+            results = E.dta_route_swap_all(self.mode, swap_prob, day_seed, routes=False)   # every chain's swap in the same launches
             tt_all = E.get_array_all(C.A_VEH_TRAVEL_TIME)
             for r, res in enumerate(results):
                 tt = tt_all[r]
@@ -316,7 +315,7 @@ class DayToDayEnsemble:
             t3 = time.perf_counter()
             self.day_seconds.append((t1 - t0, t2 - t1, t3 - t2))
             self.swap_device_ms.append(E.get_double(C.D_DTA_SWAP_MS))
-        self.routes = [(res["rs_link_ids"], res["rs_offsets"]) for res in results]
+        self.routes = [(E.get_array(C.A_DTA_RS_LINKS, r), E.get_array(C.A_DTA_RS_OFFSETS, r)) for r in range(R)]  # the solution: handed back once
         self.link_stats_sum = self._reduce_link_stats(E)
         if not keep_last_world:
             E.close()

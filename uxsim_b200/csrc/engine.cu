@@ -1578,7 +1578,7 @@ __global__ void k_dta_rs_gather(const DevWorld *worlds, const DtaDev *dd, const 
 }
 
 // exclusive scan of n ints (block per job): out[0] = 0 ... out[n] = total; used for the traversal counts and the route lengths
-struct DtaScanJob { const int *in; void *out; long long n; int out_is_i64; };
+struct DtaScanJob { const int *in; void *out; long long n; int out_is_i64; long long *total; };
 __global__ void __launch_bounds__(1024) k_dta_scan(const DtaScanJob *jobs) {
     const DtaScanJob J = jobs[blockIdx.x];
     long long *o64 = (long long *)J.out; int *o32 = (int *)J.out;
@@ -1587,6 +1587,7 @@ __global__ void __launch_bounds__(1024) k_dta_scan(const DtaScanJob *jobs) {
     long long acc = 0;
     for (long long i = 0; i < J.n; i++) { if (J.out_is_i64) o64[i] = acc; else o32[i] = (int)acc; acc += J.in[i]; }
     if (J.out_is_i64) o64[J.n] = acc; else o32[J.n] = (int)acc;
+    if (J.total) *J.total = acc;
 #else
     __shared__ long long warp_tot[32];
     __shared__ long long carry_s;
@@ -1611,8 +1612,14 @@ __global__ void __launch_bounds__(1024) k_dta_scan(const DtaScanJob *jobs) {
         if (tid == 1023) carry_s = excl + v;
         __syncthreads();
     }
-    if (tid == 0) { if (J.out_is_i64) o64[J.n] = carry_s; else o32[J.n] = (int)carry_s; }
+    if (tid == 0) { if (J.out_is_i64) o64[J.n] = carry_s; else o32[J.n] = (int)carry_s; if (J.total) *J.total = carry_s; }
 #endif
+}
+
+// number of recorded link-entry events of replicas first .. first+n-1 (one small transfer instead of n)
+__global__ void k_dta_counts(const DevWorld *worlds, int first, int n, unsigned long long *out) {
+    int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i < n) out[i] = *worlds[first + i].tv_count;
 }
 
 // RouteSwapResult totals of one replica, accumulated in platoon order exactly as the reference's loop does
@@ -3170,7 +3177,9 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     // number of link-entry events per replica (sizes the traversed-route arrays)
     std::vector<unsigned long long> n_ev(nr, 0);
     std::vector<long long> ev_base(nr + 1, 0);
-    for (int q = 0; q < nr; q++) cudaMemcpyAsync(&n_ev[q], w->hw[reps[q]].tv_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    { int rc = ensure_scratch(w, 8 * (size_t)nr + 16); if (rc) return rc; }
+    UX_LAUNCH(k_dta_counts, dim3((nr + 127) / 128), dim3(128), st, w->dworlds, reps[0], nr, (unsigned long long *)w->d_scratch);
+    cudaMemcpyAsync(n_ev.data(), w->d_scratch, 8 * (size_t)nr, cudaMemcpyDeviceToHost, st);
     CUDA_OK(cudaStreamSynchronize(st));
     unsigned long long max_ev = 0;
     for (int q = 0; q < nr; q++) {
@@ -3182,7 +3191,7 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
     const size_t o_tt = carve(8 * TL * nr), o_ext = carve(mode == 1 ? 8 * TL * nr : 0), o_troff = carve(8 * (size_t)nr * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(nP),
                  o_pair = carve(4 * nP), o_draw = carve(nP), o_ca = carve(8 * nP), o_tg = carve(8 * nP), o_ch = carve(4 * nP), o_pot = carve(nP), o_dd = carve(sizeof(DtaDev) * nr),
-                 o_len = carve(4 * nP), o_gg = carve(sizeof(DtaGather) * nr), o_jobs = carve(sizeof(DtaScanJob) * 2 * nr), o_tot = carve(8 * 3 * (size_t)nr);
+                 o_len = carve(4 * nP), o_gg = carve(sizeof(DtaGather) * nr), o_jobs = carve(sizeof(DtaScanJob) * 2 * nr), o_tot = carve(8 * 4 * (size_t)nr);
     char *buf = nullptr;
     CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
     w->swap_buf = buf;
@@ -3201,8 +3210,8 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
         auto &NR = w->next_routes[reps[q]];
         NR.ready = false;
         if (!NR.off) { if (cudaMalloc((void **)&NR.off, 4 * (size_t)(P + 1)) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "device allocation failed (next-day routes)")); }
-        jobs[q] = {w->hw[reps[q]].v_trav, (void *)D.tr_off, P, 1};                               // traversal counts -> tr_off
-        jobs[nr + q] = {(const int *)(buf + o_len) + (size_t)q * P, (void *)NR.off, P, 0};       // route lengths -> next-day offsets
+        jobs[q] = {w->hw[reps[q]].v_trav, (void *)D.tr_off, P, 1, nullptr};                               // traversal counts -> tr_off
+        jobs[nr + q] = {(const int *)(buf + o_len) + (size_t)q * P, (void *)NR.off, P, 0, (long long *)(buf + o_tot) + 3 * (size_t)nr + q};  // route lengths -> next-day offsets
     }
     const DtaDev *d_dd = (const DtaDev *)(buf + o_dd);
     const DtaScanJob *d_jobs = (const DtaScanJob *)(buf + o_jobs);
@@ -3235,8 +3244,8 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
         } else if (mode == 1) { for (long long i = 0; i < P; i++) fl[i] = udist(rng) < swap_prob; }
         else { const unsigned char *dr = draws.data() + (size_t)q * P; for (long long i = 0; i < P; i++) if (dr[i]) fl[i] = udist(rng) < swap_prob; }
     });
-    std::vector<double> totals(3 * (size_t)nr, 0.0);
-    std::vector<int> rs_tot(nr, 0);
+    std::vector<double> totals(4 * (size_t)nr, 0.0);  // [3*nr] doubles, then nr int64 route-entry totals
+    std::vector<long long> rs_tot(nr, 0);
     if (nP) {
         cudaMemcpyAsync(buf + o_fs, flag.data(), nP, cudaMemcpyHostToDevice, st);
         UX_LAUNCH(k_dta_swap, dim3((unsigned)((P + DTA_WARPS - 1) / DTA_WARPS), nr), dim3(32 * DTA_WARPS), st, w->dworlds, d_dd);
@@ -3244,14 +3253,14 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     }
     UX_LAUNCH(k_dta_scan, dim3(nr), dim3(1024), st, d_jobs + nr);
     UX_LAUNCH(k_dta_totals, dim3(nr), dim3(32), st, w->dworlds, d_dd, (double *)(buf + o_tot));
-    cudaMemcpyAsync(totals.data(), buf + o_tot, 8 * 3 * (size_t)nr, cudaMemcpyDeviceToHost, st);
-    for (int q = 0; q < nr; q++) cudaMemcpyAsync(&rs_tot[q], w->next_routes[reps[q]].off + P, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(totals.data(), buf + o_tot, 8 * 4 * (size_t)nr, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return release(fail(w, UX_ERR_CUDA, "CUDA error in the route swap: %s", cudaGetErrorString(cudaGetLastError())));
+    memcpy(rs_tot.data(), totals.data() + 3 * (size_t)nr, 8 * (size_t)nr);
     std::vector<DtaGather> hg(nr);
     for (int q = 0; q < nr; q++) {
         auto &R = w->swaps[reps[q]];
         auto &NR = w->next_routes[reps[q]];
-        if (rs_tot[q] < 0) return release(fail(w, UX_ERR_CAPACITY, "more than 2^31 route entries (replica %d)", reps[q]));
+        if (rs_tot[q] > 0x7fffffff) return release(fail(w, UX_ERR_CAPACITY, "more than 2^31 route entries (replica %d)", reps[q]));
         size_t need = (size_t)rs_tot[q] + 1;
         if (need > NR.cap) {
             if (NR.links) cudaFree(NR.links);

@@ -1754,7 +1754,8 @@ struct ux_world {
         double n_swap = 0, potential_n_swap = 0, total_t_gap = 0;
     };
     std::vector<DtaResult> swaps;  // per replica
-    char *swap_buf = nullptr;      // device scratch of the last route swap (traversed routes stay there for lazy hand-back)
+    char *swap_buf = nullptr;      // device scratch of the route swaps, kept between days (traversed routes stay there for lazy hand-back)
+    size_t swap_buf_bytes = 0;
     struct NextRoutes { int *off = nullptr, *links = nullptr; size_t cap = 0; bool ready = false; };
     std::vector<NextRoutes> next_routes;  // per replica: routes_specified of the last swap as a device CSR (next day's enforced routes)
     // re-initialisation recipe of the per-replica dynamic state (ux_dta_next_day rewinds the world instead of rebuilding it)
@@ -3158,7 +3159,6 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     w->swaps.resize(w->R); w->next_routes.resize(w->R);
     for (int r : reps) w->swaps[r].valid = false;
     for (int r = 0; r < w->R; r++) if (w->swaps[r].valid) { int rc = dta_fetch(w, r, true, false, true); if (rc) return rc; }  // other replicas' results lose their device backing
-    if (w->swap_buf) { cudaFree(w->swap_buf); w->swap_buf = nullptr; }
     if (!S.d_block || S.device != w->device) {  // the store goes to the device once per solve
         if (S.d_block) { cudaSetDevice(S.device); cudaFree(S.d_block); S.d_block = nullptr; cudaSetDevice(w->device); }
         size_t b0 = (4 * S.o.size() + 255) & ~(size_t)255, b1 = (4 * S.links.size() + 255) & ~(size_t)255, b2 = (8 * S.od_off.size() + 255) & ~(size_t)255,
@@ -3192,10 +3192,14 @@ UX_API int ux_dta_route_swap(ux_world *w, int replica, int mode, double swap_pro
     const size_t o_tt = carve(8 * TL * nr), o_ext = carve(mode == 1 ? 8 * TL * nr : 0), o_troff = carve(8 * (size_t)nr * (P + 1)), o_trl = carve(4 * ne), o_trt = carve(4 * ne), o_fs = carve(nP),
                  o_pair = carve(4 * nP), o_draw = carve(nP), o_ca = carve(8 * nP), o_tg = carve(8 * nP), o_ch = carve(4 * nP), o_pot = carve(nP), o_dd = carve(sizeof(DtaDev) * nr),
                  o_len = carve(4 * nP), o_gg = carve(sizeof(DtaGather) * nr), o_jobs = carve(sizeof(DtaScanJob) * 2 * nr), o_tot = carve(8 * 4 * (size_t)nr);
-    char *buf = nullptr;
-    CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
-    w->swap_buf = buf;
-    auto release = [&](int rc) { if (rc) { cudaFree(buf); w->swap_buf = nullptr; } return rc; };
+    if (bytes + 256 > w->swap_buf_bytes) {  // grown with headroom and kept: a day-to-day solve asks for nearly the same size every day
+        if (w->swap_buf) { cudaFree(w->swap_buf); w->swap_buf = nullptr; w->swap_buf_bytes = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        CUDA_OK(cudaMalloc((void **)&w->swap_buf, want));
+        w->swap_buf_bytes = want;
+    }
+    char *buf = w->swap_buf;
+    auto release = [&](int rc) { return rc; };
     std::vector<DtaDev> hd(nr);
     std::vector<DtaScanJob> jobs(2 * nr);
     for (int q = 0; q < nr; q++) {

@@ -488,9 +488,9 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         }
         WARP_SYNC();
     }
+    WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; } }
     WARP_FOR(ln) if (ln == 0) {
         W.gen_avail[n] = av;
-        for (int k = 0; k < nout; k++) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; }
         // ---- signal (Node::signal_update traffi.cpp:194-207)
         int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
         int ph = W.sig_phase[n];
@@ -924,14 +924,14 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
     int warp = (int)((blockIdx.y * blockDim.x + threadIdx.x) >> 5), wib = (int)((threadIdx.x >> 5) % XFER_WARPS);
     if (warp >= W.N) return;
     int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
-    int lvl = W.n_levels > 1 ? W.lvl_level[warp] : 0;
+    int lvl_raw = W.n_levels > 1 ? W.lvl_level[warp] : 0, lvl = lvl_raw & 0xffff;  // bit 16: some node waits for this one
     pre_node(W, sm_all[wib].pre, tt_all[wib], &rel_all[wib], n, t, (int)(threadIdx.x & 31));
 #ifndef UX_EMU
     __threadfence_block();
 #endif
     XferSmem<MC, MD> &S = sm_all[wib].xf;
     xfer_node(W, S, n, t, lvl > 0);
-    if (W.n_levels > 1) {
+    if (lvl_raw >> 16) {  // publish completion only where somebody is waiting: the fence is not free
         WARP_SYNC();
         WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)(W.node_done + n)) = t + 1; }
     }
@@ -2134,6 +2134,11 @@ static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<in
     }
     lvl_level.assign(N, 0);
     for (int q = 0; q < N; q++) lvl_level[q] = level[lvl_nodes[q]];
+    {   // bit 16 of a node's entry: it has dependents (it must publish node_done)
+        std::vector<char> waited(N, 0);
+        for (int a = 0; a < N; a++) for (int l : w->nodes[a].out) if (lflags[l] & LF_SEES_POPS) waited[w->links[l].end] = 1;
+        for (int q = 0; q < N; q++) if (waited[lvl_nodes[q]]) lvl_level[q] |= 0x10000;
+    }
     dep_off.assign(N + 1, 0); dep_list.clear();
     for (int a = 0; a < N; a++) {
         for (int l : w->nodes[a].out) if (lflags[l] & LF_SEES_POPS) { int b = w->links[l].end; if (std::find(dep_list.begin() + dep_off[a], dep_list.end(), b) == dep_list.end()) dep_list.push_back(b); }
@@ -2896,10 +2901,10 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
 
 static int ensure_scratch(ux_world *w, size_t bytes) {
     if (bytes <= w->scratch_bytes) return 0;
-    void *p = nullptr;
-    CUDA_OK(cudaMalloc(&p, bytes));
-    w->allocs.push_back(p);
-    w->d_scratch = (double *)p; w->scratch_bytes = bytes;
+    size_t want = std::max(bytes, std::max<size_t>(2 * w->scratch_bytes, (size_t)4 << 20));  // from the slabs: no driver allocation in steady state
+    char *p = dalloc<char>(w, want, false);
+    if (!p) return fail(w, UX_ERR_CUDA, "device allocation failed (%zu bytes of scratch)", want);
+    w->d_scratch = (double *)p; w->scratch_bytes = want;
     return 0;
 }
 

@@ -4,7 +4,7 @@ The ncu CLI prints the source page per SASS instruction only; this joins it with
 cubin extracted from the built library (same instruction order).  Usage:
   cuobjdump -xelf all uxsim_b200/libuxsim_b200.so && nvdisasm -g -c engine.sm_100a.cubin > dis.txt
   ncu -i rep.ncu-rep --page source --csv --kernel-name regex:k_node > src.csv
-  python profiles/tools/ncu_lines.py dis.txt src.csv _Z6k_nodeILi32ELi16EEvPK8DevWorldi uxsim_b200/csrc/engine.cu [top]
+  python profiles/tools/ncu_lines.py dis.txt src.csv _Z6k_nodeILi32ELi16EEvPK8DevWorldi uxsim_b200/csrc/ux_kernels_step.cuh [top]
 """
 import collections
 import csv

@@ -1,0 +1,161 @@
+// ux_host_arrays.inl -- part of engine.cu (one translation unit; included in the order engine.cu lists).
+// C-ABI, part 5: get_array (host copies of results), ensemble link statistics, last_error.
+
+static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    int dt; int64_t n = ux_array_size(w, what, &dt);
+    if (n < 0) return n;
+    const void *src = nullptr;
+    if (what >= UX_A_DTA_RS_OFFSETS) {
+        if (replica < 0 || replica >= (int)w->swaps.size() || !w->swaps[replica].valid) return fail(w, UX_ERR_RUNTIME, "no route swap result for replica %d", replica);
+        auto &r = w->swaps[replica];
+        { int rc = dta_fetch(w, replica, what != UX_A_DTA_RS_LINKS && what != UX_A_DTA_RA_LINKS && what != UX_A_DTA_RA_ENTRY_T, what == UX_A_DTA_RS_LINKS,
+                             what == UX_A_DTA_RA_LINKS || what == UX_A_DTA_RA_ENTRY_T); if (rc) return rc; }
+        switch (what) {
+        case UX_A_DTA_RS_OFFSETS: src = r.rs_off.data(); break;
+        case UX_A_DTA_RA_OFFSETS: src = r.ra_off.data(); break;
+        case UX_A_DTA_RS_LINKS: src = r.rs_links.data(); n = (int64_t)r.rs_links.size(); break;
+        case UX_A_DTA_RA_LINKS: src = r.ra_links.data(); n = (int64_t)r.ra_links.size(); break;
+        case UX_A_DTA_RA_ENTRY_T: src = r.ra_entry_t.data(); n = (int64_t)r.ra_entry_t.size(); break;
+        case UX_A_DTA_COST_ACTUAL: src = r.cost_actual.data(); break;
+        case UX_A_DTA_T_GAP: src = r.t_gap.data(); break;
+        default: src = r.choice.data(); break;
+        }
+    } else {
+        DtaStore &d = *w->dta_p;
+        src = what == UX_A_DTA_OD_ORIG ? (const void *)d.o.data() : what == UX_A_DTA_OD_DEST ? (const void *)d.d.data() : what == UX_A_DTA_OD_OFFSETS ? (const void *)d.od_off.data()
+            : what == UX_A_DTA_ROUTE_OFFSETS ? (const void *)d.route_off.data() : (const void *)d.links.data();
+    }
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    if (n > 0) memcpy(dst, src, (dt == UX_DT_I32 ? 4 : 8) * (size_t)n);
+    return n;
+}
+
+UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    if (is_log_array(what)) return get_log_array(w, what, replica, dst, capacity, nullptr, false);
+    if (what >= UX_A_DTA_OD_ORIG && what <= UX_A_DTA_RA_ENTRY_T) return get_dta_array(w, what, replica, dst, capacity);
+    if (what == UX_A_VEH_ORIG || what == UX_A_VEH_DEST || what == UX_A_VEH_DEPART_TS) {  // static: answered from the host copy (no upload forced)
+        int64_t P = (int64_t)w->vehs.size();
+        if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+        if (capacity < P) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)P);
+        int *oi = (int *)dst;
+        for (int64_t i = 0; i < P; i++) oi[i] = what == UX_A_VEH_ORIG ? w->vehs[i].orig : what == UX_A_VEH_DEST ? w->vehs[i].dest : w->vehs[i].ts;
+        return P;
+    }
+    if (replica == -1) {  // every replica's copy of a per-replica state array, replica-major, in ONE device->host transfer
+        const int R = w->R;
+        int dt0; int64_t n0 = ux_array_size(w, what, &dt0);
+        if (n0 < 0) return n0;
+        if (capacity < n0 * R) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)(n0 * R));
+        if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; }
+        cudaSetDevice(w->device);
+        if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
+        size_t es0 = dt0 == UX_DT_I32 ? 4 : 8, row = es0 * (size_t)n0;
+        std::vector<const void *> src(R, nullptr);
+        for (int r = 0; r < R; r++) {
+            const DevWorld &d = w->hw[r];
+            switch (what) {
+            case UX_A_VEH_ARRIVAL_TS: src[r] = d.v_arr_ts; break;
+            case UX_A_VEH_TRAVEL_TIME: src[r] = d.v_tt; break;
+            case UX_A_VEH_LINK: src[r] = d.v_link; break;
+            case UX_A_NODE_SIGNAL_PHASE: src[r] = d.sig_phase; break;
+            case UX_A_NODE_SIGNAL_T: src[r] = d.sig_t; break;
+            case UX_A_LINK_CAPACITY_IN_REMAIN: src[r] = d.cap_in_rem; break;
+            case UX_A_LINK_CAPACITY_OUT_REMAIN: src[r] = d.cap_out_rem; break;
+            default: break;
+            }
+        }
+        if (what == UX_A_LINK_STAT_COUNT) {  // i64 on the device, f64 in the ABI
+            int rc = ensure_scratch(w, 8 * (size_t)n0 * R + 16); if (rc) return rc;
+            for (int r = 0; r < R; r++) cudaMemcpyAsync((char *)w->d_scratch + row * r, w->hw[r].stat_count, row, cudaMemcpyDeviceToDevice, w->stream);
+            std::vector<long long> h((size_t)n0 * R);
+            if (n0 * R) CUDA_OK(cudaMemcpyAsync(h.data(), w->d_scratch, row * R, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_OK(cudaStreamSynchronize(w->stream));
+            double *o = (double *)dst;
+            for (size_t i = 0; i < h.size(); i++) o[i] = (double)h[i];
+        } else {
+            if (!src[0]) return fail(w, UX_ERR_INVALID, "array %d cannot be fetched for all replicas at once", what);
+            int rc = ensure_scratch(w, row * R + 16); if (rc) return rc;
+            for (int r = 0; r < R; r++) cudaMemcpyAsync((char *)w->d_scratch + row * r, src[r], row, cudaMemcpyDeviceToDevice, w->stream);
+            if (n0 * R) CUDA_OK(cudaMemcpyAsync(dst, w->d_scratch, row * R, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_OK(cudaStreamSynchronize(w->stream));
+        }
+        w->d2h_bytes += (long long)(row * R);
+        return n0 * R;
+    }
+    void *dptr = nullptr; int dt = 0;
+    int64_t n = device_array(w, what, replica, &dptr, &dt);
+    if (n < 0) return n;
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    size_t es = dt == UX_DT_F64 ? 8 : dt == UX_DT_I32 ? 4 : 8;
+    if (dptr) { if (n > 0) CUDA_OK(cudaMemcpy(dst, dptr, es * (size_t)n, cudaMemcpyDeviceToHost)); w->d2h_bytes += (long long)(es * (size_t)n); return n; }
+    const DevWorld &d = w->hw[replica];
+    int N = d.N, L = d.L; long long P = d.P;
+    double *o = (double *)dst; int *oi = (int *)dst;
+    switch (what) {
+    case UX_A_VEH_STATE: {  // HOME/WAIT are derived from the departure step (traffi.cpp:836-841)
+        std::vector<int> st(P); if (P) CUDA_OK(cudaMemcpy(st.data(), d.v_state, sizeof(int) * P, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < P; i++) {
+            int s = st[i];
+            if (s == UX_VS_HOME && w->eff_ts[i] <= w->timestep - 1) s = UX_VS_WAIT;
+            oi[i] = s;
+        }
+        break; }
+    case UX_A_VEH_DISTANCE: {
+        std::vector<double> dist(P), ex(P), vx(P); std::vector<int> st(P);
+        void *px = nullptr; int64_t m = device_array(w, UX_A_VEH_X, replica, &px, nullptr); if (m < 0) return m;
+        if (P) { CUDA_OK(cudaMemcpy(vx.data(), px, sizeof(double) * P, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(dist.data(), d.v_dist, sizeof(double) * P, cudaMemcpyDeviceToHost));
+                 CUDA_OK(cudaMemcpy(ex.data(), d.v_entry_x, sizeof(double) * P, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(st.data(), d.v_state, sizeof(int) * P, cudaMemcpyDeviceToHost)); }
+        for (long long i = 0; i < P; i++) o[i] = dist[i] + (st[i] == UX_VS_RUN ? vx[i] - ex[i] : 0.0);
+        break; }
+    case UX_A_LINK_NUM_VEHICLES: {
+        std::vector<int> hd(2 * (size_t)L), tl(L);
+        if (L) { CUDA_OK(cudaMemcpy(hd.data(), d.head, sizeof(int) * 2 * L, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(tl.data(), d.tail, sizeof(int) * L, cudaMemcpyDeviceToHost)); }
+        int cur = w->timestep & 1;
+        for (int l = 0; l < L; l++) oi[l] = tl[l] - hd[(size_t)cur * L + l];
+        break; }
+    case UX_A_LINK_STAT_COUNT: { std::vector<long long> h(L); if (L) CUDA_OK(cudaMemcpy(h.data(), d.stat_count, sizeof(long long) * L, cudaMemcpyDeviceToHost)); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
+    case UX_A_LINK_TRIPS_COMPLETED: { std::vector<int> h(L); if (L) CUDA_OK(cudaMemcpy(h.data(), d.trips, sizeof(int) * L, cudaMemcpyDeviceToHost)); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
+    case UX_A_ROUTE_PREF: {
+        std::vector<double> h((size_t)d.D * L); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.pref, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < N; k++) { int r = w->dest_row[k]; for (int l = 0; l < L; l++) o[(size_t)k * L + l] = r >= 0 ? h[(size_t)r * L + l] : 0.0; }
+        break; }
+    case UX_A_ROUTE_DIST: {
+        std::vector<double> h((size_t)d.D * N); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.rdist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        bool searched = w->timestep > 0;
+        for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = w->dest_row[k]; o[(size_t)i * N + k] = (r >= 0 && searched) ? h[(size_t)r * N + i] : INFINITY; }
+        break; }
+    case UX_A_ROUTE_NEXT: {
+        std::vector<int> h((size_t)d.D * N); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.rnext, sizeof(int) * h.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = w->dest_row[k]; oi[(size_t)i * N + k] = r >= 0 ? h[(size_t)r * N + i] : -1; }
+        break; }
+    default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
+    }
+    return n;
+}
+
+UX_API int64_t ux_ensemble_link_stats_device(ux_world *w, void **dptr) {
+    if (!w->uploaded) return fail(w, UX_ERR_RUNTIME, "ensemble_link_stats before the simulation ran");
+    cudaSetDevice(w->device);
+    int L = (int)w->links.size();
+    if (!w->d_ens) w->d_ens = dalloc<double>(w, (size_t)L * 4);
+    if (L > 0) {
+        int rc = ensure_scratch(w, 8 * (size_t)L * 4 * w->R + 16); if (rc) return rc;
+        UX_LAUNCH(k_ensemble_partial, dim3((L + 63) / 64, w->R), dim3(64), w->stream, w->dworlds, w->d_scratch);
+        UX_LAUNCH(k_ensemble_stats, dim3((L * 4 + 127) / 128), dim3(128), w->stream, w->dworlds, w->R, (const double *)w->d_scratch, w->d_ens);
+    }
+    CUDA_OK(cudaStreamSynchronize(w->stream));
+    *dptr = w->d_ens;
+    return (int64_t)L * 4;
+}
+
+UX_API int64_t ux_ensemble_link_stats(ux_world *w, double *dst, int64_t capacity) {
+    void *d = nullptr;
+    int64_t n = ux_ensemble_link_stats_device(w, &d);
+    if (n < 0) return n;
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "capacity too small");
+    if (n > 0) CUDA_OK(cudaMemcpy(dst, d, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+UX_API const char *ux_last_error(ux_world *w) { return w ? w->err.c_str() : g_err.c_str(); }
+

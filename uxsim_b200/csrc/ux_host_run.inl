@@ -1,0 +1,194 @@
+// ux_host_run.inl -- part of engine.cu (one translation unit; included in the order engine.cu lists).
+// C-ABI, part 2: the executor (CUDA graphs per chunk shape), ux_main_loop, mid-run setters.
+
+// enqueue the kernels of `nsteps` timesteps starting at phase (t mod route_ts) = `phase` on the stream
+static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
+    int N = (int)w->nodes.size(), R = w->R;
+    cudaStream_t st = w->stream;
+    dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_WARPS - 1) / UPD_WARPS, R);
+    long long lc = 0;
+    for (int s = 0; s < nsteps; s++) {
+        if (N > 0) {
+            KT_BEGIN(UX_K_TRANSFER)
+            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
+            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node<32, 16>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
+            else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
+            KT_END(UX_K_TRANSFER) lc++;
+        }
+        if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
+        bool route = ((phase + s) % w->route_ts) == 0;
+        if (w->n_active > 0 && w->n_edges > 0) {
+            if (route) {
+                KT_BEGIN(UX_K_EDGE_COST) UX_LAUNCH(k_edge_cost, dim3((w->n_edges + 127) / 128, R), dim3(128), st, w->dworlds, s); KT_END(UX_K_EDGE_COST) lc++;
+                KT_BEGIN(UX_K_SSSP) launch_sssp(w, st); KT_END(UX_K_SSSP) lc++;
+            }
+            if (route || w->p.route_choice_update_gradual) {
+                long long tot = (long long)w->n_active * (long long)w->links.size();
+                KT_BEGIN(UX_K_DUO) UX_LAUNCH(k_duo, dim3((unsigned)((tot + 255) / 256), R), dim3(256), st, w->dworlds, w->p.route_choice_update_gradual ? 1 : 0); KT_END(UX_K_DUO) lc++;
+                KT_BEGIN(UX_K_MISC) UX_LAUNCH(k_duo_finish, dim3((w->n_active + 127) / 128, R), dim3(128), st, w->dworlds); KT_END(UX_K_MISC) lc++;
+            }
+        }
+    }
+    KT_BEGIN(UX_K_MISC) UX_LAUNCH(k_advance, dim3(1, R), dim3(32), st, w->dworlds, nsteps); KT_END(UX_K_MISC) lc++;
+    *launch_count = lc;
+}
+
+static const char *derr_text(int code) {
+    switch (code) {
+    case DERR_RING_FULL: return "link ring buffer overflow (link %d)";
+    case DERR_ROUTE_EXHAUSTED: return "Vehicle %d: specified route has no more links";
+    case DERR_ROUTE_INCONSISTENT: return "Vehicle %d: specified route is inconsistent; the forced link is not an outgoing link of the current node";
+    case DERR_AVOID_ALL: return "Vehicle %d: links_avoid excludes all outgoing links of the current node";
+    case DERR_LOG_FULL: return "vehicle log buffer overflow (link %d)";
+    default: return "device error (info %d)";
+    }
+}
+
+// World::main_loop (traffi.cpp:1642-1866)
+UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
+    if (!w->initialized) { int rc = ux_initialize_adj_matrix(w); if (rc) return rc; }
+    int start_ts = w->timestep, end_ts;
+    double time_now = w->timestep * w->dt;
+    if (duration_t < 0 && until_t < 0) end_ts = w->total_ts;
+    else if (duration_t >= 0 && until_t < 0) end_ts = (int)std::floor((duration_t + time_now) / w->dt) + 1;
+    else if (duration_t < 0 && until_t >= 0) end_ts = (int)std::floor(until_t / w->dt) + 1;
+    else return fail(w, UX_ERR_RUNTIME, "Cannot specify both `duration_t` and `until_t` parameters for `World.main_loop`");
+    if (end_ts > w->total_ts) end_ts = w->total_ts;
+    if (end_ts <= start_ts) return 0;
+    cudaSetDevice(w->device);
+    if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
+    if ((long long)w->vehs.size() != w->P_uploaded) { int rc = extend_vehicles(w); if (rc) return rc; }
+    if (w->net_dirty) { int rc = upload_link_params(w); if (rc) return rc; w->net_dirty = false; }
+    auto t_begin = std::chrono::steady_clock::now();
+    // chunks between route updates: (steps, phase); the executable graph of a chunk shape is built once and cached
+    std::vector<std::pair<int, int>> chunks;
+    for (int t = start_ts; t < end_ts;) {
+        int phase = t % w->route_ts;
+        int nsteps = std::min(std::min(end_ts - t, w->route_ts - phase), 512);
+        chunks.push_back({nsteps, phase});
+        t += nsteps;
+    }
+#ifndef UX_EMU
+    auto graph_key = [&](int nsteps, int phase) { return ((long long)nsteps << 32) | (unsigned)phase | ((long long)w->n_levels << 48); };
+    if (!w->ktiming)
+        for (auto &c : chunks) {
+            long long key = graph_key(c.first, c.second), lc = 0;
+            if (w->graphs.count(key)) continue;
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            CUDA_OK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_steps(w, c.first, c.second, &lc);
+            CUDA_OK(cudaStreamEndCapture(w->stream, &graph));
+            CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            w->graphs.emplace(key, std::make_pair(exec, lc));
+        }
+    w->graph_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (!w->ev_begin) { CUDA_OK(cudaEventCreate(&w->ev_begin)); CUDA_OK(cudaEventCreate(&w->ev_end)); }
+    CUDA_OK(cudaEventRecord(w->ev_begin, w->stream));
+#endif
+    for (auto &c : chunks) {
+        long long lc = 0;
+#ifdef UX_EMU
+        enqueue_steps(w, c.first, c.second, &lc);
+#else
+        if (w->ktiming) enqueue_steps(w, c.first, c.second, &lc);
+        else {
+            auto &g = w->graphs[graph_key(c.first, c.second)];
+            lc = g.second;
+            CUDA_OK(cudaGraphLaunch(g.first, w->stream));
+        }
+#endif
+        w->launches += lc;
+    }
+#ifndef UX_EMU
+    CUDA_OK(cudaEventRecord(w->ev_end, w->stream));
+#endif
+    CUDA_OK(cudaStreamSynchronize(w->stream));
+    CUDA_OK(cudaGetLastError());
+#ifndef UX_EMU
+    { float ms = 0.f; cudaEventElapsedTime(&ms, w->ev_begin, w->ev_end); w->last_loop_ms = ms; }
+    for (size_t i = 0; i < w->kt_ids.size(); i++) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, w->kt_events[2 * i], w->kt_events[2 * i + 1]);
+        w->k_ms[w->kt_ids[i]] += ms; w->k_launches[w->kt_ids[i]] += 1;
+        cudaEventDestroy(w->kt_events[2 * i]); cudaEventDestroy(w->kt_events[2 * i + 1]);
+    }
+    w->kt_events.clear(); w->kt_ids.clear();
+#endif
+    w->timestep = end_ts;
+    {   // device-side error words of all replicas (one block, one copy)
+        std::vector<int> e(2 * (size_t)w->R, 0);
+        CUDA_OK(cudaMemcpy(e.data(), w->d_err_all, sizeof(int) * e.size(), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < w->R; r++) if (e[2 * r]) {
+            int c0 = e[2 * r];
+            int code = (c0 == DERR_RING_FULL || c0 == DERR_LOG_FULL) ? UX_ERR_CAPACITY : c0 == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
+            return fail(w, code, derr_text(c0), e[2 * r + 1]);
+        }
+    }
+    w->loop_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    w->timestep = end_ts;
+    return 0;
+}
+
+UX_API int ux_check_simulation_ongoing(ux_world *w) { return w->timestep < w->total_ts; }
+
+// ---- interventions ---------------------------------------------------------------------------------------
+UX_API int ux_set_link_param(ux_world *w, int link, int field, double value) {
+    if (link < 0 || link >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    HLink &l = w->links[link];
+    double *rem = nullptr; double rv = 0;
+    switch (field) {
+    case UX_LINK_VMAX: if (value >= 0) { l.vmax = value; l.w = 1.0 / l.tau / l.kappa; l.capacity = l.vmax * l.w * l.kappa / (l.vmax + l.w); l.delta = 1.0 / l.kappa; } break;
+    case UX_LINK_KAPPA: if (value >= 0) { l.kappa = value; l.w = 1.0 / l.tau / l.kappa; l.capacity = l.vmax * l.w * l.kappa / (l.vmax + l.w); l.delta = 1.0 / l.kappa; l.dpl = l.delta * l.lanes; } break;
+    case UX_LINK_CAPACITY_OUT: l.cap_out = value; break;
+    case UX_LINK_CAPACITY_IN: l.cap_in = value; break;
+    case UX_LINK_CAPACITY_OUT_REMAIN: l.cap_out_rem0 = value; rem = &l.cap_out_rem0; rv = value; break;
+    case UX_LINK_CAPACITY_IN_REMAIN: l.cap_in_rem0 = value; rem = &l.cap_in_rem0; rv = value; break;
+    case UX_LINK_MERGE_PRIORITY: l.mp = value; break;
+    case UX_LINK_ROUTE_CHOICE_PENALTY: l.penalty = value; break;
+    default: return fail(w, UX_ERR_INVALID, "unknown link field %d", field);
+    }
+    if (w->uploaded) {
+        cudaSetDevice(w->device);
+        if (rem) for (int r = 0; r < w->R; r++) CUDA_OK(cudaMemcpy((field == UX_LINK_CAPACITY_OUT_REMAIN ? w->hw[r].cap_out_rem : w->hw[r].cap_in_rem) + link, &rv, sizeof(double), cudaMemcpyHostToDevice));
+        else w->net_dirty = true;
+    }
+    return 0;
+}
+
+UX_API int ux_set_link_signal_group(ux_world *w, int link, const int *sg, int n) {
+    if (link < 0 || link >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
+    if (w->uploaded && n != (int)w->links[link].sg.size()) return fail(w, UX_ERR_RUNTIME, "changing the size of a signal group after the simulation started is not supported");
+    w->links[link].sg.assign(sg, sg + n);
+    if (w->uploaded) {
+        cudaSetDevice(w->device);
+        int off = 0; for (int i = 0; i < link; i++) off += (int)w->links[i].sg.size();
+        CUDA_OK(cudaMemcpy(w->d_sg + off, sg, sizeof(int) * n, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+UX_API int ux_set_node_signal(ux_world *w, int node, const double *sig, int nsig, int phase, double sig_t) {
+    if (node < 0 || node >= (int)w->nodes.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "node id out of range");
+    HNode &n = w->nodes[node];
+    bool reset = false;
+    if (sig && nsig > 0) {
+        if (w->uploaded && nsig != (int)n.sig.size()) return fail(w, UX_ERR_RUNTIME, "changing the number of signal phases after the simulation started is not supported");
+        n.sig.assign(sig, sig + nsig);
+    }
+    if (!w->uploaded) {
+        if (sig && nsig > 0 && n.sig_phase0 >= nsig) { n.sig_phase0 = 0; n.sig_t0 = 0; }
+        if (phase >= 0) n.sig_phase0 = phase;
+        if (sig_t >= 0) n.sig_t0 = sig_t;
+        return 0;
+    }
+    (void)reset;
+    cudaSetDevice(w->device);
+    if (sig && nsig > 0) { int off = 0; for (int i = 0; i < node; i++) off += (int)w->nodes[i].sig.size(); CUDA_OK(cudaMemcpy(w->d_n_sig + off, sig, sizeof(double) * nsig, cudaMemcpyHostToDevice)); }
+    for (int r = 0; r < w->R; r++) {
+        if (phase >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_phase + node, &phase, sizeof(int), cudaMemcpyHostToDevice));
+        if (sig_t >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_t + node, &sig_t, sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ---- results ---------------------------------------------------------------------------------------------

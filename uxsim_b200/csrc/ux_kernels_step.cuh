@@ -1,0 +1,783 @@
+// ux_kernels_step.cuh -- part of engine.cu (one translation unit; included in the order engine.cu lists).
+// The two kernels of a timestep: k_node (link update, generate, signal, transfer) and k_update (car following, link head, logs).
+
+// ---------------------------------------------------------------------------------------------------
+// K1: Link::update (traffi.cpp:542-565, 599-622) for the node's out-links, then Node::generate (105-189),
+//     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
+// ---------------------------------------------------------------------------------------------------
+template <int MC, int MD>
+struct PreSmem {
+    int choice[MC], g_vid[MC], g_err[MC];
+    int o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD];
+    long long o_roff[MD];
+    double o_ci[MD], o_dpl[MD], o_vmax[MD], o_cumarr[MD];
+    double w_x[MC];
+};
+
+template <int MC, int MD>
+UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *rel, int n, int t, int lane) {
+    int cur = t & 1, L = W.L;
+    int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
+    int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
+    bool fresh = (t % W.itt) == 0;
+    // ---- instantaneous travel time of the out-links (whole warp per link, only every `itt` steps)
+    if (fresh) {
+        for (int k = 0; k < nout; k++) {
+            int l = W.n_out[o0 + k];
+            int hd = W.head[cur * L + l], nq = W.tail[l] - hd;
+            double tt;
+            if (nq > 0) {
+                double vs = warp_queue_vsum(W, l, hd, nq, lane);
+                double avg = vs / (double)nq;
+                tt = avg > 0.0 ? W.l_length[l] / avg : W.l_length[l] / (W.l_vmax[l] / 100.0);
+            } else tt = W.l_length[l] / W.l_vmax[l];
+            if (lane == 0) tt_s[k] = tt;
+        }
+        WARP_SYNC();
+    }
+    // ---- scalar link update (Link::update traffi.cpp:542-565).  A link's inflow side (arrival curve, capacity_in
+    //      tokens, instantaneous travel time) belongs to its START node, its outflow side (departure curve, capacity_out
+    //      tokens, pops of this step) to its END node -- the same ownership the transfer uses, so that this node's whole
+    //      timestep (update, generate, signal, transfer) needs nothing from other nodes except the dependency wait.
+    WARP_FOR(ln) {
+        for (int k = ln; k < nout; k += 32) {
+            int l = W.n_out[o0 + k];
+            size_t row = (size_t)t * L + l;
+            if (fresh) W.tt_inst[row] = tt_s[k];
+            else if (t > 0) W.tt_inst[row] = W.tt_inst[row - L];
+            if (t != 0) W.cum_arr[row] = W.cum_arr[row - L];
+            double ci = W.l_cap_in[l];
+            if (ci < 10e9) { if (W.cap_in_rem[l] < W.dn * W.l_lanes[l]) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+        }
+        for (int k = ln; k < nin; k += 32) {
+            int l = W.n_in[i0 + k];
+            size_t row = (size_t)t * L + l;
+            if (t != 0) W.cum_dep[row] = W.cum_dep[row - L];
+            double co = W.l_cap_out[l];
+            if (co < 10e9) { if (W.cap_out_rem[l] < W.dn * W.l_lanes[l]) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
+            W.pop_k2[l] = 0;
+        }
+    }
+    WARP_SYNC();
+    // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
+    //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
+    int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
+    while (av < glen) {
+        WARP_FOR(ln) if (ln == 0) *rel = 0;
+        WARP_SYNC();
+        WARP_FOR(ln) { int idx = av + ln; if (idx < glen && W.gen_ts[g0 + idx] <= t - 1) atomicAdd(rel, 1); }
+        WARP_SYNC();
+        int c = *rel;
+        WARP_SYNC();
+        av += c;
+        if (c < 32) break;
+    }
+    // ---- generate (traffi.cpp:105-189).  The route draws of the first `natt` waiting platoons and the tail state of the
+    //      out-links are fetched in parallel; lane 0 then walks the attempts on shared memory and stops at the first refusal.
+    int gh = W.gen_head[n];
+    int natt = av - gh;
+    { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > MC) natt = MC; }
+    if (nout == 0) natt = 0;
+    if (natt > 0) {
+        WARP_FOR(ln) {
+            for (int i = ln; i < natt; i += 32) {
+                int vid = W.gen_list[g0 + gh + i], e = 0;
+                G.g_vid[i] = vid;
+                G.choice[i] = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
+                G.g_err[i] = e;
+            }
+            for (int q = ln; q < nout; q += 32) {
+                int ol = W.n_out[o0 + q];
+                int hd = W.head[cur * L + ol], tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+                long long o = W.l_roff[ol];
+                double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[(size_t)t * L + ol];
+                int sz = tl - hd;
+                int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
+                G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
+                G.o_ci[q] = ci_; G.o_dpl[q] = dpl_; G.o_vmax[q] = vm_; G.o_cumarr[q] = ca_; G.o_lastlane[q] = ll_;
+                G.o_win_n[q] = sz < lanes ? sz : lanes;
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(ln) if (ln == 0) { int acc = 0; for (int q = 0; q < nout; q++) { G.o_win_off[q] = acc; acc += G.o_lanes[q]; } G.o_win_off[nout] = acc; }
+        WARP_SYNC();
+        WARP_FOR(ln) {
+            int tot = G.o_win_off[nout];
+            for (int e = ln; e < tot && e < MC; e += 32) {
+                int q = 0;
+                while (G.o_win_off[q + 1] <= e) q++;
+                int k = e - G.o_win_off[q];
+                if (k < G.o_win_n[q]) {
+                    int sz = G.o_tail[q] - G.o_hd[q];
+                    G.w_x[e] = W.X[(size_t)cur * W.C + G.o_roff[q] + ring_slot(G.o_hd[q], sz - G.o_win_n[q] + k, G.o_cap[q])];
+                }
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(ln) if (ln == 0) {
+            for (int i = 0; i < natt; i++) {
+                int vid = G.g_vid[i], ol = G.choice[i];
+                if (G.g_err[i]) { dev_error(W, G.g_err[i], vid); break; }
+                W.v_next[vid] = ol;
+                if (ol < 0) break;
+                int q = 0;
+                while (q < nout && W.n_out[o0 + q] != ol) q++;
+                int lanes = G.o_lanes[q], sz = G.o_tail[q] - G.o_hd[q], w0 = G.o_win_off[q];
+                bool ok = false;  // traffi.cpp:130-142
+                if (sz < lanes) ok = true;
+                else if (G.w_x[w0] > G.o_dpl[q]) ok = true;
+                if (G.o_ci[q] < W.dn) ok = false;
+                if (!ok) break;
+                if (sz >= G.o_cap[q]) { dev_error(W, DERR_RING_FULL, ol); break; }
+                gh++;
+                int lane_new = sz > 0 ? (G.o_lastlane[q] + 1) % lanes : 0;
+                int slot = ring_slot(G.o_tail[q], 0, G.o_cap[q]);
+                long long o = G.o_roff[q];
+                W.X[(size_t)cur * W.C + o + slot] = 0.0;
+                W.X[(size_t)(cur ^ 1) * W.C + o + slot] = 0.0;
+                W.V[o + slot] = G.o_vmax[q];
+                W.VID[o + slot] = vid;
+                W.LANE[o + slot] = lane_new;
+                G.o_tail[q] += 1; G.o_lastlane[q] = lane_new;
+                if (G.o_win_n[q] < lanes) { G.w_x[w0 + G.o_win_n[q]] = 0.0; G.o_win_n[q] += 1; }
+                else { for (int e = w0; e < w0 + lanes - 1; e++) G.w_x[e] = G.w_x[e + 1]; G.w_x[w0 + lanes - 1] = 0.0; }
+                W.v_state[vid] = UX_VS_RUN;
+                if (W.log_mode) W.v_gen_ts[vid] = t;
+                W.v_atl[vid] = (double)t * W.dt;
+                W.v_entry_x[vid] = 0.0;
+                mark_entered(W, vid, ol, t);
+                G.o_cumarr[q] += W.dn;
+                G.o_ci[q] -= W.dn;
+            }
+            W.gen_head[n] = gh;
+        }
+        WARP_SYNC();
+        WARP_FOR(ln) {
+            for (int q = ln; q < nout; q += 32) {
+                int ol = W.n_out[o0 + q];
+                W.cap_in_rem[ol] = G.o_ci[q]; W.cum_arr[(size_t)t * L + ol] = G.o_cumarr[q]; W.tail[ol] = G.o_tail[q];
+            }
+        }
+        WARP_SYNC();
+    }
+    WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; } }
+    WARP_FOR(ln) if (ln == 0) {
+        W.gen_avail[n] = av;
+        // ---- signal (Node::signal_update traffi.cpp:194-207)
+        int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
+        int ph = W.sig_phase[n];
+        if (nsig > 1) {
+            double st = W.sig_t[n];
+            if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
+            st += W.dt;
+            W.sig_t[n] = st; W.sig_phase[n] = ph;
+        }
+        W.sig_log[(size_t)t * W.N + n] = ph;
+        // ---- node flow capacity (Node::flow_capacity_update traffi.cpp:226-234)
+        double fc = W.n_fc[n];
+        if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
+        else W.fc_rem[n] = 10e10;
+    }
+    WARP_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: Node::transfer (traffi.cpp:239-445).  One warp per node of dependency level `level`.
+//
+// The reference algorithm is inherently serial inside a node (slots are tried one after another and every move
+// changes the queues the next slot sees), but everything it READS can be known up front.  So the warp first
+// gathers the node's whole neighbourhood into shared memory in parallel (in-link heads, the candidate platoons at
+// those heads, and for every requested out-link its tail state plus the window of its last `lanes` platoons),
+// lane 0 then runs the serial slot loop purely on shared memory (global stores only, no dependent global loads),
+// and the lanes write the per-link accumulators back in parallel.  A dependent chain of a few hundred global
+// loads becomes five.
+// ---------------------------------------------------------------------------------------------------
+template <int MC, int MD>
+struct XferSmem {
+    // in-links
+    int il[MD], hd[MD], hc[MD], cap[MD], popped[MD], pos_off[MD + 1], evc[MD], trips[MD];
+    long long roff[MD];
+    double co_rem[MD], mp[MD], vmax[MD], cumdep[MD];
+    unsigned char sig_ok[MD];
+    // head positions of the in-links
+    int p_vid[MC], p_next[MC], p_dts[MC];
+    short p_in[MC], p_j[MC], c_idx[MC], expd[MC];
+    unsigned char p_flag[MC];
+    double p_x[MC], p_xold[MC], p_v[MC], p_mr[MC], p_atl[MC], p_ex[MC], p_dist[MC];
+    int nc, npos, nol, any_wait, nexp, first, cur_slot, n_picks;
+    int omask[MD][2];          // per requested out-link: candidates currently eligible to move onto it
+    unsigned char ogood[MD];   // per requested out-link: acceptance test result
+    unsigned char c_first[MC], c_q[MC];
+    double fc_rem;
+    short shuf_j[MC];
+    double u_merge[MC];
+    // requested out-links
+    int ol[MD], o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD];
+    long long o_roff[MD];
+    double o_ci[MD], o_dpl[MD], o_len[MD], o_vmax[MD], o_cumarr[MD];
+    double w_x[MC], w_xold[MC];  // window of the last `lanes` platoons of each out-link (oldest first)
+};
+
+template <int MC, int MD>
+UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem<MC, MD> &S, int p, int t) {  // Vehicle::end_trip traffi.cpp:886-927
+    int ii = S.p_in[p], il = S.il[ii], vid = S.p_vid[p];
+    S.trips[ii] += 1;
+    S.cumdep[ii] += W.dn;
+    double atl = S.p_atl[p];
+    {   // record_tt_event
+        int s = (int)(atl / W.dt);
+        if (s < 0) s = 0;
+        if (s >= W.T) s = W.T - 1;
+        int ord = ++S.evc[ii];
+        W.ev_ord[(size_t)s * W.L + il] = ord;
+        W.ev_tt[(size_t)s * W.L + il] = ((double)t + 1.0) * W.dt - atl;
+    }
+    W.v_atl[vid] = (double)t * W.dt;
+    W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
+    W.v_link[vid] = -1;
+    if (S.p_flag[p] & VF_ABORT) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+    else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)S.p_dts[p] * W.dt; }
+    if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 2; }
+    W.v_flags[vid] = 0;
+    S.popped[ii] += 1;
+}
+
+#ifndef XFER_WARPS
+#define XFER_WARPS 4
+#endif
+template <int MC, int MD>
+UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
+    int cur = t & 1, L = W.L;
+    size_t C = (size_t)W.C;
+    int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
+    if (nin == 0) return;
+    int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = W.sig_phase[n];
+    // ---- A1: in-link state
+    WARP_FOR(lane) {
+        for (int ii = lane; ii < nin; ii += 32) {
+            // loads first, shared stores afterwards: the pointers are generic, so a shared store between two loads
+            // would serialise them (the compiler must assume the load may target shared memory)
+            int il = W.n_in[i0 + ii];
+            int hd_ = W.head[cur * L + il], hc_ = W.hcount[il], cap_ = W.l_rcap[il], evc_ = W.ev_cnt[il], trips_ = W.trips[il];
+            long long roff_ = W.l_roff[il];
+            double co_ = W.cap_out_rem[il], mp_ = W.l_mp[il], vm_ = W.l_vmax[il], cd_ = W.cum_dep[(size_t)t * L + il];
+            bool ok = true;
+            if (nsig > 1) { int g0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - g0; ok = list_has(W.l_sg + g0, gl, phase); }
+            S.il[ii] = il; S.hd[ii] = hd_; S.hc[ii] = hc_; S.cap[ii] = cap_; S.roff[ii] = roff_;
+            S.popped[ii] = 0; S.evc[ii] = evc_; S.trips[ii] = trips_;
+            S.co_rem[ii] = co_; S.mp[ii] = mp_; S.vmax[ii] = vm_; S.cumdep[ii] = cd_;
+            S.sig_ok[ii] = ok ? 1 : 0;
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        int acc = 0;
+        for (int ii = 0; ii < nin; ii++) { S.pos_off[ii] = acc; acc += S.hc[ii]; }
+        S.pos_off[nin] = acc; S.npos = acc < MC ? acc : MC;
+    }
+    WARP_SYNC();
+    int npos = S.npos;
+    if (npos == 0) return;
+    // ---- A2: the platoons at the in-link heads
+    WARP_FOR(lane) {
+        for (int p = lane; p < npos; p += 32) {
+            int ii = 0;
+            while (S.pos_off[ii + 1] <= p) ii++;
+            int j = p - S.pos_off[ii];
+            long long o = S.roff[ii];
+            int slot = ring_slot(S.hd[ii], j, S.cap[ii]);
+            int vid = W.VID[o + slot];
+            unsigned char f = W.v_flags[vid];
+            int nx = W.v_next[vid];
+            double x_ = 0, xo_ = 0, v_ = 0, mr_ = 0, atl_ = 0, ex_ = 0, di_ = 0; int dts_ = 0;
+            if (f & (VF_CAND | VF_WAIT_END)) {
+                x_ = W.X[(size_t)cur * C + o + slot]; xo_ = W.X[(size_t)(cur ^ 1) * C + o + slot]; v_ = W.V[o + slot];
+                mr_ = W.v_mr[vid]; atl_ = W.v_atl[vid]; ex_ = W.v_entry_x[vid]; di_ = W.v_dist[vid]; dts_ = W.v_depart_ts[vid];
+            }
+            S.p_vid[p] = vid; S.p_in[p] = (short)ii; S.p_j[p] = (short)j; S.p_flag[p] = f; S.p_next[p] = nx;
+            S.p_x[p] = x_; S.p_xold[p] = xo_; S.p_v[p] = v_; S.p_mr[p] = mr_; S.p_atl[p] = atl_; S.p_ex[p] = ex_; S.p_dist[p] = di_; S.p_dts[p] = dts_;
+        }
+    }
+    WARP_SYNC();
+    // ---- A3: candidates sorted by vehicle id (traffi.cpp:250-253; rank sort, one lane per head position) and the
+    //          distinct requested out-links in order of first appearance (traffi.cpp:260-273)
+    WARP_FOR(lane) if (lane == 0) { S.nc = 0; S.any_wait = 0; }
+    WARP_SYNC();
+    WARP_FOR(lane) {
+        for (int p = lane; p < npos; p += 32) {
+            unsigned char f = S.p_flag[p];
+            if (f & VF_WAIT_END) atomicOr(&S.any_wait, 1);
+            if (f & VF_CAND) {
+                int vid = S.p_vid[p], rank = 0;
+                for (int q = 0; q < npos; q++) if ((S.p_flag[q] & VF_CAND) && S.p_vid[q] < vid) rank++;
+                S.c_idx[rank] = (short)p;
+                atomicAdd(&S.nc, 1);
+            }
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) {
+        int ncl = S.nc;
+        for (int k = lane; k < ncl; k += 32) {
+            int nl = S.p_next[S.c_idx[k]];
+            bool first = nl >= 0;
+            for (int q = 0; q < k && first; q++) if (S.p_next[S.c_idx[q]] == nl) first = false;
+            S.c_first[k] = first ? 1 : 0;
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        int nol = 0;
+        for (int k = 0; k < S.nc; k++) if (S.c_first[k] && nol < MD) S.ol[nol++] = S.p_next[S.c_idx[k]];
+        S.nol = nol;
+    }
+    WARP_SYNC();
+    int nc = S.nc, nol = S.nol;
+    if (nc == 0 && !S.any_wait) return;
+    WARP_FOR(lane) {
+        for (int k = lane; k < nc; k += 32) {
+            int nl = S.p_next[S.c_idx[k]], q = 255;
+            for (int r = 0; r < nol; r++) if (S.ol[r] == nl) { q = r; break; }
+            S.c_q[k] = (unsigned char)q;
+        }
+    }
+    // ---- dependency wait (only nodes with SEES_POPS out-links): everything above -- in-link heads, candidate sort -- is
+    //      independent of the lower-level nodes, so it overlaps their work; only the out-link tail state needs their pops.
+    if (has_deps) {
+        WARP_FOR(lane) {
+            for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
+                volatile int *done = W.node_done + W.dep_list[q];
+#ifdef UX_EMU
+                if (*done < t + 1) dev_error(W, DERR_RING_FULL, -1);
+#else
+                while (*done < t + 1) __nanosleep(32);
+#endif
+            }
+        }
+#ifndef UX_EMU
+        __threadfence();
+#endif
+        WARP_SYNC();
+    }
+    // ---- A4: out-link tail state
+    WARP_FOR(lane) {
+        for (int q = lane; q < nol; q += 32) {
+            int ol = S.ol[q];
+            int hd = W.head[cur * L + ol], fl_ = W.l_flags[ol], pk_ = ld_cg(W.pop_k2 + ol);  // written by a lower level in this launch
+            int tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+            long long o = W.l_roff[ol];
+            double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[(size_t)t * L + ol];
+            if (fl_ & LF_SEES_POPS) hd += pk_;
+            int sz = tl - hd;
+            int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
+            S.o_hd[q] = hd; S.o_tail[q] = tl; S.o_lanes[q] = lanes; S.o_cap[q] = cap; S.o_roff[q] = o;
+            S.o_ci[q] = ci_; S.o_dpl[q] = dpl_; S.o_len[q] = len_; S.o_vmax[q] = vm_; S.o_cumarr[q] = ca_;
+            S.o_lastlane[q] = ll_;
+            S.o_win_n[q] = sz < lanes ? sz : lanes;
+        }
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) if (lane == 0) {
+        int acc = 0;
+        for (int q = 0; q < nol; q++) { S.o_win_off[q] = acc; acc += S.o_lanes[q]; }
+        S.o_win_off[nol] = acc;
+    }
+    WARP_SYNC();
+    WARP_FOR(lane) {
+        int tot = S.o_win_off[nol];
+        for (int e = lane; e < tot && e < MC; e += 32) {
+            int q = 0;
+            while (S.o_win_off[q + 1] <= e) q++;
+            int k = e - S.o_win_off[q];
+            if (k < S.o_win_n[q]) {
+                int sz = S.o_tail[q] - S.o_hd[q];
+                int slot = ring_slot(S.o_hd[q], sz - S.o_win_n[q] + k, S.o_cap[q]);
+                S.w_x[e] = W.X[(size_t)cur * C + S.o_roff[q] + slot];
+                S.w_xold[e] = W.X[(size_t)(cur ^ 1) * C + S.o_roff[q] + slot];
+            }
+        }
+    }
+    WARP_SYNC();
+    // ---- B: the slot loop.  Slots are inherently sequential (each move changes what the next slot sees), but inside
+    //          a slot the eligibility scan over the candidates runs one lane per candidate, and all random numbers of
+    //          the node (shuffle indices, merge-lottery uniforms) are drawn up front in parallel: Philox is stateless.
+    WARP_FOR(lane) if (lane == 0) {
+        int nexp = 0;
+        for (int q = 0; q < nol; q++) for (int r = 0; r < S.o_lanes[q] && nexp < MC; r++) S.expd[nexp++] = (short)q;
+        S.nexp = nexp;
+    }
+    WARP_SYNC();
+    int nexp = S.nexp;
+    int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
+    if (!W.hard_det) {
+        WARP_FOR(lane) {
+            for (int i = 1 + lane; i < nexp; i += 32)  // Fisher-Yates step i uses draw number (nexp-1-i) (traffi.cpp:276-282)
+                S.shuf_j[i] = (short)ux_rng_below(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nexp - 1 - i), i + 1);
+            for (int d = lane; d < nexp; d += 32)
+                S.u_merge[d] = ux_rng_uniform(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + d));
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) {
+            for (int i = nexp - 1; i > 0; i--) { int j = S.shuf_j[i]; short tmp = S.expd[i]; S.expd[i] = S.expd[j]; S.expd[j] = tmp; }
+        }
+        WARP_SYNC();
+    }
+    // Rounds instead of slots: a slot whose out-link cannot accept or has no eligible candidate changes nothing (and
+    // draws nothing), so each round evaluates every out-link / candidate in parallel against the current state, jumps
+    // to the first slot (in shuffled order) that moves a platoon, applies that one move on lane 0, and repeats.
+    double fc = W.n_fc[n];
+    WARP_FOR(lane) if (lane == 0) { S.cur_slot = 0; S.n_picks = 0; S.fc_rem = W.fc_rem[n]; }
+    WARP_SYNC();
+    while (true) {
+        WARP_FOR(lane) {
+            if (lane == 0) S.first = 0x7fffffff;
+            for (int q = lane; q < nol; q += 32) {
+                S.omask[q][0] = 0; S.omask[q][1] = 0;
+                int lanes_ol = S.o_lanes[q], sz = S.o_tail[q] - S.o_hd[q];
+                bool ok = false;  // acceptance (traffi.cpp:285-300)
+                if (sz < lanes_ol) ok = true;
+                else if (S.w_x[S.o_win_off[q]] > S.o_dpl[q]) ok = true;
+                if (S.o_ci[q] < W.dn) ok = false;
+                if (S.fc_rem < W.dn) ok = false;
+                S.ogood[q] = ok ? 1 : 0;
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) {
+            for (int k = lane; k < nc; k += 32) {
+                int p = S.c_idx[k], q = S.c_q[k];
+                if (p < 0 || q == 255) continue;
+                int ii = S.p_in[p];
+                if (S.p_j[p] != S.popped[ii]) continue;  // front of its in-link
+                if (S.co_rem[ii] < W.dn) continue;
+                if (!S.sig_ok[ii]) continue;
+                atomicOr(&S.omask[q][k >> 5], (int)(1u << (k & 31)));
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) {
+            for (int s = S.cur_slot + lane; s < nexp; s += 32) {
+                int q = S.expd[s];
+                if (S.ogood[q] && (S.omask[q][0] | S.omask[q][1])) { atomicMin(&S.first, s); break; }
+            }
+        }
+        WARP_SYNC();
+        int s = S.first;
+        if (s == 0x7fffffff) break;
+        WARP_FOR(lane) if (lane == 0) {
+            int q = S.expd[s], ol = S.ol[q];
+            unsigned m0 = (unsigned)S.omask[q][0], m1 = (unsigned)S.omask[q][1];
+            int lanes_ol = S.o_lanes[q];
+            int sz = S.o_tail[q] - S.o_hd[q], w0 = S.o_win_off[q];
+            double fc_rem = S.fc_rem;
+            int n_picks = S.n_picks;
+            short mv[MC]; double mp[MC]; int nm = 0;
+            for (int wd = 0; wd < 2; wd++) {  // eligible candidates in ascending vehicle id
+                unsigned m = wd ? m1 : m0;
+                while (m) {
+                    int bit = 0; while (!((m >> bit) & 1u)) bit++;
+                    m &= m - 1;
+                    int k = wd * 32 + bit;
+                    mv[nm] = (short)k; mp[nm] = S.mp[S.p_in[S.c_idx[k]]]; nm++;
+                }
+            }
+            int pick;
+            if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
+            else pick = weighted_pick(mp, nm, S.u_merge[n_picks++]);
+            int k = mv[pick], p = S.c_idx[k], vid = S.p_vid[p], ii = S.p_in[p], il = S.il[ii];
+            S.co_rem[ii] -= W.dn; S.o_ci[q] -= W.dn;
+            if (fc >= 0.0) fc_rem -= W.dn;
+            S.cumdep[ii] += W.dn; S.o_cumarr[q] += W.dn;
+            double atl = S.p_atl[p];
+            {   // record_tt_event (traffi.cpp:357-362)
+                int es = (int)(atl / W.dt);
+                if (es < 0) es = 0;
+                if (es >= W.T) es = W.T - 1;
+                int ord = ++S.evc[ii];
+                W.ev_ord[(size_t)es * L + il] = ord;
+                W.ev_tt[(size_t)es * L + il] = (double)t * W.dt - atl;
+            }
+            W.v_atl[vid] = (double)t * W.dt;
+            W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
+            S.popped[ii] += 1;
+            if (W.no_cyclic) { int sn = W.l_start[ol]; W.v_visited[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
+            { int k = W.v_trav[vid]; W.v_trav[vid] = k + 1; record_traversal(W, vid, k, ol, t); }
+            W.v_link[vid] = ol;
+            W.v_flags[vid] = 0;
+            // carry the residual move onto the new link (traffi.cpp:400-419)
+            double x_next = S.p_mr[p] * S.o_vmax[q] / S.vmax[ii];
+            if (sz >= lanes_ol) {
+                double x_cong = S.w_xold[w0] - S.o_dpl[q];
+                if (x_cong < 0.0) x_cong = 0.0;
+                if (x_next > x_cong) x_next = x_cong;
+            }
+            if (x_next >= S.o_len[q]) x_next = S.o_len[q];
+            if (x_next < 0.0) x_next = 0.0;
+            if (sz >= S.o_cap[q]) dev_error(W, DERR_RING_FULL, ol);
+            else {  // push (lane rule traffi.cpp:385-390)
+                int lane_new = sz > 0 ? (S.o_lastlane[q] + 1) % lanes_ol : 0;
+                int slot = ring_slot(S.o_tail[q], 0, S.o_cap[q]);
+                long long o = S.o_roff[q];
+                W.X[(size_t)cur * C + o + slot] = x_next;
+                W.X[(size_t)(cur ^ 1) * C + o + slot] = S.p_xold[p];
+                W.V[o + slot] = S.p_v[p] + x_next / W.dt;
+                W.VID[o + slot] = vid;
+                W.LANE[o + slot] = lane_new;
+                S.o_tail[q] += 1; S.o_lastlane[q] = lane_new;
+                if (S.o_win_n[q] < lanes_ol) { int e = w0 + S.o_win_n[q]; S.w_x[e] = x_next; S.w_xold[e] = S.p_xold[p]; S.o_win_n[q] += 1; }
+                else {
+                    for (int e = w0; e < w0 + lanes_ol - 1; e++) { S.w_x[e] = S.w_x[e + 1]; S.w_xold[e] = S.w_xold[e + 1]; }
+                    S.w_x[w0 + lanes_ol - 1] = x_next; S.w_xold[w0 + lanes_ol - 1] = S.p_xold[p];
+                }
+            }
+            W.v_entry_x[vid] = x_next;
+            W.v_mr[vid] = 0.0;
+            S.c_idx[k] = -1;  // remove from incoming
+            // the new front of the in-link may be waiting for its trip end (traffi.cpp:421-424)
+            if (S.popped[ii] < S.hc[ii]) {
+                int fp = S.pos_off[ii] + S.popped[ii];
+                if (fp < npos && (S.p_flag[fp] & VF_WAIT_END)) xfer_end_trip(W, S, fp, t);
+            }
+            S.fc_rem = fc_rem; S.n_picks = n_picks; S.cur_slot = s + 1;
+        }
+        WARP_SYNC();
+    }
+    WARP_FOR(lane) if (lane == 0) {
+        // flush trip-end-waiting fronts (traffi.cpp:432-441)
+        for (int ii = 0; ii < nin; ii++) {
+            int lanes = S.hc[ii];  // hcount = min(lanes, queue length): positions beyond it cannot be waiting
+            for (int r = 0; r < lanes; r++) {
+                if (S.popped[ii] >= S.hc[ii]) break;
+                int fp = S.pos_off[ii] + S.popped[ii];
+                if (fp >= npos || !(S.p_flag[fp] & VF_WAIT_END)) break;
+                xfer_end_trip(W, S, fp, t);
+            }
+        }
+        W.fc_rem[n] = S.fc_rem;
+    }
+    WARP_SYNC();
+    // ---- C: write the per-link accumulators back
+    WARP_FOR(lane) {
+        for (int ii = lane; ii < nin; ii += 32) {
+            int il = S.il[ii];
+            W.cap_out_rem[il] = S.co_rem[ii]; W.cum_dep[(size_t)t * L + il] = S.cumdep[ii];
+            W.pop_k2[il] = S.popped[ii]; W.ev_cnt[il] = S.evc[ii]; W.trips[il] = S.trips[ii];
+        }
+        for (int q = lane; q < nol; q += 32) {
+            int ol = S.ol[q];
+            W.cap_in_rem[ol] = S.o_ci[q]; W.cum_arr[(size_t)t * L + ol] = S.o_cumarr[q]; W.tail[ol] = S.o_tail[q];
+        }
+    }
+}
+
+// k_node: one warp runs a node's whole timestep -- Link::update of the sides it owns, Node::generate, signal, node
+// capacity (pre_node) and Node::transfer (xfer_node).
+// All dependency levels run in ONE launch: warps are ordered by (level, node id), and a warp of level k > 0 waits
+// until the specific lower-level nodes it depends on have finished this step (they are dispatched earlier -- the
+// same forward-progress assumption as decoupled look-back scans).  Levels exist only for links short enough that the serial id-ordered
+// visibility of Node.transfer matters (DESIGN.md "transfer order"); most networks have a single level and never wait.
+template <int MC, int MD>
+union NodeSmem {  // the two halves of a node's timestep use shared memory one after the other
+    PreSmem<MC, MD> pre;
+    XferSmem<MC, MD> xf;
+};
+
+// MC / MD bound the sum of lanes and the degree of a node; the launcher picks the smallest instantiation the network fits
+// in, because the shared-memory footprint per warp decides how many node warps are resident.
+template <int MC, int MD>
+__global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const DevWorld *worlds, int step_off) {
+    // replica = blockIdx.x (fastest in launch order): the blocks resident together are the same nodes of different replicas
+    // -- same code path, same static tables -- and every replica's dependency chains start in the first wave
+    LOAD_WORLD_N(W, worlds, (XFER_WARPS > 1 ? 64 : 32), blockIdx.x)
+    WARP_BEGIN
+    __shared__ NodeSmem<MC, MD> sm_all[XFER_WARPS];
+    __shared__ double tt_all[XFER_WARPS][MD];
+    __shared__ int rel_all[XFER_WARPS];
+    int warp = (int)((blockIdx.y * blockDim.x + threadIdx.x) >> 5), wib = (int)((threadIdx.x >> 5) % XFER_WARPS);
+    if (warp >= W.N) return;
+    int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
+    int lvl_raw = W.n_levels > 1 ? W.lvl_level[warp] : 0, lvl = lvl_raw & 0xffff;  // bit 16: some node waits for this one
+    pre_node(W, sm_all[wib].pre, tt_all[wib], &rel_all[wib], n, t, (int)(threadIdx.x & 31));
+#ifndef UX_EMU
+    __threadfence_block();
+#endif
+    XferSmem<MC, MD> &S = sm_all[wib].xf;
+    xfer_node(W, S, n, t, lvl > 0);
+    if (lvl_raw >> 16) {  // publish completion only where somebody is waiting: the fence is not free
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)(W.node_done + n)) = t + 1; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: Vehicle::car_follow_newell (traffi.cpp:798-823) + Vehicle::update RUN branch (844-878) for every
+//     occupied ring slot.  The warp owning a link's first segment additionally handles the link head: the
+//     platoons that can be at the link end are exactly the first `lanes` queue positions (anything further back
+//     has a leader on the same link), so their trip end / abort / next-link choice is evaluated by one lane per
+//     position in parallel and only the "is it the front" prefix (traffi.cpp:861, 869) is resolved serially.
+// ---------------------------------------------------------------------------------------------------
+// One RUN log record (Vehicle::log_data traffi.cpp:1060-1110) for the platoon at queue position `pos` of link l, taken
+// BEFORE this step's move.  The spacing follows the reference's id-ordered emulation (1081-1095): a lower-id leader is
+// seen after its move (or not at all if it just ended its trip), a higher-id leader before its move.
+UX_DEV void log_run_record(const DevWorld &W, int l, int t, int cur, int hd, int n, int pos, int cap, long long o, int lanes,
+                           double len, double udt, double dpl, int n_ended, int relabel_pushes) {
+    size_t C = (size_t)W.C;
+    const double *Xc = W.X + (size_t)cur * C + o;
+    int p = ring_slot(hd, pos, cap);
+    int vid = W.VID[o + p];
+    double x = Xc[p], v = W.V[o + p];
+    int lane = pos < relabel_pushes ? pos % lanes : W.LANE[o + p];
+    double s = -1.0;
+    if (pos >= lanes) {
+        int pl = pos - lanes, lp = ring_slot(hd, pl, cap);
+        int lvid = W.VID[o + lp];
+        double xl = Xc[lp];
+        if (lvid < vid) {
+            if (pl >= n_ended) {  // leader still on the link after its own update: its post-move position
+                double xn = xl + udt;
+                if (pl >= lanes) { double gap = Xc[ring_slot(hd, pl - lanes, cap)] - dpl; if (gap < xl) gap = xl; if (xn > gap) xn = gap; }
+                if (xn < xl) xn = xl;
+                if (xn > len) xn = len;
+                s = xn - x;
+            }
+        } else s = xl - x;
+    }
+    unsigned long long idx = atomicAdd(W.lg_count, 1ull);
+    if ((long long)idx >= W.lg_cap) { dev_error(W, DERR_LOG_FULL, l); return; }
+    W.lg_vid[idx] = vid; W.lg_t[idx] = t; W.lg_link[idx] = l; W.lg_lane[idx] = lane; W.lg_x[idx] = x; W.lg_v[idx] = v; W.lg_s[idx] = s;
+}
+
+#define UX_MAXLANE 64
+#define UPD_WARPS 4
+struct HeadSmem {
+    int vid[UX_MAXLANE], next[UX_MAXLANE], dts[UX_MAXLANE];
+    unsigned char kind[UX_MAXLANE];  // 0 not at end, 1 trip end, 2 abort, 3 transfer candidate
+    double xn[UX_MAXLANE], atl[UX_MAXLANE], ex[UX_MAXLANE], dist[UX_MAXLANE];
+    int k_ended;
+};
+
+// 4 warps per block and <= 48 registers (10 blocks per SM): the kernel is a swarm of tiny, latency-bound warps -- measured
+// best among {8x4, 8x5, 4x10, 4x12} blocks-per-SM variants at 32 replicas.
+__global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *worlds, int step_off) {
+    LOAD_WORLD(W, worlds)
+    WARP_BEGIN
+    __shared__ HeadSmem hs_all[UPD_WARPS];
+    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (gw >= W.nseg) return;
+    // work item = (link, part): the warp sweeps the 32-position windows part, part+nparts, ... of the link's queue, so the
+    // work is proportional to the platoons present, and long queues are shared by several warps
+    int l = W.seg_link[gw], part = W.seg_start[gw] & 0xffff, nparts = W.seg_start[gw] >> 16, L = W.L;
+    int t = *W.t_base + step_off, cur = t & 1;
+    size_t C = (size_t)W.C;
+    int cap = W.l_rcap[l];
+    long long o = W.l_roff[l];
+    int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], tl = W.tail[l];
+    int lanes = W.l_lanes[l];
+    double len = W.l_length[l], udt = W.l_udt[l], dpl = W.l_dpl_dn[l];
+    int hd = hd0 + pk2, n = tl - hd;
+    int s0 = part;
+    const double *Xc = W.X + (size_t)cur * C + o;
+    if (s0 == 0) {
+        // ---- link head
+        HeadSmem &H = hs_all[(threadIdx.x >> 5) % UPD_WARPS];
+        int hc = n < lanes ? n : lanes;
+        if (hc > UX_MAXLANE) hc = UX_MAXLANE;
+        int end_node = W.l_end[l];
+        bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
+        WARP_FOR(lane) {
+            for (int j = lane; j < hc; j += 32) {
+                int slot = ring_slot(hd, j, cap);
+                int vid = W.VID[o + slot];
+                double x = Xc[slot];
+                int dest_ = W.v_dest[vid];
+                double atl_ = W.v_atl[vid], ex_ = W.v_entry_x[vid], di_ = W.v_dist[vid]; int dts_ = W.v_depart_ts[vid];
+                double xn = x + udt;  // positions < lanes have no leader
+                if (xn < x) xn = x;
+                bool over = xn > len;
+                double mr_ = xn - len;
+                if (over) xn = len;
+                unsigned char kind = 0;
+                int nx = -1;
+                if (fabs(xn - len) < 1e-9) {
+                    if (end_node == dest_) kind = 1;
+                    else if (dead_end) kind = 2;  // traffi.cpp:864-871 (trip_abort is always 1 in this engine)
+                    else { kind = 3; nx = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u); }
+                }
+                if (over) W.v_mr[vid] = mr_;
+                H.vid[j] = vid; H.kind[j] = kind; H.xn[j] = xn; H.next[j] = nx;
+                H.atl[j] = atl_; H.ex[j] = ex_; H.dist[j] = di_; H.dts[j] = dts_;
+            }
+        }
+        WARP_SYNC();
+        WARP_FOR(lane) if (lane == 0) {
+            // lane relabel when the end node (smaller id) emptied the link before this step's pushes
+            if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
+                int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+                if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
+            }
+            W.stat_count[l] += n;
+            int k = 0, evc = 0, trips = 0;
+            double cumdep = 0.0;
+            bool touched = false;
+            for (int j = 0; j < hc; j++) {
+                int vid = H.vid[j];
+                unsigned char kind = H.kind[j], f = 0;
+                if (kind == 3) { W.v_next[vid] = H.next[j]; f = VF_CAND; }
+                else if (kind == 1 || kind == 2) {
+                    f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
+                    if (kind == 2) W.v_next[vid] = -1;
+                    if (k == j) {  // it is the front (everything ahead ended in this pass): end_trip, traffi.cpp:886-927
+                        if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[(size_t)t * L + l]; touched = true; }
+                        trips += 1; cumdep += W.dn;
+                        double atl = H.atl[j];
+                        int es = (int)(atl / W.dt);
+                        if (es < 0) es = 0;
+                        if (es >= W.T) es = W.T - 1;
+                        evc += 1;
+                        W.ev_ord[(size_t)es * L + l] = evc;
+                        W.ev_tt[(size_t)es * L + l] = ((double)t + 1.0) * W.dt - atl;
+                        W.v_atl[vid] = (double)t * W.dt;
+                        W.v_dist[vid] = H.dist[j] + (H.xn[j] - H.ex[j]);
+                        W.v_link[vid] = -1;
+                        if (kind == 2) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+                        else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)H.dts[j] * W.dt; }
+                        if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 1; }
+                        f = 0;
+                        k++;
+                    }
+                }
+                W.v_flags[vid] = f;
+            }
+            if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[(size_t)t * L + l] = cumdep; }
+            W.head[(cur ^ 1) * L + l] = hd + k;
+            int rem = n - k;
+            W.hcount[l] = rem < lanes ? rem : lanes;
+            H.k_ended = k;
+        }
+
+        if (W.log_mode) {  // positions that may have a just-ended leader are logged here, once the ended count is known
+            WARP_SYNC();
+            int nlog = n < 2 * lanes ? n : 2 * lanes, k_ended = H.k_ended;
+            WARP_FOR(lane) { for (int pos = lane; pos < nlog; pos += 32) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, k_ended, 0); }
+            WARP_SYNC();
+        }
+    }
+    WARP_FOR(lane) {
+        for (int pos = part * 32 + lane; pos < n; pos += nparts * 32) {
+            int p = ring_slot(hd, pos, cap);
+            if (W.log_mode && pos >= 2 * lanes) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, 0, 0);
+            double x = Xc[p];
+            double xn = x + udt;
+            if (pos >= lanes) {
+                double gap = Xc[ring_slot(hd, pos - lanes, cap)] - dpl;
+                if (gap < x) gap = x;
+                if (xn > gap) xn = gap;
+            }
+            if (xn < x) xn = x;
+            if (xn > len) xn = len;
+            W.X[(size_t)(cur ^ 1) * C + o + p] = xn;
+            W.V[o + p] = (xn - x) / W.dt;
+        }
+    }
+}
+

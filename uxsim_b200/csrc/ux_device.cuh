@@ -64,6 +64,20 @@ struct DevWorld {
 
 #define UX_DEV __device__ __forceinline__
 
+// Index of (step t, link l) in the per-replica link series (cumulative curves, instantaneous travel time, travel-time
+// event tables) and of (step t, node n) in the signal log.  Time-major rows [T][L]; the getters transpose to the ABI's [L][T].
+// Link-major (-DUX_LINK_MAJOR: a link's consecutive steps share 32-byte sectors, no transpose at hand-back) was measured
+// 2-3 % SLOWER on the B200 (Chicago x32: 79.1 vs 77.4 ms; at deltan=5: 430 vs 416 ms): the loop is bound by dependent-load
+// latency, not by the DRAM sectors this layout saves.
+#ifndef UX_LINK_MAJOR
+#define UX_TIME_MAJOR 1
+#define TLI(W, t, l) ((size_t)(t) * (size_t)(W).L + (size_t)(l))
+#define TNI(W, t, n) ((size_t)(t) * (size_t)(W).N + (size_t)(n))
+#else
+#define TLI(W, t, l) ((size_t)(l) * (size_t)(W).T + (size_t)(t))
+#define TNI(W, t, n) ((size_t)(n) * (size_t)(W).T + (size_t)(t))
+#endif
+
 // The per-replica DevWorld lives in global memory; reading its ~90 pointers through a reference there would make
 // every `W.x[...]` a dependent pointer load that must be repeated after each global store (possible aliasing).
 // Each block therefore copies its replica's struct into shared memory once; shared memory cannot alias global
@@ -242,14 +256,14 @@ UX_DEV void record_tt_event(const DevWorld &W, int l, double atl, double tt) {
     if (s >= W.T) s = W.T - 1;
     int ord = W.ev_cnt[l] + 1;
     W.ev_cnt[l] = ord;
-    W.ev_ord[(size_t)s * W.L + l] = ord;
-    W.ev_tt[(size_t)s * W.L + l] = tt;
+    W.ev_ord[TLI(W, s, l)] = ord;
+    W.ev_tt[TLI(W, s, l)] = tt;
 }
 
 // Vehicle::end_trip (traffi.cpp:886-927) for the front platoon `vid` of link l, currently at position x
 UX_DEV void end_trip(const DevWorld &W, int vid, int l, int t, double x) {
     W.trips[l] += 1;
-    W.cum_dep[(size_t)t * W.L + l] += W.dn;
+    W.cum_dep[TLI(W, t, l)] += W.dn;
     double atl = W.v_atl[vid];
     record_tt_event(W, l, atl, ((double)t + 1.0) * W.dt - atl);
     W.v_atl[vid] = (double)t * W.dt;

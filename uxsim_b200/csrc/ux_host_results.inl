@@ -242,14 +242,21 @@ static int64_t device_array(ux_world *w, int what, int replica, void **dptr, int
         *dptr = w->d_scratch; return 0; };
     int rc = 0;
     switch (what) {
+#ifdef UX_TIME_MAJOR
     case UX_A_CUM_ARRIVAL: rc = transpose_d(d.cum_arr, T, L); break;
     case UX_A_CUM_DEPARTURE: rc = transpose_d(d.cum_dep, T, L); break;
     case UX_A_TRAVELTIME_INSTANT: rc = transpose_d(d.tt_inst, T, L); break;
+    case UX_A_SIGNAL_LOG: rc = transpose_i(d.sig_log, T, N); break;
+#else  // the series are kept link-major on the device: the ABI layout, no transpose
+    case UX_A_CUM_ARRIVAL: *dptr = d.cum_arr; break;
+    case UX_A_CUM_DEPARTURE: *dptr = d.cum_dep; break;
+    case UX_A_TRAVELTIME_INSTANT: *dptr = d.tt_inst; break;
+    case UX_A_SIGNAL_LOG: *dptr = d.sig_log; break;
+#endif
     case UX_A_TRAVELTIME_ACTUAL:
         rc = ensure_scratch(w, sizeof(double) * (size_t)T * L + 16); if (rc) break;
         if (L > 0) UX_LAUNCH(k_tt_actual, dim3((L + 127) / 128), dim3(128), st, w->dworlds, replica, w->d_scratch);
         *dptr = w->d_scratch; break;
-    case UX_A_SIGNAL_LOG: rc = transpose_i(d.sig_log, T, N); break;
     case UX_A_VEH_ARRIVAL_TS: *dptr = d.v_arr_ts; break;
     case UX_A_VEH_DEPART_TS: *dptr = (void *)d.v_depart_ts; break;
     case UX_A_VEH_TRAVEL_TIME: *dptr = d.v_tt; break;

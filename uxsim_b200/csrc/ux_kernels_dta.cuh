@@ -52,14 +52,14 @@ __global__ void k_dta_externality(const DevWorld *worlds, const DtaDev *dd) {
         double tt_i = ttl[i];
         int fut = i + (int)(tt_i / dt);
         if (fut >= n) break;
-        if (tt_i > fftt && W.cum_arr[(size_t)fut * L + l] - W.cum_dep[(size_t)fut * L + l] > 0) ts_end = i; else break;
+        if (tt_i > fftt && W.cum_arr[TLI(W, fut, l)] - W.cum_dep[TLI(W, fut, l)] > 0) ts_end = i; else break;
     }
-    double veh_count = W.cum_arr[(size_t)ts_end * L + l] - W.cum_arr[(size_t)ts * L + l];
+    double veh_count = W.cum_arr[TLI(W, ts_end, l)] - W.cum_arr[TLI(W, ts, l)];
     int ts_out = (int)(ts + (int)(ttl[ts] / dt)) + 1;
     if (ts_out >= n) ts_out = n - 1;
     int ts_out_leader = ts_out;
-    double dep_out = W.cum_dep[(size_t)ts_out * L + l];
-    for (int i = ts_out; i > 0; i--) if (W.cum_dep[(size_t)i * L + l] < dep_out) { ts_out_leader = i; break; }  // leader headway (backward scan)
+    double dep_out = W.cum_dep[TLI(W, ts_out, l)];
+    for (int i = ts_out; i > 0; i--) if (W.cum_dep[TLI(W, i, l)] < dep_out) { ts_out_leader = i; break; }  // leader headway (backward scan)
     ext[cell] = (double)(ts_out - ts_out_leader) * dt * veh_count;
 }
 

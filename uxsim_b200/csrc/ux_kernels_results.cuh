@@ -19,8 +19,8 @@ UX_DEV void tt_actual_link(const DevWorld &W, int l, double *out) {
     int best = 0;
 #pragma unroll 8
     for (int i = 0; i < W.T; i++) {  // the loads do not depend on the running arg-max, so they pipeline
-        int ord = W.ev_ord[(size_t)i * W.L + l];
-        double v = W.ev_tt[(size_t)i * W.L + l];
+        int ord = W.ev_ord[TLI(W, i, l)];
+        double v = W.ev_tt[TLI(W, i, l)];
         if (ord > best) { best = ord; cur = v; }
         out[(size_t)l * W.T + i] = cur;
     }
@@ -70,13 +70,13 @@ __global__ void k_ensemble_partial(const DevWorld *worlds, double *part) {
     int best = 0;
 #pragma unroll 8
     for (int i = 0; i < T; i++) {
-        int ord = W.ev_ord[(size_t)i * L + l];
-        double v = W.ev_tt[(size_t)i * L + l];
+        int ord = W.ev_ord[TLI(W, i, l)];
+        double v = W.ev_tt[TLI(W, i, l)];
         if (ord > best) { best = ord; cur = v; }
         s1 += cur; s2 += cur * cur;
     }
     double *o = part + ((size_t)blockIdx.y * L + l) * 4;
-    o[0] = T > 0 ? W.cum_arr[(size_t)(T - 1) * L + l] : 0.0; o[1] = s1; o[2] = s2;
+    o[0] = T > 0 ? W.cum_arr[TLI(W, (T - 1), l)] : 0.0; o[1] = s1; o[2] = s2;
     o[3] = (double)(W.tail[l] - W.head[(*W.t_base & 1) * L + l]);
 }
 __global__ void k_ensemble_stats(const DevWorld *worlds, int R, const double *part, double *out) {

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int s
     int m0 = W.l_pair_off[g], m1 = W.l_pair_off[g + 1], cntr = 0;
     for (int m = m0; m < m1; m++) {  // members of the node pair in link-id order, running average
         int l = W.l_pair_list[m];
-        double tt = W.tt_inst[(size_t)t * W.L + l];
+        double tt = W.tt_inst[TLI(W, t, l)];
         if (tt <= 0.0) tt = W.l_length[l] / W.l_vmax[l];
         double pen = W.l_toll ? W.l_toll[(size_t)t * W.L + l] : W.l_penalty[l];
         double c;

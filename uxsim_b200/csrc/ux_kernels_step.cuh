@@ -42,17 +42,17 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     WARP_FOR(ln) {
         for (int k = ln; k < nout; k += 32) {
             int l = W.n_out[o0 + k];
-            size_t row = (size_t)t * L + l;
+            size_t row = TLI(W, t, l), prev = TLI(W, t - 1, l);
             if (fresh) W.tt_inst[row] = tt_s[k];
-            else if (t > 0) W.tt_inst[row] = W.tt_inst[row - L];
-            if (t != 0) W.cum_arr[row] = W.cum_arr[row - L];
+            else if (t > 0) W.tt_inst[row] = W.tt_inst[prev];
+            if (t != 0) W.cum_arr[row] = W.cum_arr[prev];
             double ci = W.l_cap_in[l];
             if (ci < 10e9) { if (W.cap_in_rem[l] < W.dn * W.l_lanes[l]) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
         }
         for (int k = ln; k < nin; k += 32) {
             int l = W.n_in[i0 + k];
-            size_t row = (size_t)t * L + l;
-            if (t != 0) W.cum_dep[row] = W.cum_dep[row - L];
+            size_t row = TLI(W, t, l);
+            if (t != 0) W.cum_dep[row] = W.cum_dep[TLI(W, t - 1, l)];
             double co = W.l_cap_out[l];
             if (co < 10e9) { if (W.cap_out_rem[l] < W.dn * W.l_lanes[l]) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
             W.pop_k2[l] = 0;
@@ -90,7 +90,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
                 int ol = W.n_out[o0 + q];
                 int hd = W.head[cur * L + ol], tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
                 long long o = W.l_roff[ol];
-                double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[(size_t)t * L + ol];
+                double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
                 int sz = tl - hd;
                 int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
                 G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
@@ -155,7 +155,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         WARP_FOR(ln) {
             for (int q = ln; q < nout; q += 32) {
                 int ol = W.n_out[o0 + q];
-                W.cap_in_rem[ol] = G.o_ci[q]; W.cum_arr[(size_t)t * L + ol] = G.o_cumarr[q]; W.tail[ol] = G.o_tail[q];
+                W.cap_in_rem[ol] = G.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = G.o_cumarr[q]; W.tail[ol] = G.o_tail[q];
             }
         }
         WARP_SYNC();
@@ -172,7 +172,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
             st += W.dt;
             W.sig_t[n] = st; W.sig_phase[n] = ph;
         }
-        W.sig_log[(size_t)t * W.N + n] = ph;
+        W.sig_log[TNI(W, t, n)] = ph;
         // ---- node flow capacity (Node::flow_capacity_update traffi.cpp:226-234)
         double fc = W.n_fc[n];
         if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
@@ -229,8 +229,8 @@ UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem<MC, MD> &S, int p, int t) 
         if (s < 0) s = 0;
         if (s >= W.T) s = W.T - 1;
         int ord = ++S.evc[ii];
-        W.ev_ord[(size_t)s * W.L + il] = ord;
-        W.ev_tt[(size_t)s * W.L + il] = ((double)t + 1.0) * W.dt - atl;
+        W.ev_ord[TLI(W, s, il)] = ord;
+        W.ev_tt[TLI(W, s, il)] = ((double)t + 1.0) * W.dt - atl;
     }
     W.v_atl[vid] = (double)t * W.dt;
     W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
@@ -260,7 +260,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             int il = W.n_in[i0 + ii];
             int hd_ = W.head[cur * L + il], hc_ = W.hcount[il], cap_ = W.l_rcap[il], evc_ = W.ev_cnt[il], trips_ = W.trips[il];
             long long roff_ = W.l_roff[il];
-            double co_ = W.cap_out_rem[il], mp_ = W.l_mp[il], vm_ = W.l_vmax[il], cd_ = W.cum_dep[(size_t)t * L + il];
+            double co_ = W.cap_out_rem[il], mp_ = W.l_mp[il], vm_ = W.l_vmax[il], cd_ = W.cum_dep[TLI(W, t, il)];
             bool ok = true;
             if (nsig > 1) { int g0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - g0; ok = list_has(W.l_sg + g0, gl, phase); }
             S.il[ii] = il; S.hd[ii] = hd_; S.hc[ii] = hc_; S.cap[ii] = cap_; S.roff[ii] = roff_;
@@ -366,7 +366,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             int hd = W.head[cur * L + ol], fl_ = W.l_flags[ol], pk_ = ld_cg(W.pop_k2 + ol);  // written by a lower level in this launch
             int tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
             long long o = W.l_roff[ol];
-            double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[(size_t)t * L + ol];
+            double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
             if (fl_ & LF_SEES_POPS) hd += pk_;
             int sz = tl - hd;
             int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
@@ -494,8 +494,8 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
                 if (es < 0) es = 0;
                 if (es >= W.T) es = W.T - 1;
                 int ord = ++S.evc[ii];
-                W.ev_ord[(size_t)es * L + il] = ord;
-                W.ev_tt[(size_t)es * L + il] = (double)t * W.dt - atl;
+                W.ev_ord[TLI(W, es, il)] = ord;
+                W.ev_tt[TLI(W, es, il)] = (double)t * W.dt - atl;
             }
             W.v_atl[vid] = (double)t * W.dt;
             W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
@@ -560,12 +560,12 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     WARP_FOR(lane) {
         for (int ii = lane; ii < nin; ii += 32) {
             int il = S.il[ii];
-            W.cap_out_rem[il] = S.co_rem[ii]; W.cum_dep[(size_t)t * L + il] = S.cumdep[ii];
+            W.cap_out_rem[il] = S.co_rem[ii]; W.cum_dep[TLI(W, t, il)] = S.cumdep[ii];
             W.pop_k2[il] = S.popped[ii]; W.ev_cnt[il] = S.evc[ii]; W.trips[il] = S.trips[ii];
         }
         for (int q = lane; q < nol; q += 32) {
             int ol = S.ol[q];
-            W.cap_in_rem[ol] = S.o_ci[q]; W.cum_arr[(size_t)t * L + ol] = S.o_cumarr[q]; W.tail[ol] = S.o_tail[q];
+            W.cap_in_rem[ol] = S.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = S.o_cumarr[q]; W.tail[ol] = S.o_tail[q];
         }
     }
 }
@@ -727,15 +727,15 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                     f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
                     if (kind == 2) W.v_next[vid] = -1;
                     if (k == j) {  // it is the front (everything ahead ended in this pass): end_trip, traffi.cpp:886-927
-                        if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[(size_t)t * L + l]; touched = true; }
+                        if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[TLI(W, t, l)]; touched = true; }
                         trips += 1; cumdep += W.dn;
                         double atl = H.atl[j];
                         int es = (int)(atl / W.dt);
                         if (es < 0) es = 0;
                         if (es >= W.T) es = W.T - 1;
                         evc += 1;
-                        W.ev_ord[(size_t)es * L + l] = evc;
-                        W.ev_tt[(size_t)es * L + l] = ((double)t + 1.0) * W.dt - atl;
+                        W.ev_ord[TLI(W, es, l)] = evc;
+                        W.ev_tt[TLI(W, es, l)] = ((double)t + 1.0) * W.dt - atl;
                         W.v_atl[vid] = (double)t * W.dt;
                         W.v_dist[vid] = H.dist[j] + (H.xn[j] - H.ex[j]);
                         W.v_link[vid] = -1;
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                 }
                 W.v_flags[vid] = f;
             }
-            if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[(size_t)t * L + l] = cumdep; }
+            if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[TLI(W, t, l)] = cumdep; }
             W.head[(cur ^ 1) * L + l] = hd + k;
             int rem = n - k;
             W.hcount[l] = rem < lanes ? rem : lanes;

@@ -292,7 +292,12 @@ enum {
     UX_A_DTA_COST_ACTUAL = 114, /* f64 [P]    arrival_time - first link entry time */
     UX_A_DTA_T_GAP = 115,       /* f64 [P]    per-platoon cost gap; total_t_gap is its sum in index order */
     UX_A_DTA_CHOICE = 116,      /* i32 [P]    -2 nothing enforced (trip unfinished), -1 keeps the traversed route, r >= 0 = index into the store's routes */
-    UX_A_DTA_RA_ENTRY_T = 117   /* f64        entry time of each link of route_actual (TraveledRouteInfo::entry_times) */
+    UX_A_DTA_RA_ENTRY_T = 117,  /* f64        entry time of each link of route_actual (TraveledRouteInfo::entry_times) */
+    /* result of the last edie_state: link l owns cells [off[l], off[l+1]) = a row-major [nt_l][nx_l] grid */
+    UX_A_EDIE_OFFSETS = 120,    /* i64 [L+1] */
+    UX_A_EDIE_NX = 121,         /* i32 [L]   cells along the link; nt_l = (off[l+1] - off[l]) / nx_l */
+    UX_A_EDIE_TN = 122,         /* f64 [cells]  vehicle-seconds spent in the cell  (Link.tn_mat) */
+    UX_A_EDIE_DN = 123          /* f64 [cells]  vehicle-metres travelled in the cell (Link.dn_mat) */
 };
 enum { UX_DT_F64 = 1, UX_DT_I32 = 2, UX_DT_I64 = 3 };
 
@@ -345,6 +350,14 @@ UX_API int UX_FN(dta_route_swap)(ux_world *w, int replica, int mode, double swap
  * tables / captured graphs kept.  Same results as: new world + batch_enforce_routes_csr(rs) + main_loop.  The reference
  * builds a new World per day (DTAsolvers_cpp_adapter.py:318-330), so the CPU engines answer UX_ERR_RUNTIME. */
 UX_API int UX_FN(dta_next_day)(ux_world *w);
+
+/* Analyzer.compute_edie_state (analyzer.py:205-330, with compute_accurate_traj 205-247): Edie's generalised traffic state
+ * per link on an (edie_dt[l] x edie_dx[l]) time-space grid, from the per-step platoon trajectories (needs vehicle_log_mode):
+ * every trajectory segment adds its travel time and distance to the cells it crosses (time cell of the segment's start), the
+ * ends of a link traversal are extrapolated at free-flow speed.  k = tn / (dt dx), q = dn / (dt dx), v = q / k.
+ * Contributions are accumulated in 2^-24 fixed point, so the sums do not depend on the order of accumulation (and are
+ * identical in the three engines); they differ from the reference's float sums by < 1e-7 relative. */
+UX_API int UX_FN(edie_state)(ux_world *w, int replica, const double *edie_dt, const double *edie_dx);
 
 /* Message of the last failure on `w` (or of the last failed create_world when w == NULL). */
 UX_API const char *UX_FN(last_error)(ux_world *w);

@@ -104,6 +104,8 @@ struct ux_world {
     int64_t dta_n_od; int *dta_o, *dta_d; int64_t *dta_od_off, *dta_route_off; int *dta_links;
     int64_t *rs_off, *ra_off; int *rs_links, *ra_links; double *ra_entry_t, *cost_actual, *t_gap; int *choice;
     double n_swap, potential_n_swap, total_t_gap; int has_swap;
+    /* Edie states (last edie_state call) */
+    int64_t *edie_off; int *edie_nx; double *edie_tn, *edie_dn;
     char err[512];
 };
 
@@ -175,6 +177,7 @@ UX_API void uxo_destroy_world(ux_world *w) {
     free(w->pair_first); free(w->pair_cost); free(w->in_pair_list); free(w->in_pair_off); free(w->snapshot);
     free(w->dta_o); free(w->dta_d); free(w->dta_od_off); free(w->dta_route_off); free(w->dta_links);
     free(w->rs_off); free(w->ra_off); free(w->rs_links); free(w->ra_links); free(w->ra_entry_t); free(w->cost_actual); free(w->t_gap); free(w->choice);
+    free(w->edie_off); free(w->edie_nx); free(w->edie_tn); free(w->edie_dn);
     free(w);
 }
 
@@ -1026,6 +1029,9 @@ UX_API int64_t uxo_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_LOG_N_MISSING: n = P; dt = UX_DT_I32; break;
     case UX_A_LTL_T: case UX_A_LTL_ID: { n = 0; for (int64_t i = 0; i < P; i++) n += ltl_count(&w->vehs[i]); dt = what == UX_A_LTL_T ? UX_DT_F64 : UX_DT_I32; break; }
     case UX_A_ENTER_LINK: case UX_A_ENTER_VEH: case UX_A_ENTER_TIME: { n = 0; for (int64_t i = 0; i < P; i++) n += enter_count(&w->vehs[i]); dt = what == UX_A_ENTER_TIME ? UX_DT_F64 : UX_DT_I32; break; }
+    case UX_A_EDIE_OFFSETS: n = w->edie_off ? L + 1 : 0; dt = UX_DT_I64; break;
+    case UX_A_EDIE_NX: n = w->edie_off ? L : 0; dt = UX_DT_I32; break;
+    case UX_A_EDIE_TN: case UX_A_EDIE_DN: n = w->edie_off ? w->edie_off[L] : 0; break;
     case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = w->dta_n_od; dt = UX_DT_I32; break;
     case UX_A_DTA_OD_OFFSETS: n = w->dta_n_od + 1; dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_OFFSETS: n = (w->dta_od_off ? w->dta_od_off[w->dta_n_od] : 0) + 1; dt = UX_DT_I64; break;
@@ -1117,6 +1123,10 @@ UX_API int64_t uxo_get_array(ux_world *w, int what, int replica, void *dst, int6
             for (int k = 0; k < v->log_size; k++) { int lid = v->log_link[k]; if (lid >= 0 && lid != prev) { if (what == UX_A_ENTER_LINK) ii[s] = lid; else if (what == UX_A_ENTER_TIME) d[s] = log_t_at(w, v, k); else ii[s] = (int)i; s++; prev = lid; } }
         }
         break; }
+    case UX_A_EDIE_OFFSETS: memcpy(dst, w->edie_off, sizeof(int64_t) * n); break;
+    case UX_A_EDIE_NX: memcpy(dst, w->edie_nx, sizeof(int) * n); break;
+    case UX_A_EDIE_TN: memcpy(dst, w->edie_tn, sizeof(double) * n); break;
+    case UX_A_EDIE_DN: memcpy(dst, w->edie_dn, sizeof(double) * n); break;
     case UX_A_DTA_OD_ORIG: memcpy(dst, w->dta_o, sizeof(int) * n); break;
     case UX_A_DTA_OD_DEST: memcpy(dst, w->dta_d, sizeof(int) * n); break;
     case UX_A_DTA_OD_OFFSETS: if (w->dta_od_off) memcpy(dst, w->dta_od_off, sizeof(int64_t) * n); else ((int64_t *)dst)[0] = 0; break;
@@ -1461,6 +1471,89 @@ UX_API int uxo_dta_route_swap(ux_world *w, int replica, int mode, double swap_pr
         if (n > 0) memcpy(w->rs_links + w->rs_off[vi], c == -1 ? w->ra_links + w->ra_off[vi] : w->dta_links + w->dta_route_off[c], sizeof(int) * (size_t)n);
     }
     w->has_swap = 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Edie states: restatement of Analyzer.compute_accurate_traj + compute_edie_state  */
+/* (analyzer.py:205-330).                                                                            */
+/* ------------------------------------------------------------------------------------------------ */
+#define EDIE_FX 16777216.0 /* 2^24: contributions are rounded to this fixed point (include/uxsim_b200.h) */
+static long long edie_fx(double v) { return (long long)floor(v * EDIE_FX + 0.5); }
+/* Python's float floor division and modulo for a positive divisor (floatobject.c float_divmod) */
+static double py_mod(double x, double y) { double m = fmod(x, y); if (m != 0.0 && ((y < 0) != (m < 0))) m += y; return m; }
+static double py_floordiv(double x, double y) {
+    double m = fmod(x, y), div = (x - m) / y;
+    if (m != 0.0 && ((y < 0) != (m < 0))) div -= 1.0;
+    if (div == 0.0) return 0.0;
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+/* one trajectory segment (x0,t0) -> (x1,t1) on a link whose grid is nt x nx cells of dt x dx (analyzer.py:272-312) */
+static void edie_segment(long long *tn, long long *dn, int nt, int nx, double dt, double dx, double x0, double t0, double x1, double t1) {
+    double v0 = (t1 - t0 != 0) ? (x1 - x0) / (t1 - t0) : 0.0;
+    int tt = (int)py_floordiv(t0, dt), xx = (int)py_floordiv(x0, dx);
+    if (tt < 0) tt += nt;  /* Python's negative index: an extrapolated start before t = 0 lands in the last rows */
+    if (tt < 0 || !(tt < nt && xx < nx)) return;
+    if (v0 > 0) {
+        double xl0 = dx - py_mod(x0, dx), xl1 = py_mod(x1, dx), tl0 = xl0 / v0, tl1 = xl1 / v0;
+        double x1c = py_floordiv(x1, dx);
+        if ((double)xx == x1c) { dn[(size_t)tt * nx + xx] += edie_fx(x1 - x0); tn[(size_t)tt * nx + xx] += edie_fx(t1 - t0); }
+        else {
+            int jj = (int)(x1c - xx + 1);
+            for (int j = 0; j < jj; j++) {
+                if (xx + j >= nx) continue;
+                size_t c = (size_t)tt * nx + xx + j;
+                if (j == 0) { dn[c] += edie_fx(xl0); tn[c] += edie_fx(tl0); }
+                else if (j == jj - 1) { dn[c] += edie_fx(xl1); tn[c] += edie_fx(tl1); }
+                else { dn[c] += edie_fx(dx); tn[c] += edie_fx(dx / v0); }
+            }
+        }
+    } else tn[(size_t)tt * nx + xx] += edie_fx(t1 - t0);
+}
+
+UX_API int uxo_edie_state(ux_world *w, int replica, const double *edie_dt, const double *edie_dx) {
+    if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "oracle has a single replica");
+    if (!w->p.vehicle_log_mode) return fail(w, UX_ERR_RUNTIME, "edie_state needs the per-step vehicle logs (vehicle_log_mode)");
+    int L = w->nl;
+    free(w->edie_off); free(w->edie_nx); free(w->edie_tn); free(w->edie_dn);
+    w->edie_off = (int64_t *)calloc((size_t)L + 1, sizeof(int64_t)); w->edie_nx = (int *)calloc((size_t)L + 1, sizeof(int));
+    for (int l = 0; l < L; l++) {
+        if (!(edie_dt[l] > 0) || !(edie_dx[l] > 0)) return fail(w, UX_ERR_INVALID, "edie_state: cell sizes must be positive");
+        int nt = (int)(w->p.t_max / edie_dt[l]), nx = (int)(w->links[l].length / edie_dx[l]);
+        w->edie_nx[l] = nx; w->edie_off[l + 1] = w->edie_off[l] + (int64_t)nt * nx;
+    }
+    int64_t cells = w->edie_off[L];
+    long long *tn = (long long *)calloc((size_t)cells + 1, sizeof(long long)), *dn = (long long *)calloc((size_t)cells + 1, sizeof(long long));
+    for (int64_t vi = 0; vi < w->nv; vi++) {
+        const OVeh *v = &w->vehs[vi];
+        int i = 0;
+        while (i < v->log_size) {  /* a maximal run of records on one link = one trajectory on that link (analyzer.py:217-231) */
+            int l = v->log_link[i];
+            if (l < 0) { i++; continue; }
+            int j = i;
+            while (j + 1 < v->log_size && v->log_link[j + 1] == l) j++;
+            const OLink *ln = &w->links[l];
+            int nx = w->edie_nx[l], nt = nx > 0 ? (int)((w->edie_off[l + 1] - w->edie_off[l]) / nx) : 0;
+            long long *ltn = tn + w->edie_off[l], *ldn = dn + w->edie_off[l];
+            double dt = edie_dt[l], dx = edie_dx[l], u = ln->vmax;
+            if (nx > 0 && nt > 0) {
+                double xf = v->log_x[i], tf = log_t_at(w, v, i);
+                if (xf != 0 && xf / u > w->delta_t * 0.01) edie_segment(ltn, ldn, nt, nx, dt, dx, 0.0, tf - xf / u, xf, tf);  /* extrapolated entry */
+                for (int k = i; k < j; k++) edie_segment(ltn, ldn, nt, nx, dt, dx, v->log_x[k], log_t_at(w, v, k), v->log_x[k + 1], log_t_at(w, v, k + 1));
+                double xe = v->log_x[j], te = log_t_at(w, v, j);
+                if (ln->length - u * w->delta_t <= xe && xe < ln->length) {  /* extrapolated exit */
+                    double rem = ln->length - xe;
+                    if (rem / u > w->delta_t * 0.01) edie_segment(ltn, ldn, nt, nx, dt, dx, xe, te, ln->length, te + rem / u);
+                }
+            }
+            i = j + 1;
+        }
+    }
+    w->edie_tn = (double *)calloc((size_t)cells + 1, sizeof(double)); w->edie_dn = (double *)calloc((size_t)cells + 1, sizeof(double));
+    for (int64_t c = 0; c < cells; c++) { w->edie_tn[c] = (double)tn[c] / EDIE_FX * w->p.delta_n; w->edie_dn[c] = (double)dn[c] / EDIE_FX * w->p.delta_n; }
+    free(tn); free(dn);
     return 0;
 }
 

@@ -51,6 +51,7 @@ A_ROUTE_PREF, A_ROUTE_DIST, A_ROUTE_NEXT = 50, 51, 52
 A_LOG_OFFSETS, A_LOG_T, A_LOG_X, A_LOG_V, A_LOG_STATE, A_LOG_S, A_LOG_LANE, A_LOG_LINK = 60, 61, 62, 63, 64, 65, 66, 67
 A_LOG_N_MISSING, A_LTL_OFFSETS, A_LTL_T, A_LTL_ID = 68, 69, 70, 71
 A_DTA_OD_ORIG, A_DTA_OD_DEST, A_DTA_OD_OFFSETS, A_DTA_ROUTE_OFFSETS, A_DTA_ROUTE_LINKS = 100, 101, 102, 103, 104
+A_EDIE_OFFSETS, A_EDIE_NX, A_EDIE_TN, A_EDIE_DN = 120, 121, 122, 123
 A_DTA_RS_OFFSETS, A_DTA_RS_LINKS, A_DTA_RA_OFFSETS, A_DTA_RA_LINKS, A_DTA_COST_ACTUAL, A_DTA_T_GAP, A_DTA_CHOICE, A_DTA_RA_ENTRY_T = 110, 111, 112, 113, 114, 115, 116, 117
 A_ENTER_LINK, A_ENTER_TIME, A_ENTER_VEH = 80, 81, 82
 
@@ -73,7 +74,7 @@ ABI_SYMBOLS = (
     "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
     "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
     "ensemble_link_stats", "last_error", "dta_enumerate_route_sets", "dta_set_route_sets", "dta_share_route_sets",
-    "dta_enforce_routes", "dta_route_swap", "dta_next_day",
+    "dta_enforce_routes", "dta_route_swap", "dta_next_day", "edie_state",
 )
 
 
@@ -166,6 +167,7 @@ class CApi:
         self.dta_share_route_sets = fn("dta_share_route_sets", C.c_int, [p, p])
         self.dta_enforce_routes = fn("dta_enforce_routes", C.c_int, [p, C.c_int, i32p, i64p, C.c_int64])
         self.dta_next_day = fn("dta_next_day", C.c_int, [p])
+        self.edie_state = fn("edie_state", C.c_int, [p, C.c_int, f64p, f64p])
         self.dta_route_swap = fn("dta_route_swap", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint])
 
     def exported(self, name: str) -> bool:
@@ -322,6 +324,20 @@ class EngineWorld:
         ids, off = _as_i32(link_ids), np.ascontiguousarray(offsets, dtype=np.int64)
         self._check(self.api.dta_enforce_routes(self.h, int(replica), ids.ctypes.data_as(C.POINTER(C.c_int32)),
                                                 off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1))
+
+    def edie_state(self, edie_dt, edie_dx, replica: int = 0):
+        """Analyzer.compute_edie_state (analyzer.py:249-330) for every link: list of (tn_mat, dn_mat), each ``[nt_l, nx_l]``
+        (vehicle-seconds and vehicle-metres per cell); k = tn / (dt dx), q = dn / (dt dx), v = q / k."""
+        a, b = _as_f64(edie_dt), _as_f64(edie_dx)
+        dp = C.POINTER(C.c_double)
+        self._check(self.api.edie_state(self.h, int(replica), a.ctypes.data_as(dp), b.ctypes.data_as(dp)))
+        off, nx = self.get_array(A_EDIE_OFFSETS, replica), self.get_array(A_EDIE_NX, replica)
+        tn, dn = self.get_array(A_EDIE_TN, replica), self.get_array(A_EDIE_DN, replica)
+        out = []
+        for l in range(len(nx)):
+            shape = (-1, int(nx[l])) if nx[l] > 0 else (0, 0)
+            out.append((tn[off[l]:off[l + 1]].reshape(shape), dn[off[l]:off[l + 1]].reshape(shape)))
+        return out
 
     def dta_next_day(self):
         """Rewind the finished world to t = 0 with the last route swap's routes enforced (CUDA engine only)."""

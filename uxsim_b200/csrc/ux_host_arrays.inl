@@ -30,9 +30,76 @@ static int64_t get_dta_array(ux_world *w, int what, int replica, void *dst, int6
     return n;
 }
 
+// Analyzer.compute_edie_state (analyzer.py:205-330) on the device, from the RUN records of `replica`
+UX_API int ux_edie_state(ux_world *w, int replica, const double *edie_dt, const double *edie_dx) {
+    if (!w->uploaded || w->timestep == 0) return fail(w, UX_ERR_RUNTIME, "edie_state needs a run");
+    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    if (!w->p.vehicle_log_mode) return fail(w, UX_ERR_RUNTIME, "edie_state needs the per-step vehicle logs (vehicle_log_mode)");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    int L = (int)w->links.size();
+    auto &R = w->edie;
+    R.replica = -1;
+    R.off.assign(L + 1, 0); R.nx.assign(L, 0);
+    for (int l = 0; l < L; l++) {
+        if (!(edie_dt[l] > 0) || !(edie_dx[l] > 0)) return fail(w, UX_ERR_INVALID, "edie_state: cell sizes must be positive");
+        int nt = (int)(w->p.t_max / edie_dt[l]), nx = (int)(w->links[l].length / edie_dx[l]);
+        R.nx[l] = nx; R.off[l + 1] = R.off[l] + (long long)nt * nx;
+    }
+    long long cells = R.off[L];
+    std::vector<long long> roff;
+    unsigned long long nrec = 0;
+    { int rc = log_offsets(w, replica, roff, nrec); if (rc) return rc; }
+    long long P = (long long)roff.size() - 1;
+    size_t bytes = 0;
+    auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
+    size_t o_off = carve(8 * (size_t)(P + 1)), o_vid = carve(4 * (size_t)nrec), o_lnk = carve(4 * (size_t)nrec), o_x = carve(8 * (size_t)nrec), o_coff = carve(8 * (size_t)(L + 1)),
+           o_cnx = carve(4 * (size_t)L), o_dt = carve(8 * (size_t)L), o_dx = carve(8 * (size_t)L), o_tn = carve(8 * (size_t)cells), o_dn = carve(8 * (size_t)cells),
+           o_otn = carve(8 * (size_t)cells), o_odn = carve(8 * (size_t)cells);
+    char *buf = nullptr;
+    CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
+    cudaMemcpyAsync(buf + o_off, roff.data(), 8 * (size_t)(P + 1), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + o_coff, R.off.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + o_cnx, R.nx.data(), 4 * (size_t)L, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + o_dt, edie_dt, 8 * (size_t)L, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + o_dx, edie_dx, 8 * (size_t)L, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(buf + o_tn, 0, o_otn - o_tn, st);
+    if (nrec) {
+        UX_LAUNCH(k_edie_order, dim3((unsigned)((nrec + 255) / 256)), dim3(256), st, w->dworlds, replica, (long long)nrec, (const long long *)(buf + o_off), (int *)(buf + o_vid),
+                  (int *)(buf + o_lnk), (double *)(buf + o_x));
+        UX_LAUNCH(k_edie_accumulate, dim3((unsigned)((nrec + 255) / 256)), dim3(256), st, w->dworlds, replica, (long long)nrec, (const long long *)(buf + o_off),
+                  (const int *)(buf + o_vid), (const int *)(buf + o_lnk), (const double *)(buf + o_x), (const long long *)(buf + o_coff), (const int *)(buf + o_cnx),
+                  (const double *)(buf + o_dt), (const double *)(buf + o_dx), (unsigned long long *)(buf + o_tn), (unsigned long long *)(buf + o_dn));
+    }
+    R.tn.assign((size_t)cells, 0.0); R.dn.assign((size_t)cells, 0.0);
+    if (cells) {
+        UX_LAUNCH(k_edie_finish, dim3((unsigned)((cells + 255) / 256)), dim3(256), st, cells, (const unsigned long long *)(buf + o_tn), (const unsigned long long *)(buf + o_dn),
+                  w->p.delta_n, (double *)(buf + o_otn), (double *)(buf + o_odn));
+        cudaMemcpyAsync(R.tn.data(), buf + o_otn, 8 * (size_t)cells, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(R.dn.data(), buf + o_odn, 8 * (size_t)cells, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(w, UX_ERR_CUDA, "CUDA error in edie_state: %s", cudaGetErrorString(e));
+    w->d2h_bytes += 16 * cells; w->h2d_bytes += 8 * (P + 1) + 28 * (long long)L;
+    R.replica = replica;
+    return 0;
+}
+
+static int64_t get_edie_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    auto &R = w->edie;
+    if (R.replica != replica) return fail(w, UX_ERR_RUNTIME, "no Edie state for replica %d", replica);
+    int64_t n = what == UX_A_EDIE_OFFSETS ? (int64_t)R.off.size() : what == UX_A_EDIE_NX ? (int64_t)R.nx.size() : (int64_t)R.tn.size();
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    const void *src = what == UX_A_EDIE_OFFSETS ? (const void *)R.off.data() : what == UX_A_EDIE_NX ? (const void *)R.nx.data() : what == UX_A_EDIE_TN ? (const void *)R.tn.data() : (const void *)R.dn.data();
+    if (n > 0) memcpy(dst, src, (what == UX_A_EDIE_NX ? 4 : 8) * (size_t)n);
+    return n;
+}
+
 UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
     if (is_log_array(what)) return get_log_array(w, what, replica, dst, capacity, nullptr, false);
     if (what >= UX_A_DTA_OD_ORIG && what <= UX_A_DTA_RA_ENTRY_T) return get_dta_array(w, what, replica, dst, capacity);
+    if (what >= UX_A_EDIE_OFFSETS && what <= UX_A_EDIE_DN) return get_edie_array(w, what, replica, dst, capacity);
     if (what == UX_A_VEH_ORIG || what == UX_A_VEH_DEST || what == UX_A_VEH_DEPART_TS) {  // static: answered from the host copy (no upload forced)
         int64_t P = (int64_t)w->vehs.size();
         if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);

@@ -64,13 +64,14 @@ UX_API double ux_get_double(ux_world *w, int what) {
 // ---- per-platoon logs: World::build_all_vehicle_logs_flat_compact (traffi.cpp:1990-2081) + build_enter_log_data (1965-1983) ----
 // The device holds only the RUN records; HOME / WAIT / END entries are implied by the departure, generation and end
 // steps (the reference reconstructs log_t / log_state from the same counters, traffi.cpp:1117-1133).
-static int build_logs(ux_world *w, int replica) {
-    auto &G = w->logs;
-    if (G.replica == replica && G.timestep == w->timestep) return 0;
+// RUN records per platoon (from the generation / end steps) and their offsets in per-platoon time order
+static int log_offsets(ux_world *w, int replica, std::vector<long long> &roff, unsigned long long &nrec, std::vector<int> *gen_out = nullptr,
+                       std::vector<int> *st_out = nullptr, std::vector<int> *arr_out = nullptr, std::vector<int> *end_out = nullptr,
+                       std::vector<unsigned char> *kind_out = nullptr) {
     const DevWorld &d = w->hw[replica];
-    long long P = d.P; int Tnow = w->timestep; double dt = w->dt;
+    long long P = d.P; int Tnow = w->timestep;
     std::vector<int> gen(P), endt(P), st(P), arr(P); std::vector<unsigned char> kind(P);
-    unsigned long long nrec = 0;
+    nrec = 0;
     if (P) {
         CUDA_OK(cudaMemcpy(gen.data(), d.v_gen_ts, sizeof(int) * P, cudaMemcpyDeviceToHost));
         CUDA_OK(cudaMemcpy(endt.data(), d.v_end_ts, sizeof(int) * P, cudaMemcpyDeviceToHost));
@@ -79,14 +80,30 @@ static int build_logs(ux_world *w, int replica) {
         CUDA_OK(cudaMemcpy(arr.data(), d.v_arr_ts, sizeof(int) * P, cudaMemcpyDeviceToHost));
     }
     CUDA_OK(cudaMemcpy(&nrec, d.lg_count, sizeof(nrec), cudaMemcpyDeviceToHost));
-    // RUN entries per platoon and their offsets in the time-ordered record array
-    std::vector<long long> roff(P + 1, 0);
+    roff.assign(P + 1, 0);
     for (long long i = 0; i < P; i++) {
         long long r = 0;
         if (gen[i] >= 0) { int last = kind[i] == 1 ? endt[i] : kind[i] == 2 ? endt[i] - 1 : Tnow - 1; r = last - gen[i] + 1; if (r < 0) r = 0; }
         roff[i + 1] = roff[i] + r;
     }
     if ((unsigned long long)roff[P] != nrec) return fail(w, UX_ERR_RUNTIME, "vehicle log bookkeeping mismatch: %lld expected, %llu recorded", roff[P], nrec);
+    if (gen_out) gen_out->swap(gen);
+    if (st_out) st_out->swap(st);
+    if (arr_out) arr_out->swap(arr);
+    if (end_out) end_out->swap(endt);
+    if (kind_out) kind_out->swap(kind);
+    return 0;
+}
+
+static int build_logs(ux_world *w, int replica) {
+    auto &G = w->logs;
+    if (G.replica == replica && G.timestep == w->timestep) return 0;
+    const DevWorld &d = w->hw[replica];
+    long long P = d.P; int Tnow = w->timestep; double dt = w->dt;
+    std::vector<int> gen, st, arr, endt; std::vector<unsigned char> kind;
+    std::vector<long long> roff;
+    unsigned long long nrec = 0;
+    { int rc = log_offsets(w, replica, roff, nrec, &gen, &st, &arr, &endt, &kind); if (rc) return rc; }
     std::vector<int> r_t(nrec), r_link(nrec), r_lane(nrec); std::vector<double> r_x(nrec), r_v(nrec), r_s(nrec);
     if (nrec) {
         size_t need = sizeof(long long) * (P + 1) + nrec * (3 * sizeof(int) + 3 * sizeof(double)) + 256;
@@ -193,6 +210,9 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_ROUTE_PREF: n = N * L; break;
     case UX_A_ROUTE_DIST: n = N * N; break;
     case UX_A_ROUTE_NEXT: n = N * N; dt = UX_DT_I32; break;
+    case UX_A_EDIE_OFFSETS: n = (int64_t)w->edie.off.size(); dt = UX_DT_I64; break;
+    case UX_A_EDIE_NX: n = (int64_t)w->edie.nx.size(); dt = UX_DT_I32; break;
+    case UX_A_EDIE_TN: case UX_A_EDIE_DN: n = (int64_t)w->edie.tn.size(); break;
     case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = (int64_t)w->dta_p->o.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_OD_OFFSETS: n = (int64_t)w->dta_p->od_off.size(); dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta_p->route_off.size(); dt = UX_DT_I64; break;

@@ -88,3 +88,91 @@ __global__ void k_ensemble_stats(const DevWorld *worlds, int R, const double *pa
     out[i] = a;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Edie states: Analyzer.compute_accurate_traj + compute_edie_state (analyzer.py:205-330) from the RUN
+// records.  Contributions are accumulated in 2^-24 fixed point with integer atomics: the sums are independent of the order.
+// ---------------------------------------------------------------------------------------------------
+#define EDIE_FX 16777216.0
+UX_DEV unsigned long long edie_fx(double v) { return (unsigned long long)(long long)floor(v * EDIE_FX + 0.5); }
+// Python's float % and // for a positive divisor (floatobject.c float_divmod)
+UX_DEV double py_mod(double x, double y) { double m = fmod(x, y); if (m != 0.0 && ((y < 0) != (m < 0))) m += y; return m; }
+UX_DEV double py_floordiv(double x, double y) {
+    double m = fmod(x, y), div = (x - m) / y;
+    if (m != 0.0 && ((y < 0) != (m < 0))) div -= 1.0;
+    if (div == 0.0) return 0.0;
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+UX_DEV void edie_add(unsigned long long *cell, unsigned long long v) {
+#ifdef UX_EMU
+    *cell += v;
+#else
+    atomicAdd(cell, v);
+#endif
+}
+// one trajectory segment (x0,t0) -> (x1,t1) on a link with an nt x nx grid of dt x dx cells (analyzer.py:272-312)
+UX_DEV void edie_segment(unsigned long long *tn, unsigned long long *dn, int nt, int nx, double dt, double dx, double x0, double t0, double x1, double t1) {
+    double v0 = (t1 - t0 != 0) ? (x1 - x0) / (t1 - t0) : 0.0;
+    int tt = (int)py_floordiv(t0, dt), xx = (int)py_floordiv(x0, dx);
+    if (tt < 0) tt += nt;  // Python's negative index
+    if (tt < 0 || !(tt < nt && xx < nx)) return;
+    if (v0 > 0) {
+        double xl0 = dx - py_mod(x0, dx), xl1 = py_mod(x1, dx), tl0 = xl0 / v0, tl1 = xl1 / v0;
+        double x1c = py_floordiv(x1, dx);
+        if ((double)xx == x1c) { edie_add(dn + (size_t)tt * nx + xx, edie_fx(x1 - x0)); edie_add(tn + (size_t)tt * nx + xx, edie_fx(t1 - t0)); }
+        else {
+            int jj = (int)(x1c - xx + 1);
+            for (int j = 0; j < jj; j++) {
+                if (xx + j >= nx) continue;
+                size_t c = (size_t)tt * nx + xx + j;
+                if (j == 0) { edie_add(dn + c, edie_fx(xl0)); edie_add(tn + c, edie_fx(tl0)); }
+                else if (j == jj - 1) { edie_add(dn + c, edie_fx(xl1)); edie_add(tn + c, edie_fx(tl1)); }
+                else { edie_add(dn + c, edie_fx(dx)); edie_add(tn + c, edie_fx(dx / v0)); }
+            }
+        }
+    } else edie_add(tn + (size_t)tt * nx + xx, edie_fx(t1 - t0));
+}
+
+// RUN records -> per-platoon time order (platoon id, link, position)
+__global__ void k_edie_order(const DevWorld *worlds, int replica, long long n, const long long *off, int *o_vid, int *o_link, double *o_x) {
+    const DevWorld &W = worlds[replica];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int vid = W.lg_vid[i];
+    long long d = off[vid] + (W.lg_t[i] - W.v_gen_ts[vid]);
+    o_vid[d] = vid; o_link[d] = W.lg_link[i]; o_x[d] = W.lg_x[i];
+}
+
+// thread per ordered record j: the segment to the platoon's next record on the same link, plus the free-flow extrapolation
+// of the first / last record of a link traversal (compute_accurate_traj, analyzer.py:233-246)
+__global__ void k_edie_accumulate(const DevWorld *worlds, int replica, long long n, const long long *off, const int *o_vid, const int *o_link, const double *o_x,
+                                  const long long *cell_off, const int *cell_nx, const double *edie_dt, const double *edie_dx,
+                                  unsigned long long *tn, unsigned long long *dn) {
+    const DevWorld &W = worlds[replica];
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int vid = o_vid[j], l = o_link[j];
+    long long a = off[vid], b = off[vid + 1];
+    int nx = cell_nx[l];
+    if (nx <= 0) return;
+    int nt = (int)((cell_off[l + 1] - cell_off[l]) / nx);
+    if (nt <= 0) return;
+    unsigned long long *ltn = tn + cell_off[l], *ldn = dn + cell_off[l];
+    double dt = edie_dt[l], dx = edie_dx[l], u = W.l_vmax[l], len = W.l_length[l];
+    double x = o_x[j], t = (double)(W.v_gen_ts[vid] + (int)(j - a)) * W.dt;  // log_t_at: (first step + k) * delta_t
+    bool first = j == a || o_link[j - 1] != l, last = j + 1 == b || o_link[j + 1] != l;
+    if (first && x != 0 && x / u > W.dt * 0.01) edie_segment(ltn, ldn, nt, nx, dt, dx, 0.0, t - x / u, x, t);
+    if (!last) edie_segment(ltn, ldn, nt, nx, dt, dx, x, t, o_x[j + 1], (double)(W.v_gen_ts[vid] + (int)(j + 1 - a)) * W.dt);
+    else if (len - u * W.dt <= x && x < len) {
+        double rem = len - x;
+        if (rem / u > W.dt * 0.01) edie_segment(ltn, ldn, nt, nx, dt, dx, x, t, len, t + rem / u);
+    }
+}
+
+__global__ void k_edie_finish(long long cells, const unsigned long long *tn, const unsigned long long *dn, double dn_scale, double *out_tn, double *out_dn) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    out_tn[c] = (double)(long long)tn[c] / EDIE_FX * dn_scale; out_dn[c] = (double)(long long)dn[c] / EDIE_FX * dn_scale;
+}

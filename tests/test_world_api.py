@@ -110,3 +110,25 @@ def test_vehicle_log_properties(cuda_api):
     route, ts = veh.traveled_route()
     assert route.links == [link] and len(ts) == 2
     assert list(link.vehicles_enter_log.values()) == [veh]
+
+
+@pytest.mark.gpu
+def test_analyzer_edie_and_od_through_the_world_api(cuda_api):
+    """BasicAnalyzer (used when the reference package is not installed): Edie k/q/v grids from the device and OD statistics
+    agree with each other and with the link curves."""
+    from uxsim_b200.analysis import BasicAnalyzer
+
+    W = S.straight_3link_spillback().to_world(print_mode=0)
+    W.exec_simulation()
+    A = BasicAnalyzer(W)
+    A.basic_analysis()
+    A.compute_edie_state()
+    for l in W.LINKS:
+        assert l.k_mat.shape == l.q_mat.shape == l.v_mat.shape and l.k_mat.shape[1] == int(l.length / l.edie_dx)
+        assert np.isfinite(l.v_mat).all() and (l.v_mat <= l.u * (1 + 1e-9)).all()
+        # vehicle-metres in the grid ~ vehicles that traversed the link x its length (up to the cells cut off at the end)
+        assert l.dn_mat.sum() <= l.cum_arrival[-1] * l.length * (1 + 1e-9)
+        assert l.dn_mat.sum() > 0.5 * l.cum_departure[-1] * l.length
+    od = A.od_analysis()
+    assert od["total_trips"].sum() == A.trip_all and od["completed_trips"].sum() == A.trip_completed
+    assert np.isclose((od["completed_trips"] * np.where(od["completed_trips"] > 0, od["average_travel_time"], 0)).sum(), A.total_travel_time)

@@ -95,6 +95,46 @@ class BasicAnalyzer:
             p(f" delay ratio:\t\t\t {self.average_delay / self.average_travel_time:.3f}")
             p(f" total distance traveled:\t {self.total_distance_traveled:.1f} m")
 
+    def compute_edie_state(self):
+        """Edie's traffic state per link (analyzer.py:249-330): fills ``tn_mat, dn_mat, k_mat, q_mat, v_mat`` of every link
+        from the device (one pass over the RUN records, ``ux_edie_state``) instead of Python loops over every log entry."""
+        W = self.W
+        if getattr(self, "flag_edie_state_computed", 0):
+            return 0
+        self.flag_edie_state_computed = 1
+        res = W._E.edie_state([l.edie_dt for l in W.LINKS], [l.edie_dx for l in W.LINKS])
+        for l, (tn, dn) in zip(W.LINKS, res):
+            nt, nx = tn.shape
+            l.tn_mat[:nt, :nx], l.dn_mat[:nt, :nx] = tn, dn
+            l.k_mat, l.q_mat = tn / l.edie_dt / l.edie_dx, dn / l.edie_dt / l.edie_dx
+            with np.errstate(invalid="ignore", divide="ignore"):
+                l.v_mat = np.nan_to_num(l.q_mat / l.k_mat, nan=l.u)
+
+    def od_analysis(self):
+        """OD-specific stats (analyzer.py:121-181) from the per-platoon arrays: dict of arrays over the OD pairs that occur,
+        keys ``orig, dest`` (node ids), ``total_trips, completed_trips, free_travel_time, average_travel_time,
+        stddiv_travel_time, average_distance_traveled_per_veh, stddiv_distance_traveled_per_veh``."""
+        W = self.W
+        dn = W.DELTAN
+        n = len(W.NODES)
+        o, d = W._E.get_array(C.A_VEH_ORIG).astype(np.int64), W._E.get_array(C.A_VEH_DEST).astype(np.int64)
+        tt, dist = W._veh("travel_time"), W._veh("distance")
+        key, inv = np.unique(o * n + d, return_inverse=True)
+        k = len(key)
+        done = tt >= 0
+        trips, comp = np.bincount(inv, minlength=k) * dn, np.bincount(inv[done], minlength=k) * dn
+        cnt = np.maximum(np.bincount(inv[done], minlength=k), 1)
+        tt_ave = np.bincount(inv[done], weights=tt[done], minlength=k) / cnt
+        tt_var = np.bincount(inv[done], weights=(tt[done] - tt_ave[inv[done]]) ** 2, minlength=k) / cnt
+        call = np.maximum(np.bincount(inv, minlength=k), 1)
+        d_ave = np.bincount(inv, weights=dist, minlength=k) / call
+        d_var = np.bincount(inv, weights=(dist - d_ave[inv]) ** 2, minlength=k) / call
+        ff = free_flow_times(W)
+        has = comp > 0
+        return dict(orig=key // n, dest=key % n, total_trips=trips, completed_trips=comp, free_travel_time=ff[key // n, key % n],
+                    average_travel_time=np.where(has, tt_ave, -1.0), stddiv_travel_time=np.where(has, np.sqrt(tt_var), -1.0),
+                    average_distance_traveled_per_veh=d_ave, stddiv_distance_traveled_per_veh=np.sqrt(d_var))
+
     def link_summary(self):
         """traffic_volume / vehicles_remain / free and average travel time per link (link_analysis_coarse, analyzer.py:183-203)."""
         W = self.W

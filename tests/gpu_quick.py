@@ -16,6 +16,7 @@ def probe(wl, R):
     ks = " ".join(f"{C.K_NAMES[k]}={E.get_double(C.D_KERNEL_MS_OF+k)/max(1,E.get_int(C.I_KERNEL_LAUNCHES_OF+k))*1e3:.1f}us x{E.get_int(C.I_KERNEL_LAUNCHES_OF+k)}" for k in range(6))
     print(f"{wl:12s} R={R:3d} graph loop {ms:8.2f} ms  {upd/ms*1e3:.3e} upd/s | eager-timed: {ks}", flush=True)
     E.close()
+RS = [int(r) for r in os.environ.get("UX_RS", "1,8,32").split(",")]
 for wl in sys.argv[1:] or ["chicago", "chicago_dn5", "grid11"]:
-    for R in (1, 8, 32):
+    for R in RS:
         probe(wl, R)

@@ -55,6 +55,16 @@ def test_stochastic_bit_exact(name, mk, cuda_api, oracle_api):
     assert Eg.get_int(C.I_TRIPS_COMPLETED) == Eo.get_int(C.I_TRIPS_COMPLETED)
 
 
+@pytest.mark.parametrize("mode", ["wave", "frontier", "sweep"])
+@pytest.mark.parametrize("name", ["siouxfalls", "grid6_signals", "chicago_dn30"])
+def test_shortest_path_kernel_variants_bit_exact(name, mode, cuda_api, oracle_api, monkeypatch):
+    """Every route-search kernel (whole-edge sweeps, shared-memory worklist, L2-resident near-far wavefront) reaches the same
+    fixed point: forced on networks of any size with UXSIM_B200_SSSP, results stay bit-identical to the oracle."""
+    monkeypatch.setenv("UXSIM_B200_SSSP", mode)
+    Eg, Eo = run_pair(dict(STOCHASTIC)[name](), cuda_api, oracle_api)
+    assert compare_engines(Eg, Eo) == []
+
+
 def test_chunked_execution_equals_single_run(cuda_api, oracle_api):
     """exec_simulation(until_t=...) in chunks (test_verification_straight_road.py:940-1113) == one run."""
     sc = S.grid(n=5, seed=9, tmax=3000, demand_t=1000)

@@ -34,6 +34,8 @@ struct DevWorld {
     const int *seg_link, *seg_start;
     const int *e_from, *e_to, *e_link;  // node-pair edges (leading link of each pair)
     const int *ein_off, *ein_from, *ein_eid;  // the same edges grouped by their END node (CSR), for the frontier search
+    const int *eout_off, *eout_to;            // ... and grouped by their START node, end nodes ascending (next-hop pass)
+    const int *e_inpos, *e_outpos;            // position of edge e in the two CSRs (k_edge_cost scatters the costs there)
     int n_edges;
     // dynamic (per replica)
     int *head, *tail, *tail_k1, *pop_k2, *hcount, *trips, *ev_cnt;
@@ -54,6 +56,8 @@ struct DevWorld {
     double *cum_arr, *cum_dep, *tt_inst, *ev_tt;
     int *ev_ord, *sig_log;
     double *pref, *rdist, *pair_cost;
+    double *sssp_delta;          // bucket width of the near-far shortest-path search (k_cost_stats)
+    double *cost_in, *cost_out;  // pair_cost in ein / eout order with unusable edges (cost <= 0, inf) already +inf
     int *pref_active, *has_path, *rnext;
     // link-entry events (platoon, ordinal of the link on its route, link, step) in arrival order; only with UX_OPT_RECORD_TRAVERSALS
     int4 *tv_ev; unsigned long long *tv_count; long long tv_cap;

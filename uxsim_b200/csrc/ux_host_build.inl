@@ -394,6 +394,13 @@ static int upload(ux_world *w) {
         for (int i = 0; i < N; i++) ein_off[i + 1] += ein_off[i];
         for (int e = 0; e < Ep; e++) { int j = e_to[e], q = ein_off[j] + fill[j]++; ein_from[q] = e_from[e]; ein_eid[q] = e; }
         base.ein_off = dupload(w, ein_off); base.ein_from = dupload(w, ein_from); base.ein_eid = dupload(w, ein_eid);
+        std::vector<int> e_inpos(Ep), e_outpos(Ep), eout_off(N + 1, 0), eout_to(Ep), order(Ep);
+        for (int q = 0; q < Ep; q++) e_inpos[ein_eid[q]] = q;
+        for (int e = 0; e < Ep; e++) { eout_off[e_from[e] + 1]++; order[e] = e; }
+        for (int i = 0; i < N; i++) eout_off[i + 1] += eout_off[i];
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return e_from[a] != e_from[b] ? e_from[a] < e_from[b] : e_to[a] < e_to[b]; });
+        for (int q = 0; q < Ep; q++) { e_outpos[order[q]] = q; eout_to[q] = e_to[order[q]]; }
+        base.eout_off = dupload(w, eout_off); base.eout_to = dupload(w, eout_to); base.e_inpos = dupload(w, e_inpos); base.e_outpos = dupload(w, e_outpos);
     }
     // ---- nodes
     std::vector<int> out_off(N + 1, 0), in_off(N + 1, 0), out, in, sig_off(N + 1, 0), n_lanes(N), n_out_lanes(N);
@@ -505,6 +512,7 @@ static int upload(ux_world *w) {
         d.cum_arr = dalloc<double>(w, TL); d.cum_dep = dalloc<double>(w, TL); d.tt_inst = dalloc<double>(w, TL); d.ev_tt = dalloc<double>(w, TL);
         d.ev_ord = dalloc<int>(w, TL); d.sig_log = dalloc<int>(w, (size_t)T * N);
         d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
+        d.cost_in = dalloc<double>(w, w->n_edges); d.cost_out = dalloc<double>(w, w->n_edges); d.sssp_delta = dalloc<double>(w, 1);
         d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
         reg_ff(d.rnext, sizeof(int) * (size_t)D * N);
         d.err = w->d_err_all + 2 * r; d.t_base = dupload(w, tb); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
@@ -522,7 +530,7 @@ static int upload(ux_world *w) {
     return 0;
 }
 
-static void launch_sssp(ux_world *w, cudaStream_t st) {
+static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of kernels launched
     int N = (int)w->nodes.size();
 #ifdef UX_EMU
     UX_LAUNCH(k_sssp<false>, dim3(w->n_active, w->R), dim3(SSSP_THREADS), st, w->dworlds);
@@ -530,16 +538,34 @@ static void launch_sssp(ux_world *w, cudaStream_t st) {
     size_t bytes = (size_t)N * 12 + 16, fbytes = (size_t)((N + 3) & ~3) * 17 + 64;
     int use_smem = bytes <= 200 * 1024;
     // small graphs converge in a few dozen whole-edge sweeps (cheaper than one barrier per wavefront); large sparse graphs
-    // are dominated by sweeps x E and switch to the worklist kernel
-    if (N >= 2048 && N < 65536 && fbytes <= 220 * 1024) {
+    // are dominated by sweeps x E and switch to a worklist kernel: k_sssp_wave (labels in L2, ~10 destinations per SM), or
+    // k_sssp_frontier (labels in shared memory, one destination per SM; UXSIM_B200_SSSP=frontier keeps it reachable for tests)
+    const int mode = [] { const char *e = getenv("UXSIM_B200_SSSP"); return !e ? 0 : !strcmp(e, "sweep") ? 1 : !strcmp(e, "frontier") ? 2 : !strcmp(e, "wave") ? 3 : 0; }();
+    const int wave_pad = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_PAD"); return e ? atoi(e) : -1; }();
+    bool large = N >= 2048 && N < 65536;
+    if ((mode == 3 || (mode == 0 && large)) && N < 65536) {
+        // shared memory per block = queue + bitmap, padded so that the dist rows of the resident blocks stay within ~96 MB of L2
+        size_t wbytes = (size_t)((N + 2 * SSSP_WAVE_THREADS + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 16;
+        size_t row_bytes = (size_t)N * 8, per_sm = std::max<size_t>(1, ((size_t)96 << 20) / 148 / std::max<size_t>(row_bytes, 1));
+        size_t pad_to = wave_pad >= 0 ? (size_t)wave_pad : (per_sm >= 16 ? 0 : ((size_t)220 * 1024) / per_sm);
+        if (pad_to > wbytes) wbytes = std::min<size_t>(pad_to, (size_t)220 * 1024);
+        if (wbytes <= 220 * 1024) {
+            if (wbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
+            k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds);
+            k_sssp_wave<<<dim3(w->n_active, w->R), dim3(SSSP_WAVE_THREADS), wbytes, st>>>(w->dworlds);
+            return 2;
+        }
+    }
+    if ((mode == 2 || (mode == 0 && large)) && N < 65536 && fbytes <= 220 * 1024) {
         if (fbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fbytes);
         k_sssp_frontier<<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), fbytes, st>>>(w->dworlds);
-        return;
+        return 1;
     }
     if (use_smem && bytes > 48 * 1024) cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (use_smem) k_sssp<true><<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), bytes, st>>>(w->dworlds);
     else k_sssp<false><<<dim3(w->n_active, w->R), dim3(SSSP_THREADS), 0, st>>>(w->dworlds);
 #endif
+    return 1;
 }
 
 #ifdef UX_EMU

@@ -20,7 +20,7 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
         if (w->n_active > 0 && w->n_edges > 0) {
             if (route) {
                 KT_BEGIN(UX_K_EDGE_COST) UX_LAUNCH(k_edge_cost, dim3((w->n_edges + 127) / 128, R), dim3(128), st, w->dworlds, s); KT_END(UX_K_EDGE_COST) lc++;
-                KT_BEGIN(UX_K_SSSP) launch_sssp(w, st); KT_END(UX_K_SSSP) lc++;
+                KT_BEGIN(UX_K_SSSP) lc += launch_sssp(w, st); KT_END(UX_K_SSSP)
             }
             if (route || w->p.route_choice_update_gradual) {
                 long long tot = (long long)w->n_active * (long long)w->links.size();

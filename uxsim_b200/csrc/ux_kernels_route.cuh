@@ -26,6 +26,9 @@ __global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int s
         if (W.l_cap_in[l] == 0.0) cost = INFINITY;
     }
     W.pair_cost[e] = cost;
+    double cf = (cost > 0.0) ? cost : INFINITY;  // adj > 0 filter (traffi.cpp:1331) folded in: +inf never relaxes anything
+    W.cost_in[W.e_inpos[e]] = cf;
+    W.cost_out[W.e_outpos[e]] = cf;
 }
 
 // One block per active destination: label-correcting relaxation to the fixed point dist[i] = min_j c_ij + dist[j]
@@ -199,6 +202,143 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp_frontier(const DevWorld *
         gnext[i] = nx;
         gdist[i] = dist[i];
     }
+    if (tid == 0) W.has_path[row] = any ? 1 : 0;
+#endif
+}
+
+// Wavefront variant for large sparse graphs (N >= 2048): a label-correcting worklist like k_sssp_frontier, but
+//  * the destination's dist row stays where it will end up -- in its global row, i.e. in the 126 MB L2 -- and only the
+//    worklist lives in shared memory: one circular queue of node ids (a node is queued at most once, so N entries hold
+//    the current and the next wavefront together) plus the queued bitmap, 2N + N/8 bytes.  k_sssp_frontier keeps 17N
+//    bytes per destination in shared memory and runs ONE destination per SM; here 7-10 destinations per SM are in flight
+//    (the launcher pads shared memory so that the rows of the resident blocks, 8N bytes each, stay L2-resident);
+//  * the worklist is processed near-far (Delta-stepping with a single queue): only nodes with label < tau relax their
+//    in-edges, the others go round once more; when no queued label is below tau, tau jumps to (smallest queued label +
+//    Delta), Delta = 2 x mean edge cost (k_cost_stats).  On congested networks (edge costs spread over two orders of
+//    magnitude) plain FIFO order re-relaxes every node 5-10 times; this order brings it to ~1.1 and the L2 requests per
+//    destination from ~450k to ~105k (tests/micro/sssp_order_proto.py, measured on the C4 grid's own costs).
+// tau and the queue minimum are kept on the grid of the labels' upper 32 bits (monotone for non-negative doubles): the
+// order only steers the work, the fixed point -- hence dist / next -- is the one of k_sssp and the oracle.
+// Relaxation = red.min on the bit pattern (no return value needed: whoever saw a larger label queues the node, the
+// bitmap removes duplicates).
+#define SSSP_WAVE_THREADS 128
+__global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds) {
+#ifndef UX_EMU
+    const DevWorld &W = worlds[blockIdx.y];
+    __shared__ double ssum[256];
+    __shared__ int scnt[256];
+    int tid = (int)threadIdx.x;
+    double s = 0.0; int c = 0;
+    for (int e = tid; e < W.n_edges; e += 256) { double v = W.cost_in[e]; if (v < INFINITY) { s += v; c++; } }
+    ssum[tid] = s; scnt[tid] = c;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) { if (tid < h) { ssum[tid] += ssum[tid + h]; scnt[tid] += scnt[tid + h]; } __syncthreads(); }
+    if (tid == 0) *W.sssp_delta = scnt[0] > 0 ? 2.0 * ssum[0] / (double)scnt[0] : 1.0;
+#endif
+}
+
+__global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld *worlds) {
+#ifndef UX_EMU
+    LOAD_WORLD(W, worlds)
+    int row = (int)blockIdx.x;
+    if (row >= W.D) return;
+    int N = W.N, k = W.row_dest[row];
+    int tid = (int)threadIdx.x, nth = (int)blockDim.x, cap = N + 2 * nth;
+    extern __shared__ unsigned long long sssp_smem[];
+    unsigned short *Q = reinterpret_cast<unsigned short *>(sssp_smem);
+    unsigned int *inq = reinterpret_cast<unsigned int *>(Q + ((cap + 3) & ~3));
+    __shared__ int q_tail;
+    __shared__ unsigned int lo_min[2];  // per round parity: lower bound of the queued labels (upper 32 bits)
+    unsigned long long *du = reinterpret_cast<unsigned long long *>(W.rdist + (size_t)row * N);
+    int *gnext = W.rnext + (size_t)row * N;
+    const double *cin = W.cost_in;
+    const int *ein_off = W.ein_off, *ein_from = W.ein_from;
+    const unsigned long long INF_BITS = 0x7ff0000000000000ull;
+    double delta = *W.sssp_delta;
+    for (int i = tid; i < N; i += nth) __stcg(du + i, i == k ? 0ull : INF_BITS);
+    for (int i = tid; i < (N + 31) / 32; i += nth) inq[i] = 0u;
+    if (tid == 0) { Q[0] = (unsigned short)k; q_tail = 1; inq[k >> 5] = 1u << (k & 31); lo_min[0] = 0u; lo_min[1] = 0xffffffffu; }
+    __syncthreads();
+    int head = 0;  // monotone counters; slot = counter % cap
+    unsigned int tau_hi = 0u;
+    for (int r = 0;; r++) {
+        int tail = q_tail, p = r & 1;
+        if (tail == head) break;
+        unsigned int m_hi = lo_min[p];
+        if (m_hi >= tau_hi) {  // nothing queued is below tau: jump
+            double tnew = __longlong_as_double((long long)((unsigned long long)m_hi << 32)) + delta;
+            unsigned int th = (unsigned int)((unsigned long long)__double_as_longlong(tnew) >> 32);
+            tau_hi = th > m_hi ? th : m_hi + 1u;
+        }
+        unsigned int mymin = 0xffffffffu;
+        for (int base = head; base < tail; base += nth) {
+            int idx = base + tid, j = -1;
+            unsigned long long dj = 0ull;
+            bool near = false, far = false;
+            if (idx < tail) {
+                j = Q[idx % cap]; dj = __ldcg(du + j);
+                near = (unsigned int)(dj >> 32) < tau_hi;
+                far = !near;
+                if (near) atomicAnd(&inq[j >> 5], ~(1u << (j & 31)));
+            }
+            // every queued bit of this chunk is cleared before anyone can re-queue, and everybody has read q_tail / lo_min[p]
+            // before the first append of the round
+            __syncthreads();
+            if (base == head && tid == 0) lo_min[p] = 0xffffffffu;  // round r+1 collects into it
+            if (far) {  // stays queued (its bit is still set): goes round once more
+                unsigned int hj = (unsigned int)(dj >> 32);
+                Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)j;
+                if (hj < mymin) mymin = hj;
+            }
+            if (near) {
+                double djd = __longlong_as_double((long long)dj);
+                int q0 = __ldg(ein_off + j), q1 = __ldg(ein_off + j + 1);
+                for (int q = q0; q < q1; q += 4) {  // loads of four in-edges in flight together
+                    int ii[4]; unsigned long long nd[4], cu[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        bool in = q + u < q1;
+                        ii[u] = in ? __ldg(ein_from + q + u) : -1;
+                        nd[u] = in ? (unsigned long long)__double_as_longlong(__ldg(cin + q + u) + djd) : INF_BITS;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) cu[u] = ii[u] >= 0 ? __ldcg(du + ii[u]) : 0ull;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (ii[u] >= 0 && nd[u] < cu[u]) {
+                            atomicMin(du + ii[u], nd[u]);
+                            unsigned int hn = (unsigned int)(nd[u] >> 32), bit = 1u << (ii[u] & 31);
+                            if (hn < mymin) mymin = hn;
+                            if (!(atomicOr(&inq[ii[u] >> 5], bit) & bit)) Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)ii[u];
+                        }
+                    }
+                }
+            }
+            if (base + nth < tail) __syncthreads();  // the next chunk's pops (label read + bit clear) must not overlap these relaxations
+        }
+        unsigned int wm = __reduce_min_sync(0xffffffffu, mymin);
+        if ((tid & 31) == 0 && wm != 0xffffffffu) atomicMin(&lo_min[p ^ 1], wm);
+        head = tail;
+        __syncthreads();  // this round's red.min / queue appends are visible before the next round reads them
+    }
+    // next hop: smallest end node j of an out-edge with c_ij + dist[j] == dist[i] (out-edges are stored ends ascending)
+    int any = 0;
+    const double *cout_ = W.cost_out;
+    for (int i = tid; i < N; i += nth) {
+        int nx = -1;
+        if (i == k) nx = k;
+        else {
+            double di = __longlong_as_double((long long)__ldcg(du + i));
+            if (!is_inf(di)) {
+                for (int q = __ldg(W.eout_off + i); q < __ldg(W.eout_off + i + 1); q++) {
+                    int j = __ldg(W.eout_to + q);
+                    if (__ldg(cout_ + q) + __longlong_as_double((long long)__ldcg(du + j)) == di) { nx = j; any = 1; break; }
+                }
+            }
+        }
+        gnext[i] = nx;
+    }
+    any = __syncthreads_or(any);
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
 #endif
 }

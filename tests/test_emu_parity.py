@@ -53,6 +53,15 @@ def test_emulated_vehicle_logs_match_oracle(name, mk, emu_api, oracle_api):
     assert compare_logs(Ee, Eo) == [] and compare_engines(Ee, Eo) == []
 
 
+@pytest.mark.parametrize("name,mk", LOG_CASES[1:] + [("siouxfalls", lambda: S.sioux_falls(seed=1))], ids=[c[0] for c in LOG_CASES[1:]] + ["siouxfalls"])
+def test_emulated_replica_lane_update(name, mk, emu_api, oracle_api, monkeypatch):
+    """k_update_rl (thread per link and replica; what ensembles run) forced on a single scenario: same results, same logs."""
+    monkeypatch.setenv("UXSIM_B200_UPDATE", "rl")
+    sc = mk()
+    Ee, Eo = run_pair(sc, emu_api, oracle_api, vehicle_logging_timestep_interval=1)
+    assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
+
+
 def test_all_replica_getter_matches_per_replica(emu_api):
     """get_array(replica=-1): [R, n] in one transfer == the per-replica getters."""
     from uxsim_b200 import _capi as C

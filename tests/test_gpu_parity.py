@@ -90,6 +90,36 @@ def test_replicas_match_independent_seeds(cuda_api, oracle_api):
     assert np.array_equal(ens[:, 0], vol)
 
 
+@pytest.mark.parametrize("name,R,force", [("chicago_dn30", 40, True), ("grid6_signals", 33, True), ("siouxfalls", 8, True), ("grid6_signals", 64, False)])
+def test_replica_lane_update_kernel(name, R, force, cuda_api, oracle_api, monkeypatch):
+    """Large ensembles run the link update with one thread per (link, replica) (k_update_rl; picked by itself from 64 replicas
+    on lightly loaded networks, forced here for ragged replica counts): every replica still equals the single-seed oracle run."""
+    if force:
+        monkeypatch.setenv("UXSIM_B200_UPDATE", "rl")
+    sc = dict(STOCHASTIC)[name]()
+    Eg = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1, num_replicas=R)
+    Eg.main_loop()
+    for r in (0, 7, R - 1):
+        Eo = sc.to_engine(oracle_api, vehicle_logging_timestep_interval=-1, random_seed=sc.world.get("random_seed", 0) + r)
+        Eo.main_loop()
+        assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"
+
+
+@pytest.mark.parametrize("mode", ["rl", "warp"])
+@pytest.mark.parametrize("name,mk", [("3lane", S.multilane_3lane), ("short_chain", S.short_links_chain), ("grid6_signals", dict(STOCHASTIC)["grid6_signals"]),
+                                     ("chicago_dn30", dict(STOCHASTIC)["chicago_dn30"]), ("chicago_dn5", lambda: S.chicago_sketch(deltan=5, seed=0, tmax=2500))],
+                         ids=["3lane", "short_chain", "grid6_signals", "chicago_dn30", "chicago_dn5"])
+def test_update_kernel_variants_bit_exact(name, mk, mode, cuda_api, oracle_api, monkeypatch):
+    """Both forms of the link update (warp per link / thread per link and replica) forced on single scenarios, logs on:
+    long queues (Chicago at deltan=5) exercise the warp-cooperative tail of k_update_rl."""
+    monkeypatch.setenv("UXSIM_B200_UPDATE", mode)
+    log = 1 if name != "chicago_dn5" else -1
+    Eg, Eo = run_pair(mk(), cuda_api, oracle_api, vehicle_logging_timestep_interval=log)
+    assert compare_engines(Eg, Eo) == []
+    if log == 1:
+        assert compare_logs(Eg, Eo) == []
+
+
 def test_run_to_run_determinism(cuda_api):
     sc = S.sioux_falls(seed=5)
     Ea = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)

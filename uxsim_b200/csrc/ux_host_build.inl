@@ -551,7 +551,8 @@ static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of
         if (pad_to > wbytes) wbytes = std::min<size_t>(pad_to, (size_t)220 * 1024);
         if (wbytes <= 220 * 1024) {
             if (wbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
-            k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds);
+            static const double factor = [] { const char *e = getenv("UXSIM_B200_SSSP_DELTA"); return e ? atof(e) : 2.0; }();  // bucket width / mean edge cost
+            k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds, factor);
             k_sssp_wave<<<dim3(w->n_active, w->R), dim3(SSSP_WAVE_THREADS), wbytes, st>>>(w->dworlds);
             return 2;
         }

@@ -7,6 +7,11 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
     cudaStream_t st = w->stream;
     dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_WARPS - 1) / UPD_WARPS, R);
     long long lc = 0;
+    // Large ensembles of lightly loaded networks run the link update with one thread per (link, replica) (k_update_rl: 4x fewer
+    // warp instructions; B200, Chicago sketch: 102 -> 77 us at 64 replicas, 198 -> 116 us at 128); below 64 replicas, or with
+    // long queues (more than 32 platoons per link on average), the warp-per-link kernel wins.  UXSIM_B200_UPDATE=rl|warp forces one.
+    const char *upd_env = getenv("UXSIM_B200_UPDATE");
+    bool update_rl = upd_env ? !strcmp(upd_env, "rl") : (R >= 64 && (long long)w->vehs.size() <= 32ll * (long long)w->links.size());
     for (int s = 0; s < nsteps; s++) {
         if (N > 0) {
             KT_BEGIN(UX_K_TRANSFER)
@@ -15,7 +20,23 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
             else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
             KT_END(UX_K_TRANSFER) lc++;
         }
-        if (w->nseg > 0) { KT_BEGIN(UX_K_UPDATE) UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s); KT_END(UX_K_UPDATE) lc++; }
+        if (w->nseg > 0) {
+            KT_BEGIN(UX_K_UPDATE)
+            if (update_rl) {
+                // helper blocks (grid z) share long queues; the head-of-link log records need the whole queue in one block
+                static const int rl_parts = [] { const char *e = getenv("UXSIM_B200_RL_PARTS"); return e ? atoi(e) : 4; }();
+                dim3 g_rl(((int)w->links.size() + UPD_RL_WARPS - 1) / UPD_RL_WARPS, (R + 31) / 32, w->p.vehicle_log_mode ? 1 : std::max(1, rl_parts));
+#ifdef UX_EMU
+                UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R);
+#else
+                const size_t rl_bytes = 32 * UPD_RL_STRIDE * 8;  // the replicas' DevWorld structs
+                if (s == 0) cudaFuncSetAttribute(k_update_rl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_bytes);  // per device
+                k_update_rl<<<g_rl, dim3(32 * UPD_RL_WARPS), rl_bytes, st>>>(w->dworlds, s, R);
+#endif
+            }
+            else UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s);
+            KT_END(UX_K_UPDATE) lc++;
+        }
         bool route = ((phase + s) % w->route_ts) == 0;
         if (w->n_active > 0 && w->n_edges > 0) {
             if (route) {

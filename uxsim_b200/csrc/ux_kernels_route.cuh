@@ -221,8 +221,10 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp_frontier(const DevWorld *
 // order only steers the work, the fixed point -- hence dist / next -- is the one of k_sssp and the oracle.
 // Relaxation = red.min on the bit pattern (no return value needed: whoever saw a larger label queues the node, the
 // bitmap removes duplicates).
-#define SSSP_WAVE_THREADS 128
-__global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds) {
+#ifndef SSSP_WAVE_THREADS
+#define SSSP_WAVE_THREADS 256
+#endif
+__global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds, double factor) {
 #ifndef UX_EMU
     const DevWorld &W = worlds[blockIdx.y];
     __shared__ double ssum[256];
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds) {
     ssum[tid] = s; scnt[tid] = c;
     __syncthreads();
     for (int h = 128; h > 0; h >>= 1) { if (tid < h) { ssum[tid] += ssum[tid + h]; scnt[tid] += scnt[tid + h]; } __syncthreads(); }
-    if (tid == 0) *W.sssp_delta = scnt[0] > 0 ? 2.0 * ssum[0] / (double)scnt[0] : 1.0;
+    if (tid == 0) *W.sssp_delta = scnt[0] > 0 ? factor * ssum[0] / (double)scnt[0] : 1.0;
 #endif
 }
 

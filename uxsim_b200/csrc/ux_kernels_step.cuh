@@ -676,6 +676,10 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
     double len = W.l_length[l], udt = W.l_udt[l], dpl = W.l_dpl_dn[l];
     int hd = hd0 + pk2, n = tl - hd;
     int s0 = part;
+    if (n == 0) {  // empty link: nothing moves, nothing is counted; only the double-buffered head is carried over
+        if (s0 == 0 && (threadIdx.x & 31) == 0) { W.head[(cur ^ 1) * L + l] = hd; W.hcount[l] = 0; }
+        return;
+    }
     const double *Xc = W.X + (size_t)cur * C + o;
     if (s0 == 0) {
         // ---- link head
@@ -781,3 +785,248 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K3, ensemble form ("replica lanes"): the same link update, but one THREAD per (link, replica) -- a warp is one link in
+// 32 seeded replicas.  k_update spends a whole warp on a link whose head has 1-3 positions and whose queue holds two
+// platoons on average (Chicago sketch: 343 warp instructions per link and replica, 13 lanes active); here the 32 replicas
+// of the link walk the same code together, the static link constants are one broadcast load per warp, and the kernel is one
+// wave of L*R/32 warps instead of L*R.  Each thread runs the head positions and the first UPD_RL_SERIAL queue positions
+// serially; longer queues are finished warp-cooperatively, one replica at a time (32 positions per pass, as k_update does).
+// The replicas' DevWorld structs are staged in shared memory once per block (row stride = odd number of 8-byte words: the
+// per-lane pointer reads are bank-conflict free), so every helper (route_choice, log_run_record, dev_error) is shared with
+// k_update.  Bit-identical to k_update: the arithmetic per link is the same and links do not interact within this kernel.
+// ---------------------------------------------------------------------------------------------------
+#define UPD_RL_WARPS 8
+#define UPD_RL_SERIAL 32
+#define UPD_RL_STRIDE (((sizeof(DevWorld) + 7) / 8) | 1)
+
+UX_DEV void upd_newell(const DevWorld &W, int l, int t, int cur, int hd, int n, int pos, int cap, long long o, int lanes,
+                       double len, double udt, double dpl, const double *Xc) {
+    int p = ring_slot(hd, pos, cap);
+    if (W.log_mode && pos >= 2 * lanes) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, 0, 0);
+    double x = Xc[p];
+    double xn = x + udt;
+    if (pos >= lanes) {
+        double gap = Xc[ring_slot(hd, pos - lanes, cap)] - dpl;
+        if (gap < x) gap = x;
+        if (xn > gap) xn = gap;
+    }
+    if (xn < x) xn = x;
+    if (xn > len) xn = len;
+    W.X[(size_t)(cur ^ 1) * (size_t)W.C + o + p] = xn;
+    W.V[o + p] = (xn - x) / W.dt;
+}
+
+#define UPD_RL_HITEMS 64
+struct HeadItems { int vid[UPD_RL_HITEMS], next[UPD_RL_HITEMS]; double xn[UPD_RL_HITEMS]; unsigned char kind[UPD_RL_HITEMS]; };
+
+// The front logic of one head position (what lane 0 of k_update does per position): flags, and the trip end when everything
+// ahead of it has ended in this pass (Vehicle::end_trip, traffi.cpp:886-927).
+struct HeadState { int k, evc, trips; double cumdep; bool touched; };
+UX_DEV void upd_head_position(const DevWorld &W, HeadState &H, int l, int t, int j, int vid, int kind, int nx, double xn) {
+    unsigned char f = 0;
+    if (kind == 3) { W.v_next[vid] = nx; f = VF_CAND; }
+    else if (kind == 1 || kind == 2) {
+        f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
+        if (kind == 2) W.v_next[vid] = -1;
+        if (H.k == j) {
+            if (!H.touched) { H.evc = W.ev_cnt[l]; H.trips = W.trips[l]; H.cumdep = W.cum_dep[TLI(W, t, l)]; H.touched = true; }
+            H.trips += 1; H.cumdep += W.dn;
+            double atl = W.v_atl[vid];
+            int es = (int)(atl / W.dt);
+            if (es < 0) es = 0;
+            if (es >= W.T) es = W.T - 1;
+            H.evc += 1;
+            W.ev_ord[TLI(W, es, l)] = H.evc;
+            W.ev_tt[TLI(W, es, l)] = ((double)t + 1.0) * W.dt - atl;
+            W.v_atl[vid] = (double)t * W.dt;
+            W.v_dist[vid] = W.v_dist[vid] + (xn - W.v_entry_x[vid]);
+            W.v_link[vid] = -1;
+            if (kind == 2) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+            else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)W.v_depart_ts[vid] * W.dt; }
+            if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 1; }
+            f = 0;
+            H.k++;
+        }
+    }
+    W.v_flags[vid] = f;
+}
+
+// The decision of one head position (the parallel phase of k_update's link head): where it gets to, and whether that is
+// the link end -- then trip end (1), abort at a dead end (2) or a next-link draw (3).
+UX_DEV int upd_head_decide(const DevWorld &W, int t, int vid, double x, double udt, double len, int end_node, bool dead_end, double *xn_out, int *nx_out) {
+    double xn = x + udt;  // positions < lanes have no leader
+    if (xn < x) xn = x;
+    bool over = xn > len;
+    double mr_ = xn - len;
+    if (over) xn = len;
+    int kind = 0, nx = -1;
+    if (fabs(xn - len) < 1e-9) {
+        if (end_node == W.v_dest[vid]) kind = 1;
+        else if (dead_end) kind = 2;  // traffi.cpp:864-871 (trip_abort is always 1 in this engine)
+        else { kind = 3; nx = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u); }
+    }
+    if (over) W.v_mr[vid] = mr_;
+    *xn_out = xn; *nx_out = nx;
+    return kind;
+}
+
+__global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld *worlds, int step_off, int R) {
+    int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    int r = (int)blockIdx.y * 32 + lane, l = (int)blockIdx.x * UPD_RL_WARPS + warp;
+    // blockIdx.z > 0: helper blocks for long queues -- they take every gridDim.z-th pass of the car-following list and leave
+    // at once (before staging anything) when none of their eight links has that much queued
+    const int part = (int)blockIdx.z, nparts = (int)gridDim.z;
+#ifdef UX_EMU
+    if (r >= R || part > 0) return;
+    static DevWorld W_sh; W_sh = worlds[r]; const DevWorld &W = W_sh;
+    if (l >= W.L) return;
+    const bool active = true;
+#else
+    if (part > 0) {
+        int n_q = 0;
+        const DevWorld *Wg = worlds + (r < R ? r : 0);
+        int L_ = Wg->L;
+        if (r < R && l < L_) { int cur_ = (*Wg->t_base + step_off) & 1; n_q = Wg->tail[l] - (Wg->head[cur_ * L_ + l] + Wg->pop_k2[l]); }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) n_q += __shfl_xor_sync(0xffffffffu, n_q, d);
+        if (!__syncthreads_or(n_q > part * 128)) return;
+    }
+    extern __shared__ unsigned long long upd_rl_smem[];
+    unsigned long long (*sw)[UPD_RL_STRIDE] = reinterpret_cast<unsigned long long (*)[UPD_RL_STRIDE]>(upd_rl_smem);
+    {
+        const int nw = (int)(sizeof(DevWorld) / 8);
+        int nrep = R - (int)blockIdx.y * 32; if (nrep > 32) nrep = 32;
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(worlds + (size_t)blockIdx.y * 32);
+        for (int q = (int)threadIdx.x; q < nrep * nw; q += 32 * UPD_RL_WARPS) sw[q / nw][q % nw] = src[q];
+    }
+    __syncthreads();
+    const bool active = r < R;
+    const DevWorld &W = *reinterpret_cast<const DevWorld *>(&sw[active ? lane : 0][0]);
+    if (l >= W.L) return;  // warp-uniform
+#endif
+    int L = W.L, t = *W.t_base + step_off, cur = t & 1;
+    size_t C = (size_t)W.C;
+    int cap = W.l_rcap[l], lanes = W.l_lanes[l];
+    long long o = W.l_roff[l];
+    double len = W.l_length[l], udt = W.l_udt[l], dpl = W.l_dpl_dn[l];
+    int end_node = W.l_end[l];
+    bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
+    int hd = 0, n = 0, hc = 0;
+    if (active) {
+        int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], tl = W.tail[l];
+        hd = hd0 + pk2; n = tl - hd;
+        if (part == 0) { hc = n < lanes ? n : lanes; if (hc > UX_MAXLANE) hc = UX_MAXLANE; }
+        if (part == 0 && pk2 > 0) {  // lane relabel when the end node (smaller id) emptied the link before this step's pushes
+            int fl = W.l_flags[l];
+            if ((fl & LF_END_LT_START) && !(fl & LF_SEES_POPS)) {
+                int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+                if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
+            }
+        }
+        if (part == 0 && n > 0) W.stat_count[l] += n;
+    }
+    HeadState H = {0, 0, 0, 0.0, false};
+#ifdef UX_EMU
+    const double *Xc = W.X + (size_t)cur * C + o;
+    for (int j = 0; j < hc; j++) {
+        int vid = W.VID[o + ring_slot(hd, j, cap)], nx; double xn;
+        int kind = upd_head_decide(W, t, vid, Xc[ring_slot(hd, j, cap)], udt, len, end_node, dead_end, &xn, &nx);
+        upd_head_position(W, H, l, t, j, vid, kind, nx, xn);
+    }
+#else
+    // ---- link head.  The head positions of the link in all 32 replicas form one item list (prefix sum of min(lanes, n));
+    //      decisions are taken one lane per item -- the route draws of different replicas run side by side -- then every lane
+    //      walks the items of its own replica in order for the "is it the front" logic.
+    __shared__ int pre_all[UPD_RL_WARPS][33], hd_all[UPD_RL_WARPS][32], hpre_all[UPD_RL_WARPS][33];
+    __shared__ HeadItems hi_all[UPD_RL_WARPS];
+    int *pre = pre_all[warp], *hdv = hd_all[warp], *hpre = hpre_all[warp];
+    HeadItems &HI = hi_all[warp];
+    int incl = n, hincl = hc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d), hv = __shfl_up_sync(0xffffffffu, hincl, d);
+        if (lane >= d) { incl += v; hincl += hv; }
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31), htotal = __shfl_sync(0xffffffffu, hincl, 31);
+    pre[lane] = incl - n; hpre[lane] = hincl - hc; hdv[lane] = hd;
+    if (lane == 31) { pre[32] = total; hpre[32] = htotal; }
+    __syncwarp();
+    for (int hbase = 0; hbase < htotal; hbase += UPD_RL_HITEMS) {
+        int hend = hbase + UPD_RL_HITEMS < htotal ? hbase + UPD_RL_HITEMS : htotal;
+        for (int i = hbase + lane; i < hend; i += 32) {
+            int lo = 0;
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) if (hpre[lo + st] <= i) lo += st;
+            const DevWorld &Ws = *reinterpret_cast<const DevWorld *>(&sw[lo][0]);
+            int slot = ring_slot(hdv[lo], i - hpre[lo], cap);
+            int vid = Ws.VID[o + slot], nx; double xn;
+            int kind = upd_head_decide(Ws, t, vid, Ws.X[(size_t)cur * C + o + slot], udt, len, end_node, dead_end, &xn, &nx);
+            HI.vid[i - hbase] = vid; HI.next[i - hbase] = nx; HI.xn[i - hbase] = xn; HI.kind[i - hbase] = (unsigned char)kind;
+        }
+        __syncwarp();
+        if (active) {
+            int i0 = hpre[lane] > hbase ? hpre[lane] : hbase, i1 = hpre[lane] + hc < hend ? hpre[lane] + hc : hend;
+            for (int i = i0; i < i1; i++) upd_head_position(W, H, l, t, i - hpre[lane], HI.vid[i - hbase], HI.kind[i - hbase], HI.next[i - hbase], HI.xn[i - hbase]);
+        }
+        __syncwarp();
+    }
+#endif
+    if (active && part == 0) {
+        if (H.touched) { W.ev_cnt[l] = H.evc; W.trips[l] = H.trips; W.cum_dep[TLI(W, t, l)] = H.cumdep; }
+        W.head[(cur ^ 1) * L + l] = hd + H.k;
+        int rem = n - H.k;
+        W.hcount[l] = rem < lanes ? rem : lanes;
+        if (W.log_mode) {  // positions that may have a just-ended leader, now that the ended count is known
+            int nlog = n < 2 * lanes ? n : 2 * lanes;
+            for (int pos = 0; pos < nlog; pos++) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, H.k, 0);
+        }
+#ifdef UX_EMU
+        for (int pos = 0; pos < n; pos++) upd_newell(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, Xc);
+#endif
+    }
+#ifndef UX_EMU
+    // ---- car following: the queue positions of the link in all 32 replicas form one list of work items (prefix sum of the
+    //      queue lengths over the lanes); every lane takes four items per pass and issues their loads before the first store,
+    //      so a pass costs one memory round trip for 128 platoons whatever replica they belong to
+    __syncwarp();  // the log records above read V before this step's move
+    for (int base = part * 128; base < total; base += nparts * 128) {
+        int rr[4], ps[4], pp[4];
+        double xx[4], gg[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int i = base + q * 32 + lane;
+            rr[q] = -1;
+            if (i < total) {
+                int lo = 0;  // largest replica lane with pre[lo] <= i (empty queues share their successor's offset and lose)
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) if (pre[lo + st] <= i) lo += st;
+                int pos = i - pre[lo], hs = hdv[lo];
+                const DevWorld &Ws = *reinterpret_cast<const DevWorld *>(&sw[lo][0]);
+                const double *Xs = Ws.X + (size_t)cur * C + o;
+                int p = ring_slot(hs, pos, cap);
+                rr[q] = lo; ps[q] = pos; pp[q] = p;
+                xx[q] = Xs[p];
+                gg[q] = pos >= lanes ? Xs[ring_slot(hs, pos - lanes, cap)] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (rr[q] < 0) continue;
+            const DevWorld &Ws = *reinterpret_cast<const DevWorld *>(&sw[rr[q]][0]);
+            int pos = ps[q];
+            if (Ws.log_mode && pos >= 2 * lanes) log_run_record(Ws, l, t, cur, hdv[rr[q]], pre[rr[q] + 1] - pre[rr[q]], pos, cap, o, lanes, len, udt, dpl, 0, 0);
+            double x = xx[q], xn = x + udt;
+            if (pos >= lanes) {
+                double gap = gg[q] - dpl;
+                if (gap < x) gap = x;
+                if (xn > gap) xn = gap;
+            }
+            if (xn < x) xn = x;
+            if (xn > len) xn = len;
+            Ws.X[(size_t)(cur ^ 1) * C + o + pp[q]] = xn;
+            Ws.V[o + pp[q]] = (xn - x) / Ws.dt;
+        }
+    }
+#endif
+}

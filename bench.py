@@ -32,6 +32,7 @@ WORKLOADS = {
     "siouxfalls": ("sioux_falls", dict(deltan=5, tmax=7200), "Sioux Falls: 24 nodes, 76 links, 6938 platoons, 1440 steps"),
     "grid100": ("grid_random_od", dict(n=100, n_platoons=1_000_000, deltan=5, tmax=7200), "100x100 grid, signals at every node, random OD: 10000 nodes, 39600 links, 1M platoons = 5M veh, 1440 steps"),
 }
+GRID100_CPU_SAMPLE_T = 300.0  # simulated seconds of C4 the CPU legs run (one route search + 60 steps: ~30 s on one core)
 ALG_BYTES = {  # algorithmic bytes (SURVEY.md 8d / DESIGN.md)
     "per_platoon_update": 32, "per_link_step": 40, "per_node_step": 20, "per_transfer": 160,
 }
@@ -106,6 +107,44 @@ def time_reference(workload, seeds, threads):
     return upd, secs, kind
 
 
+_GUARDED_CHILD = r"""
+import json, os, resource, sys, time
+sys.path.insert(0, sys.argv[1])
+workload, seed, until_t, lib, mem_gb = sys.argv[2], int(sys.argv[3]), float(sys.argv[4]), sys.argv[5], int(sys.argv[6])
+resource.setrlimit(resource.RLIMIT_AS, (mem_gb << 30, mem_gb << 30))  # fail with bad_alloc instead of meeting the OOM killer
+import bench
+from uxsim_b200 import _capi as C
+api = C.CApi(os.path.join(sys.argv[1], "oracle", "_ref", "libuxsim_ref.so"), "uxr_") if lib == "reference" else C.CApi(os.path.join(sys.argv[1], "oracle", "liboracle.so"), "uxo_")
+sc = bench.make_scenario(workload, seed)
+E = sc.engine_from_tables(api, sc.tables(), vehicle_logging_timestep_interval=-1, threads=-1 if lib == "reference" else 1)
+t0 = time.perf_counter()
+E.main_loop(until_t=until_t)
+print(json.dumps({"updates": E.get_int(C.I_PLATOON_UPDATES), "seconds": time.perf_counter() - t0}))
+"""
+
+
+def time_cpu_guarded(workload, seed, until_t):
+    """CPU leg for scenarios that may not fit the host (C4): a child process with an address-space limit runs the first
+    `until_t` simulated seconds on the reference C++ engine; if that fails (it does on C4: the engine keeps a route-preference
+    vector over all links per vehicle, ~320 GB for 1M platoons x 39 600 links -> std::bad_alloc) the oracle port runs the same
+    sample on one core.  Returns (updates, seconds, kind, note)."""
+    try:
+        mem_gb = max(8, min(48, int(os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") * 0.6) >> 30))
+    except (ValueError, OSError):
+        mem_gb = 32
+    note = ""
+    for lib in ("reference", "port"):
+        if lib == "reference" and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libuxsim_ref.so")):
+            continue
+        r = subprocess.run([sys.executable, "-c", _GUARDED_CHILD, ROOT, workload, str(seed), str(until_t), lib, str(mem_gb)], capture_output=True, text=True)
+        if r.returncode == 0 and r.stdout.strip():
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            return d["updates"], d["seconds"], lib, note
+        err = (r.stderr.strip().splitlines() or ["killed"])[-1][:120]
+        note += f"{lib} engine failed under a {mem_gb} GB address-space limit ({err}); "
+    raise RuntimeError("no CPU engine could run the sample: " + note)
+
+
 def _ref_worker(job):
     workload, seeds = job
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -130,6 +169,21 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     threads = -1 if cores > 1 else 1
+    if args.workload == "grid100":  # bounded sample in a guarded child (see time_cpu_guarded)
+        ms, upd_total, t_total, kind, note = [], 0, 0.0, "port", ""
+        for i in range(args.warmup + args.steps):
+            u, s_, kind, note = time_cpu_guarded(args.workload, 1000 + i, GRID100_CPU_SAMPLE_T)
+            if i >= args.warmup:
+                ms.append(s_ * 1e3); upd_total += u; t_total += s_
+        value = upd_total / t_total
+        ncores = cores if kind == "reference" else 1
+        sample = f"{note}first {GRID100_CPU_SAMPLE_T:.0f} s of simulated time (route search at t=0 + {int(GRID100_CPU_SAMPLE_T / 5)} steps) per step, " + ("reference C++ engine" if kind == "reference" else "oracle port (plain C, 1 thread)")
+        print(json.dumps({"impl": "reference", "metric": "platoon_updates_per_sec", "value": value, "unit": "platoon-updates/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][2], "sample": sample},
+                          "cpu_baseline": {"value": value, "unit": "platoon-updates/s", "cores": ncores, "kind": kind, "sample": sample},
+                          "e2e": {"value": value, "unit": "platoon-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
     # Two arrangements of the same engine on the same cores; the line reports the faster one:
     #  "omp"      one scenario at a time, OpenMP threads inside it (what cpp=True does for a single run)
     #  "ensemble" `cores` single-thread scenarios side by side (what a CPU user would do for a seed ensemble)
@@ -358,7 +412,12 @@ def main():
             E1.close()
         single = {"scenario_wall_ms": float(np.median(lat)), "platoon_updates": u1, "updates_per_sec": u1 / (np.median(lat) / 1e3)}
         # CPU baseline on this box's host cores: bounded sample of the same workload
-        if world == 1:
+        if world == 1 and args.workload == "grid100":
+            u_cpu, t_cpu, kind, note = time_cpu_guarded(args.workload, 2000, GRID100_CPU_SAMPLE_T)
+            cpu_baseline = {"value": u_cpu / t_cpu, "unit": "platoon-updates/s", "cores": (os.cpu_count() or 1) if kind == "reference" else 1, "kind": kind,
+                            "sample": f"{note}first {GRID100_CPU_SAMPLE_T:.0f} s of simulated time (route search at t=0 + {int(GRID100_CPU_SAMPLE_T / 5)} steps), {t_cpu:.1f} s, "
+                                      + ("reference C++ engine" if kind == "reference" else "oracle port (plain C, 1 thread)")}
+        elif world == 1:
             cores = os.cpu_count() or 1
             t_cpu, u_cpu, n_seed, kind = 0.0, 0, 0, "reference"
             while t_cpu < args.cpu_seconds / 2 and n_seed < 64:  # one scenario at a time, OpenMP inside it

@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds, doub
 #endif
 }
 
+// SMEM_DIST: graphs small enough for the label row to sit in shared memory next to the queue (8N more bytes) keep it there --
+// same near-far order, shared-memory atomics instead of L2 round trips -- and copy it out at the end.
+template <bool SMEM_DIST>
 __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld *worlds) {
 #ifndef UX_EMU
     LOAD_WORLD(W, worlds)
@@ -247,17 +250,19 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
     int N = W.N, k = W.row_dest[row];
     int tid = (int)threadIdx.x, nth = (int)blockDim.x, cap = N + 2 * nth;
     extern __shared__ unsigned long long sssp_smem[];
-    unsigned short *Q = reinterpret_cast<unsigned short *>(sssp_smem);
+    unsigned long long *du_s = sssp_smem;  // [N] when SMEM_DIST
+    unsigned short *Q = reinterpret_cast<unsigned short *>(sssp_smem + (SMEM_DIST ? N : 0));
     unsigned int *inq = reinterpret_cast<unsigned int *>(Q + ((cap + 3) & ~3));
     __shared__ int q_tail;
     __shared__ unsigned int lo_min[2];  // per round parity: lower bound of the queued labels (upper 32 bits)
-    unsigned long long *du = reinterpret_cast<unsigned long long *>(W.rdist + (size_t)row * N);
+    unsigned long long *du_g = reinterpret_cast<unsigned long long *>(W.rdist + (size_t)row * N);
+#define WAVE_LD(i) (SMEM_DIST ? du_s[i] : __ldcg(du_g + (i)))
     int *gnext = W.rnext + (size_t)row * N;
     const double *cin = W.cost_in;
     const int *ein_off = W.ein_off, *ein_from = W.ein_from;
     const unsigned long long INF_BITS = 0x7ff0000000000000ull;
     double delta = *W.sssp_delta;
-    for (int i = tid; i < N; i += nth) __stcg(du + i, i == k ? 0ull : INF_BITS);
+    for (int i = tid; i < N; i += nth) { if (SMEM_DIST) du_s[i] = i == k ? 0ull : INF_BITS; else __stcg(du_g + i, i == k ? 0ull : INF_BITS); }
     for (int i = tid; i < (N + 31) / 32; i += nth) inq[i] = 0u;
     if (tid == 0) { Q[0] = (unsigned short)k; q_tail = 1; inq[k >> 5] = 1u << (k & 31); lo_min[0] = 0u; lo_min[1] = 0xffffffffu; }
     __syncthreads();
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
             unsigned long long dj = 0ull;
             bool near = false, far = false;
             if (idx < tail) {
-                j = Q[idx % cap]; dj = __ldcg(du + j);
+                j = Q[idx % cap]; dj = WAVE_LD(j);
                 near = (unsigned int)(dj >> 32) < tau_hi;
                 far = !near;
                 if (near) atomicAnd(&inq[j >> 5], ~(1u << (j & 31)));
@@ -304,11 +309,11 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
                         nd[u] = in ? (unsigned long long)__double_as_longlong(__ldg(cin + q + u) + djd) : INF_BITS;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) cu[u] = ii[u] >= 0 ? __ldcg(du + ii[u]) : 0ull;
+                    for (int u = 0; u < 4; u++) cu[u] = ii[u] >= 0 ? WAVE_LD(ii[u]) : 0ull;
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         if (ii[u] >= 0 && nd[u] < cu[u]) {
-                            atomicMin(du + ii[u], nd[u]);
+                            atomicMin((SMEM_DIST ? du_s : du_g) + ii[u], nd[u]);
                             unsigned int hn = (unsigned int)(nd[u] >> 32), bit = 1u << (ii[u] & 31);
                             if (hn < mymin) mymin = hn;
                             if (!(atomicOr(&inq[ii[u] >> 5], bit) & bit)) Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)ii[u];
@@ -328,13 +333,15 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
     const double *cout_ = W.cost_out;
     for (int i = tid; i < N; i += nth) {
         int nx = -1;
-        if (i == k) nx = k;
+        if (i == k) { nx = k; if (SMEM_DIST) du_g[i] = 0ull; }
         else {
-            double di = __longlong_as_double((long long)__ldcg(du + i));
+            unsigned long long dib = WAVE_LD(i);
+            double di = __longlong_as_double((long long)dib);
+            if (SMEM_DIST) du_g[i] = dib;
             if (!is_inf(di)) {
                 for (int q = __ldg(W.eout_off + i); q < __ldg(W.eout_off + i + 1); q++) {
                     int j = __ldg(W.eout_to + q);
-                    if (__ldg(cout_ + q) + __longlong_as_double((long long)__ldcg(du + j)) == di) { nx = j; any = 1; break; }
+                    if (__ldg(cout_ + q) + __longlong_as_double((long long)WAVE_LD(j)) == di) { nx = j; any = 1; break; }
                 }
             }
         }
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
     }
     any = __syncthreads_or(any);
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
+#undef WAVE_LD
 #endif
 }
 

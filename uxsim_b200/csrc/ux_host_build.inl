@@ -543,11 +543,14 @@ static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of
     const int mode = [] { const char *e = getenv("UXSIM_B200_SSSP"); return !e ? 0 : !strcmp(e, "sweep") ? 1 : !strcmp(e, "frontier") ? 2 : !strcmp(e, "wave") ? 3 : 0; }();
     const int wave_pad = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_PAD"); return e ? atoi(e) : -1; }();
     bool large = N >= 2048 && N < 65536;
-    if ((mode == 3 || (mode == 0 && large)) && N < 65536) {
+    // mid-size graphs (Chicago sketch: 546 nodes) already gain from the worklist order when the labels stay in shared memory
+    // (817 -> 698 us per update at 32 replicas); below ~256 nodes a handful of whole-edge sweeps is cheaper
+    bool mid = N >= 256 && N < 2048 && (long long)w->n_active * w->R >= 4096;  // a single scenario is one wave of blocks: the sweeps' shorter chain wins (56 vs 135 us)
+    if ((mode == 3 || (mode == 0 && (large || mid))) && N < 65536) {
         // shared memory per block = queue + bitmap, padded so that the dist rows of the resident blocks stay within ~96 MB of L2
         size_t wbytes = (size_t)((N + 2 * SSSP_WAVE_THREADS + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 16;
         if (N <= 2048) {  // small graph (forced by UXSIM_B200_SSSP=wave): labels in shared memory too, narrow blocks
-            static const int small_threads = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_THREADS"); return e ? atoi(e) : 64; }();
+            static const int small_threads = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_THREADS"); return e ? std::max(64, atoi(e)) : 64; }();  // LOAD_WORLD needs >= 64
             k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds, 2.0);
             k_sssp_wave<true><<<dim3(w->n_active, w->R), dim3(small_threads), wbytes + (size_t)N * 8, st>>>(w->dworlds);
             return 2;

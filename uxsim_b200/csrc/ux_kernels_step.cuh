@@ -545,7 +545,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     WARP_FOR(lane) if (lane == 0) {
         // flush trip-end-waiting fronts (traffi.cpp:432-441)
         for (int ii = 0; ii < nin; ii++) {
-            int lanes = S.hc[ii];  // hcount = min(lanes, queue length): positions beyond it cannot be waiting
+            int lanes = S.hc[ii];  // hcount = head positions up to the last flagged one: positions beyond it cannot be waiting
             for (int r = 0; r < lanes; r++) {
                 if (S.popped[ii] >= S.hc[ii]) break;
                 int fp = S.pos_off[ii] + S.popped[ii];
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                 if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
             }
             W.stat_count[l] += n;
-            int k = 0, evc = 0, trips = 0;
+            int k = 0, evc = 0, trips = 0, last_f = -1;
             double cumdep = 0.0;
             bool touched = false;
             for (int j = 0; j < hc; j++) {
@@ -751,11 +751,13 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                     }
                 }
                 W.v_flags[vid] = f;
+                if (f) last_f = j;
             }
             if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[TLI(W, t, l)] = cumdep; }
             W.head[(cur ^ 1) * L + l] = hd + k;
-            int rem = n - k;
-            W.hcount[l] = rem < lanes ? rem : lanes;
+            // head positions the next transfer has to look at: up to the last one that is a candidate or waits for its trip
+            // end (everything behind it is mid-link), counted from the new head -- 0 for most links in most steps
+            W.hcount[l] = last_f >= 0 ? last_f - k + 1 : 0;
             H.k_ended = k;
         }
 
@@ -822,7 +824,7 @@ struct HeadItems { int vid[UPD_RL_HITEMS], next[UPD_RL_HITEMS]; double xn[UPD_RL
 
 // The front logic of one head position (what lane 0 of k_update does per position): flags, and the trip end when everything
 // ahead of it has ended in this pass (Vehicle::end_trip, traffi.cpp:886-927).
-struct HeadState { int k, evc, trips; double cumdep; bool touched; };
+struct HeadState { int k, evc, trips, last_f; double cumdep; bool touched; };
 UX_DEV void upd_head_position(const DevWorld &W, HeadState &H, int l, int t, int j, int vid, int kind, int nx, double xn) {
     unsigned char f = 0;
     if (kind == 3) { W.v_next[vid] = nx; f = VF_CAND; }
@@ -850,6 +852,7 @@ UX_DEV void upd_head_position(const DevWorld &W, HeadState &H, int l, int t, int
         }
     }
     W.v_flags[vid] = f;
+    if (f) H.last_f = j;
 }
 
 // The decision of one head position (the parallel phase of k_update's link head): where it gets to, and whether that is
@@ -926,7 +929,7 @@ __global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld 
         }
         if (part == 0 && n > 0) W.stat_count[l] += n;
     }
-    HeadState H = {0, 0, 0, 0.0, false};
+    HeadState H = {0, 0, 0, -1, 0.0, false};
 #ifdef UX_EMU
     const double *Xc = W.X + (size_t)cur * C + o;
     for (int j = 0; j < hc; j++) {
@@ -975,8 +978,7 @@ __global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld 
     if (active && part == 0) {
         if (H.touched) { W.ev_cnt[l] = H.evc; W.trips[l] = H.trips; W.cum_dep[TLI(W, t, l)] = H.cumdep; }
         W.head[(cur ^ 1) * L + l] = hd + H.k;
-        int rem = n - H.k;
-        W.hcount[l] = rem < lanes ? rem : lanes;
+        W.hcount[l] = H.last_f >= 0 ? H.last_f - H.k + 1 : 0;  // as in k_update
         if (W.log_mode) {  // positions that may have a just-ended leader, now that the ended count is known
             int nlog = n < 2 * lanes ? n : 2 * lanes;
             for (int pos = 0; pos < nlog; pos++) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, H.k, 0);

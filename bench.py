@@ -371,6 +371,10 @@ def main():
             "k_update": ALG_BYTES["per_platoon_update"] * upd,
             "k_node": (ALG_BYTES["per_link_step"] * L + ALG_BYTES["per_node_step"] * N) * T * R + ALG_BYTES["per_transfer"] * events,
         }
+        D = E.get_int(C.I_NUM_ACTIVE_DESTS)
+        n_route = kl.get("k_sssp", 0)  # route updates in the run; SURVEY 8(d): 12*D*N bytes of dist/next out, 16*D*L for the DUO rows
+        alg["k_sssp"] = 12 * D * N * R * n_route
+        alg["k_duo"] = 16 * D * L * R * kl.get("k_duo", 0)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -551,7 +551,8 @@ static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of
         size_t wbytes = (size_t)((N + 2 * SSSP_WAVE_THREADS + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 16;
         if (N <= 2048) {  // small graph (forced by UXSIM_B200_SSSP=wave): labels in shared memory too, narrow blocks
             static const int small_threads = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_THREADS"); return e ? std::max(64, atoi(e)) : 64; }();  // LOAD_WORLD needs >= 64
-            k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds, 2.0);
+            static const double factor_s = [] { const char *e = getenv("UXSIM_B200_SSSP_DELTA"); return e ? atof(e) : 2.0; }();
+            k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds, factor_s);
             k_sssp_wave<true><<<dim3(w->n_active, w->R), dim3(small_threads), wbytes + (size_t)N * 8, st>>>(w->dworlds);
             return 2;
         }

@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="chicago", choices=sorted(WORKLOADS))
-    ap.add_argument("--replicas", type=int, default=64, help="seeded replicas per GPU per step")
+    ap.add_argument("--replicas", type=int, default=128, help="seeded replicas per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     args = ap.parse_args()

@@ -78,11 +78,12 @@ static inline void __threadfence() {}
     do {                                                                              \
         dim3 g_ = (grid), b_ = (block);                                               \
         gridDim = g_; blockDim = b_;                                                  \
+        for (unsigned bz_ = 0; bz_ < g_.z; bz_++)                                     \
         for (unsigned by_ = 0; by_ < g_.y; by_++)                                     \
             for (unsigned bx_ = 0; bx_ < g_.x; bx_++)                                 \
                 for (unsigned ty_ = 0; ty_ < b_.y; ty_++)                             \
                     for (unsigned tx_ = 0; tx_ < b_.x; tx_++) {                       \
-                        blockIdx = dim3(bx_, by_, 0); threadIdx = dim3(tx_, ty_, 0);  \
+                        blockIdx = dim3(bx_, by_, bz_); threadIdx = dim3(tx_, ty_, 0); \
                         kernel(__VA_ARGS__);                                          \
                     }                                                                 \
     } while (0)

@@ -353,14 +353,14 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
 #endif
 }
 
+// grid = (link tiles, destination rows, replicas): no index arithmetic beyond one add, coalesced rows of `pref`
 __global__ void __launch_bounds__(256) k_duo(const DevWorld *worlds, int gradual_step) {
-    LOAD_WORLD(W, worlds)
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)W.D * W.L;
-    if (idx >= total) return;
-    int r = (int)(idx / W.L), l = (int)(idx % W.L);
+    const DevWorld &W = worlds[blockIdx.z];  // a handful of block-uniform field loads; nothing here aliases them
+    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x), r = (int)blockIdx.y, L = W.L;
+    if (l >= L || r >= W.D) return;
     double wt = gradual_step ? W.duo_w * (W.dt / W.duo_time) : W.duo_w;
     if (!W.pref_active[r]) wt = 1.0;
+    size_t idx = (size_t)r * (size_t)L + (size_t)l;
     double p = W.pref[idx];
     if (W.rnext[(size_t)r * W.N + W.l_start[l]] == W.l_end[l]) p = (1.0 - wt) * p + wt;
     else p = (1.0 - wt) * p;

@@ -132,3 +132,41 @@ def test_analyzer_edie_and_od_through_the_world_api(cuda_api):
     od = A.od_analysis()
     assert od["total_trips"].sum() == A.trip_all and od["completed_trips"].sum() == A.trip_completed
     assert np.isclose((od["completed_trips"] * np.where(od["completed_trips"] > 0, od["average_travel_time"], 0)).sum(), A.total_travel_time)
+
+
+def test_lazy_vehicle_registry_over_emulated_kernels(emu_api, monkeypatch):
+    """Host logic of the wrapper on the CPU (kernels emulated, test infrastructure only): ``adddemand`` records batches, no
+    proxy object exists until somebody asks for a platoon, and the name -> vehicle mappings behave like the reference's
+    OrderedDicts (creation order, renamed vehicles, LIVING / RUNNING subsets)."""
+    import uxsim_b200.world as wmod
+    from uxsim_b200 import World
+
+    monkeypatch.setattr(wmod.C, "load_product", lambda: emu_api)
+    W = World(name="", deltan=5, tmax=1200, print_mode=0, random_seed=0, cuda=True)
+    W.addNode("orig1", 0, 0); W.addNode("orig2", 0, 2); W.addNode("merge", 1, 1); W.addNode("dest", 2, 1)
+    W.addLink("link1", "orig1", "merge", length=1000, free_flow_speed=20, merge_priority=0.5)
+    W.addLink("link2", "orig2", "merge", length=1000, free_flow_speed=20, merge_priority=2)
+    W.addLink("link3", "merge", "dest", length=1000, free_flow_speed=20)
+    W.adddemand("orig1", "dest", 0, 1000, 0.4); W.adddemand("orig2", "dest", 500, 1000, 0.6)
+    special = W.addVehicle("orig1", "dest", 30, name="special")
+    n = len(W.VEHICLES)
+    assert n == 80 + 60 + 1 and len(W._veh_by_index._made) == 1  # only the vehicle handed back by addVehicle exists
+    assert list(W.VEHICLES)[:3] == ["0", "1", "2"] and list(W.VEHICLES)[-1] == "special"
+    assert "special" in W.VEHICLES and str(n - 1) not in W.VEHICLES and "17" in W.VEHICLES and "0017" not in W.VEHICLES
+    assert W.VEHICLES["special"] is special and special.id == n - 1
+    with pytest.raises(ValueError):
+        W.addVehicle("orig1", "dest", 40, name="17")
+    n = len(W.VEHICLES)  # the rejected vehicle keeps its default name, as in the reference (it is created before the check)
+    v17 = W.VEHICLES["17"]
+    assert v17.orig.name == "orig1" and v17.dest.name == "dest" and W.VEHICLES["100"].orig.name == "orig2"
+    v17.user_attribute = {"tag": 1}
+    assert W.VEHICLES["17"] is v17 and W._veh_by_index[17] is v17 and len(W._veh_by_index._made) <= 4
+    W.exec_simulation(until_t=300)
+    running = W.VEHICLES_RUNNING
+    assert 0 < len(running) < len(W.VEHICLES_LIVING) <= n
+    assert all(v.state == "run" for v in running.values()) and all(name in W.VEHICLES for name in running)
+    W.exec_simulation()
+    assert len(W.VEHICLES_RUNNING) == int((W._veh("state") == C.VS_RUN).sum()) < len(running)
+    tt = np.array([v.travel_time for v in W.VEHICLES.values()], dtype=float)
+    assert len(tt) == n and (tt[tt >= 0] >= 100).all()
+    assert [v.name for v in W._veh_by_index][:2] == ["0", "1"] and W._veh_by_index.names()[-2] == "special"

@@ -187,7 +187,7 @@ class _CudaSolverBase:
             s.iteration_seconds.append((t1 - t0, t3 - t2))
             s.swap_device_ms.append(E.get_double(C.D_DTA_SWAP_MS))
             prev_rs = (res["rs_link_ids"], res["rs_offsets"])
-            veh_names = [v.name for v in W._veh_by_index]
+            veh_names = W._veh_by_index.names()
             t_gap_per_vehicle = res["total_t_gap"] / len(W.VEHICLES)
             if print_progress:
                 gap = "time gap" if s._mode == 0 else "marginal time gap"

@@ -26,8 +26,10 @@ import math
 import string
 import time
 import warnings
+import bisect
 from collections import OrderedDict, deque
 from collections import defaultdict as ddict
+from collections.abc import Mapping, Sequence
 
 import numpy as np
 
@@ -476,6 +478,113 @@ class CudaRouteChoice:
         return self.W._E.get_array(C.A_ROUTE_PREF).reshape(len(self.W.NODES), len(self.W.LINKS))
 
 
+class _VehicleRegistry(Sequence):
+    """All platoons of a world in creation order, WITHOUT a Python object per platoon (building 10^5-10^6 proxies
+    is the wall-clock floor of the wrapper, uxsim_cpp_wrapper.py:1204-1251).  ``adddemand`` records one batch (first id, count,
+    origin, destination, attribute, colours); a :class:`CudaVehicle` proxy is made the first time somebody asks for that
+    platoon and kept from then on, so attributes a caller sets on it persist.  Indexing = platoon id."""
+
+    def __init__(self, W):
+        self.W, self.n = W, 0
+        self._first, self._batch = [], []       # batch k covers ids [_first[k], _first[k] + count)
+        self._made = {}                         # id -> CudaVehicle
+        self._name, self._id_of_name = {}, {}   # only platoons whose name is not str(id)
+
+    def add_batch(self, count, orig, dest, attribute, colors):
+        if count > 0:
+            self._first.append(self.n)
+            self._batch.append((count, orig, dest, attribute, colors))
+            self.n += count
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(self.n))]
+        i = int(i)
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        v = self._made.get(i)
+        if v is None:
+            k = bisect.bisect_right(self._first, i) - 1
+            _, orig, dest, attribute, colors = self._batch[k]
+            c = colors[i - self._first[k]]
+            v = CudaVehicle.__new__(CudaVehicle)
+            v.W, v.id, v.name = self.W, i, self.name_of(i)
+            v.orig, v.dest = orig, dest
+            v.color = (float(c[0]), float(c[1]), float(c[2]))
+            v.attribute, v.user_attribute, v.user_function = attribute, None, None
+            v.mode, v.dest_list, v.node_event, v.route_pref = "single_trip", [], {}, {}
+            v.links_prefer, v.links_avoid, v.specified_route, v.route_choice_principle, v.link_old = [], [], None, self.W.route_choice_principle, None
+            self._made[i] = v
+        return v
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+    def name_of(self, i):
+        return self._name.get(i) or str(i)
+
+    def names(self):
+        return [self._name.get(i) or str(i) for i in range(self.n)]
+
+    def id_of(self, name):
+        """Platoon id of a name, or -1."""
+        i = self._id_of_name.get(name)
+        if i is not None:
+            return i
+        if isinstance(name, str) and name.isdigit() and str(int(name)) == name and int(name) < self.n and int(name) not in self._name:
+            return int(name)
+        return -1
+
+    def rename(self, i, name):
+        self._name[i] = name
+        self._id_of_name[name] = i
+        if i in self._made:
+            self._made[i].name = name
+
+
+class _VehicleDict(Mapping):
+    """``W.VEHICLES`` / ``VEHICLES_LIVING`` / ``VEHICLES_RUNNING``: name -> vehicle in creation order over a
+    :class:`_VehicleRegistry` (all platoons, or the given ids), read-only like the reference's use of them after set-up."""
+
+    def __init__(self, reg, ids=None):
+        self._reg, self._ids = reg, ids
+        self._idset = None
+
+    def __len__(self):
+        return len(self._reg) if self._ids is None else len(self._ids)
+
+    def __iter__(self):
+        r = self._reg
+        return (r.name_of(int(i)) for i in (range(len(r)) if self._ids is None else self._ids))
+
+    def __contains__(self, name):
+        i = self._reg.id_of(name)
+        if i < 0:
+            return False
+        if self._ids is None:
+            return True
+        if self._idset is None:
+            self._idset = set(int(k) for k in self._ids)
+        return i in self._idset
+
+    def __getitem__(self, name):
+        if name not in self:
+            raise KeyError(name)
+        return self._reg[self._reg.id_of(name)]
+
+    def values(self):
+        r = self._reg
+        return [r[int(i)] for i in (range(len(r)) if self._ids is None else self._ids)]
+
+    def items(self):
+        return [(v.name, v) for v in self.values()]
+
+
 class CudaWorld:
     """uxsim_cpp_wrapper.py:800-1533 (CppWorld), in front of libuxsim_b200.so."""
 
@@ -492,7 +601,8 @@ class CudaWorld:
         self.DUO_UPDATE_TIME, self.DUO_UPDATE_WEIGHT, self.DUO_NOISE, self.EULAR_DT = duo_update_time, duo_update_weight, duo_noise, eular_dt
         self.DELTAT = self.REACTION_TIME * self.DELTAN
         self.DELTAT_ROUTE = max(1, int(self.DUO_UPDATE_TIME / self.DELTAT))
-        self.VEHICLES, self.VEHICLES_LIVING, self.VEHICLES_RUNNING = OrderedDict(), OrderedDict(), OrderedDict()
+        self._veh_by_index = _VehicleRegistry(self)
+        self.VEHICLES, self.VEHICLES_LIVING, self.VEHICLES_RUNNING = _VehicleDict(self._veh_by_index), _VehicleDict(self._veh_by_index), _VehicleDict(self._veh_by_index, [])
         self.NODES, self.LINKS, self.NODES_NAME_DICT, self.LINKS_NAME_DICT = [], [], {}, {}
         self.vehicle_logging_timestep_interval = vehicle_logging_timestep_interval
         self.route_choice_principle = route_choice_principle
@@ -522,7 +632,6 @@ class CudaWorld:
         if all_destinations:  # keep route preferences for every node (needed to add demand to NEW destinations mid-run)
             self._E.set_option(C.OPT_ALL_DESTINATIONS, 1)
         self._cache = {}
-        self._veh_by_index = []
         self._simulation_done = False
         self.T, self.TIME = 0, 0
 
@@ -601,20 +710,7 @@ class CudaWorld:
                         eular_dx=eular_dx, attribute=attribute, user_attribute=user_attribute, user_function=user_function, auto_rename=auto_rename)
 
     def _register(self, n_new, orig, dest, attribute=None):
-        colors = self.rng.random(size=(n_new, 3))
-        rcp = self.route_choice_principle
-        for j in range(n_new):
-            v = CudaVehicle.__new__(CudaVehicle)
-            v.W, v.id = self, len(self._veh_by_index)
-            v.name = str(v.id)
-            v.orig, v.dest = orig, dest
-            v.color = (float(colors[j, 0]), float(colors[j, 1]), float(colors[j, 2]))
-            v.attribute, v.user_attribute, v.user_function = attribute, None, None
-            v.mode, v.dest_list, v.node_event, v.route_pref = "single_trip", [], {}, {}
-            v.links_prefer, v.links_avoid, v.specified_route, v.route_choice_principle, v.link_old = [], [], None, rcp, None
-            self.VEHICLES[v.name] = v
-            self.VEHICLES_LIVING[v.name] = v
-            self._veh_by_index.append(v)
+        self._veh_by_index.add_batch(n_new, orig, dest, attribute, self.rng.random(size=(n_new, 3)))
 
     def addVehicle(self, orig, dest, departure_time, name=None, route_pref=None, route_choice_principle=None, mode="single_trip",
                    links_prefer=[], links_avoid=[], trip_abort=1, departure_time_is_time_step=0, attribute=None, user_attribute=None,
@@ -632,10 +728,7 @@ class CudaWorld:
                 if not auto_rename:
                     raise ValueError(f"Vehicle name {name} already used by another vehicle. Please specify a unique name.")
                 name = name + "_renamed" + "".join(self.rng.choice(list(string.ascii_letters + string.digits), size=8))
-            self.VEHICLES.pop(v.name), self.VEHICLES_LIVING.pop(v.name)
-            v.name = name
-            self.VEHICLES[name] = v
-            self.VEHICLES_LIVING[name] = v
+            self._veh_by_index.rename(v.id, name)
         if links_prefer:
             v.links_prefer = [self.get_link(l) for l in links_prefer]
             self._E.set_vehicle_links(v.id, 1, [l.id for l in v.links_prefer])
@@ -763,8 +856,8 @@ class CudaWorld:
 
     def _sync_registries(self):
         st = self._veh("state")
-        self.VEHICLES_LIVING = OrderedDict((v.name, v) for v, s in zip(self._veh_by_index, st) if s < C.VS_END)
-        self.VEHICLES_RUNNING = OrderedDict((v.name, v) for v, s in zip(self._veh_by_index, st) if s == C.VS_RUN)
+        self.VEHICLES_LIVING = _VehicleDict(self._veh_by_index, np.nonzero(st < C.VS_END)[0])
+        self.VEHICLES_RUNNING = _VehicleDict(self._veh_by_index, np.nonzero(st == C.VS_RUN)[0])
 
     def simulation_terminated(self):
         self.print(" simulation finished")

@@ -549,21 +549,28 @@ static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of
     if ((mode == 3 || (mode == 0 && (large || mid))) && N < 65536) {
         // shared memory per block = queue + bitmap, padded so that the dist rows of the resident blocks stay within ~96 MB of L2
         size_t wbytes = (size_t)((N + 2 * SSSP_WAVE_THREADS + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 16;
-        if (N <= 2048) {  // small graph (forced by UXSIM_B200_SSSP=wave): labels in shared memory too, narrow blocks
-            static const int small_threads = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_THREADS"); return e ? std::max(64, atoi(e)) : 64; }();  // LOAD_WORLD needs >= 64
+        if (N <= 2048) {  // small / mid-size graph: labels in shared memory too; one destination per warp, four per block
             static const double factor_s = [] { const char *e = getenv("UXSIM_B200_SSSP_DELTA"); return e ? atof(e) : 2.0; }();
+            static const int per_block = [] { const char *e = getenv("UXSIM_B200_SSSP_WAVE_THREADS"); return e ? atoi(e) : 0; }();  // > 0: one destination per block of that many threads
             k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds, factor_s);
-            k_sssp_wave<true><<<dim3(w->n_active, w->R), dim3(small_threads), wbytes + (size_t)N * 8, st>>>(w->dworlds);
+            if (per_block >= 64) {
+                k_sssp_wave<true, false><<<dim3(w->n_active, w->R), dim3(per_block), wbytes + (size_t)N * 8, st>>>(w->dworlds, 0);
+            } else {
+                size_t ww = (((size_t)((N + 64 + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 15) / 8) + (size_t)N + 2;  // 8-byte words per warp
+                size_t bytes_w = ww * 8 * SSSP_WARPS_PER_BLOCK;
+                if (bytes_w > 48 * 1024) cudaFuncSetAttribute(k_sssp_wave<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_w);
+                k_sssp_wave<true, true><<<dim3((w->n_active + SSSP_WARPS_PER_BLOCK - 1) / SSSP_WARPS_PER_BLOCK, w->R), dim3(32 * SSSP_WARPS_PER_BLOCK), bytes_w, st>>>(w->dworlds, (int)ww);
+            }
             return 2;
         }
         size_t row_bytes = (size_t)N * 8, per_sm = std::max<size_t>(1, ((size_t)96 << 20) / 148 / std::max<size_t>(row_bytes, 1));
         size_t pad_to = wave_pad >= 0 ? (size_t)wave_pad : (per_sm >= 16 ? 0 : ((size_t)220 * 1024) / per_sm);
         if (pad_to > wbytes) wbytes = std::min<size_t>(pad_to, (size_t)220 * 1024);
         if (wbytes <= 220 * 1024) {
-            if (wbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
+            if (wbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp_wave<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
             static const double factor = [] { const char *e = getenv("UXSIM_B200_SSSP_DELTA"); return e ? atof(e) : 2.0; }();  // bucket width / mean edge cost
             k_cost_stats<<<dim3(1, w->R), dim3(256), 0, st>>>(w->dworlds, factor);
-            k_sssp_wave<false><<<dim3(w->n_active, w->R), dim3(SSSP_WAVE_THREADS), wbytes, st>>>(w->dworlds);
+            k_sssp_wave<false, false><<<dim3(w->n_active, w->R), dim3(SSSP_WAVE_THREADS), wbytes, st>>>(w->dworlds, 0);
             return 2;
         }
     }

@@ -241,20 +241,30 @@ __global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds, doub
 
 // SMEM_DIST: graphs small enough for the label row to sit in shared memory next to the queue (8N more bytes) keep it there --
 // same near-far order, shared-memory atomics instead of L2 round trips -- and copy it out at the end.
-template <bool SMEM_DIST>
-__global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld *worlds) {
+// WARP: one destination per WARP instead of per block (graphs whose wavefront rarely exceeds 32 nodes): every barrier becomes a
+// __syncwarp, no warp idles through the rounds of a narrow wavefront, and the block's warps share one staged DevWorld.
+#ifndef SSSP_WARPS_PER_BLOCK
+#define SSSP_WARPS_PER_BLOCK 4
+#endif
+template <bool SMEM_DIST, bool WARP>
+__global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld *worlds, int smem_words_per_warp) {
 #ifndef UX_EMU
     LOAD_WORLD(W, worlds)
-    int row = (int)blockIdx.x;
-    if (row >= W.D) return;
+    const int wib = WARP ? (int)(threadIdx.x >> 5) : 0;
+    int row = WARP ? (int)blockIdx.x * SSSP_WARPS_PER_BLOCK + wib : (int)blockIdx.x;
+    if (row >= W.D) return;  // WARP: whole warps leave; only warp-level synchronisation follows
     int N = W.N, k = W.row_dest[row];
-    int tid = (int)threadIdx.x, nth = (int)blockDim.x, cap = N + 2 * nth;
-    extern __shared__ unsigned long long sssp_smem[];
+    int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x, nth = WARP ? 32 : (int)blockDim.x, cap = N + 2 * nth;
+    extern __shared__ unsigned long long sssp_smem_all[];
+    unsigned long long *sssp_smem = sssp_smem_all + (WARP ? (size_t)wib * smem_words_per_warp : 0);
+#define WAVE_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
     unsigned long long *du_s = sssp_smem;  // [N] when SMEM_DIST
     unsigned short *Q = reinterpret_cast<unsigned short *>(sssp_smem + (SMEM_DIST ? N : 0));
     unsigned int *inq = reinterpret_cast<unsigned int *>(Q + ((cap + 3) & ~3));
-    __shared__ int q_tail;
-    __shared__ unsigned int lo_min[2];  // per round parity: lower bound of the queued labels (upper 32 bits)
+    __shared__ int q_tail_all[SSSP_WARPS_PER_BLOCK];
+    __shared__ unsigned int lo_min_all[SSSP_WARPS_PER_BLOCK][2];  // per round parity: lower bound of the queued labels (upper 32 bits)
+    int &q_tail = q_tail_all[wib];
+    unsigned int *lo_min = lo_min_all[wib];
     unsigned long long *du_g = reinterpret_cast<unsigned long long *>(W.rdist + (size_t)row * N);
 #define WAVE_LD(i) (SMEM_DIST ? du_s[i] : __ldcg(du_g + (i)))
     int *gnext = W.rnext + (size_t)row * N;
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
     for (int i = tid; i < N; i += nth) { if (SMEM_DIST) du_s[i] = i == k ? 0ull : INF_BITS; else __stcg(du_g + i, i == k ? 0ull : INF_BITS); }
     for (int i = tid; i < (N + 31) / 32; i += nth) inq[i] = 0u;
     if (tid == 0) { Q[0] = (unsigned short)k; q_tail = 1; inq[k >> 5] = 1u << (k & 31); lo_min[0] = 0u; lo_min[1] = 0xffffffffu; }
-    __syncthreads();
+    WAVE_SYNC();
     int head = 0;  // monotone counters; slot = counter % cap
     unsigned int tau_hi = 0u;
     for (int r = 0;; r++) {
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
             }
             // every queued bit of this chunk is cleared before anyone can re-queue, and everybody has read q_tail / lo_min[p]
             // before the first append of the round
-            __syncthreads();
+            WAVE_SYNC();
             if (base == head && tid == 0) lo_min[p] = 0xffffffffu;  // round r+1 collects into it
             if (far) {  // stays queued (its bit is still set): goes round once more
                 unsigned int hj = (unsigned int)(dj >> 32);
@@ -321,12 +331,12 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
                     }
                 }
             }
-            if (base + nth < tail) __syncthreads();  // the next chunk's pops (label read + bit clear) must not overlap these relaxations
+            if (base + nth < tail) WAVE_SYNC();  // the next chunk's pops (label read + bit clear) must not overlap these relaxations
         }
         unsigned int wm = __reduce_min_sync(0xffffffffu, mymin);
         if ((tid & 31) == 0 && wm != 0xffffffffu) atomicMin(&lo_min[p ^ 1], wm);
         head = tail;
-        __syncthreads();  // this round's red.min / queue appends are visible before the next round reads them
+        WAVE_SYNC();  // this round's red.min / queue appends are visible before the next round reads them
     }
     // next hop: smallest end node j of an out-edge with c_ij + dist[j] == dist[i] (out-edges are stored ends ascending)
     int any = 0;
@@ -347,9 +357,10 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
         }
         gnext[i] = nx;
     }
-    any = __syncthreads_or(any);
+    any = WARP ? __any_sync(0xffffffffu, any) : __syncthreads_or(any);
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
 #undef WAVE_LD
+#undef WAVE_SYNC
 #endif
 }
 

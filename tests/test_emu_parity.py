@@ -62,6 +62,15 @@ def test_emulated_replica_lane_update(name, mk, emu_api, oracle_api, monkeypatch
     assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
 
 
+@pytest.mark.parametrize("name,mk", [("grid6_signals", lambda: S.grid(n=6, seed=5, tmax=3000, demand_t=1200, signals=True)), ("dta_grid9", lambda: S.dta_grid9(seed=1)),
+                                     ("lane_drop", S.lane_drop_2to1)], ids=["grid6_signals", "dta_grid9", "lane_drop"])
+def test_emulated_link_pre_kernel(name, mk, emu_api, oracle_api, monkeypatch):
+    """k_link_pre (scalar link / node bookkeeping as its own launch; what large worlds run) forced on small scenarios."""
+    monkeypatch.setenv("UXSIM_B200_PRE_SPLIT", "1")
+    Ee, Eo = run_pair(mk(), emu_api, oracle_api, vehicle_logging_timestep_interval=1)
+    assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
+
+
 def test_all_replica_getter_matches_per_replica(emu_api):
     """get_array(replica=-1): [R, n] in one transfer == the per-replica getters."""
     from uxsim_b200 import _capi as C

@@ -143,6 +143,16 @@ def test_c4_full_size_route_search_and_conservation(cuda_api, monkeypatch):
     assert np.array_equal((arr[:, -1] - dep[:, -1]) / 5.0, nveh)  # platoons on a link = entered - left
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("name", ["grid6_signals", "dta_grid9", "chicago_dn30"])
+def test_scalar_bookkeeping_kernel_split_bit_exact(name, split, cuda_api, oracle_api, monkeypatch):
+    """The per-link / per-node scalar step (tokens, curve carries, signals) either runs inside k_node (small worlds) or as its
+    own thread-per-link kernel k_link_pre (large worlds): forced both ways, results are bit-identical to the oracle."""
+    monkeypatch.setenv("UXSIM_B200_PRE_SPLIT", split)
+    Eg, Eo = run_pair(dict(STOCHASTIC)[name](), cuda_api, oracle_api)
+    assert compare_engines(Eg, Eo) == []
+
+
 def test_run_to_run_determinism(cuda_api):
     sc = S.sioux_falls(seed=5)
     Ea = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1)

@@ -35,7 +35,7 @@ I_NUM_NODES, I_NUM_LINKS, I_NUM_VEHICLES, I_TIMESTEP, I_TOTAL_TIMESTEPS, I_NUM_R
 I_ROUTE_UPDATE_STEPS, I_PLATOON_UPDATES, I_TRIPS_COMPLETED, I_LOG_ENTRIES, I_KERNEL_LAUNCHES = 7, 8, 9, 10, 11
 I_NUM_ACTIVE_DESTS, I_TRANSFER_LEVELS, I_LINK_EVENTS = 12, 13, 14
 I_H2D_BYTES, I_D2H_BYTES, I_RING_SLOTS, I_MAX_DEPART_TS, I_KERNEL_LAUNCHES_OF = 15, 16, 17, 18, 100
-K_NAMES = ("k_pre(unused)", "k_node", "k_update", "k_edge_cost", "k_sssp", "k_duo", "misc")
+K_NAMES = ("k_link_pre", "k_node", "k_update", "k_edge_cost", "k_sssp", "k_duo", "misc")
 OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS, OPT_RECORD_TRAVERSALS = 1, 2, 3
 D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT, D_LAST_LOOP_MS, D_KERNEL_MS_OF = 1, 2, 3, 4, 5, 6, 100
 D_UPLOAD_MS, D_GRAPH_BUILD_MS, D_LAST_LOOP_WALL_MS = 7, 8, 9

@@ -21,6 +21,7 @@ struct DevWorld {
     int nseg;
     double dn, dt, duo_w, duo_time, noise;
     int itt, route_ts, hard_det, gradual, no_cyclic, log_mode;
+    int pre_split;  // the scalar link / node bookkeeping of a step runs in k_link_pre (large worlds) instead of inside k_node
     long long seed;
     // static network (shared by all replicas)
     const int *l_start, *l_end, *l_lanes, *l_rcap, *l_flags, *l_sg_off, *l_sg, *l_pair_first, *l_pair_off, *l_pair_list;

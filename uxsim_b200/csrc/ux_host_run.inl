@@ -13,6 +13,7 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
     const char *upd_env = getenv("UXSIM_B200_UPDATE");
     bool update_rl = upd_env ? !strcmp(upd_env, "rl") : (R >= 64 && (long long)w->vehs.size() <= 32ll * (long long)w->links.size());
     for (int s = 0; s < nsteps; s++) {
+        if (w->pre_split) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre, dim3(((unsigned)w->links.size() + (unsigned)N + 255) / 256, R), dim3(256), st, w->dworlds, s); KT_END(UX_K_PRE) lc++; }
         if (N > 0) {
             KT_BEGIN(UX_K_TRANSFER)
             if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);

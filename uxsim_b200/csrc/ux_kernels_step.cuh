@@ -5,6 +5,22 @@
 // K1: Link::update (traffi.cpp:542-565, 599-622) for the node's out-links, then Node::generate (105-189),
 //     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
 // ---------------------------------------------------------------------------------------------------
+// Node::signal_update (traffi.cpp:194-207) and Node::flow_capacity_update (226-234) of node n at step t
+UX_DEV void node_signal_capacity(const DevWorld &W, int n, int t) {
+    int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
+    int ph = W.sig_phase[n];
+    if (nsig > 1) {
+        double st = W.sig_t[n];
+        if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
+        st += W.dt;
+        W.sig_t[n] = st; W.sig_phase[n] = ph;
+    }
+    W.sig_log[TNI(W, t, n)] = ph;
+    double fc = W.n_fc[n];
+    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
+    else W.fc_rem[n] = 10e10;
+}
+
 template <int MC, int MD>
 struct PreSmem {
     int choice[MC], g_vid[MC], g_err[MC];
@@ -35,10 +51,17 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         }
         WARP_SYNC();
     }
-    // ---- scalar link update (Link::update traffi.cpp:542-565).  A link's inflow side (arrival curve, capacity_in
-    //      tokens, instantaneous travel time) belongs to its START node, its outflow side (departure curve, capacity_out
-    //      tokens, pops of this step) to its END node -- the same ownership the transfer uses, so that this node's whole
-    //      timestep (update, generate, signal, transfer) needs nothing from other nodes except the dependency wait.
+    if (W.pre_split) {
+        // the scalar link update -- curve carries, capacity tokens -- and the node's signal / capacity step ran before this
+        // kernel, one thread per link / node (k_link_pre): only the freshly measured travel times are left to store
+        if (fresh) {
+            WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) W.tt_inst[TLI(W, t, W.n_out[o0 + k])] = tt_s[k]; }
+            WARP_SYNC();
+        }
+    } else {
+    // ---- scalar link update (Link::update traffi.cpp:542-565), small worlds only (a separate launch would cost more than it
+    //      saves).  A link's inflow side (arrival curve, capacity_in tokens, instantaneous travel time) belongs to its START
+    //      node, its outflow side (departure curve, capacity_out tokens, pops of this step) to its END node.
     WARP_FOR(ln) {
         for (int k = ln; k < nout; k += 32) {
             int l = W.n_out[o0 + k];
@@ -59,6 +82,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         }
     }
     WARP_SYNC();
+    }
     // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
     //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
     int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
@@ -163,20 +187,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; } }
     WARP_FOR(ln) if (ln == 0) {
         W.gen_avail[n] = av;
-        // ---- signal (Node::signal_update traffi.cpp:194-207)
-        int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
-        int ph = W.sig_phase[n];
-        if (nsig > 1) {
-            double st = W.sig_t[n];
-            if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
-            st += W.dt;
-            W.sig_t[n] = st; W.sig_phase[n] = ph;
-        }
-        W.sig_log[TNI(W, t, n)] = ph;
-        // ---- node flow capacity (Node::flow_capacity_update traffi.cpp:226-234)
-        double fc = W.n_fc[n];
-        if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
-        else W.fc_rem[n] = 10e10;
+        if (!W.pre_split) node_signal_capacity(W, n, t);
     }
     WARP_SYNC();
 }
@@ -568,6 +579,31 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             W.cap_in_rem[ol] = S.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = S.o_cumarr[q]; W.tail[ol] = S.o_tail[q];
         }
     }
+}
+
+// K0: the per-link and per-node scalar bookkeeping of a timestep, one THREAD per link / node and replica (coalesced rows):
+// Link::update (traffi.cpp:542-565: capacity tokens, carry of the cumulative curves and of the instantaneous travel time to
+// row t), reset of the per-step pop count, Node::signal_update (194-207) and Node::flow_capacity_update (226-234).  Nothing here
+// depends on the order of links or nodes, and everything k_node reads of it is final before k_node starts -- inside k_node the
+// same updates cost a warp per node with 4-9 of 32 lanes busy and a quarter of that kernel's stall samples.
+__global__ void __launch_bounds__(256) k_link_pre(const DevWorld *worlds, int step_off) {
+    const DevWorld &W = worlds[blockIdx.y];  // block-uniform field loads
+    int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), t = *W.t_base + step_off, L = W.L;
+    if (i < L) {
+        int l = i;
+        if (t > 0) {
+            size_t row = TLI(W, t, l), prev = TLI(W, t - 1, l);
+            W.tt_inst[row] = W.tt_inst[prev];  // k_node overwrites it on the steps that measure the mean speed
+            W.cum_arr[row] = W.cum_arr[prev];
+            W.cum_dep[row] = W.cum_dep[prev];
+        }
+        double thr = W.dn * W.l_lanes[l];
+        double ci = W.l_cap_in[l];
+        if (ci < 10e9) { if (W.cap_in_rem[l] < thr) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+        double co = W.l_cap_out[l];
+        if (co < 10e9) { if (W.cap_out_rem[l] < thr) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
+        W.pop_k2[l] = 0;
+    } else if (i < L + W.N) node_signal_capacity(W, i - L, t);
 }
 
 // k_node: one warp runs a node's whole timestep -- Link::update of the sides it owns, Node::generate, signal, node

@@ -529,6 +529,15 @@ static int upload(ux_world *w) {
     w->dworlds = dalloc<DevWorld>(w, w->R, false);
     if (!w->dworlds) return fail(w, UX_ERR_CUDA, "device allocation failed");
     CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice, w->stream));
+    {
+        std::vector<unsigned long long> tab((size_t)4 * w->R);
+        for (int r = 0; r < w->R; r++) {
+            tab[r] = (unsigned long long)(uintptr_t)w->hw[r].t_base; tab[(size_t)w->R + r] = (unsigned long long)(uintptr_t)w->hw[r].tail;
+            tab[(size_t)2 * w->R + r] = (unsigned long long)(uintptr_t)w->hw[r].head; tab[(size_t)3 * w->R + r] = (unsigned long long)(uintptr_t)w->hw[r].pop_k2;
+        }
+        w->d_rl_tab = dupload(w, tab);
+        if (!w->d_rl_tab) return fail(w, UX_ERR_CUDA, "device allocation failed");
+    }
     CUDA_OK(cudaStreamSynchronize(w->stream));
     w->uploaded = true;
     w->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

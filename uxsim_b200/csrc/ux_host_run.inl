@@ -28,11 +28,11 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
                 static const int rl_parts = [] { const char *e = getenv("UXSIM_B200_RL_PARTS"); return e ? atoi(e) : 4; }();
                 dim3 g_rl(((int)w->links.size() + UPD_RL_WARPS - 1) / UPD_RL_WARPS, (R + 31) / 32, w->p.vehicle_log_mode ? 1 : std::max(1, rl_parts));
 #ifdef UX_EMU
-                UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R);
+                UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R, (int)w->links.size(), (const unsigned long long *)w->d_rl_tab);
 #else
                 const size_t rl_bytes = 32 * UPD_RL_STRIDE * 8;  // the replicas' DevWorld structs
                 if (s == 0) cudaFuncSetAttribute(k_update_rl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_bytes);  // per device
-                k_update_rl<<<g_rl, dim3(32 * UPD_RL_WARPS), rl_bytes, st>>>(w->dworlds, s, R);
+                k_update_rl<<<g_rl, dim3(32 * UPD_RL_WARPS), rl_bytes, st>>>(w->dworlds, s, R, (int)w->links.size(), (const unsigned long long *)w->d_rl_tab);
 #endif
             }
             else UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s);

@@ -38,6 +38,7 @@ struct ux_world {
     std::vector<Slab> slabs;     // state memory (returned to the slab cache)
     std::vector<DevWorld> hw;  // host copies of the per-replica device worlds
     DevWorld *dworlds = nullptr;
+    unsigned long long *d_rl_tab = nullptr;  // [4][R] pointers (t_base, tail, head, pop_k2) for k_update_rl's helper blocks
     int n_levels = 1, n_active = 0;
     long long launches = 0, C = 0; int nseg = 0, n_edges = 0;
     std::vector<int> dest_row, row_dest;

@@ -40,6 +40,7 @@ struct DevWorld {
     int n_edges;
     // dynamic (per replica)
     int *head, *tail, *tail_k1, *pop_k2, *hcount, *trips, *ev_cnt;
+    int *node_act;  // per node: (step + 1) of the last link update that left a candidate / trip-end waiter at the head of an in-link
     long long *stat_count;
     double *cap_out_rem, *cap_in_rem;
     double *X, *V;

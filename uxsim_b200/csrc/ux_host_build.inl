@@ -481,7 +481,7 @@ static int upload(ux_world *w) {
     for (int r = 0; r < w->R; r++) {
         DevWorld &d = w->hw[r];
         d.seed = w->p.random_seed + r;
-        d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L);
+        d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L); d.node_act = dalloc<int>(w, N + 1);
         d.trips = dalloc<int>(w, L); d.ev_cnt = dalloc<int>(w, L); d.stat_count = dalloc<long long>(w, L);
         d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem);
         reg_copy(d.cap_out_rem, h_co); reg_copy(d.cap_in_rem, h_ci);

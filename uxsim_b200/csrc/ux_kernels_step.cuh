@@ -184,7 +184,8 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         }
         WARP_SYNC();
     }
-    WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; } }
+    // tail after generation (the link update tells transfer pushes from generated ones): k_link_pre already copied the unchanged tails
+    if (!W.pre_split || natt > 0) WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; } }
     WARP_FOR(ln) if (ln == 0) {
         W.gen_avail[n] = av;
         if (!W.pre_split) node_signal_capacity(W, n, t);
@@ -260,6 +261,7 @@ template <int MC, int MD>
 UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
     int cur = t & 1, L = W.L;
     size_t C = (size_t)W.C;
+    if (W.node_act[n] != t) return;  // no in-link of this node has a flagged head position (hcount == 0 everywhere): nothing to do
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     if (nin == 0) return;
     int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = W.sig_phase[n];
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(256) k_link_pre(const DevWorld *worlds, int st
         double co = W.l_cap_out[l];
         if (co < 10e9) { if (W.cap_out_rem[l] < thr) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
         W.pop_k2[l] = 0;
+        W.tail_k1[l] = W.tail[l];  // k_node rewrites it for the out-links of nodes that generate
     } else if (i < L + W.N) node_signal_capacity(W, i - L, t);
 }
 
@@ -794,6 +797,7 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
             // head positions the next transfer has to look at: up to the last one that is a candidate or waits for its trip
             // end (everything behind it is mid-link), counted from the new head -- 0 for most links in most steps
             W.hcount[l] = last_f >= 0 ? last_f - k + 1 : 0;
+            if (last_f >= 0) W.node_act[end_node] = t + 1;  // the end node has something to transfer next step (same value from every in-link)
             H.k_ended = k;
         }
 
@@ -1021,6 +1025,7 @@ __global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld 
         if (H.touched) { W.ev_cnt[l] = H.evc; W.trips[l] = H.trips; W.cum_dep[TLI(W, t, l)] = H.cumdep; }
         W.head[(cur ^ 1) * L + l] = hd + H.k;
         W.hcount[l] = H.last_f >= 0 ? H.last_f - H.k + 1 : 0;  // as in k_update
+        if (H.last_f >= 0) W.node_act[end_node] = t + 1;
         if (W.log_mode) {  // positions that may have a just-ended leader, now that the ended count is known
             int nlog = n < 2 * lanes ? n : 2 * lanes;
             for (int pos = 0; pos < nlog; pos++) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, H.k, 0);

@@ -397,12 +397,19 @@ class EngineWorld:
     def get_double(self, what: int) -> float:
         return float(self.api.get_double(self.h, int(what)))
 
-    def get_array_all(self, what: int) -> np.ndarray:
-        """A per-replica state array of EVERY replica, shape ``[R, n]``, in one device->host transfer (CUDA engine)."""
+    def get_array_all(self, what: int, out: np.ndarray = None) -> np.ndarray:
+        """A per-replica state array of EVERY replica, shape ``[R, n]``, in one device->host transfer (CUDA engine).
+        ``out``: a caller-owned C-contiguous buffer of that shape and dtype to receive it -- a page-locked one (e.g.
+        ``torch.empty(..., pin_memory=True).numpy()``), reused from run to run, turns the copy into a plain DMA; a fresh
+        ``np.empty`` costs a page fault per 4 KB on top of the pageable copy (75 MB: 15 ms against 3)."""
         dt = C.c_int(0)
         n = self._check(self.api.array_size(self.h, int(what), C.byref(dt)))
         R = self.get_int(I_NUM_REPLICAS)
-        out = np.empty((R, int(n)), dtype=_NP_DTYPE[dt.value])
+        if out is not None:
+            if out.shape != (R, int(n)) or out.dtype != _NP_DTYPE[dt.value] or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a C-contiguous {(R, int(n))} array of {_NP_DTYPE[dt.value]}")
+        else:
+            out = np.empty((R, int(n)), dtype=_NP_DTYPE[dt.value])
         if out.size:
             self._check(self.api.get_array(self.h, int(what), -1, out.ctypes.data_as(C.c_void_p), out.size))
         return out

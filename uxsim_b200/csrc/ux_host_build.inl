@@ -483,10 +483,14 @@ static int upload(ux_world *w) {
         d.seed = w->p.random_seed + r;
         d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L); d.node_act = dalloc<int>(w, N + 1);
         d.trips = dalloc<int>(w, L); d.ev_cnt = dalloc<int>(w, L); d.stat_count = dalloc<long long>(w, L);
-        d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem);
+        // initial values: staged from the host once (replica 0), cloned on the device for the other replicas
+        const DevWorld &d0 = w->hw[0];
+        if (r == 0) { d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem); }
+        else { d.cap_out_rem = dclone(w, d0.cap_out_rem, co_rem.size()); d.cap_in_rem = dclone(w, d0.cap_in_rem, ci_rem.size()); }
         reg_copy(d.cap_out_rem, h_co); reg_copy(d.cap_in_rem, h_ci);
         d.X = dalloc<double>(w, 2 * (size_t)C); d.V = dalloc<double>(w, C); d.VID = dalloc<int>(w, C); d.LANE = dalloc<int>(w, C);
-        d.sig_phase = dupload(w, sig_ph); d.sig_t = dupload(w, sig_t); d.fc_rem = dupload(w, fc_rem);
+        if (r == 0) { d.sig_phase = dupload(w, sig_ph); d.sig_t = dupload(w, sig_t); d.fc_rem = dupload(w, fc_rem); }
+        else { d.sig_phase = dclone(w, d0.sig_phase, sig_ph.size()); d.sig_t = dclone(w, d0.sig_t, sig_t.size()); d.fc_rem = dclone(w, d0.fc_rem, fc_rem.size()); }
         reg_copy(d.sig_phase, h_sp); reg_copy(d.sig_t, h_st); reg_copy(d.fc_rem, h_fc);
         d.gen_head = dalloc<int>(w, N); d.gen_avail = dalloc<int>(w, N);
         d.v_state = dalloc<int>(w, P); d.v_next = dalloc<int>(w, P); d.v_link = dalloc<int>(w, P, false); d.v_arr_ts = dalloc<int>(w, P, false); d.v_trav = dalloc<int>(w, P);
@@ -520,7 +524,7 @@ static int upload(ux_world *w) {
         d.cost_in = dalloc<double>(w, w->n_edges); d.cost_out = dalloc<double>(w, w->n_edges); d.sssp_delta = dalloc<double>(w, 1);
         d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
         reg_ff(d.rnext, sizeof(int) * (size_t)D * N);
-        d.err = w->d_err_all + 2 * r; d.t_base = dupload(w, tb); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
+        d.err = w->d_err_all + 2 * r; d.t_base = r == 0 ? dupload(w, tb) : dclone(w, w->hw[0].t_base, 1); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
         if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
             return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
     }

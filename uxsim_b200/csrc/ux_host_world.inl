@@ -190,6 +190,14 @@ static T *dupload(ux_world *w, const std::vector<T> &v) {
     return p;
 }
 
+// a replica's copy of an array that replica 0 already holds: device-to-device, nothing staged on the host
+template <typename T>
+static T *dclone(ux_world *w, const T *src, size_t n) {
+    T *p = dalloc<T>(w, n, false);
+    if (p && n) cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyDeviceToDevice, w->stream);
+    return p;
+}
+
 template <typename T>
 static T *dgrow(ux_world *w, T *old, size_t oldn, size_t newn, int fill_byte) {
     T *p = dalloc<T>(w, newn, false);

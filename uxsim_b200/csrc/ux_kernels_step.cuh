@@ -359,7 +359,9 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     if (has_deps) {
         WARP_FOR(lane) {
             for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
-                volatile int *done = W.node_done + W.dep_list[q];
+                int dep = W.dep_list[q];
+                if (W.node_act[dep] != t) continue;  // that node has nothing to transfer in this step: it pops nothing (and does not publish)
+                volatile int *done = W.node_done + dep;
 #ifdef UX_EMU
                 if (*done < t + 1) dev_error(W, DERR_RING_FULL, -1);
 #else
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
 #endif
     XferSmem<MC, MD> &S = sm_all[wib].xf;
     xfer_node(W, S, n, t, lvl > 0);
-    if (lvl_raw >> 16) {  // publish completion only where somebody is waiting: the fence is not free
+    if ((lvl_raw >> 16) && W.node_act[n] == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes): the fence is not free
         WARP_SYNC();
         WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)(W.node_done + n)) = t + 1; }
     }

@@ -734,8 +734,7 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                 int slot = ring_slot(hd, j, cap);
                 int vid = W.VID[o + slot];
                 double x = Xc[slot];
-                int dest_ = W.v_dest[vid];
-                double atl_ = W.v_atl[vid], ex_ = W.v_entry_x[vid], di_ = W.v_dist[vid]; int dts_ = W.v_depart_ts[vid];
+                double atl_ = 0.0, ex_ = 0.0, di_ = 0.0; int dts_ = 0;
                 double xn = x + udt;  // positions < lanes have no leader
                 if (xn < x) xn = x;
                 bool over = xn > len;
@@ -743,10 +742,11 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                 if (over) xn = len;
                 unsigned char kind = 0;
                 int nx = -1;
-                if (fabs(xn - len) < 1e-9) {
-                    if (end_node == dest_) kind = 1;
+                if (fabs(xn - len) < 1e-9) {  // only a platoon that reaches the link end needs its per-platoon fields (most do not)
+                    if (end_node == W.v_dest[vid]) kind = 1;
                     else if (dead_end) kind = 2;  // traffi.cpp:864-871 (trip_abort is always 1 in this engine)
                     else { kind = 3; nx = route_choice(W, vid, end_node, t, (unsigned)vid, UX_RNG_VEHROUTE, 0u); }
+                    if (kind != 3) { atl_ = W.v_atl[vid]; ex_ = W.v_entry_x[vid]; di_ = W.v_dist[vid]; dts_ = W.v_depart_ts[vid]; }
                 }
                 if (over) W.v_mr[vid] = mr_;
                 H.vid[j] = vid; H.kind[j] = kind; H.xn[j] = xn; H.next[j] = nx;

@@ -348,8 +348,8 @@ static int upload(ux_world *w) {
         while (cap < need) cap <<= 1;  // power of two: slot = position & (cap - 1)
         if (cap > 0x20000000) return fail(w, UX_ERR_INVALID, "link %d: ring too large", i);
         l_rcap[i] = (int)cap; l_roff[i] = C; C += cap;
-        {   // work items of the update kernel: one warp per 512 ring slots, at least one per link
-            int nparts = (int)((cap + 511) / 512);
+        {   // work items of the update kernel: one 16-lane group per 16*UPD_GROUP = 256 ring slots, at least one per link
+            int nparts = (int)((cap + 16 * UPD_GROUP - 1) / (16 * UPD_GROUP));
             for (int part = 0; part < nparts; part++) { seg_link.push_back(i); seg_start.push_back(part | (nparts << 16)); }
         }
         sg_off[i + 1] = sg_off[i] + (int)l.sg.size();

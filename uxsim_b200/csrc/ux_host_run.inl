@@ -5,7 +5,7 @@
 static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
     int N = (int)w->nodes.size(), R = w->R;
     cudaStream_t st = w->stream;
-    dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_WARPS - 1) / UPD_WARPS, R);
+    dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_GROUPS_PER_BLOCK - 1) / UPD_GROUPS_PER_BLOCK, R);
     long long lc = 0;
     // Large ensembles of lightly loaded networks run the link update with one thread per (link, replica) (k_update_rl: 4x fewer
     // warp instructions; B200, Chicago sketch: 102 -> 77 us at 64 replicas, 198 -> 116 us at 128); below 64 replicas, or with

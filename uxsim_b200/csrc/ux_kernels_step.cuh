@@ -699,11 +699,28 @@ struct HeadSmem {
 
 // 4 warps per block and <= 48 registers (10 blocks per SM): the kernel is a swarm of tiny, latency-bound warps -- measured
 // best among {8x4, 8x5, 4x10, 4x12} blocks-per-SM variants at 32 replicas.
+// A work item gets UPD_GROUP lanes.  With -DUPD_GROUP=16 a warp carries two (link, part) items side by side (a link head has 1-13
+// positions and most queues a handful of platoons); the halves never exchange anything and every synchronisation is a
+// __syncwarp over the half's own lane mask.  Measured on the B200 (first cut, 512-slot parts): C4 68.7 -> 57.7 us and Chicago
+// x32 56.7 -> 54.3 us, but long queues lose (Chicago dn=5 x16 47.6 -> 53.0, Sioux Falls x64 15.1 -> 18.1), so the default stays 32.
+#ifndef UPD_GROUP
+#define UPD_GROUP 32
+#endif
+#define UPD_GROUPS_PER_BLOCK (UPD_WARPS * 32 / UPD_GROUP)
+#ifdef UX_EMU
+#define UPD_BEGIN if (threadIdx.x & (UPD_GROUP - 1)) return;
+#define UPD_FOR(lane) for (int lane = 0; lane < UPD_GROUP; lane++)
+#define UPD_SYNC()
+#else
+#define UPD_BEGIN const unsigned upd_mask_ = UPD_GROUP == 32 ? 0xffffffffu : ((0xffffffffu >> (32 - UPD_GROUP)) << ((threadIdx.x & 31u) & ~(unsigned)(UPD_GROUP - 1)));
+#define UPD_FOR(lane) for (int lane = (int)(threadIdx.x & (UPD_GROUP - 1)), once_ = 1; once_; once_ = 0)
+#define UPD_SYNC() __syncwarp(upd_mask_)
+#endif
 __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
-    WARP_BEGIN
-    __shared__ HeadSmem hs_all[UPD_WARPS];
-    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    UPD_BEGIN
+    __shared__ HeadSmem hs_all[UPD_GROUPS_PER_BLOCK];
+    int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) / UPD_GROUP);
     if (gw >= W.nseg) return;
     // work item = (link, part): the warp sweeps the 32-position windows part, part+nparts, ... of the link's queue, so the
     // work is proportional to the platoons present, and long queues are shared by several warps
@@ -718,19 +735,19 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
     int hd = hd0 + pk2, n = tl - hd;
     int s0 = part;
     if (n == 0) {  // empty link: nothing moves, nothing is counted; only the double-buffered head is carried over
-        if (s0 == 0 && (threadIdx.x & 31) == 0) { W.head[(cur ^ 1) * L + l] = hd; W.hcount[l] = 0; }
+        if (s0 == 0 && (threadIdx.x & (UPD_GROUP - 1)) == 0) { W.head[(cur ^ 1) * L + l] = hd; W.hcount[l] = 0; }
         return;
     }
     const double *Xc = W.X + (size_t)cur * C + o;
     if (s0 == 0) {
         // ---- link head
-        HeadSmem &H = hs_all[(threadIdx.x >> 5) % UPD_WARPS];
+        HeadSmem &H = hs_all[(threadIdx.x / UPD_GROUP) % UPD_GROUPS_PER_BLOCK];
         int hc = n < lanes ? n : lanes;
         if (hc > UX_MAXLANE) hc = UX_MAXLANE;
         int end_node = W.l_end[l];
         bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
-        WARP_FOR(lane) {
-            for (int j = lane; j < hc; j += 32) {
+        UPD_FOR(lane) {
+            for (int j = lane; j < hc; j += UPD_GROUP) {
                 int slot = ring_slot(hd, j, cap);
                 int vid = W.VID[o + slot];
                 double x = Xc[slot];
@@ -753,8 +770,8 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                 H.atl[j] = atl_; H.ex[j] = ex_; H.dist[j] = di_; H.dts[j] = dts_;
             }
         }
-        WARP_SYNC();
-        WARP_FOR(lane) if (lane == 0) {
+        UPD_SYNC();
+        UPD_FOR(lane) if (lane == 0) {
             // lane relabel when the end node (smaller id) emptied the link before this step's pushes
             if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
                 int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
@@ -804,14 +821,14 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
         }
 
         if (W.log_mode) {  // positions that may have a just-ended leader are logged here, once the ended count is known
-            WARP_SYNC();
+            UPD_SYNC();
             int nlog = n < 2 * lanes ? n : 2 * lanes, k_ended = H.k_ended;
-            WARP_FOR(lane) { for (int pos = lane; pos < nlog; pos += 32) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, k_ended, 0); }
-            WARP_SYNC();
+            UPD_FOR(lane) { for (int pos = lane; pos < nlog; pos += UPD_GROUP) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, k_ended, 0); }
+            UPD_SYNC();
         }
     }
-    WARP_FOR(lane) {
-        for (int pos = part * 32 + lane; pos < n; pos += nparts * 32) {
+    UPD_FOR(lane) {
+        for (int pos = part * UPD_GROUP + lane; pos < n; pos += nparts * UPD_GROUP) {
             int p = ring_slot(hd, pos, cap);
             if (W.log_mode && pos >= 2 * lanes) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, 0, 0);
             double x = Xc[p];

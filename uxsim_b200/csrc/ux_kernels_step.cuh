@@ -701,8 +701,9 @@ struct HeadSmem {
 // best among {8x4, 8x5, 4x10, 4x12} blocks-per-SM variants at 32 replicas.
 // A work item gets UPD_GROUP lanes.  With -DUPD_GROUP=16 a warp carries two (link, part) items side by side (a link head has 1-13
 // positions and most queues a handful of platoons); the halves never exchange anything and every synchronisation is a
-// __syncwarp over the half's own lane mask.  Measured on the B200 (first cut, 512-slot parts): C4 68.7 -> 57.7 us and Chicago
-// x32 56.7 -> 54.3 us, but long queues lose (Chicago dn=5 x16 47.6 -> 53.0, Sioux Falls x64 15.1 -> 18.1), so the default stays 32.
+// __syncwarp over the half's own lane mask.  Measured on the B200 (parts of 16*UPD_GROUP ring slots): C4 69.2 -> 58.1 us and
+// Chicago x32 56.7 -> 54.7 us, but long queues and single scenarios lose (Chicago dn=5 x16 47.8 -> 54.5, x1 16.5 -> 22.9; Sioux
+// Falls x64 15.0 -> 18.3; Chicago x1 12.6 -> 16.0), so the default stays 32.
 #ifndef UPD_GROUP
 #define UPD_GROUP 32
 #endif

@@ -71,6 +71,14 @@ def test_emulated_link_pre_kernel(name, mk, emu_api, oracle_api, monkeypatch):
     assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
 
 
+@pytest.mark.parametrize("name,mk", LOG_CASES[1:4] + [("grid6_signals", LOG_CASES[-1][1])], ids=[c[0] for c in LOG_CASES[1:4]] + ["grid6_signals"])
+def test_emulated_update_lane_groups(name, mk, emu_api, oracle_api, monkeypatch):
+    """k_update with two work items per warp (16-lane groups; what large, lightly loaded worlds run) forced on small scenarios."""
+    monkeypatch.setenv("UXSIM_B200_UPDATE_GROUP", "16")
+    Ee, Eo = run_pair(mk(), emu_api, oracle_api, vehicle_logging_timestep_interval=1)
+    assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
+
+
 def test_all_replica_getter_matches_per_replica(emu_api):
     """get_array(replica=-1): [R, n] in one transfer == the per-replica getters."""
     from uxsim_b200 import _capi as C

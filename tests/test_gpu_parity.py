@@ -105,6 +105,17 @@ def test_replica_lane_update_kernel(name, R, force, cuda_api, oracle_api, monkey
         assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"
 
 
+@pytest.mark.parametrize("group", ["16", "32"])
+@pytest.mark.parametrize("name", ["3lane", "grid6_signals", "chicago_dn30"])
+def test_update_kernel_lane_groups_bit_exact(name, group, cuda_api, oracle_api, monkeypatch):
+    """k_update with one (link, part) work item per warp or two (16-lane groups; picked by itself for large, lightly loaded
+    worlds): forced both ways, logs on -- identical results."""
+    monkeypatch.setenv("UXSIM_B200_UPDATE_GROUP", group)
+    mk = S.multilane_3lane if name == "3lane" else dict(STOCHASTIC)[name]
+    Eg, Eo = run_pair(mk(), cuda_api, oracle_api, vehicle_logging_timestep_interval=1)
+    assert compare_engines(Eg, Eo) == [] and compare_logs(Eg, Eo) == []
+
+
 @pytest.mark.parametrize("mode", ["rl", "warp"])
 @pytest.mark.parametrize("name,mk", [("3lane", S.multilane_3lane), ("short_chain", S.short_links_chain), ("grid6_signals", dict(STOCHASTIC)["grid6_signals"]),
                                      ("chicago_dn30", dict(STOCHASTIC)["chicago_dn30"]), ("chicago_dn5", lambda: S.chicago_sketch(deltan=5, seed=0, tmax=2500))],

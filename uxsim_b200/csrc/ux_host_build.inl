@@ -337,6 +337,10 @@ static int upload(ux_world *w) {
     std::vector<double> l_length(L);
     long long C = 0;
     std::vector<int> seg_link, seg_start;
+    {   // two work items per warp in k_update where queues are short and there are enough items to fill the GPU either way
+        const char *e = getenv("UXSIM_B200_UPDATE_GROUP");
+        w->upd_group = e ? (atoi(e) == 16 ? 16 : 32) : ((P <= 32ll * L && (long long)L * w->R >= 20000) ? 16 : 32);
+    }
     bool any_toll = false;
     for (int i = 0; i < L; i++) {
         const HLink &l = w->links[i];
@@ -348,8 +352,8 @@ static int upload(ux_world *w) {
         while (cap < need) cap <<= 1;  // power of two: slot = position & (cap - 1)
         if (cap > 0x20000000) return fail(w, UX_ERR_INVALID, "link %d: ring too large", i);
         l_rcap[i] = (int)cap; l_roff[i] = C; C += cap;
-        {   // work items of the update kernel: one 16-lane group per 16*UPD_GROUP = 256 ring slots, at least one per link
-            int nparts = (int)((cap + 16 * UPD_GROUP - 1) / (16 * UPD_GROUP));
+        {   // work items of the update kernel: one lane group per 16 * (lanes of a group) ring slots, at least one per link
+            int nparts = (int)((cap + 16 * w->upd_group - 1) / (16 * w->upd_group));
             for (int part = 0; part < nparts; part++) { seg_link.push_back(i); seg_start.push_back(part | (nparts << 16)); }
         }
         sg_off[i + 1] = sg_off[i] + (int)l.sg.size();

@@ -5,7 +5,7 @@
 static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_count) {
     int N = (int)w->nodes.size(), R = w->R;
     cudaStream_t st = w->stream;
-    dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_GROUPS_PER_BLOCK - 1) / UPD_GROUPS_PER_BLOCK, R);
+    dim3 g_nodes(R, (N + XFER_WARPS - 1) / XFER_WARPS), g_update((w->nseg + UPD_GROUPS_PER_BLOCK(w->upd_group) - 1) / UPD_GROUPS_PER_BLOCK(w->upd_group), R);
     long long lc = 0;
     // Large ensembles of lightly loaded networks run the link update with one thread per (link, replica) (k_update_rl: 4x fewer
     // warp instructions; B200, Chicago sketch: 102 -> 77 us at 64 replicas, 198 -> 116 us at 128); below 64 replicas, or with
@@ -35,7 +35,8 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
                 k_update_rl<<<g_rl, dim3(32 * UPD_RL_WARPS), rl_bytes, st>>>(w->dworlds, s, R, (int)w->links.size(), (const unsigned long long *)w->d_rl_tab);
 #endif
             }
-            else UX_LAUNCH(k_update, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s);
+            else if (w->upd_group == 16) UX_LAUNCH(k_update<16>, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s);
+            else UX_LAUNCH(k_update<32>, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s);
             KT_END(UX_K_UPDATE) lc++;
         }
         bool route = ((phase + s) % w->route_ts) == 0;

@@ -699,15 +699,12 @@ struct HeadSmem {
 
 // 4 warps per block and <= 48 registers (10 blocks per SM): the kernel is a swarm of tiny, latency-bound warps -- measured
 // best among {8x4, 8x5, 4x10, 4x12} blocks-per-SM variants at 32 replicas.
-// A work item gets UPD_GROUP lanes.  With -DUPD_GROUP=16 a warp carries two (link, part) items side by side (a link head has 1-13
+// A work item gets UPD_GROUP lanes (template parameter).  With 16 a warp carries two (link, part) items side by side (a link head has 1-13
 // positions and most queues a handful of platoons); the halves never exchange anything and every synchronisation is a
 // __syncwarp over the half's own lane mask.  Measured on the B200 (parts of 16*UPD_GROUP ring slots): C4 69.2 -> 58.1 us and
 // Chicago x32 56.7 -> 54.7 us, but long queues and single scenarios lose (Chicago dn=5 x16 47.8 -> 54.5, x1 16.5 -> 22.9; Sioux
-// Falls x64 15.0 -> 18.3; Chicago x1 12.6 -> 16.0), so the default stays 32.
-#ifndef UPD_GROUP
-#define UPD_GROUP 32
-#endif
-#define UPD_GROUPS_PER_BLOCK (UPD_WARPS * 32 / UPD_GROUP)
+// Falls x64 15.0 -> 18.3; Chicago x1 12.6 -> 16.0), so the host picks 16 only for large, lightly loaded worlds (ux_world::upd_group).
+#define UPD_GROUPS_PER_BLOCK(G) (UPD_WARPS * 32 / (G))
 #ifdef UX_EMU
 #define UPD_BEGIN if (threadIdx.x & (UPD_GROUP - 1)) return;
 #define UPD_FOR(lane) for (int lane = 0; lane < UPD_GROUP; lane++)
@@ -717,10 +714,11 @@ struct HeadSmem {
 #define UPD_FOR(lane) for (int lane = (int)(threadIdx.x & (UPD_GROUP - 1)), once_ = 1; once_; once_ = 0)
 #define UPD_SYNC() __syncwarp(upd_mask_)
 #endif
+template <int UPD_GROUP>
 __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
     UPD_BEGIN
-    __shared__ HeadSmem hs_all[UPD_GROUPS_PER_BLOCK];
+    __shared__ HeadSmem hs_all[UPD_GROUPS_PER_BLOCK(UPD_GROUP)];
     int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) / UPD_GROUP);
     if (gw >= W.nseg) return;
     // work item = (link, part): the warp sweeps the 32-position windows part, part+nparts, ... of the link's queue, so the
@@ -742,7 +740,7 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
     const double *Xc = W.X + (size_t)cur * C + o;
     if (s0 == 0) {
         // ---- link head
-        HeadSmem &H = hs_all[(threadIdx.x / UPD_GROUP) % UPD_GROUPS_PER_BLOCK];
+        HeadSmem &H = hs_all[(threadIdx.x / UPD_GROUP) % UPD_GROUPS_PER_BLOCK(UPD_GROUP)];
         int hc = n < lanes ? n : lanes;
         if (hc > UX_MAXLANE) hc = UX_MAXLANE;
         int end_node = W.l_end[l];

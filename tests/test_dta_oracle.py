@@ -127,3 +127,50 @@ def check_batched_swap_equals_per_replica(api, mode):
 @pytest.mark.parametrize("mode", [0, 1])
 def test_emu_batched_swap_equals_per_replica(emu_api, mode):
     check_batched_swap_equals_per_replica(emu_api, mode)
+
+
+# ---- aborted trips: a platoon whose enforced route ends in a dead end aborts; dta_solver.cpp:168 / 308 skip every
+#      state other than END, so it keeps no route for the next day and consumes no draw of the swap stream ----------------------
+def run_with_aborts(api, **kw):
+    """dead_end scenario (links l1 orig->mid, l2 mid->dest, l3 mid->deadend): every 4th platoon bound for `dest` is forced onto
+    l1, l3 and aborts at the dead end; the route store knows the pair (orig, dest), so a backend that treated aborts like
+    finished trips would draw for them and re-enforce their route."""
+    sc = S.dead_end()
+    E = sc.to_engine(api, vehicle_logging_timestep_interval=1, hard_deterministic_mode=True, **kw)
+    E.set_option(C.OPT_RECORD_TRAVERSALS, 1)
+    E.dta_enumerate_route_sets(3, 5)
+    dest = E.get_array(C.A_VEH_DEST)
+    d_main = int(np.bincount(dest).argmax())
+    ids, off, k = [], [0], 0
+    for d in dest:
+        if int(d) == d_main:
+            ids.extend([0, 2] if k % 4 == 0 else [0, 1])
+            k += 1
+        else:
+            ids.extend([0, 2])
+        off.append(len(ids))
+    E.batch_enforce_routes_csr(np.asarray(ids, np.int32), np.asarray(off, np.int64))
+    E.main_loop()
+    assert (E.get_array(C.A_VEH_STATE) == C.VS_ABORT).sum() >= 10
+    return E
+
+
+def check_swap_with_aborts(api_a, api_b, mode):
+    Ea, Eb = run_with_aborts(api_a), run_with_aborts(api_b)
+    assert np.array_equal(Ea.get_array(C.A_VEH_STATE), Eb.get_array(C.A_VEH_STATE))
+    for swap_prob, rng_seed in ((0.3, 7), (1.0, 9)):
+        a, b = Ea.dta_route_swap(mode, swap_prob, rng_seed), Eb.dta_route_swap(mode, swap_prob, rng_seed)
+        assert_swap_equal(a, b)
+    aborted = np.flatnonzero(Ea.get_array(C.A_VEH_STATE) == C.VS_ABORT)
+    assert np.all(np.diff(a["rs_offsets"])[aborted] == 0)  # no route kept for an aborted platoon
+    Ea.close(); Eb.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_route_swap_with_aborts_oracle_matches_reference(oracle_api, ref_api, mode):
+    check_swap_with_aborts(oracle_api, ref_api, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_emu_route_swap_with_aborts(oracle_api, emu_api, mode):
+    check_swap_with_aborts(oracle_api, emu_api, mode)

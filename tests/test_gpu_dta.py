@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from uxsim_b200 import _capi as C
-from test_dta_oracle import SCENARIOS, check_batched_swap_equals_per_replica, check_swap_against_oracle, run
+from test_dta_oracle import SCENARIOS, check_batched_swap_equals_per_replica, check_swap_against_oracle, check_swap_with_aborts, run
 
 pytestmark = pytest.mark.gpu
 
@@ -47,3 +47,9 @@ def test_gpu_route_swap_needs_recorded_traversals(cuda_api):
 @pytest.mark.parametrize("mode", [0, 1])
 def test_gpu_batched_swap_equals_per_replica(cuda_api, mode):
     check_batched_swap_equals_per_replica(cuda_api, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gpu_route_swap_with_aborts(oracle_api, cuda_api, mode):
+    """Aborted platoons keep no route and draw nothing (dta_solver.cpp:168 / 308)."""
+    check_swap_with_aborts(oracle_api, cuda_api, mode)

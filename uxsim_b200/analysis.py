@@ -25,10 +25,10 @@ def free_flow_times(W) -> np.ndarray:
     if hit is not None:
         return hit
     best = {}
-    for l in W.LINKS:
-        if l.capacity_in != 0:
-            k = (l.start_node.id, l.end_node.id)
-            best[k] = min(best.get(k, np.inf), l.length / l.u)
+    for l in W.LINKS:  # analyzer.py:146-157: the matrix cell is overwritten link by link, so the LAST link of a node pair decides
+        k = (l.start_node.id, l.end_node.id)
+        best[k] = np.inf if l.capacity_in == 0 else l.length / l.u
+    best = {k: v for k, v in best.items() if np.isfinite(v)}
     try:
         from scipy.sparse import csr_matrix
         from scipy.sparse.csgraph import dijkstra

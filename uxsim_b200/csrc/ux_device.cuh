@@ -10,7 +10,8 @@
 
 enum { LF_SEES_POPS = 1, LF_END_LT_START = 2 };            // link flags
 enum { VF_WAIT_END = 1, VF_ABORT = 2, VF_CAND = 4 };       // vehicle flags
-enum { DERR_NONE = 0, DERR_RING_FULL = 1, DERR_ROUTE_EXHAUSTED = 2, DERR_ROUTE_INCONSISTENT = 3, DERR_AVOID_ALL = 4, DERR_LOG_FULL = 5 };
+enum { DERR_NONE = 0, DERR_RING_FULL = 1, DERR_ROUTE_EXHAUSTED = 2, DERR_ROUTE_INCONSISTENT = 3, DERR_AVOID_ALL = 4, DERR_LOG_FULL = 5, DERR_DEP_TIMEOUT = 6 };
+#define UX_DEP_SPIN_BUDGET (1ll << 24)  // x >= 64 ns: about 2 s before a dependency wait gives up with DERR_DEP_TIMEOUT
 
 // ---------------------------------------------------------------------------------------------------
 // device world

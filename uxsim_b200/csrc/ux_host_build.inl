@@ -627,7 +627,12 @@ static int extend_vehicles(ux_world *w) {
     int N = (int)w->nodes.size(), T = w->total_ts, start_ts = w->timestep;
     long long P0 = w->P_uploaded, P = (long long)w->vehs.size();
     if (!w->rep_routes.empty()) return fail(w, UX_ERR_RUNTIME, "adding vehicles to a world with per-replica routes is not supported");
+    if (w->record_traversals) return fail(w, UX_ERR_RUNTIME, "adding vehicles after the start is not supported with UX_OPT_RECORD_TRAVERSALS (the traversal log is sized at upload)");
     w->rewindable = false;  // the per-platoon arrays move out of the recorded dynamic region
+#ifndef UX_EMU
+    for (auto &g : w->graphs) cudaGraphExecDestroy(g.second.first);  // kernel choices (link-update form, lane groups) depend on the platoon count
+    w->graphs.clear();
+#endif
     for (long long i = P0; i < P; i++) if (w->dest_row[w->vehs[i].dest] < 0)
         return fail(w, UX_ERR_RUNTIME, "vehicle %lld added after the start has destination node %d, which had no demand before: set UX_OPT_ALL_DESTINATIONS "
                     "(World(..., all_destinations=True)) before the first exec_simulation", i, w->vehs[i].dest);

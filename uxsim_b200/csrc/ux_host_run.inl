@@ -62,6 +62,7 @@ static const char *derr_text(int code) {
     case DERR_ROUTE_INCONSISTENT: return "Vehicle %d: specified route is inconsistent; the forced link is not an outgoing link of the current node";
     case DERR_AVOID_ALL: return "Vehicle %d: links_avoid excludes all outgoing links of the current node";
     case DERR_LOG_FULL: return "vehicle log buffer overflow (link %d)";
+    case DERR_DEP_TIMEOUT: return "transfer of node %d timed out waiting for a lower dependency level";
     default: return "device error (info %d)";
     }
 }
@@ -142,7 +143,7 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
         CUDA_OK(cudaMemcpy(e.data(), w->d_err_all, sizeof(int) * e.size(), cudaMemcpyDeviceToHost));
         for (int r = 0; r < w->R; r++) if (e[2 * r]) {
             int c0 = e[2 * r];
-            int code = (c0 == DERR_RING_FULL || c0 == DERR_LOG_FULL) ? UX_ERR_CAPACITY : c0 == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : UX_ERR_INVALID;
+            int code = (c0 == DERR_RING_FULL || c0 == DERR_LOG_FULL) ? UX_ERR_CAPACITY : c0 == DERR_ROUTE_EXHAUSTED ? UX_ERR_OUT_OF_RANGE : c0 == DERR_DEP_TIMEOUT ? UX_ERR_RUNTIME : UX_ERR_INVALID;
             return fail(w, code, derr_text(c0), e[2 * r + 1]);
         }
     }

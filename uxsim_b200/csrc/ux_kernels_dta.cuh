@@ -100,7 +100,7 @@ __global__ void k_dta_prepare(const DevWorld *worlds, const DtaDev *dd) {
     double arrival = (st == UX_VS_END && arr >= 0) ? (double)arr * W.dt : -1.0;
     D.cost_actual[vi] = ntr > 0 ? arrival - (double)D.tr_t[a0] * W.dt : 0.0;
     int choice = -2, pair = -1; unsigned char draws = 0;
-    if (st == UX_VS_END || st == UX_VS_ABORT) {
+    if (st == UX_VS_END) {  // dta_solver.cpp:168 / 308: every other state -- aborted trips included -- keeps no route and draws nothing
         choice = -1;
         int o = W.v_orig[vi], d = W.v_dest[vi];
         long long lo = 0, hi = D.n_od;

@@ -363,9 +363,12 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
                 if (W.node_act[dep] != t) continue;  // that node has nothing to transfer in this step: it pops nothing (and does not publish)
                 volatile int *done = W.node_done + dep;
 #ifdef UX_EMU
-                if (*done < t + 1) dev_error(W, DERR_RING_FULL, -1);
+                if (*done < t + 1) dev_error(W, DERR_DEP_TIMEOUT, n);
 #else
-                while (*done < t + 1) __nanosleep(32);
+                // bounded: the awaited warp has a smaller linear index and is normally resident or finished already; if the
+                // launch order ever broke that assumption the step fails with an error code instead of hanging the device
+                long long spins = 0;
+                while (*done < t + 1) { __nanosleep(64); if (++spins > UX_DEP_SPIN_BUDGET) { dev_error(W, DERR_DEP_TIMEOUT, n); break; } }
 #endif
             }
         }
@@ -378,7 +381,11 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     WARP_FOR(lane) {
         for (int q = lane; q < nol; q += 32) {
             int ol = S.ol[q];
-            int hd = W.head[cur * L + ol], fl_ = W.l_flags[ol], pk_ = ld_cg(W.pop_k2 + ol);  // written by a lower level in this launch
+            int hd = W.head[cur * L + ol], fl_ = W.l_flags[ol];
+            // pops of this step by the link's end node (a lower level of this launch).  Only a node that transfers in this step
+            // writes the count -- an idle end node may not even have reset last step's value yet (small worlds reset it inside
+            // this launch, in that node's own pre_node), so its count is taken as 0 without reading it.
+            int pk_ = ((fl_ & LF_SEES_POPS) && W.node_act[W.l_end[ol]] == t) ? ld_cg(W.pop_k2 + ol) : 0;
             int tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
             long long o = W.l_roff[ol];
             double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];

@@ -177,6 +177,8 @@ class _CudaSolverBase:
                 if s.W_intermid_solution is None or avg_tt < best_avg_tt:
                     best_avg_tt = avg_tt
                     W.analyzer = copy.copy(W.analyzer)
+                    if s.W_intermid_solution is not None:
+                        s.W_intermid_solution._E.close()  # the superseded best day gives its device slabs back now, not at GC
                     s.W_intermid_solution = W
             s.dfs_link.append(W.analyzer.link_to_pandas() if hasattr(W.analyzer, "link_to_pandas") else W.analyzer.link_summary())
             rng_seed = random.randint(0, 2**31 - 1)

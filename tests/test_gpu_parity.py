@@ -301,3 +301,34 @@ def test_large_graph_worklist_shortest_paths(cuda_api, oracle_api):
     sc = S.grid_random_od(n=46, n_platoons=6000, tmax=2400, demand_t=900, seed=5)
     Eg, Eo = run_pair(sc, cuda_api, oracle_api)
     assert compare_engines(Eg, Eo) == []
+
+
+def test_bench_shape_chicago_128_replicas(cuda_api, oracle_api):
+    """The configuration bench.py measures: Chicago sketch, 128 replicas in one world, ingested from flat tables, kernels picked
+    by the engine itself (ensemble forms of the step kernels, warp-per-destination route search) -- replicas 0, 63 and 127
+    equal the single-seed oracle runs bit for bit."""
+    sc = S.chicago_sketch()
+    tab = sc.tables()
+    R, seed0 = 128, 1000
+    Eg = sc.engine_from_tables(cuda_api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, random_seed=seed0)
+    Eg.main_loop()
+    for r in (0, 63, 127):
+        Eo = sc.engine_from_tables(oracle_api, tab, vehicle_logging_timestep_interval=-1, random_seed=seed0 + r)
+        Eo.main_loop()
+        assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"
+        assert summary_stats(Eg, r)[0] == summary_stats(Eo)[0]
+        Eo.close()
+    Eg.close()
+
+
+def test_c4_full_size_against_oracle(cuda_api, oracle_api):
+    """BASELINE configs[3] at FULL size (100x100 signalised grid, 1 M platoons, 10 000 destinations) against the oracle for the
+    first 600 s of simulated time (two route updates, 10 M platoon-updates; about a minute and 6.5 GB on the CPU side)."""
+    sc = S.grid_random_od(n=100, n_platoons=1_000_000, deltan=5, tmax=7200, seed=0)
+    tab = sc.tables()
+    Eg = sc.engine_from_tables(cuda_api, tab, vehicle_logging_timestep_interval=-1, random_seed=0)
+    Eo = sc.engine_from_tables(oracle_api, tab, vehicle_logging_timestep_interval=-1, random_seed=0)
+    Eg.main_loop(until_t=600), Eo.main_loop(until_t=600)
+    assert Eg.get_int(C.I_PLATOON_UPDATES) == Eo.get_int(C.I_PLATOON_UPDATES) > 9e6
+    assert compare_engines(Eg, Eo) == []
+    Eg.close(); Eo.close()

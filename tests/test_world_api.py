@@ -60,9 +60,9 @@ def test_readme_merge_example(cuda_api, oracle_api):
 
 
 @pytest.mark.gpu
-def test_chunked_exec_and_interventions(cuda_api):
+def test_chunked_exec_and_interventions(cuda_api, oracle_api):
     """exec_simulation(until_t=...) returns 0 until the horizon; signals can be changed between chunks
-    (uxsim_cpp_wrapper.py:89-124; test_cpp_mode.py:8485-8643)."""
+    (uxsim_cpp_wrapper.py:89-124; test_cpp_mode.py:8485-8643) -- and the result equals the oracle's under the same interventions."""
     W = uxsim_b200.World(cuda=True, deltan=5, tmax=2000, print_mode=0, save_mode=0, random_seed=0)
     W.addNode("o", 0, 0), W.addNode("m", 1, 0, signal=[60, 60]), W.addNode("d", 2, 0)
     l1 = W.addLink("l1", "o", "m", length=1000, signal_group=0)
@@ -74,7 +74,21 @@ def test_chunked_exec_and_interventions(cuda_api):
     assert n_mid >= 0
     W.get_node("m").signal = [30, 90]
     assert W.exec_simulation() == 1
-    assert l1.cum_departure[-1] == 80 * 5 or l1.cum_departure[-1] > 0
+    sc = S.Scenario("sig", S._world(deltan=5, tmax=2000, random_seed=0))
+    sc.addNode("o", 0, 0), sc.addNode("m", 1, 0, signal=[60, 60]), sc.addNode("d", 2, 0)
+    sc.addLink("l1", "o", "m", length=1000, signal_group=0), sc.addLink("l2", "m", "d", length=1000)
+    sc.adddemand("o", "d", 0, 1000, 0.4)
+    Eo = sc.to_engine(oracle_api, vehicle_logging_timestep_interval=-1)
+    Eo.main_loop(until_t=500)
+    Eo.set_node_signal(1, [30.0, 90.0])
+    Eo.main_loop()
+    L, T = 2, Eo.get_int(C.I_TOTAL_TIMESTEPS)
+    for k, l in enumerate(W.LINKS):
+        assert np.array_equal(l.cum_departure, Eo.get_array(C.A_CUM_DEPARTURE).reshape(L, T)[k])
+        assert np.array_equal(l.cum_arrival, Eo.get_array(C.A_CUM_ARRIVAL).reshape(L, T)[k])
+        assert np.array_equal(l.traveltime_actual, Eo.get_array(C.A_TRAVELTIME_ACTUAL).reshape(L, T)[k])
+    assert np.array_equal(W.get_node("m").signal_log, Eo.get_array(C.A_SIGNAL_LOG).reshape(3, T)[1])
+    assert l1.cum_departure[-1] == 80 * 5
     assert len(W.VEHICLES_RUNNING) == (W._veh("state") == C.VS_RUN).sum()
 
 

@@ -27,6 +27,7 @@ struct DevWorld {
     // static network (shared by all replicas)
     const int *l_start, *l_end, *l_lanes, *l_rcap, *l_flags, *l_sg_off, *l_sg, *l_pair_first, *l_pair_off, *l_pair_list;
     const long long *l_roff;
+    const double *l_tt0;  // length / vmax at initialize_adj_matrix: what traveltime_actual holds before the first exit event
     const double *l_length, *l_vmax, *l_dpl_dn, *l_udt, *l_cap_out, *l_cap_in, *l_mp, *l_penalty, *l_toll;
     const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes, *lvl_level, *dep_off, *dep_list;
     int n_levels;

@@ -219,6 +219,7 @@ UX_API int ux_initialize_adj_matrix(ux_world *w) {
             if (w->links[l].end == (int)i) return fail(w, UX_ERR_INVALID, "link %d: self-loops are not supported", l);
         }
     }
+    for (auto &l : w->links) l.tt0 = l.length / l.vmax;  // traveltime_actual before the first exit event (traffi.cpp:519)
     w->initialized = true;
     return 0;
 }
@@ -311,6 +312,21 @@ static int upload_link_params(ux_world *w) {
     return 0;
 }
 
+// Signal plans (per node) and signal groups (per link) are CSR tables; a setter that changes the LENGTH of one list after the
+// upload rebuilds both tables here (new arrays from the slabs, pointers swapped in every replica's DevWorld).
+static int upload_signal_tables(ux_world *w) {
+    w->rewindable = false;  // the new tables come from the slab tail, inside the range a day rewind would zero
+    std::vector<int> sg_off(w->links.size() + 1, 0), sg, sig_off(w->nodes.size() + 1, 0);
+    std::vector<double> n_sig;
+    for (size_t i = 0; i < w->links.size(); i++) { sg.insert(sg.end(), w->links[i].sg.begin(), w->links[i].sg.end()); sg_off[i + 1] = (int)sg.size(); }
+    for (size_t i = 0; i < w->nodes.size(); i++) { n_sig.insert(n_sig.end(), w->nodes[i].sig.begin(), w->nodes[i].sig.end()); sig_off[i + 1] = (int)n_sig.size(); }
+    w->d_sg_off = dupload(w, sg_off); w->d_sg = dupload(w, sg); w->d_n_sig_off = dupload(w, sig_off); w->d_n_sig = dupload(w, n_sig);
+    if (!w->d_sg_off || !w->d_sg || !w->d_n_sig_off || !w->d_n_sig) return fail(w, UX_ERR_CUDA, "device allocation of the signal tables failed");
+    for (auto &d : w->hw) { d.l_sg_off = w->d_sg_off; d.l_sg = w->d_sg; d.n_sig_off = w->d_n_sig_off; d.n_sig = w->d_n_sig; }
+    CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->hw.size(), cudaMemcpyHostToDevice, w->stream));
+    return 0;
+}
+
 // Build all device state.  Called lazily by the first main_loop (so that vehicles added after
 // initialize_adj_matrix but before the run are included, like the reference).
 static int upload(ux_world *w) {
@@ -364,6 +380,7 @@ static int upload(ux_world *w) {
     base.C = C; base.nseg = w->nseg;
     base.l_start = dupload(w, l_start); base.l_end = dupload(w, l_end); base.l_lanes = dupload(w, l_lanes); base.l_rcap = dupload(w, l_rcap);
     base.l_roff = dupload(w, l_roff); base.l_length = dupload(w, l_length);
+    { std::vector<double> tt0(L); for (int i = 0; i < L; i++) tt0[i] = w->links[i].tt0; base.l_tt0 = dupload(w, tt0); }
     w->d_sg_off = dupload(w, sg_off); w->d_sg = dupload(w, sg);
     base.l_sg_off = w->d_sg_off; base.l_sg = w->d_sg;
     base.seg_link = dupload(w, seg_link); base.seg_start = dupload(w, seg_start);

@@ -82,6 +82,7 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
     if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
     if ((long long)w->vehs.size() != w->P_uploaded) { int rc = extend_vehicles(w); if (rc) return rc; }
     if (w->net_dirty) { int rc = upload_link_params(w); if (rc) return rc; w->net_dirty = false; }
+    if (w->sig_tables_dirty) { int rc = upload_signal_tables(w); if (rc) return rc; w->sig_tables_dirty = false; }
     auto t_begin = std::chrono::steady_clock::now();
     // chunks between route updates: (steps, phase); the executable graph of a chunk shape is built once and cached
     std::vector<std::pair<int, int>> chunks;
@@ -180,9 +181,10 @@ UX_API int ux_set_link_param(ux_world *w, int link, int field, double value) {
 
 UX_API int ux_set_link_signal_group(ux_world *w, int link, const int *sg, int n) {
     if (link < 0 || link >= (int)w->links.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "link id out of range");
-    if (w->uploaded && n != (int)w->links[link].sg.size()) return fail(w, UX_ERR_RUNTIME, "changing the size of a signal group after the simulation started is not supported");
+    bool resized = n != (int)w->links[link].sg.size();
     w->links[link].sg.assign(sg, sg + n);
-    if (w->uploaded) {
+    if (w->uploaded && resized) w->sig_tables_dirty = true;  // the CSR of all groups is rebuilt before the next step
+    else if (w->uploaded) {
         cudaSetDevice(w->device);
         int off = 0; for (int i = 0; i < link; i++) off += (int)w->links[i].sg.size();
         CUDA_OK(cudaMemcpy(w->d_sg + off, sg, sizeof(int) * n, cudaMemcpyHostToDevice));
@@ -193,20 +195,24 @@ UX_API int ux_set_link_signal_group(ux_world *w, int link, const int *sg, int n)
 UX_API int ux_set_node_signal(ux_world *w, int node, const double *sig, int nsig, int phase, double sig_t) {
     if (node < 0 || node >= (int)w->nodes.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "node id out of range");
     HNode &n = w->nodes[node];
-    bool reset = false;
-    if (sig && nsig > 0) {
-        if (w->uploaded && nsig != (int)n.sig.size()) return fail(w, UX_ERR_RUNTIME, "changing the number of signal phases after the simulation started is not supported");
-        n.sig.assign(sig, sig + nsig);
-    }
+    bool resized = false;
+    if (sig && nsig > 0) { resized = nsig != (int)n.sig.size(); n.sig.assign(sig, sig + nsig); }
     if (!w->uploaded) {
         if (sig && nsig > 0 && n.sig_phase0 >= nsig) { n.sig_phase0 = 0; n.sig_t0 = 0; }
         if (phase >= 0) n.sig_phase0 = phase;
         if (sig_t >= 0) n.sig_t0 = sig_t;
         return 0;
     }
-    (void)reset;
     cudaSetDevice(w->device);
-    if (sig && nsig > 0) { int off = 0; for (int i = 0; i < node; i++) off += (int)w->nodes[i].sig.size(); CUDA_OK(cudaMemcpy(w->d_n_sig + off, sig, sizeof(double) * nsig, cudaMemcpyHostToDevice)); }
+    if (resized) {
+        // a different number of phases: the CSR of all signal plans is rebuilt before the next step; a running phase beyond
+        // the new plan restarts at phase 0 (the reference would index past the end of the list)
+        w->sig_tables_dirty = true;
+        for (int r = 0; r < w->R; r++) {
+            int ph = 0; CUDA_OK(cudaMemcpy(&ph, w->hw[r].sig_phase + node, sizeof(int), cudaMemcpyDeviceToHost));
+            if (ph >= nsig && phase < 0) { int z = 0; double zt = 0.0; CUDA_OK(cudaMemcpy(w->hw[r].sig_phase + node, &z, sizeof(int), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(w->hw[r].sig_t + node, &zt, sizeof(double), cudaMemcpyHostToDevice)); }
+        }
+    } else if (sig && nsig > 0) { int off = 0; for (int i = 0; i < node; i++) off += (int)w->nodes[i].sig.size(); CUDA_OK(cudaMemcpy(w->d_n_sig + off, sig, sizeof(double) * nsig, cudaMemcpyHostToDevice)); }
     for (int r = 0; r < w->R; r++) {
         if (phase >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_phase + node, &phase, sizeof(int), cudaMemcpyHostToDevice));
         if (sig_t >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_t + node, &sig_t, sizeof(double), cudaMemcpyHostToDevice));

@@ -10,7 +10,7 @@ struct HNode {
     std::vector<int> in, out;
 };
 struct HLink {
-    int start, end, lanes; double length, vmax, kappa, delta, dpl, tau, w, capacity, mp, cap_out, cap_in, cap_out_rem0, cap_in_rem0, penalty;
+    int start, end, lanes; double length, vmax, kappa, delta, dpl, tau, w, capacity, mp, cap_out, cap_in, cap_out_rem0, cap_in_rem0, penalty, tt0;
     std::vector<int> sg; std::vector<double> toll;
 };
 struct HVeh { int orig, dest, ts; };
@@ -30,7 +30,7 @@ struct ux_world {
     double dt; int total_ts, route_ts, timestep; int R;
     std::vector<HNode> nodes; std::vector<HLink> links; std::vector<HVeh> vehs;
     std::map<long long, std::vector<int>> vlinks[3];
-    bool initialized = false, uploaded = false, net_dirty = false;
+    bool initialized = false, uploaded = false, net_dirty = false, sig_tables_dirty = false;
     std::string err;
     int device = 0;
     cudaStream_t stream = nullptr;

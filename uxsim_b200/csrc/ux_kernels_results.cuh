@@ -15,7 +15,7 @@ __global__ void k_transpose(const T *src, T *dst, int rows, int cols) {
 
 // Link::ensure_traveltime_real (traffi.cpp:631-648): position i takes the value of the latest event whose entry step <= i.
 UX_DEV void tt_actual_link(const DevWorld &W, int l, double *out) {
-    double cur = W.l_length[l] / W.l_vmax[l];
+    double cur = W.l_tt0[l];  // the fill value of Link::Link (traffi.cpp:519): free-flow time at the speed the link was frozen with
     int best = 0;
 #pragma unroll 8
     for (int i = 0; i < W.T; i++) {  // the loads do not depend on the running arg-max, so they pipeline
@@ -66,7 +66,7 @@ __global__ void k_ensemble_partial(const DevWorld *worlds, double *part) {
     int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     int T = W.T, L = W.L;
     if (l >= L) return;
-    double cur = W.l_length[l] / W.l_vmax[l], s1 = 0, s2 = 0;
+    double cur = W.l_tt0[l], s1 = 0, s2 = 0;
     int best = 0;
 #pragma unroll 8
     for (int i = 0; i < T; i++) {

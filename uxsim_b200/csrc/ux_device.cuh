@@ -16,6 +16,15 @@ enum { DERR_NONE = 0, DERR_RING_FULL = 1, DERR_ROUTE_EXHAUSTED = 2, DERR_ROUTE_I
 // ---------------------------------------------------------------------------------------------------
 // device world
 // ---------------------------------------------------------------------------------------------------
+// 16-byte records of the replica-minor dynamic state.  LOADS may take a whole record (one 128-bit access); STORES always go
+// to single members, because different members of one record belong to different writers (tail: the link's start node,
+// head: the link update, pop_k2: the end node ...).
+struct LinkQ { int head[2], tail, tail_k1; };  // monotone queue counters: head double-buffered by step parity, tail, tail after this step's generation
+struct LinkC { int pop_k2, hcount, trips, ev_cnt; };  // pops by this step's transfer, head positions the next transfer must look at, finished trips, exit events
+struct LinkR { double cap_out_rem, cap_in_rem; };
+struct NodeS { int sig_phase, gen_head, gen_avail, node_act; };  // node_act: (step + 1) of the last link update that left a candidate / trip-end waiter at the head of an in-link
+struct NodeR { double sig_t, fc_rem; };
+
 struct DevWorld {
     int N, L, T, D, vis_words;
     long long P, C;
@@ -40,15 +49,21 @@ struct DevWorld {
     const int *eout_off, *eout_to;            // ... and grouped by their START node, end nodes ascending (next-hop pass)
     const int *e_inpos, *e_outpos;            // position of edge e in the two CSRs (k_edge_cost scatters the costs there)
     int n_edges;
-    // dynamic (per replica)
-    int *head, *tail, *tail_k1, *pop_k2, *hcount, *trips, *ev_cnt;
-    int *node_act;  // per node: (step + 1) of the last link update that left a candidate / trip-end waiter at the head of an in-link
+    // dynamic, REPLICA-MINOR: the per-link / per-node scalars of all replicas interleaved -- element (entity e, replica r) lives at
+    // base[e * RS + r]; each replica's DevWorld holds base + r, so `field[e * RS]` is its own element.  A kernel whose lanes are
+    // the replicas of one entity (k_link_pre, k_node_rl, k_update_rl) reads them fully coalesced; a kernel whose lanes walk the
+    // entities of one replica sees the old layout at RS == 1.  The scalars are packed into 16-byte records by who reads them together.
+    int RS, rep;            // replica stride (elements); this replica's index
+    long long rep_stride;   // bytes between the replica-major arrays (rings, per-platoon state, route tables, logs) of consecutive replicas; 0 = not uniform
+    LinkQ *lq;              // queue counters of a link
+    LinkC *lc;              // per-step / cumulative counts of a link
+    LinkR *lr;              // capacity tokens of the two link sides
+    NodeS *ns;              // signal phase, vertical-queue cursors, activity step of a node
+    NodeR *nr;              // signal clock, node capacity tokens
     long long *stat_count;
-    double *cap_out_rem, *cap_in_rem;
+    // dynamic, replica-major (contiguous per replica)
     double *X, *V;
     int *VID, *LANE;
-    int *sig_phase, *gen_head, *gen_avail;
-    double *sig_t, *fc_rem;
     int *v_state, *v_next, *v_link, *v_arr_ts, *v_trav;
     double *v_mr, *v_atl, *v_tt, *v_dist, *v_entry_x;
     unsigned char *v_flags;
@@ -77,14 +92,23 @@ struct DevWorld {
 // Link-major (-DUX_LINK_MAJOR: a link's consecutive steps share 32-byte sectors, no transpose at hand-back) was measured
 // 2-3 % SLOWER on the B200 (Chicago x32: 79.1 vs 77.4 ms; at deltan=5: 430 vs 416 ms): the loop is bound by dependent-load
 // latency, not by the DRAM sectors this layout saves.
+// The series are replica-minor as well ([T][L][RS]): a step writes one contiguous row for all links and replicas.
 #ifndef UX_LINK_MAJOR
 #define UX_TIME_MAJOR 1
-#define TLI(W, t, l) ((size_t)(t) * (size_t)(W).L + (size_t)(l))
-#define TNI(W, t, n) ((size_t)(t) * (size_t)(W).N + (size_t)(n))
+#define TLI(W, t, l) (((size_t)(t) * (size_t)(W).L + (size_t)(l)) * (size_t)(W).RS)
+#define TNI(W, t, n) (((size_t)(t) * (size_t)(W).N + (size_t)(n)) * (size_t)(W).RS)
 #else
-#define TLI(W, t, l) ((size_t)(l) * (size_t)(W).T + (size_t)(t))
-#define TNI(W, t, n) ((size_t)(n) * (size_t)(W).T + (size_t)(t))
+#define TLI(W, t, l) (((size_t)(l) * (size_t)(W).T + (size_t)(t)) * (size_t)(W).RS)
+#define TNI(W, t, n) (((size_t)(n) * (size_t)(W).T + (size_t)(t)) * (size_t)(W).RS)
 #endif
+// replica-minor per-link / per-node state of the replica W belongs to
+#define LQ(W, l) ((W).lq[(size_t)(l) * (size_t)(W).RS])
+#define LC(W, l) ((W).lc[(size_t)(l) * (size_t)(W).RS])
+#define LR(W, l) ((W).lr[(size_t)(l) * (size_t)(W).RS])
+#define LSTAT(W, l) ((W).stat_count[(size_t)(l) * (size_t)(W).RS])
+#define NS(W, n) ((W).ns[(size_t)(n) * (size_t)(W).RS])
+#define NR(W, n) ((W).nr[(size_t)(n) * (size_t)(W).RS])
+#define NDONE(W, n) ((W).node_done[(size_t)(n) * (size_t)(W).RS])
 
 // The per-replica DevWorld lives in global memory; reading its ~90 pointers through a reference there would make
 // every `W.x[...]` a dependent pointer load that must be repeated after each global store (possible aliasing).
@@ -212,20 +236,20 @@ UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned en
 
 // acceptance test of an out-link seen with effective head `hd` (traffi.cpp:130-142, 285-297)
 UX_DEV bool can_accept(const DevWorld &W, int l, int hd, int cur) {
-    int sz = W.tail[l] - hd, lanes = W.l_lanes[l];
+    int sz = LQ(W, l).tail - hd, lanes = W.l_lanes[l];
     bool ok = false;
     if (sz < lanes) ok = true;
     else {
         int slot = ring_slot(hd, sz - lanes, W.l_rcap[l]);
         if (W.X[(size_t)cur * W.C + W.l_roff[l] + slot] > W.l_dpl_dn[l]) ok = true;
     }
-    if (W.cap_in_rem[l] < W.dn) ok = false;
+    if (LR(W, l).cap_in_rem < W.dn) ok = false;
     return ok;
 }
 
 // push a platoon at the tail of link l (lane + leader rule traffi.cpp:168-183 / 385-398).  Returns the slot.
 UX_DEV int ring_push(const DevWorld &W, int l, int hd, int cur, double x, double x_old, double v, int vid) {
-    int cap = W.l_rcap[l], tl = W.tail[l], sz = tl - hd, lanes = W.l_lanes[l];
+    int cap = W.l_rcap[l], tl = LQ(W, l).tail, sz = tl - hd, lanes = W.l_lanes[l];
     if (sz >= cap) { dev_error(W, DERR_RING_FULL, l); return -1; }
     long long o = W.l_roff[l];
     int lane = 0;
@@ -236,7 +260,7 @@ UX_DEV int ring_push(const DevWorld &W, int l, int hd, int cur, double x, double
     W.V[o + slot] = v;
     W.VID[o + slot] = vid;
     W.LANE[o + slot] = lane;
-    W.tail[l] = tl + 1;
+    LQ(W, l).tail = tl + 1;
     return slot;
 }
 
@@ -262,15 +286,15 @@ UX_DEV void record_tt_event(const DevWorld &W, int l, double atl, double tt) {
     int s = (int)(atl / W.dt);
     if (s < 0) s = 0;
     if (s >= W.T) s = W.T - 1;
-    int ord = W.ev_cnt[l] + 1;
-    W.ev_cnt[l] = ord;
+    int ord = LC(W, l).ev_cnt + 1;
+    LC(W, l).ev_cnt = ord;
     W.ev_ord[TLI(W, s, l)] = ord;
     W.ev_tt[TLI(W, s, l)] = tt;
 }
 
 // Vehicle::end_trip (traffi.cpp:886-927) for the front platoon `vid` of link l, currently at position x
 UX_DEV void end_trip(const DevWorld &W, int vid, int l, int t, double x) {
-    W.trips[l] += 1;
+    LC(W, l).trips += 1;
     W.cum_dep[TLI(W, t, l)] += W.dn;
     double atl = W.v_atl[vid];
     record_tt_event(W, l, atl, ((double)t + 1.0) * W.dt - atl);

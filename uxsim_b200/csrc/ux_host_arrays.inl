@@ -117,6 +117,31 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         cudaSetDevice(w->device);
         if (!w->uploaded) { int rc = upload(w); if (rc) return rc; }
         size_t es0 = dt0 == UX_DT_I32 ? 4 : 8, row = es0 * (size_t)n0;
+        {   // replica-minor members: one gather kernel writes the replica-major [R, n] block
+            const DevWorld &d0 = w->hw[0];
+            const void *first = nullptr; size_t rec = 0;
+            switch (what) {
+            case UX_A_NODE_SIGNAL_PHASE: first = &NS(d0, 0).sig_phase; rec = sizeof(NodeS); break;
+            case UX_A_NODE_SIGNAL_T: first = &NR(d0, 0).sig_t; rec = sizeof(NodeR); break;
+            case UX_A_LINK_CAPACITY_IN_REMAIN: first = &LR(d0, 0).cap_in_rem; rec = sizeof(LinkR); break;
+            case UX_A_LINK_CAPACITY_OUT_REMAIN: first = &LR(d0, 0).cap_out_rem; rec = sizeof(LinkR); break;
+            case UX_A_LINK_STAT_COUNT: first = &LSTAT(d0, 0); rec = sizeof(long long); break;
+            default: break;
+            }
+            if (first) {
+                int rc = ensure_scratch(w, row * R + 16); if (rc) return rc;
+                long long tot = (long long)n0 * R;
+                if (tot > 0) {
+                    if (es0 == 4) UX_LAUNCH(k_gather_all<int>, dim3((unsigned)((tot + 255) / 256)), dim3(256), w->stream, (const char *)first, rec, d0.RS, R, (long long)n0, (int *)w->d_scratch);
+                    else UX_LAUNCH(k_gather_all<long long>, dim3((unsigned)((tot + 255) / 256)), dim3(256), w->stream, (const char *)first, rec, d0.RS, R, (long long)n0, (long long *)w->d_scratch);
+                    CUDA_OK(cudaMemcpyAsync(dst, w->d_scratch, row * R, cudaMemcpyDeviceToHost, w->stream));
+                }
+                CUDA_OK(cudaStreamSynchronize(w->stream));
+                if (what == UX_A_LINK_STAT_COUNT) { long long *hi = (long long *)dst; double *o = (double *)dst; for (long long i = 0; i < tot; i++) o[i] = (double)hi[i]; }  // i64 on the device, f64 in the ABI
+                w->d2h_bytes += (long long)(row * R);
+                return n0 * R;
+            }
+        }
         std::vector<const void *> src(R, nullptr);
         for (int r = 0; r < R; r++) {
             const DevWorld &d = w->hw[r];
@@ -124,22 +149,10 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
             case UX_A_VEH_ARRIVAL_TS: src[r] = d.v_arr_ts; break;
             case UX_A_VEH_TRAVEL_TIME: src[r] = d.v_tt; break;
             case UX_A_VEH_LINK: src[r] = d.v_link; break;
-            case UX_A_NODE_SIGNAL_PHASE: src[r] = d.sig_phase; break;
-            case UX_A_NODE_SIGNAL_T: src[r] = d.sig_t; break;
-            case UX_A_LINK_CAPACITY_IN_REMAIN: src[r] = d.cap_in_rem; break;
-            case UX_A_LINK_CAPACITY_OUT_REMAIN: src[r] = d.cap_out_rem; break;
             default: break;
             }
         }
-        if (what == UX_A_LINK_STAT_COUNT) {  // i64 on the device, f64 in the ABI
-            int rc = ensure_scratch(w, 8 * (size_t)n0 * R + 16); if (rc) return rc;
-            for (int r = 0; r < R; r++) cudaMemcpyAsync((char *)w->d_scratch + row * r, w->hw[r].stat_count, row, cudaMemcpyDeviceToDevice, w->stream);
-            std::vector<long long> h((size_t)n0 * R);
-            if (n0 * R) CUDA_OK(cudaMemcpyAsync(h.data(), w->d_scratch, row * R, cudaMemcpyDeviceToHost, w->stream));
-            CUDA_OK(cudaStreamSynchronize(w->stream));
-            double *o = (double *)dst;
-            for (size_t i = 0; i < h.size(); i++) o[i] = (double)h[i];
-        } else {
+        {
             if (!src[0]) return fail(w, UX_ERR_INVALID, "array %d cannot be fetched for all replicas at once", what);
             int rc = ensure_scratch(w, row * R + 16); if (rc) return rc;
             for (int r = 0; r < R; r++) cudaMemcpyAsync((char *)w->d_scratch + row * r, src[r], row, cudaMemcpyDeviceToDevice, w->stream);
@@ -175,13 +188,12 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         for (long long i = 0; i < P; i++) o[i] = dist[i] + (st[i] == UX_VS_RUN ? vx[i] - ex[i] : 0.0);
         break; }
     case UX_A_LINK_NUM_VEHICLES: {
-        std::vector<int> hd(2 * (size_t)L), tl(L);
-        if (L) { CUDA_OK(cudaMemcpy(hd.data(), d.head, sizeof(int) * 2 * L, cudaMemcpyDeviceToHost)); CUDA_OK(cudaMemcpy(tl.data(), d.tail, sizeof(int) * L, cudaMemcpyDeviceToHost)); }
-        int cur = w->timestep & 1;
-        for (int l = 0; l < L; l++) oi[l] = tl[l] - hd[(size_t)cur * L + l];
+        std::vector<int> hd, tl;
+        if (!fetch_field(w, &LQ(d, 0).head[w->timestep & 1], sizeof(LinkQ), L, hd) || !fetch_field(w, &LQ(d, 0).tail, sizeof(LinkQ), L, tl)) return fail(w, UX_ERR_CUDA, "device read failed");
+        for (int l = 0; l < L; l++) oi[l] = tl[l] - hd[l];
         break; }
-    case UX_A_LINK_STAT_COUNT: { std::vector<long long> h(L); if (L) CUDA_OK(cudaMemcpy(h.data(), d.stat_count, sizeof(long long) * L, cudaMemcpyDeviceToHost)); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
-    case UX_A_LINK_TRIPS_COMPLETED: { std::vector<int> h(L); if (L) CUDA_OK(cudaMemcpy(h.data(), d.trips, sizeof(int) * L, cudaMemcpyDeviceToHost)); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
+    case UX_A_LINK_STAT_COUNT: { std::vector<long long> h; if (!fetch_field(w, &LSTAT(d, 0), sizeof(long long), L, h)) return fail(w, UX_ERR_CUDA, "device read failed"); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
+    case UX_A_LINK_TRIPS_COMPLETED: { std::vector<int> h; if (!fetch_field(w, &LC(d, 0).trips, sizeof(LinkC), L, h)) return fail(w, UX_ERR_CUDA, "device read failed"); for (int l = 0; l < L; l++) o[l] = (double)h[l]; break; }
     case UX_A_ROUTE_PREF: {
         std::vector<double> h((size_t)d.D * L); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.pref, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         for (int k = 0; k < N; k++) { int r = w->dest_row[k]; for (int l = 0; l < L; l++) o[(size_t)k * L + l] = r >= 0 ? h[(size_t)r * L + l] : 0.0; }

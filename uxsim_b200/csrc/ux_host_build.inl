@@ -327,6 +327,13 @@ static int upload_signal_tables(ux_world *w) {
     return 0;
 }
 
+// the non-zero initial values of the replica-minor state, broadcast over the replicas (upload, and every day rewind)
+static void launch_init_dyn(ux_world *w) {
+    int L = (int)w->links.size(), N = (int)w->nodes.size();
+    long long tot = (long long)(L + N) * w->R;
+    if (tot > 0) UX_LAUNCH(k_init_dyn, dim3((unsigned)((tot + 255) / 256)), dim3(256), w->stream, w->dworlds, w->R, w->d_init_co, w->d_init_ci, w->d_init_ph, w->d_init_st, w->d_init_fc);
+}
+
 // Build all device state.  Called lazily by the first main_loop (so that vehicles added after
 // initialize_adj_matrix but before the run are included, like the reference).
 static int upload(ux_world *w) {
@@ -474,95 +481,95 @@ static int upload(ux_world *w) {
         base.vl_off[kind] = dupload(w, off); base.vl_list[kind] = dupload(w, list);
     }
     w->P_uploaded = P;
-    // ---- per-replica dynamic state
+    // ---- dynamic state
     std::vector<double> co_rem(L), ci_rem(L), sig_t(N), fc_rem(N);
     std::vector<int> sig_ph(N);
     for (int i = 0; i < L; i++) { co_rem[i] = w->links[i].cap_out_rem0; ci_rem[i] = w->links[i].cap_in_rem0; }
     for (int i = 0; i < N; i++) { sig_t[i] = w->nodes[i].sig_t0; sig_ph[i] = w->nodes[i].sig_phase0; fc_rem[i] = w->nodes[i].fc_rem0; }
-    std::vector<int> tb(1, w->timestep);
-    w->hw.assign(w->R, base);
+    // the non-zero initial values, kept on the device: k_init_dyn broadcasts them over the replicas (at upload and at every day rewind)
+    w->d_init_co = dupload(w, co_rem); w->d_init_ci = dupload(w, ci_rem); w->d_init_ph = dupload(w, sig_ph); w->d_init_st = dupload(w, sig_t); w->d_init_fc = dupload(w, fc_rem);
+    const int R = w->R, RS = (R + 7) & ~7;  // rows of 4-byte elements start on 32-byte sectors
+    base.RS = RS;
+    w->hw.assign(R, base);
     for (auto &kv : w->rep_routes) {  // per-replica enforced routes (ux_dta_enforce_routes): specified_route and links_preferred of that replica
         DevWorld &d = w->hw[kv.first];
         const int *o_ = dupload(w, kv.second.first), *l_ = dupload(w, kv.second.second);
         d.vl_off[0] = d.vl_off[1] = o_; d.vl_list[0] = d.vl_list[1] = l_;
     }
-    // Everything allocated from here to the end of the replica loop is per-replica DYNAMIC state: zero, except what the
-    // ReInit list records.  ux_dta_next_day rewinds a finished world by zeroing these slab ranges and replaying the list.
+    // Everything allocated from here to the second mark is DYNAMIC state: zero, except what k_init_dyn and the ReInit list
+    // restore.  ux_dta_next_day rewinds a finished world by zeroing these slab ranges and replaying both.
     dalloc<char>(w, 1);  // make sure the marks below sit inside a slab
     w->dyn_slab0 = w->slabs.size() - 1; w->dyn_used0 = w->slabs.back().used;
     w->reinit.clear();
-    auto share = [](const void *p_, size_t b) { auto v = std::make_shared<std::vector<char>>(b); if (b) memcpy(v->data(), p_, b); return v; };
-    auto h_co = share(co_rem.data(), 8 * co_rem.size()), h_ci = share(ci_rem.data(), 8 * ci_rem.size()), h_sp = share(sig_ph.data(), 4 * sig_ph.size()),
-         h_st = share(sig_t.data(), 8 * sig_t.size()), h_fc = share(fc_rem.data(), 8 * fc_rem.size());
     auto reg_ff = [&](void *q, size_t b) { if (q) { cudaMemsetAsync(q, 0xff, b ? b : 1, w->stream); w->reinit.push_back({q, b ? b : 1, 0, nullptr}); } };
-    auto reg_copy = [&](void *q, const std::shared_ptr<std::vector<char>> &src) { if (q && !src->empty()) w->reinit.push_back({q, src->size(), 2, src}); };
-    w->d_err_all = dalloc<int>(w, 2 * (size_t)w->R);
+    w->d_err_all = dalloc<int>(w, 2 * (size_t)R);
     if (!w->d_err_all) return fail(w, UX_ERR_CUDA, "device allocation failed");
     size_t TL = (size_t)T * L;
-    for (int r = 0; r < w->R; r++) {
-        DevWorld &d = w->hw[r];
-        d.seed = w->p.random_seed + r;
-        d.head = dalloc<int>(w, 2 * (size_t)L); d.tail = dalloc<int>(w, L); d.tail_k1 = dalloc<int>(w, L); d.pop_k2 = dalloc<int>(w, L); d.hcount = dalloc<int>(w, L); d.node_act = dalloc<int>(w, N + 1);
-        d.trips = dalloc<int>(w, L); d.ev_cnt = dalloc<int>(w, L); d.stat_count = dalloc<long long>(w, L);
-        // initial values: staged from the host once (replica 0), cloned on the device for the other replicas
-        const DevWorld &d0 = w->hw[0];
-        if (r == 0) { d.cap_out_rem = dupload(w, co_rem); d.cap_in_rem = dupload(w, ci_rem); }
-        else { d.cap_out_rem = dclone(w, d0.cap_out_rem, co_rem.size()); d.cap_in_rem = dclone(w, d0.cap_in_rem, ci_rem.size()); }
-        reg_copy(d.cap_out_rem, h_co); reg_copy(d.cap_in_rem, h_ci);
-        d.X = dalloc<double>(w, 2 * (size_t)C); d.V = dalloc<double>(w, C); d.VID = dalloc<int>(w, C); d.LANE = dalloc<int>(w, C);
-        if (r == 0) { d.sig_phase = dupload(w, sig_ph); d.sig_t = dupload(w, sig_t); d.fc_rem = dupload(w, fc_rem); }
-        else { d.sig_phase = dclone(w, d0.sig_phase, sig_ph.size()); d.sig_t = dclone(w, d0.sig_t, sig_t.size()); d.fc_rem = dclone(w, d0.fc_rem, fc_rem.size()); }
-        reg_copy(d.sig_phase, h_sp); reg_copy(d.sig_t, h_st); reg_copy(d.fc_rem, h_fc);
-        d.gen_head = dalloc<int>(w, N); d.gen_avail = dalloc<int>(w, N);
-        d.v_state = dalloc<int>(w, P); d.v_next = dalloc<int>(w, P); d.v_link = dalloc<int>(w, P, false); d.v_arr_ts = dalloc<int>(w, P, false); d.v_trav = dalloc<int>(w, P);
-        reg_ff(d.v_link, sizeof(int) * P); reg_ff(d.v_arr_ts, sizeof(int) * P);
-        d.v_mr = dalloc<double>(w, P); d.v_atl = dalloc<double>(w, P); d.v_dist = dalloc<double>(w, P); d.v_entry_x = dalloc<double>(w, P);
-        d.v_tt = dalloc<double>(w, P);
-        if (d.v_tt && P) { UX_LAUNCH(k_fill_f64, dim3((unsigned)((P + 255) / 256)), dim3(256), w->stream, d.v_tt, (long long)P, -1.0); w->reinit.push_back({d.v_tt, (size_t)P * 8, 1, nullptr}); }
-        d.v_flags = dalloc<unsigned char>(w, P);
-        if (base.log_mode) {
-            long long cap = 0;
-            for (long long i = 0; i < P; i++) cap += std::max(0, T - w->vehs[i].ts - 1);  // a platoon can be RUN from ts+1 to T-1
-            d.lg_cap = cap;
-            d.v_gen_ts = dalloc<int>(w, P, false); d.v_end_ts = dalloc<int>(w, P, false); d.v_end_kind = dalloc<unsigned char>(w, P);
-            reg_ff(d.v_gen_ts, sizeof(int) * P); reg_ff(d.v_end_ts, sizeof(int) * P);
-            d.lg_vid = dalloc<int>(w, cap, false); d.lg_t = dalloc<int>(w, cap, false); d.lg_link = dalloc<int>(w, cap, false); d.lg_lane = dalloc<int>(w, cap, false);
-            d.lg_x = dalloc<double>(w, cap, false); d.lg_v = dalloc<double>(w, cap, false); d.lg_s = dalloc<double>(w, cap, false);
-            d.lg_count = dalloc<unsigned long long>(w, 1);
-            if (!d.lg_vid || !d.lg_s || !d.lg_count || !d.v_gen_ts) return fail(w, UX_ERR_CUDA, "device allocation of the vehicle logs failed (%lld records)", cap);
-        }
-        if (w->record_traversals) {  // at most one link entry per platoon and step; in practice a few dozen per trip
-            long long bound = 0;
-            for (long long i = 0; i < P; i++) bound += std::max(0, T - w->vehs[i].ts - 1);
-            d.tv_cap = std::min(bound, std::max(P * 48, (long long)1 << 20));
-            d.tv_ev = dalloc<int4>(w, (size_t)d.tv_cap, false); d.tv_count = dalloc<unsigned long long>(w, 1);
-            if (!d.tv_ev || !d.tv_count) return fail(w, UX_ERR_CUDA, "device allocation of the traversal log failed (%lld events)", d.tv_cap);
-        }
-        d.v_visited = base.no_cyclic ? dalloc<unsigned>(w, (size_t)P * base.vis_words) : nullptr;
-        d.cum_arr = dalloc<double>(w, TL); d.cum_dep = dalloc<double>(w, TL); d.tt_inst = dalloc<double>(w, TL); d.ev_tt = dalloc<double>(w, TL);
-        d.ev_ord = dalloc<int>(w, TL); d.sig_log = dalloc<int>(w, (size_t)T * N);
-        d.pref = dalloc<double>(w, (size_t)D * L); d.rdist = dalloc<double>(w, (size_t)D * N); d.pair_cost = dalloc<double>(w, w->n_edges);
-        d.cost_in = dalloc<double>(w, w->n_edges); d.cost_out = dalloc<double>(w, w->n_edges); d.sssp_delta = dalloc<double>(w, 1);
-        d.pref_active = dalloc<int>(w, D); d.has_path = dalloc<int>(w, D); d.rnext = dalloc<int>(w, (size_t)D * N, false);
-        reg_ff(d.rnext, sizeof(int) * (size_t)D * N);
-        d.err = w->d_err_all + 2 * r; d.t_base = r == 0 ? dupload(w, tb) : dclone(w, w->hw[0].t_base, 1); d.node_done = dalloc<int>(w, N + 2); d.n_levels = w->n_levels;
-        if (!d.head || !d.X || !d.cum_arr || !d.ev_ord || !d.pref || !d.t_base || !d.v_flags || !d.sig_log || !d.rnext)
-            return fail(w, UX_ERR_CUDA, "device allocation failed (replica %d)", r);
+    // (1) replica-minor state: one array per field for ALL replicas, element (entity, replica) at [entity * RS + replica]
+    LinkQ *lq = dalloc<LinkQ>(w, (size_t)L * RS); LinkC *lc = dalloc<LinkC>(w, (size_t)L * RS); LinkR *lr = dalloc<LinkR>(w, (size_t)L * RS);
+    long long *stat = dalloc<long long>(w, (size_t)L * RS);
+    NodeS *ns = dalloc<NodeS>(w, (size_t)(N + 2) * RS); NodeR *nr = dalloc<NodeR>(w, (size_t)(N + 2) * RS); int *node_done = dalloc<int>(w, (size_t)(N + 2) * RS);
+    double *cum_arr = dalloc<double>(w, TL * RS), *cum_dep = dalloc<double>(w, TL * RS), *tt_inst = dalloc<double>(w, TL * RS), *ev_tt = dalloc<double>(w, TL * RS);
+    int *ev_ord = dalloc<int>(w, TL * RS), *sig_log = dalloc<int>(w, (size_t)T * N * RS), *t_base = dalloc<int>(w, RS);
+    if (!lq || !lc || !lr || !stat || !ns || !nr || !node_done || !cum_arr || !cum_dep || !tt_inst || !ev_tt || !ev_ord || !sig_log || !t_base)
+        return fail(w, UX_ERR_CUDA, "device allocation failed (replica-minor state, %d replicas)", R);
+    { std::vector<int> tb(RS, w->timestep); CUDA_OK(cudaMemcpyAsync(t_base, tb.data(), sizeof(int) * RS, cudaMemcpyHostToDevice, w->stream)); }
+    // (2) replica-major state: rings, per-platoon arrays, route tables, logs -- contiguous per replica, and at the SAME offsets
+    // inside one block per replica, so the array of replica r is the array of replica 0 + r * rep_stride bytes (the kernels
+    // whose lanes are replicas compute the address instead of loading 32 pointer tables)
+    long long lg_cap = 0, tv_cap = 0;
+    if (base.log_mode) for (long long i = 0; i < P; i++) lg_cap += std::max(0, T - w->vehs[i].ts - 1);  // a platoon can be RUN from ts+1 to T-1
+    if (w->record_traversals) {  // at most one link entry per platoon and step; in practice a few dozen per trip
+        long long bound = 0;
+        for (long long i = 0; i < P; i++) bound += std::max(0, T - w->vehs[i].ts - 1);
+        tv_cap = std::min(bound, std::max(P * 48, (long long)1 << 20));
     }
+    auto layout = [&](DevWorld &d, char *blk) -> size_t {
+        size_t off = 0;
+        auto take = [&](size_t bytes) -> char * { off = (off + 255) & ~(size_t)255; char *q = blk ? blk + off : nullptr; off += bytes ? bytes : 1; return q; };
+#define TAKE(T_, n_) ((T_ *)take(sizeof(T_) * (size_t)(n_)))
+        d.X = TAKE(double, 2 * (size_t)C); d.V = TAKE(double, C); d.VID = TAKE(int, C); d.LANE = TAKE(int, C);
+        d.v_state = TAKE(int, P); d.v_next = TAKE(int, P); d.v_link = TAKE(int, P); d.v_arr_ts = TAKE(int, P); d.v_trav = TAKE(int, P);
+        d.v_mr = TAKE(double, P); d.v_atl = TAKE(double, P); d.v_dist = TAKE(double, P); d.v_entry_x = TAKE(double, P); d.v_tt = TAKE(double, P);
+        d.v_flags = TAKE(unsigned char, P);
+        if (base.log_mode) {
+            d.lg_cap = lg_cap;
+            d.v_gen_ts = TAKE(int, P); d.v_end_ts = TAKE(int, P); d.v_end_kind = TAKE(unsigned char, P);
+            d.lg_vid = TAKE(int, lg_cap); d.lg_t = TAKE(int, lg_cap); d.lg_link = TAKE(int, lg_cap); d.lg_lane = TAKE(int, lg_cap);
+            d.lg_x = TAKE(double, lg_cap); d.lg_v = TAKE(double, lg_cap); d.lg_s = TAKE(double, lg_cap);
+            d.lg_count = TAKE(unsigned long long, 1);
+        }
+        if (w->record_traversals) { d.tv_cap = tv_cap; d.tv_ev = TAKE(int4, tv_cap); d.tv_count = TAKE(unsigned long long, 1); }
+        d.v_visited = base.no_cyclic ? TAKE(unsigned, (size_t)P * base.vis_words) : nullptr;
+        d.pref = TAKE(double, (size_t)D * L); d.rdist = TAKE(double, (size_t)D * N); d.pair_cost = TAKE(double, w->n_edges);
+        d.cost_in = TAKE(double, w->n_edges); d.cost_out = TAKE(double, w->n_edges); d.sssp_delta = TAKE(double, 1);
+        d.pref_active = TAKE(int, D); d.has_path = TAKE(int, D); d.rnext = TAKE(int, (size_t)D * N);
+#undef TAKE
+        return (off + 255) & ~(size_t)255;
+    };
+    DevWorld probe = base;
+    const size_t rep_bytes = layout(probe, nullptr);
+    char *rep_blk = dalloc<char>(w, rep_bytes * (size_t)R);
+    if (!rep_blk) return fail(w, UX_ERR_CUDA, "device allocation failed (%d replicas x %zu bytes of per-replica state)", R, rep_bytes);
+    for (int r = 0; r < R; r++) {
+        DevWorld &d = w->hw[r];
+        d.seed = w->p.random_seed + r; d.rep = r; d.rep_stride = (long long)rep_bytes;
+        d.lq = lq + r; d.lc = lc + r; d.lr = lr + r; d.stat_count = stat + r; d.ns = ns + r; d.nr = nr + r; d.node_done = node_done + r;
+        d.cum_arr = cum_arr + r; d.cum_dep = cum_dep + r; d.tt_inst = tt_inst + r; d.ev_tt = ev_tt + r; d.ev_ord = ev_ord + r; d.sig_log = sig_log + r; d.t_base = t_base + r;
+        layout(d, rep_blk + (size_t)r * rep_bytes);
+        reg_ff(d.v_link, sizeof(int) * P); reg_ff(d.v_arr_ts, sizeof(int) * P);
+        if (P) { UX_LAUNCH(k_fill_f64, dim3((unsigned)((P + 255) / 256)), dim3(256), w->stream, d.v_tt, (long long)P, -1.0); w->reinit.push_back({d.v_tt, (size_t)P * 8, 1, nullptr}); }
+        if (base.log_mode) { reg_ff(d.v_gen_ts, sizeof(int) * P); reg_ff(d.v_end_ts, sizeof(int) * P); }
+        reg_ff(d.rnext, sizeof(int) * (size_t)D * N);
+        d.err = w->d_err_all + 2 * r; d.n_levels = w->n_levels;
+    }
+    w->uniform = true;
     w->dyn_slab1 = w->slabs.size() - 1; w->dyn_used1 = w->slabs.back().used;
     w->rewindable = w->timestep == 0;
-    w->dworlds = dalloc<DevWorld>(w, w->R, false);
+    w->dworlds = dalloc<DevWorld>(w, R, false);
     if (!w->dworlds) return fail(w, UX_ERR_CUDA, "device allocation failed");
-    CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->R, cudaMemcpyHostToDevice, w->stream));
-    {
-        std::vector<unsigned long long> tab((size_t)4 * w->R);
-        for (int r = 0; r < w->R; r++) {
-            tab[r] = (unsigned long long)(uintptr_t)w->hw[r].t_base; tab[(size_t)w->R + r] = (unsigned long long)(uintptr_t)w->hw[r].tail;
-            tab[(size_t)2 * w->R + r] = (unsigned long long)(uintptr_t)w->hw[r].head; tab[(size_t)3 * w->R + r] = (unsigned long long)(uintptr_t)w->hw[r].pop_k2;
-        }
-        w->d_rl_tab = dupload(w, tab);
-        if (!w->d_rl_tab) return fail(w, UX_ERR_CUDA, "device allocation failed");
-    }
+    CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * R, cudaMemcpyHostToDevice, w->stream));
+    launch_init_dyn(w);
     CUDA_OK(cudaStreamSynchronize(w->stream));
     w->uploaded = true;
     w->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
@@ -646,6 +653,7 @@ static int extend_vehicles(ux_world *w) {
     if (!w->rep_routes.empty()) return fail(w, UX_ERR_RUNTIME, "adding vehicles to a world with per-replica routes is not supported");
     if (w->record_traversals) return fail(w, UX_ERR_RUNTIME, "adding vehicles after the start is not supported with UX_OPT_RECORD_TRAVERSALS (the traversal log is sized at upload)");
     w->rewindable = false;  // the per-platoon arrays move out of the recorded dynamic region
+    w->uniform = false;
 #ifndef UX_EMU
     for (auto &g : w->graphs) cudaGraphExecDestroy(g.second.first);  // kernel choices (link-update form, lane groups) depend on the platoon count
     w->graphs.clear();
@@ -686,6 +694,7 @@ static int extend_vehicles(ux_world *w) {
     for (long long i = P0; i < P; i++) extra_log += std::max(0, T - w->eff_ts[i] - 1);
     for (int r = 0; r < w->R; r++) {
         DevWorld &d = w->hw[r];
+        d.rep_stride = 0;  // the regrown per-platoon arrays are separate allocations: the replica-lane kernels are off for this world
         d.P = P; d.v_orig = d_orig; d.v_dest = d_dest; d.v_depart_ts = d_ts; d.gen_off = d_goff; d.gen_list = d_glist; d.gen_ts = d_gts;
         for (int kind = 0; kind < 3; kind++) { d.vl_off[kind] = vl_off[kind]; d.vl_list[kind] = vl_list[kind]; }
         d.v_state = dgrow(w, d.v_state, P0, P, 0); d.v_next = dgrow(w, d.v_next, P0, P, 0); d.v_link = dgrow(w, d.v_link, P0, P, 0xff);

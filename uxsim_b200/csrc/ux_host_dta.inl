@@ -310,6 +310,7 @@ UX_API int ux_dta_next_day(ux_world *w) {
         else if (ri.kind == 1) { long long n = (long long)(ri.bytes / 8); UX_LAUNCH(k_fill_f64, dim3((unsigned)((n + 255) / 256)), dim3(256), st, (double *)ri.dst, n, -1.0); }
         else cudaMemcpyAsync(ri.dst, ri.src->data(), ri.bytes, cudaMemcpyHostToDevice, st);
     }
+    launch_init_dyn(w);  // capacity tokens, signal phases / clocks, node tokens of every replica
     for (int r = 0; r < w->R && r < (int)w->next_routes.size(); r++) {
         auto &NR = w->next_routes[r];
         if (!NR.ready) continue;

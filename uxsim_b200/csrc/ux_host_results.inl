@@ -2,12 +2,12 @@
 // C-ABI, part 3: scalar queries, per-platoon logs, array sizes, device-side array production.
 
 static int64_t get_log_array(ux_world *w, int what, int replica, void *dst, int64_t capacity, int *dtype, bool size_only);
-static long long dsum_ll(ux_world *w, const long long *d, int n) {
-    std::vector<long long> h(n); if (n) cudaMemcpy(h.data(), d, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+static long long dsum_ll(ux_world *w, const long long *first, int n) {
+    std::vector<long long> h; fetch_field(w, first, sizeof(long long), n, h);
     long long s = 0; for (auto v : h) s += v; return s;
 }
-static long long dsum_i(ux_world *w, const int *d, int n) {
-    std::vector<int> h(n); if (n) cudaMemcpy(h.data(), d, sizeof(int) * n, cudaMemcpyDeviceToHost);
+static long long dsum_i(ux_world *w, const int *first, int n) {
+    std::vector<int> h; fetch_field(w, first, sizeof(LinkC), n, h);
     long long s = 0; for (auto v : h) s += v; return s;
 }
 
@@ -21,12 +21,12 @@ UX_API int64_t ux_get_int(ux_world *w, int what) {
     case UX_I_NUM_REPLICAS: return w->R;
     case UX_I_ROUTE_UPDATE_STEPS: return w->route_ts;
     case UX_I_PLATOON_UPDATES: return w->uploaded ? dsum_ll(w, w->hw[0].stat_count, (int)w->links.size()) : 0;
-    case UX_I_TRIPS_COMPLETED: return w->uploaded ? dsum_i(w, w->hw[0].trips, (int)w->links.size()) : 0;
+    case UX_I_TRIPS_COMPLETED: return w->uploaded ? dsum_i(w, &LC(w->hw[0], 0).trips, (int)w->links.size()) : 0;
     case UX_I_LOG_ENTRIES: { if (!w->uploaded || !w->p.vehicle_log_mode) return 0; int dt_; return get_log_array(w, UX_A_LOG_T, 0, nullptr, 0, &dt_, true); }
     case UX_I_KERNEL_LAUNCHES: return w->launches;
     case UX_I_NUM_ACTIVE_DESTS: return w->n_active;
     case UX_I_TRANSFER_LEVELS: return w->n_levels;
-    case UX_I_LINK_EVENTS: return w->uploaded ? dsum_i(w, w->hw[0].ev_cnt, (int)w->links.size()) : 0;
+    case UX_I_LINK_EVENTS: return w->uploaded ? dsum_i(w, &LC(w->hw[0], 0).ev_cnt, (int)w->links.size()) : 0;
     case UX_I_H2D_BYTES: return w->h2d_bytes;
     case UX_I_D2H_BYTES: return w->d2h_bytes;
     case UX_I_RING_SLOTS: return w->C;
@@ -229,15 +229,6 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     return n;
 }
 
-static int ensure_scratch(ux_world *w, size_t bytes) {
-    if (bytes <= w->scratch_bytes) return 0;
-    size_t want = std::max(bytes, std::max<size_t>(2 * w->scratch_bytes, (size_t)4 << 20));  // from the slabs: no driver allocation in steady state
-    char *p = dalloc<char>(w, want, false);
-    if (!p) return fail(w, UX_ERR_CUDA, "device allocation failed (%zu bytes of scratch)", want);
-    w->d_scratch = (double *)p; w->scratch_bytes = want;
-    return 0;
-}
-
 // Produce the array `what` of `replica` in DEVICE memory in its ABI layout; *dptr is either state memory or scratch.
 static int64_t device_array(ux_world *w, int what, int replica, void **dptr, int *dtype) {
     int dt; int64_t n = ux_array_size(w, what, &dt);
@@ -253,12 +244,12 @@ static int64_t device_array(ux_world *w, int what, int replica, void **dptr, int
     auto transpose_d = [&](const double *src, int rows, int cols) -> int {
         int rc = ensure_scratch(w, sizeof(double) * (size_t)rows * cols + 16); if (rc) return rc;
         long long tot = (long long)rows * cols;
-        if (tot > 0) UX_LAUNCH(k_transpose<double>, dim3((unsigned)((tot + 255) / 256)), dim3(256), st, src, w->d_scratch, rows, cols);
+        if (tot > 0) UX_LAUNCH(k_transpose<double>, dim3((unsigned)((tot + 255) / 256)), dim3(256), st, src, w->d_scratch, rows, cols, d.RS);
         *dptr = w->d_scratch; return 0; };
     auto transpose_i = [&](const int *src, int rows, int cols) -> int {
         int rc = ensure_scratch(w, sizeof(int) * (size_t)rows * cols + 16); if (rc) return rc;
         long long tot = (long long)rows * cols;
-        if (tot > 0) UX_LAUNCH(k_transpose<int>, dim3((unsigned)((tot + 255) / 256)), dim3(256), st, src, (int *)w->d_scratch, rows, cols);
+        if (tot > 0) UX_LAUNCH(k_transpose<int>, dim3((unsigned)((tot + 255) / 256)), dim3(256), st, src, (int *)w->d_scratch, rows, cols, d.RS);
         *dptr = w->d_scratch; return 0; };
     int rc = 0;
     switch (what) {
@@ -283,10 +274,10 @@ static int64_t device_array(ux_world *w, int what, int replica, void **dptr, int
     case UX_A_VEH_ORIG: *dptr = (void *)d.v_orig; break;
     case UX_A_VEH_DEST: *dptr = (void *)d.v_dest; break;
     case UX_A_VEH_LINK: *dptr = d.v_link; break;
-    case UX_A_NODE_SIGNAL_PHASE: *dptr = d.sig_phase; break;
-    case UX_A_NODE_SIGNAL_T: *dptr = d.sig_t; break;
-    case UX_A_LINK_CAPACITY_IN_REMAIN: *dptr = d.cap_in_rem; break;
-    case UX_A_LINK_CAPACITY_OUT_REMAIN: *dptr = d.cap_out_rem; break;
+    case UX_A_NODE_SIGNAL_PHASE: *dptr = gather_device<int>(w, &NS(d, 0).sig_phase, sizeof(NodeS), N); break;
+    case UX_A_NODE_SIGNAL_T: *dptr = gather_device<double>(w, &NR(d, 0).sig_t, sizeof(NodeR), N); break;
+    case UX_A_LINK_CAPACITY_IN_REMAIN: *dptr = gather_device<double>(w, &LR(d, 0).cap_in_rem, sizeof(LinkR), L); break;
+    case UX_A_LINK_CAPACITY_OUT_REMAIN: *dptr = gather_device<double>(w, &LR(d, 0).cap_out_rem, sizeof(LinkR), L); break;
     case UX_A_VEH_X: case UX_A_VEH_V: case UX_A_VEH_LANE: {
         rc = ensure_scratch(w, (sizeof(double) * 2 + sizeof(int)) * (size_t)(P ? P : 1) + 64); if (rc) break;
         double *vx = w->d_scratch, *vv = vx + P; int *vl = (int *)(vv + P);

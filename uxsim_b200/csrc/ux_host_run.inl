@@ -28,11 +28,11 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
                 static const int rl_parts = [] { const char *e = getenv("UXSIM_B200_RL_PARTS"); return e ? atoi(e) : 4; }();
                 dim3 g_rl(((int)w->links.size() + UPD_RL_WARPS - 1) / UPD_RL_WARPS, (R + 31) / 32, w->p.vehicle_log_mode ? 1 : std::max(1, rl_parts));
 #ifdef UX_EMU
-                UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R, (int)w->links.size(), (const unsigned long long *)w->d_rl_tab);
+                UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R, (int)w->links.size());
 #else
                 const size_t rl_bytes = 32 * UPD_RL_STRIDE * 8;  // the replicas' DevWorld structs
                 if (s == 0) cudaFuncSetAttribute(k_update_rl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_bytes);  // per device
-                k_update_rl<<<g_rl, dim3(32 * UPD_RL_WARPS), rl_bytes, st>>>(w->dworlds, s, R, (int)w->links.size(), (const unsigned long long *)w->d_rl_tab);
+                k_update_rl<<<g_rl, dim3(32 * UPD_RL_WARPS), rl_bytes, st>>>(w->dworlds, s, R, (int)w->links.size());
 #endif
             }
             else if (w->upd_group == 16) UX_LAUNCH(k_update<16>, g_update, dim3(32 * UPD_WARPS), st, w->dworlds, s);
@@ -173,7 +173,7 @@ UX_API int ux_set_link_param(ux_world *w, int link, int field, double value) {
     }
     if (w->uploaded) {
         cudaSetDevice(w->device);
-        if (rem) for (int r = 0; r < w->R; r++) CUDA_OK(cudaMemcpy((field == UX_LINK_CAPACITY_OUT_REMAIN ? w->hw[r].cap_out_rem : w->hw[r].cap_in_rem) + link, &rv, sizeof(double), cudaMemcpyHostToDevice));
+        if (rem) for (int r = 0; r < w->R; r++) CUDA_OK(cudaMemcpy(field == UX_LINK_CAPACITY_OUT_REMAIN ? &LR(w->hw[r], link).cap_out_rem : &LR(w->hw[r], link).cap_in_rem, &rv, sizeof(double), cudaMemcpyHostToDevice));
         else w->net_dirty = true;
     }
     return 0;
@@ -209,13 +209,13 @@ UX_API int ux_set_node_signal(ux_world *w, int node, const double *sig, int nsig
         // the new plan restarts at phase 0 (the reference would index past the end of the list)
         w->sig_tables_dirty = true;
         for (int r = 0; r < w->R; r++) {
-            int ph = 0; CUDA_OK(cudaMemcpy(&ph, w->hw[r].sig_phase + node, sizeof(int), cudaMemcpyDeviceToHost));
-            if (ph >= nsig && phase < 0) { int z = 0; double zt = 0.0; CUDA_OK(cudaMemcpy(w->hw[r].sig_phase + node, &z, sizeof(int), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(w->hw[r].sig_t + node, &zt, sizeof(double), cudaMemcpyHostToDevice)); }
+            int ph = 0; CUDA_OK(cudaMemcpy(&ph, &NS(w->hw[r], node).sig_phase, sizeof(int), cudaMemcpyDeviceToHost));
+            if (ph >= nsig && phase < 0) { int z = 0; double zt = 0.0; CUDA_OK(cudaMemcpy(&NS(w->hw[r], node).sig_phase, &z, sizeof(int), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(&NR(w->hw[r], node).sig_t, &zt, sizeof(double), cudaMemcpyHostToDevice)); }
         }
     } else if (sig && nsig > 0) { int off = 0; for (int i = 0; i < node; i++) off += (int)w->nodes[i].sig.size(); CUDA_OK(cudaMemcpy(w->d_n_sig + off, sig, sizeof(double) * nsig, cudaMemcpyHostToDevice)); }
     for (int r = 0; r < w->R; r++) {
-        if (phase >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_phase + node, &phase, sizeof(int), cudaMemcpyHostToDevice));
-        if (sig_t >= 0) CUDA_OK(cudaMemcpy(w->hw[r].sig_t + node, &sig_t, sizeof(double), cudaMemcpyHostToDevice));
+        if (phase >= 0) CUDA_OK(cudaMemcpy(&NS(w->hw[r], node).sig_phase, &phase, sizeof(int), cudaMemcpyHostToDevice));
+        if (sig_t >= 0) CUDA_OK(cudaMemcpy(&NR(w->hw[r], node).sig_t, &sig_t, sizeof(double), cudaMemcpyHostToDevice));
     }
     return 0;
 }

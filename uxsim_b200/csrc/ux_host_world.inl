@@ -38,7 +38,8 @@ struct ux_world {
     std::vector<Slab> slabs;     // state memory (returned to the slab cache)
     std::vector<DevWorld> hw;  // host copies of the per-replica device worlds
     DevWorld *dworlds = nullptr;
-    unsigned long long *d_rl_tab = nullptr;  // [4][R] pointers (t_base, tail, head, pop_k2) for k_update_rl's helper blocks
+    const double *d_init_co = nullptr, *d_init_ci = nullptr, *d_init_st = nullptr, *d_init_fc = nullptr; const int *d_init_ph = nullptr;  // initial tokens / signal state (k_init_dyn)
+    bool uniform = false;  // the replica-major arrays of replica r sit at replica 0's + r * rep_stride (what the replica-lane kernels need)
     int n_levels = 1, n_active = 0;
     long long launches = 0, C = 0; int nseg = 0, n_edges = 0;
     std::vector<int> dest_row, row_dest;
@@ -206,6 +207,33 @@ static T *dgrow(ux_world *w, T *old, size_t oldn, size_t newn, int fill_byte) {
     if (fill_byte) cudaMemsetAsync(p, fill_byte, (newn ? newn : 1) * sizeof(T), w->stream);
     if (old && oldn) cudaMemcpyAsync(p, old, oldn * sizeof(T), cudaMemcpyDeviceToDevice, w->stream);
     return p;
+}
+
+static int ensure_scratch(ux_world *w, size_t bytes) {
+    if (bytes <= w->scratch_bytes) return 0;
+    size_t want = std::max(bytes, std::max<size_t>(2 * w->scratch_bytes, (size_t)4 << 20));  // from the slabs: no driver allocation in steady state
+    char *p = dalloc<char>(w, want, false);
+    if (!p) return fail(w, UX_ERR_CUDA, "device allocation failed (%zu bytes of scratch)", want);
+    w->d_scratch = (double *)p; w->scratch_bytes = want;
+    return 0;
+}
+
+// One member of a replica-minor record array, for one replica, as a contiguous DEVICE array in scratch: `first` = address of the
+// member in entity 0 (e.g. &LQ(d, 0).tail), consecutive entities are RS records apart.
+template <typename T>
+static T *gather_device(ux_world *w, const void *first, size_t rec_bytes, long long n, size_t scratch_off = 0) {
+    if (ensure_scratch(w, scratch_off + sizeof(T) * (size_t)(n > 0 ? n : 1) + 16)) return nullptr;
+    T *out = (T *)((char *)w->d_scratch + scratch_off);
+    if (n > 0) UX_LAUNCH(k_gather<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), w->stream, (const char *)first, rec_bytes * (size_t)w->hw[0].RS, n, out);
+    return out;
+}
+template <typename T>
+static bool fetch_field(ux_world *w, const void *first, size_t rec_bytes, long long n, std::vector<T> &h) {
+    h.resize((size_t)n);
+    T *d = gather_device<T>(w, first, rec_bytes, n);
+    if (!d) return false;
+    if (n > 0 && cudaMemcpyAsync(h.data(), d, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) return false;
+    return cudaStreamSynchronize(w->stream) == cudaSuccess;
 }
 
 namespace {

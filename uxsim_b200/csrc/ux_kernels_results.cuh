@@ -4,13 +4,37 @@
 // ---------------------------------------------------------------------------------------------------
 // result kernels (off the hot path)
 // ---------------------------------------------------------------------------------------------------
-// [T][L] -> [L][T]
+// [T][L][RS] (one replica's column of a replica-minor series) -> [L][T] contiguous
 template <typename T>
-__global__ void k_transpose(const T *src, T *dst, int rows, int cols) {
+__global__ void k_transpose(const T *src, T *dst, int rows, int cols, int RS) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * cols) return;
     int r = (int)(idx / cols), c = (int)(idx % cols);
-    dst[(size_t)c * rows + r] = src[idx];
+    dst[(size_t)c * rows + r] = src[(size_t)idx * RS];
+}
+// one member of a replica-minor record array -> contiguous: dst[i] = the T at src + i * stride bytes
+template <typename T>
+__global__ void k_gather(const char *src, size_t stride, long long n, T *dst) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = *reinterpret_cast<const T *>(src + (size_t)i * stride);
+}
+// ... the same member of ALL replicas, replica-major: dst[r * n + i] = the T at src + (i * RS + r) * rec bytes
+template <typename T>
+__global__ void k_gather_all(const char *src, size_t rec, int RS, int R, long long n, T *dst) {
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * R) return;
+    long long i = q / R; int r = (int)(q % R);
+    dst[(size_t)r * n + i] = *reinterpret_cast<const T *>(src + ((size_t)i * RS + r) * rec);
+}
+
+// initial capacity tokens and signal state of every (link, replica) / (node, replica): thread index = entity * R + replica
+__global__ void k_init_dyn(const DevWorld *worlds, int R, const double *co, const double *ci, const int *ph, const double *st, const double *fc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)(worlds[0].L + worlds[0].N) * R) return;
+    const DevWorld &W = worlds[(int)(i % R)];
+    long long e = i / R;
+    if (e < W.L) { LR(W, e).cap_out_rem = co[e]; LR(W, e).cap_in_rem = ci[e]; }
+    else if (e < (long long)W.L + W.N) { long long n = e - W.L; NS(W, n).sig_phase = ph[n]; NR(W, n).sig_t = st[n]; NR(W, n).fc_rem = fc[n]; }
 }
 
 // Link::ensure_traveltime_real (traffi.cpp:631-648): position i takes the value of the latest event whose entry step <= i.
@@ -49,7 +73,7 @@ __global__ void k_veh_snapshot(const DevWorld *worlds, int replica, double *vx, 
     if (gw >= W.nseg) return;
     int l = W.seg_link[gw], part = W.seg_start[gw] & 0xffff, nparts = W.seg_start[gw] >> 16, cap = W.l_rcap[l];
     int cur = *W.t_base & 1;
-    int hd = W.head[cur * W.L + l], n = W.tail[l] - hd;
+    int hd = LQ(W, l).head[cur], n = LQ(W, l).tail - hd;
     long long o = W.l_roff[l];
     for (int pos = part * 32 + lane; pos < n; pos += nparts * 32) {
         int p = ring_slot(hd, pos, cap);
@@ -77,7 +101,7 @@ __global__ void k_ensemble_partial(const DevWorld *worlds, double *part) {
     }
     double *o = part + ((size_t)blockIdx.y * L + l) * 4;
     o[0] = T > 0 ? W.cum_arr[TLI(W, (T - 1), l)] : 0.0; o[1] = s1; o[2] = s2;
-    o[3] = (double)(W.tail[l] - W.head[(*W.t_base & 1) * L + l]);
+    o[3] = (double)(LQ(W, l).tail - LQ(W, l).head[*W.t_base & 1]);
 }
 __global__ void k_ensemble_stats(const DevWorld *worlds, int R, const double *part, double *out) {
     int L = worlds[0].L;

@@ -8,17 +8,17 @@
 // Node::signal_update (traffi.cpp:194-207) and Node::flow_capacity_update (226-234) of node n at step t
 UX_DEV void node_signal_capacity(const DevWorld &W, int n, int t) {
     int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
-    int ph = W.sig_phase[n];
+    int ph = NS(W, n).sig_phase;
     if (nsig > 1) {
-        double st = W.sig_t[n];
+        double st = NR(W, n).sig_t;
         if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
         st += W.dt;
-        W.sig_t[n] = st; W.sig_phase[n] = ph;
+        NR(W, n).sig_t = st; NS(W, n).sig_phase = ph;
     }
     W.sig_log[TNI(W, t, n)] = ph;
     double fc = W.n_fc[n];
-    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (W.fc_rem[n] < W.dn * (nl > 0 ? nl : 1)) W.fc_rem[n] += fc * W.dt; }
-    else W.fc_rem[n] = 10e10;
+    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (NR(W, n).fc_rem < W.dn * (nl > 0 ? nl : 1)) NR(W, n).fc_rem += fc * W.dt; }
+    else NR(W, n).fc_rem = 10e10;
 }
 
 template <int MC, int MD>
@@ -40,7 +40,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     if (fresh) {
         for (int k = 0; k < nout; k++) {
             int l = W.n_out[o0 + k];
-            int hd = W.head[cur * L + l], nq = W.tail[l] - hd;
+            int hd = LQ(W, l).head[cur], nq = LQ(W, l).tail - hd;
             double tt;
             if (nq > 0) {
                 double vs = warp_queue_vsum(W, l, hd, nq, lane);
@@ -70,22 +70,22 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
             else if (t > 0) W.tt_inst[row] = W.tt_inst[prev];
             if (t != 0) W.cum_arr[row] = W.cum_arr[prev];
             double ci = W.l_cap_in[l];
-            if (ci < 10e9) { if (W.cap_in_rem[l] < W.dn * W.l_lanes[l]) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+            if (ci < 10e9) { if (LR(W, l).cap_in_rem < W.dn * W.l_lanes[l]) LR(W, l).cap_in_rem += ci * W.dt; } else LR(W, l).cap_in_rem = 10e9;
         }
         for (int k = ln; k < nin; k += 32) {
             int l = W.n_in[i0 + k];
             size_t row = TLI(W, t, l);
             if (t != 0) W.cum_dep[row] = W.cum_dep[TLI(W, t - 1, l)];
             double co = W.l_cap_out[l];
-            if (co < 10e9) { if (W.cap_out_rem[l] < W.dn * W.l_lanes[l]) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
-            W.pop_k2[l] = 0;
+            if (co < 10e9) { if (LR(W, l).cap_out_rem < W.dn * W.l_lanes[l]) LR(W, l).cap_out_rem += co * W.dt; } else LR(W, l).cap_out_rem = 10e9;
+            LC(W, l).pop_k2 = 0;
         }
     }
     WARP_SYNC();
     }
     // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
     //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
-    int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = W.gen_avail[n];
+    int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = NS(W, n).gen_avail;
     while (av < glen) {
         WARP_FOR(ln) if (ln == 0) *rel = 0;
         WARP_SYNC();
@@ -98,7 +98,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     }
     // ---- generate (traffi.cpp:105-189).  The route draws of the first `natt` waiting platoons and the tail state of the
     //      out-links are fetched in parallel; lane 0 then walks the attempts on shared memory and stops at the first refusal.
-    int gh = W.gen_head[n];
+    int gh = NS(W, n).gen_head;
     int natt = av - gh;
     { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > MC) natt = MC; }
     if (nout == 0) natt = 0;
@@ -112,9 +112,9 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
             }
             for (int q = ln; q < nout; q += 32) {
                 int ol = W.n_out[o0 + q];
-                int hd = W.head[cur * L + ol], tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+                int hd = LQ(W, ol).head[cur], tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
                 long long o = W.l_roff[ol];
-                double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
+                double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
                 int sz = tl - hd;
                 int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
                 G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
@@ -173,21 +173,21 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
                 G.o_cumarr[q] += W.dn;
                 G.o_ci[q] -= W.dn;
             }
-            W.gen_head[n] = gh;
+            NS(W, n).gen_head = gh;
         }
         WARP_SYNC();
         WARP_FOR(ln) {
             for (int q = ln; q < nout; q += 32) {
                 int ol = W.n_out[o0 + q];
-                W.cap_in_rem[ol] = G.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = G.o_cumarr[q]; W.tail[ol] = G.o_tail[q];
+                LR(W, ol).cap_in_rem = G.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = G.o_cumarr[q]; LQ(W, ol).tail = G.o_tail[q];
             }
         }
         WARP_SYNC();
     }
     // tail after generation (the link update tells transfer pushes from generated ones): k_link_pre already copied the unchanged tails
-    if (!W.pre_split || natt > 0) WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; W.tail_k1[l] = W.tail[l]; } }
+    if (!W.pre_split || natt > 0) WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; LQ(W, l).tail_k1 = LQ(W, l).tail; } }
     WARP_FOR(ln) if (ln == 0) {
-        W.gen_avail[n] = av;
+        NS(W, n).gen_avail = av;
         if (!W.pre_split) node_signal_capacity(W, n, t);
     }
     WARP_SYNC();
@@ -261,19 +261,19 @@ template <int MC, int MD>
 UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
     int cur = t & 1, L = W.L;
     size_t C = (size_t)W.C;
-    if (W.node_act[n] != t) return;  // no in-link of this node has a flagged head position (hcount == 0 everywhere): nothing to do
+    if (NS(W, n).node_act != t) return;  // no in-link of this node has a flagged head position (hcount == 0 everywhere): nothing to do
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     if (nin == 0) return;
-    int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = W.sig_phase[n];
+    int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = NS(W, n).sig_phase;
     // ---- A1: in-link state
     WARP_FOR(lane) {
         for (int ii = lane; ii < nin; ii += 32) {
             // loads first, shared stores afterwards: the pointers are generic, so a shared store between two loads
             // would serialise them (the compiler must assume the load may target shared memory)
             int il = W.n_in[i0 + ii];
-            int hd_ = W.head[cur * L + il], hc_ = W.hcount[il], cap_ = W.l_rcap[il], evc_ = W.ev_cnt[il], trips_ = W.trips[il];
+            int hd_ = LQ(W, il).head[cur], hc_ = LC(W, il).hcount, cap_ = W.l_rcap[il], evc_ = LC(W, il).ev_cnt, trips_ = LC(W, il).trips;
             long long roff_ = W.l_roff[il];
-            double co_ = W.cap_out_rem[il], mp_ = W.l_mp[il], vm_ = W.l_vmax[il], cd_ = W.cum_dep[TLI(W, t, il)];
+            double co_ = LR(W, il).cap_out_rem, mp_ = W.l_mp[il], vm_ = W.l_vmax[il], cd_ = W.cum_dep[TLI(W, t, il)];
             bool ok = true;
             if (nsig > 1) { int g0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - g0; ok = list_has(W.l_sg + g0, gl, phase); }
             S.il[ii] = il; S.hd[ii] = hd_; S.hc[ii] = hc_; S.cap[ii] = cap_; S.roff[ii] = roff_;
@@ -360,8 +360,8 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
         WARP_FOR(lane) {
             for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
                 int dep = W.dep_list[q];
-                if (W.node_act[dep] != t) continue;  // that node has nothing to transfer in this step: it pops nothing (and does not publish)
-                volatile int *done = W.node_done + dep;
+                if (NS(W, dep).node_act != t) continue;  // that node has nothing to transfer in this step: it pops nothing (and does not publish)
+                volatile int *done = &NDONE(W, dep);
 #ifdef UX_EMU
                 if (*done < t + 1) dev_error(W, DERR_DEP_TIMEOUT, n);
 #else
@@ -381,14 +381,14 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     WARP_FOR(lane) {
         for (int q = lane; q < nol; q += 32) {
             int ol = S.ol[q];
-            int hd = W.head[cur * L + ol], fl_ = W.l_flags[ol];
+            int hd = LQ(W, ol).head[cur], fl_ = W.l_flags[ol];
             // pops of this step by the link's end node (a lower level of this launch).  Only a node that transfers in this step
             // writes the count -- an idle end node may not even have reset last step's value yet (small worlds reset it inside
             // this launch, in that node's own pre_node), so its count is taken as 0 without reading it.
-            int pk_ = ((fl_ & LF_SEES_POPS) && W.node_act[W.l_end[ol]] == t) ? ld_cg(W.pop_k2 + ol) : 0;
-            int tl = W.tail[ol], lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+            int pk_ = ((fl_ & LF_SEES_POPS) && NS(W, W.l_end[ol]).node_act == t) ? ld_cg(&LC(W, ol).pop_k2) : 0;
+            int tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
             long long o = W.l_roff[ol];
-            double ci_ = W.cap_in_rem[ol], dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
+            double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
             if (fl_ & LF_SEES_POPS) hd += pk_;
             int sz = tl - hd;
             int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
@@ -448,7 +448,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     // draws nothing), so each round evaluates every out-link / candidate in parallel against the current state, jumps
     // to the first slot (in shuffled order) that moves a platoon, applies that one move on lane 0, and repeats.
     double fc = W.n_fc[n];
-    WARP_FOR(lane) if (lane == 0) { S.cur_slot = 0; S.n_picks = 0; S.fc_rem = W.fc_rem[n]; }
+    WARP_FOR(lane) if (lane == 0) { S.cur_slot = 0; S.n_picks = 0; S.fc_rem = NR(W, n).fc_rem; }
     WARP_SYNC();
     while (true) {
         WARP_FOR(lane) {
@@ -575,19 +575,19 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
                 xfer_end_trip(W, S, fp, t);
             }
         }
-        W.fc_rem[n] = S.fc_rem;
+        NR(W, n).fc_rem = S.fc_rem;
     }
     WARP_SYNC();
     // ---- C: write the per-link accumulators back
     WARP_FOR(lane) {
         for (int ii = lane; ii < nin; ii += 32) {
             int il = S.il[ii];
-            W.cap_out_rem[il] = S.co_rem[ii]; W.cum_dep[TLI(W, t, il)] = S.cumdep[ii];
-            W.pop_k2[il] = S.popped[ii]; W.ev_cnt[il] = S.evc[ii]; W.trips[il] = S.trips[ii];
+            LR(W, il).cap_out_rem = S.co_rem[ii]; W.cum_dep[TLI(W, t, il)] = S.cumdep[ii];
+            LC(W, il).pop_k2 = S.popped[ii]; LC(W, il).ev_cnt = S.evc[ii]; LC(W, il).trips = S.trips[ii];
         }
         for (int q = lane; q < nol; q += 32) {
             int ol = S.ol[q];
-            W.cap_in_rem[ol] = S.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = S.o_cumarr[q]; W.tail[ol] = S.o_tail[q];
+            LR(W, ol).cap_in_rem = S.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = S.o_cumarr[q]; LQ(W, ol).tail = S.o_tail[q];
         }
     }
 }
@@ -610,11 +610,11 @@ __global__ void __launch_bounds__(256) k_link_pre(const DevWorld *worlds, int st
         }
         double thr = W.dn * W.l_lanes[l];
         double ci = W.l_cap_in[l];
-        if (ci < 10e9) { if (W.cap_in_rem[l] < thr) W.cap_in_rem[l] += ci * W.dt; } else W.cap_in_rem[l] = 10e9;
+        if (ci < 10e9) { if (LR(W, l).cap_in_rem < thr) LR(W, l).cap_in_rem += ci * W.dt; } else LR(W, l).cap_in_rem = 10e9;
         double co = W.l_cap_out[l];
-        if (co < 10e9) { if (W.cap_out_rem[l] < thr) W.cap_out_rem[l] += co * W.dt; } else W.cap_out_rem[l] = 10e9;
-        W.pop_k2[l] = 0;
-        W.tail_k1[l] = W.tail[l];  // k_node rewrites it for the out-links of nodes that generate
+        if (co < 10e9) { if (LR(W, l).cap_out_rem < thr) LR(W, l).cap_out_rem += co * W.dt; } else LR(W, l).cap_out_rem = 10e9;
+        LC(W, l).pop_k2 = 0;
+        LQ(W, l).tail_k1 = LQ(W, l).tail;  // k_node rewrites it for the out-links of nodes that generate
     } else if (i < L + W.N) node_signal_capacity(W, i - L, t);
 }
 
@@ -651,9 +651,9 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
 #endif
     XferSmem<MC, MD> &S = sm_all[wib].xf;
     xfer_node(W, S, n, t, lvl > 0);
-    if ((lvl_raw >> 16) && W.node_act[n] == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes): the fence is not free
+    if ((lvl_raw >> 16) && NS(W, n).node_act == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes): the fence is not free
         WARP_SYNC();
-        WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)(W.node_done + n)) = t + 1; }
+        WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)&NDONE(W, n)) = t + 1; }
     }
 }
 
@@ -735,13 +735,13 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
     size_t C = (size_t)W.C;
     int cap = W.l_rcap[l];
     long long o = W.l_roff[l];
-    int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], tl = W.tail[l];
+    int hd0 = LQ(W, l).head[cur], pk2 = LC(W, l).pop_k2, tl = LQ(W, l).tail;
     int lanes = W.l_lanes[l];
     double len = W.l_length[l], udt = W.l_udt[l], dpl = W.l_dpl_dn[l];
     int hd = hd0 + pk2, n = tl - hd;
     int s0 = part;
     if (n == 0) {  // empty link: nothing moves, nothing is counted; only the double-buffered head is carried over
-        if (s0 == 0 && (threadIdx.x & (UPD_GROUP - 1)) == 0) { W.head[(cur ^ 1) * L + l] = hd; W.hcount[l] = 0; }
+        if (s0 == 0 && (threadIdx.x & (UPD_GROUP - 1)) == 0) { LQ(W, l).head[cur ^ 1] = hd; LC(W, l).hcount = 0; }
         return;
     }
     const double *Xc = W.X + (size_t)cur * C + o;
@@ -780,10 +780,10 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
         UPD_FOR(lane) if (lane == 0) {
             // lane relabel when the end node (smaller id) emptied the link before this step's pushes
             if ((W.l_flags[l] & LF_END_LT_START) && !(W.l_flags[l] & LF_SEES_POPS) && pk2 > 0) {
-                int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+                int n0 = LQ(W, l).tail_k1 - hd0, pushes = tl - LQ(W, l).tail_k1;
                 if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
             }
-            W.stat_count[l] += n;
+            LSTAT(W, l) += n;
             int k = 0, evc = 0, trips = 0, last_f = -1;
             double cumdep = 0.0;
             bool touched = false;
@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                     f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
                     if (kind == 2) W.v_next[vid] = -1;
                     if (k == j) {  // it is the front (everything ahead ended in this pass): end_trip, traffi.cpp:886-927
-                        if (!touched) { evc = W.ev_cnt[l]; trips = W.trips[l]; cumdep = W.cum_dep[TLI(W, t, l)]; touched = true; }
+                        if (!touched) { evc = LC(W, l).ev_cnt; trips = LC(W, l).trips; cumdep = W.cum_dep[TLI(W, t, l)]; touched = true; }
                         trips += 1; cumdep += W.dn;
                         double atl = H.atl[j];
                         int es = (int)(atl / W.dt);
@@ -817,12 +817,12 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
                 W.v_flags[vid] = f;
                 if (f) last_f = j;
             }
-            if (touched) { W.ev_cnt[l] = evc; W.trips[l] = trips; W.cum_dep[TLI(W, t, l)] = cumdep; }
-            W.head[(cur ^ 1) * L + l] = hd + k;
+            if (touched) { LC(W, l).ev_cnt = evc; LC(W, l).trips = trips; W.cum_dep[TLI(W, t, l)] = cumdep; }
+            LQ(W, l).head[cur ^ 1] = hd + k;
             // head positions the next transfer has to look at: up to the last one that is a candidate or waits for its trip
             // end (everything behind it is mid-link), counted from the new head -- 0 for most links in most steps
-            W.hcount[l] = last_f >= 0 ? last_f - k + 1 : 0;
-            if (last_f >= 0) W.node_act[end_node] = t + 1;  // the end node has something to transfer next step (same value from every in-link)
+            LC(W, l).hcount = last_f >= 0 ? last_f - k + 1 : 0;
+            if (last_f >= 0) NS(W, end_node).node_act = t + 1;  // the end node has something to transfer next step (same value from every in-link)
             H.k_ended = k;
         }
 
@@ -897,7 +897,7 @@ UX_DEV void upd_head_position(const DevWorld &W, HeadState &H, int l, int t, int
         f = kind == 1 ? VF_WAIT_END : (VF_WAIT_END | VF_ABORT);
         if (kind == 2) W.v_next[vid] = -1;
         if (H.k == j) {
-            if (!H.touched) { H.evc = W.ev_cnt[l]; H.trips = W.trips[l]; H.cumdep = W.cum_dep[TLI(W, t, l)]; H.touched = true; }
+            if (!H.touched) { H.evc = LC(W, l).ev_cnt; H.trips = LC(W, l).trips; H.cumdep = W.cum_dep[TLI(W, t, l)]; H.touched = true; }
             H.trips += 1; H.cumdep += W.dn;
             double atl = W.v_atl[vid];
             int es = (int)(atl / W.dt);
@@ -939,9 +939,7 @@ UX_DEV int upd_head_decide(const DevWorld &W, int t, int vid, double x, double u
     return kind;
 }
 
-// `tab` = [4][R] device pointers (t_base, tail, head, pop_k2 of every replica, replica fastest): what a helper block needs to
-// decide whether it has work, readable with coalesced loads instead of through 32 DevWorld structs.
-__global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld *worlds, int step_off, int R, int L_all, const unsigned long long *tab) {
+__global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld *worlds, int step_off, int R, int L_all) {
     int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
     int r = (int)blockIdx.y * 32 + lane, l = (int)blockIdx.x * UPD_RL_WARPS + warp;
     // blockIdx.z > 0: helper blocks for long queues -- they take every gridDim.z-th pass of the car-following list and leave
@@ -955,11 +953,11 @@ __global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld 
 #else
     if (part > 0) {
         int n_q = 0;
-        if (r < R && l < L_all) {
-            const int *tb = reinterpret_cast<const int *>(tab[r]), *tl_ = reinterpret_cast<const int *>(tab[R + r]);
-            const int *hd_ = reinterpret_cast<const int *>(tab[2 * R + r]), *pk_ = reinterpret_cast<const int *>(tab[3 * R + r]);
-            int cur_ = (*tb + step_off) & 1;
-            n_q = tl_[l] - (hd_[cur_ * L_all + l] + pk_[l]);
+        if (r < R && l < L_all) {  // the queue counters are replica-minor: the lanes' loads are one contiguous row
+            const DevWorld &W0 = worlds[0];
+            int cur_ = (*W0.t_base + step_off) & 1;
+            size_t e = (size_t)l * (size_t)W0.RS + (size_t)r;
+            n_q = W0.lq[e].tail - (W0.lq[e].head[cur_] + W0.lc[e].pop_k2);
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) n_q += __shfl_xor_sync(0xffffffffu, n_q, d);
@@ -988,17 +986,17 @@ __global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld 
     bool dead_end = W.n_out_off[end_node + 1] == W.n_out_off[end_node];
     int hd = 0, n = 0, hc = 0;
     if (active) {
-        int hd0 = W.head[cur * L + l], pk2 = W.pop_k2[l], tl = W.tail[l];
+        int hd0 = LQ(W, l).head[cur], pk2 = LC(W, l).pop_k2, tl = LQ(W, l).tail;
         hd = hd0 + pk2; n = tl - hd;
         if (part == 0) { hc = n < lanes ? n : lanes; if (hc > UX_MAXLANE) hc = UX_MAXLANE; }
         if (part == 0 && pk2 > 0) {  // lane relabel when the end node (smaller id) emptied the link before this step's pushes
             int fl = W.l_flags[l];
             if ((fl & LF_END_LT_START) && !(fl & LF_SEES_POPS)) {
-                int n0 = W.tail_k1[l] - hd0, pushes = tl - W.tail_k1[l];
+                int n0 = LQ(W, l).tail_k1 - hd0, pushes = tl - LQ(W, l).tail_k1;
                 if (pk2 == n0 && pushes > 0) for (int j = 0; j < pushes; j++) W.LANE[o + ring_slot(hd, j, cap)] = j % lanes;
             }
         }
-        if (part == 0 && n > 0) W.stat_count[l] += n;
+        if (part == 0 && n > 0) LSTAT(W, l) += n;
     }
     HeadState H = {0, 0, 0, -1, 0.0, false};
 #ifdef UX_EMU
@@ -1047,10 +1045,10 @@ __global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld 
     }
 #endif
     if (active && part == 0) {
-        if (H.touched) { W.ev_cnt[l] = H.evc; W.trips[l] = H.trips; W.cum_dep[TLI(W, t, l)] = H.cumdep; }
-        W.head[(cur ^ 1) * L + l] = hd + H.k;
-        W.hcount[l] = H.last_f >= 0 ? H.last_f - H.k + 1 : 0;  // as in k_update
-        if (H.last_f >= 0) W.node_act[end_node] = t + 1;
+        if (H.touched) { LC(W, l).ev_cnt = H.evc; LC(W, l).trips = H.trips; W.cum_dep[TLI(W, t, l)] = H.cumdep; }
+        LQ(W, l).head[cur ^ 1] = hd + H.k;
+        LC(W, l).hcount = H.last_f >= 0 ? H.last_f - H.k + 1 : 0;  // as in k_update
+        if (H.last_f >= 0) NS(W, end_node).node_act = t + 1;
         if (W.log_mode) {  // positions that may have a just-ended leader, now that the ended count is known
             int nlog = n < 2 * lanes ? n : 2 * lanes;
             for (int pos = 0; pos < nlog; pos++) log_run_record(W, l, t, cur, hd, n, pos, cap, o, lanes, len, udt, dpl, H.k, 0);

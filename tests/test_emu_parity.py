@@ -79,6 +79,34 @@ def test_emulated_update_lane_groups(name, mk, emu_api, oracle_api, monkeypatch)
     assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
 
 
+RL_CASES = [("short_chain", S.short_links_chain), ("3lane", S.multilane_3lane), ("dead_end", S.dead_end), ("lane_drop", S.lane_drop_2to1),
+            ("merge_stochastic", lambda: S.merge_y(hard_deterministic_mode=False, random_seed=3)),
+            ("grid6_signals", lambda: S.grid(n=6, seed=5, tmax=3000, demand_t=1200, signals=True)), ("siouxfalls", lambda: S.sioux_falls(seed=1)),
+            ("dta_grid9", lambda: S.dta_grid9(seed=1)), ("gradual", lambda: S.grid(n=5, seed=4, tmax=3000, demand_t=1000, route_choice_update_gradual=True))]
+
+
+@pytest.mark.parametrize("name,mk", RL_CASES, ids=[c[0] for c in RL_CASES])
+def test_emulated_replica_lane_node_kernel(name, mk, emu_api, oracle_api, monkeypatch):
+    """k_link_pre<true> + k_node_rl (thread per node and replica; what ensembles of >= 32 replicas run) forced on single
+    scenarios, together with the replica-lane link update: same results, same logs."""
+    monkeypatch.setenv("UXSIM_B200_NODE", "rl")
+    monkeypatch.setenv("UXSIM_B200_UPDATE", "rl")
+    Ee, Eo = run_pair(mk(), emu_api, oracle_api, vehicle_logging_timestep_interval=1)
+    assert compare_engines(Ee, Eo) == [] and compare_logs(Ee, Eo) == []
+
+
+def test_emulated_replica_lane_node_kernel_levels_and_ragged_groups(emu_api, oracle_api, monkeypatch):
+    """Chicago sketch (4 dependency levels) with 35 replicas = one full lane group + a ragged one; first 900 s; replicas 0, 31, 34."""
+    sc = S.chicago_sketch(seed=0)
+    Ee = sc.to_engine(emu_api, vehicle_logging_timestep_interval=-1, num_replicas=35)
+    Ee.main_loop(until_t=900)
+    assert Ee.get_int(C.I_TRANSFER_LEVELS) == 4
+    for r in (0, 31, 34):
+        Eo = sc.to_engine(oracle_api, vehicle_logging_timestep_interval=-1, random_seed=r)
+        Eo.main_loop(until_t=900)
+        assert compare_engines(Ee, Eo, replica_a=r) == [], f"replica {r}"
+
+
 def test_all_replica_getter_matches_per_replica(emu_api):
     """get_array(replica=-1): [R, n] in one transfer == the per-replica getters."""
     from uxsim_b200 import _capi as C

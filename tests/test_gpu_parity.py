@@ -332,3 +332,48 @@ def test_c4_full_size_against_oracle(cuda_api, oracle_api):
     assert Eg.get_int(C.I_PLATOON_UPDATES) == Eo.get_int(C.I_PLATOON_UPDATES) > 9e6
     assert compare_engines(Eg, Eo) == []
     Eg.close(); Eo.close()
+
+
+RL_NODE_CASES = [("short_chain", S.short_links_chain, 1), ("3lane", S.multilane_3lane, 1), ("dead_end", S.dead_end, 1),
+                 ("grid6_signals", dict(STOCHASTIC)["grid6_signals"], 1), ("siouxfalls", dict(STOCHASTIC)["siouxfalls"], 1),
+                 ("chicago_dn30", dict(STOCHASTIC)["chicago_dn30"], 1), ("chicago_dn5", lambda: S.chicago_sketch(deltan=5, seed=0, tmax=2500), -1),
+                 ("gradual_duo", dict(STOCHASTIC)["gradual_duo"], 1)]
+
+
+@pytest.mark.parametrize("name,mk,log", RL_NODE_CASES, ids=[c[0] for c in RL_NODE_CASES])
+def test_replica_lane_node_kernel_forced(name, mk, log, cuda_api, oracle_api, monkeypatch):
+    """k_link_pre<true> + k_node_rl (thread per node and replica) forced on single scenarios (one live lane per warp), logs on:
+    bit-identical to the oracle incl. the multi-level Chicago sketch and its long queues at deltan = 5."""
+    monkeypatch.setenv("UXSIM_B200_NODE", "rl")
+    Eg, Eo = run_pair(mk(), cuda_api, oracle_api, vehicle_logging_timestep_interval=log)
+    assert compare_engines(Eg, Eo) == []
+    if log == 1:
+        assert compare_logs(Eg, Eo) == []
+
+
+@pytest.mark.parametrize("name,R", [("chicago_dn30", 35), ("grid6_signals", 64), ("siouxfalls", 33), ("grid11", 32)])
+def test_replica_lane_node_kernel_ensembles(name, R, cuda_api, oracle_api):
+    """From 32 replicas the engine picks the replica-lane node step by itself (ragged lane groups included): every checked
+    replica equals the single-seed oracle run; and forcing the warp-per-node kernel on the same ensemble gives the same bits."""
+    sc = dict(STOCHASTIC)[name]()
+    seed0 = sc.world.get("random_seed", 0) or 0
+    Eg = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1, num_replicas=R)
+    Eg.main_loop()
+    for r in sorted({0, 1, 31, R - 1}):
+        Eo = sc.to_engine(oracle_api, vehicle_logging_timestep_interval=-1, random_seed=seed0 + r)
+        Eo.main_loop()
+        assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"
+        Eo.close()
+    Eg.close()
+
+
+def test_node_kernel_forms_agree_on_an_ensemble(cuda_api, monkeypatch):
+    sc = dict(STOCHASTIC)["chicago_dn30"]()
+    Es = []
+    for mode in ("rl", "warp"):
+        monkeypatch.setenv("UXSIM_B200_NODE", mode)
+        E = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1, num_replicas=40)
+        E.main_loop()
+        Es.append(E)
+    for r in (0, 17, 39):
+        assert compare_engines(Es[0], Es[1], replica_a=r, replica_b=r) == []

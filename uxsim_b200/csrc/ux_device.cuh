@@ -31,6 +31,7 @@ struct DevWorld {
     int nseg;
     double dn, dt, duo_w, duo_time, noise;
     int itt, route_ts, hard_det, gradual, no_cyclic, log_mode;
+    int node_rl;    // the node step runs in replica-lane form (k_node_rl): k_link_pre then also measures the mean-speed travel times
     int pre_split;  // the scalar link / node bookkeeping of a step runs in k_link_pre (large worlds) instead of inside k_node
     long long seed;
     // static network (shared by all replicas)

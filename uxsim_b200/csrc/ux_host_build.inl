@@ -352,6 +352,10 @@ static int upload(ux_world *w) {
         const char *e = getenv("UXSIM_B200_PRE_SPLIT");
         w->pre_split = e ? atoi(e) != 0 : ((long long)(L + N) * w->R >= 40000);
         base.pre_split = w->pre_split ? 1 : 0;
+        const char *e2 = getenv("UXSIM_B200_NODE");  // rl | warp
+        w->node_rl = e2 ? !strcmp(e2, "rl") : w->R >= 32;
+        base.node_rl = w->node_rl ? 1 : 0;
+        if (w->node_rl) { w->pre_split = true; base.pre_split = 1; }  // the scalar bookkeeping always runs in k_link_pre<true> then
     }
     base.vis_words = (N + 31) / 32;
     // ---- links
@@ -694,7 +698,7 @@ static int extend_vehicles(ux_world *w) {
     for (long long i = P0; i < P; i++) extra_log += std::max(0, T - w->eff_ts[i] - 1);
     for (int r = 0; r < w->R; r++) {
         DevWorld &d = w->hw[r];
-        d.rep_stride = 0;  // the regrown per-platoon arrays are separate allocations: the replica-lane kernels are off for this world
+        d.rep_stride = 0; d.node_rl = 0;  // the regrown per-platoon arrays are separate allocations: the replica-lane node kernel is off for this world
         d.P = P; d.v_orig = d_orig; d.v_dest = d_dest; d.v_depart_ts = d_ts; d.gen_off = d_goff; d.gen_list = d_glist; d.gen_ts = d_gts;
         for (int kind = 0; kind < 3; kind++) { d.vl_off[kind] = vl_off[kind]; d.vl_list[kind] = vl_list[kind]; }
         d.v_state = dgrow(w, d.v_state, P0, P, 0); d.v_next = dgrow(w, d.v_next, P0, P, 0); d.v_link = dgrow(w, d.v_link, P0, P, 0xff);

@@ -13,8 +13,20 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
     const char *upd_env = getenv("UXSIM_B200_UPDATE");
     bool update_rl = upd_env ? !strcmp(upd_env, "rl") : (R >= 64 && (long long)w->vehs.size() <= 32ll * (long long)w->links.size());
     for (int s = 0; s < nsteps; s++) {
-        if (w->pre_split) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre, dim3(((unsigned)w->links.size() + (unsigned)N + 255) / 256, R), dim3(256), st, w->dworlds, s); KT_END(UX_K_PRE) lc++; }
-        if (N > 0) {
+        // Ensembles (from 32 replicas): the node step in replica-lane form -- k_link_pre<true> (warp = one link / node in 32 replicas,
+        // incl. the mean-speed travel times) + k_node_rl (thread per node and replica).  Otherwise warp-per-node k_node, with the scalar
+        // bookkeeping peeled into k_link_pre<false> for large worlds.
+        const bool node_rl = w->node_rl && w->uniform;
+        if (node_rl) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre<true>, dim3((((unsigned)w->links.size() + (unsigned)N) * 32u + 255u) / 256u, (R + 31) / 32), dim3(256), st, w->dworlds, s, R); KT_END(UX_K_PRE) lc++; }
+        else if (w->pre_split) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre<false>, dim3(((unsigned)w->links.size() + (unsigned)N + 255) / 256, R), dim3(256), st, w->dworlds, s, R); KT_END(UX_K_PRE) lc++; }
+        if (N > 0 && node_rl) {
+            KT_BEGIN(UX_K_TRANSFER)
+            dim3 g_nrl((N + NRL_WARPS - 1) / NRL_WARPS, (R + 31) / 32);
+            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node_rl<8, 8>), g_nrl, dim3(32 * NRL_WARPS), st, w->dworlds, s, R);
+            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node_rl<32, 16>), g_nrl, dim3(32 * NRL_WARPS), st, w->dworlds, s, R);
+            else UX_LAUNCH((k_node_rl<UX_MAXC, UX_MAXDEG>), g_nrl, dim3(32 * NRL_WARPS), st, w->dworlds, s, R);
+            KT_END(UX_K_TRANSFER) lc++;
+        } else if (N > 0) {
             KT_BEGIN(UX_K_TRANSFER)
             if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
             else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node<32, 16>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);

@@ -6,19 +6,21 @@
 //     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
 // ---------------------------------------------------------------------------------------------------
 // Node::signal_update (traffi.cpp:194-207) and Node::flow_capacity_update (226-234) of node n at step t
-UX_DEV void node_signal_capacity(const DevWorld &W, int n, int t) {
+// `ln` = replica offset from W's own replica (0 unless the caller's lanes are the replicas of a group whose first world is W)
+UX_DEV void node_signal_capacity(const DevWorld &W, int n, int t, int ln = 0) {
     int s0 = W.n_sig_off[n], nsig = W.n_sig_off[n + 1] - s0;
-    int ph = NS(W, n).sig_phase;
+    NodeS *ns = &NS(W, n) + ln; NodeR *nr = &NR(W, n) + ln;
+    int ph = ns->sig_phase;
     if (nsig > 1) {
-        double st = NR(W, n).sig_t;
+        double st = nr->sig_t;
         if (st > W.n_sig[s0 + ph]) { ph++; st = 0; if (ph >= nsig) ph = 0; }
         st += W.dt;
-        NR(W, n).sig_t = st; NS(W, n).sig_phase = ph;
+        nr->sig_t = st; ns->sig_phase = ph;
     }
-    W.sig_log[TNI(W, t, n)] = ph;
+    W.sig_log[TNI(W, t, n) + ln] = ph;
     double fc = W.n_fc[n];
-    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (NR(W, n).fc_rem < W.dn * (nl > 0 ? nl : 1)) NR(W, n).fc_rem += fc * W.dt; }
-    else NR(W, n).fc_rem = 10e10;
+    if (fc >= 0.0) { int nl = W.n_lanes[n]; if (nr->fc_rem < W.dn * (nl > 0 ? nl : 1)) nr->fc_rem += fc * W.dt; }
+    else nr->fc_rem = 10e10;
 }
 
 template <int MC, int MD>
@@ -592,30 +594,75 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     }
 }
 
-// K0: the per-link and per-node scalar bookkeeping of a timestep, one THREAD per link / node and replica (coalesced rows):
+// K0: the per-link and per-node scalar bookkeeping of a timestep, one THREAD per (link | node, replica):
 // Link::update (traffi.cpp:542-565: capacity tokens, carry of the cumulative curves and of the instantaneous travel time to
 // row t), reset of the per-step pop count, Node::signal_update (194-207) and Node::flow_capacity_update (226-234).  Nothing here
 // depends on the order of links or nodes, and everything k_node reads of it is final before k_node starts -- inside k_node the
 // same updates cost a warp per node with 4-9 of 32 lanes busy and a quarter of that kernel's stall samples.
-__global__ void __launch_bounds__(256) k_link_pre(const DevWorld *worlds, int step_off) {
-    const DevWorld &W = worlds[blockIdx.y];  // block-uniform field loads
-    int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), t = *W.t_base + step_off, L = W.L;
+// RL = true (ensembles): a warp is ONE entity in 32 replicas -- with the replica-minor layout every load and store of the warp
+// is one contiguous row -- and on the steps that measure the mean speed (every `itt`-th) the thread also sums its own queue, in
+// the oracle's fixed order (32 interleaved partial sums + butterfly, strided_sum32): the 32 replicas of a link have queues of
+// similar length, so the lanes stay balanced, which a thread per link of ONE replica would not be.
+// RL = false (few replicas): thread per entity, blockIdx.y = replica; the mean speed stays in k_node (warp per node).
+UX_DEV double queue_vsum_serial(const double *V, int hd, int n, int cap) {
+    double part[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) part[k] = 0.0;
+    if (n <= 32) {
+#pragma unroll
+        for (int k = 0; k < 32; k++) if (k < n) part[k] = V[ring_slot(hd, k, cap)];
+    } else {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) if (i0 + k < n) part[k] += V[ring_slot(hd, i0 + k, cap)];
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 32; k++) if (!(k & off)) part[k] = part[k] + part[k | off];  // == part[k] + part[k ^ off] of the butterfly, for the entries that reach part[0]
+    }
+    return part[0];
+}
+
+template <bool RL>
+__global__ void __launch_bounds__(256) k_link_pre(const DevWorld *worlds, int step_off, int R) {
+    int idx = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    int r = RL ? (int)blockIdx.y * 32 + (idx & 31) : (int)blockIdx.y, i = RL ? idx >> 5 : idx;
+    if (r >= R) return;
+    const DevWorld &W = worlds[RL ? (int)blockIdx.y * 32 : r];  // block-uniform field loads; RL: the group's first replica + lane offsets
+    const int ln = RL ? (idx & 31) : 0;
+    int t = *W.t_base + step_off, L = W.L;
     if (i < L) {
         int l = i;
+        LinkQ *lq = &LQ(W, l) + ln; LinkC *lc = &LC(W, l) + ln; LinkR *lr = &LR(W, l) + ln;
         if (t > 0) {
-            size_t row = TLI(W, t, l), prev = TLI(W, t - 1, l);
-            W.tt_inst[row] = W.tt_inst[prev];  // k_node overwrites it on the steps that measure the mean speed
+            size_t row = TLI(W, t, l) + ln, prev = TLI(W, t - 1, l) + ln;
+            W.tt_inst[row] = W.tt_inst[prev];  // overwritten below / by k_node on the steps that measure the mean speed
             W.cum_arr[row] = W.cum_arr[prev];
             W.cum_dep[row] = W.cum_dep[prev];
         }
         double thr = W.dn * W.l_lanes[l];
         double ci = W.l_cap_in[l];
-        if (ci < 10e9) { if (LR(W, l).cap_in_rem < thr) LR(W, l).cap_in_rem += ci * W.dt; } else LR(W, l).cap_in_rem = 10e9;
+        if (ci < 10e9) { if (lr->cap_in_rem < thr) lr->cap_in_rem += ci * W.dt; } else lr->cap_in_rem = 10e9;
         double co = W.l_cap_out[l];
-        if (co < 10e9) { if (LR(W, l).cap_out_rem < thr) LR(W, l).cap_out_rem += co * W.dt; } else LR(W, l).cap_out_rem = 10e9;
-        LC(W, l).pop_k2 = 0;
-        LQ(W, l).tail_k1 = LQ(W, l).tail;  // k_node rewrites it for the out-links of nodes that generate
-    } else if (i < L + W.N) node_signal_capacity(W, i - L, t);
+        if (co < 10e9) { if (lr->cap_out_rem < thr) lr->cap_out_rem += co * W.dt; } else lr->cap_out_rem = 10e9;
+        lc->pop_k2 = 0;
+        int tl = lq->tail;
+        lq->tail_k1 = tl;  // k_node rewrites it for the out-links of nodes that generate
+        if (RL && W.node_rl && (t % W.itt) == 0) {  // Link::set_travel_time (traffi.cpp:599-622); with the warp-per-node kernel it stays there
+            int hd = lq->head[t & 1], nq = tl - hd;
+            double tt;
+            if (nq > 0) {
+                const double *V = (const double *)((const char *)W.V + (size_t)ln * (size_t)W.rep_stride) + W.l_roff[l];
+                double avg = queue_vsum_serial(V, hd, nq, W.l_rcap[l]) / (double)nq;
+                tt = avg > 0.0 ? W.l_length[l] / avg : W.l_length[l] / (W.l_vmax[l] / 100.0);
+            } else tt = W.l_length[l] / W.l_vmax[l];
+            W.tt_inst[TLI(W, t, l) + ln] = tt;
+        }
+    } else if (i < L + W.N) {
+        node_signal_capacity(W, i - L, t, ln);
+    }
 }
 
 // k_node: one warp runs a node's whole timestep -- Link::update of the sides it owns, Node::generate, signal, node
@@ -654,6 +701,316 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
     if ((lvl_raw >> 16) && NS(W, n).node_act == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes): the fence is not free
         WARP_SYNC();
         WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)&NDONE(W, n)) = t + 1; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_node_rl -- the node step in REPLICA-LANE form (ensembles): one THREAD per (node, replica); a warp is one node in 32 seeded
+// replicas.  k_node spends a warp on a node whose transfer has one to three candidates (9-12 of 32 lanes busy, ~2 000 warp
+// instructions per node and step, shared-memory staging that caps residency); here every lane walks the reference's serial
+// algorithm (Node::generate traffi.cpp:105-189, Node::transfer 239-445) for its own replica.  The static tables of the node are
+// warp-uniform loads, the per-link / per-node scalars of the 32 replicas are contiguous rows (replica-minor layout), and the
+// ring / per-platoon arrays of replica r are replica 0's + r * rep_stride -- no pointer table per lane.  Order-free bookkeeping
+// and the mean-speed travel times are done by k_link_pre<true> before this kernel.  Nothing is staged: a thread re-reads what
+// it wrote itself (ring slots it pushed, counters it advanced) from global memory, which is coherent for a single thread.
+// Dependency levels (links short enough that the id-ordered visibility of pops matters) work as in k_node: warps are ordered by
+// (level, id), a lane waits for the completion flag of exactly the lower-level nodes it depends on, in its own replica.
+// Random draws are the same counters as in k_node / the oracle, so the results are bit-identical.
+// ---------------------------------------------------------------------------------------------------
+#define NRL_WARPS 4
+#define RLP(T_, ptr_) ((T_ *)((char *)(ptr_) + ro))  // the lane's replica-major array
+
+// Vehicle::end_trip (traffi.cpp:886-927) for the front platoon of in-link il, sitting in ring slot `slot`
+UX_DEV void rl_end_trip(const DevWorld &W, int ln, size_t ro, int il, int slot, int vid, unsigned char flags, int t, int cur) {
+    long long o = W.l_roff[il];
+    LinkC *lc = &LC(W, il) + ln;
+    lc->trips += 1;
+    W.cum_dep[TLI(W, t, il) + ln] += W.dn;
+    double *v_atl = RLP(double, W.v_atl);
+    double atl = v_atl[vid];
+    {   // record_tt_event
+        int s = (int)(atl / W.dt);
+        if (s < 0) s = 0;
+        if (s >= W.T) s = W.T - 1;
+        int ord = lc->ev_cnt + 1;
+        lc->ev_cnt = ord;
+        W.ev_ord[TLI(W, s, il) + ln] = ord;
+        W.ev_tt[TLI(W, s, il) + ln] = ((double)t + 1.0) * W.dt - atl;
+    }
+    v_atl[vid] = (double)t * W.dt;
+    double x = RLP(double, W.X)[(size_t)cur * (size_t)W.C + o + slot];
+    RLP(double, W.v_dist)[vid] += x - RLP(double, W.v_entry_x)[vid];
+    RLP(int, W.v_link)[vid] = -1;
+    if (flags & VF_ABORT) { RLP(int, W.v_state)[vid] = UX_VS_ABORT; RLP(int, W.v_arr_ts)[vid] = -1; RLP(double, W.v_tt)[vid] = -1.0; }
+    else { RLP(int, W.v_state)[vid] = UX_VS_END; RLP(int, W.v_arr_ts)[vid] = t; RLP(double, W.v_tt)[vid] = (double)t * W.dt - (double)W.v_depart_ts[vid] * W.dt; }
+    if (W.log_mode) { RLP(int, W.v_end_ts)[vid] = t; RLP(unsigned char, W.v_end_kind)[vid] = 2; }
+    RLP(unsigned char, W.v_flags)[vid] = 0;
+}
+
+template <int MC, int MD>
+__global__ void __launch_bounds__(32 * NRL_WARPS) k_node_rl(const DevWorld *worlds, int step_off, int R) {
+    LOAD_WORLD_N(W, worlds, 64, (int)blockIdx.y * 32)  // the group's first replica; the lanes add their offsets
+    const int ln = (int)(threadIdx.x & 31), r = (int)blockIdx.y * 32 + ln;
+    const int warp = (int)blockIdx.x * NRL_WARPS + (int)(threadIdx.x >> 5);
+    if (warp >= W.N || r >= R) return;
+    const DevWorld &Wr = worlds[r];  // the lane's own pointer table, for the rare helpers only (route choice, error word, traversal log)
+    const size_t ro = (size_t)ln * (size_t)W.rep_stride;
+    const int n = W.lvl_nodes[warp], t = *W.t_base + step_off, cur = t & 1;
+    const int lvl_raw = W.n_levels > 1 ? W.lvl_level[warp] : 0;
+    const size_t C = (size_t)W.C;
+    double *Xc = RLP(double, W.X) + (size_t)cur * C, *Xo = RLP(double, W.X) + (size_t)(cur ^ 1) * C, *V = RLP(double, W.V);
+    int *VID = RLP(int, W.VID), *LANE = RLP(int, W.LANE);
+    const int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
+    const int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
+    NodeS *ns = &NS(W, n) + ln; NodeR *nr = &NR(W, n) + ln;
+
+    // ---- release HOME -> WAIT (traffi.cpp:836-841): the per-origin list is sorted by departure step
+    const int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0;
+    int av = ns->gen_avail, gh = ns->gen_head;
+    if (av < glen) {
+        int av0 = av;
+        while (av < glen && W.gen_ts[g0 + av] <= t - 1) av++;
+        if (av != av0) ns->gen_avail = av;
+    }
+    // ---- generate (traffi.cpp:105-189): attempts in order, the first refusal ends them
+    int natt = av - gh;
+    { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; }
+    if (nout == 0) natt = 0;
+    if (natt > 0) {
+        const int gh0 = gh;
+        for (int i = 0; i < natt; i++) {
+            int vid = W.gen_list[g0 + gh], e = 0;
+            int ol = route_choice(Wr, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
+            if (e) { dev_error(Wr, e, vid); break; }
+            RLP(int, W.v_next)[vid] = ol;
+            if (ol < 0) break;
+            LinkQ *lq = &LQ(W, ol) + ln; LinkR *lr = &LR(W, ol) + ln;
+            int hd = lq->head[cur], tl = lq->tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol], sz = tl - hd;
+            long long o = W.l_roff[ol];
+            bool ok = false;  // traffi.cpp:130-142
+            if (sz < lanes) ok = true;
+            else if (Xc[o + ring_slot(hd, sz - lanes, cap)] > W.l_dpl_dn[ol]) ok = true;
+            double ci = lr->cap_in_rem;
+            if (ci < W.dn) ok = false;
+            if (!ok) break;
+            if (sz >= cap) { dev_error(Wr, DERR_RING_FULL, ol); break; }
+            gh++;
+            int lane_new = sz > 0 ? (LANE[o + ring_slot(tl - 1, 0, cap)] + 1) % lanes : 0;
+            int slot = ring_slot(tl, 0, cap);
+            Xc[o + slot] = 0.0; Xo[o + slot] = 0.0; V[o + slot] = W.l_vmax[ol]; VID[o + slot] = vid; LANE[o + slot] = lane_new;
+            lq->tail = tl + 1;
+            RLP(int, W.v_state)[vid] = UX_VS_RUN;
+            if (W.log_mode) RLP(int, W.v_gen_ts)[vid] = t;
+            RLP(double, W.v_atl)[vid] = (double)t * W.dt;
+            RLP(double, W.v_entry_x)[vid] = 0.0;
+            mark_entered(Wr, vid, ol, t);
+            W.cum_arr[TLI(W, t, ol) + ln] += W.dn;
+            lr->cap_in_rem = ci - W.dn;
+        }
+        if (gh != gh0) {
+            ns->gen_head = gh;
+            for (int k = 0; k < nout; k++) { LinkQ *lq = &LQ(W, W.n_out[o0 + k]) + ln; lq->tail_k1 = lq->tail; }  // tail after generation (k_link_pre copied the unchanged ones)
+        }
+    }
+
+    // ---- transfer (traffi.cpp:239-445)
+    const bool act = ns->node_act == t && nin > 0;
+    if (act) {
+        const int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = ns->sig_phase;
+        // candidates = the flagged head positions of the in-links, sorted by platoon id (250-253)
+        int c_vid[MC], c_next[MC]; short c_pos[MC];  // c_pos = in-link index << 8 | position from the head
+        int hd_in[MD], hc_in[MD], popped[MD];
+        unsigned sig_ok = 0;
+        int nc = 0; bool any_wait = false;
+        for (int ii = 0; ii < nin; ii++) {
+            int il = W.n_in[i0 + ii];
+            int hd = (&LQ(W, il) + ln)->head[cur], hc = (&LC(W, il) + ln)->hcount;
+            hd_in[ii] = hd; hc_in[ii] = hc; popped[ii] = 0;
+            if (hc == 0) continue;
+            bool ok = true;
+            if (nsig > 1) { int s0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - s0; ok = list_has(W.l_sg + s0, gl, phase); }
+            if (ok) sig_ok |= 1u << ii;
+            long long o = W.l_roff[il]; int cap = W.l_rcap[il];
+            for (int j = 0; j < hc && nc < MC; j++) {
+                int vid = VID[o + ring_slot(hd, j, cap)];
+                unsigned char f = RLP(unsigned char, W.v_flags)[vid];
+                if (f & VF_WAIT_END) any_wait = true;
+                if (f & VF_CAND) {
+                    int nx = RLP(int, W.v_next)[vid], k = nc++;
+                    while (k > 0 && c_vid[k - 1] > vid) { c_vid[k] = c_vid[k - 1]; c_next[k] = c_next[k - 1]; c_pos[k] = c_pos[k - 1]; k--; }
+                    c_vid[k] = vid; c_next[k] = nx; c_pos[k] = (short)((ii << 8) | j);
+                }
+            }
+        }
+        if (nc > 0 || any_wait) {
+            // requested out-links in order of first appearance, each `lanes` times (260-273)
+            int ol_id[MD], o_hd[MD]; unsigned char expd[MC]; unsigned char c_q[MC];
+            int nol = 0, nexp = 0;
+            for (int k = 0; k < nc; k++) {
+                int nl = c_next[k], q = 255;
+                if (nl >= 0) {
+                    for (int x = 0; x < nol; x++) if (ol_id[x] == nl) { q = x; break; }
+                    if (q == 255 && nol < MD) { q = nol; ol_id[nol++] = nl; }
+                }
+                c_q[k] = (unsigned char)q;
+            }
+            for (int q = 0; q < nol; q++) { int lanes = W.l_lanes[ol_id[q]]; for (int x = 0; x < lanes && nexp < MC; x++) expd[nexp++] = (unsigned char)q; }
+            const int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
+            if (!W.hard_det) {  // Fisher-Yates (276-282); step i uses draw number nexp-1-i
+                for (int i = nexp - 1; i > 0; i--) {
+                    int j = ux_rng_below(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nexp - 1 - i), i + 1);
+                    unsigned char tmp = expd[i]; expd[i] = expd[j]; expd[j] = tmp;
+                }
+            }
+            // ---- dependency wait: only now are the pops of lower-level end nodes needed
+            if ((lvl_raw & 0xffff) > 0) {
+                for (int q = W.dep_off[n]; q < W.dep_off[n + 1]; q++) {
+                    int dep = W.dep_list[q];
+                    if ((&NS(W, dep) + ln)->node_act != t) continue;  // idle there: it pops nothing and does not publish
+                    volatile int *done = &NDONE(W, dep) + ln;
+#ifdef UX_EMU
+                    if (*done < t + 1) dev_error(Wr, DERR_DEP_TIMEOUT, n);
+#else
+                    long long spins = 0;
+                    while (*done < t + 1) { __nanosleep(64); if (++spins > UX_DEP_SPIN_BUDGET) { dev_error(Wr, DERR_DEP_TIMEOUT, n); break; } }
+#endif
+                }
+#ifndef UX_EMU
+                __threadfence();
+#endif
+            }
+            for (int q = 0; q < nol; q++) {
+                int ol = ol_id[q], fl = W.l_flags[ol];
+                int hd = (&LQ(W, ol) + ln)->head[cur];
+                if ((fl & LF_SEES_POPS) && (&NS(W, W.l_end[ol]) + ln)->node_act == t) hd += ld_cg(&(&LC(W, ol) + ln)->pop_k2);
+                o_hd[q] = hd;
+            }
+            const double fc = W.n_fc[n];
+            double fc_rem = nr->fc_rem;
+            int n_picks = 0;
+            for (int s = 0; s < nexp; s++) {
+                const int q = expd[s], ol = ol_id[q];
+                LinkQ *olq = &LQ(W, ol) + ln; LinkR *olr = &LR(W, ol) + ln;
+                const int lanes_ol = W.l_lanes[ol], cap_ol = W.l_rcap[ol];
+                const long long oo = W.l_roff[ol];
+                const int tl = olq->tail, sz = tl - o_hd[q];
+                const double dpl = W.l_dpl_dn[ol];
+                bool ok = false;  // acceptance (285-300)
+                if (sz < lanes_ol) ok = true;
+                else if (Xc[oo + ring_slot(o_hd[q], sz - lanes_ol, cap_ol)] > dpl) ok = true;
+                double ci = olr->cap_in_rem;
+                if (ci < W.dn) ok = false;
+                if (fc_rem < W.dn) ok = false;
+                if (!ok) continue;
+                // eligible candidates in ascending id: front of their in-link, outflow tokens, green (305-330)
+                double wsum = 0.0, wbest = 0.0; int nm = 0, kbest = -1;
+                for (int k = 0; k < nc; k++) {
+                    if (c_q[k] != q) continue;
+                    int ii = c_pos[k] >> 8;
+                    if ((c_pos[k] & 255) != popped[ii] || !((sig_ok >> ii) & 1u)) continue;
+                    int il = W.n_in[i0 + ii];
+                    if ((&LR(W, il) + ln)->cap_out_rem < W.dn) continue;
+                    double mp = W.l_mp[il];
+                    if (nm == 0 || mp > wbest) { wbest = mp; kbest = k; }
+                    wsum += mp; nm++;
+                }
+                if (nm == 0) continue;
+                int kp = kbest;
+                if (!W.hard_det) {  // random_choice over the merge priorities (utils.h:62-87)
+                    double u = ux_rng_uniform(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + n_picks));
+                    n_picks++;
+                    int target; double rr = u * wsum;
+                    if (wsum <= 0.0) { target = (int)(u * (double)nm); if (target >= nm) target = nm - 1; } else target = -1;
+                    double accum = 0.0; int seen = 0; kp = -1;
+                    for (int k = 0; k < nc; k++) {
+                        if (c_q[k] != q) continue;
+                        int ii = c_pos[k] >> 8;
+                        if ((c_pos[k] & 255) != popped[ii] || !((sig_ok >> ii) & 1u)) continue;
+                        int il = W.n_in[i0 + ii];
+                        if ((&LR(W, il) + ln)->cap_out_rem < W.dn) continue;
+                        kp = k;  // the last eligible one is the fallback of random_choice
+                        if (target >= 0) { if (seen == target) break; }
+                        else { accum += W.l_mp[il]; if (rr <= accum) break; }
+                        seen++;
+                    }
+                }
+                // ---- move candidate kp onto ol
+                const int vid = c_vid[kp], ii = c_pos[kp] >> 8, jj = c_pos[kp] & 255, il = W.n_in[i0 + ii];
+                const long long io = W.l_roff[il];
+                const int cap_il = W.l_rcap[il], slot_in = ring_slot(hd_in[ii], jj, cap_il);
+                LinkR *ilr = &LR(W, il) + ln; LinkC *ilc = &LC(W, il) + ln;
+                ilr->cap_out_rem -= W.dn; olr->cap_in_rem = ci - W.dn;
+                if (fc >= 0.0) fc_rem -= W.dn;
+                W.cum_dep[TLI(W, t, il) + ln] += W.dn; W.cum_arr[TLI(W, t, ol) + ln] += W.dn;
+                double *v_atl = RLP(double, W.v_atl);
+                const double atl = v_atl[vid];
+                {   // record_tt_event (357-362)
+                    int es = (int)(atl / W.dt);
+                    if (es < 0) es = 0;
+                    if (es >= W.T) es = W.T - 1;
+                    int ord = ilc->ev_cnt + 1;
+                    ilc->ev_cnt = ord;
+                    W.ev_ord[TLI(W, es, il) + ln] = ord;
+                    W.ev_tt[TLI(W, es, il) + ln] = (double)t * W.dt - atl;
+                }
+                v_atl[vid] = (double)t * W.dt;
+                const double px = Xc[io + slot_in], pxold = Xo[io + slot_in], pv = V[io + slot_in];
+                RLP(double, W.v_dist)[vid] += px - RLP(double, W.v_entry_x)[vid];
+                popped[ii] += 1;
+                if (W.no_cyclic) { int sn = W.l_start[ol]; RLP(unsigned, W.v_visited)[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
+                { int *v_trav = RLP(int, W.v_trav); int k = v_trav[vid]; v_trav[vid] = k + 1; record_traversal(Wr, vid, k, ol, t); }
+                RLP(int, W.v_link)[vid] = ol;
+                RLP(unsigned char, W.v_flags)[vid] = 0;
+                // carry the residual move onto the new link (400-419)
+                double x_next = RLP(double, W.v_mr)[vid] * W.l_vmax[ol] / W.l_vmax[il];
+                if (sz >= lanes_ol) {
+                    double x_cong = Xo[oo + ring_slot(o_hd[q], sz - lanes_ol, cap_ol)] - dpl;
+                    if (x_cong < 0.0) x_cong = 0.0;
+                    if (x_next > x_cong) x_next = x_cong;
+                }
+                const double len_ol = W.l_length[ol];
+                if (x_next >= len_ol) x_next = len_ol;
+                if (x_next < 0.0) x_next = 0.0;
+                if (sz >= cap_ol) dev_error(Wr, DERR_RING_FULL, ol);
+                else {  // push (lane rule 385-390)
+                    int lane_new = sz > 0 ? (LANE[oo + ring_slot(tl - 1, 0, cap_ol)] + 1) % lanes_ol : 0;
+                    int slot = ring_slot(tl, 0, cap_ol);
+                    Xc[oo + slot] = x_next; Xo[oo + slot] = pxold; V[oo + slot] = pv + x_next / W.dt; VID[oo + slot] = vid; LANE[oo + slot] = lane_new;
+                    olq->tail = tl + 1;
+                }
+                RLP(double, W.v_entry_x)[vid] = x_next;
+                RLP(double, W.v_mr)[vid] = 0.0;
+                c_q[kp] = 254;  // removed from the incoming list
+                // the new front of the in-link may be waiting for its trip end (421-424)
+                if (popped[ii] < hc_in[ii]) {
+                    int fslot = ring_slot(hd_in[ii], popped[ii], cap_il), fvid = VID[io + fslot];
+                    unsigned char ff = RLP(unsigned char, W.v_flags)[fvid];
+                    if (ff & VF_WAIT_END) { rl_end_trip(W, ln, ro, il, fslot, fvid, ff, t, cur); popped[ii] += 1; }
+                }
+            }
+            // flush trip-end-waiting fronts (432-441)
+            for (int ii = 0; ii < nin; ii++) {
+                int hc = hc_in[ii];
+                if (hc == 0) continue;
+                int il = W.n_in[i0 + ii], cap_il = W.l_rcap[il];
+                long long io = W.l_roff[il];
+                for (int x = 0; x < hc; x++) {
+                    if (popped[ii] >= hc) break;
+                    int fslot = ring_slot(hd_in[ii], popped[ii], cap_il), fvid = VID[io + fslot];
+                    unsigned char ff = RLP(unsigned char, W.v_flags)[fvid];
+                    if (!(ff & VF_WAIT_END)) break;
+                    rl_end_trip(W, ln, ro, il, fslot, fvid, ff, t, cur); popped[ii] += 1;
+                }
+                if (popped[ii]) (&LC(W, il) + ln)->pop_k2 = popped[ii];
+            }
+            nr->fc_rem = fc_rem;
+        }
+    }
+    if ((lvl_raw >> 16) && ns->node_act == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes)
+#ifndef UX_EMU
+        __threadfence();
+#endif
+        *((volatile int *)(&NDONE(W, n) + ln)) = t + 1;
     }
 }
 

@@ -351,10 +351,15 @@ def test_replica_lane_node_kernel_forced(name, mk, log, cuda_api, oracle_api, mo
         assert compare_logs(Eg, Eo) == []
 
 
-@pytest.mark.parametrize("name,R", [("chicago_dn30", 35), ("grid6_signals", 64), ("siouxfalls", 33), ("grid11", 32)])
-def test_replica_lane_node_kernel_ensembles(name, R, cuda_api, oracle_api):
-    """From 32 replicas the engine picks the replica-lane node step by itself (ragged lane groups included): every checked
-    replica equals the single-seed oracle run; and forcing the warp-per-node kernel on the same ensemble gives the same bits."""
+@pytest.mark.parametrize("name,R,mode", [("chicago_dn30", 35, "rl"), ("grid6_signals", 64, "hybrid"), ("siouxfalls", 33, "hybrid"), ("grid11", 32, "rl"),
+                                         ("chicago_dn30", 40, "hybrid"), ("grid6_signals", 256, None)])
+def test_replica_lane_node_kernel_ensembles(name, R, mode, cuda_api, oracle_api, monkeypatch):
+    """The node step with a thread per (node, replica) (k_node_h; picked by itself from 256 replicas, forced below that) on
+    ensembles with ragged lane groups, in its pure form and with the heavy nodes stepped by warps: every checked replica equals
+    the single-seed oracle run."""
+    if mode:
+        monkeypatch.setenv("UXSIM_B200_NODE", mode)
+        monkeypatch.setenv("UXSIM_B200_NODE_HEAVY", "4" if mode == "hybrid" else "1000000")
     sc = dict(STOCHASTIC)[name]()
     seed0 = sc.world.get("random_seed", 0) or 0
     Eg = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1, num_replicas=R)

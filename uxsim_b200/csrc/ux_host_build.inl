@@ -263,9 +263,30 @@ static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<in
         }
         for (int a = N - 1; a >= 0; a--)  // a dependency always has the smaller id, so height[a] is final here
             for (int l : w->nodes[a].out) if (lflags[l] & LF_SEES_POPS) { int b = w->links[l].end; height[b] = std::max(height[b], height[a] + 1); }
+        // Ensembles (k_node_h): heavy nodes -- many lanes in or out -- are stepped by a warp each, light ones by a thread per replica;
+        // inside a height the heavy ones come first, so that the block table is a few long runs of one form
+        std::vector<char> heavy(N, 0);
+        if (w->node_rl) for (int a = 0; a < N; a++) {
+            int li = 0, lo = 0;
+            for (int l : w->nodes[a].in) li += w->links[l].lanes;
+            for (int l : w->nodes[a].out) lo += w->links[l].lanes;
+            heavy[a] = std::max(li, lo) > w->node_heavy_lanes;
+        }
         std::stable_sort(lvl_nodes.begin(), lvl_nodes.end(), [&](int a, int b) {
             if (height[a] != height[b]) return height[a] > height[b];
+            if (heavy[a] != heavy[b]) return heavy[a] > heavy[b];
             return weight[a] > weight[b]; });
+        w->h_node_blks.clear();
+        if (w->node_rl) {  // {form, first position in lvl_nodes, nodes, replica | lane group}, four nodes per block
+            const int groups = (w->R + 31) / 32;
+            for (int q = 0; q < N;) {
+                int e = q + 1;
+                while (e < N && e - q < NRL_WARPS && heavy[lvl_nodes[e]] == heavy[lvl_nodes[q]] && height[lvl_nodes[e]] == height[lvl_nodes[q]]) e++;
+                if (heavy[lvl_nodes[q]]) for (int r = 0; r < w->R; r++) w->h_node_blks.push_back(make_int4(0, q, e - q, r));
+                else for (int g = 0; g < groups; g++) w->h_node_blks.push_back(make_int4(1, q, e - q, g));
+                q = e;
+            }
+        }
     }
     lvl_level.assign(N, 0);
     for (int q = 0; q < N; q++) lvl_level[q] = level[lvl_nodes[q]];
@@ -305,6 +326,15 @@ static int upload_link_params(ux_world *w) {
     CUDA_OK(cudaMemcpyAsync(w->d_lvl_level, lvl_level.data(), sizeof(int) * lvl_level.size(), cudaMemcpyHostToDevice, w->stream));
     for (auto &d : w->hw) d.n_levels = w->n_levels;
     if (w->dworlds) CUDA_OK(cudaMemcpyAsync(w->dworlds, w->hw.data(), sizeof(DevWorld) * w->hw.size(), cudaMemcpyHostToDevice, w->stream));
+    if (w->node_rl) {  // block table of k_node_h (a changed table invalidates the captured graphs: their grids are part of them)
+        if (w->h_node_blks.size() > w->node_blks_cap) { w->node_blks_cap = w->h_node_blks.size() + 64; w->d_node_blks = dalloc<int4>(w, w->node_blks_cap, false); w->rewindable = w->rewindable && !w->uploaded; }
+        if (!w->d_node_blks) return fail(w, UX_ERR_CUDA, "device allocation failed");
+        CUDA_OK(cudaMemcpyAsync(w->d_node_blks, w->h_node_blks.data(), sizeof(int4) * w->h_node_blks.size(), cudaMemcpyHostToDevice, w->stream));
+#ifndef UX_EMU
+        if ((int)w->h_node_blks.size() != w->n_node_blks) { for (auto &g : w->graphs) cudaGraphExecDestroy(g.second.first); w->graphs.clear(); }
+#endif
+        w->n_node_blks = (int)w->h_node_blks.size();
+    }
     lvl_off.resize(w->nodes.size() + 2, lvl_off.back());
     CUDA_OK(cudaMemcpyAsync(w->d_l_flags, lflags.data(), sizeof(int) * L, cudaMemcpyHostToDevice, w->stream));
     CUDA_OK(cudaMemcpyAsync(w->d_lvl_off, lvl_off.data(), sizeof(int) * lvl_off.size(), cudaMemcpyHostToDevice, w->stream));
@@ -353,7 +383,13 @@ static int upload(ux_world *w) {
         w->pre_split = e ? atoi(e) != 0 : ((long long)(L + N) * w->R >= 40000);
         base.pre_split = w->pre_split ? 1 : 0;
         const char *e2 = getenv("UXSIM_B200_NODE");  // rl | warp
-        w->node_rl = e2 ? !strcmp(e2, "rl") : w->R >= 32;
+        // Node step: warp per (node, replica) (k_node), or -- large ensembles -- thread per (node, replica) (k_node_h).  Measured on the
+        // B200, Chicago sketch, us per launch (warp | thread form): 32 replicas 127 | 546, 128: 320 | 647, 256: 609 | ~600, 512: 1210 | 820 --
+        // the thread form is bound by the serial chain of its busiest node (flat in R), the warp form by residency (linear in R).
+        // UXSIM_B200_NODE = warp | rl | hybrid (hybrid: nodes with more than UXSIM_B200_NODE_HEAVY lanes in or out by warps, inside k_node_h)
+        w->node_rl = e2 ? strcmp(e2, "warp") != 0 : w->R >= 256;
+        const char *e3 = getenv("UXSIM_B200_NODE_HEAVY");
+        w->node_heavy_lanes = e3 ? atoi(e3) : (e2 && !strcmp(e2, "hybrid")) ? 8 : 1 << 30;
         base.node_rl = w->node_rl ? 1 : 0;
         if (w->node_rl) { w->pre_split = true; base.pre_split = 1; }  // the scalar bookkeeping always runs in k_link_pre<true> then
     }

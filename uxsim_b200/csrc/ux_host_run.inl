@@ -18,13 +18,25 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
         // bookkeeping peeled into k_link_pre<false> for large worlds.
         const bool node_rl = w->node_rl && w->uniform;
         if (node_rl) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre<true>, dim3((((unsigned)w->links.size() + (unsigned)N) * 32u + 255u) / 256u, (R + 31) / 32), dim3(256), st, w->dworlds, s, R); KT_END(UX_K_PRE) lc++; }
+        else if (w->pre_split && R >= 8) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre<true>, dim3((((unsigned)w->links.size() + (unsigned)N) * 32u + 255u) / 256u, (R + 31) / 32), dim3(256), st, w->dworlds, s, R); KT_END(UX_K_PRE) lc++; }  // (the mean speeds stay in k_node: W.node_rl == 0)
         else if (w->pre_split) { KT_BEGIN(UX_K_PRE) UX_LAUNCH(k_link_pre<false>, dim3(((unsigned)w->links.size() + (unsigned)N + 255) / 256, R), dim3(256), st, w->dworlds, s, R); KT_END(UX_K_PRE) lc++; }
         if (N > 0 && node_rl) {
             KT_BEGIN(UX_K_TRANSFER)
-            dim3 g_nrl((N + NRL_WARPS - 1) / NRL_WARPS, (R + 31) / 32);
-            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node_rl<8, 8>), g_nrl, dim3(32 * NRL_WARPS), st, w->dworlds, s, R);
-            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node_rl<32, 16>), g_nrl, dim3(32 * NRL_WARPS), st, w->dworlds, s, R);
-            else UX_LAUNCH((k_node_rl<UX_MAXC, UX_MAXDEG>), g_nrl, dim3(32 * NRL_WARPS), st, w->dworlds, s, R);
+            dim3 g_nh(w->n_node_blks);
+            const bool heavy = w->node_heavy_lanes < w->max_node_lanes;  // some node is stepped by a warp
+#ifndef UX_EMU
+            if (s == 0 && !heavy) {  // pure replica-lane form: no shared-memory staging, all of the L1 for the threads' local arrays
+                cudaFuncSetAttribute(k_node_h<8, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+                cudaFuncSetAttribute(k_node_h<32, 16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+                cudaFuncSetAttribute(k_node_h<UX_MAXC, UX_MAXDEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+            }
+#endif
+#define UX_NODE_H(MC_, MD_) { if (heavy) UX_LAUNCH((k_node_h<MC_, MD_, true>), g_nh, dim3(32 * NRL_WARPS), st, w->dworlds, s, R, (const int4 *)w->d_node_blks); \
+                              else UX_LAUNCH((k_node_h<MC_, MD_, false>), g_nh, dim3(32 * NRL_WARPS), st, w->dworlds, s, R, (const int4 *)w->d_node_blks); }
+            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_NODE_H(8, 8)
+            else if (w->max_node_lanes <= 32) UX_NODE_H(32, 16)
+            else UX_NODE_H(UX_MAXC, UX_MAXDEG)
+#undef UX_NODE_H
             KT_END(UX_K_TRANSFER) lc++;
         } else if (N > 0) {
             KT_BEGIN(UX_K_TRANSFER)
@@ -160,6 +172,17 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
             return fail(w, code, derr_text(c0), e[2 * r + 1]);
         }
     }
+#ifdef UX_PROFILE_NODE
+    {   // measurement build: per-step maxima of the k_node_rl phases (cycles), averaged over the steps of this call
+        static unsigned long long h[4096][8];
+        cudaMemcpyFromSymbol(h, g_node_prof, sizeof(h));
+        double sum[8] = {0}, mx[8] = {0}; int cnt = 0;
+        for (int t = start_ts; t < end_ts && t < 4096; t++) { cnt++; for (int k = 0; k < 8; k++) { sum[k] += (double)h[t][k]; if ((double)h[t][k] > mx[k]) mx[k] = (double)h[t][k]; } }
+        const char *nm[8] = {"generate", "gather", "dep-wait", "out-links", "slot loop", "flush+writeback", "total(active)", "-"};
+        for (int k = 0; k < 7; k++) fprintf(stderr, "[node_prof] %-16s mean of per-step max %9.0f cycles, max %9.0f\n", nm[k], sum[k] / (cnt ? cnt : 1), mx[k]);
+        static unsigned long long z[4096][8]; cudaMemcpyToSymbol(g_node_prof, z, sizeof(z));
+    }
+#endif
     w->loop_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     w->timestep = end_ts;
     return 0;

@@ -86,6 +86,7 @@ struct ux_world {
     size_t dyn_slab0 = 0, dyn_used0 = 0, dyn_slab1 = 0, dyn_used1 = 0;
     bool rewindable = false;
     int upd_group = 32;      // lanes per (link, part) item of k_update: 16 for large, lightly loaded worlds
+    std::vector<int4> h_node_blks; int4 *d_node_blks = nullptr; size_t node_blks_cap = 0; int n_node_blks = 0, node_heavy_lanes = 12;  // block table of k_node_h
     bool node_rl = false;    // node step in replica-lane form (k_link_pre<true> + k_node_rl): ensembles of >= 32 replicas
     bool pre_split = false;  // k_link_pre runs the scalar link / node bookkeeping (worlds with >= 40k link+node states per step)
     int swap_last = 0;             // replica of the most recent result (scalar queries without a replica index)

@@ -37,7 +37,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     int cur = t & 1, L = W.L;
     int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
-    bool fresh = (t % W.itt) == 0;
+    bool fresh = (t % W.itt) == 0 && !W.node_rl;  // (ensembles: k_link_pre<true> has measured the mean speeds already)
     // ---- instantaneous travel time of the out-links (whole warp per link, only every `itt` steps)
     if (fresh) {
         for (int k = 0; k < nout; k++) {
@@ -718,45 +718,22 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
 // Random draws are the same counters as in k_node / the oracle, so the results are bit-identical.
 // ---------------------------------------------------------------------------------------------------
 #define NRL_WARPS 4
+#ifdef UX_PROFILE_NODE  // measurement build only (uxsim_b200/variants/): per step, the longest time any thread spent in each phase of k_node_rl
+__device__ unsigned long long g_node_prof[4096][8];
+#define NPROF_T(v) const long long v = clock64();
+#define NPROF_MAX(k, a, b) atomicMax(&g_node_prof[t & 4095][k], (unsigned long long)((b) - (a)));
+#else
+#define NPROF_T(v)
+#define NPROF_MAX(k, a, b)
+#endif
 #define RLP(T_, ptr_) ((T_ *)((char *)(ptr_) + ro))  // the lane's replica-major array
 
-// Vehicle::end_trip (traffi.cpp:886-927) for the front platoon of in-link il, sitting in ring slot `slot`
-UX_DEV void rl_end_trip(const DevWorld &W, int ln, size_t ro, int il, int slot, int vid, unsigned char flags, int t, int cur) {
-    long long o = W.l_roff[il];
-    LinkC *lc = &LC(W, il) + ln;
-    lc->trips += 1;
-    W.cum_dep[TLI(W, t, il) + ln] += W.dn;
-    double *v_atl = RLP(double, W.v_atl);
-    double atl = v_atl[vid];
-    {   // record_tt_event
-        int s = (int)(atl / W.dt);
-        if (s < 0) s = 0;
-        if (s >= W.T) s = W.T - 1;
-        int ord = lc->ev_cnt + 1;
-        lc->ev_cnt = ord;
-        W.ev_ord[TLI(W, s, il) + ln] = ord;
-        W.ev_tt[TLI(W, s, il) + ln] = ((double)t + 1.0) * W.dt - atl;
-    }
-    v_atl[vid] = (double)t * W.dt;
-    double x = RLP(double, W.X)[(size_t)cur * (size_t)W.C + o + slot];
-    RLP(double, W.v_dist)[vid] += x - RLP(double, W.v_entry_x)[vid];
-    RLP(int, W.v_link)[vid] = -1;
-    if (flags & VF_ABORT) { RLP(int, W.v_state)[vid] = UX_VS_ABORT; RLP(int, W.v_arr_ts)[vid] = -1; RLP(double, W.v_tt)[vid] = -1.0; }
-    else { RLP(int, W.v_state)[vid] = UX_VS_END; RLP(int, W.v_arr_ts)[vid] = t; RLP(double, W.v_tt)[vid] = (double)t * W.dt - (double)W.v_depart_ts[vid] * W.dt; }
-    if (W.log_mode) { RLP(int, W.v_end_ts)[vid] = t; RLP(unsigned char, W.v_end_kind)[vid] = 2; }
-    RLP(unsigned char, W.v_flags)[vid] = 0;
-}
-
+// W = the staged world of the lane group's first replica (the lanes add their offsets), Wr = the lane's own pointer table, for
+// the rare helpers only (route choice, error word, traversal log)
 template <int MC, int MD>
-__global__ void __launch_bounds__(32 * NRL_WARPS) k_node_rl(const DevWorld *worlds, int step_off, int R) {
-    LOAD_WORLD_N(W, worlds, 64, (int)blockIdx.y * 32)  // the group's first replica; the lanes add their offsets
-    const int ln = (int)(threadIdx.x & 31), r = (int)blockIdx.y * 32 + ln;
-    const int warp = (int)blockIdx.x * NRL_WARPS + (int)(threadIdx.x >> 5);
-    if (warp >= W.N || r >= R) return;
-    const DevWorld &Wr = worlds[r];  // the lane's own pointer table, for the rare helpers only (route choice, error word, traversal log)
+UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, const int n, const int t, const int lvl_raw) {
     const size_t ro = (size_t)ln * (size_t)W.rep_stride;
-    const int n = W.lvl_nodes[warp], t = *W.t_base + step_off, cur = t & 1;
-    const int lvl_raw = W.n_levels > 1 ? W.lvl_level[warp] : 0;
+    const int cur = t & 1;
     const size_t C = (size_t)W.C;
     double *Xc = RLP(double, W.X) + (size_t)cur * C, *Xo = RLP(double, W.X) + (size_t)(cur ^ 1) * C, *V = RLP(double, W.V);
     int *VID = RLP(int, W.VID), *LANE = RLP(int, W.LANE);
@@ -764,6 +741,7 @@ __global__ void __launch_bounds__(32 * NRL_WARPS) k_node_rl(const DevWorld *worl
     const int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     NodeS *ns = &NS(W, n) + ln; NodeR *nr = &NR(W, n) + ln;
 
+    NPROF_T(pt0)
     // ---- release HOME -> WAIT (traffi.cpp:836-841): the per-origin list is sorted by departure step
     const int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0;
     int av = ns->gen_avail, gh = ns->gen_head;
@@ -813,204 +791,338 @@ __global__ void __launch_bounds__(32 * NRL_WARPS) k_node_rl(const DevWorld *worl
         }
     }
 
-    // ---- transfer (traffi.cpp:239-445)
+    // ---- transfer (traffi.cpp:239-445).  What bounds this kernel is the chain of dependent memory round trips of the busiest
+    //      node, so everything the serial slot loop reads is fetched first, in batches of independent loads (registers, then
+    //      thread-local arrays), and the loop itself runs on local data: global memory only sees its stores.
+    NPROF_T(pt1) NPROF_MAX(0, pt0, pt1)
     const bool act = ns->node_act == t && nin > 0;
     if (act) {
         const int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = ns->sig_phase;
-        // candidates = the flagged head positions of the in-links, sorted by platoon id (250-253)
-        int c_vid[MC], c_next[MC]; short c_pos[MC];  // c_pos = in-link index << 8 | position from the head
-        int hd_in[MD], hc_in[MD], popped[MD];
-        unsigned sig_ok = 0;
-        int nc = 0; bool any_wait = false;
-        for (int ii = 0; ii < nin; ii++) {
-            int il = W.n_in[i0 + ii];
-            int hd = (&LQ(W, il) + ln)->head[cur], hc = (&LC(W, il) + ln)->hcount;
-            hd_in[ii] = hd; hc_in[ii] = hc; popped[ii] = 0;
-            if (hc == 0) continue;
-            bool ok = true;
-            if (nsig > 1) { int s0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - s0; ok = list_has(W.l_sg + s0, gl, phase); }
-            if (ok) sig_ok |= 1u << ii;
-            long long o = W.l_roff[il]; int cap = W.l_rcap[il];
-            for (int j = 0; j < hc && nc < MC; j++) {
-                int vid = VID[o + ring_slot(hd, j, cap)];
-                unsigned char f = RLP(unsigned char, W.v_flags)[vid];
-                if (f & VF_WAIT_END) any_wait = true;
-                if (f & VF_CAND) {
-                    int nx = RLP(int, W.v_next)[vid], k = nc++;
-                    while (k > 0 && c_vid[k - 1] > vid) { c_vid[k] = c_vid[k - 1]; c_next[k] = c_next[k - 1]; c_pos[k] = c_pos[k - 1]; k--; }
-                    c_vid[k] = vid; c_next[k] = nx; c_pos[k] = (short)((ii << 8) | j);
-                }
+        int i_hd[MD], i_hc[MD], i_pop[MD], i_evc[MD], i_trips[MD], i_poff[MD + 1];
+        double i_co[MD], i_cumdep[MD];
+        unsigned sig_ok = 0, i_dirty = 0;
+        int npos = 0;
+        // A: in-link records, four links per batch (two 128-bit records + tokens + curve value each)
+        for (int b = 0; b < nin; b += 4) {
+            int il_[4]; int4 q_[4], c_[4]; double co_[4], cd_[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) il_[u] = b + u < nin ? W.n_in[i0 + b + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int il = il_[u] < 0 ? il_[0] : il_[u];
+                q_[u] = *reinterpret_cast<const int4 *>(&LQ(W, il) + ln); c_[u] = *reinterpret_cast<const int4 *>(&LC(W, il) + ln);
+                co_[u] = (&LR(W, il) + ln)->cap_out_rem; cd_[u] = W.cum_dep[TLI(W, t, il) + ln];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (il_[u] >= 0) {
+                int ii = b + u, hc = c_[u].y;  // LinkQ {head[0], head[1], tail, tail_k1}, LinkC {pop_k2, hcount, trips, ev_cnt}
+                i_hd[ii] = cur ? q_[u].y : q_[u].x; i_hc[ii] = hc; i_pop[ii] = 0; i_trips[ii] = c_[u].z; i_evc[ii] = c_[u].w;
+                i_co[ii] = co_[u]; i_cumdep[ii] = cd_[u]; i_poff[ii] = npos;
+                if (npos + hc > MC) hc = MC - npos;
+                npos += hc;
             }
         }
-        if (nc > 0 || any_wait) {
-            // requested out-links in order of first appearance, each `lanes` times (260-273)
-            int ol_id[MD], o_hd[MD]; unsigned char expd[MC]; unsigned char c_q[MC];
-            int nol = 0, nexp = 0;
-            for (int k = 0; k < nc; k++) {
-                int nl = c_next[k], q = 255;
-                if (nl >= 0) {
-                    for (int x = 0; x < nol; x++) if (ol_id[x] == nl) { q = x; break; }
-                    if (q == 255 && nol < MD) { q = nol; ol_id[nol++] = nl; }
+        i_poff[nin] = npos;
+        if (npos > 0) {
+            // B: the platoons at the flagged head positions: ids (eight per batch), then flags and next links (four per batch)
+            int p_vid[MC], p_next[MC]; unsigned char p_flag[MC], p_ii[MC];
+            { int ii = 0; for (int p = 0; p < npos; p++) { while (i_poff[ii + 1] <= p) ii++; p_ii[p] = (unsigned char)ii; } }
+            for (int b = 0; b < npos; b += 8) {
+                int v_[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    int p = b + u < npos ? b + u : b, ii = p_ii[p], il = W.n_in[i0 + ii];
+                    v_[u] = VID[W.l_roff[il] + ring_slot(i_hd[ii], p - i_poff[ii], W.l_rcap[il])];
                 }
-                c_q[k] = (unsigned char)q;
+#pragma unroll
+                for (int u = 0; u < 8; u++) if (b + u < npos) p_vid[b + u] = v_[u];
             }
-            for (int q = 0; q < nol; q++) { int lanes = W.l_lanes[ol_id[q]]; for (int x = 0; x < lanes && nexp < MC; x++) expd[nexp++] = (unsigned char)q; }
-            const int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
-            if (!W.hard_det) {  // Fisher-Yates (276-282); step i uses draw number nexp-1-i
-                for (int i = nexp - 1; i > 0; i--) {
-                    int j = ux_rng_below(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nexp - 1 - i), i + 1);
-                    unsigned char tmp = expd[i]; expd[i] = expd[j]; expd[j] = tmp;
-                }
-            }
-            // ---- dependency wait: only now are the pops of lower-level end nodes needed
-            if ((lvl_raw & 0xffff) > 0) {
-                for (int q = W.dep_off[n]; q < W.dep_off[n + 1]; q++) {
-                    int dep = W.dep_list[q];
-                    if ((&NS(W, dep) + ln)->node_act != t) continue;  // idle there: it pops nothing and does not publish
-                    volatile int *done = &NDONE(W, dep) + ln;
-#ifdef UX_EMU
-                    if (*done < t + 1) dev_error(Wr, DERR_DEP_TIMEOUT, n);
-#else
-                    long long spins = 0;
-                    while (*done < t + 1) { __nanosleep(64); if (++spins > UX_DEP_SPIN_BUDGET) { dev_error(Wr, DERR_DEP_TIMEOUT, n); break; } }
-#endif
-                }
-#ifndef UX_EMU
-                __threadfence();
-#endif
-            }
-            for (int q = 0; q < nol; q++) {
-                int ol = ol_id[q], fl = W.l_flags[ol];
-                int hd = (&LQ(W, ol) + ln)->head[cur];
-                if ((fl & LF_SEES_POPS) && (&NS(W, W.l_end[ol]) + ln)->node_act == t) hd += ld_cg(&(&LC(W, ol) + ln)->pop_k2);
-                o_hd[q] = hd;
-            }
-            const double fc = W.n_fc[n];
-            double fc_rem = nr->fc_rem;
-            int n_picks = 0;
-            for (int s = 0; s < nexp; s++) {
-                const int q = expd[s], ol = ol_id[q];
-                LinkQ *olq = &LQ(W, ol) + ln; LinkR *olr = &LR(W, ol) + ln;
-                const int lanes_ol = W.l_lanes[ol], cap_ol = W.l_rcap[ol];
-                const long long oo = W.l_roff[ol];
-                const int tl = olq->tail, sz = tl - o_hd[q];
-                const double dpl = W.l_dpl_dn[ol];
-                bool ok = false;  // acceptance (285-300)
-                if (sz < lanes_ol) ok = true;
-                else if (Xc[oo + ring_slot(o_hd[q], sz - lanes_ol, cap_ol)] > dpl) ok = true;
-                double ci = olr->cap_in_rem;
-                if (ci < W.dn) ok = false;
-                if (fc_rem < W.dn) ok = false;
-                if (!ok) continue;
-                // eligible candidates in ascending id: front of their in-link, outflow tokens, green (305-330)
-                double wsum = 0.0, wbest = 0.0; int nm = 0, kbest = -1;
-                for (int k = 0; k < nc; k++) {
-                    if (c_q[k] != q) continue;
-                    int ii = c_pos[k] >> 8;
-                    if ((c_pos[k] & 255) != popped[ii] || !((sig_ok >> ii) & 1u)) continue;
-                    int il = W.n_in[i0 + ii];
-                    if ((&LR(W, il) + ln)->cap_out_rem < W.dn) continue;
-                    double mp = W.l_mp[il];
-                    if (nm == 0 || mp > wbest) { wbest = mp; kbest = k; }
-                    wsum += mp; nm++;
-                }
-                if (nm == 0) continue;
-                int kp = kbest;
-                if (!W.hard_det) {  // random_choice over the merge priorities (utils.h:62-87)
-                    double u = ux_rng_uniform(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + n_picks));
-                    n_picks++;
-                    int target; double rr = u * wsum;
-                    if (wsum <= 0.0) { target = (int)(u * (double)nm); if (target >= nm) target = nm - 1; } else target = -1;
-                    double accum = 0.0; int seen = 0; kp = -1;
-                    for (int k = 0; k < nc; k++) {
-                        if (c_q[k] != q) continue;
-                        int ii = c_pos[k] >> 8;
-                        if ((c_pos[k] & 255) != popped[ii] || !((sig_ok >> ii) & 1u)) continue;
-                        int il = W.n_in[i0 + ii];
-                        if ((&LR(W, il) + ln)->cap_out_rem < W.dn) continue;
-                        kp = k;  // the last eligible one is the fallback of random_choice
-                        if (target >= 0) { if (seen == target) break; }
-                        else { accum += W.l_mp[il]; if (rr <= accum) break; }
-                        seen++;
+            const unsigned char *v_flags = RLP(unsigned char, W.v_flags); const int *v_next = RLP(int, W.v_next);
+            bool any_wait = false;
+            unsigned char c_idx[MC]; int nc = 0;  // candidate positions sorted by platoon id (250-253)
+            for (int b = 0; b < npos; b += 4) {
+                unsigned char f_[4]; int x_[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { int vid = p_vid[b + u < npos ? b + u : b]; f_[u] = v_flags[vid]; x_[u] = v_next[vid]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (b + u < npos) {
+                    int p = b + u;
+                    p_flag[p] = f_[u]; p_next[p] = x_[u];
+                    if (f_[u] & VF_WAIT_END) any_wait = true;
+                    if (f_[u] & VF_CAND) {
+                        int k = nc++, vid = p_vid[p];
+                        while (k > 0 && p_vid[c_idx[k - 1]] > vid) { c_idx[k] = c_idx[k - 1]; k--; }
+                        c_idx[k] = (unsigned char)p;
                     }
                 }
-                // ---- move candidate kp onto ol
-                const int vid = c_vid[kp], ii = c_pos[kp] >> 8, jj = c_pos[kp] & 255, il = W.n_in[i0 + ii];
-                const long long io = W.l_roff[il];
-                const int cap_il = W.l_rcap[il], slot_in = ring_slot(hd_in[ii], jj, cap_il);
-                LinkR *ilr = &LR(W, il) + ln; LinkC *ilc = &LC(W, il) + ln;
-                ilr->cap_out_rem -= W.dn; olr->cap_in_rem = ci - W.dn;
-                if (fc >= 0.0) fc_rem -= W.dn;
-                W.cum_dep[TLI(W, t, il) + ln] += W.dn; W.cum_arr[TLI(W, t, ol) + ln] += W.dn;
-                double *v_atl = RLP(double, W.v_atl);
-                const double atl = v_atl[vid];
-                {   // record_tt_event (357-362)
-                    int es = (int)(atl / W.dt);
-                    if (es < 0) es = 0;
-                    if (es >= W.T) es = W.T - 1;
-                    int ord = ilc->ev_cnt + 1;
-                    ilc->ev_cnt = ord;
-                    W.ev_ord[TLI(W, es, il) + ln] = ord;
-                    W.ev_tt[TLI(W, es, il) + ln] = (double)t * W.dt - atl;
-                }
-                v_atl[vid] = (double)t * W.dt;
-                const double px = Xc[io + slot_in], pxold = Xo[io + slot_in], pv = V[io + slot_in];
-                RLP(double, W.v_dist)[vid] += px - RLP(double, W.v_entry_x)[vid];
-                popped[ii] += 1;
-                if (W.no_cyclic) { int sn = W.l_start[ol]; RLP(unsigned, W.v_visited)[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
-                { int *v_trav = RLP(int, W.v_trav); int k = v_trav[vid]; v_trav[vid] = k + 1; record_traversal(Wr, vid, k, ol, t); }
-                RLP(int, W.v_link)[vid] = ol;
-                RLP(unsigned char, W.v_flags)[vid] = 0;
-                // carry the residual move onto the new link (400-419)
-                double x_next = RLP(double, W.v_mr)[vid] * W.l_vmax[ol] / W.l_vmax[il];
-                if (sz >= lanes_ol) {
-                    double x_cong = Xo[oo + ring_slot(o_hd[q], sz - lanes_ol, cap_ol)] - dpl;
-                    if (x_cong < 0.0) x_cong = 0.0;
-                    if (x_next > x_cong) x_next = x_cong;
-                }
-                const double len_ol = W.l_length[ol];
-                if (x_next >= len_ol) x_next = len_ol;
-                if (x_next < 0.0) x_next = 0.0;
-                if (sz >= cap_ol) dev_error(Wr, DERR_RING_FULL, ol);
-                else {  // push (lane rule 385-390)
-                    int lane_new = sz > 0 ? (LANE[oo + ring_slot(tl - 1, 0, cap_ol)] + 1) % lanes_ol : 0;
-                    int slot = ring_slot(tl, 0, cap_ol);
-                    Xc[oo + slot] = x_next; Xo[oo + slot] = pxold; V[oo + slot] = pv + x_next / W.dt; VID[oo + slot] = vid; LANE[oo + slot] = lane_new;
-                    olq->tail = tl + 1;
-                }
-                RLP(double, W.v_entry_x)[vid] = x_next;
-                RLP(double, W.v_mr)[vid] = 0.0;
-                c_q[kp] = 254;  // removed from the incoming list
-                // the new front of the in-link may be waiting for its trip end (421-424)
-                if (popped[ii] < hc_in[ii]) {
-                    int fslot = ring_slot(hd_in[ii], popped[ii], cap_il), fvid = VID[io + fslot];
-                    unsigned char ff = RLP(unsigned char, W.v_flags)[fvid];
-                    if (ff & VF_WAIT_END) { rl_end_trip(W, ln, ro, il, fslot, fvid, ff, t, cur); popped[ii] += 1; }
-                }
             }
-            // flush trip-end-waiting fronts (432-441)
-            for (int ii = 0; ii < nin; ii++) {
-                int hc = hc_in[ii];
-                if (hc == 0) continue;
-                int il = W.n_in[i0 + ii], cap_il = W.l_rcap[il];
-                long long io = W.l_roff[il];
-                for (int x = 0; x < hc; x++) {
-                    if (popped[ii] >= hc) break;
-                    int fslot = ring_slot(hd_in[ii], popped[ii], cap_il), fvid = VID[io + fslot];
-                    unsigned char ff = RLP(unsigned char, W.v_flags)[fvid];
-                    if (!(ff & VF_WAIT_END)) break;
-                    rl_end_trip(W, ln, ro, il, fslot, fvid, ff, t, cur); popped[ii] += 1;
+            if (nc > 0 || any_wait) {
+                if (nsig > 1) {
+                    for (int ii = 0; ii < nin; ii++) if (i_hc[ii] > 0) { int il = W.n_in[i0 + ii], s0 = W.l_sg_off[il], gl = W.l_sg_off[il + 1] - s0; if (list_has(W.l_sg + s0, gl, phase)) sig_ok |= 1u << ii; }
+                } else sig_ok = 0xffffffffu;
+                // requested out-links in order of first appearance, each `lanes` times (260-273)
+                int o_id[MD], o_hd[MD], o_tail[MD], o_tail0[MD], o_lastlane[MD], o_lanes[MD], o_woff[MD + 1]; double o_ci[MD], o_cumarr[MD];
+                unsigned char expd[MC], c_q[MC];
+                int nol = 0, nexp = 0;
+                for (int k = 0; k < nc; k++) {
+                    int nl = p_next[c_idx[k]], q = 255;
+                    if (nl >= 0) {
+                        for (int x = 0; x < nol; x++) if (o_id[x] == nl) { q = x; break; }
+                        if (q == 255 && nol < MD) { q = nol; o_id[nol++] = nl; }
+                    }
+                    c_q[k] = (unsigned char)q;
                 }
-                if (popped[ii]) (&LC(W, il) + ln)->pop_k2 = popped[ii];
+                { int acc = 0; for (int q = 0; q < nol; q++) { int lanes = W.l_lanes[o_id[q]]; o_lanes[q] = lanes; o_woff[q] = acc; acc += lanes; for (int x = 0; x < lanes && nexp < MC; x++) expd[nexp++] = (unsigned char)q; } o_woff[nol] = acc; }
+                const int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
+                if (!W.hard_det) {  // Fisher-Yates (276-282); step i uses draw number nexp-1-i
+                    for (int i = nexp - 1; i > 0; i--) {
+                        int j = ux_rng_below(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nexp - 1 - i), i + 1);
+                        unsigned char tmp = expd[i]; expd[i] = expd[j]; expd[j] = tmp;
+                    }
+                }
+                NPROF_T(pt2) NPROF_MAX(1, pt1, pt2)
+                // ---- dependency wait: only now are the pops of lower-level end nodes needed
+                if ((lvl_raw & 0xffff) > 0) {
+                    for (int q = W.dep_off[n]; q < W.dep_off[n + 1]; q++) {
+                        int dep = W.dep_list[q];
+                        if ((&NS(W, dep) + ln)->node_act != t) continue;  // idle there: it pops nothing and does not publish
+                        volatile int *done = &NDONE(W, dep) + ln;
+#ifdef UX_EMU
+                        if (*done < t + 1) dev_error(Wr, DERR_DEP_TIMEOUT, n);
+#else
+                        long long spins = 0;
+                        while (*done < t + 1) { __nanosleep(64); if (++spins > UX_DEP_SPIN_BUDGET) { dev_error(Wr, DERR_DEP_TIMEOUT, n); break; } }
+#endif
+                    }
+#ifndef UX_EMU
+                    __threadfence();
+#endif
+                }
+                NPROF_T(pt3) NPROF_MAX(2, pt2, pt3)
+                // C: out-link records (four per batch), then the lane of the last platoon and the window of the last `lanes` ones
+                for (int b = 0; b < nol; b += 4) {
+                    int4 q_[4]; double ci_[4], ca_[4]; int pk_[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        int ol = o_id[b + u < nol ? b + u : b];
+                        q_[u] = *reinterpret_cast<const int4 *>(&LQ(W, ol) + ln); ci_[u] = (&LR(W, ol) + ln)->cap_in_rem; ca_[u] = W.cum_arr[TLI(W, t, ol) + ln];
+                        pk_[u] = ((W.l_flags[ol] & LF_SEES_POPS) && (&NS(W, W.l_end[ol]) + ln)->node_act == t) ? ld_cg(&(&LC(W, ol) + ln)->pop_k2) : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (b + u < nol) {
+                        int q = b + u;
+                        o_hd[q] = (cur ? q_[u].y : q_[u].x) + pk_[u]; o_tail[q] = o_tail0[q] = q_[u].z; o_ci[q] = ci_[u]; o_cumarr[q] = ca_[u];
+                    }
+                }
+                double w_x[MC], w_xo[MC];  // window of the last `lanes` platoons of each out-link, oldest first (as many as there are)
+                {
+                    const int wtot = o_woff[nol] < MC ? o_woff[nol] : MC;
+                    for (int b = 0; b < wtot; b += 4) {
+                        double a_[4], o_[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            int e = b + u < wtot ? b + u : b, q = 0;
+                            while (o_woff[q + 1] <= e) q++;
+                            int k = e - o_woff[q], sz = o_tail[q] - o_hd[q], wn = sz < o_lanes[q] ? sz : o_lanes[q];
+                            a_[u] = 0.0; o_[u] = 0.0;
+                            if (k < wn) {
+                                size_t at = (size_t)W.l_roff[o_id[q]] + ring_slot(o_hd[q], sz - wn + k, W.l_rcap[o_id[q]]);
+                                a_[u] = Xc[at]; o_[u] = Xo[at];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if (b + u < wtot) { w_x[b + u] = a_[u]; w_xo[b + u] = o_[u]; }
+                    }
+                    for (int q = 0; q < nol; q++) {
+                        int sz = o_tail[q] - o_hd[q];
+                        o_lastlane[q] = sz > 0 ? LANE[W.l_roff[o_id[q]] + ring_slot(o_tail[q] - 1, 0, W.l_rcap[o_id[q]])] : -1;
+                    }
+                }
+                unsigned char w_n[MD];  // platoons currently in the window
+                for (int q = 0; q < nol; q++) { int sz = o_tail[q] - o_hd[q]; w_n[q] = (unsigned char)(sz < o_lanes[q] ? sz : o_lanes[q]); }
+                NPROF_T(pt4) NPROF_MAX(3, pt3, pt4)
+                const double fc = W.n_fc[n];
+                double fc_rem = nr->fc_rem;
+                int n_picks = 0;
+                // trip end of the front platoon (position p) of in-link ii: Vehicle::end_trip (886-927)
+                auto end_front = [&](int ii, int p) {
+                    const int il = W.n_in[i0 + ii], vid = p_vid[p];
+                    const double atl = RLP(double, W.v_atl)[vid], ex = RLP(double, W.v_entry_x)[vid], di = RLP(double, W.v_dist)[vid];
+                    const double x = Xc[W.l_roff[il] + ring_slot(i_hd[ii], p - i_poff[ii], W.l_rcap[il])];
+                    i_trips[ii] += 1; i_cumdep[ii] += W.dn; i_dirty |= 1u << ii;
+                    int s = (int)(atl / W.dt);
+                    if (s < 0) s = 0;
+                    if (s >= W.T) s = W.T - 1;
+                    int ord = ++i_evc[ii];
+                    W.ev_ord[TLI(W, s, il) + ln] = ord;
+                    W.ev_tt[TLI(W, s, il) + ln] = ((double)t + 1.0) * W.dt - atl;
+                    RLP(double, W.v_atl)[vid] = (double)t * W.dt;
+                    RLP(double, W.v_dist)[vid] = di + (x - ex);
+                    RLP(int, W.v_link)[vid] = -1;
+                    if (p_flag[p] & VF_ABORT) { RLP(int, W.v_state)[vid] = UX_VS_ABORT; RLP(int, W.v_arr_ts)[vid] = -1; RLP(double, W.v_tt)[vid] = -1.0; }
+                    else { RLP(int, W.v_state)[vid] = UX_VS_END; RLP(int, W.v_arr_ts)[vid] = t; RLP(double, W.v_tt)[vid] = (double)t * W.dt - (double)W.v_depart_ts[vid] * W.dt; }
+                    if (W.log_mode) { RLP(int, W.v_end_ts)[vid] = t; RLP(unsigned char, W.v_end_kind)[vid] = 2; }
+                    RLP(unsigned char, W.v_flags)[vid] = 0;
+                    i_pop[ii] += 1;
+                };
+                for (int s = 0; s < nexp; s++) {
+                    const int q = expd[s];
+                    const int lanes_ol = o_lanes[q], sz = o_tail[q] - o_hd[q], w0 = o_woff[q];
+                    bool ok = false;  // acceptance (285-300)
+                    if (sz < lanes_ol) ok = true;
+                    else if (w_x[w0] > W.l_dpl_dn[o_id[q]]) ok = true;
+                    if (o_ci[q] < W.dn) ok = false;
+                    if (fc_rem < W.dn) ok = false;
+                    if (!ok) continue;
+                    // eligible candidates in ascending id: front of their in-link, outflow tokens, green (305-330)
+                    double wsum = 0.0, wbest = 0.0; int nm = 0, kbest = -1;
+                    for (int k = 0; k < nc; k++) {
+                        if (c_q[k] != q) continue;
+                        int p = c_idx[k], ii = p_ii[p];
+                        if (p - i_poff[ii] != i_pop[ii] || !((sig_ok >> ii) & 1u) || i_co[ii] < W.dn) continue;
+                        double mp = W.l_mp[W.n_in[i0 + ii]];
+                        if (nm == 0 || mp > wbest) { wbest = mp; kbest = k; }
+                        wsum += mp; nm++;
+                    }
+                    if (nm == 0) continue;
+                    int kp = kbest;
+                    if (!W.hard_det) {  // random_choice over the merge priorities (utils.h:62-87)
+                        double u = ux_rng_uniform(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + n_picks));
+                        n_picks++;
+                        int target = -1; double rr = u * wsum;
+                        if (wsum <= 0.0) { target = (int)(u * (double)nm); if (target >= nm) target = nm - 1; }
+                        double accum = 0.0; int seen = 0; kp = -1;
+                        for (int k = 0; k < nc; k++) {
+                            if (c_q[k] != q) continue;
+                            int p = c_idx[k], ii = p_ii[p];
+                            if (p - i_poff[ii] != i_pop[ii] || !((sig_ok >> ii) & 1u) || i_co[ii] < W.dn) continue;
+                            kp = k;  // the last eligible one is the fallback of random_choice
+                            if (target >= 0) { if (seen == target) break; }
+                            else { accum += W.l_mp[W.n_in[i0 + ii]]; if (rr <= accum) break; }
+                            seen++;
+                        }
+                    }
+                    // ---- move candidate kp onto the out-link: everything it needs in one batch of loads, then stores only
+                    const int p = c_idx[kp], vid = p_vid[p], ii = p_ii[p], il = W.n_in[i0 + ii], ol = o_id[q];
+                    const size_t in_at = (size_t)W.l_roff[il] + ring_slot(i_hd[ii], p - i_poff[ii], W.l_rcap[il]);
+                    const double atl = RLP(double, W.v_atl)[vid], px = Xc[in_at], pxold = Xo[in_at], pv = V[in_at], ex = RLP(double, W.v_entry_x)[vid],
+                                 di = RLP(double, W.v_dist)[vid], mr = RLP(double, W.v_mr)[vid];
+                    const int trav = RLP(int, W.v_trav)[vid];
+                    const double vm_ol = W.l_vmax[ol], vm_il = W.l_vmax[il], len_ol = W.l_length[ol], dpl = W.l_dpl_dn[ol];
+                    i_co[ii] -= W.dn; o_ci[q] -= W.dn; i_dirty |= 1u << ii;
+                    if (fc >= 0.0) fc_rem -= W.dn;
+                    i_cumdep[ii] += W.dn; o_cumarr[q] += W.dn;
+                    {   // record_tt_event (357-362)
+                        int es = (int)(atl / W.dt);
+                        if (es < 0) es = 0;
+                        if (es >= W.T) es = W.T - 1;
+                        int ord = ++i_evc[ii];
+                        W.ev_ord[TLI(W, es, il) + ln] = ord;
+                        W.ev_tt[TLI(W, es, il) + ln] = (double)t * W.dt - atl;
+                    }
+                    RLP(double, W.v_atl)[vid] = (double)t * W.dt;
+                    RLP(double, W.v_dist)[vid] = di + (px - ex);
+                    i_pop[ii] += 1;
+                    if (W.no_cyclic) { int sn = W.l_start[ol]; RLP(unsigned, W.v_visited)[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
+                    RLP(int, W.v_trav)[vid] = trav + 1; record_traversal(Wr, vid, trav, ol, t);
+                    RLP(int, W.v_link)[vid] = ol;
+                    RLP(unsigned char, W.v_flags)[vid] = 0;
+                    // carry the residual move onto the new link (400-419)
+                    double x_next = mr * vm_ol / vm_il;
+                    if (sz >= lanes_ol) {
+                        double x_cong = w_xo[w0] - dpl;
+                        if (x_cong < 0.0) x_cong = 0.0;
+                        if (x_next > x_cong) x_next = x_cong;
+                    }
+                    if (x_next >= len_ol) x_next = len_ol;
+                    if (x_next < 0.0) x_next = 0.0;
+                    if (sz >= W.l_rcap[ol]) dev_error(Wr, DERR_RING_FULL, ol);
+                    else {  // push (lane rule 385-390)
+                        int lane_new = sz > 0 ? (o_lastlane[q] + 1) % lanes_ol : 0;
+                        size_t at = (size_t)W.l_roff[ol] + ring_slot(o_tail[q], 0, W.l_rcap[ol]);
+                        Xc[at] = x_next; Xo[at] = pxold; V[at] = pv + x_next / W.dt; VID[at] = vid; LANE[at] = lane_new;
+                        o_tail[q] += 1; o_lastlane[q] = lane_new;
+                        if (w_n[q] < lanes_ol) { w_x[w0 + w_n[q]] = x_next; w_xo[w0 + w_n[q]] = pxold; w_n[q] += 1; }
+                        else {
+                            for (int e = w0; e < w0 + lanes_ol - 1; e++) { w_x[e] = w_x[e + 1]; w_xo[e] = w_xo[e + 1]; }
+                            w_x[w0 + lanes_ol - 1] = x_next; w_xo[w0 + lanes_ol - 1] = pxold;
+                        }
+                    }
+                    RLP(double, W.v_entry_x)[vid] = x_next;
+                    RLP(double, W.v_mr)[vid] = 0.0;
+                    c_q[kp] = 254;  // removed from the incoming list
+                    // the new front of the in-link may be waiting for its trip end (421-424)
+                    if (i_pop[ii] < i_hc[ii]) { int fp = i_poff[ii] + i_pop[ii]; if (fp < npos && (p_flag[fp] & VF_WAIT_END)) end_front(ii, fp); }
+                }
+                NPROF_T(pt5) NPROF_MAX(4, pt4, pt5)
+                // flush trip-end-waiting fronts (432-441)
+                for (int ii = 0; ii < nin; ii++) {
+                    int hc = i_hc[ii];
+                    for (int x = 0; x < hc; x++) {
+                        if (i_pop[ii] >= hc) break;
+                        int fp = i_poff[ii] + i_pop[ii];
+                        if (fp >= npos || !(p_flag[fp] & VF_WAIT_END)) break;
+                        end_front(ii, fp);
+                    }
+                }
+                // write the per-link accumulators back
+                for (int ii = 0; ii < nin; ii++) if ((i_dirty >> ii) & 1u) {
+                    int il = W.n_in[i0 + ii];
+                    LinkC *lc = &LC(W, il) + ln;
+                    (&LR(W, il) + ln)->cap_out_rem = i_co[ii]; W.cum_dep[TLI(W, t, il) + ln] = i_cumdep[ii];
+                    lc->pop_k2 = i_pop[ii]; lc->ev_cnt = i_evc[ii]; lc->trips = i_trips[ii];
+                }
+                for (int q = 0; q < nol; q++) if (o_tail[q] != o_tail0[q]) {
+                    int ol = o_id[q];
+                    (&LR(W, ol) + ln)->cap_in_rem = o_ci[q]; W.cum_arr[TLI(W, t, ol) + ln] = o_cumarr[q]; (&LQ(W, ol) + ln)->tail = o_tail[q];
+                }
+                nr->fc_rem = fc_rem;
+                NPROF_T(pt6) NPROF_MAX(5, pt5, pt6) NPROF_MAX(6, pt0, pt6)
             }
-            nr->fc_rem = fc_rem;
         }
     }
-    if ((lvl_raw >> 16) && ns->node_act == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes)
+    if ((lvl_raw & 0x10000) && ns->node_act == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes)
 #ifndef UX_EMU
         __threadfence();
 #endif
         *((volatile int *)(&NDONE(W, n) + ln)) = t + 1;
+    }
+}
+
+// k_node_h -- the node step of an ensemble as ONE launch over a table of blocks, each in one of two forms:
+//   form 1 (replica lanes): four nodes x 32 replicas, node_step_rl above -- all light nodes;
+//   form 0 (warp per node): four nodes of one replica, pre_node + xfer_node of k_node -- the heavy nodes (many lanes in or out:
+//   a single thread walking 30 slots x 20 candidates is slower than a warp that scans them in parallel on shared memory).
+// The table is ordered by dependency level (heavy blocks of a level, then its light blocks), so a waiting lane or warp only
+// ever waits for blocks with a smaller index, as in k_node.
+// HEAVY = false: the table holds form-1 blocks only (no shared-memory staging is declared, the L1 keeps the threads' local arrays).
+template <int MC, int MD, bool HEAVY>
+__global__ void __launch_bounds__(32 * NRL_WARPS, 4) k_node_h(const DevWorld *worlds, int step_off, int R, const int4 *blks) {
+    const int4 b = blks[blockIdx.x];  // {form, first position in lvl_nodes, nodes in this block, replica (form 0) | lane group (form 1)}
+    LOAD_WORLD_N(W, worlds, 64, b.x ? b.w * 32 : b.w)
+    const int wib = (int)(threadIdx.x >> 5), ln = (int)(threadIdx.x & 31);
+    if (wib >= b.z) return;
+    const int pos = b.y + wib, n = W.lvl_nodes[pos], t = *W.t_base + step_off;
+    const int lvl_raw = W.lvl_level[pos];
+    if (b.x) {
+        const int r = b.w * 32 + ln;
+        if (r < R) node_step_rl<MC, MD>(W, worlds[r], ln, n, t, lvl_raw);
+        return;
+    }
+    if constexpr (HEAVY) {
+        __shared__ NodeSmem<MC, MD> sm_all[NRL_WARPS];
+        __shared__ double tt_all[NRL_WARPS][MD];
+        __shared__ int rel_all[NRL_WARPS];
+        WARP_BEGIN
+        pre_node(W, sm_all[wib].pre, tt_all[wib], &rel_all[wib], n, t, ln);
+#ifndef UX_EMU
+        __threadfence_block();
+#endif
+        xfer_node(W, sm_all[wib].xf, n, t, (lvl_raw & 0xffff) > 0);
+        if ((lvl_raw & 0x10000) && NS(W, n).node_act == t) {
+            WARP_SYNC();
+            WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)&NDONE(W, n)) = t + 1; }
+        }
     }
 }
 

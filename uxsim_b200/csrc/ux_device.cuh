@@ -182,12 +182,16 @@ UX_DEV bool list_has(const int *a, int n, int v) {
 }
 
 // Vehicle::route_next_link_choice (traffi.cpp:934-1033).  Returns the chosen link id or -1.
-UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned entity, unsigned purpose, unsigned draw, int *deferred_err = nullptr) {
-    int o0 = W.n_out_off[node], nset = W.n_out_off[node + 1] - o0;
+// S supplies the static tables (network, platoon destinations), W the replica's own state (route lists, traversal counts,
+// visited sets, preference rows, seed, error word).  They are the same struct except in the replica-lane kernels, where S is the
+// lane group's world staged in shared memory and W the lane's own pointer table in global memory (read for a handful of pointers only).
+UX_DEV int route_choice(const DevWorld &S, const DevWorld &W, int vid, int node, int t, unsigned entity, unsigned purpose, unsigned draw, int *deferred_err = nullptr) {
+    int o0 = S.n_out_off[node], nset = S.n_out_off[node + 1] - o0;
     if (nset == 0) return -1;
-    const int *linkset = W.n_out + o0;
-    if (W.vl_off[0]) {  // specified_route
-        int r0 = W.vl_off[0][vid], len = W.vl_off[0][vid + 1] - r0;
+    const int *linkset = S.n_out + o0;
+    const int *vo0 = W.vl_off[0], *vo1 = W.vl_off[1], *vo2 = W.vl_off[2];
+    if (vo0) {  // specified_route
+        int r0 = vo0[vid], len = vo0[vid + 1] - r0;
         if (len > 0) {
             int traveled = W.v_trav[vid];
             if (traveled >= len) { if (deferred_err) *deferred_err = DERR_ROUTE_EXHAUSTED; else dev_error(W, DERR_ROUTE_EXHAUSTED, vid); return -1; }
@@ -199,16 +203,16 @@ UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned en
     int bufa[UX_MAXDEG], bufb[UX_MAXDEG];
     int *out = bufa, *tmp = bufb, n = 0;
     for (int i = 0; i < nset; i++) out[n++] = linkset[i];
-    if (W.vl_off[1]) {  // links_preferred: intersection if non-empty
-        int r0 = W.vl_off[1][vid], len = W.vl_off[1][vid + 1] - r0;
+    if (vo1) {  // links_preferred: intersection if non-empty
+        int r0 = vo1[vid], len = vo1[vid + 1] - r0;
         if (len > 0) {
             int m = 0;
             for (int i = 0; i < n; i++) if (list_has(W.vl_list[1] + r0, len, out[i])) tmp[m++] = out[i];
             if (m > 0) { int *s = out; out = tmp; tmp = s; n = m; }
         }
     }
-    if (W.vl_off[2]) {  // links_avoid: subtraction, error if nothing is left
-        int r0 = W.vl_off[2][vid], len = W.vl_off[2][vid + 1] - r0;
+    if (vo2) {  // links_avoid: subtraction, error if nothing is left
+        int r0 = vo2[vid], len = vo2[vid + 1] - r0;
         if (len > 0) {
             int m = 0;
             for (int i = 0; i < n; i++) if (!list_has(W.vl_list[2] + r0, len, out[i])) tmp[m++] = out[i];
@@ -216,23 +220,27 @@ UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned en
             if (n == 0) { if (deferred_err) *deferred_err = DERR_AVOID_ALL; else dev_error(W, DERR_AVOID_ALL, vid); return -1; }
         }
     }
-    if (W.no_cyclic) {
-        const unsigned *vis = W.v_visited + (size_t)vid * W.vis_words;
+    if (S.no_cyclic) {
+        const unsigned *vis = W.v_visited + (size_t)vid * S.vis_words;
         int m = 0;
-        for (int i = 0; i < n; i++) { int e = W.l_end[out[i]]; if (!((vis[e >> 5] >> (e & 31)) & 1u)) tmp[m++] = out[i]; }
+        for (int i = 0; i < n; i++) { int e = S.l_end[out[i]]; if (!((vis[e >> 5] >> (e & 31)) & 1u)) tmp[m++] = out[i]; }
         if (m > 0) { int *s = out; out = tmp; tmp = s; n = m; }
     }
     if (n == 0) return -1;
     double pw[UX_MAXDEG];
-    int row = W.dest_row[W.v_dest[vid]];
-    for (int i = 0; i < n; i++) pw[i] = row >= 0 ? W.pref[(size_t)row * W.L + out[i]] : 0.0;
-    if (W.hard_det) {
+    int row = S.dest_row[S.v_dest[vid]];
+    const double *pref = W.pref + (size_t)(row >= 0 ? row : 0) * S.L;
+    for (int i = 0; i < n; i++) pw[i] = row >= 0 ? pref[out[i]] : 0.0;
+    if (S.hard_det) {
         int best = 0;
         for (int i = 1; i < n; i++) if (pw[i] > pw[best]) best = i;
         return out[best];
     }
     double u = ux_rng_uniform(W.seed, (uint32_t)t, entity, purpose, draw);
     return out[weighted_pick(pw, n, u)];
+}
+UX_DEV int route_choice(const DevWorld &W, int vid, int node, int t, unsigned entity, unsigned purpose, unsigned draw, int *deferred_err = nullptr) {
+    return route_choice(W, W, vid, node, t, entity, purpose, draw, deferred_err);
 }
 
 // acceptance test of an out-link seen with effective head `hd` (traffi.cpp:130-142, 285-297)

@@ -758,7 +758,7 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
         const int gh0 = gh;
         for (int i = 0; i < natt; i++) {
             int vid = W.gen_list[g0 + gh], e = 0;
-            int ol = route_choice(Wr, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
+            int ol = route_choice(W, Wr, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
             if (e) { dev_error(Wr, e, vid); break; }
             RLP(int, W.v_next)[vid] = ol;
             if (ol < 0) break;
@@ -781,7 +781,8 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
             if (W.log_mode) RLP(int, W.v_gen_ts)[vid] = t;
             RLP(double, W.v_atl)[vid] = (double)t * W.dt;
             RLP(double, W.v_entry_x)[vid] = 0.0;
-            mark_entered(Wr, vid, ol, t);
+            if (W.no_cyclic) { int sn = W.l_start[ol]; RLP(unsigned, W.v_visited)[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }  // mark_entered (160-166)
+            { int *v_trav = RLP(int, W.v_trav); int k = v_trav[vid]; v_trav[vid] = k + 1; RLP(int, W.v_link)[vid] = ol; if (W.tv_count) record_traversal(Wr, vid, k, ol, t); }
             W.cum_arr[TLI(W, t, ol) + ln] += W.dn;
             lr->cap_in_rem = ci - W.dn;
         }
@@ -798,9 +799,12 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
     const bool act = ns->node_act == t && nin > 0;
     if (act) {
         const int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = ns->sig_phase;
-        int i_hd[MD], i_hc[MD], i_pop[MD], i_evc[MD], i_trips[MD], i_poff[MD + 1];
-        double i_co[MD], i_cumdep[MD];
-        unsigned sig_ok = 0, i_dirty = 0;
+        int i_hd[MD], i_hc[MD], i_evc[MD], i_trips[MD], i_poff[MD + 1];
+        unsigned long long pops0 = 0, pops1 = 0;  // platoons popped from in-link ii so far: 8 bits each, in registers (read by every eligibility test)
+#define I_POP(ii_) ((int)(((ii_) < 8 ? pops0 >> ((ii_) * 8) : pops1 >> (((ii_) - 8) * 8)) & 255ull))
+#define I_POP_INC(ii_) { if ((ii_) < 8) pops0 += 1ull << ((ii_) * 8); else pops1 += 1ull << (((ii_) - 8) * 8); }
+        double i_co[MD], i_cumdep[MD], i_mp[MD];
+        unsigned sig_ok = 0, i_dirty = 0, co_ok = 0;  // co_ok: in-links with outflow tokens left
         int npos = 0;
         // A: in-link records, four links per batch (two 128-bit records + tokens + curve value each)
         for (int b = 0; b < nin; b += 4) {
@@ -816,8 +820,9 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
 #pragma unroll
             for (int u = 0; u < 4; u++) if (il_[u] >= 0) {
                 int ii = b + u, hc = c_[u].y;  // LinkQ {head[0], head[1], tail, tail_k1}, LinkC {pop_k2, hcount, trips, ev_cnt}
-                i_hd[ii] = cur ? q_[u].y : q_[u].x; i_hc[ii] = hc; i_pop[ii] = 0; i_trips[ii] = c_[u].z; i_evc[ii] = c_[u].w;
-                i_co[ii] = co_[u]; i_cumdep[ii] = cd_[u]; i_poff[ii] = npos;
+                i_hd[ii] = cur ? q_[u].y : q_[u].x; i_hc[ii] = hc; i_trips[ii] = c_[u].z; i_evc[ii] = c_[u].w;
+                i_co[ii] = co_[u]; i_cumdep[ii] = cd_[u]; i_poff[ii] = npos; i_mp[ii] = W.l_mp[il_[u]];
+                if (co_[u] >= W.dn) co_ok |= 1u << ii;
                 if (npos + hc > MC) hc = MC - npos;
                 npos += hc;
             }
@@ -862,15 +867,15 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                 } else sig_ok = 0xffffffffu;
                 // requested out-links in order of first appearance, each `lanes` times (260-273)
                 int o_id[MD], o_hd[MD], o_tail[MD], o_tail0[MD], o_lastlane[MD], o_lanes[MD], o_woff[MD + 1]; double o_ci[MD], o_cumarr[MD];
-                unsigned char expd[MC], c_q[MC];
+                unsigned char expd[MC]; int c_w[MC];  // c_w: out-link index | in-link index << 8 | position from the head << 16 (out-link 255: none, 254: moved)
                 int nol = 0, nexp = 0;
                 for (int k = 0; k < nc; k++) {
-                    int nl = p_next[c_idx[k]], q = 255;
+                    int p = c_idx[k], nl = p_next[p], q = 255;
                     if (nl >= 0) {
                         for (int x = 0; x < nol; x++) if (o_id[x] == nl) { q = x; break; }
                         if (q == 255 && nol < MD) { q = nol; o_id[nol++] = nl; }
                     }
-                    c_q[k] = (unsigned char)q;
+                    c_w[k] = q | ((int)p_ii[p] << 8) | ((p - i_poff[p_ii[p]]) << 16);
                 }
                 { int acc = 0; for (int q = 0; q < nol; q++) { int lanes = W.l_lanes[o_id[q]]; o_lanes[q] = lanes; o_woff[q] = acc; acc += lanes; for (int x = 0; x < lanes && nexp < MC; x++) expd[nexp++] = (unsigned char)q; } o_woff[nol] = acc; }
                 const int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
@@ -917,10 +922,10 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                 double w_x[MC], w_xo[MC];  // window of the last `lanes` platoons of each out-link, oldest first (as many as there are)
                 {
                     const int wtot = o_woff[nol] < MC ? o_woff[nol] : MC;
-                    for (int b = 0; b < wtot; b += 4) {
-                        double a_[4], o_[4];
+                    for (int b = 0; b < wtot; b += 8) {
+                        double a_[8], o_[8];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
+                        for (int u = 0; u < 8; u++) {
                             int e = b + u < wtot ? b + u : b, q = 0;
                             while (o_woff[q + 1] <= e) q++;
                             int k = e - o_woff[q], sz = o_tail[q] - o_hd[q], wn = sz < o_lanes[q] ? sz : o_lanes[q];
@@ -931,14 +936,21 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; u++) if (b + u < wtot) { w_x[b + u] = a_[u]; w_xo[b + u] = o_[u]; }
+                        for (int u = 0; u < 8; u++) if (b + u < wtot) { w_x[b + u] = a_[u]; w_xo[b + u] = o_[u]; }
                     }
-                    for (int q = 0; q < nol; q++) {
-                        int sz = o_tail[q] - o_hd[q];
-                        o_lastlane[q] = sz > 0 ? LANE[W.l_roff[o_id[q]] + ring_slot(o_tail[q] - 1, 0, W.l_rcap[o_id[q]])] : -1;
+                    for (int b = 0; b < nol; b += 4) {
+                        int l_[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            int q = b + u < nol ? b + u : b, sz = o_tail[q] - o_hd[q];
+                            l_[u] = sz > 0 ? LANE[W.l_roff[o_id[q]] + ring_slot(o_tail[q] - 1, 0, W.l_rcap[o_id[q]])] : -1;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if (b + u < nol) o_lastlane[b + u] = l_[u];
                     }
                 }
-                unsigned char w_n[MD];  // platoons currently in the window
+                unsigned char w_n[MD], w_f[MD];  // platoons in the window; once it is full (`lanes` entries) it is circular and w_f is its oldest entry
+                for (int q = 0; q < nol; q++) w_f[q] = 0;
                 for (int q = 0; q < nol; q++) { int sz = o_tail[q] - o_hd[q]; w_n[q] = (unsigned char)(sz < o_lanes[q] ? sz : o_lanes[q]); }
                 NPROF_T(pt4) NPROF_MAX(3, pt3, pt4)
                 const double fc = W.n_fc[n];
@@ -963,28 +975,31 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     else { RLP(int, W.v_state)[vid] = UX_VS_END; RLP(int, W.v_arr_ts)[vid] = t; RLP(double, W.v_tt)[vid] = (double)t * W.dt - (double)W.v_depart_ts[vid] * W.dt; }
                     if (W.log_mode) { RLP(int, W.v_end_ts)[vid] = t; RLP(unsigned char, W.v_end_kind)[vid] = 2; }
                     RLP(unsigned char, W.v_flags)[vid] = 0;
-                    i_pop[ii] += 1;
+                    I_POP_INC(ii)
                 };
+                unsigned dead = 0;  // out-links whose slot found nothing to move since the last move: nothing they depend on has changed, skip
                 for (int s = 0; s < nexp; s++) {
                     const int q = expd[s];
+                    if ((dead >> q) & 1u) continue;
                     const int lanes_ol = o_lanes[q], sz = o_tail[q] - o_hd[q], w0 = o_woff[q];
                     bool ok = false;  // acceptance (285-300)
                     if (sz < lanes_ol) ok = true;
-                    else if (w_x[w0] > W.l_dpl_dn[o_id[q]]) ok = true;
+                    else if (w_x[w0 + w_f[q]] > W.l_dpl_dn[o_id[q]]) ok = true;
                     if (o_ci[q] < W.dn) ok = false;
                     if (fc_rem < W.dn) ok = false;
-                    if (!ok) continue;
+                    if (!ok) { dead |= 1u << q; continue; }
                     // eligible candidates in ascending id: front of their in-link, outflow tokens, green (305-330)
+                    const unsigned in_ok = sig_ok & co_ok;
                     double wsum = 0.0, wbest = 0.0; int nm = 0, kbest = -1;
                     for (int k = 0; k < nc; k++) {
-                        if (c_q[k] != q) continue;
-                        int p = c_idx[k], ii = p_ii[p];
-                        if (p - i_poff[ii] != i_pop[ii] || !((sig_ok >> ii) & 1u) || i_co[ii] < W.dn) continue;
-                        double mp = W.l_mp[W.n_in[i0 + ii]];
+                        const int cw = c_w[k], ii = (cw >> 8) & 255;
+                        if ((cw & 255) != q || !((in_ok >> ii) & 1u) || (cw >> 16) != I_POP(ii)) continue;
+                        double mp = i_mp[ii];
                         if (nm == 0 || mp > wbest) { wbest = mp; kbest = k; }
                         wsum += mp; nm++;
                     }
-                    if (nm == 0) continue;
+                    if (nm == 0) { dead |= 1u << q; continue; }
+                    dead = 0;
                     int kp = kbest;
                     if (!W.hard_det) {  // random_choice over the merge priorities (utils.h:62-87)
                         double u = ux_rng_uniform(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + n_picks));
@@ -993,12 +1008,11 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                         if (wsum <= 0.0) { target = (int)(u * (double)nm); if (target >= nm) target = nm - 1; }
                         double accum = 0.0; int seen = 0; kp = -1;
                         for (int k = 0; k < nc; k++) {
-                            if (c_q[k] != q) continue;
-                            int p = c_idx[k], ii = p_ii[p];
-                            if (p - i_poff[ii] != i_pop[ii] || !((sig_ok >> ii) & 1u) || i_co[ii] < W.dn) continue;
+                            const int cw = c_w[k], ii = (cw >> 8) & 255;
+                            if ((cw & 255) != q || !((in_ok >> ii) & 1u) || (cw >> 16) != I_POP(ii)) continue;
                             kp = k;  // the last eligible one is the fallback of random_choice
                             if (target >= 0) { if (seen == target) break; }
-                            else { accum += W.l_mp[W.n_in[i0 + ii]]; if (rr <= accum) break; }
+                            else { accum += i_mp[ii]; if (rr <= accum) break; }
                             seen++;
                         }
                     }
@@ -1010,6 +1024,7 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     const int trav = RLP(int, W.v_trav)[vid];
                     const double vm_ol = W.l_vmax[ol], vm_il = W.l_vmax[il], len_ol = W.l_length[ol], dpl = W.l_dpl_dn[ol];
                     i_co[ii] -= W.dn; o_ci[q] -= W.dn; i_dirty |= 1u << ii;
+                    if (i_co[ii] < W.dn) co_ok &= ~(1u << ii);
                     if (fc >= 0.0) fc_rem -= W.dn;
                     i_cumdep[ii] += W.dn; o_cumarr[q] += W.dn;
                     {   // record_tt_event (357-362)
@@ -1022,15 +1037,15 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     }
                     RLP(double, W.v_atl)[vid] = (double)t * W.dt;
                     RLP(double, W.v_dist)[vid] = di + (px - ex);
-                    i_pop[ii] += 1;
+                    I_POP_INC(ii)
                     if (W.no_cyclic) { int sn = W.l_start[ol]; RLP(unsigned, W.v_visited)[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
-                    RLP(int, W.v_trav)[vid] = trav + 1; record_traversal(Wr, vid, trav, ol, t);
+                    RLP(int, W.v_trav)[vid] = trav + 1; if (W.tv_count) record_traversal(Wr, vid, trav, ol, t);
                     RLP(int, W.v_link)[vid] = ol;
                     RLP(unsigned char, W.v_flags)[vid] = 0;
                     // carry the residual move onto the new link (400-419)
                     double x_next = mr * vm_ol / vm_il;
                     if (sz >= lanes_ol) {
-                        double x_cong = w_xo[w0] - dpl;
+                        double x_cong = w_xo[w0 + w_f[q]] - dpl;
                         if (x_cong < 0.0) x_cong = 0.0;
                         if (x_next > x_cong) x_next = x_cong;
                     }
@@ -1043,24 +1058,21 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                         Xc[at] = x_next; Xo[at] = pxold; V[at] = pv + x_next / W.dt; VID[at] = vid; LANE[at] = lane_new;
                         o_tail[q] += 1; o_lastlane[q] = lane_new;
                         if (w_n[q] < lanes_ol) { w_x[w0 + w_n[q]] = x_next; w_xo[w0 + w_n[q]] = pxold; w_n[q] += 1; }
-                        else {
-                            for (int e = w0; e < w0 + lanes_ol - 1; e++) { w_x[e] = w_x[e + 1]; w_xo[e] = w_xo[e + 1]; }
-                            w_x[w0 + lanes_ol - 1] = x_next; w_xo[w0 + lanes_ol - 1] = pxold;
-                        }
+                        else { int e = w0 + w_f[q]; w_x[e] = x_next; w_xo[e] = pxold; w_f[q] = (unsigned char)(w_f[q] + 1 == lanes_ol ? 0 : w_f[q] + 1); }
                     }
                     RLP(double, W.v_entry_x)[vid] = x_next;
                     RLP(double, W.v_mr)[vid] = 0.0;
-                    c_q[kp] = 254;  // removed from the incoming list
+                    c_w[kp] |= 254;  // removed from the incoming list (out-link index 254 matches no slot)
                     // the new front of the in-link may be waiting for its trip end (421-424)
-                    if (i_pop[ii] < i_hc[ii]) { int fp = i_poff[ii] + i_pop[ii]; if (fp < npos && (p_flag[fp] & VF_WAIT_END)) end_front(ii, fp); }
+                    if (I_POP(ii) < i_hc[ii]) { int fp = i_poff[ii] + I_POP(ii); if (fp < npos && (p_flag[fp] & VF_WAIT_END)) end_front(ii, fp); }
                 }
                 NPROF_T(pt5) NPROF_MAX(4, pt4, pt5)
                 // flush trip-end-waiting fronts (432-441)
                 for (int ii = 0; ii < nin; ii++) {
                     int hc = i_hc[ii];
                     for (int x = 0; x < hc; x++) {
-                        if (i_pop[ii] >= hc) break;
-                        int fp = i_poff[ii] + i_pop[ii];
+                        if (I_POP(ii) >= hc) break;
+                        int fp = i_poff[ii] + I_POP(ii);
                         if (fp >= npos || !(p_flag[fp] & VF_WAIT_END)) break;
                         end_front(ii, fp);
                     }
@@ -1070,7 +1082,7 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     int il = W.n_in[i0 + ii];
                     LinkC *lc = &LC(W, il) + ln;
                     (&LR(W, il) + ln)->cap_out_rem = i_co[ii]; W.cum_dep[TLI(W, t, il) + ln] = i_cumdep[ii];
-                    lc->pop_k2 = i_pop[ii]; lc->ev_cnt = i_evc[ii]; lc->trips = i_trips[ii];
+                    lc->pop_k2 = I_POP(ii); lc->ev_cnt = i_evc[ii]; lc->trips = i_trips[ii];
                 }
                 for (int q = 0; q < nol; q++) if (o_tail[q] != o_tail0[q]) {
                     int ol = o_id[q];
@@ -1089,6 +1101,8 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
     }
 }
 
+#undef I_POP
+#undef I_POP_INC
 // k_node_h -- the node step of an ensemble as ONE launch over a table of blocks, each in one of two forms:
 //   form 1 (replica lanes): four nodes x 32 replicas, node_step_rl above -- all light nodes;
 //   form 0 (warp per node): four nodes of one replica, pre_node + xfer_node of k_node -- the heavy nodes (many lanes in or out:

@@ -163,6 +163,75 @@ def time_reference_ensemble(workload, seeds, procs):
     return sum(r[0] for r in res), max(r[1] for r in res), res[0][2]
 
 
+_PYMODE_CHILD = r"""
+import json, os, sys, time
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "oracle"))
+os.environ["UXSIM_REFERENCE_ROOT"] = os.path.join(root, "baseline", "_ref")
+import numpy as np
+import bench
+from ref_python_shim import import_reference  # test infrastructure: stub modules for matplotlib, nothing else
+from uxsim_b200 import scenario as S
+ux = import_reference()
+workload, seed, log = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+sc = bench.make_scenario(workload, seed)
+W = ux.World(**{**sc.world, "vehicle_logging_timestep_interval": log, "print_mode": 0, "save_mode": 0, "show_mode": 0})
+S.replay_into(sc, W)
+t0 = time.perf_counter()
+W.exec_simulation()
+secs = time.perf_counter() - t0
+upd = int(round(sum(float((np.asarray(l.cum_arrival) - np.asarray(l.cum_departure)).sum()) for l in W.LINKS) / W.DELTAN))  # platoons on links, summed over steps
+print(json.dumps({"workload": workload, "seconds": secs, "platoon_updates": upd, "logging": log > 0}))
+"""
+
+
+def time_python_mode(jobs, timeout=600):
+    """The reference's pure-Python engine (uxsim/uxsim.py, staged UNMODIFIED under baseline/_ref by baseline/stage_reference.py),
+    timed around exec_simulation() as example_28en_benchmark_cpp_mode.py:44-46 does; `jobs` = [(workload, logging interval)], one
+    single-thread process each, side by side.  Returns {key: {...}} or {"unavailable": why}."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "uxsim")):
+        return {"unavailable": "baseline/_ref/uxsim is not staged (python baseline/stage_reference.py needs /root/reference)"}
+    procs = [(w, lg, subprocess.Popen([sys.executable, "-c", _PYMODE_CHILD, ROOT, w, "0", str(lg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)) for w, lg in jobs]
+    out = {"engine": "reference pure-Python engine (uxsim.py), one single-thread process per run, timing around exec_simulation() only", "cores_used": len(procs)}
+    for w, lg, pr in procs:
+        key = f"{w}{'_logging_on' if lg > 0 else ''}"
+        try:
+            so, se = pr.communicate(timeout=timeout)
+            d = json.loads(so.strip().splitlines()[-1])
+            out[key] = {"seconds": d["seconds"], "platoon_updates": d["platoon_updates"], "updates_per_sec": d["platoon_updates"] / d["seconds"], "vehicle_logging": lg > 0}
+        except Exception as e:  # a missing dependency of the reference on this box must not take the bench line down
+            pr.kill()
+            out[key] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    return out
+
+
+def time_reference_logging(workload, cores):
+    """The reference C++ engine with vehicle logging ON (the API default; Vehicle::log_data traffi.cpp:1060-1110): one seed per
+    core side by side, single-threaded each.  Returns updates/s."""
+    import multiprocessing as mp
+
+    n = max(1, min(cores, 16))
+    with mp.get_context("spawn").Pool(n) as pool:
+        res = pool.map(_ref_log_worker, [(workload, 4000 + k) for k in range(n)])
+    return sum(r[0] for r in res) / max(r[1] for r in res), n
+
+
+def _ref_log_worker(job):
+    from uxsim_b200 import _capi as C
+
+    workload, seed = job
+    os.environ["OMP_NUM_THREADS"] = "1"
+    api, _ = load_reference_lib()
+    sc = make_scenario(workload, seed)
+    E = sc.engine_from_tables(api, sc.tables(), vehicle_logging_timestep_interval=1, threads=1)
+    t0 = time.perf_counter()
+    E.main_loop()
+    secs = time.perf_counter() - t0
+    upd = E.get_int(C.I_PLATOON_UPDATES)
+    E.close()
+    return upd, secs
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,6 +292,12 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "platoon-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_extras:
+        # the same engine with vehicle logging ON (the API default), and the reference's OTHER mode: the pure-Python engine
+        if kind == "reference":
+            v_log, n_log = time_reference_logging(args.workload, cores)
+            line["logging_on"] = {"value": v_log, "unit": "platoon-updates/s", "sample": f"{n_log} seeds as {n_log} single-thread processes side by side, vehicle_log_mode = 1"}
+        line["python_mode"] = time_python_mode([(args.workload, -1), (args.workload, 1)])
     print(json.dumps(line), flush=True)
 
 
@@ -232,9 +307,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="chicago", choices=sorted(WORKLOADS))
-    ap.add_argument("--replicas", type=int, default=128, help="seeded replicas per GPU per step")
+    ap.add_argument("--replicas", type=int, default=0, help="seeded replicas per GPU per step (0: the workload's default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (logging on, other workloads, DUE ensemble, Python mode)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -258,7 +334,9 @@ def main():
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
     api = C.load_product()  # raises without the CUDA library: no fallback
-    R = args.replicas
+    # replicas per GPU: throughput keeps growing with the ensemble (Chicago sketch: 1.10e9 platoon-updates/s at 128, 1.60e9 at 512,
+    # 1.86e9 at 1024 -- from 256 on the node step runs with a thread per node and replica); memory bounds the fine-platoon workloads
+    R = args.replicas or {"chicago": 1024, "chicago_dn5": 32, "grid11": 512, "siouxfalls": 512, "grid100": 1}[args.workload]
     sc = make_scenario(args.workload, 0)
     tab = sc.tables()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -282,7 +360,7 @@ def main():
         return t
 
     def updates_of(E):
-        return sum(int(E.get_array(C.A_LINK_STAT_COUNT, r).sum()) for r in range(R))
+        return int(E.get_array_all(C.A_LINK_STAT_COUNT).sum())  # RUN platoon-updates of every replica (one gather + one transfer)
 
     # ------------------------------------------------------------------ value: device-timed, inputs resident
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -366,7 +444,6 @@ def main():
         E.main_loop()
         T, L, N = E.get_int(C.I_TOTAL_TIMESTEPS), E.get_int(C.I_NUM_LINKS), E.get_int(C.I_NUM_NODES)
         upd = updates_of(E)
-        transfers = sum(int(E.get_array(C.A_LINK_TRIPS_COMPLETED, r).sum()) for r in range(R))
         events = E.get_int(C.I_LINK_EVENTS) * R
         kms = {C.K_NAMES[k]: E.get_double(C.D_KERNEL_MS_OF + k) for k in range(len(C.K_NAMES))}
         kl = {C.K_NAMES[k]: E.get_int(C.I_KERNEL_LAUNCHES_OF + k) for k in range(len(C.K_NAMES))}
@@ -419,6 +496,15 @@ def main():
             u1 = int(E1.get_array(C.A_LINK_STAT_COUNT, 0).sum())
             E1.close()
         single = {"scenario_wall_ms": float(np.median(lat)), "platoon_updates": u1, "updates_per_sec": u1 / (np.median(lat) / 1e3)}
+        lat8 = []
+        for i in range(3):  # ... and a small ensemble (8 replicas: what one GPU holds when 64 chains are spread over 8)
+            E8 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, num_replicas=8, device=local_rank, random_seed=42)
+            E8.get_array(C.A_LINK_NUM_VEHICLES)
+            E8.main_loop()
+            lat8.append(E8.get_double(C.D_LAST_LOOP_MS))
+            u8 = int(E8.get_array_all(C.A_LINK_STAT_COUNT).sum())
+            E8.close()
+        single["replicas_8"] = {"wall_ms": float(np.median(lat8)), "updates_per_sec": u8 / (np.median(lat8) / 1e3)}
         # CPU baseline on this box's host cores: bounded sample of the same workload
         if world == 1 and args.workload == "grid100":
             u_cpu, t_cpu, kind, note = time_cpu_guarded(args.workload, 2000, GRID100_CPU_SAMPLE_T)
@@ -447,6 +533,103 @@ def main():
             cpu_baseline = {"value": best_v, "unit": "platoon-updates/s", "cores": cores if kind == "reference" else 1, "kind": kind,
                             "sample": sample, "omp_value": omp_v, "ensemble_value": ens_v, "scenario_wall_ms": 1e3 * t_cpu / n_seed}
 
+    # ------------------------------------------------------------------ extra legs (BASELINE.md section 3 / VERDICT r1)
+    logging_on, other, due, python_mode = None, None, None, None
+    if not args.no_extras:
+        flush_buf = None
+        torch.cuda.empty_cache()
+        if rank == 0 and args.workload != "grid100":
+            # (1) vehicle logging ON (vehicle_logging_timestep_interval=1, the API default): every RUN platoon-update also appends a
+            #     36-byte record (Vehicle::log_data traffi.cpp:1060-1110).  Bounded replica count: the log arena is ~350 MB per replica.
+            R_log = min(R, 128 if args.workload == "chicago" else 16 if args.workload == "chicago_dn5" else 64)
+            res = {}
+            for tag, interval in (("off", -1), ("on", 1)):
+                ms_l, upd_l = [], 0
+                for i in range(3):
+                    El = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=interval, num_replicas=R_log, device=local_rank, random_seed=7000 + i)
+                    El.get_array(C.A_LINK_NUM_VEHICLES)
+                    El.main_loop()
+                    if i > 0:
+                        ms_l.append(El.get_double(C.D_LAST_LOOP_MS))
+                        upd_l += int(El.get_array_all(C.A_LINK_STAT_COUNT).sum())
+                    if tag == "on" and i == 2:  # hand-back of ONE replica's logs in the reference's compact flat layout (what the analyzer asks for)
+                        t0 = time.perf_counter()
+                        n_rec = El.get_array(C.A_LOG_T, 0).size
+                        res["handback_ms"], res["log_entries"] = 1e3 * (time.perf_counter() - t0), int(n_rec)
+                    El.close()
+                res[tag] = upd_l / (sum(ms_l) / 1e3)
+            logging_on = {"value": res["on"], "unit": "platoon-updates/s", "replicas": R_log, "logging_off_same_replicas": res["off"], "on_over_off_time": res["off"] / res["on"],
+                          "handback_one_replica_ms": res["handback_ms"], "log_entries_one_replica": res["log_entries"],
+                          "note": "device loop with the per-step RUN records written; hand-back = scatter by platoon + D2H + host assembly of log_t/x/v/s/lane/link/state for one replica"}
+        if rank == 0:
+            # (2) the other named sizes, device-timed like `value`: C3' (Chicago at deltan=5, 1.06 M vehicles) and C4 (100x100 grid, 5 M vehicles)
+            other = {}
+            for wl, Rw in (("chicago_dn5", 16), ("grid100", 1)):
+                if wl == args.workload:
+                    continue
+                scw = make_scenario(wl, 0)
+                tabw = scw.tables()
+                ms_w, upd_w = [], 0
+                for i in range(2):
+                    Ew = scw.engine_from_tables(api, tabw, vehicle_logging_timestep_interval=-1, num_replicas=Rw, device=local_rank, random_seed=9000 + i)
+                    Ew.get_array(C.A_LINK_NUM_VEHICLES)
+                    Ew.main_loop()
+                    if i > 0:
+                        ms_w.append(Ew.get_double(C.D_LAST_LOOP_MS))
+                        upd_w += int(Ew.get_array_all(C.A_LINK_STAT_COUNT).sum())
+                    Ew.close()
+                other[wl] = {"workload": WORKLOADS[wl][2], "replicas": Rw, "ms_per_step": float(np.mean(ms_w)), "value": upd_w / (sum(ms_w) / 1e3), "unit": "platoon-updates/s",
+                             "scenario_wall_ms": float(np.mean(ms_w)) if Rw == 1 else None}
+                del scw, tabw
+        if args.workload in ("chicago", "grid11", "siouxfalls"):
+            # (3) BASELINE configs[4]: day-to-day DUE (route swap between simulated days) as seeded chains sharded over the ranks; ALL ranks.
+            #     "fixed": 64 chains in total (BASELINE's wording: strong scaling); "weak": 64 chains per GPU.  One route-set enumeration serves both.
+            from uxsim_b200.dta import DayToDayEnsemble
+
+            days, k_routes = 4, 4
+            E0 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, device=local_rank)
+            t0 = time.perf_counter()
+            E0.dta_enumerate_route_sets(k_routes, 12345)
+            enum_s = time.perf_counter() - t0
+            due = {"config": {"mode": "DUE", "days": days, "routes_per_od": k_routes, "swap_prob": 0.05, "workload": args.workload}, "route_enumeration_s": enum_s,
+                   "unit": "chain-days/s (days 1.. : rewind + simulation + route swap; day 0 builds the world and the graphs)"}
+            for tag, chains in (("fixed_64_chains", 64), ("weak_64_per_gpu", 64 * world)):
+                if chains < world:
+                    continue
+                ens = DayToDayEnsemble(sc, chains, mode="DUE", device=local_rank)
+                barrier()
+                ens.solve(max_iter=days, n_routes_per_od=k_routes, swap_prob=0.05, route_sets_from=E0)
+                torch.cuda.synchronize()
+                ds = np.array(ens.day_seconds)
+                steady = float(ds[1:].sum())
+                if world > 1:
+                    t = torch.tensor([steady], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    steady = float(t.item())
+                due[tag] = {"chains": chains, "chains_per_gpu": len(ens.local), "value": chains * (days - 1) / steady,
+                            "day_ms": {"rewind": float(ds[1:, 0].mean() * 1e3), "simulation": float(ds[1:, 1].mean() * 1e3), "route_swaps": float(ds[1:, 2].mean() * 1e3)},
+                            "link_volume_mean": float(ens.link_stats_sum[:, 0].sum() / chains)}
+                del ens
+            if rank == 0:  # the same day in the reference C++ (traffi.cpp + dta_solver.cpp via oracle/_ref) on one host core, logs on (it reads routes from them)
+                try:
+                    ref, kind = load_reference_lib()
+                    if kind == "reference":
+                        store = E0.dta_route_sets_csr()
+                        Er = sc.engine_from_tables(ref, tab, vehicle_logging_timestep_interval=1, threads=1)
+                        a = time.perf_counter(); Er.dta_set_route_sets(*store); Er.main_loop(); Er.dta_route_swap(0, 0.05, 1); b = time.perf_counter()
+                        Er.close()
+                        cores = os.cpu_count() or 1
+                        due["reference_cpu"] = {"kind": kind, "one_core_day_ms": (b - a) * 1e3, "cores": cores, "chain_days_per_sec_all_cores": cores / (b - a)}
+                except Exception as e:
+                    due["reference_cpu"] = {"unavailable": str(e)[:200]}
+            E0.close()
+        if rank == 0 and world == 1:
+            # (4) the reference's pure-Python mode on this box's host cores (C1, C2, C3; logging off, and on for the benched workload)
+            jobs = [("siouxfalls", -1), ("grid11", -1), ("chicago", -1)]
+            if args.workload in ("chicago", "grid11", "siouxfalls"):
+                jobs.append((args.workload, 1))
+            python_mode = time_python_mode(jobs)
+
     if rank == 0:
         line = {
             "metric": "platoon_updates_per_sec", "value": value, "unit": "platoon-updates/s", "n_gpus": world, "steps": args.steps,
@@ -460,7 +643,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "platoon-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "single_scenario": single,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "logging_on": logging_on, "workloads": other, "due_ensemble": due, "python_mode": python_mode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -321,6 +321,24 @@ def test_bench_shape_chicago_128_replicas(cuda_api, oracle_api):
     Eg.close()
 
 
+def test_bench_shape_chicago_1024_replicas(cuda_api, oracle_api):
+    """bench.py's default since round 2: 1024 replicas in one world -- the node step with a thread per (node, replica), picked by
+    the engine itself.  Replicas 0, 511 and 1023 equal the single-seed oracle runs bit for bit; conservation over all replicas."""
+    sc = S.chicago_sketch()
+    tab = sc.tables()
+    R, seed0 = 1024, 300000
+    Eg = sc.engine_from_tables(cuda_api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, random_seed=seed0)
+    Eg.main_loop()
+    for r in (0, 511, 1023):
+        Eo = sc.engine_from_tables(oracle_api, tab, vehicle_logging_timestep_interval=-1, random_seed=seed0 + r)
+        Eo.main_loop()
+        assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"
+        Eo.close()
+    arr = Eg.get_array_all(C.A_VEH_ARRIVAL_TS)
+    assert arr.shape == (R, 32284) and len({int((a >= 0).sum()) for a in arr}) > 32  # genuinely different runs
+    Eg.close()
+
+
 def test_c4_full_size_against_oracle(cuda_api, oracle_api):
     """BASELINE configs[3] at FULL size (100x100 signalised grid, 1 M platoons, 10 000 destinations) against the oracle for the
     first 600 s of simulated time (two route updates, 10 M platoon-updates; about a minute and 6.5 GB on the CPU side)."""

@@ -283,11 +283,16 @@ class DayToDayEnsemble:
         self.swap_device_ms = []   # per day: device time of the batched route-swap kernels
         self.routes = None         # per chain: (link ids, offsets) enforced on the next day
 
-    def solve(self, max_iter, n_routes_per_od=10, swap_prob=0.05, enum_seed=12345, swap_seed=0, keep_last_world=False):
+    def solve(self, max_iter, n_routes_per_od=10, swap_prob=0.05, enum_seed=12345, swap_seed=0, keep_last_world=False, route_sets_from=None):
+        """``route_sets_from``: an engine world that already holds the OD route sets (one enumeration can serve several
+        ensembles of the same scenario, as one ``ODRouteSetStore`` serves every day of a reference solve); it is left open."""
         sc, api, R = self.scenario, self.api, self.R
         tab = sc.tables()
-        E0 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, device=self.device, **self.world_over)
-        E0.dta_enumerate_route_sets(n_routes_per_od, enum_seed)
+        if route_sets_from is not None:
+            E0 = route_sets_from
+        else:
+            E0 = sc.engine_from_tables(api, tab, vehicle_logging_timestep_interval=-1, device=self.device, **self.world_over)
+            E0.dta_enumerate_route_sets(n_routes_per_od, enum_seed)
         dn = sc.deltan
         shape = (R, max_iter)
         self.ttts, self.n_swaps, self.potential_swaps, self.t_gaps, self.trips = (np.zeros(shape) for _ in range(5))
@@ -322,7 +327,8 @@ class DayToDayEnsemble:
         if not keep_last_world:
             E.close()
             E = None
-        E0.close()
+        if route_sets_from is None:
+            E0.close()
         return E if keep_last_world else None
 
     def _reduce_link_stats(self, E):

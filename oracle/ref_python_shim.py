@@ -49,7 +49,12 @@ def import_reference():
 
     def _stub(name):
         m = types.ModuleType(name)
-        m.__getattr__ = lambda attr: _Anything()  # type: ignore[attr-defined]
+        def _attr(attr):  # dunder lookups (__file__, __path__, __spec__ ...) must fail like on a real attribute-less module:
+            if attr.startswith("__"):  # other packages (torch) walk sys.modules and inspect them
+                raise AttributeError(attr)
+            return _Anything()
+
+        m.__getattr__ = _attr  # type: ignore[attr-defined]
         return m
 
     if "matplotlib" not in sys.modules:

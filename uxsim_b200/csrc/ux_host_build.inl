@@ -362,6 +362,8 @@ static void launch_init_dyn(ux_world *w) {
     int L = (int)w->links.size(), N = (int)w->nodes.size();
     long long tot = (long long)(L + N) * w->R;
     if (tot > 0) UX_LAUNCH(k_init_dyn, dim3((unsigned)((tot + 255) / 256)), dim3(256), w->stream, w->dworlds, w->R, w->d_init_co, w->d_init_ci, w->d_init_ph, w->d_init_st, w->d_init_fc);
+    long long per = std::max((long long)w->P_uploaded, (long long)w->n_active * N);
+    if (per > 0) UX_LAUNCH(k_init_rep, dim3((unsigned)((per + 255) / 256), w->R), dim3(256), w->stream, w->dworlds);
 }
 
 // Build all device state.  Called lazily by the first main_loop (so that vehicles added after
@@ -541,7 +543,6 @@ static int upload(ux_world *w) {
     dalloc<char>(w, 1);  // make sure the marks below sit inside a slab
     w->dyn_slab0 = w->slabs.size() - 1; w->dyn_used0 = w->slabs.back().used;
     w->reinit.clear();
-    auto reg_ff = [&](void *q, size_t b) { if (q) { cudaMemsetAsync(q, 0xff, b ? b : 1, w->stream); w->reinit.push_back({q, b ? b : 1, 0, nullptr}); } };
     w->d_err_all = dalloc<int>(w, 2 * (size_t)R);
     if (!w->d_err_all) return fail(w, UX_ERR_CUDA, "device allocation failed");
     size_t TL = (size_t)T * L;
@@ -597,10 +598,6 @@ static int upload(ux_world *w) {
         d.lq = lq + r; d.lc = lc + r; d.lr = lr + r; d.stat_count = stat + r; d.ns = ns + r; d.nr = nr + r; d.node_done = node_done + r;
         d.cum_arr = cum_arr + r; d.cum_dep = cum_dep + r; d.tt_inst = tt_inst + r; d.ev_tt = ev_tt + r; d.ev_ord = ev_ord + r; d.sig_log = sig_log + r; d.t_base = t_base + r;
         layout(d, rep_blk + (size_t)r * rep_bytes);
-        reg_ff(d.v_link, sizeof(int) * P); reg_ff(d.v_arr_ts, sizeof(int) * P);
-        if (P) { UX_LAUNCH(k_fill_f64, dim3((unsigned)((P + 255) / 256)), dim3(256), w->stream, d.v_tt, (long long)P, -1.0); w->reinit.push_back({d.v_tt, (size_t)P * 8, 1, nullptr}); }
-        if (base.log_mode) { reg_ff(d.v_gen_ts, sizeof(int) * P); reg_ff(d.v_end_ts, sizeof(int) * P); }
-        reg_ff(d.rnext, sizeof(int) * (size_t)D * N);
         d.err = w->d_err_all + 2 * r; d.n_levels = w->n_levels;
     }
     w->uniform = true;

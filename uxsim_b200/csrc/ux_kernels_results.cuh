@@ -37,6 +37,17 @@ __global__ void k_init_dyn(const DevWorld *worlds, int R, const double *co, cons
     else if (e < (long long)W.L + W.N) { long long n = e - W.L; NS(W, n).sig_phase = ph[n]; NR(W, n).sig_t = st[n]; NR(W, n).fc_rem = fc[n]; }
 }
 
+// the non-zero initial values of the replica-major state of every replica (blockIdx.y): "none" markers and travel times of -1
+__global__ void k_init_rep(const DevWorld *worlds) {
+    const DevWorld &W = worlds[blockIdx.y];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W.P) {
+        W.v_link[i] = -1; W.v_arr_ts[i] = -1; W.v_tt[i] = -1.0;
+        if (W.log_mode) { W.v_gen_ts[i] = -1; W.v_end_ts[i] = -1; }
+    }
+    if (i < (long long)W.D * W.N) W.rnext[i] = -1;
+}
+
 // Link::ensure_traveltime_real (traffi.cpp:631-648): position i takes the value of the latest event whose entry step <= i.
 UX_DEV void tt_actual_link(const DevWorld &W, int l, double *out) {
     double cur = W.l_tt0[l];  // the fill value of Link::Link (traffi.cpp:519): free-flow time at the speed the link was frozen with

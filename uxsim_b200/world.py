@@ -386,23 +386,34 @@ class CudaVehicle:
     def log_lane(self):
         return self._log("log_lane")
 
+    # The three list-valued logs are converted once per state of the run and kept next to the arrays they come from
+    # (uxsim_cpp_wrapper.py:580-664 caches them the same way): analyzer.py indexes `veh.log_state[i]` inside loops over i.
     @property
     def log_state(self):
-        return [_STATE_NAMES[s] if 0 <= s < 5 else "end" for s in self._log("log_state")]
+        d = self.W._vehicle_log(self.id)
+        if "log_state_names" not in d:
+            d["log_state_names"] = [_STATE_NAMES[s] if 0 <= s < 5 else "end" for s in d["log_state"]]
+        return d["log_state_names"]
 
     @property
     def log_link(self):
-        links = self.W.LINKS
-        return [links[i] if 0 <= i < len(links) else -1 for i in self._log("log_link")]
+        d = self.W._vehicle_log(self.id)
+        if "log_link_objs" not in d:
+            links = self.W.LINKS
+            d["log_link_objs"] = [links[i] if 0 <= i < len(links) else -1 for i in d["log_link"]]
+        return d["log_link_objs"]
 
     @property
     def log_t_link(self):
-        links = self.W.LINKS
-        out = []
-        for t, lid in zip(self._log("log_t_link_t"), self._log("log_t_link_id")):
-            lid = int(lid)
-            out.append([t, "home" if lid == -1 else "end" if lid == -2 else links[lid] if 0 <= lid < len(links) else -1])
-        return out
+        d = self.W._vehicle_log(self.id)
+        if "log_t_link" not in d:
+            links = self.W.LINKS
+            out = []
+            for t, lid in zip(d["log_t_link_t"], d["log_t_link_id"]):
+                lid = int(lid)
+                out.append([t, "home" if lid == -1 else "end" if lid == -2 else links[lid] if 0 <= lid < len(links) else -1])
+            d["log_t_link"] = out
+        return d["log_t_link"]
 
     def traveled_route(self, include_arrival_time=True, include_departure_time=False):
         """uxsim_cpp_wrapper.py:666-681."""

@@ -99,7 +99,7 @@ def test_unsupported_like_cpp_mode(cuda_api):
     W.addLink("l", "a", "b", length=500)
     with pytest.raises(NotImplementedError):
         W.addVehicle("a", "b", 0, mode="taxi")
-    for f in (W.copy, lambda: W.save("x"), lambda: W.load_scenario("x"), lambda: W.save_scenario("x")):
+    for f in (W.copy, lambda: W.save("x"), lambda: W.save_scenario("x")):  # (load_scenario IS supported here: tests/test_load_scenario.py)
         with pytest.raises(NotImplementedError):
             f()
     with pytest.raises(ValueError):

@@ -943,7 +943,70 @@ class CudaWorld:
         raise NotImplementedError("save_scenario is not supported in CUDA mode (as in C++ mode).")
 
     def load_scenario(self, fname, network=True, demand=True):
-        raise NotImplementedError("load_scenario is not supported in CUDA mode (as in C++ mode).")
+        """scenario_reader_writer.py:152-224: read a `.uxsim_scenario` file (a pickled dict of the recorded addNode / addLink /
+        adddemand* keyword arguments) into this world.  The reference's C++ mode does not support this (uxsim_cpp_wrapper.py:1529-1533);
+        here the plain `adddemand` records -- 8 406 of them in dat/chicago_sketch.uxsim_scenario -- go through the vectorised ingest
+        (one FFI call, ux_add_demands), everything else through the same methods the reference's loader calls."""
+        import pickle
+
+        with open(fname, "rb") as f:
+            try:
+                dat = pickle.load(f)
+            except Exception:  # files written by dill with objects plain pickle cannot resolve
+                import dill
+
+                f.seek(0)
+                dat = dill.load(f)
+        self.print(f"loading scenario from '{fname}'")
+        meta = dat.get("meta_data")
+        if meta:
+            if isinstance(meta, dict):
+                for key in meta:
+                    self.print("", key, ":", meta[key])
+            else:
+                self.print("", meta)
+        if network:
+            for n in dat["Nodes"]:
+                self.addNode(**n)
+            for l in dat["Links"]:
+                self.addLink(**l)
+            self.print(" Number of loaded nodes:", len(dat["Nodes"]))
+            self.print(" Number of loaded links:", len(dat["Links"]))
+        if demand:
+            for demand_type in dat:
+                if demand_type == "adddemand":
+                    self._adddemand_batch(dat[demand_type])
+                elif demand_type in ("adddemand_point2point", "adddemand_area2area", "adddemand_nodes2nodes", "adddemand_area2area2", "adddemand_nodes2nodes2"):
+                    for dem in dat[demand_type]:
+                        getattr(self, demand_type)(**dem)
+                else:
+                    continue
+                self.print(f" Number of loaded `{demand_type}`s:", len(dat[demand_type]))
+
+    def _adddemand_batch(self, demands):
+        """Many `adddemand(**kwargs)` records at once: one ux_add_demands call creates the platoons of all of them in order
+        (the same FP64 accumulation per record), the registry gets one batch per run of equal (orig, dest)."""
+        if not demands:
+            return
+        if any(d.get("attribute") is not None for d in demands):  # per-record attributes: the per-call path keeps them apart
+            for d in demands:
+                self.adddemand(**d)
+            return
+        nodes = [(self.get_node(d["orig"]), self.get_node(d["dest"])) for d in demands]
+        t0 = np.array([d["t_start"] for d in demands], np.float64)
+        t1 = np.array([d["t_end"] for d in demands], np.float64)
+        flow = np.array([(d.get("volume", -1) / (d["t_end"] - d["t_start"])) if d.get("volume", -1) > 0 else d.get("flow", -1) for d in demands], np.float64)
+        p0 = self._E.get_int(C.I_NUM_VEHICLES)
+        self._E.add_demands([o.id for o, _ in nodes], [d.id for _, d in nodes], t0, t1, flow)
+        p1 = self._E.get_int(C.I_NUM_VEHICLES)
+        if p1 > p0:
+            vo, vd = self._E.get_array(C.A_VEH_ORIG)[p0:p1], self._E.get_array(C.A_VEH_DEST)[p0:p1]
+            cut = np.flatnonzero((np.diff(vo) != 0) | (np.diff(vd) != 0)) + 1
+            for a, b in zip(np.r_[0, cut], np.r_[cut, p1 - p0]):
+                self._register(int(b - a), self.NODES[int(vo[a])], self.NODES[int(vd[a])], None)
+        for (o, d), dem, f in zip(nodes, demands, flow):
+            self.demand_info["adddemand"].append(dict(orig=o.name, dest=d.name, t_start=dem["t_start"], t_end=dem["t_end"], flow=float(f), volume=dem.get("volume", -1)))
+        self._invalidate()
 
     def copy(self):
         raise NotImplementedError("copy() is not supported in CUDA mode (as in C++ mode)")

@@ -173,14 +173,20 @@ UX_API int ux_main_loop(ux_world *w, double duration_t, double until_t) {
         }
     }
 #ifdef UX_PROFILE_NODE
-    {   // measurement build: per-step maxima of the k_node_rl phases (cycles), averaged over the steps of this call
-        static unsigned long long h[4096][8];
-        cudaMemcpyFromSymbol(h, g_node_prof, sizeof(h));
-        double sum[8] = {0}, mx[8] = {0}; int cnt = 0;
-        for (int t = start_ts; t < end_ts && t < 4096; t++) { cnt++; for (int k = 0; k < 8; k++) { sum[k] += (double)h[t][k]; if ((double)h[t][k] > mx[k]) mx[k] = (double)h[t][k]; } }
-        const char *nm[8] = {"generate", "gather", "dep-wait", "out-links", "slot loop", "flush+writeback", "total(active)", "-"};
-        for (int k = 0; k < 7; k++) fprintf(stderr, "[node_prof] %-16s mean of per-step max %9.0f cycles, max %9.0f\n", nm[k], sum[k] / (cnt ? cnt : 1), mx[k]);
-        static unsigned long long z[4096][8]; cudaMemcpyToSymbol(g_node_prof, z, sizeof(z));
+    {   // measurement build: per-step maxima of the node-step phases (cycles), averaged over the steps of this call
+        static unsigned long long h[4096][8], h2[4096][8];
+        cudaMemcpyFromSymbol(h, g_node_prof, sizeof(h)); cudaMemcpyFromSymbol(h2, g_node_prof2, sizeof(h2));
+        const char *nm_rl[8] = {"generate", "gather", "dep-wait", "out-links", "slot loop", "flush+writeback", "total(active)", "-"};
+        const char *nm_w[8] = {"xfer gather A1-A3", "xfer dep-wait", "xfer A4+window", "xfer rng+shuffle", "xfer rounds", "xfer flush+wb", "xfer total", "kernel total/warp"};
+        const char *nm_p[8] = {"pre fresh tt", "pre scalar", "pre release", "gen choice+gather", "gen window", "gen serial", "gen wb+tail", "pre total"};
+        for (int tab = 0; tab < 2; tab++) {
+            double sum[8] = {0}, mx[8] = {0}; int cnt = 0;
+            auto &H = tab ? h2 : h;
+            for (int t = start_ts; t < end_ts && t < 4096; t++) { cnt++; for (int k = 0; k < 8; k++) { sum[k] += (double)H[t][k]; if ((double)H[t][k] > mx[k]) mx[k] = (double)H[t][k]; } }
+            const char **nm = tab ? nm_p : (w->node_rl ? nm_rl : nm_w);
+            for (int k = 0; k < 8; k++) fprintf(stderr, "[node_prof] %-18s mean of per-step max %9.0f cycles, max %9.0f\n", nm[k], sum[k] / (cnt ? cnt : 1), mx[k]);
+        }
+        static unsigned long long z[4096][8]; cudaMemcpyToSymbol(g_node_prof, z, sizeof(z)); cudaMemcpyToSymbol(g_node_prof2, z, sizeof(z));
     }
 #endif
     w->loop_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

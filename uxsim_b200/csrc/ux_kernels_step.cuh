@@ -1,6 +1,23 @@
 // ux_kernels_step.cuh -- part of engine.cu (one translation unit; included in the order engine.cu lists).
 // The two kernels of a timestep: k_node (link update, generate, signal, transfer) and k_update (car following, link head, logs).
 
+#ifdef UX_PROFILE_NODE  // measurement build only (uxsim_b200/variants/): per step, the longest time any thread spent in each phase of k_node_rl
+__device__ unsigned long long g_node_prof[4096][8];
+__device__ unsigned long long g_node_prof2[4096][8];  // warp form: phases of pre_node
+#define NPROF_T(v) const long long v = clock64();
+#define NPROF_MAX(k, a, b) atomicMax(&g_node_prof[t & 4095][k], (unsigned long long)((b) - (a)));
+#define NPROF2_MAX(k, a, b) atomicMax(&g_node_prof2[t & 4095][k], (unsigned long long)((b) - (a)));
+#define NLAP_INIT long long lap_ = clock64(); const long long lap0_ = lap_;
+#define NLAP(tab, k) { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) atomicMax(&tab[t & 4095][k], (unsigned long long)(now_ - lap_)); lap_ = now_; }
+#define NLAP_TOTAL(tab, k) if ((threadIdx.x & 31) == 0) atomicMax(&tab[t & 4095][k], (unsigned long long)(clock64() - lap0_));
+#else
+#define NPROF_T(v)
+#define NPROF_MAX(k, a, b)
+#define NPROF2_MAX(k, a, b)
+#define NLAP_INIT
+#define NLAP(tab, k)
+#define NLAP_TOTAL(tab, k)
+#endif
 // ---------------------------------------------------------------------------------------------------
 // K1: Link::update (traffi.cpp:542-565, 599-622) for the node's out-links, then Node::generate (105-189),
 //     Node::signal_update (194-207), Node::flow_capacity_update (226-234).  One warp per node.
@@ -38,6 +55,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     bool fresh = (t % W.itt) == 0 && !W.node_rl;  // (ensembles: k_link_pre<true> has measured the mean speeds already)
+    NLAP_INIT
     // ---- instantaneous travel time of the out-links (whole warp per link, only every `itt` steps)
     if (fresh) {
         for (int k = 0; k < nout; k++) {
@@ -53,6 +71,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         }
         WARP_SYNC();
     }
+    NLAP(g_node_prof2, 0)
     if (W.pre_split) {
         // the scalar link update -- curve carries, capacity tokens -- and the node's signal / capacity step ran before this
         // kernel, one thread per link / node (k_link_pre): only the freshly measured travel times are left to store
@@ -85,6 +104,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     }
     WARP_SYNC();
     }
+    NLAP(g_node_prof2, 1)
     // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
     //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
     int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = NS(W, n).gen_avail;
@@ -100,6 +120,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
     }
     // ---- generate (traffi.cpp:105-189).  The route draws of the first `natt` waiting platoons and the tail state of the
     //      out-links are fetched in parallel; lane 0 then walks the attempts on shared memory and stops at the first refusal.
+    NLAP(g_node_prof2, 2)
     int gh = NS(W, n).gen_head;
     int natt = av - gh;
     { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > MC) natt = MC; }
@@ -125,6 +146,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
             }
         }
         WARP_SYNC();
+        NLAP(g_node_prof2, 3)
         WARP_FOR(ln) if (ln == 0) { int acc = 0; for (int q = 0; q < nout; q++) { G.o_win_off[q] = acc; acc += G.o_lanes[q]; } G.o_win_off[nout] = acc; }
         WARP_SYNC();
         WARP_FOR(ln) {
@@ -140,6 +162,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
             }
         }
         WARP_SYNC();
+        NLAP(g_node_prof2, 4)
         WARP_FOR(ln) if (ln == 0) {
             for (int i = 0; i < natt; i++) {
                 int vid = G.g_vid[i], ol = G.choice[i];
@@ -178,6 +201,7 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
             NS(W, n).gen_head = gh;
         }
         WARP_SYNC();
+        NLAP(g_node_prof2, 5)
         WARP_FOR(ln) {
             for (int q = ln; q < nout; q += 32) {
                 int ol = W.n_out[o0 + q];
@@ -193,6 +217,8 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         if (!W.pre_split) node_signal_capacity(W, n, t);
     }
     WARP_SYNC();
+    NLAP(g_node_prof2, 6)
+    NLAP_TOTAL(g_node_prof2, 7)
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -263,6 +289,7 @@ template <int MC, int MD>
 UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
     int cur = t & 1, L = W.L;
     size_t C = (size_t)W.C;
+    NLAP_INIT
     if (NS(W, n).node_act != t) return;  // no in-link of this node has a flagged head position (hcount == 0 everywhere): nothing to do
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     if (nin == 0) return;
@@ -356,6 +383,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             S.c_q[k] = (unsigned char)q;
         }
     }
+    NLAP(g_node_prof, 0)
     // ---- dependency wait (only nodes with SEES_POPS out-links): everything above -- in-link heads, candidate sort -- is
     //      independent of the lower-level nodes, so it overlaps their work; only the out-link tail state needs their pops.
     if (has_deps) {
@@ -379,6 +407,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
 #endif
         WARP_SYNC();
     }
+    NLAP(g_node_prof, 1)
     // ---- A4: out-link tail state
     WARP_FOR(lane) {
         for (int q = lane; q < nol; q += 32) {
@@ -422,6 +451,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
         }
     }
     WARP_SYNC();
+    NLAP(g_node_prof, 2)
     // ---- B: the slot loop.  Slots are inherently sequential (each move changes what the next slot sees), but inside
     //          a slot the eligibility scan over the candidates runs one lane per candidate, and all random numbers of
     //          the node (shuffle indices, merge-lottery uniforms) are drawn up front in parallel: Philox is stateless.
@@ -449,6 +479,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     // Rounds instead of slots: a slot whose out-link cannot accept or has no eligible candidate changes nothing (and
     // draws nothing), so each round evaluates every out-link / candidate in parallel against the current state, jumps
     // to the first slot (in shuffled order) that moves a platoon, applies that one move on lane 0, and repeats.
+    NLAP(g_node_prof, 3)
     double fc = W.n_fc[n];
     WARP_FOR(lane) if (lane == 0) { S.cur_slot = 0; S.n_picks = 0; S.fc_rem = NR(W, n).fc_rem; }
     WARP_SYNC();
@@ -566,6 +597,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
         }
         WARP_SYNC();
     }
+    NLAP(g_node_prof, 4)
     WARP_FOR(lane) if (lane == 0) {
         // flush trip-end-waiting fronts (traffi.cpp:432-441)
         for (int ii = 0; ii < nin; ii++) {
@@ -592,6 +624,8 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             LR(W, ol).cap_in_rem = S.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = S.o_cumarr[q]; LQ(W, ol).tail = S.o_tail[q];
         }
     }
+    NLAP(g_node_prof, 5)
+    NLAP_TOTAL(g_node_prof, 6)
 }
 
 // K0: the per-link and per-node scalar bookkeeping of a timestep, one THREAD per (link | node, replica):
@@ -625,8 +659,13 @@ UX_DEV double queue_vsum_serial(const double *V, int hd, int n, int cap) {
     return part[0];
 }
 
+// 6 blocks of 256 threads per SM (<= 40 registers; the 32 partial sums of the mean-speed pass spill to L1): a streaming kernel wants the
+// residency, measured on the B200 at 1024 replicas: 157 us (no bound, 94 registers) -> 100 (4) -> 96 (6)
+#ifndef LPRE_MINB
+#define LPRE_MINB 6
+#endif
 template <bool RL>
-__global__ void __launch_bounds__(256) k_link_pre(const DevWorld *worlds, int step_off, int R) {
+__global__ void __launch_bounds__(256, LPRE_MINB) k_link_pre(const DevWorld *worlds, int step_off, int R) {
     int idx = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     int r = RL ? (int)blockIdx.y * 32 + (idx & 31) : (int)blockIdx.y, i = RL ? idx >> 5 : idx;
     if (r >= R) return;
@@ -683,6 +722,9 @@ template <int MC, int MD>
 __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const DevWorld *worlds, int step_off) {
     // replica = blockIdx.x (fastest in launch order): the blocks resident together are the same nodes of different replicas
     // -- same code path, same static tables -- and every replica's dependency chains start in the first wave
+#ifdef UX_PROFILE_NODE
+    const long long kstart_ = clock64();
+#endif
     LOAD_WORLD_N(W, worlds, (XFER_WARPS > 1 ? 64 : 32), blockIdx.x)
     WARP_BEGIN
     __shared__ NodeSmem<MC, MD> sm_all[XFER_WARPS];
@@ -702,6 +744,9 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
         WARP_SYNC();
         WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)&NDONE(W, n)) = t + 1; }
     }
+#ifdef UX_PROFILE_NODE
+    if ((threadIdx.x & 31) == 0) atomicMax(&g_node_prof[t & 4095][7], (unsigned long long)(clock64() - kstart_));
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -718,13 +763,10 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
 // Random draws are the same counters as in k_node / the oracle, so the results are bit-identical.
 // ---------------------------------------------------------------------------------------------------
 #define NRL_WARPS 4
-#ifdef UX_PROFILE_NODE  // measurement build only (uxsim_b200/variants/): per step, the longest time any thread spent in each phase of k_node_rl
-__device__ unsigned long long g_node_prof[4096][8];
-#define NPROF_T(v) const long long v = clock64();
-#define NPROF_MAX(k, a, b) atomicMax(&g_node_prof[t & 4095][k], (unsigned long long)((b) - (a)));
-#else
-#define NPROF_T(v)
-#define NPROF_MAX(k, a, b)
+// 4 blocks per SM: more residency LOSES here (B200, x1024: 878 us at 3-4 blocks, 945 at 5, 1025 at 6, 1069 at 8) -- the threads' local
+// arrays (the gathered neighbourhood of the node) already fill the L1, and more threads push them out to the L2
+#ifndef NRL_MINB
+#define NRL_MINB 4
 #endif
 #define RLP(T_, ptr_) ((T_ *)((char *)(ptr_) + ro))  // the lane's replica-major array
 
@@ -1111,7 +1153,7 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
 // ever waits for blocks with a smaller index, as in k_node.
 // HEAVY = false: the table holds form-1 blocks only (no shared-memory staging is declared, the L1 keeps the threads' local arrays).
 template <int MC, int MD, bool HEAVY>
-__global__ void __launch_bounds__(32 * NRL_WARPS, 4) k_node_h(const DevWorld *worlds, int step_off, int R, const int4 *blks) {
+__global__ void __launch_bounds__(32 * NRL_WARPS, NRL_MINB) k_node_h(const DevWorld *worlds, int step_off, int R, const int4 *blks) {
     const int4 b = blks[blockIdx.x];  // {form, first position in lvl_nodes, nodes in this block, replica (form 0) | lane group (form 1)}
     LOAD_WORLD_N(W, worlds, 64, b.x ? b.w * 32 : b.w)
     const int wib = (int)(threadIdx.x >> 5), ln = (int)(threadIdx.x & 31);
@@ -1347,6 +1389,11 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
 // k_update.  Bit-identical to k_update: the arithmetic per link is the same and links do not interact within this kernel.
 // ---------------------------------------------------------------------------------------------------
 #define UPD_RL_WARPS 8
+// 4 blocks per SM (64 registers, 32 warps resident): the kernel is bound by load latency, not by registers -- B200, Chicago sketch x1024:
+// 649 us (95 registers, 2 blocks) -> 506 (80, 3 blocks) -> 488 (64, 4 blocks) -> 554 (5 blocks: spills)
+#ifndef UPD_RL_MINB
+#define UPD_RL_MINB 4
+#endif
 #define UPD_RL_SERIAL 32
 #define UPD_RL_STRIDE (((sizeof(DevWorld) + 7) / 8) | 1)
 
@@ -1422,7 +1469,7 @@ UX_DEV int upd_head_decide(const DevWorld &W, int t, int vid, double x, double u
     return kind;
 }
 
-__global__ void __launch_bounds__(32 * UPD_RL_WARPS) k_update_rl(const DevWorld *worlds, int step_off, int R, int L_all) {
+__global__ void __launch_bounds__(32 * UPD_RL_WARPS, UPD_RL_MINB) k_update_rl(const DevWorld *worlds, int step_off, int R, int L_all) {
     int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
     int r = (int)blockIdx.y * 32 + lane, l = (int)blockIdx.x * UPD_RL_WARPS + warp;
     // blockIdx.z > 0: helper blocks for long queues -- they take every gridDim.z-th pass of the car-following list and leave

@@ -297,7 +297,14 @@ enum {
     UX_A_EDIE_OFFSETS = 120,    /* i64 [L+1] */
     UX_A_EDIE_NX = 121,         /* i32 [L]   cells along the link; nt_l = (off[l+1] - off[l]) / nx_l */
     UX_A_EDIE_TN = 122,         /* f64 [cells]  vehicle-seconds spent in the cell  (Link.tn_mat) */
-    UX_A_EDIE_DN = 123          /* f64 [cells]  vehicle-metres travelled in the cell (Link.dn_mat) */
+    UX_A_EDIE_DN = 123,         /* f64 [cells]  vehicle-metres travelled in the cell (Link.dn_mat) */
+    /* result of the last analysis_summary: Analyzer.od_analysis / link_analysis_coarse (analyzer.py:121-203) */
+    UX_A_OD_ORIG = 130,         /* i32 [K]    OD pairs that occur in the demand, ascending in (orig * N + dest) */
+    UX_A_OD_DEST = 131,         /* i32 [K] */
+    UX_A_OD_STATS = 132,        /* f64 [K][6] platoons, completed platoons, mean and std of their travel time (-1 if none completed),
+                                              mean and std of the distance travelled by all platoons of the pair */
+    UX_A_LINKC_STATS = 133      /* f64 [L][4] traffic volume, vehicles remaining, mean and std of traveltime_actual over the steps where it
+                                              is > 0 (-1, -1 for a link without volume) */
 };
 enum { UX_DT_F64 = 1, UX_DT_I32 = 2, UX_DT_I64 = 3 };
 
@@ -358,6 +365,14 @@ UX_API int UX_FN(dta_next_day)(ux_world *w);
  * Contributions are accumulated in 2^-24 fixed point, so the sums do not depend on the order of accumulation (and are
  * identical in the three engines); they differ from the reference's float sums by < 1e-7 relative. */
 UX_API int UX_FN(edie_state)(ux_world *w, int replica, const double *edie_dt, const double *edie_dx);
+
+/* Analyzer.od_analysis (analyzer.py:121-181) and Analyzer.link_analysis_coarse (183-203) of the finished run of `replica` as
+ * reductions over the per-platoon and per-link results (the reference loops over every vehicle and link in Python): per OD pair
+ * the trip counts and the mean / population standard deviation of travel time (completed trips) and of distance travelled (all
+ * platoons of the pair); per link the volume, the remaining vehicles and the mean / std of the positive entries of
+ * traveltime_actual.  Sums run in platoon-id / time order, so the three engines agree bit for bit; free-flow times and minimum
+ * distances (static shortest paths) stay with the caller.  Results: UX_A_OD_* and UX_A_LINKC_STATS. */
+UX_API int UX_FN(analysis_summary)(ux_world *w, int replica);
 
 /* Message of the last failure on `w` (or of the last failed create_world when w == NULL). */
 UX_API const char *UX_FN(last_error)(ux_world *w);

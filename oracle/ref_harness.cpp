@@ -466,6 +466,7 @@ UX_API int uxr_dta_share_route_sets(ux_world *w, ux_world *from) {
     if (from != w) { w->store = from->store; w->od_keys = from->od_keys; }
     return 0;
 }
+UX_API int uxr_analysis_summary(ux_world *w, int) { return fail(w, UX_ERR_RUNTIME, "od_analysis / link_analysis_coarse are computed by the reference's Python analyzer (analyzer.py:121-203), not by its C++ engine"); }
 UX_API int uxr_edie_state(ux_world *w, int, const double *, const double *) { return fail(w, UX_ERR_RUNTIME, "Edie states are computed by the reference's Python analyzer (analyzer.py:249-330), not by its C++ engine"); }
 UX_API int uxr_dta_next_day(ux_world *w) { return fail(w, UX_ERR_RUNTIME, "the reference builds a new World per day (DTAsolvers_cpp_adapter.py:318-330)"); }
 UX_API int uxr_dta_enforce_routes(ux_world *w, int replica, const int *ids, const int64_t *off, int64_t nveh) {

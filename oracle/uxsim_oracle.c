@@ -106,6 +106,8 @@ struct ux_world {
     double n_swap, potential_n_swap, total_t_gap; int has_swap;
     /* Edie states (last edie_state call) */
     int64_t *edie_off; int *edie_nx; double *edie_tn, *edie_dn;
+    /* OD / link summary (last analysis_summary call) */
+    int64_t sum_k; int *sum_o, *sum_d; double *sum_od, *sum_link;
     char err[512];
 };
 
@@ -178,6 +180,7 @@ UX_API void uxo_destroy_world(ux_world *w) {
     free(w->dta_o); free(w->dta_d); free(w->dta_od_off); free(w->dta_route_off); free(w->dta_links);
     free(w->rs_off); free(w->ra_off); free(w->rs_links); free(w->ra_links); free(w->ra_entry_t); free(w->cost_actual); free(w->t_gap); free(w->choice);
     free(w->edie_off); free(w->edie_nx); free(w->edie_tn); free(w->edie_dn);
+    free(w->sum_o); free(w->sum_d); free(w->sum_od); free(w->sum_link);
     free(w);
 }
 
@@ -1032,6 +1035,9 @@ UX_API int64_t uxo_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_EDIE_OFFSETS: n = w->edie_off ? L + 1 : 0; dt = UX_DT_I64; break;
     case UX_A_EDIE_NX: n = w->edie_off ? L : 0; dt = UX_DT_I32; break;
     case UX_A_EDIE_TN: case UX_A_EDIE_DN: n = w->edie_off ? w->edie_off[L] : 0; break;
+    case UX_A_OD_ORIG: case UX_A_OD_DEST: n = w->sum_od ? w->sum_k : 0; dt = UX_DT_I32; break;
+    case UX_A_OD_STATS: n = w->sum_od ? w->sum_k * 6 : 0; break;
+    case UX_A_LINKC_STATS: n = w->sum_link ? L * 4 : 0; break;
     case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = w->dta_n_od; dt = UX_DT_I32; break;
     case UX_A_DTA_OD_OFFSETS: n = w->dta_n_od + 1; dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_OFFSETS: n = (w->dta_od_off ? w->dta_od_off[w->dta_n_od] : 0) + 1; dt = UX_DT_I64; break;
@@ -1127,6 +1133,10 @@ UX_API int64_t uxo_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_EDIE_NX: memcpy(dst, w->edie_nx, sizeof(int) * n); break;
     case UX_A_EDIE_TN: memcpy(dst, w->edie_tn, sizeof(double) * n); break;
     case UX_A_EDIE_DN: memcpy(dst, w->edie_dn, sizeof(double) * n); break;
+    case UX_A_OD_ORIG: memcpy(dst, w->sum_o, sizeof(int) * n); break;
+    case UX_A_OD_DEST: memcpy(dst, w->sum_d, sizeof(int) * n); break;
+    case UX_A_OD_STATS: memcpy(dst, w->sum_od, sizeof(double) * n); break;
+    case UX_A_LINKC_STATS: memcpy(dst, w->sum_link, sizeof(double) * n); break;
     case UX_A_DTA_OD_ORIG: memcpy(dst, w->dta_o, sizeof(int) * n); break;
     case UX_A_DTA_OD_DEST: memcpy(dst, w->dta_d, sizeof(int) * n); break;
     case UX_A_DTA_OD_OFFSETS: if (w->dta_od_off) memcpy(dst, w->dta_od_off, sizeof(int64_t) * n); else ((int64_t *)dst)[0] = 0; break;
@@ -1554,6 +1564,74 @@ UX_API int uxo_edie_state(ux_world *w, int replica, const double *edie_dt, const
     w->edie_tn = (double *)calloc((size_t)cells + 1, sizeof(double)); w->edie_dn = (double *)calloc((size_t)cells + 1, sizeof(double));
     for (int64_t c = 0; c < cells; c++) { w->edie_tn[c] = (double)tn[c] / EDIE_FX * w->p.delta_n; w->edie_dn[c] = (double)dn[c] / EDIE_FX * w->p.delta_n; }
     free(tn); free(dn);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------- */
+/* Analyzer.od_analysis (analyzer.py:121-181) and Analyzer.link_analysis_coarse (183-203), restated:     */
+/* per OD pair the lists of travel times (completed trips) and of distances travelled (all vehicles),    */
+/* np.average / np.std over them; per link volume, remaining vehicles, mean / std of the positive        */
+/* entries of traveltime_actual.  Pairs are reported ascending in (orig * N + dest).                     */
+/* ------------------------------------------------------------------------------------------------- */
+static int cmp_pair_key(const void *a, const void *b) {
+    const int64_t *x = (const int64_t *)a, *y = (const int64_t *)b;  /* {key, vehicle id} */
+    if (x[0] != y[0]) return x[0] < y[0] ? -1 : 1;
+    return x[1] < y[1] ? -1 : x[1] > y[1];
+}
+UX_API int uxo_analysis_summary(ux_world *w, int replica) {
+    if (replica != 0) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    if (w->timestep == 0) return fail(w, UX_ERR_RUNTIME, "analysis_summary needs a run");
+    int64_t P = w->nv; int L = w->nl, T = w->total_ts, N = w->nn;
+    free(w->sum_o); free(w->sum_d); free(w->sum_od); free(w->sum_link);
+    int64_t *kv = (int64_t *)calloc((size_t)P * 2 + 2, sizeof(int64_t));
+    for (int64_t i = 0; i < P; i++) { kv[2 * i] = (int64_t)w->vehs[i].orig * N + w->vehs[i].dest; kv[2 * i + 1] = i; }
+    qsort(kv, (size_t)P, 2 * sizeof(int64_t), cmp_pair_key);
+    int64_t K = 0;
+    for (int64_t q = 0; q < P; q++) if (q == 0 || kv[2 * q] != kv[2 * q - 2]) K++;
+    w->sum_k = K;
+    w->sum_o = (int *)calloc((size_t)K + 1, sizeof(int)); w->sum_d = (int *)calloc((size_t)K + 1, sizeof(int));
+    w->sum_od = (double *)calloc((size_t)K * 6 + 1, sizeof(double)); w->sum_link = (double *)calloc((size_t)L * 4 + 1, sizeof(double));
+    int64_t k = -1;
+    for (int64_t q = 0; q < P;) {
+        int64_t e = q; while (e < P && kv[2 * e] == kv[2 * q]) e++;
+        k++;
+        w->sum_o[k] = (int)(kv[2 * q] / N); w->sum_d[k] = (int)(kv[2 * q] % N);
+        double n = 0, nc = 0, stt = 0, sd = 0;
+        for (int64_t j = q; j < e; j++) {  /* od_trips, od_dist, od_trips_comp, od_tt (analyzer.py:164-176) */
+            const OVeh *v = &w->vehs[kv[2 * j + 1]];
+            double d = v->distance + (v->state == UX_VS_RUN ? v->x - v->entry_x : 0.0);
+            n += 1; sd += d;
+            if (v->travel_time != -1.0) { nc += 1; stt += v->travel_time; }
+        }
+        double md = sd / n, mt = nc > 0 ? stt / nc : 0.0, vd = 0, vt = 0;
+        for (int64_t j = q; j < e; j++) {  /* np.std: population standard deviation */
+            const OVeh *v = &w->vehs[kv[2 * j + 1]];
+            double d = v->distance + (v->state == UX_VS_RUN ? v->x - v->entry_x : 0.0);
+            vd += (d - md) * (d - md);
+            if (v->travel_time != -1.0) vt += (v->travel_time - mt) * (v->travel_time - mt);
+        }
+        double *o = w->sum_od + k * 6;
+        o[0] = n; o[1] = nc; o[2] = nc > 0 ? mt : -1.0; o[3] = nc > 0 ? sqrt(vt / nc) : -1.0; o[4] = md; o[5] = sqrt(vd / n);
+        q = e;
+    }
+    free(kv);
+    for (int l = 0; l < L; l++) {  /* link_analysis_coarse (analyzer.py:183-203) */
+        OLink *lk = &w->links[l];
+        double vol = lk->dep[T - 1], mean = -1.0, sdev = -1.0;
+        if (vol != 0.0) {
+            ensure_traveltime_real(w, lk);
+            double s = 0, n = 0;
+            for (int i = 0; i < T; i++) if (lk->tt_real[i] > 0.0) { s += lk->tt_real[i]; n += 1; }
+            if (n > 0) {
+                mean = s / n;
+                double qq = 0;
+                for (int i = 0; i < T; i++) if (lk->tt_real[i] > 0.0) qq += (lk->tt_real[i] - mean) * (lk->tt_real[i] - mean);
+                sdev = sqrt(qq / n);
+            }
+        }
+        double *o = w->sum_link + (size_t)l * 4;
+        o[0] = vol; o[1] = lk->arr[T - 1] - vol; o[2] = mean; o[3] = sdev;
+    }
     return 0;
 }
 

@@ -52,6 +52,7 @@ A_LOG_OFFSETS, A_LOG_T, A_LOG_X, A_LOG_V, A_LOG_STATE, A_LOG_S, A_LOG_LANE, A_LO
 A_LOG_N_MISSING, A_LTL_OFFSETS, A_LTL_T, A_LTL_ID = 68, 69, 70, 71
 A_DTA_OD_ORIG, A_DTA_OD_DEST, A_DTA_OD_OFFSETS, A_DTA_ROUTE_OFFSETS, A_DTA_ROUTE_LINKS = 100, 101, 102, 103, 104
 A_EDIE_OFFSETS, A_EDIE_NX, A_EDIE_TN, A_EDIE_DN = 120, 121, 122, 123
+A_OD_ORIG, A_OD_DEST, A_OD_STATS, A_LINKC_STATS = 130, 131, 132, 133
 A_DTA_RS_OFFSETS, A_DTA_RS_LINKS, A_DTA_RA_OFFSETS, A_DTA_RA_LINKS, A_DTA_COST_ACTUAL, A_DTA_T_GAP, A_DTA_CHOICE, A_DTA_RA_ENTRY_T = 110, 111, 112, 113, 114, 115, 116, 117
 A_ENTER_LINK, A_ENTER_TIME, A_ENTER_VEH = 80, 81, 82
 
@@ -74,7 +75,7 @@ ABI_SYMBOLS = (
     "check_simulation_ongoing", "set_link_param", "set_link_signal_group", "set_node_signal", "get_int",
     "get_double", "array_size", "get_array", "get_device_array", "ensemble_link_stats_device",
     "ensemble_link_stats", "last_error", "dta_enumerate_route_sets", "dta_set_route_sets", "dta_share_route_sets",
-    "dta_enforce_routes", "dta_route_swap", "dta_next_day", "edie_state",
+    "dta_enforce_routes", "dta_route_swap", "dta_next_day", "edie_state", "analysis_summary",
 )
 
 
@@ -168,6 +169,7 @@ class CApi:
         self.dta_enforce_routes = fn("dta_enforce_routes", C.c_int, [p, C.c_int, i32p, i64p, C.c_int64])
         self.dta_next_day = fn("dta_next_day", C.c_int, [p])
         self.edie_state = fn("edie_state", C.c_int, [p, C.c_int, f64p, f64p])
+        self.analysis_summary = fn("analysis_summary", C.c_int, [p, C.c_int])
         self.dta_route_swap = fn("dta_route_swap", C.c_int, [p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint])
 
     def exported(self, name: str) -> bool:
@@ -338,6 +340,15 @@ class EngineWorld:
             shape = (-1, int(nx[l])) if nx[l] > 0 else (0, 0)
             out.append((tn[off[l]:off[l + 1]].reshape(shape), dn[off[l]:off[l + 1]].reshape(shape)))
         return out
+
+    def analysis_summary(self, replica: int = 0) -> dict:
+        """Analyzer.od_analysis / link_analysis_coarse (analyzer.py:121-203) as reductions inside the engine: ``od_orig, od_dest``
+        (node ids of the K pairs that occur), ``od`` ``[K, 6]`` = platoons, completed platoons, mean / std travel time (-1 without
+        completed trips), mean / std distance travelled; ``link`` ``[L, 4]`` = volume, vehicles remaining, mean / std of the
+        positive entries of traveltime_actual (-1 without volume)."""
+        self._check(self.api.analysis_summary(self.h, int(replica)))
+        return dict(od_orig=self.get_array(A_OD_ORIG, replica), od_dest=self.get_array(A_OD_DEST, replica),
+                    od=self.get_array(A_OD_STATS, replica).reshape(-1, 6), link=self.get_array(A_LINKC_STATS, replica).reshape(-1, 4))
 
     def dta_next_day(self):
         """Rewind the finished world to t = 0 with the last route swap's routes enforced (CUDA engine only)."""

@@ -111,36 +111,26 @@ class BasicAnalyzer:
                 l.v_mat = np.nan_to_num(l.q_mat / l.k_mat, nan=l.u)
 
     def od_analysis(self):
-        """OD-specific stats (analyzer.py:121-181) from the per-platoon arrays: dict of arrays over the OD pairs that occur,
-        keys ``orig, dest`` (node ids), ``total_trips, completed_trips, free_travel_time, average_travel_time,
-        stddiv_travel_time, average_distance_traveled_per_veh, stddiv_distance_traveled_per_veh``."""
+        """OD-specific stats (analyzer.py:121-181) as a reduction inside the engine (``ux_analysis_summary``: one thread per OD pair
+        over the per-platoon results): dict of arrays over the OD pairs that occur, keys ``orig, dest`` (node ids),
+        ``total_trips, completed_trips, free_travel_time, average_travel_time, stddiv_travel_time,
+        average_distance_traveled_per_veh, stddiv_distance_traveled_per_veh`` -- the columns of ``od_to_pandas``.  As in the
+        reference, a pair without a completed trip reports 0 for the averages (its lists are never evaluated there)."""
         W = self.W
         dn = W.DELTAN
-        n = len(W.NODES)
-        o, d = W._E.get_array(C.A_VEH_ORIG).astype(np.int64), W._E.get_array(C.A_VEH_DEST).astype(np.int64)
-        tt, dist = W._veh("travel_time"), W._veh("distance")
-        key, inv = np.unique(o * n + d, return_inverse=True)
-        k = len(key)
-        done = tt >= 0
-        trips, comp = np.bincount(inv, minlength=k) * dn, np.bincount(inv[done], minlength=k) * dn
-        cnt = np.maximum(np.bincount(inv[done], minlength=k), 1)
-        tt_ave = np.bincount(inv[done], weights=tt[done], minlength=k) / cnt
-        tt_var = np.bincount(inv[done], weights=(tt[done] - tt_ave[inv[done]]) ** 2, minlength=k) / cnt
-        call = np.maximum(np.bincount(inv, minlength=k), 1)
-        d_ave = np.bincount(inv, weights=dist, minlength=k) / call
-        d_var = np.bincount(inv, weights=(dist - d_ave[inv]) ** 2, minlength=k) / call
+        res = W._E.analysis_summary()
+        o, d, od = res["od_orig"].astype(np.int64), res["od_dest"].astype(np.int64), res["od"]
+        has = od[:, 1] > 0
         ff = free_flow_times(W)
-        has = comp > 0
-        return dict(orig=key // n, dest=key % n, total_trips=trips, completed_trips=comp, free_travel_time=ff[key // n, key % n],
-                    average_travel_time=np.where(has, tt_ave, -1.0), stddiv_travel_time=np.where(has, np.sqrt(tt_var), -1.0),
-                    average_distance_traveled_per_veh=d_ave, stddiv_distance_traveled_per_veh=np.sqrt(d_var))
+        z = np.zeros(len(o))
+        return dict(orig=o, dest=d, total_trips=od[:, 0] * dn, completed_trips=od[:, 1] * dn, free_travel_time=np.where(has, ff[o, d], 0.0),
+                    average_travel_time=np.where(has, od[:, 2], z), stddiv_travel_time=np.where(has, od[:, 3], z),
+                    average_distance_traveled_per_veh=np.where(has, od[:, 4], z), stddiv_distance_traveled_per_veh=np.where(has, od[:, 5], z))
 
     def link_summary(self):
-        """traffic_volume / vehicles_remain / free and average travel time per link (link_analysis_coarse, analyzer.py:183-203)."""
+        """traffic_volume / vehicles_remain / free, average and std travel time per link (link_analysis_coarse, analyzer.py:183-203),
+        reduced inside the engine (one thread per link over the travel-time event table)."""
         W = self.W
-        arr, dep, tta = W._series("cum_arrival"), W._series("cum_departure"), W._series("traveltime_actual")
-        vol = dep[:, -1]
-        pos = np.where(tta > 0, tta, np.nan)
-        return dict(traffic_volume=vol, vehicles_remain=arr[:, -1] - dep[:, -1],
-                    free_travel_time=np.array([l.length / l.u for l in W.LINKS]),
-                    average_travel_time=np.where(vol > 0, np.nanmean(pos, axis=1), -1.0))
+        lk = W._E.analysis_summary()["link"]
+        return dict(traffic_volume=lk[:, 0], vehicles_remain=lk[:, 1], free_travel_time=np.array([l.length / l.u for l in W.LINKS]),
+                    average_travel_time=lk[:, 2], stddiv_travel_time=lk[:, 3])

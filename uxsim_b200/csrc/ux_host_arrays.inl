@@ -96,8 +96,68 @@ static int64_t get_edie_array(ux_world *w, int what, int replica, void *dst, int
     return n;
 }
 
+// Analyzer.od_analysis / link_analysis_coarse (analyzer.py:121-203) of `replica` on the device
+UX_API int ux_analysis_summary(ux_world *w, int replica) {
+    if (!w->uploaded || w->timestep == 0) return fail(w, UX_ERR_RUNTIME, "analysis_summary needs a run");
+    if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    auto &S = w->summary;
+    S.replica = -1;
+    const int L = (int)w->links.size(), N = (int)w->nodes.size();
+    const long long P = (long long)w->vehs.size();
+    // the OD pairs of the demand, ascending in (orig * N + dest), each with its platoons in id order (static: host side)
+    std::vector<int> order((size_t)P);
+    for (long long i = 0; i < P; i++) order[(size_t)i] = (int)i;
+    auto key = [&](int v) { return (long long)w->vehs[v].orig * N + w->vehs[v].dest; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+    std::vector<long long> off;
+    S.o.clear(); S.d.clear();
+    for (long long q = 0; q < P; q++) {
+        if (q == 0 || key(order[(size_t)q]) != key(order[(size_t)q - 1])) { off.push_back(q); S.o.push_back(w->vehs[order[(size_t)q]].orig); S.d.push_back(w->vehs[order[(size_t)q]].dest); }
+    }
+    off.push_back(P);
+    const int K = (int)S.o.size();
+    void *px = nullptr;
+    if (P > 0) { int64_t m = device_array(w, UX_A_VEH_X, replica, &px, nullptr); if (m < 0) return (int)m; }
+    size_t bytes = 0;
+    auto carve = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
+    size_t o_off = carve(8 * (size_t)(K + 1)), o_veh = carve(4 * (size_t)P), o_od = carve(48 * (size_t)K), o_lk = carve(32 * (size_t)L);
+    char *buf = nullptr;
+    CUDA_OK(cudaMalloc((void **)&buf, bytes + 256));
+    cudaMemcpyAsync(buf + o_off, off.data(), 8 * (size_t)(K + 1), cudaMemcpyHostToDevice, st);
+    if (P) cudaMemcpyAsync(buf + o_veh, order.data(), 4 * (size_t)P, cudaMemcpyHostToDevice, st);
+    S.od.assign((size_t)K * 6, 0.0); S.link.assign((size_t)L * 4, 0.0);
+    if (K) {
+        UX_LAUNCH(k_od_stats, dim3((unsigned)((K + 127) / 128)), dim3(128), st, w->dworlds, replica, K, (const long long *)(buf + o_off), (const int *)(buf + o_veh),
+                  (const double *)px, (double *)(buf + o_od));
+        cudaMemcpyAsync(S.od.data(), buf + o_od, 48 * (size_t)K, cudaMemcpyDeviceToHost, st);
+    }
+    if (L) {
+        UX_LAUNCH(k_linkc_stats, dim3((unsigned)((L + 127) / 128)), dim3(128), st, w->dworlds, replica, (double *)(buf + o_lk));
+        cudaMemcpyAsync(S.link.data(), buf + o_lk, 32 * (size_t)L, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(w, UX_ERR_CUDA, "CUDA error in analysis_summary: %s", cudaGetErrorString(e));
+    w->d2h_bytes += 48ll * K + 32ll * L; w->h2d_bytes += 8ll * (K + 1) + 4 * P;
+    S.replica = replica;
+    return 0;
+}
+
+static int64_t get_summary_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
+    auto &S = w->summary;
+    if (S.replica != replica) return fail(w, UX_ERR_RUNTIME, "no analysis summary for replica %d", replica);
+    const void *src = what == UX_A_OD_ORIG ? (const void *)S.o.data() : what == UX_A_OD_DEST ? (const void *)S.d.data() : what == UX_A_OD_STATS ? (const void *)S.od.data() : (const void *)S.link.data();
+    int64_t n = what == UX_A_OD_ORIG || what == UX_A_OD_DEST ? (int64_t)S.o.size() : what == UX_A_OD_STATS ? (int64_t)S.od.size() : (int64_t)S.link.size();
+    if (capacity < n) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)n);
+    if (n > 0) memcpy(dst, src, (what == UX_A_OD_ORIG || what == UX_A_OD_DEST ? 4 : 8) * (size_t)n);
+    return n;
+}
+
 UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64_t capacity) {
     if (is_log_array(what)) return get_log_array(w, what, replica, dst, capacity, nullptr, false);
+    if (what >= UX_A_OD_ORIG && what <= UX_A_LINKC_STATS) return get_summary_array(w, what, replica, dst, capacity);
     if (what >= UX_A_DTA_OD_ORIG && what <= UX_A_DTA_RA_ENTRY_T) return get_dta_array(w, what, replica, dst, capacity);
     if (what >= UX_A_EDIE_OFFSETS && what <= UX_A_EDIE_DN) return get_edie_array(w, what, replica, dst, capacity);
     if (what == UX_A_VEH_ORIG || what == UX_A_VEH_DEST || what == UX_A_VEH_DEPART_TS) {  // static: answered from the host copy (no upload forced)

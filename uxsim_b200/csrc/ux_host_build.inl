@@ -640,6 +640,19 @@ static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of
                 k_sssp_wave<true, false><<<dim3(w->n_active, w->R), dim3(per_block), wbytes + (size_t)N * 8, st>>>(w->dworlds, 0);
             } else {
                 size_t ww = (((size_t)((N + 64 + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 15) / 8) + (size_t)N + 2;  // 8-byte words per warp
+                {   // ensembles: the in-edge CSR and the replica's edge costs staged in shared memory, as many destinations (warps) per
+                    // block as let two blocks share an SM.  UXSIM_B200_SSSP_STAGE=0 keeps the unstaged kernel (tests compare them).
+                    static const int stage_on = [] { const char *e = getenv("UXSIM_B200_SSSP_STAGE"); return e ? atoi(e) : 1; }();
+                    size_t sw = ((size_t)w->n_edges * 8 + (size_t)(N + 1) * 4 + (size_t)w->n_edges * 2 + 7) / 8;  // 8-byte words of the staged tables
+                    long long room = (long long)110 * 1024 - (long long)sw * 8;
+                    int wpb = room > 0 ? (int)std::min<long long>(SSSP_STAGE_MAX_WARPS, room / (long long)(ww * 8)) : 0;
+                    if (stage_on && wpb >= 8 && (long long)w->n_active * w->R >= 16384) {
+                        size_t bytes_s = (sw + ww * (size_t)wpb) * 8;
+                        cudaFuncSetAttribute(k_sssp_wave<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_s);
+                        k_sssp_wave<true, true, true><<<dim3((w->n_active + wpb - 1) / wpb, w->R), dim3(32 * wpb), bytes_s, st>>>(w->dworlds, (int)ww, (int)sw);
+                        return 2;
+                    }
+                }
                 size_t bytes_w = ww * 8 * SSSP_WARPS_PER_BLOCK;
                 if (bytes_w > 48 * 1024) cudaFuncSetAttribute(k_sssp_wave<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_w);
                 k_sssp_wave<true, true><<<dim3((w->n_active + SSSP_WARPS_PER_BLOCK - 1) / SSSP_WARPS_PER_BLOCK, w->R), dim3(32 * SSSP_WARPS_PER_BLOCK), bytes_w, st>>>(w->dworlds, (int)ww);

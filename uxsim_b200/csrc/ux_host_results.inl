@@ -213,6 +213,9 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_EDIE_OFFSETS: n = (int64_t)w->edie.off.size(); dt = UX_DT_I64; break;
     case UX_A_EDIE_NX: n = (int64_t)w->edie.nx.size(); dt = UX_DT_I32; break;
     case UX_A_EDIE_TN: case UX_A_EDIE_DN: n = (int64_t)w->edie.tn.size(); break;
+    case UX_A_OD_ORIG: case UX_A_OD_DEST: n = (int64_t)w->summary.o.size(); dt = UX_DT_I32; break;
+    case UX_A_OD_STATS: n = (int64_t)w->summary.od.size(); break;
+    case UX_A_LINKC_STATS: n = (int64_t)w->summary.link.size(); break;
     case UX_A_DTA_OD_ORIG: case UX_A_DTA_OD_DEST: n = (int64_t)w->dta_p->o.size(); dt = UX_DT_I32; break;
     case UX_A_DTA_OD_OFFSETS: n = (int64_t)w->dta_p->od_off.size(); dt = UX_DT_I64; break;
     case UX_A_DTA_ROUTE_OFFSETS: n = (int64_t)w->dta_p->route_off.size(); dt = UX_DT_I64; break;

@@ -93,6 +93,8 @@ struct ux_world {
     double swap_ms = 0;
     // Edie states of the last ux_edie_state call
     struct EdieResult { int replica = -1; std::vector<long long> off; std::vector<int> nx; std::vector<double> tn, dn; } edie;
+    // OD / link summary of the last ux_analysis_summary call
+    struct SummaryResult { int replica = -1; std::vector<int> o, d; std::vector<double> od, link; } summary;
     // measurement
     long long h2d_bytes = 0, d2h_bytes = 0;
     double last_loop_ms = 0.0, upload_ms = 0.0, loop_wall_ms = 0.0, graph_build_ms = 0.0;

@@ -211,3 +211,65 @@ __global__ void k_edie_finish(long long cells, const unsigned long long *tn, con
     if (c >= cells) return;
     out_tn[c] = (double)(long long)tn[c] / EDIE_FX * dn_scale; out_dn[c] = (double)(long long)dn[c] / EDIE_FX * dn_scale;
 }
+
+// Analyzer.od_analysis (analyzer.py:121-181) as a reduction: one thread per OD pair walks the pair's platoons in id order
+// (pair_off / pair_veh: the static CSR of the demand) -- counts, then mean and population standard deviation of the travel
+// time of the completed trips and of the distance travelled by all of them (two passes, as numpy's std).  `vx` = the platoons'
+// current positions (k_veh_snapshot): a RUN platoon's distance includes the part of its current link (oracle R4).
+__global__ void k_od_stats(const DevWorld *worlds, int replica, int K, const long long *pair_off, const int *pair_veh, const double *vx, double *out) {
+    const DevWorld &W = worlds[replica];
+    int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= K) return;
+    long long a = pair_off[k], b = pair_off[k + 1];
+    double n = 0.0, nc = 0.0, stt = 0.0, sd = 0.0;
+    for (long long q = a; q < b; q++) {
+        int v = pair_veh[q];
+        double d = W.v_dist[v] + (W.v_state[v] == UX_VS_RUN ? vx[v] - W.v_entry_x[v] : 0.0), tt = W.v_tt[v];
+        n += 1.0; sd += d;
+        if (tt != -1.0) { nc += 1.0; stt += tt; }
+    }
+    double md = n > 0.0 ? sd / n : 0.0, mt = nc > 0.0 ? stt / nc : 0.0, vd = 0.0, vt = 0.0;
+    for (long long q = a; q < b; q++) {
+        int v = pair_veh[q];
+        double d = W.v_dist[v] + (W.v_state[v] == UX_VS_RUN ? vx[v] - W.v_entry_x[v] : 0.0), tt = W.v_tt[v];
+        vd += (d - md) * (d - md);
+        if (tt != -1.0) vt += (tt - mt) * (tt - mt);
+    }
+    double *o = out + (size_t)k * 6;
+    o[0] = n; o[1] = nc; o[2] = nc > 0.0 ? mt : -1.0; o[3] = nc > 0.0 ? sqrt(vt / nc) : -1.0; o[4] = md; o[5] = n > 0.0 ? sqrt(vd / n) : 0.0;
+}
+
+// Analyzer.link_analysis_coarse (analyzer.py:183-203): one thread per link -- volume and remaining vehicles from the last row
+// of the cumulative curves, mean and population std of the positive entries of traveltime_actual, which is materialised on the
+// fly from the event tables (running arg-max as in tt_actual_link), twice (mean, then squared deviations).
+__global__ void k_linkc_stats(const DevWorld *worlds, int replica, double *out) {
+    const DevWorld &W = worlds[replica];
+    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (l >= W.L) return;
+    double vol = W.cum_dep[TLI(W, W.T - 1, l)], arr = W.cum_arr[TLI(W, W.T - 1, l)];
+    double mean = -1.0, sdev = -1.0;
+    if (vol != 0.0) {
+        double cur = W.l_tt0[l], s = 0.0, n = 0.0;
+        int best = 0;
+        for (int i = 0; i < W.T; i++) {
+            int ord = W.ev_ord[TLI(W, i, l)];
+            double v = W.ev_tt[TLI(W, i, l)];
+            if (ord > best) { best = ord; cur = v; }
+            if (cur > 0.0) { s += cur; n += 1.0; }
+        }
+        if (n > 0.0) {
+            mean = s / n;
+            double q = 0.0;
+            cur = W.l_tt0[l]; best = 0;
+            for (int i = 0; i < W.T; i++) {
+                int ord = W.ev_ord[TLI(W, i, l)];
+                double v = W.ev_tt[TLI(W, i, l)];
+                if (ord > best) { best = ord; cur = v; }
+                if (cur > 0.0) q += (cur - mean) * (cur - mean);
+            }
+            sdev = sqrt(q / n);
+        }
+    }
+    double *o = out + (size_t)l * 4;
+    o[0] = vol; o[1] = arr - vol; o[2] = mean; o[3] = sdev;
+}

@@ -246,23 +246,39 @@ __global__ void __launch_bounds__(256) k_cost_stats(const DevWorld *worlds, doub
 #ifndef SSSP_WARPS_PER_BLOCK
 #define SSSP_WARPS_PER_BLOCK 4
 #endif
-template <bool SMEM_DIST, bool WARP>
-__global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld *worlds, int smem_words_per_warp) {
+// STAGE (with WARP): the block's warps -- up to SSSP_STAGE_MAX_WARPS destinations of ONE replica -- first copy what every
+// relaxation reads into shared memory: the in-edge CSR (offsets, start nodes as uint16) and the replica's edge costs in that
+// order.  A round's chain "pop -> label -> CSR offsets -> start nodes / costs -> neighbour labels" then has no global round
+// trip left; `stage_words` 8-byte words precede the per-warp regions.
+#define SSSP_STAGE_MAX_WARPS 16
+template <bool SMEM_DIST, bool WARP, bool STAGE = false>
+__global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld *worlds, int smem_words_per_warp, int stage_words = 0) {
 #ifndef UX_EMU
     LOAD_WORLD(W, worlds)
     const int wib = WARP ? (int)(threadIdx.x >> 5) : 0;
-    int row = WARP ? (int)blockIdx.x * SSSP_WARPS_PER_BLOCK + wib : (int)blockIdx.x;
+    int row = WARP ? (int)blockIdx.x * (int)(blockDim.x >> 5) + wib : (int)blockIdx.x;
+    extern __shared__ unsigned long long sssp_smem_all[];
+    const int *s_off = nullptr; const unsigned short *s_from = nullptr; const double *s_cin = nullptr;
+    if (STAGE) {
+        const int N_ = W.N, E_ = W.n_edges;
+        double *c_ = reinterpret_cast<double *>(sssp_smem_all);
+        int *o_ = reinterpret_cast<int *>(c_ + E_);
+        unsigned short *f_ = reinterpret_cast<unsigned short *>(o_ + N_ + 1);
+        for (int e = (int)threadIdx.x; e < E_; e += (int)blockDim.x) { c_[e] = W.cost_in[e]; f_[e] = (unsigned short)__ldg(W.ein_from + e); }
+        for (int i = (int)threadIdx.x; i <= N_; i += (int)blockDim.x) o_[i] = __ldg(W.ein_off + i);
+        __syncthreads();
+        s_off = o_; s_from = f_; s_cin = c_;
+    }
     if (row >= W.D) return;  // WARP: whole warps leave; only warp-level synchronisation follows
     int N = W.N, k = W.row_dest[row];
     int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x, nth = WARP ? 32 : (int)blockDim.x, cap = N + 2 * nth;
-    extern __shared__ unsigned long long sssp_smem_all[];
-    unsigned long long *sssp_smem = sssp_smem_all + (WARP ? (size_t)wib * smem_words_per_warp : 0);
+    unsigned long long *sssp_smem = sssp_smem_all + (STAGE ? (size_t)stage_words : 0) + (WARP ? (size_t)wib * smem_words_per_warp : 0);
 #define WAVE_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
     unsigned long long *du_s = sssp_smem;  // [N] when SMEM_DIST
     unsigned short *Q = reinterpret_cast<unsigned short *>(sssp_smem + (SMEM_DIST ? N : 0));
     unsigned int *inq = reinterpret_cast<unsigned int *>(Q + ((cap + 3) & ~3));
-    __shared__ int q_tail_all[SSSP_WARPS_PER_BLOCK];
-    __shared__ unsigned int lo_min_all[SSSP_WARPS_PER_BLOCK][2];  // per round parity: lower bound of the queued labels (upper 32 bits)
+    __shared__ int q_tail_all[SSSP_STAGE_MAX_WARPS];
+    __shared__ unsigned int lo_min_all[SSSP_STAGE_MAX_WARPS][2];  // per round parity: lower bound of the queued labels (upper 32 bits)
     int &q_tail = q_tail_all[wib];
     unsigned int *lo_min = lo_min_all[wib];
     unsigned long long *du_g = reinterpret_cast<unsigned long long *>(W.rdist + (size_t)row * N);
@@ -309,14 +325,14 @@ __global__ void __launch_bounds__(SSSP_WAVE_THREADS) k_sssp_wave(const DevWorld 
             }
             if (near) {
                 double djd = __longlong_as_double((long long)dj);
-                int q0 = __ldg(ein_off + j), q1 = __ldg(ein_off + j + 1);
+                int q0 = STAGE ? s_off[j] : __ldg(ein_off + j), q1 = STAGE ? s_off[j + 1] : __ldg(ein_off + j + 1);
                 for (int q = q0; q < q1; q += 4) {  // loads of four in-edges in flight together
                     int ii[4]; unsigned long long nd[4], cu[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         bool in = q + u < q1;
-                        ii[u] = in ? __ldg(ein_from + q + u) : -1;
-                        nd[u] = in ? (unsigned long long)__double_as_longlong(__ldg(cin + q + u) + djd) : INF_BITS;
+                        ii[u] = in ? (STAGE ? (int)s_from[q + u] : __ldg(ein_from + q + u)) : -1;
+                        nd[u] = in ? (unsigned long long)__double_as_longlong((STAGE ? s_cin[q + u] : __ldg(cin + q + u)) + djd) : INF_BITS;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) cu[u] = ii[u] >= 0 ? WAVE_LD(ii[u]) : 0ull;

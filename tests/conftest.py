@@ -14,7 +14,12 @@ def pytest_configure(config):
 
 
 def _make(target_dir, *targets):
-    subprocess.run(["make", "-C", target_dir, *targets], check=True, capture_output=True)
+    # one build at a time per directory: pytest-xdist workers would otherwise load a half-written library
+    import fcntl
+
+    with open(os.path.join(target_dir, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        subprocess.run(["make", "-C", target_dir, *targets], check=True, capture_output=True)
 
 
 @pytest.fixture(scope="session")

@@ -386,12 +386,14 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     NLAP(g_node_prof, 0)
     // ---- dependency wait (only nodes with SEES_POPS out-links): everything above -- in-link heads, candidate sort -- is
     //      independent of the lower-level nodes, so it overlaps their work; only the out-link tail state needs their pops.
+    //      The wait is per REQUESTED out-link: only a link some candidate wants to enter is looked at below, and its end node can
+    //      pop from it only if the last link update flagged head positions there (hcount > 0, final before this launch).
     if (has_deps) {
         WARP_FOR(lane) {
-            for (int q = W.dep_off[n] + lane; q < W.dep_off[n + 1]; q += 32) {
-                int dep = W.dep_list[q];
-                if (NS(W, dep).node_act != t) continue;  // that node has nothing to transfer in this step: it pops nothing (and does not publish)
-                volatile int *done = &NDONE(W, dep);
+            for (int q = lane; q < nol; q += 32) {
+                int ol = S.ol[q];
+                if (!(W.l_flags[ol] & LF_SEES_POPS) || LC(W, ol).hcount == 0) continue;  // nothing can leave that link in this step
+                volatile int *done = &NDONE(W, W.l_end[ol]);
 #ifdef UX_EMU
                 if (*done < t + 1) dev_error(W, DERR_DEP_TIMEOUT, n);
 #else
@@ -413,10 +415,10 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
         for (int q = lane; q < nol; q += 32) {
             int ol = S.ol[q];
             int hd = LQ(W, ol).head[cur], fl_ = W.l_flags[ol];
-            // pops of this step by the link's end node (a lower level of this launch).  Only a node that transfers in this step
-            // writes the count -- an idle end node may not even have reset last step's value yet (small worlds reset it inside
-            // this launch, in that node's own pre_node), so its count is taken as 0 without reading it.
-            int pk_ = ((fl_ & LF_SEES_POPS) && NS(W, W.l_end[ol]).node_act == t) ? ld_cg(&LC(W, ol).pop_k2) : 0;
+            // pops of this step by the link's end node (a lower level of this launch).  Only a node with flagged head positions on
+            // this link can pop from it -- otherwise the end node may not even have reset last step's value yet (small worlds reset
+            // it inside this launch, in that node's own pre_node), so the count is taken as 0 without reading it.
+            int pk_ = ((fl_ & LF_SEES_POPS) && LC(W, ol).hcount > 0) ? ld_cg(&LC(W, ol).pop_k2) : 0;
             int tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
             long long o = W.l_roff[ol];
             double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
@@ -930,10 +932,10 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                 NPROF_T(pt2) NPROF_MAX(1, pt1, pt2)
                 // ---- dependency wait: only now are the pops of lower-level end nodes needed
                 if ((lvl_raw & 0xffff) > 0) {
-                    for (int q = W.dep_off[n]; q < W.dep_off[n + 1]; q++) {
-                        int dep = W.dep_list[q];
-                        if ((&NS(W, dep) + ln)->node_act != t) continue;  // idle there: it pops nothing and does not publish
-                        volatile int *done = &NDONE(W, dep) + ln;
+                    for (int q = 0; q < nol; q++) {  // per requested out-link: its end node can pop only flagged head positions (hcount > 0)
+                        const int ol = o_id[q];
+                        if (!(W.l_flags[ol] & LF_SEES_POPS) || (&LC(W, ol) + ln)->hcount == 0) continue;
+                        volatile int *done = &NDONE(W, W.l_end[ol]) + ln;
 #ifdef UX_EMU
                         if (*done < t + 1) dev_error(Wr, DERR_DEP_TIMEOUT, n);
 #else
@@ -953,7 +955,7 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     for (int u = 0; u < 4; u++) {
                         int ol = o_id[b + u < nol ? b + u : b];
                         q_[u] = *reinterpret_cast<const int4 *>(&LQ(W, ol) + ln); ci_[u] = (&LR(W, ol) + ln)->cap_in_rem; ca_[u] = W.cum_arr[TLI(W, t, ol) + ln];
-                        pk_[u] = ((W.l_flags[ol] & LF_SEES_POPS) && (&NS(W, W.l_end[ol]) + ln)->node_act == t) ? ld_cg(&(&LC(W, ol) + ln)->pop_k2) : 0;
+                        pk_[u] = ((W.l_flags[ol] & LF_SEES_POPS) && (&LC(W, ol) + ln)->hcount > 0) ? ld_cg(&(&LC(W, ol) + ln)->pop_k2) : 0;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) if (b + u < nol) {

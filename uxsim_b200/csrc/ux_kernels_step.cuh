@@ -42,19 +42,29 @@ UX_DEV void node_signal_capacity(const DevWorld &W, int n, int t, int ln = 0) {
 
 template <int MC, int MD>
 struct PreSmem {
-    int choice[MC], g_vid[MC], g_err[MC];
-    int o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD];
+    // generation attempts (the first platoons of the node's vertical queue)
+    int choice[MC], g_vid[MC], g_err[MC], g_trav[MC], g_slot[MC];
+    unsigned char g_q[MC], g_lane[MC];
+    int tried, accepted;
+    // out-links
+    int o_hd[MD], o_tail[MD], o_tail0[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD], o_win_n[MD], o_win_f[MD];
     long long o_roff[MD];
     double o_ci[MD], o_dpl[MD], o_vmax[MD], o_cumarr[MD];
-    double w_x[MC];
+    double w_x[MC];  // window of the last `lanes` platoons of each out-link; circular once full (o_win_f = oldest entry)
 };
 
+// One warp runs the first half of a node's timestep.  Everything it reads is known when the kernel starts, so the loads of all
+// parts are issued in ONE parallel phase, each part on its own lanes: the route draws of the waiting platoons (the longest chain),
+// the out-links' inflow side (Link::update + tail state + window), the in-links' outflow side, the signal / node capacity step.
+// Lane 0 then walks the generation attempts on shared memory only, and the lanes apply what it decided.
 template <int MC, int MD>
-UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *rel, int n, int t, int lane) {
+UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int n, int t, int lane) {
     int cur = t & 1, L = W.L;
+    size_t C = (size_t)W.C;
     int o0 = W.n_out_off[n], nout = W.n_out_off[n + 1] - o0;
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
     bool fresh = (t % W.itt) == 0 && !W.node_rl;  // (ensembles: k_link_pre<true> has measured the mean speeds already)
+    const bool split = W.pre_split != 0;  // the scalar link update and the node's signal / capacity step ran before this kernel (k_link_pre)
     NLAP_INIT
     // ---- instantaneous travel time of the out-links (whole warp per link, only every `itt` steps)
     if (fresh) {
@@ -72,149 +82,127 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int *r
         WARP_SYNC();
     }
     NLAP(g_node_prof2, 0)
-    if (W.pre_split) {
-        // the scalar link update -- curve carries, capacity tokens -- and the node's signal / capacity step ran before this
-        // kernel, one thread per link / node (k_link_pre): only the freshly measured travel times are left to store
-        if (fresh) {
-            WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) W.tt_inst[TLI(W, t, W.n_out[o0 + k])] = tt_s[k]; }
-            WARP_SYNC();
-        }
-    } else {
-    // ---- scalar link update (Link::update traffi.cpp:542-565), small worlds only (a separate launch would cost more than it
-    //      saves).  A link's inflow side (arrival curve, capacity_in tokens, instantaneous travel time) belongs to its START
-    //      node, its outflow side (departure curve, capacity_out tokens, pops of this step) to its END node.
+    // ---- the parallel phase.  Attempts: the vertical queue of an origin is sorted by departure step, and platoons with departure
+    //      step <= t-1 are in it (HOME -> WAIT, traffi.cpp:836-841), so the attempts of this step are the released prefix of the next
+    //      `sum of out-link lanes` entries; every lane tests its own entry.
+    const int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0;
+    int gh = NS(W, n).gen_head;
+    int amax = glen - gh;
+    { int tl_ = W.n_out_lanes[n]; if (amax > tl_) amax = tl_; if (amax > MC) amax = MC; }
+    if (nout == 0) amax = 0;
+    const int rB = amax, rC = rB + nout, rD = rC + (split ? 0 : nin);  // first lane of the out-link / in-link / node parts
     WARP_FOR(ln) {
-        for (int k = ln; k < nout; k += 32) {
-            int l = W.n_out[o0 + k];
-            size_t row = TLI(W, t, l), prev = TLI(W, t - 1, l);
-            if (fresh) W.tt_inst[row] = tt_s[k];
-            else if (t > 0) W.tt_inst[row] = W.tt_inst[prev];
-            if (t != 0) W.cum_arr[row] = W.cum_arr[prev];
-            double ci = W.l_cap_in[l];
-            if (ci < 10e9) { if (LR(W, l).cap_in_rem < W.dn * W.l_lanes[l]) LR(W, l).cap_in_rem += ci * W.dt; } else LR(W, l).cap_in_rem = 10e9;
+        for (int i = ln; i < amax; i += 32) {  // Node::generate, the draw (traffi.cpp:112-128)
+            int vid = W.gen_list[g0 + gh + i], e = 0, ch = -1, q = 255, trav = 0;
+            if (W.gen_ts[g0 + gh + i] <= t - 1) {
+                ch = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
+                if (ch >= 0) { q = 0; while (q < nout && W.n_out[o0 + q] != ch) q++; trav = W.v_trav[vid]; }
+            } else vid = -1;
+            G.g_vid[i] = vid; G.choice[i] = ch; G.g_err[i] = e; G.g_q[i] = (unsigned char)q; G.g_trav[i] = trav;
         }
-        for (int k = ln; k < nin; k += 32) {
-            int l = W.n_in[i0 + k];
-            size_t row = TLI(W, t, l);
-            if (t != 0) W.cum_dep[row] = W.cum_dep[TLI(W, t - 1, l)];
-            double co = W.l_cap_out[l];
-            if (co < 10e9) { if (LR(W, l).cap_out_rem < W.dn * W.l_lanes[l]) LR(W, l).cap_out_rem += co * W.dt; } else LR(W, l).cap_out_rem = 10e9;
-            LC(W, l).pop_k2 = 0;
+        for (int q = (ln - rB) & 31; q < nout; q += 32) {  // out-links: Link::update of the inflow side (traffi.cpp:542-565), tail state, window
+            int ol = W.n_out[o0 + q];
+            int hd = LQ(W, ol).head[cur], tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+            long long o = W.l_roff[ol];
+            size_t row = TLI(W, t, ol);
+            double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_;
+            if (!split) {
+                size_t prev = TLI(W, t - 1, ol);
+                ca_ = t != 0 ? W.cum_arr[prev] : W.cum_arr[row];
+                double cin = W.l_cap_in[ol];
+                if (fresh) W.tt_inst[row] = tt_s[q];
+                else if (t > 0) W.tt_inst[row] = W.tt_inst[prev];
+                if (cin < 10e9) { if (ci_ < W.dn * lanes) ci_ += cin * W.dt; } else ci_ = 10e9;
+            } else {
+                ca_ = W.cum_arr[row];
+                if (fresh) W.tt_inst[row] = tt_s[q];
+            }
+            int sz = tl - hd, wn = sz < lanes ? sz : lanes, woff = 0;
+            for (int k = 0; k < q; k++) woff += W.l_lanes[W.n_out[o0 + k]];
+            int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
+            for (int k = 0; k < wn && woff + k < MC; k++) G.w_x[woff + k] = W.X[(size_t)cur * C + o + ring_slot(hd, sz - wn + k, cap)];
+            G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_tail0[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
+            G.o_ci[q] = ci_; G.o_dpl[q] = dpl_; G.o_vmax[q] = vm_; G.o_cumarr[q] = ca_; G.o_lastlane[q] = ll_;
+            G.o_win_off[q] = woff; G.o_win_n[q] = wn; G.o_win_f[q] = 0;
+        }
+        if (!split) {
+            for (int k = (ln - rC) & 31; k < nin; k += 32) {  // in-links: the outflow side (departure curve, capacity_out tokens, pops of this step)
+                int l = W.n_in[i0 + k];
+                size_t row = TLI(W, t, l);
+                if (t != 0) W.cum_dep[row] = W.cum_dep[TLI(W, t - 1, l)];
+                double co = W.l_cap_out[l];
+                if (co < 10e9) { if (LR(W, l).cap_out_rem < W.dn * W.l_lanes[l]) LR(W, l).cap_out_rem += co * W.dt; } else LR(W, l).cap_out_rem = 10e9;
+                LC(W, l).pop_k2 = 0;
+            }
+            if (ln == (rD & 31)) node_signal_capacity(W, n, t);
         }
     }
     WARP_SYNC();
-    }
-    NLAP(g_node_prof2, 1)
-    // ---- release HOME -> WAIT: platoons with departure step <= t-1 are in the vertical queue (traffi.cpp:836-841).
-    //      The per-origin list is sorted by departure step, so the released ones are a prefix: 32 entries per probe.
-    int g0 = W.gen_off[n], glen = W.gen_off[n + 1] - g0, av = NS(W, n).gen_avail;
-    while (av < glen) {
-        WARP_FOR(ln) if (ln == 0) *rel = 0;
-        WARP_SYNC();
-        WARP_FOR(ln) { int idx = av + ln; if (idx < glen && W.gen_ts[g0 + idx] <= t - 1) atomicAdd(rel, 1); }
-        WARP_SYNC();
-        int c = *rel;
-        WARP_SYNC();
-        av += c;
-        if (c < 32) break;
-    }
-    // ---- generate (traffi.cpp:105-189).  The route draws of the first `natt` waiting platoons and the tail state of the
-    //      out-links are fetched in parallel; lane 0 then walks the attempts on shared memory and stops at the first refusal.
-    NLAP(g_node_prof2, 2)
-    int gh = NS(W, n).gen_head;
-    int natt = av - gh;
-    { int tl_ = W.n_out_lanes[n]; if (natt > tl_) natt = tl_; if (natt > MC) natt = MC; }
-    if (nout == 0) natt = 0;
-    if (natt > 0) {
-        WARP_FOR(ln) {
-            for (int i = ln; i < natt; i += 32) {
-                int vid = W.gen_list[g0 + gh + i], e = 0;
-                G.g_vid[i] = vid;
-                G.choice[i] = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
-                G.g_err[i] = e;
-            }
-            for (int q = ln; q < nout; q += 32) {
-                int ol = W.n_out[o0 + q];
-                int hd = LQ(W, ol).head[cur], tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
-                long long o = W.l_roff[ol];
-                double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
-                int sz = tl - hd;
-                int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
-                G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
-                G.o_ci[q] = ci_; G.o_dpl[q] = dpl_; G.o_vmax[q] = vm_; G.o_cumarr[q] = ca_; G.o_lastlane[q] = ll_;
-                G.o_win_n[q] = sz < lanes ? sz : lanes;
-            }
-        }
-        WARP_SYNC();
-        NLAP(g_node_prof2, 3)
-        WARP_FOR(ln) if (ln == 0) { int acc = 0; for (int q = 0; q < nout; q++) { G.o_win_off[q] = acc; acc += G.o_lanes[q]; } G.o_win_off[nout] = acc; }
-        WARP_SYNC();
-        WARP_FOR(ln) {
-            int tot = G.o_win_off[nout];
-            for (int e = ln; e < tot && e < MC; e += 32) {
-                int q = 0;
-                while (G.o_win_off[q + 1] <= e) q++;
-                int k = e - G.o_win_off[q];
-                if (k < G.o_win_n[q]) {
-                    int sz = G.o_tail[q] - G.o_hd[q];
-                    G.w_x[e] = W.X[(size_t)cur * W.C + G.o_roff[q] + ring_slot(G.o_hd[q], sz - G.o_win_n[q] + k, G.o_cap[q])];
-                }
-            }
-        }
-        WARP_SYNC();
-        NLAP(g_node_prof2, 4)
-        WARP_FOR(ln) if (ln == 0) {
-            for (int i = 0; i < natt; i++) {
-                int vid = G.g_vid[i], ol = G.choice[i];
-                if (G.g_err[i]) { dev_error(W, G.g_err[i], vid); break; }
-                W.v_next[vid] = ol;
-                if (ol < 0) break;
-                int q = 0;
-                while (q < nout && W.n_out[o0 + q] != ol) q++;
-                int lanes = G.o_lanes[q], sz = G.o_tail[q] - G.o_hd[q], w0 = G.o_win_off[q];
-                bool ok = false;  // traffi.cpp:130-142
-                if (sz < lanes) ok = true;
-                else if (G.w_x[w0] > G.o_dpl[q]) ok = true;
-                if (G.o_ci[q] < W.dn) ok = false;
-                if (!ok) break;
-                if (sz >= G.o_cap[q]) { dev_error(W, DERR_RING_FULL, ol); break; }
-                gh++;
-                int lane_new = sz > 0 ? (G.o_lastlane[q] + 1) % lanes : 0;
-                int slot = ring_slot(G.o_tail[q], 0, G.o_cap[q]);
-                long long o = G.o_roff[q];
-                W.X[(size_t)cur * W.C + o + slot] = 0.0;
-                W.X[(size_t)(cur ^ 1) * W.C + o + slot] = 0.0;
-                W.V[o + slot] = G.o_vmax[q];
-                W.VID[o + slot] = vid;
-                W.LANE[o + slot] = lane_new;
-                G.o_tail[q] += 1; G.o_lastlane[q] = lane_new;
-                if (G.o_win_n[q] < lanes) { G.w_x[w0 + G.o_win_n[q]] = 0.0; G.o_win_n[q] += 1; }
-                else { for (int e = w0; e < w0 + lanes - 1; e++) G.w_x[e] = G.w_x[e + 1]; G.w_x[w0 + lanes - 1] = 0.0; }
-                W.v_state[vid] = UX_VS_RUN;
-                if (W.log_mode) W.v_gen_ts[vid] = t;
-                W.v_atl[vid] = (double)t * W.dt;
-                W.v_entry_x[vid] = 0.0;
-                mark_entered(W, vid, ol, t);
-                G.o_cumarr[q] += W.dn;
-                G.o_ci[q] -= W.dn;
-            }
-            NS(W, n).gen_head = gh;
-        }
-        WARP_SYNC();
-        NLAP(g_node_prof2, 5)
-        WARP_FOR(ln) {
-            for (int q = ln; q < nout; q += 32) {
-                int ol = W.n_out[o0 + q];
-                LR(W, ol).cap_in_rem = G.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = G.o_cumarr[q]; LQ(W, ol).tail = G.o_tail[q];
-            }
-        }
-        WARP_SYNC();
-    }
-    // tail after generation (the link update tells transfer pushes from generated ones): k_link_pre already copied the unchanged tails
-    if (!W.pre_split || natt > 0) WARP_FOR(ln) { for (int k = ln; k < nout; k += 32) { int l = W.n_out[o0 + k]; LQ(W, l).tail_k1 = LQ(W, l).tail; } }
+    NLAP(g_node_prof2, 3)
+    // ---- generate (traffi.cpp:105-189): lane 0 walks the attempts in order on shared memory; the first refusal ends them
     WARP_FOR(ln) if (ln == 0) {
-        NS(W, n).gen_avail = av;
-        if (!W.pre_split) node_signal_capacity(W, n, t);
+        int tried = 0, accepted = 0;
+        for (int i = 0; i < amax; i++) {
+            int vid = G.g_vid[i];
+            if (vid < 0) break;  // not released yet
+            if (G.g_err[i]) { dev_error(W, G.g_err[i], vid); break; }
+            tried = i + 1;
+            if (G.choice[i] < 0) break;
+            int q = G.g_q[i];
+            int lanes = G.o_lanes[q], sz = G.o_tail[q] - G.o_hd[q], w0 = G.o_win_off[q];
+            bool ok = false;  // traffi.cpp:130-142
+            if (sz < lanes) ok = true;
+            else if (G.w_x[w0 + G.o_win_f[q]] > G.o_dpl[q]) ok = true;
+            if (G.o_ci[q] < W.dn) ok = false;
+            if (!ok) break;
+            if (sz >= G.o_cap[q]) { dev_error(W, DERR_RING_FULL, G.choice[i]); break; }
+            accepted = i + 1;
+            int lane_new = sz > 0 ? (G.o_lastlane[q] + 1) % lanes : 0;
+            G.g_slot[i] = ring_slot(G.o_tail[q], 0, G.o_cap[q]); G.g_lane[i] = (unsigned char)lane_new;
+            G.o_tail[q] += 1; G.o_lastlane[q] = lane_new;
+            if (G.o_win_n[q] < lanes) { G.w_x[w0 + G.o_win_n[q]] = 0.0; G.o_win_n[q] += 1; }
+            else { G.w_x[w0 + G.o_win_f[q]] = 0.0; G.o_win_f[q] = G.o_win_f[q] + 1 == lanes ? 0 : G.o_win_f[q] + 1; }
+            G.o_cumarr[q] += W.dn;
+            G.o_ci[q] -= W.dn;
+        }
+        G.tried = tried; G.accepted = accepted;
+        if (accepted) NS(W, n).gen_head = gh + accepted;
+        { int nv = 0; while (nv < amax && G.g_vid[nv] >= 0) nv++; if (gh + nv > NS(W, n).gen_avail) NS(W, n).gen_avail = gh + nv; }  // released so far (the replica-lane form keeps counting from here)
+    }
+    WARP_SYNC();
+    NLAP(g_node_prof2, 5)
+    // ---- apply: the platoons that were tried / generated, then the out-link scalars
+    WARP_FOR(ln) {
+        const int tried = G.tried, accepted = G.accepted;
+        for (int i = ln; i < tried; i += 32) {
+            int vid = G.g_vid[i], ol = G.choice[i];
+            W.v_next[vid] = ol;
+            if (i >= accepted) continue;
+            int q = G.g_q[i], slot = G.g_slot[i];
+            long long o = G.o_roff[q];
+            W.X[(size_t)cur * C + o + slot] = 0.0;
+            W.X[(size_t)(cur ^ 1) * C + o + slot] = 0.0;
+            W.V[o + slot] = G.o_vmax[q];
+            W.VID[o + slot] = vid;
+            W.LANE[o + slot] = G.g_lane[i];
+            W.v_state[vid] = UX_VS_RUN;
+            if (W.log_mode) W.v_gen_ts[vid] = t;
+            W.v_atl[vid] = (double)t * W.dt;
+            W.v_entry_x[vid] = 0.0;
+            // mark_entered (traffi.cpp:160-166)
+            if (W.no_cyclic) { int sn = W.l_start[ol]; W.v_visited[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
+            W.v_trav[vid] = G.g_trav[i] + 1;
+            W.v_link[vid] = ol;
+            record_traversal(W, vid, G.g_trav[i], ol, t);
+        }
+        for (int q = (ln - rB) & 31; q < nout; q += 32) {
+            int ol = W.n_out[o0 + q];
+            const bool pushed = G.o_tail[q] != G.o_tail0[q];
+            if (!split || pushed) { LR(W, ol).cap_in_rem = G.o_ci[q]; W.cum_arr[TLI(W, t, ol)] = G.o_cumarr[q]; }
+            if (pushed) LQ(W, ol).tail = G.o_tail[q];
+            // tail after generation (the link update tells transfer pushes from generated ones): k_link_pre already copied the unchanged tails
+            if (!split || pushed) LQ(W, ol).tail_k1 = G.o_tail[q];
+        }
     }
     WARP_SYNC();
     NLAP(g_node_prof2, 6)
@@ -239,60 +227,74 @@ struct XferSmem {
     long long roff[MD];
     double co_rem[MD], mp[MD], vmax[MD], cumdep[MD];
     unsigned char sig_ok[MD];
-    // head positions of the in-links
-    int p_vid[MC], p_next[MC], p_dts[MC];
+    // head positions of the in-links (gathered once; the serial loop below reads and writes only these)
+    int p_vid[MC], p_next[MC], p_dts[MC], p_trav[MC], p_es[MC];
     short p_in[MC], p_j[MC], c_idx[MC], expd[MC];
-    unsigned char p_flag[MC];
-    double p_x[MC], p_xold[MC], p_v[MC], p_mr[MC], p_atl[MC], p_ex[MC], p_dist[MC];
-    int nc, npos, nol, any_wait, nexp, first, cur_slot, n_picks;
-    int omask[MD][2];          // per requested out-link: candidates currently eligible to move onto it
+    unsigned char p_flag[MC], p_q[MC];  // p_q: index of the requested out-link (255: none)
+    double p_xold[MC], p_v[MC], p_mr[MC], p_atl[MC], p_dist[MC];  // p_mr: residual move, rescaled to the wanted out-link's speed before the loop; p_dist: distance incl. this link
+    // what the loop decided for a position, applied to global memory afterwards by all lanes
+    unsigned char p_act[MC], p_olane[MC];  // 0 untouched, 1 moved onto out-link p_q, 2 trip ended
+    int p_ord[MC], p_oslot[MC];            // exit-event number on the in-link; ring slot on the out-link (-1: ring full)
+    double p_xn[MC];                       // position on the out-link
+    int nc, npos, nol, any_wait, nexp;
+    int omask[MD];             // per requested out-link: in-links whose front platoon may move onto it now (bit per in-link)
     unsigned char ogood[MD];   // per requested out-link: acceptance test result
-    unsigned char c_first[MC], c_q[MC];
+    unsigned char c_first[MC];
     double fc_rem;
     short shuf_j[MC];
     double u_merge[MC];
     // requested out-links
-    int ol[MD], o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD];
+    int ol[MD], o_hd[MD], o_tail[MD], o_lanes[MD], o_cap[MD], o_lastlane[MD], o_win_off[MD + 1], o_win_n[MD], o_win_f[MD];
     long long o_roff[MD];
     double o_ci[MD], o_dpl[MD], o_len[MD], o_vmax[MD], o_cumarr[MD];
-    double w_x[MC], w_xold[MC];  // window of the last `lanes` platoons of each out-link (oldest first)
+    double w_x[MC], w_xold[MC];  // window of the last `lanes` platoons of each out-link; circular once full (o_win_f = oldest entry)
 };
 
+// Vehicle::end_trip (traffi.cpp:886-927) of the front platoon (position p) of an in-link, inside the serial loop: counters only,
+// the per-platoon stores follow in the apply phase
 template <int MC, int MD>
-UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem<MC, MD> &S, int p, int t) {  // Vehicle::end_trip traffi.cpp:886-927
-    int ii = S.p_in[p], il = S.il[ii], vid = S.p_vid[p];
+UX_DEV void xfer_end_trip(const DevWorld &W, XferSmem<MC, MD> &S, int p) {
+    int ii = S.p_in[p];
     S.trips[ii] += 1;
     S.cumdep[ii] += W.dn;
-    double atl = S.p_atl[p];
-    {   // record_tt_event
-        int s = (int)(atl / W.dt);
-        if (s < 0) s = 0;
-        if (s >= W.T) s = W.T - 1;
-        int ord = ++S.evc[ii];
-        W.ev_ord[TLI(W, s, il)] = ord;
-        W.ev_tt[TLI(W, s, il)] = ((double)t + 1.0) * W.dt - atl;
-    }
-    W.v_atl[vid] = (double)t * W.dt;
-    W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
-    W.v_link[vid] = -1;
-    if (S.p_flag[p] & VF_ABORT) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
-    else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = (double)t * W.dt - (double)S.p_dts[p] * W.dt; }
-    if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 2; }
-    W.v_flags[vid] = 0;
+    S.p_ord[p] = ++S.evc[ii];
+    S.p_act[p] = 2;
     S.popped[ii] += 1;
+}
+
+// the out-link (index) that the front platoon of in-link ii may move onto now, 255 if none (traffi.cpp:305-330: front of its
+// link, outflow tokens, green)
+template <int MC, int MD>
+UX_DEV int xfer_front_q(const DevWorld &W, const XferSmem<MC, MD> &S, int ii, int npos) {
+    if (S.popped[ii] >= S.hc[ii]) return 255;
+    int fp = S.pos_off[ii] + S.popped[ii];
+    if (fp >= npos || !(S.p_flag[fp] & VF_CAND)) return 255;
+    if (S.co_rem[ii] < W.dn || !S.sig_ok[ii]) return 255;
+    return S.p_q[fp];
+}
+
+template <int MC, int MD>
+UX_DEV bool xfer_accepts(const DevWorld &W, const XferSmem<MC, MD> &S, int q) {  // traffi.cpp:285-300 (the node capacity is tested by the caller)
+    int lanes_ol = S.o_lanes[q], sz = S.o_tail[q] - S.o_hd[q];
+    bool ok = false;
+    if (sz < lanes_ol) ok = true;
+    else if (S.w_x[S.o_win_off[q] + S.o_win_f[q]] > S.o_dpl[q]) ok = true;
+    if (S.o_ci[q] < W.dn) ok = false;
+    return ok;
 }
 
 #ifndef XFER_WARPS
 #define XFER_WARPS 4
 #endif
+// Returns true when it has published the node's completion itself (`publish`: some node may be waiting for this one).
 template <int MC, int MD>
-UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps) {
+UX_DEV bool xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool has_deps, bool publish) {
     int cur = t & 1, L = W.L;
     size_t C = (size_t)W.C;
     NLAP_INIT
-    if (NS(W, n).node_act != t) return;  // no in-link of this node has a flagged head position (hcount == 0 everywhere): nothing to do
+    if (NS(W, n).node_act != t) return false;  // no in-link of this node has a flagged head position (hcount == 0 everywhere): nothing to do
     int i0 = W.n_in_off[n], nin = W.n_in_off[n + 1] - i0;
-    if (nin == 0) return;
+    if (nin == 0) return false;
     int nsig = W.n_sig_off[n + 1] - W.n_sig_off[n], phase = NS(W, n).sig_phase;
     // ---- A1: in-link state
     WARP_FOR(lane) {
@@ -319,7 +321,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     }
     WARP_SYNC();
     int npos = S.npos;
-    if (npos == 0) return;
+    if (npos == 0) return false;
     // ---- A2: the platoons at the in-link heads
     WARP_FOR(lane) {
         for (int p = lane; p < npos; p += 32) {
@@ -331,13 +333,18 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             int vid = W.VID[o + slot];
             unsigned char f = W.v_flags[vid];
             int nx = W.v_next[vid];
-            double x_ = 0, xo_ = 0, v_ = 0, mr_ = 0, atl_ = 0, ex_ = 0, di_ = 0; int dts_ = 0;
+            double x_ = 0, xo_ = 0, v_ = 0, mr_ = 0, atl_ = 0, ex_ = 0, di_ = 0; int dts_ = 0, trav_ = 0;
             if (f & (VF_CAND | VF_WAIT_END)) {
                 x_ = W.X[(size_t)cur * C + o + slot]; xo_ = W.X[(size_t)(cur ^ 1) * C + o + slot]; v_ = W.V[o + slot];
                 mr_ = W.v_mr[vid]; atl_ = W.v_atl[vid]; ex_ = W.v_entry_x[vid]; di_ = W.v_dist[vid]; dts_ = W.v_depart_ts[vid];
+                if (f & VF_CAND) trav_ = W.v_trav[vid];
             }
-            S.p_vid[p] = vid; S.p_in[p] = (short)ii; S.p_j[p] = (short)j; S.p_flag[p] = f; S.p_next[p] = nx;
-            S.p_x[p] = x_; S.p_xold[p] = xo_; S.p_v[p] = v_; S.p_mr[p] = mr_; S.p_atl[p] = atl_; S.p_ex[p] = ex_; S.p_dist[p] = di_; S.p_dts[p] = dts_;
+            int es = (int)(atl_ / W.dt);  // entry step of the link-exit event (record_tt_event, traffi.cpp:357-362)
+            if (es < 0) es = 0;
+            if (es >= W.T) es = W.T - 1;
+            S.p_vid[p] = vid; S.p_in[p] = (short)ii; S.p_j[p] = (short)j; S.p_flag[p] = f; S.p_next[p] = nx; S.p_q[p] = 255; S.p_act[p] = 0;
+            S.p_xold[p] = xo_; S.p_v[p] = v_; S.p_mr[p] = mr_; S.p_atl[p] = atl_; S.p_dist[p] = di_ + (x_ - ex_); S.p_dts[p] = dts_;
+            S.p_trav[p] = trav_; S.p_es[p] = es;
         }
     }
     WARP_SYNC();
@@ -375,12 +382,12 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     }
     WARP_SYNC();
     int nc = S.nc, nol = S.nol;
-    if (nc == 0 && !S.any_wait) return;
+    if (nc == 0 && !S.any_wait) return false;
     WARP_FOR(lane) {
         for (int k = lane; k < nc; k += 32) {
-            int nl = S.p_next[S.c_idx[k]], q = 255;
+            int p = S.c_idx[k], nl = S.p_next[p], q = 255;
             for (int r = 0; r < nol; r++) if (S.ol[r] == nl) { q = r; break; }
-            S.c_q[k] = (unsigned char)q;
+            S.p_q[p] = (unsigned char)q;
         }
     }
     NLAP(g_node_prof, 0)
@@ -428,16 +435,18 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             S.o_hd[q] = hd; S.o_tail[q] = tl; S.o_lanes[q] = lanes; S.o_cap[q] = cap; S.o_roff[q] = o;
             S.o_ci[q] = ci_; S.o_dpl[q] = dpl_; S.o_len[q] = len_; S.o_vmax[q] = vm_; S.o_cumarr[q] = ca_;
             S.o_lastlane[q] = ll_;
-            S.o_win_n[q] = sz < lanes ? sz : lanes;
+            S.o_win_n[q] = sz < lanes ? sz : lanes; S.o_win_f[q] = 0; S.omask[q] = 0;
         }
     }
     WARP_SYNC();
     WARP_FOR(lane) if (lane == 0) {
-        int acc = 0;
-        for (int q = 0; q < nol; q++) { S.o_win_off[q] = acc; acc += S.o_lanes[q]; }
-        S.o_win_off[nol] = acc;
+        int acc = 0, nexp = 0;
+        for (int q = 0; q < nol; q++) { S.o_win_off[q] = acc; acc += S.o_lanes[q]; for (int r = 0; r < S.o_lanes[q] && nexp < MC; r++) S.expd[nexp++] = (short)q; }
+        S.o_win_off[nol] = acc; S.nexp = nexp;
     }
     WARP_SYNC();
+    int nexp = S.nexp;
+    int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
     WARP_FOR(lane) {
         int tot = S.o_win_off[nol];
         for (int e = lane; e < tot && e < MC; e += 32) {
@@ -451,156 +460,90 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
                 S.w_xold[e] = W.X[(size_t)(cur ^ 1) * C + S.o_roff[q] + slot];
             }
         }
-    }
-    WARP_SYNC();
-    NLAP(g_node_prof, 2)
-    // ---- B: the slot loop.  Slots are inherently sequential (each move changes what the next slot sees), but inside
-    //          a slot the eligibility scan over the candidates runs one lane per candidate, and all random numbers of
-    //          the node (shuffle indices, merge-lottery uniforms) are drawn up front in parallel: Philox is stateless.
-    WARP_FOR(lane) if (lane == 0) {
-        int nexp = 0;
-        for (int q = 0; q < nol; q++) for (int r = 0; r < S.o_lanes[q] && nexp < MC; r++) S.expd[nexp++] = (short)q;
-        S.nexp = nexp;
-    }
-    WARP_SYNC();
-    int nexp = S.nexp;
-    int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
-    if (!W.hard_det) {
-        WARP_FOR(lane) {
+        // all random numbers of the node (shuffle indices, merge-lottery uniforms) are drawn up front: Philox is stateless
+        if (!W.hard_det) {
             for (int i = 1 + lane; i < nexp; i += 32)  // Fisher-Yates step i uses draw number (nexp-1-i) (traffi.cpp:276-282)
                 S.shuf_j[i] = (short)ux_rng_below(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nexp - 1 - i), i + 1);
             for (int d = lane; d < nexp; d += 32)
                 S.u_merge[d] = ux_rng_uniform(W.seed, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + d));
         }
-        WARP_SYNC();
-        WARP_FOR(lane) if (lane == 0) {
-            for (int i = nexp - 1; i > 0; i--) { int j = S.shuf_j[i]; short tmp = S.expd[i]; S.expd[i] = S.expd[j]; S.expd[j] = tmp; }
+        // the residual move of every candidate in the speed of the link it wants to enter (traffi.cpp:400-402): the division stays out of the loop
+        for (int k = lane; k < nc; k += 32) {
+            int p = S.c_idx[k], q = S.p_q[p];
+            if (q != 255) S.p_mr[p] = S.p_mr[p] * S.o_vmax[q] / S.vmax[S.p_in[p]];
         }
-        WARP_SYNC();
     }
-    // Rounds instead of slots: a slot whose out-link cannot accept or has no eligible candidate changes nothing (and
-    // draws nothing), so each round evaluates every out-link / candidate in parallel against the current state, jumps
-    // to the first slot (in shuffled order) that moves a platoon, applies that one move on lane 0, and repeats.
-    NLAP(g_node_prof, 3)
-    double fc = W.n_fc[n];
-    WARP_FOR(lane) if (lane == 0) { S.cur_slot = 0; S.n_picks = 0; S.fc_rem = NR(W, n).fc_rem; }
     WARP_SYNC();
-    while (true) {
-        WARP_FOR(lane) {
-            if (lane == 0) S.first = 0x7fffffff;
-            for (int q = lane; q < nol; q += 32) {
-                S.omask[q][0] = 0; S.omask[q][1] = 0;
-                int lanes_ol = S.o_lanes[q], sz = S.o_tail[q] - S.o_hd[q];
-                bool ok = false;  // acceptance (traffi.cpp:285-300)
-                if (sz < lanes_ol) ok = true;
-                else if (S.w_x[S.o_win_off[q]] > S.o_dpl[q]) ok = true;
-                if (S.o_ci[q] < W.dn) ok = false;
-                if (S.fc_rem < W.dn) ok = false;
-                S.ogood[q] = ok ? 1 : 0;
+    NLAP(g_node_prof, 2)
+    WARP_FOR(lane) {
+        for (int q = lane; q < nol; q += 32) S.ogood[q] = xfer_accepts(W, S, q) ? 1 : 0;
+        for (int ii = lane; ii < nin; ii += 32) { int f = xfer_front_q(W, S, ii, npos); if (f != 255) atomicOr(&S.omask[f], 1 << ii); }
+    }
+    WARP_SYNC();
+    NLAP(g_node_prof, 3)
+    // ---- B: the slot loop (traffi.cpp:283-430), lane 0, on shared memory only.  Slots are inherently sequential -- each move
+    //          changes what the next slot sees -- but at any moment an in-link offers at most ONE platoon (its front), so the state a
+    //          slot looks at is one mask of in-links per out-link plus the out-link's acceptance flag, both refreshed only for the
+    //          links a move touched.  Global memory sees nothing here: what the loop decides per head position (moved where / trip
+    //          ended, event number, slot, lane, position) is applied afterwards by all lanes.
+    double fc = W.n_fc[n];
+    WARP_FOR(lane) if (lane == 0) {
+        if (!W.hard_det) for (int i = nexp - 1; i > 0; i--) { int j = S.shuf_j[i]; short tmp = S.expd[i]; S.expd[i] = S.expd[j]; S.expd[j] = tmp; }
+        double fc_rem = NR(W, n).fc_rem;
+        int n_picks = 0;
+        for (int s = 0; s < nexp; s++) {
+            if (fc_rem < W.dn) break;  // no slot can move anything any more (traffi.cpp:298-300)
+            const int q = S.expd[s];
+            int m = S.omask[q];
+            if (!m || !S.ogood[q]) continue;
+            short mv[MD]; double mp[MD]; int nm = 0;
+            while (m) {  // eligible fronts in ascending vehicle id
+                int ii = 0; while (!((m >> ii) & 1)) ii++;
+                m &= m - 1;
+                int vid = S.p_vid[S.pos_off[ii] + S.popped[ii]], at = nm++;
+                while (at > 0 && S.p_vid[S.pos_off[mv[at - 1]] + S.popped[mv[at - 1]]] > vid) { mv[at] = mv[at - 1]; at--; }
+                mv[at] = (short)ii;
             }
-        }
-        WARP_SYNC();
-        WARP_FOR(lane) {
-            for (int k = lane; k < nc; k += 32) {
-                int p = S.c_idx[k], q = S.c_q[k];
-                if (p < 0 || q == 255) continue;
-                int ii = S.p_in[p];
-                if (S.p_j[p] != S.popped[ii]) continue;  // front of its in-link
-                if (S.co_rem[ii] < W.dn) continue;
-                if (!S.sig_ok[ii]) continue;
-                atomicOr(&S.omask[q][k >> 5], (int)(1u << (k & 31)));
-            }
-        }
-        WARP_SYNC();
-        WARP_FOR(lane) {
-            for (int s = S.cur_slot + lane; s < nexp; s += 32) {
-                int q = S.expd[s];
-                if (S.ogood[q] && (S.omask[q][0] | S.omask[q][1])) { atomicMin(&S.first, s); break; }
-            }
-        }
-        WARP_SYNC();
-        int s = S.first;
-        if (s == 0x7fffffff) break;
-        WARP_FOR(lane) if (lane == 0) {
-            int q = S.expd[s], ol = S.ol[q];
-            unsigned m0 = (unsigned)S.omask[q][0], m1 = (unsigned)S.omask[q][1];
-            int lanes_ol = S.o_lanes[q];
-            int sz = S.o_tail[q] - S.o_hd[q], w0 = S.o_win_off[q];
-            double fc_rem = S.fc_rem;
-            int n_picks = S.n_picks;
-            short mv[MC]; double mp[MC]; int nm = 0;
-            for (int wd = 0; wd < 2; wd++) {  // eligible candidates in ascending vehicle id
-                unsigned m = wd ? m1 : m0;
-                while (m) {
-                    int bit = 0; while (!((m >> bit) & 1u)) bit++;
-                    m &= m - 1;
-                    int k = wd * 32 + bit;
-                    mv[nm] = (short)k; mp[nm] = S.mp[S.p_in[S.c_idx[k]]]; nm++;
-                }
-            }
+            for (int i = 0; i < nm; i++) mp[i] = S.mp[mv[i]];
             int pick;
             if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
-            else pick = weighted_pick(mp, nm, S.u_merge[n_picks++]);
-            int k = mv[pick], p = S.c_idx[k], vid = S.p_vid[p], ii = S.p_in[p], il = S.il[ii];
+            else pick = nm == 1 ? (n_picks++, 0) : weighted_pick(mp, nm, S.u_merge[n_picks++]);
+            const int ii = mv[pick], p = S.pos_off[ii] + S.popped[ii];
+            const int lanes_ol = S.o_lanes[q], sz = S.o_tail[q] - S.o_hd[q], w0 = S.o_win_off[q];
             S.co_rem[ii] -= W.dn; S.o_ci[q] -= W.dn;
             if (fc >= 0.0) fc_rem -= W.dn;
             S.cumdep[ii] += W.dn; S.o_cumarr[q] += W.dn;
-            double atl = S.p_atl[p];
-            {   // record_tt_event (traffi.cpp:357-362)
-                int es = (int)(atl / W.dt);
-                if (es < 0) es = 0;
-                if (es >= W.T) es = W.T - 1;
-                int ord = ++S.evc[ii];
-                W.ev_ord[TLI(W, es, il)] = ord;
-                W.ev_tt[TLI(W, es, il)] = (double)t * W.dt - atl;
-            }
-            W.v_atl[vid] = (double)t * W.dt;
-            W.v_dist[vid] = S.p_dist[p] + (S.p_x[p] - S.p_ex[p]);
+            S.p_ord[p] = ++S.evc[ii];
+            S.p_act[p] = 1;
             S.popped[ii] += 1;
-            if (W.no_cyclic) { int sn = W.l_start[ol]; W.v_visited[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
-            { int k = W.v_trav[vid]; W.v_trav[vid] = k + 1; record_traversal(W, vid, k, ol, t); }
-            W.v_link[vid] = ol;
-            W.v_flags[vid] = 0;
             // carry the residual move onto the new link (traffi.cpp:400-419)
-            double x_next = S.p_mr[p] * S.o_vmax[q] / S.vmax[ii];
+            double x_next = S.p_mr[p];
             if (sz >= lanes_ol) {
-                double x_cong = S.w_xold[w0] - S.o_dpl[q];
+                double x_cong = S.w_xold[w0 + S.o_win_f[q]] - S.o_dpl[q];
                 if (x_cong < 0.0) x_cong = 0.0;
                 if (x_next > x_cong) x_next = x_cong;
             }
             if (x_next >= S.o_len[q]) x_next = S.o_len[q];
             if (x_next < 0.0) x_next = 0.0;
-            if (sz >= S.o_cap[q]) dev_error(W, DERR_RING_FULL, ol);
+            S.p_xn[p] = x_next;
+            if (sz >= S.o_cap[q]) { dev_error(W, DERR_RING_FULL, S.ol[q]); S.p_oslot[p] = -1; }
             else {  // push (lane rule traffi.cpp:385-390)
                 int lane_new = sz > 0 ? (S.o_lastlane[q] + 1) % lanes_ol : 0;
-                int slot = ring_slot(S.o_tail[q], 0, S.o_cap[q]);
-                long long o = S.o_roff[q];
-                W.X[(size_t)cur * C + o + slot] = x_next;
-                W.X[(size_t)(cur ^ 1) * C + o + slot] = S.p_xold[p];
-                W.V[o + slot] = S.p_v[p] + x_next / W.dt;
-                W.VID[o + slot] = vid;
-                W.LANE[o + slot] = lane_new;
+                S.p_oslot[p] = ring_slot(S.o_tail[q], 0, S.o_cap[q]); S.p_olane[p] = (unsigned char)lane_new;
                 S.o_tail[q] += 1; S.o_lastlane[q] = lane_new;
                 if (S.o_win_n[q] < lanes_ol) { int e = w0 + S.o_win_n[q]; S.w_x[e] = x_next; S.w_xold[e] = S.p_xold[p]; S.o_win_n[q] += 1; }
-                else {
-                    for (int e = w0; e < w0 + lanes_ol - 1; e++) { S.w_x[e] = S.w_x[e + 1]; S.w_xold[e] = S.w_xold[e + 1]; }
-                    S.w_x[w0 + lanes_ol - 1] = x_next; S.w_xold[w0 + lanes_ol - 1] = S.p_xold[p];
-                }
+                else { int e = w0 + S.o_win_f[q]; S.w_x[e] = x_next; S.w_xold[e] = S.p_xold[p]; S.o_win_f[q] = S.o_win_f[q] + 1 == lanes_ol ? 0 : S.o_win_f[q] + 1; }
             }
-            W.v_entry_x[vid] = x_next;
-            W.v_mr[vid] = 0.0;
-            S.c_idx[k] = -1;  // remove from incoming
             // the new front of the in-link may be waiting for its trip end (traffi.cpp:421-424)
             if (S.popped[ii] < S.hc[ii]) {
                 int fp = S.pos_off[ii] + S.popped[ii];
-                if (fp < npos && (S.p_flag[fp] & VF_WAIT_END)) xfer_end_trip(W, S, fp, t);
+                if (fp < npos && (S.p_flag[fp] & VF_WAIT_END)) xfer_end_trip(W, S, fp);
             }
-            S.fc_rem = fc_rem; S.n_picks = n_picks; S.cur_slot = s + 1;
+            // what this move changed for the slots to come: the in-link's front and tokens, the out-link's tail
+            S.omask[q] &= ~(1 << ii);
+            { int f = xfer_front_q(W, S, ii, npos); if (f != 255) S.omask[f] |= 1 << ii; }
+            S.ogood[q] = xfer_accepts(W, S, q) ? 1 : 0;
         }
-        WARP_SYNC();
-    }
-    NLAP(g_node_prof, 4)
-    WARP_FOR(lane) if (lane == 0) {
         // flush trip-end-waiting fronts (traffi.cpp:432-441)
         for (int ii = 0; ii < nin; ii++) {
             int lanes = S.hc[ii];  // hcount = head positions up to the last flagged one: positions beyond it cannot be waiting
@@ -608,18 +551,65 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
                 if (S.popped[ii] >= S.hc[ii]) break;
                 int fp = S.pos_off[ii] + S.popped[ii];
                 if (fp >= npos || !(S.p_flag[fp] & VF_WAIT_END)) break;
-                xfer_end_trip(W, S, fp, t);
+                xfer_end_trip(W, S, fp);
             }
         }
-        NR(W, n).fc_rem = S.fc_rem;
+        NR(W, n).fc_rem = fc_rem;
+        if (publish) {
+            // A waiting node needs one thing of this node: how many platoons left each in-link.  That is final here, so the
+            // completion flag goes out before the apply phase (nothing it writes is read by another node of this launch).
+            for (int ii = 0; ii < nin; ii++) LC(W, S.il[ii]).pop_k2 = S.popped[ii];
+#ifndef UX_EMU
+            __threadfence();
+#endif
+            *((volatile int *)&NDONE(W, n)) = t + 1;
+        }
     }
     WARP_SYNC();
-    // ---- C: write the per-link accumulators back
+    NLAP(g_node_prof, 4)
+    // ---- C: apply.  One lane per head position the loop touched: the per-platoon fields, the ring slot on the new link, the
+    //          link-exit travel-time event (of two events of one in-link with the same entry step the later one stays, as in the
+    //          serial order); then the per-link accumulators.
     WARP_FOR(lane) {
+        for (int p = lane; p < npos; p += 32) {
+            const int act = S.p_act[p];
+            if (!act) continue;
+            const int ii = S.p_in[p], il = S.il[ii], vid = S.p_vid[p], ord = S.p_ord[p], es = S.p_es[p];
+            bool last = true;
+            { int pe = S.pos_off[ii + 1] < npos ? S.pos_off[ii + 1] : npos; for (int p2 = S.pos_off[ii]; p2 < pe; p2++) if (S.p_act[p2] && S.p_es[p2] == es && S.p_ord[p2] > ord) { last = false; break; } }
+            const double now = (double)t * W.dt;
+            if (last) { W.ev_ord[TLI(W, es, il)] = ord; W.ev_tt[TLI(W, es, il)] = (act == 2 ? ((double)t + 1.0) * W.dt : now) - S.p_atl[p]; }
+            W.v_atl[vid] = now;
+            W.v_dist[vid] = S.p_dist[p];
+            W.v_flags[vid] = 0;
+            if (act == 2) {  // Vehicle::end_trip (traffi.cpp:886-927)
+                W.v_link[vid] = -1;
+                if (S.p_flag[p] & VF_ABORT) { W.v_state[vid] = UX_VS_ABORT; W.v_arr_ts[vid] = -1; W.v_tt[vid] = -1.0; }
+                else { W.v_state[vid] = UX_VS_END; W.v_arr_ts[vid] = t; W.v_tt[vid] = now - (double)S.p_dts[p] * W.dt; }
+                if (W.log_mode) { W.v_end_ts[vid] = t; W.v_end_kind[vid] = 2; }
+            } else {
+                const int q = S.p_q[p], ol = S.ol[q], slot = S.p_oslot[p];
+                const double x_next = S.p_xn[p];
+                if (W.no_cyclic) { int sn = W.l_start[ol]; W.v_visited[(size_t)vid * W.vis_words + (sn >> 5)] |= 1u << (sn & 31); }
+                W.v_trav[vid] = S.p_trav[p] + 1; record_traversal(W, vid, S.p_trav[p], ol, t);
+                W.v_link[vid] = ol;
+                if (slot >= 0) {
+                    long long o = S.o_roff[q];
+                    W.X[(size_t)cur * C + o + slot] = x_next;
+                    W.X[(size_t)(cur ^ 1) * C + o + slot] = S.p_xold[p];
+                    W.V[o + slot] = S.p_v[p] + x_next / W.dt;
+                    W.VID[o + slot] = vid;
+                    W.LANE[o + slot] = S.p_olane[p];
+                }
+                W.v_entry_x[vid] = x_next;
+                W.v_mr[vid] = 0.0;
+            }
+        }
         for (int ii = lane; ii < nin; ii += 32) {
             int il = S.il[ii];
             LR(W, il).cap_out_rem = S.co_rem[ii]; W.cum_dep[TLI(W, t, il)] = S.cumdep[ii];
-            LC(W, il).pop_k2 = S.popped[ii]; LC(W, il).ev_cnt = S.evc[ii]; LC(W, il).trips = S.trips[ii];
+            if (!publish) LC(W, il).pop_k2 = S.popped[ii];
+            LC(W, il).ev_cnt = S.evc[ii]; LC(W, il).trips = S.trips[ii];
         }
         for (int q = lane; q < nol; q += 32) {
             int ol = S.ol[q];
@@ -628,6 +618,7 @@ UX_DEV void xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
     }
     NLAP(g_node_prof, 5)
     NLAP_TOTAL(g_node_prof, 6)
+    return publish;
 }
 
 // K0: the per-link and per-node scalar bookkeeping of a timestep, one THREAD per (link | node, replica):
@@ -731,18 +722,17 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
     WARP_BEGIN
     __shared__ NodeSmem<MC, MD> sm_all[XFER_WARPS];
     __shared__ double tt_all[XFER_WARPS][MD];
-    __shared__ int rel_all[XFER_WARPS];
     int warp = (int)((blockIdx.y * blockDim.x + threadIdx.x) >> 5), wib = (int)((threadIdx.x >> 5) % XFER_WARPS);
     if (warp >= W.N) return;
     int n = W.lvl_nodes[warp], t = *W.t_base + step_off;
     int lvl_raw = W.n_levels > 1 ? W.lvl_level[warp] : 0, lvl = lvl_raw & 0xffff;  // bit 16: some node waits for this one
-    pre_node(W, sm_all[wib].pre, tt_all[wib], &rel_all[wib], n, t, (int)(threadIdx.x & 31));
+    pre_node(W, sm_all[wib].pre, tt_all[wib], n, t, (int)(threadIdx.x & 31));
 #ifndef UX_EMU
     __threadfence_block();
 #endif
     XferSmem<MC, MD> &S = sm_all[wib].xf;
-    xfer_node(W, S, n, t, lvl > 0);
-    if ((lvl_raw >> 16) && NS(W, n).node_act == t) {  // publish completion only where somebody may be waiting (waiters skip idle nodes): the fence is not free
+    const bool publish = (lvl_raw >> 16) != 0;  // publish completion only where somebody may be waiting: the fence is not free
+    if (!xfer_node(W, S, n, t, lvl > 0, publish) && publish && NS(W, n).node_act == t) {  // (waiters skip nodes without flagged head positions)
         WARP_SYNC();
         WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)&NDONE(W, n)) = t + 1; }
     }
@@ -1170,14 +1160,13 @@ __global__ void __launch_bounds__(32 * NRL_WARPS, NRL_MINB) k_node_h(const DevWo
     if constexpr (HEAVY) {
         __shared__ NodeSmem<MC, MD> sm_all[NRL_WARPS];
         __shared__ double tt_all[NRL_WARPS][MD];
-        __shared__ int rel_all[NRL_WARPS];
         WARP_BEGIN
-        pre_node(W, sm_all[wib].pre, tt_all[wib], &rel_all[wib], n, t, ln);
+        pre_node(W, sm_all[wib].pre, tt_all[wib], n, t, ln);
 #ifndef UX_EMU
         __threadfence_block();
 #endif
-        xfer_node(W, sm_all[wib].xf, n, t, (lvl_raw & 0xffff) > 0);
-        if ((lvl_raw & 0x10000) && NS(W, n).node_act == t) {
+        const bool publish = (lvl_raw & 0x10000) != 0;
+        if (!xfer_node(W, sm_all[wib].xf, n, t, (lvl_raw & 0xffff) > 0, publish) && publish && NS(W, n).node_act == t) {
             WARP_SYNC();
             WARP_FOR(lane) if (lane == 0) { __threadfence(); *((volatile int *)&NDONE(W, n)) = t + 1; }
         }

@@ -39,7 +39,7 @@ struct DevWorld {
     const long long *l_roff;
     const double *l_tt0;  // length / vmax at initialize_adj_matrix: what traveltime_actual holds before the first exit event
     const double *l_length, *l_vmax, *l_dpl_dn, *l_udt, *l_cap_out, *l_cap_in, *l_mp, *l_penalty, *l_toll;
-    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *lvl_off, *lvl_nodes, *lvl_level, *dep_off, *dep_list;
+    const int *n_out_off, *n_out, *n_in_off, *n_in, *n_sig_off, *n_lanes, *n_out_lanes, *n_out_woff, *lvl_off, *lvl_nodes, *lvl_level, *dep_off, *dep_list;
     int n_levels;
     const double *n_sig, *n_fc;
     const int *v_orig, *v_dest, *v_depart_ts, *gen_off, *gen_list, *gen_ts, *dest_row, *row_dest;

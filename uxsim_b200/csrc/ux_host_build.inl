@@ -478,7 +478,7 @@ static int upload(ux_world *w) {
         base.eout_off = dupload(w, eout_off); base.eout_to = dupload(w, eout_to); base.e_inpos = dupload(w, e_inpos); base.e_outpos = dupload(w, e_outpos);
     }
     // ---- nodes
-    std::vector<int> out_off(N + 1, 0), in_off(N + 1, 0), out, in, sig_off(N + 1, 0), n_lanes(N), n_out_lanes(N);
+    std::vector<int> out_off(N + 1, 0), in_off(N + 1, 0), out, in, sig_off(N + 1, 0), n_lanes(N), n_out_lanes(N), out_woff;
     std::vector<double> n_sig, n_fc(N);
     for (int i = 0; i < N; i++) {
         const HNode &n = w->nodes[i];
@@ -486,11 +486,11 @@ static int upload(ux_world *w) {
         out.insert(out.end(), n.out.begin(), n.out.end()); in.insert(in.end(), n.in.begin(), n.in.end());
         sig_off[i + 1] = sig_off[i] + (int)n.sig.size(); n_sig.insert(n_sig.end(), n.sig.begin(), n.sig.end());
         n_fc[i] = n.fc; n_lanes[i] = n.lanes;
-        int tl = 0; for (int l : n.out) tl += w->links[l].lanes; n_out_lanes[i] = tl;
+        int tl = 0; for (int l : n.out) { out_woff.push_back(tl); tl += w->links[l].lanes; } n_out_lanes[i] = tl;  // out_woff: lanes of the node's earlier out-links
     }
     base.n_out_off = dupload(w, out_off); base.n_out = dupload(w, out); base.n_in_off = dupload(w, in_off); base.n_in = dupload(w, in);
     w->d_n_sig_off = dupload(w, sig_off); w->d_n_sig = dupload(w, n_sig);
-    base.n_sig_off = w->d_n_sig_off; base.n_sig = w->d_n_sig; base.n_fc = dupload(w, n_fc); base.n_lanes = dupload(w, n_lanes); base.n_out_lanes = dupload(w, n_out_lanes);
+    base.n_sig_off = w->d_n_sig_off; base.n_sig = w->d_n_sig; base.n_fc = dupload(w, n_fc); base.n_lanes = dupload(w, n_lanes); base.n_out_lanes = dupload(w, n_out_lanes); base.n_out_woff = dupload(w, out_woff);
     // ---- vehicles
     std::vector<int> v_orig(P), v_dest(P), v_ts(P), gen_off(N + 1, 0), gen_list(P);
     w->dest_row.assign(N, -1); w->row_dest.clear();

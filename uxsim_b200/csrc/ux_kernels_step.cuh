@@ -95,35 +95,39 @@ UX_DEV void pre_node(const DevWorld &W, PreSmem<MC, MD> &G, double *tt_s, int n,
         for (int i = ln; i < amax; i += 32) {  // Node::generate, the draw (traffi.cpp:112-128)
             int vid = W.gen_list[g0 + gh + i], e = 0, ch = -1, q = 255, trav = 0;
             if (W.gen_ts[g0 + gh + i] <= t - 1) {
+                trav = W.v_trav[vid];
                 ch = route_choice(W, vid, n, t, (unsigned)n, UX_RNG_GENERATE, (unsigned)i, &e);
-                if (ch >= 0) { q = 0; while (q < nout && W.n_out[o0 + q] != ch) q++; trav = W.v_trav[vid]; }
+                if (ch >= 0) { q = 0; while (q < nout && W.n_out[o0 + q] != ch) q++; }
             } else vid = -1;
             G.g_vid[i] = vid; G.choice[i] = ch; G.g_err[i] = e; G.g_q[i] = (unsigned char)q; G.g_trav[i] = trav;
         }
         for (int q = (ln - rB) & 31; q < nout; q += 32) {  // out-links: Link::update of the inflow side (traffi.cpp:542-565), tail state, window
-            int ol = W.n_out[o0 + q];
+            int ol = W.n_out[o0 + q], woff = W.n_out_woff[o0 + q];
             int hd = LQ(W, ol).head[cur], tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
             long long o = W.l_roff[ol];
-            size_t row = TLI(W, t, ol);
-            double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], ca_;
-            if (!split) {
-                size_t prev = TLI(W, t - 1, ol);
-                ca_ = t != 0 ? W.cum_arr[prev] : W.cum_arr[row];
-                double cin = W.l_cap_in[ol];
-                if (fresh) W.tt_inst[row] = tt_s[q];
-                else if (t > 0) W.tt_inst[row] = W.tt_inst[prev];
-                if (cin < 10e9) { if (ci_ < W.dn * lanes) ci_ += cin * W.dt; } else ci_ = 10e9;
-            } else {
-                ca_ = W.cum_arr[row];
-                if (fresh) W.tt_inst[row] = tt_s[q];
-            }
-            int sz = tl - hd, wn = sz < lanes ? sz : lanes, woff = 0;
-            for (int k = 0; k < q; k++) woff += W.l_lanes[W.n_out[o0 + k]];
+            size_t row = TLI(W, t, ol), prev = TLI(W, t - 1, ol);
+            // loads first, in two rounds (the record, then the ring entries it points at); stores afterwards
+            double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], vm_ = W.l_vmax[ol], cin = W.l_cap_in[ol];
+            double ca_ = (!split && t != 0) ? W.cum_arr[prev] : W.cum_arr[row];
+            double ttp_ = (!split && !fresh && t > 0) ? W.tt_inst[prev] : 0.0;
+            int sz = tl - hd, wn = sz < lanes ? sz : lanes;
             int ll_ = sz > 0 ? W.LANE[o + ring_slot(tl - 1, 0, cap)] : -1;
-            for (int k = 0; k < wn && woff + k < MC; k++) G.w_x[woff + k] = W.X[(size_t)cur * C + o + ring_slot(hd, sz - wn + k, cap)];
+            if (fresh) W.tt_inst[row] = tt_s[q];
+            else if (!split && t > 0) W.tt_inst[row] = ttp_;
+            if (!split) { if (cin < 10e9) { if (ci_ < W.dn * lanes) ci_ += cin * W.dt; } else ci_ = 10e9; }
             G.o_hd[q] = hd; G.o_tail[q] = tl; G.o_tail0[q] = tl; G.o_lanes[q] = lanes; G.o_cap[q] = cap; G.o_roff[q] = o;
             G.o_ci[q] = ci_; G.o_dpl[q] = dpl_; G.o_vmax[q] = vm_; G.o_cumarr[q] = ca_; G.o_lastlane[q] = ll_;
             G.o_win_off[q] = woff; G.o_win_n[q] = wn; G.o_win_f[q] = 0;
+        }
+        {   // the window of every out-link (its last `lanes` platoons), one lane per entry
+            int wtot = W.n_out_lanes[n]; if (wtot > MC) wtot = MC; if (amax == 0) wtot = 0;
+            for (int e = (ln - rD - 1) & 31; e < wtot; e += 32) {
+                int q = 0;
+                while (q + 1 < nout && W.n_out_woff[o0 + q + 1] <= e) q++;
+                int ol = W.n_out[o0 + q], k = e - W.n_out_woff[o0 + q];
+                int hd = LQ(W, ol).head[cur], sz = LQ(W, ol).tail - hd, lanes = W.l_lanes[ol], wn = sz < lanes ? sz : lanes;
+                if (k < wn) G.w_x[e] = W.X[(size_t)cur * C + W.l_roff[ol] + ring_slot(hd, sz - wn + k, W.l_rcap[ol])];
+            }
         }
         if (!split) {
             for (int k = (ln - rC) & 31; k < nin; k += 32) {  // in-links: the outflow side (departure curve, capacity_out tokens, pops of this step)
@@ -399,7 +403,12 @@ UX_DEV bool xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
         WARP_FOR(lane) {
             for (int q = lane; q < nol; q += 32) {
                 int ol = S.ol[q];
-                if (!(W.l_flags[ol] & LF_SEES_POPS) || LC(W, ol).hcount == 0) continue;  // nothing can leave that link in this step
+                if (!(W.l_flags[ol] & LF_SEES_POPS)) continue;
+                const int hc_ = LC(W, ol).hcount;
+                if (hc_ == 0) continue;  // nothing can leave that link in this step
+                // ... and even if all flagged platoons leave, a link that keeps `lanes` platoons looks the same from its tail: the
+                // acceptance test, the carry-over bound and the lane rule read the platoon `lanes` positions from the tail
+                if (LQ(W, ol).tail - LQ(W, ol).head[cur] - hc_ >= W.l_lanes[ol]) continue;
                 volatile int *done = &NDONE(W, W.l_end[ol]);
 #ifdef UX_EMU
                 if (*done < t + 1) dev_error(W, DERR_DEP_TIMEOUT, n);
@@ -425,8 +434,9 @@ UX_DEV bool xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             // pops of this step by the link's end node (a lower level of this launch).  Only a node with flagged head positions on
             // this link can pop from it -- otherwise the end node may not even have reset last step's value yet (small worlds reset
             // it inside this launch, in that node's own pre_node), so the count is taken as 0 without reading it.
-            int pk_ = ((fl_ & LF_SEES_POPS) && LC(W, ol).hcount > 0) ? ld_cg(&LC(W, ol).pop_k2) : 0;
             int tl = LQ(W, ol).tail, lanes = W.l_lanes[ol], cap = W.l_rcap[ol];
+            int pk_ = 0;
+            if (fl_ & LF_SEES_POPS) { int hc_ = LC(W, ol).hcount; if (hc_ > 0 && tl - hd - hc_ < lanes) pk_ = ld_cg(&LC(W, ol).pop_k2); }  // (same test as the wait above)
             long long o = W.l_roff[ol];
             double ci_ = LR(W, ol).cap_in_rem, dpl_ = W.l_dpl_dn[ol], len_ = W.l_length[ol], vm_ = W.l_vmax[ol], ca_ = W.cum_arr[TLI(W, t, ol)];
             if (fl_ & LF_SEES_POPS) hd += pk_;
@@ -496,19 +506,26 @@ UX_DEV bool xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             const int q = S.expd[s];
             int m = S.omask[q];
             if (!m || !S.ogood[q]) continue;
-            short mv[MD]; double mp[MD]; int nm = 0;
-            while (m) {  // eligible fronts in ascending vehicle id
-                int ii = 0; while (!((m >> ii) & 1)) ii++;
-                m &= m - 1;
-                int vid = S.p_vid[S.pos_off[ii] + S.popped[ii]], at = nm++;
-                while (at > 0 && S.p_vid[S.pos_off[mv[at - 1]] + S.popped[mv[at - 1]]] > vid) { mv[at] = mv[at - 1]; at--; }
-                mv[at] = (short)ii;
+            int ii;
+            if (!(m & (m - 1))) {  // one in-link offers a platoon (the usual case): no lottery, but its draw is consumed (traffi.cpp:332-340)
+                ii = 0; while (!((m >> ii) & 1)) ii++;
+                n_picks++;
+            } else {
+                short mv[MD]; double mp[MD]; int nm = 0;
+                while (m) {  // eligible fronts in ascending vehicle id
+                    int i2 = 0; while (!((m >> i2) & 1)) i2++;
+                    m &= m - 1;
+                    int vid = S.p_vid[S.pos_off[i2] + S.popped[i2]], at = nm++;
+                    while (at > 0 && S.p_vid[S.pos_off[mv[at - 1]] + S.popped[mv[at - 1]]] > vid) { mv[at] = mv[at - 1]; at--; }
+                    mv[at] = (short)i2;
+                }
+                for (int i = 0; i < nm; i++) mp[i] = S.mp[mv[i]];
+                int pick;
+                if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
+                else pick = weighted_pick(mp, nm, S.u_merge[n_picks++]);
+                ii = mv[pick];
             }
-            for (int i = 0; i < nm; i++) mp[i] = S.mp[mv[i]];
-            int pick;
-            if (W.hard_det) { pick = 0; for (int i = 1; i < nm; i++) if (mp[i] > mp[pick]) pick = i; }
-            else pick = nm == 1 ? (n_picks++, 0) : weighted_pick(mp, nm, S.u_merge[n_picks++]);
-            const int ii = mv[pick], p = S.pos_off[ii] + S.popped[ii];
+            const int p = S.pos_off[ii] + S.popped[ii];
             const int lanes_ol = S.o_lanes[q], sz = S.o_tail[q] - S.o_hd[q], w0 = S.o_win_off[q];
             S.co_rem[ii] -= W.dn; S.o_ci[q] -= W.dn;
             if (fc >= 0.0) fc_rem -= W.dn;
@@ -528,7 +545,8 @@ UX_DEV bool xfer_node(const DevWorld &W, XferSmem<MC, MD> &S, int n, int t, bool
             S.p_xn[p] = x_next;
             if (sz >= S.o_cap[q]) { dev_error(W, DERR_RING_FULL, S.ol[q]); S.p_oslot[p] = -1; }
             else {  // push (lane rule traffi.cpp:385-390)
-                int lane_new = sz > 0 ? (S.o_lastlane[q] + 1) % lanes_ol : 0;
+                int lane_new = sz > 0 ? S.o_lastlane[q] + 1 : 0;  // (lane + 1) % lanes: lane labels are < lanes
+                if (lane_new >= lanes_ol) lane_new = 0;
                 S.p_oslot[p] = ring_slot(S.o_tail[q], 0, S.o_cap[q]); S.p_olane[p] = (unsigned char)lane_new;
                 S.o_tail[q] += 1; S.o_lastlane[q] = lane_new;
                 if (S.o_win_n[q] < lanes_ol) { int e = w0 + S.o_win_n[q]; S.w_x[e] = x_next; S.w_xold[e] = S.p_xold[p]; S.o_win_n[q] += 1; }
@@ -924,7 +942,10 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                 if ((lvl_raw & 0xffff) > 0) {
                     for (int q = 0; q < nol; q++) {  // per requested out-link: its end node can pop only flagged head positions (hcount > 0)
                         const int ol = o_id[q];
-                        if (!(W.l_flags[ol] & LF_SEES_POPS) || (&LC(W, ol) + ln)->hcount == 0) continue;
+                        if (!(W.l_flags[ol] & LF_SEES_POPS)) continue;
+                        const int hc_ = (&LC(W, ol) + ln)->hcount;
+                        if (hc_ == 0) continue;
+                        { const LinkQ *lq = &LQ(W, ol) + ln; if (lq->tail - lq->head[cur] - hc_ >= W.l_lanes[ol]) continue; }  // keeps `lanes` platoons whatever leaves: looks the same from its tail
                         volatile int *done = &NDONE(W, W.l_end[ol]) + ln;
 #ifdef UX_EMU
                         if (*done < t + 1) dev_error(Wr, DERR_DEP_TIMEOUT, n);
@@ -945,7 +966,8 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     for (int u = 0; u < 4; u++) {
                         int ol = o_id[b + u < nol ? b + u : b];
                         q_[u] = *reinterpret_cast<const int4 *>(&LQ(W, ol) + ln); ci_[u] = (&LR(W, ol) + ln)->cap_in_rem; ca_[u] = W.cum_arr[TLI(W, t, ol) + ln];
-                        pk_[u] = ((W.l_flags[ol] & LF_SEES_POPS) && (&LC(W, ol) + ln)->hcount > 0) ? ld_cg(&(&LC(W, ol) + ln)->pop_k2) : 0;
+                        pk_[u] = 0;
+                        if (W.l_flags[ol] & LF_SEES_POPS) { const int hc_ = (&LC(W, ol) + ln)->hcount; if (hc_ > 0 && q_[u].z - (cur ? q_[u].y : q_[u].x) - hc_ < W.l_lanes[ol]) pk_[u] = ld_cg(&(&LC(W, ol) + ln)->pop_k2); }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) if (b + u < nol) {

@@ -39,6 +39,20 @@ def stage() -> bool:
         return drop
 
     shutil.copytree(pkg, out, ignore=ignore)
+    # the reference's own verification tests and the three small CSVs they read (tests/test_reference_suite.py runs them, unmodified,
+    # against this backend on the GPU box: the `--cuda` counterpart of the reference's `pytest --cpp`)
+    tdir = os.path.join(DST, "tests")
+    if os.path.isdir(tdir):
+        shutil.rmtree(tdir)
+    os.makedirs(tdir)
+    for n in sorted(os.listdir(os.path.join(SRC, "tests"))):
+        if n == "conftest.py" or (n.startswith("test_verification_") and n.endswith(".py")):
+            shutil.copy2(os.path.join(SRC, "tests", n), os.path.join(tdir, n))
+    ddir = os.path.join(DST, "dat")
+    os.makedirs(ddir, exist_ok=True)
+    for n in ("siouxfalls_nodes.csv", "siouxfalls_links.csv", "siouxfalls_demand.csv"):
+        if os.path.exists(os.path.join(SRC, "dat", n)):
+            shutil.copy2(os.path.join(SRC, "dat", n), os.path.join(ddir, n))
     with open(os.path.join(DST, "STAGED_FROM"), "w") as f:
         f.write(f"{SRC} (uxsim package tree copied unmodified by baseline/stage_reference.py; pip install fails: nanobind absent)\n")
     return True

@@ -249,6 +249,8 @@ enum {
     UX_A_SIGNAL_LOG = 30,       /* i32 [N][T]  Node.signal_log                            */
     UX_A_NODE_SIGNAL_PHASE = 31,/* i32 [N] */
     UX_A_NODE_SIGNAL_T = 32,    /* f64 [N] */
+    UX_A_NODE_FLOW_CAPACITY = 33, /* f64 [N]  Node.flow_capacity (-1: none), after adjust_node_capacity (bindings.cpp: Node rw fields) */
+    UX_A_NODE_NUM_LANES = 34,   /* i32 [N]  Node.number_of_lanes */
     /* per link, current state */
     UX_A_LINK_NUM_VEHICLES = 40,/* i32 [L]  len(link.vehicles)                            */
     UX_A_LINK_CAPACITY_IN_REMAIN = 41,  /* f64 [L] */

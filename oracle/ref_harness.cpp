@@ -291,7 +291,8 @@ UX_API int64_t uxr_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
     case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
-    case UX_A_NODE_SIGNAL_T: n = N; break;
+    case UX_A_NODE_SIGNAL_T: case UX_A_NODE_FLOW_CAPACITY: n = N; break;
+    case UX_A_NODE_NUM_LANES: n = N; dt = UX_DT_I32; break;
     case UX_A_LINK_NUM_VEHICLES: n = L; dt = UX_DT_I32; break;
     case UX_A_LINK_CAPACITY_IN_REMAIN: case UX_A_LINK_CAPACITY_OUT_REMAIN: case UX_A_LINK_STAT_COUNT: case UX_A_LINK_TRIPS_COMPLETED: case UX_A_LINK_AVE_V_SUM: n = L; break;
     case UX_A_ROUTE_PREF: n = N * L; break;
@@ -347,6 +348,8 @@ UX_API int64_t uxr_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_SIGNAL_LOG: for (int64_t k = 0; k < N; k++) for (int64_t t = 0; t < T; t++) ii[k * T + t] = t < (int64_t)W->nodes[k]->signal_log.size() ? W->nodes[k]->signal_log[t] : 0; break;
     case UX_A_NODE_SIGNAL_PHASE: for (int64_t k = 0; k < N; k++) ii[k] = W->nodes[k]->signal_phase; break;
     case UX_A_NODE_SIGNAL_T: for (int64_t k = 0; k < N; k++) d[k] = W->nodes[k]->signal_t; break;
+    case UX_A_NODE_FLOW_CAPACITY: for (int64_t k = 0; k < N; k++) d[k] = W->nodes[k]->flow_capacity; break;
+    case UX_A_NODE_NUM_LANES: for (int64_t k = 0; k < N; k++) ii[k] = W->nodes[k]->number_of_lanes; break;
     case UX_A_LINK_NUM_VEHICLES: for (int64_t l = 0; l < L; l++) ii[l] = (int)W->links[l]->vehicles.size(); break;
     case UX_A_LINK_CAPACITY_IN_REMAIN: for (int64_t l = 0; l < L; l++) d[l] = W->links[l]->capacity_in_remain; break;
     case UX_A_LINK_CAPACITY_OUT_REMAIN: for (int64_t l = 0; l < L; l++) d[l] = W->links[l]->capacity_out_remain; break;

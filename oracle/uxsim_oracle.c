@@ -1020,7 +1020,8 @@ UX_API int64_t uxo_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
     case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
-    case UX_A_NODE_SIGNAL_T: n = N; break;
+    case UX_A_NODE_SIGNAL_T: case UX_A_NODE_FLOW_CAPACITY: n = N; break;
+    case UX_A_NODE_NUM_LANES: n = N; dt = UX_DT_I32; break;
     case UX_A_LINK_NUM_VEHICLES: n = L; dt = UX_DT_I32; break;
     case UX_A_LINK_CAPACITY_IN_REMAIN: case UX_A_LINK_CAPACITY_OUT_REMAIN: case UX_A_LINK_STAT_COUNT: case UX_A_LINK_TRIPS_COMPLETED: case UX_A_LINK_AVE_V_SUM: n = L; break;
     case UX_A_ROUTE_PREF: n = N * L; break;
@@ -1081,6 +1082,8 @@ UX_API int64_t uxo_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_SIGNAL_LOG: for (int64_t k = 0; k < N; k++) for (int64_t t = 0; t < T; t++) ii[k * T + t] = t < w->nodes[k].n_sig_log ? w->nodes[k].sig_log[t] : 0; break;
     case UX_A_NODE_SIGNAL_PHASE: for (int64_t k = 0; k < N; k++) ii[k] = w->nodes[k].sig_phase; break;
     case UX_A_NODE_SIGNAL_T: for (int64_t k = 0; k < N; k++) d[k] = w->nodes[k].sig_t; break;
+    case UX_A_NODE_FLOW_CAPACITY: for (int64_t k = 0; k < N; k++) d[k] = w->nodes[k].fc; break;
+    case UX_A_NODE_NUM_LANES: for (int64_t k = 0; k < N; k++) ii[k] = w->nodes[k].lanes; break;
     case UX_A_LINK_NUM_VEHICLES: for (int64_t l = 0; l < L; l++) ii[l] = q_size(&w->links[l]); break;
     case UX_A_LINK_CAPACITY_IN_REMAIN: for (int64_t l = 0; l < L; l++) d[l] = w->links[l].cap_in_remain; break;
     case UX_A_LINK_CAPACITY_OUT_REMAIN: for (int64_t l = 0; l < L; l++) d[l] = w->links[l].cap_out_remain; break;

@@ -160,6 +160,12 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
     if (what >= UX_A_OD_ORIG && what <= UX_A_LINKC_STATS) return get_summary_array(w, what, replica, dst, capacity);
     if (what >= UX_A_DTA_OD_ORIG && what <= UX_A_DTA_RA_ENTRY_T) return get_dta_array(w, what, replica, dst, capacity);
     if (what >= UX_A_EDIE_OFFSETS && what <= UX_A_EDIE_DN) return get_edie_array(w, what, replica, dst, capacity);
+    if (what == UX_A_NODE_FLOW_CAPACITY || what == UX_A_NODE_NUM_LANES) {  // static after initialize_adj_matrix: answered from the host copy
+        int64_t N = (int64_t)w->nodes.size();
+        if (capacity < N) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)N);
+        for (int64_t i = 0; i < N; i++) { if (what == UX_A_NODE_FLOW_CAPACITY) ((double *)dst)[i] = w->nodes[i].fc; else ((int *)dst)[i] = w->nodes[i].lanes; }
+        return N;
+    }
     if (what == UX_A_VEH_ORIG || what == UX_A_VEH_DEST || what == UX_A_VEH_DEPART_TS) {  // static: answered from the host copy (no upload forced)
         int64_t P = (int64_t)w->vehs.size();
         if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);

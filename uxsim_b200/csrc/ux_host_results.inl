@@ -204,7 +204,8 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
     case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
-    case UX_A_NODE_SIGNAL_T: n = N; break;
+    case UX_A_NODE_SIGNAL_T: case UX_A_NODE_FLOW_CAPACITY: n = N; break;
+    case UX_A_NODE_NUM_LANES: n = N; dt = UX_DT_I32; break;
     case UX_A_LINK_NUM_VEHICLES: n = L; dt = UX_DT_I32; break;
     case UX_A_LINK_CAPACITY_IN_REMAIN: case UX_A_LINK_CAPACITY_OUT_REMAIN: case UX_A_LINK_STAT_COUNT: case UX_A_LINK_TRIPS_COMPLETED: n = L; break;
     case UX_A_ROUTE_PREF: n = N * L; break;

@@ -22,6 +22,7 @@ numbers from the same attributes.
 from __future__ import annotations
 
 import csv
+import os
 import math
 import string
 import time
@@ -105,6 +106,41 @@ class CudaNode:
     @property
     def signal_log(self):
         return list(self.W._series("signal_log")[self.id][: self.W.T])
+
+    def override_signal(self, signal, groups=None, signal_offset=0, reset=False, signal_offset_old=None):
+        """uxsim_cpp_wrapper.py:126-170 (uxsim.py:143-190): a new signal plan for this node and, with `groups`, the phases in
+        which each in-link has green.  `groups[i]` lists the links (names or objects) that are green in phase i."""
+        self.signal = signal
+        self.signal_offset = signal_offset
+        if reset:
+            self.W._E.set_node_signal(self.id, None, phase=0, signal_t=0.0)
+        if signal_offset_old is not None:
+            self.signal_offset = self.cycle_length - signal_offset_old
+        self.signal_offset = float(self.signal_offset)  # (like the reference's C++ mode, the offset only documents the plan once the node exists)
+        if groups is None:
+            return None
+        if len(groups) != len(signal):
+            raise ValueError("The length of `group` must match the length of `signal`.")
+        phase_info = ddict(list)
+        for i, group in enumerate(groups):
+            for link in group:
+                l = self.W.get_link(link)
+                if l not in self.inlinks.values():
+                    raise ValueError(f"Link {l.name} is not an incoming link of node {self.name}.")
+                phase_info[l].append(i)
+        for l, phases in phase_info.items():
+            l.signal_group = phases
+            self.W._E.set_link_signal_group(l.id, phases)
+
+    def adjust_node_capacity(self):
+        """uxsim_cpp_wrapper.py:172-181: the engine derives the capacity of nodes without one from the connected links when the
+        network is frozen (ux_initialize_adj_matrix, traffi.cpp:212-224); this reads the result back."""
+        fc = float(self.W._E.get_array(C.A_NODE_FLOW_CAPACITY)[self.id])
+        nl = int(self.W._E.get_array(C.A_NODE_NUM_LANES)[self.id])
+        if (nl if nl > 0 else None) != self.number_of_lanes:
+            self.flag_lanes_automatically_determined = True
+        self.flow_capacity = fc if fc >= 0.0 else None
+        self.number_of_lanes = nl if nl > 0 else None
 
 
 class CudaLink:
@@ -275,6 +311,27 @@ class CudaLink:
         tt = self.actual_travel_time(t)
         return self.length / tt if tt > 0 else self.u
 
+    # uxsim_cpp_wrapper.py:386-445: derived link measures
+    def num_vehicles_queue(self):
+        """Vehicles on the link slower than its free-flow speed (Link::count_vehicles_in_queue, traffi.cpp:589-597)."""
+        on_link = self.W._veh("link") == self.id
+        return int(np.count_nonzero(on_link & (self.W._veh("v") < self.u))) * self.W.DELTAN
+
+    def inflow_between(self, t0, t1):
+        return (self.arrival_count(t1) - self.arrival_count(t0)) / (t1 - t0) if t1 != t0 else 0
+
+    def average_travel_time_between(self, t0, t1):
+        t_list = [t for t in self.vehicles_enter_log.keys() if t0 <= t < t1]
+        if len(t_list) == 0:
+            return self.length / self.u
+        return np.average([self.actual_travel_time(t) for t in t_list])
+
+    def average_density(self, t):
+        return self.num_vehicles_t(t) / self.length
+
+    def average_flow(self, t):
+        return self.average_density(t) * self.average_speed(t)
+
     def change_free_flow_speed(self, new_value):
         if new_value >= 0:
             self.W._E.set_link_param(self.id, C.LINK_VMAX, float(new_value))
@@ -354,6 +411,14 @@ class CudaVehicle:
         self.specified_route = links
         self.links_prefer = list(links)
         self.W._E.set_vehicle_links(self.id, 0, [l.id for l in links])
+
+    def set_links_prefer(self, links):  # uxsim_cpp_wrapper.py:695-707
+        self.links_prefer = [self.W.get_link(l) for l in links]
+        self.W._E.set_vehicle_links(self.id, 1, [l.id for l in self.links_prefer])
+
+    def set_links_avoid(self, links):
+        self.links_avoid = [self.W.get_link(l) for l in links]
+        self.W._E.set_vehicle_links(self.id, 2, [l.id for l in self.links_avoid])
 
     def get_xy_coords(self, t=-1):
         l = self.link
@@ -487,6 +552,13 @@ class CudaRouteChoice:
     @property
     def route_pref(self):
         return self.W._E.get_array(C.A_ROUTE_PREF).reshape(len(self.W.NODES), len(self.W.LINKS))
+
+    @property
+    def dist_record(self):
+        """uxsim_cpp_wrapper.py:782-797, the fallback branch: the engine keeps the shortest-path table of the latest route update
+        only (a table per update would be N*N*8 B x updates of device memory), so every update step maps to the current one."""
+        dist = self.dist
+        return {ts: dist for ts in range(0, self.W.TSIZE, self.W.DELTAT_ROUTE)}
 
 
 class _VehicleRegistry(Sequence):
@@ -830,6 +902,9 @@ class CudaWorld:
             self.ADJ_MAT_LINKS[l.start_node.id, l.end_node.id] = l
             self.NODE_PAIR_LINKS[l.start_node.name, l.end_node.name] = l
         self._E.initialize_adj_matrix()
+        if self.adjust_node_capacity:  # sync the wrapper-side attributes (uxsim_cpp_wrapper.py:1101-1104)
+            for node in self.NODES:
+                node.adjust_node_capacity()
         self.ROUTECHOICE = CudaRouteChoice(self)
         self.analyzer = _make_analyzer(self)
         self.finalized = 1
@@ -1013,6 +1088,38 @@ class CudaWorld:
 
     def save(self, fname):
         raise NotImplementedError("save() is not supported in CUDA mode (as in C++ mode)")
+
+    def show_network(self, width=1, left_handed=1, figsize=(6, 6), network_font_size=10, node_size=6, show_id=True):
+        """uxsim_cpp_wrapper.py:1496-1527.  Drawing is outside the simulation loop (out of scope): the sketch below needs
+        matplotlib; like the reference's `catch_exceptions_and_warn`, a failure to draw is a warning, never an error."""
+        try:
+            import matplotlib.pyplot as plt
+
+            os.makedirs(f"out{self.name}", exist_ok=True)
+            fig = plt.figure(figsize=figsize)
+            ax = fig.add_subplot(111, aspect="equal")
+            side = 1.0 if left_handed else -1.0
+            for l in self.LINKS:  # a link is drawn bent towards its driving side, so that the two directions of a road do not overlap
+                a, b = l.start_node, l.end_node
+                ox, oy = side * (a.y - b.y) * 0.05, side * (b.x - a.x) * 0.05
+                px = [a.x, (2 * a.x + b.x) / 3 + ox, (a.x + 2 * b.x) / 3 + ox, b.x]
+                py = [a.y, (2 * a.y + b.y) / 3 + oy, (a.y + 2 * b.y) / 3 + oy, b.y]
+                ax.plot(px, py, "gray", lw=width, zorder=6, solid_capstyle="butt")
+                if network_font_size > 0:
+                    ax.text(px[1], py[1], f"{l.id}: {l.name}" if show_id else l.name, c="b", zorder=20, fontsize=network_font_size)
+            for n in self.NODES:
+                ax.plot(n.x, n.y, "o", c="gray", ms=node_size, zorder=10)
+                if network_font_size > 0:
+                    ax.text(n.x, n.y, f"{n.id}: {n.name}" if show_id else n.name, c="g", ha="center", va="top", zorder=20, fontsize=network_font_size)
+            fig.tight_layout()
+            if self.save_mode:
+                fig.savefig(f"out{self.name}/network.png")
+            if self.show_mode:
+                plt.show()
+            else:
+                plt.close("all")
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"show_network: {type(e).__name__}: {e}")
 
     def on_time(self, time_val):
         return self.T == int(time_val / self.DELTAT)

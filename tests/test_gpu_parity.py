@@ -65,6 +65,22 @@ def test_shortest_path_kernel_variants_bit_exact(name, mode, cuda_api, oracle_ap
     assert compare_engines(Eg, Eo) == []
 
 
+def test_staged_route_search_equals_unstaged(cuda_api, monkeypatch):
+    """k_sssp_wave<smem, warp, STAGE> (the in-edge tables of a replica staged in shared memory; off by default, measured slower)
+    against the default kernel on an ensemble large enough to take it (>= 16384 destination rows per launch)."""
+    sc = dict(STOCHASTIC)["chicago_dn30"]()
+    out = []
+    for stage in ("0", "1"):
+        monkeypatch.setenv("UXSIM_B200_SSSP_STAGE", stage)
+        E = sc.to_engine(cuda_api, vehicle_logging_timestep_interval=-1, num_replicas=56)
+        E.main_loop(until_t=1500.0)
+        out.append([(E.get_array(C.A_ROUTE_NEXT, r), E.get_array(C.A_ROUTE_DIST, r), E.get_array(C.A_CUM_ARRIVAL, r)) for r in (0, 31, 55)])
+        E.close()
+    for a, b in zip(*out):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 def test_chunked_execution_equals_single_run(cuda_api, oracle_api):
     """exec_simulation(until_t=...) in chunks (test_verification_straight_road.py:940-1113) == one run."""
     sc = S.grid(n=5, seed=9, tmax=3000, demand_t=1000)

@@ -640,9 +640,11 @@ static int launch_sssp(ux_world *w, cudaStream_t st) {  // returns the number of
                 k_sssp_wave<true, false><<<dim3(w->n_active, w->R), dim3(per_block), wbytes + (size_t)N * 8, st>>>(w->dworlds, 0);
             } else {
                 size_t ww = (((size_t)((N + 64 + 3) & ~3) * 2 + (size_t)((N + 31) / 32) * 4 + 15) / 8) + (size_t)N + 2;  // 8-byte words per warp
-                {   // ensembles: the in-edge CSR and the replica's edge costs staged in shared memory, as many destinations (warps) per
-                    // block as let two blocks share an SM.  UXSIM_B200_SSSP_STAGE=0 keeps the unstaged kernel (tests compare them).
-                    static const int stage_on = [] { const char *e = getenv("UXSIM_B200_SSSP_STAGE"); return e ? atoi(e) : 1; }();
+                {   // UXSIM_B200_SSSP_STAGE=1: the in-edge CSR and the replica's edge costs staged in shared memory, as many destinations
+                    // (warps) per block as let two blocks share an SM.  Measured SLOWER on the B200 (Chicago x1024: 15.3 vs 14.3 ms per update:
+                    // the kernel is bound by instruction issue, 74 % of the issue slots, not by the L1 hits the staging saves), so it is
+                    // off by default and kept for the tests that compare the variants.
+                    const int stage_on = [] { const char *e = getenv("UXSIM_B200_SSSP_STAGE"); return e ? atoi(e) : 0; }();  // (read per call: the tests switch it)
                     size_t sw = ((size_t)w->n_edges * 8 + (size_t)(N + 1) * 4 + (size_t)w->n_edges * 2 + 7) / 8;  // 8-byte words of the staged tables
                     long long room = (long long)110 * 1024 - (long long)sw * 8;
                     int wpb = room > 0 ? (int)std::min<long long>(SSSP_STAGE_MAX_WARPS, room / (long long)(ww * 8)) : 0;

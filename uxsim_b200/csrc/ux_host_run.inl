@@ -70,7 +70,7 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
                 KT_BEGIN(UX_K_SSSP) lc += launch_sssp(w, st); KT_END(UX_K_SSSP)
             }
             if (route || w->p.route_choice_update_gradual) {
-                KT_BEGIN(UX_K_DUO) UX_LAUNCH(k_duo, dim3((unsigned)((w->links.size() + 255) / 256), w->n_active, R), dim3(256), st, w->dworlds, w->p.route_choice_update_gradual ? 1 : 0); KT_END(UX_K_DUO) lc++;
+                KT_BEGIN(UX_K_DUO) UX_LAUNCH(k_duo, dim3((unsigned)((w->links.size() + 128 * DUO_PER_THREAD - 1) / (128 * DUO_PER_THREAD)), w->n_active, R), dim3(128), st, w->dworlds, w->p.route_choice_update_gradual ? 1 : 0); KT_END(UX_K_DUO) lc++;
                 KT_BEGIN(UX_K_MISC) UX_LAUNCH(k_duo_finish, dim3((w->n_active + 127) / 128, R), dim3(128), st, w->dworlds); KT_END(UX_K_MISC) lc++;
             }
         }

@@ -380,18 +380,32 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
 #endif
 }
 
-// grid = (link tiles, destination rows, replicas): no index arithmetic beyond one add, coalesced rows of `pref`
+// grid = (link tiles, destination rows, replicas): no index arithmetic beyond one add, coalesced rows of `pref`.
+// The kernel is a pure stream (16 B per element in and out): a thread takes DUO_PER_THREAD consecutive links with 16-byte loads and stores, so
+// that enough bytes are in flight per SM to approach the HBM rate.
+#define DUO_PER_THREAD 4
+UX_DEV double duo_one(double p, bool on_path, double wt) { return on_path ? (1.0 - wt) * p + wt : (1.0 - wt) * p; }
 __global__ void __launch_bounds__(256) k_duo(const DevWorld *worlds, int gradual_step) {
     const DevWorld &W = worlds[blockIdx.z];  // a handful of block-uniform field loads; nothing here aliases them
-    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x), r = (int)blockIdx.y, L = W.L;
-    if (l >= L || r >= W.D) return;
+    int l0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * DUO_PER_THREAD, r = (int)blockIdx.y, L = W.L;
+    if (l0 >= L || r >= W.D) return;
     double wt = gradual_step ? W.duo_w * (W.dt / W.duo_time) : W.duo_w;
     if (!W.pref_active[r]) wt = 1.0;
-    size_t idx = (size_t)r * (size_t)L + (size_t)l;
-    double p = W.pref[idx];
-    if (W.rnext[(size_t)r * W.N + W.l_start[l]] == W.l_end[l]) p = (1.0 - wt) * p + wt;
-    else p = (1.0 - wt) * p;
-    W.pref[idx] = p;
+    double *pp = W.pref + (size_t)r * (size_t)L + (size_t)l0;
+    const int *rn = W.rnext + (size_t)r * W.N;
+#ifndef UX_EMU
+    if (l0 + DUO_PER_THREAD <= L && (reinterpret_cast<unsigned long long>(pp) & 15ull) == 0ull) {
+        double2 a = *reinterpret_cast<const double2 *>(pp), b = *reinterpret_cast<const double2 *>(pp + 2);
+        int nx[4], en[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { nx[u] = rn[W.l_start[l0 + u]]; en[u] = W.l_end[l0 + u]; }
+        a.x = duo_one(a.x, nx[0] == en[0], wt); a.y = duo_one(a.y, nx[1] == en[1], wt);
+        b.x = duo_one(b.x, nx[2] == en[2], wt); b.y = duo_one(b.y, nx[3] == en[3], wt);
+        *reinterpret_cast<double2 *>(pp) = a; *reinterpret_cast<double2 *>(pp + 2) = b;
+        return;
+    }
+#endif
+    for (int u = 0; u < DUO_PER_THREAD && l0 + u < L; u++) pp[u] = duo_one(pp[u], rn[W.l_start[l0 + u]] == W.l_end[l0 + u], wt);
 }
 
 __global__ void k_duo_finish(const DevWorld *worlds) {

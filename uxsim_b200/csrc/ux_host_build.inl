@@ -281,7 +281,7 @@ static void compute_levels(ux_world *w, std::vector<int> &lflags, std::vector<in
             const int groups = (w->R + 31) / 32;
             for (int q = 0; q < N;) {
                 int e = q + 1;
-                while (e < N && e - q < NRL_WARPS && heavy[lvl_nodes[e]] == heavy[lvl_nodes[q]] && height[lvl_nodes[e]] == height[lvl_nodes[q]]) e++;
+                while (e < N && e - q < (heavy[lvl_nodes[q]] ? NRL_HEAVY_WARPS : NRL_WARPS) && heavy[lvl_nodes[e]] == heavy[lvl_nodes[q]] && height[lvl_nodes[e]] == height[lvl_nodes[q]]) e++;
                 if (heavy[lvl_nodes[q]]) for (int r = 0; r < w->R; r++) w->h_node_blks.push_back(make_int4(0, q, e - q, r));
                 else for (int g = 0; g < groups; g++) w->h_node_blks.push_back(make_int4(1, q, e - q, g));
                 q = e;

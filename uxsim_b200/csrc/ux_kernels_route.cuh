@@ -323,7 +323,37 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
                 Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)j;
                 if (hj < mymin) mymin = hj;
             }
-            if (near) {
+            if (WARP) {
+                // Warp per destination: the in-edges of the chunk's near nodes form ONE list (prefix sum of the in-degrees over the
+                // lanes) that the lanes share out edge by edge.  A wavefront here is ~10 nodes of in-degree ~4: one lane per NODE keeps a
+                // third of the warp busy for max-degree/4 serial batches, one lane per EDGE fills the warp for one or two passes -- the
+                // kernel is bound by instruction issue (74 % of the issue slots at 1024 replicas), so the instruction count is the time.
+                int q0 = 0, dg = 0;
+                if (near) { q0 = STAGE ? s_off[j] : __ldg(ein_off + j); dg = (STAGE ? s_off[j + 1] : __ldg(ein_off + j + 1)) - q0; }
+                int incl = dg;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31), pre = incl - dg;
+                for (int eb = 0; eb < total; eb += 32) {
+                    const bool in = eb + tid < total;
+                    const int e = in ? eb + tid : 0;
+                    int lo = 0;  // owner: the largest lane whose list offset is <= e (lanes without edges share their successor's offset and lose)
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) { int v = __shfl_sync(0xffffffffu, pre, lo + st); if (v <= e) lo += st; }
+                    const unsigned long long djo = __shfl_sync(0xffffffffu, dj, lo);
+                    const int q = __shfl_sync(0xffffffffu, q0, lo) + (e - __shfl_sync(0xffffffffu, pre, lo));
+                    if (in) {
+                        const int i = STAGE ? (int)s_from[q] : __ldg(ein_from + q);
+                        const unsigned long long nd = (unsigned long long)__double_as_longlong((STAGE ? s_cin[q] : __ldg(cin + q)) + __longlong_as_double((long long)djo));
+                        if (nd < WAVE_LD(i)) {
+                            atomicMin((SMEM_DIST ? du_s : du_g) + i, nd);
+                            unsigned int hn = (unsigned int)(nd >> 32), bit = 1u << (i & 31);
+                            if (hn < mymin) mymin = hn;
+                            if (!(atomicOr(&inq[i >> 5], bit) & bit)) Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)i;
+                        }
+                    }
+                }
+            } else if (near) {
                 double djd = __longlong_as_double((long long)dj);
                 int q0 = STAGE ? s_off[j] : __ldg(ein_off + j), q1 = STAGE ? s_off[j + 1] : __ldg(ein_off + j + 1);
                 for (int q = q0; q < q1; q += 4) {  // loads of four in-edges in flight together

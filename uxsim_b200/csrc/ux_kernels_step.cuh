@@ -772,7 +772,10 @@ __global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const
 // (level, id), a lane waits for the completion flag of exactly the lower-level nodes it depends on, in its own replica.
 // Random draws are the same counters as in k_node / the oracle, so the results are bit-identical.
 // ---------------------------------------------------------------------------------------------------
+#ifndef NRL_WARPS
 #define NRL_WARPS 4
+#endif
+#define NRL_HEAVY_WARPS (NRL_WARPS < 4 ? NRL_WARPS : 4)
 // 4 blocks per SM: more residency LOSES here (B200, x1024: 878 us at 3-4 blocks, 945 at 5, 1025 at 6, 1069 at 8) -- the threads' local
 // arrays (the gathered neighbourhood of the node) already fill the L1, and more threads push them out to the L2
 #ifndef NRL_MINB
@@ -1169,7 +1172,7 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
 template <int MC, int MD, bool HEAVY>
 __global__ void __launch_bounds__(32 * NRL_WARPS, NRL_MINB) k_node_h(const DevWorld *worlds, int step_off, int R, const int4 *blks) {
     const int4 b = blks[blockIdx.x];  // {form, first position in lvl_nodes, nodes in this block, replica (form 0) | lane group (form 1)}
-    LOAD_WORLD_N(W, worlds, 64, b.x ? b.w * 32 : b.w)
+    LOAD_WORLD_N(W, worlds, (NRL_WARPS > 1 ? 64 : 32), b.x ? b.w * 32 : b.w)
     const int wib = (int)(threadIdx.x >> 5), ln = (int)(threadIdx.x & 31);
     if (wib >= b.z) return;
     const int pos = b.y + wib, n = W.lvl_nodes[pos], t = *W.t_base + step_off;
@@ -1180,8 +1183,8 @@ __global__ void __launch_bounds__(32 * NRL_WARPS, NRL_MINB) k_node_h(const DevWo
         return;
     }
     if constexpr (HEAVY) {
-        __shared__ NodeSmem<MC, MD> sm_all[NRL_WARPS];
-        __shared__ double tt_all[NRL_WARPS][MD];
+        __shared__ NodeSmem<MC, MD> sm_all[NRL_HEAVY_WARPS];  // (the host puts at most NRL_HEAVY_WARPS nodes into a warp-form block)
+        __shared__ double tt_all[NRL_HEAVY_WARPS][MD];
         WARP_BEGIN
         pre_node(W, sm_all[wib].pre, tt_all[wib], n, t, ln);
 #ifndef UX_EMU

@@ -293,6 +293,10 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
     if (tid == 0) { Q[0] = (unsigned short)k; q_tail = 1; inq[k >> 5] = 1u << (k & 31); lo_min[0] = 0u; lo_min[1] = 0xffffffffu; }
     WAVE_SYNC();
     int head = 0;  // monotone counters; slot = counter % cap
+    // (counter % cap without a division: umulhi(x, ceil(2^32 / cap)) is floor(x / cap) or one more, for any x < 2^31)
+    const unsigned cap_m = (unsigned)((0x100000000ull + (unsigned long long)cap - 1ull) / (unsigned long long)cap);
+    auto wave_slot = [cap, cap_m](int x) { int r = x - (int)__umulhi((unsigned)x, cap_m) * cap; return r < 0 ? r + cap : r; };
+#define WAVE_SLOT(x) wave_slot(x)
     unsigned int tau_hi = 0u;
     for (int r = 0;; r++) {
         int tail = q_tail, p = r & 1;
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
             unsigned long long dj = 0ull;
             bool near = false, far = false;
             if (idx < tail) {
-                j = Q[idx % cap]; dj = WAVE_LD(j);
+                j = Q[WAVE_SLOT(idx)]; dj = WAVE_LD(j);
                 near = (unsigned int)(dj >> 32) < tau_hi;
                 far = !near;
                 if (near) atomicAnd(&inq[j >> 5], ~(1u << (j & 31)));
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
             if (base == head && tid == 0) lo_min[p] = 0xffffffffu;  // round r+1 collects into it
             if (far) {  // stays queued (its bit is still set): goes round once more
                 unsigned int hj = (unsigned int)(dj >> 32);
-                Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)j;
+                Q[WAVE_SLOT(atomicAdd(&q_tail, 1))] = (unsigned short)j;
                 if (hj < mymin) mymin = hj;
             }
             if (WARP) {
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
                             atomicMin((SMEM_DIST ? du_s : du_g) + i, nd);
                             unsigned int hn = (unsigned int)(nd >> 32), bit = 1u << (i & 31);
                             if (hn < mymin) mymin = hn;
-                            if (!(atomicOr(&inq[i >> 5], bit) & bit)) Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)i;
+                            if (!(atomicOr(&inq[i >> 5], bit) & bit)) Q[WAVE_SLOT(atomicAdd(&q_tail, 1))] = (unsigned short)i;
                         }
                     }
                 }
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
                             atomicMin((SMEM_DIST ? du_s : du_g) + ii[u], nd[u]);
                             unsigned int hn = (unsigned int)(nd[u] >> 32), bit = 1u << (ii[u] & 31);
                             if (hn < mymin) mymin = hn;
-                            if (!(atomicOr(&inq[ii[u] >> 5], bit) & bit)) Q[atomicAdd(&q_tail, 1) % cap] = (unsigned short)ii[u];
+                            if (!(atomicOr(&inq[ii[u] >> 5], bit) & bit)) Q[WAVE_SLOT(atomicAdd(&q_tail, 1))] = (unsigned short)ii[u];
                         }
                     }
                 }
@@ -407,6 +411,7 @@ __global__ void __launch_bounds__(STAGE ? 32 * SSSP_STAGE_MAX_WARPS : SSSP_WAVE_
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
 #undef WAVE_LD
 #undef WAVE_SYNC
+#undef WAVE_SLOT
 #endif
 }
 

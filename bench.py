@@ -334,9 +334,10 @@ def main():
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
     api = C.load_product()  # raises without the CUDA library: no fallback
-    # replicas per GPU: throughput keeps growing with the ensemble (Chicago sketch: 1.10e9 platoon-updates/s at 128, 1.60e9 at 512,
-    # 1.86e9 at 1024 -- from 256 on the node step runs with a thread per node and replica); memory bounds the fine-platoon workloads
-    R = args.replicas or {"chicago": 1024, "chicago_dn5": 32, "grid11": 512, "siouxfalls": 512, "grid100": 1}[args.workload]
+    # replicas per GPU: throughput keeps growing with the ensemble (Chicago sketch: 1.20e9 platoon-updates/s at 128, 2.28e9 at 1024,
+    # 2.46e9 at 2048 = 68 GB of state -- from 256 on the node step runs with a thread per node and replica); memory bounds the
+    # fine-platoon workloads
+    R = args.replicas or {"chicago": 2048, "chicago_dn5": 32, "grid11": 512, "siouxfalls": 512, "grid100": 1}[args.workload]
     sc = make_scenario(args.workload, 0)
     tab = sc.tables()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2

@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): replica-batched day-to-day DUE -- R chains per day in one world."""
 import sys, time, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import bench
 from uxsim_b200 import scenario as S

@@ -1,7 +1,7 @@
 """Ad-hoc GPU probe (not a test): one day of the DUE / DSO day-to-day loop -- enforce routes, simulate, swap routes -- on the GPU
 and in the reference C++ (oracle/_ref harness: traffi.cpp + dta_solver.cpp) on the host cores."""
 import sys, time, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import bench
 from uxsim_b200 import _capi as C

@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): where a batched route swap spends its wall time."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from uxsim_b200 import _capi as C
 from uxsim_b200 import scenario as S

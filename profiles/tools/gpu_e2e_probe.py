@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): where the wall time of one end-to-end ensemble run goes (host stages vs device loop)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from uxsim_b200 import _capi as C
 

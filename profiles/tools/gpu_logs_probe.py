@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): cost of the per-platoon vehicle logs (API default) on the GPU and in the reference C++."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from uxsim_b200 import _capi as C
 

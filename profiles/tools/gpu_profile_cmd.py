@@ -1,7 +1,7 @@
 """Profiling target (not a test): one main_loop of the bench workload, nothing else.  Used under ncu:
    python profiles/tools/gpu_profile_cmd.py [workload] [replicas] [until_t]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from uxsim_b200 import _capi as C
 

@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): per-kernel event timing for a workload at several replica counts."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import bench
 from uxsim_b200 import _capi as C

@@ -1,6 +1,6 @@
 """Ad-hoc probe: one workload, given replica counts."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, bench
 from uxsim_b200 import _capi as C
 api = C.load_product()

@@ -1,7 +1,7 @@
 """Target for compute-sanitizer (not a test): small stochastic scenarios through every kernel variant.
    compute-sanitizer --tool memcheck|racecheck python profiles/tools/gpu_sanitize_cmd.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from uxsim_b200 import _capi as C
 from uxsim_b200 import scenario as S
 

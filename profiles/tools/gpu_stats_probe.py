@@ -1,7 +1,7 @@
 """Ad-hoc GPU probe (not a test): 32-seed means of the CUDA engine vs the reference C++ (oracle/_ref) on a workload."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np
 import bench
 from uxsim_b200 import _capi as C

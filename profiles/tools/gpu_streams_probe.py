@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): do independent replica groups on separate streams overlap each other's kernel tails?"""
 import sys, time, os, threading
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from uxsim_b200 import _capi as C
 

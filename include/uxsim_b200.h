@@ -245,6 +245,7 @@ enum {
     UX_A_VEH_X = 18,            /* f64 [P]  current position on link                      */
     UX_A_VEH_V = 19,            /* f64 [P]  current speed                                 */
     UX_A_VEH_LANE = 20,         /* i32 [P] */
+    UX_A_VEH_LINK_ARRIVAL_TIME = 21, /* f64 [P]  Vehicle.arrival_time_link: time the platoon entered its current link (bindings.cpp Vehicle fields) */
     /* per node */
     UX_A_SIGNAL_LOG = 30,       /* i32 [N][T]  Node.signal_log                            */
     UX_A_NODE_SIGNAL_PHASE = 31,/* i32 [N] */

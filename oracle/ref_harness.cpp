@@ -288,7 +288,7 @@ UX_API int64_t uxr_array_size(ux_world *w, int what, int *dtype) {
     switch (what) {
     case UX_A_CUM_ARRIVAL: case UX_A_CUM_DEPARTURE: case UX_A_TRAVELTIME_INSTANT: case UX_A_TRAVELTIME_ACTUAL: n = L * T; break;
     case UX_A_VEH_STATE: case UX_A_VEH_ARRIVAL_TS: case UX_A_VEH_DEPART_TS: case UX_A_VEH_ORIG: case UX_A_VEH_DEST: case UX_A_VEH_LINK: case UX_A_VEH_LANE: n = P; dt = UX_DT_I32; break;
-    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
+    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: case UX_A_VEH_LINK_ARRIVAL_TIME: n = P; break;
     case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_T: case UX_A_NODE_FLOW_CAPACITY: n = N; break;
@@ -339,6 +339,7 @@ UX_API int64_t uxr_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_VEH_DEPART_TS: for (int64_t i = 0; i < P; i++) ii[i] = (int)(W->vehicles[i]->departure_time / W->delta_t); break;
     case UX_A_VEH_TRAVEL_TIME: for (int64_t i = 0; i < P; i++) d[i] = eff_state(W->vehicles[i]) == vsABORT ? -1.0 : W->vehicles[i]->travel_time; break;
     case UX_A_VEH_DISTANCE: for (int64_t i = 0; i < P; i++) d[i] = W->vehicles[i]->distance_traveled; break;
+    case UX_A_VEH_LINK_ARRIVAL_TIME: for (int64_t i = 0; i < P; i++) d[i] = W->vehicles[i]->arrival_time_link; break;
     case UX_A_VEH_ORIG: for (int64_t i = 0; i < P; i++) ii[i] = W->vehicles[i]->orig->id; break;
     case UX_A_VEH_DEST: for (int64_t i = 0; i < P; i++) ii[i] = W->vehicles[i]->dest->id; break;
     case UX_A_VEH_LINK: for (int64_t i = 0; i < P; i++) ii[i] = W->vehicles[i]->link ? W->vehicles[i]->link->id : -1; break;

@@ -1017,7 +1017,7 @@ UX_API int64_t uxo_array_size(ux_world *w, int what, int *dtype) {
     switch (what) {
     case UX_A_CUM_ARRIVAL: case UX_A_CUM_DEPARTURE: case UX_A_TRAVELTIME_INSTANT: case UX_A_TRAVELTIME_ACTUAL: n = L * T; break;
     case UX_A_VEH_STATE: case UX_A_VEH_ARRIVAL_TS: case UX_A_VEH_DEPART_TS: case UX_A_VEH_ORIG: case UX_A_VEH_DEST: case UX_A_VEH_LINK: case UX_A_VEH_LANE: n = P; dt = UX_DT_I32; break;
-    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
+    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: case UX_A_VEH_LINK_ARRIVAL_TIME: n = P; break;
     case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_T: case UX_A_NODE_FLOW_CAPACITY: n = N; break;
@@ -1072,6 +1072,7 @@ UX_API int64_t uxo_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_VEH_ARRIVAL_TS: for (int64_t i = 0; i < P; i++) { const OVeh *v = &w->vehs[i]; ii[i] = (v->arrival_time >= 0 && veh_effective_state(v) != UX_VS_ABORT) ? (int)(v->arrival_time / w->delta_t) : -1; } break;
     case UX_A_VEH_DEPART_TS: for (int64_t i = 0; i < P; i++) ii[i] = (int)(w->vehs[i].departure_time / w->delta_t); break;
     case UX_A_VEH_TRAVEL_TIME: for (int64_t i = 0; i < P; i++) d[i] = veh_effective_state(&w->vehs[i]) == UX_VS_ABORT ? -1.0 : w->vehs[i].travel_time; break;
+    case UX_A_VEH_LINK_ARRIVAL_TIME: for (int64_t i = 0; i < P; i++) d[i] = w->vehs[i].arrival_time_link; break;
     case UX_A_VEH_DISTANCE: for (int64_t i = 0; i < P; i++) { const OVeh *v = &w->vehs[i]; d[i] = v->distance + (v->state == UX_VS_RUN ? v->x - v->entry_x : 0.0); } break;
     case UX_A_VEH_ORIG: for (int64_t i = 0; i < P; i++) ii[i] = w->vehs[i].orig; break;
     case UX_A_VEH_DEST: for (int64_t i = 0; i < P; i++) ii[i] = w->vehs[i].dest; break;

@@ -184,3 +184,27 @@ def test_lazy_vehicle_registry_over_emulated_kernels(emu_api, monkeypatch):
     tt = np.array([v.travel_time for v in W.VEHICLES.values()], dtype=float)
     assert len(tt) == n and (tt[tt >= 0] >= 100).all()
     assert [v.name for v in W._veh_by_index][:2] == ["0", "1"] and W._veh_by_index.names()[-2] == "special"
+
+
+def test_link_and_vehicle_measures_match_reference_wrapper_formulas(emu_api, monkeypatch):
+    """The derived measures the reference's wrapper offers (uxsim_cpp_wrapper.py:386-445, 564-566, 695-718) over the emulated kernels."""
+    import uxsim_b200.world as wmod
+
+    monkeypatch.setattr(wmod.C, "load_product", lambda: emu_api)
+    W = wmod.CudaWorld(name="", deltan=5, tmax=1200, print_mode=0, save_mode=0, random_seed=0)
+    W.addNode("o", 0, 0); W.addNode("m", 1, 0); W.addNode("d", 2, 0)
+    l1 = W.addLink("l1", "o", "m", length=1000, free_flow_speed=20, jam_density=0.2)
+    l2 = W.addLink("l2", "m", "d", length=1000, free_flow_speed=10, jam_density=0.2)
+    W.adddemand("o", "d", 0, 500, 0.5)
+    v0 = W.VEHICLES["0"]
+    v0.add_dests(["m", "d"])
+    assert [n.name for n in v0.dest_list] == ["m", "d"]
+    W.exec_simulation(until_t=400)
+    assert l2.num_vehicles_queue() >= 0 and l1.num_vehicles_queue() % W.DELTAN == 0
+    assert v0.link_arrival_time >= 0.0
+    W.exec_simulation()
+    assert l1.inflow_between(0, 500) == (l1.arrival_count(500) - l1.arrival_count(0)) / 500
+    assert l1.average_density(300) == l1.num_vehicles_t(300) / l1.length
+    assert l1.average_flow(300) == l1.average_density(300) * l1.average_speed(300)
+    assert l2.average_travel_time_between(0, 10) >= l2.length / l2.u - 1e-9
+    assert set(W.ROUTECHOICE.dist_record) == set(range(0, W.TSIZE, W.DELTAT_ROUTE))

@@ -43,7 +43,7 @@ D_DTA_N_SWAP, D_DTA_POTENTIAL_N_SWAP, D_DTA_TOTAL_T_GAP, D_DTA_SWAP_MS, D_DTA_N_
 
 A_CUM_ARRIVAL, A_CUM_DEPARTURE, A_TRAVELTIME_INSTANT, A_TRAVELTIME_ACTUAL = 1, 2, 3, 4
 A_VEH_STATE, A_VEH_ARRIVAL_TS, A_VEH_DEPART_TS, A_VEH_TRAVEL_TIME, A_VEH_DISTANCE = 10, 11, 12, 13, 14
-A_VEH_ORIG, A_VEH_DEST, A_VEH_LINK, A_VEH_X, A_VEH_V, A_VEH_LANE = 15, 16, 17, 18, 19, 20
+A_VEH_ORIG, A_VEH_DEST, A_VEH_LINK, A_VEH_X, A_VEH_V, A_VEH_LANE, A_VEH_LINK_ARRIVAL_TIME = 15, 16, 17, 18, 19, 20, 21
 A_SIGNAL_LOG, A_NODE_SIGNAL_PHASE, A_NODE_SIGNAL_T, A_NODE_FLOW_CAPACITY, A_NODE_NUM_LANES = 30, 31, 32, 33, 34
 A_LINK_NUM_VEHICLES, A_LINK_CAPACITY_IN_REMAIN, A_LINK_CAPACITY_OUT_REMAIN = 40, 41, 42
 A_LINK_STAT_COUNT, A_LINK_TRIPS_COMPLETED, A_LINK_AVE_V_SUM = 43, 44, 45

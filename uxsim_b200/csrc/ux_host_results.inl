@@ -201,7 +201,7 @@ UX_API int64_t ux_array_size(ux_world *w, int what, int *dtype) {
     switch (what) {
     case UX_A_CUM_ARRIVAL: case UX_A_CUM_DEPARTURE: case UX_A_TRAVELTIME_INSTANT: case UX_A_TRAVELTIME_ACTUAL: n = L * T; break;
     case UX_A_VEH_STATE: case UX_A_VEH_ARRIVAL_TS: case UX_A_VEH_DEPART_TS: case UX_A_VEH_ORIG: case UX_A_VEH_DEST: case UX_A_VEH_LINK: case UX_A_VEH_LANE: n = P; dt = UX_DT_I32; break;
-    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: n = P; break;
+    case UX_A_VEH_TRAVEL_TIME: case UX_A_VEH_DISTANCE: case UX_A_VEH_X: case UX_A_VEH_V: case UX_A_VEH_LINK_ARRIVAL_TIME: n = P; break;
     case UX_A_SIGNAL_LOG: n = N * T; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_PHASE: n = N; dt = UX_DT_I32; break;
     case UX_A_NODE_SIGNAL_T: case UX_A_NODE_FLOW_CAPACITY: n = N; break;
@@ -275,6 +275,7 @@ static int64_t device_array(ux_world *w, int what, int replica, void **dptr, int
     case UX_A_VEH_ARRIVAL_TS: *dptr = d.v_arr_ts; break;
     case UX_A_VEH_DEPART_TS: *dptr = (void *)d.v_depart_ts; break;
     case UX_A_VEH_TRAVEL_TIME: *dptr = d.v_tt; break;
+    case UX_A_VEH_LINK_ARRIVAL_TIME: *dptr = d.v_atl; break;
     case UX_A_VEH_ORIG: *dptr = (void *)d.v_orig; break;
     case UX_A_VEH_DEST: *dptr = (void *)d.v_dest; break;
     case UX_A_VEH_LINK: *dptr = d.v_link; break;

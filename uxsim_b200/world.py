@@ -406,6 +406,21 @@ class CudaVehicle:
     def lane(self):
         return int(self.W._veh("lane")[self.id])
 
+    @property
+    def link_arrival_time(self):  # uxsim_cpp_wrapper.py:564-566
+        return float(self.W._veh("link_arrival_time")[self.id])
+
+    def add_dest(self, dest, order=-1):  # uxsim_cpp_wrapper.py:709-718 (taxi mode keeps the list; the loop does not read it)
+        dest = self.W.get_node(dest)
+        if order == -1:
+            self.dest_list.append(dest)
+        else:
+            self.dest_list.insert(order, dest)
+
+    def add_dests(self, dests):
+        for d in dests:
+            self.add_dest(d)
+
     def enforce_route(self, route, set_avoid=False):
         links = [self.W.get_link(l) for l in route]
         self.specified_route = links
@@ -725,7 +740,8 @@ class CudaWorld:
     _SERIES = {"cum_arrival": C.A_CUM_ARRIVAL, "cum_departure": C.A_CUM_DEPARTURE, "traveltime_instant": C.A_TRAVELTIME_INSTANT,
                "traveltime_actual": C.A_TRAVELTIME_ACTUAL, "signal_log": C.A_SIGNAL_LOG}
     _VEH = {"state": C.A_VEH_STATE, "arrival_ts": C.A_VEH_ARRIVAL_TS, "depart_ts": C.A_VEH_DEPART_TS, "travel_time": C.A_VEH_TRAVEL_TIME,
-            "distance": C.A_VEH_DISTANCE, "link": C.A_VEH_LINK, "x": C.A_VEH_X, "v": C.A_VEH_V, "lane": C.A_VEH_LANE}
+            "distance": C.A_VEH_DISTANCE, "link": C.A_VEH_LINK, "x": C.A_VEH_X, "v": C.A_VEH_V, "lane": C.A_VEH_LANE,
+            "link_arrival_time": C.A_VEH_LINK_ARRIVAL_TIME}
 
     def _series(self, key):
         if key not in self._cache:

@@ -67,6 +67,7 @@ static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; retu
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline int atomicCAS(int *p, int c, int v) { int o = *p; if (o == c) *p = v; return o; }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 static inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 static inline double __longlong_as_double(long long l) { double r; memcpy(&r, &l, 8); return r; }

@@ -922,15 +922,16 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                 } else sig_ok = 0xffffffffu;
                 // requested out-links in order of first appearance, each `lanes` times (260-273)
                 int o_id[MD], o_hd[MD], o_tail[MD], o_tail0[MD], o_lastlane[MD], o_lanes[MD], o_woff[MD + 1]; double o_ci[MD], o_cumarr[MD];
-                unsigned char expd[MC]; int c_w[MC];  // c_w: out-link index | in-link index << 8 | position from the head << 16 (out-link 255: none, 254: moved)
+                unsigned char expd[MC], p_q[MC];  // p_q: per head position, the index of the out-link it wants to enter (255: none / not a candidate)
                 int nol = 0, nexp = 0;
+                for (int p = 0; p < npos; p++) p_q[p] = 255;
                 for (int k = 0; k < nc; k++) {
                     int p = c_idx[k], nl = p_next[p], q = 255;
                     if (nl >= 0) {
                         for (int x = 0; x < nol; x++) if (o_id[x] == nl) { q = x; break; }
                         if (q == 255 && nol < MD) { q = nol; o_id[nol++] = nl; }
                     }
-                    c_w[k] = q | ((int)p_ii[p] << 8) | ((p - i_poff[p_ii[p]]) << 16);
+                    p_q[p] = (unsigned char)q;
                 }
                 { int acc = 0; for (int q = 0; q < nol; q++) { int lanes = W.l_lanes[o_id[q]]; o_lanes[q] = lanes; o_woff[q] = acc; acc += lanes; for (int x = 0; x < lanes && nexp < MC; x++) expd[nexp++] = (unsigned char)q; } o_woff[nol] = acc; }
                 const int nshuf = (!W.hard_det && nexp > 1) ? nexp - 1 : 0;
@@ -1015,6 +1016,26 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                 const double fc = W.n_fc[n];
                 double fc_rem = nr->fc_rem;
                 int n_picks = 0;
+                // per in-link: the out-link its front platoon may move onto now (255: none) -- a byte each, in two registers
+                unsigned long long fq0 = ~0ull, fq1 = ~0ull;
+#define F_SET(ii_, v_) { if ((ii_) < 8) fq0 = (fq0 & ~(255ull << ((ii_) * 8))) | ((unsigned long long)(v_) << ((ii_) * 8)); else fq1 = (fq1 & ~(255ull << (((ii_) - 8) * 8))) | ((unsigned long long)(v_) << (((ii_) - 8) * 8)); }
+                auto front_q = [&](int ii) -> int {  // front of its link, outflow tokens, green (305-330)
+                    const int pop = I_POP(ii);
+                    if (pop >= i_hc[ii] || !(((sig_ok & co_ok) >> ii) & 1u)) return 255;
+                    const int fp = i_poff[ii] + pop;
+                    return fp < npos ? (int)p_q[fp] : 255;
+                };
+                for (int ii = 0; ii < nin; ii++) if (i_hc[ii] > 0) { const int f = front_q(ii); F_SET(ii, f) }
+                unsigned good = 0;  // out-links that accept a platoon now (285-297; the node capacity is tested once per slot)
+                auto accepts = [&](int q) -> bool {
+                    const int sz = o_tail[q] - o_hd[q];
+                    bool ok = false;
+                    if (sz < o_lanes[q]) ok = true;
+                    else if (w_x[o_woff[q] + w_f[q]] > W.l_dpl_dn[o_id[q]]) ok = true;
+                    if (o_ci[q] < W.dn) ok = false;
+                    return ok;
+                };
+                for (int q = 0; q < nol; q++) if (accepts(q)) good |= 1u << q;
                 // trip end of the front platoon (position p) of in-link ii: Vehicle::end_trip (886-927)
                 auto end_front = [&](int ii, int p) {
                     const int il = W.n_in[i0 + ii], vid = p_vid[p];
@@ -1036,47 +1057,45 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     RLP(unsigned char, W.v_flags)[vid] = 0;
                     I_POP_INC(ii)
                 };
-                unsigned dead = 0;  // out-links whose slot found nothing to move since the last move: nothing they depend on has changed, skip
                 for (int s = 0; s < nexp; s++) {
+                    if (fc_rem < W.dn) break;  // no slot can move anything any more (298-300)
                     const int q = expd[s];
-                    if ((dead >> q) & 1u) continue;
-                    const int lanes_ol = o_lanes[q], sz = o_tail[q] - o_hd[q], w0 = o_woff[q];
-                    bool ok = false;  // acceptance (285-300)
-                    if (sz < lanes_ol) ok = true;
-                    else if (w_x[w0 + w_f[q]] > W.l_dpl_dn[o_id[q]]) ok = true;
-                    if (o_ci[q] < W.dn) ok = false;
-                    if (fc_rem < W.dn) ok = false;
-                    if (!ok) { dead |= 1u << q; continue; }
-                    // eligible candidates in ascending id: front of their in-link, outflow tokens, green (305-330)
-                    const unsigned in_ok = sig_ok & co_ok;
-                    double wsum = 0.0, wbest = 0.0; int nm = 0, kbest = -1;
-                    for (int k = 0; k < nc; k++) {
-                        const int cw = c_w[k], ii = (cw >> 8) & 255;
-                        if ((cw & 255) != q || !((in_ok >> ii) & 1u) || (cw >> 16) != I_POP(ii)) continue;
-                        double mp = i_mp[ii];
-                        if (nm == 0 || mp > wbest) { wbest = mp; kbest = k; }
-                        wsum += mp; nm++;
-                    }
-                    if (nm == 0) { dead |= 1u << q; continue; }
-                    dead = 0;
-                    int kp = kbest;
-                    if (!W.hard_det) {  // random_choice over the merge priorities (utils.h:62-87)
-                        double u = ux_rng_uniform(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + n_picks));
-                        n_picks++;
-                        int target = -1; double rr = u * wsum;
-                        if (wsum <= 0.0) { target = (int)(u * (double)nm); if (target >= nm) target = nm - 1; }
-                        double accum = 0.0; int seen = 0; kp = -1;
-                        for (int k = 0; k < nc; k++) {
-                            const int cw = c_w[k], ii = (cw >> 8) & 255;
-                            if ((cw & 255) != q || !((in_ok >> ii) & 1u) || (cw >> 16) != I_POP(ii)) continue;
-                            kp = k;  // the last eligible one is the fallback of random_choice
-                            if (target >= 0) { if (seen == target) break; }
-                            else { accum += i_mp[ii]; if (rr <= accum) break; }
-                            seen++;
+                    if (!((good >> q) & 1u)) continue;
+                    // in-links whose front wants this out-link: byte-wise compare of the packed fronts with q
+                    const unsigned long long pat = 0x0101010101010101ull * (unsigned long long)q;
+                    const unsigned long long x0 = fq0 ^ pat, x1 = fq1 ^ pat;
+                    const unsigned long long z0 = (x0 - 0x0101010101010101ull) & ~x0 & 0x8080808080808080ull, z1 = (x1 - 0x0101010101010101ull) & ~x1 & 0x8080808080808080ull;
+                    if (!(z0 | z1)) continue;
+                    int ii;
+                    if (!(z0 & (z0 - 1)) && !z1) { ii = (__ffsll((long long)z0) - 1) >> 3; n_picks++; }  // one offer (the usual case): no lottery, its draw is consumed
+                    else if (!z0 && !(z1 & (z1 - 1))) { ii = 8 + ((__ffsll((long long)z1) - 1) >> 3); n_picks++; }
+                    else {
+                        // several in-links offer a platoon: candidates in ascending platoon id, random_choice over their merge priorities (utils.h:62-87)
+                        // (the borrow of the zero-byte test can flag a byte above a true match: every flagged byte is checked)
+                        int cand[MD]; int nm = 0;
+                        for (int i2 = 0; i2 < nin; i2++) {
+                            const int f = (int)(((i2 < 8 ? fq0 >> (i2 * 8) : fq1 >> ((i2 - 8) * 8))) & 255ull);
+                            if (f != q) continue;
+                            const int vid2 = p_vid[i_poff[i2] + I_POP(i2)];
+                            int at = nm++;
+                            while (at > 0 && p_vid[i_poff[cand[at - 1]] + I_POP(cand[at - 1])] > vid2) { cand[at] = cand[at - 1]; at--; }
+                            cand[at] = i2;
                         }
+                        int pick = 0;
+                        if (W.hard_det) { for (int i = 1; i < nm; i++) if (i_mp[cand[i]] > i_mp[cand[pick]]) pick = i; }
+                        else {
+                            const double u = ux_rng_uniform(W.seed + ln, (uint32_t)t, (uint32_t)n, UX_RNG_TRANSFER, (uint32_t)(nshuf + n_picks));
+                            n_picks++;
+                            double wsum = 0.0;
+                            for (int i = 0; i < nm; i++) wsum += i_mp[cand[i]];
+                            if (wsum <= 0.0) { pick = (int)(u * (double)nm); if (pick >= nm) pick = nm - 1; }
+                            else { const double rr = u * wsum; double accum = 0.0; pick = nm - 1; for (int i = 0; i < nm; i++) { accum += i_mp[cand[i]]; if (rr <= accum) { pick = i; break; } } }
+                        }
+                        ii = cand[pick];
                     }
-                    // ---- move candidate kp onto the out-link: everything it needs in one batch of loads, then stores only
-                    const int p = c_idx[kp], vid = p_vid[p], ii = p_ii[p], il = W.n_in[i0 + ii], ol = o_id[q];
+                    // ---- move the front platoon of in-link ii onto out-link q: everything it needs in one batch of loads, then stores only
+                    const int p = i_poff[ii] + I_POP(ii), vid = p_vid[p], il = W.n_in[i0 + ii], ol = o_id[q];
+                    const int lanes_ol = o_lanes[q], sz = o_tail[q] - o_hd[q], w0 = o_woff[q];
                     const size_t in_at = (size_t)W.l_roff[il] + ring_slot(i_hd[ii], p - i_poff[ii], W.l_rcap[il]);
                     const double atl = RLP(double, W.v_atl)[vid], px = Xc[in_at], pxold = Xo[in_at], pv = V[in_at], ex = RLP(double, W.v_entry_x)[vid],
                                  di = RLP(double, W.v_dist)[vid], mr = RLP(double, W.v_mr)[vid];
@@ -1112,7 +1131,8 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     if (x_next < 0.0) x_next = 0.0;
                     if (sz >= W.l_rcap[ol]) dev_error(Wr, DERR_RING_FULL, ol);
                     else {  // push (lane rule 385-390)
-                        int lane_new = sz > 0 ? (o_lastlane[q] + 1) % lanes_ol : 0;
+                        int lane_new = sz > 0 ? o_lastlane[q] + 1 : 0;  // (lane + 1) % lanes: lane labels are < lanes
+                        if (lane_new >= lanes_ol) lane_new = 0;
                         size_t at = (size_t)W.l_roff[ol] + ring_slot(o_tail[q], 0, W.l_rcap[ol]);
                         Xc[at] = x_next; Xo[at] = pxold; V[at] = pv + x_next / W.dt; VID[at] = vid; LANE[at] = lane_new;
                         o_tail[q] += 1; o_lastlane[q] = lane_new;
@@ -1121,10 +1141,13 @@ UX_DEV void node_step_rl(const DevWorld &W, const DevWorld &Wr, const int ln, co
                     }
                     RLP(double, W.v_entry_x)[vid] = x_next;
                     RLP(double, W.v_mr)[vid] = 0.0;
-                    c_w[kp] |= 254;  // removed from the incoming list (out-link index 254 matches no slot)
                     // the new front of the in-link may be waiting for its trip end (421-424)
                     if (I_POP(ii) < i_hc[ii]) { int fp = i_poff[ii] + I_POP(ii); if (fp < npos && (p_flag[fp] & VF_WAIT_END)) end_front(ii, fp); }
+                    // what this move changed for the slots to come: the in-link's front and tokens, the out-link's tail
+                    { const int f = front_q(ii); F_SET(ii, f) }
+                    if (accepts(q)) good |= 1u << q; else good &= ~(1u << q);
                 }
+#undef F_SET
                 NPROF_T(pt5) NPROF_MAX(4, pt4, pt5)
                 // flush trip-end-waiting fronts (432-441)
                 for (int ii = 0; ii < nin; ii++) {

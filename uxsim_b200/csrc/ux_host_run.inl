@@ -49,7 +49,11 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
             KT_BEGIN(UX_K_UPDATE)
             if (update_rl) {
                 // helper blocks (grid z) share long queues; the head-of-link log records need the whole queue in one block
-                static const int rl_parts = [] { const char *e = getenv("UXSIM_B200_RL_PARTS"); return e ? atoi(e) : 4; }();
+                // Only where queues get long: on a lightly loaded network (the regime in which this kernel is picked by itself) no link has
+                // 128 platoons over 32 replicas, and helper blocks that look and leave still cost 16 % of the launch (B200, Chicago x2048: 969 ->
+                // 814 us without them; forced on Chicago deltan=5 x16 they take it from 143 to 56 us).
+                static const int rl_parts_env = [] { const char *e = getenv("UXSIM_B200_RL_PARTS"); return e ? atoi(e) : 0; }();
+                const int rl_parts = rl_parts_env > 0 ? rl_parts_env : ((long long)w->vehs.size() <= 32ll * (long long)w->links.size() ? 1 : 4);
                 dim3 g_rl(((int)w->links.size() + UPD_RL_WARPS - 1) / UPD_RL_WARPS, (R + 31) / 32, w->p.vehicle_log_mode ? 1 : std::max(1, rl_parts));
 #ifdef UX_EMU
                 UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R, (int)w->links.size());

@@ -53,7 +53,8 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
                 // 128 platoons over 32 replicas, and helper blocks that look and leave still cost 16 % of the launch (B200, Chicago x2048: 969 ->
                 // 814 us without them; forced on Chicago deltan=5 x16 they take it from 143 to 56 us).
                 static const int rl_parts_env = [] { const char *e = getenv("UXSIM_B200_RL_PARTS"); return e ? atoi(e) : 0; }();
-                const int rl_parts = rl_parts_env > 0 ? rl_parts_env : ((long long)w->vehs.size() <= 32ll * (long long)w->links.size() ? 1 : 4);
+                const bool rl_full = ((long long)w->links.size() / UPD_RL_WARPS) * ((R + 31) / 32) >= 2048;  // enough blocks to fill the GPU without splitting queues (x128: 98 us with helpers, 107 without)
+                const int rl_parts = rl_parts_env > 0 ? rl_parts_env : ((rl_full && (long long)w->vehs.size() <= 32ll * (long long)w->links.size()) ? 1 : 4);
                 dim3 g_rl(((int)w->links.size() + UPD_RL_WARPS - 1) / UPD_RL_WARPS, (R + 31) / 32, w->p.vehicle_log_mode ? 1 : std::max(1, rl_parts));
 #ifdef UX_EMU
                 UX_LAUNCH(k_update_rl, g_rl, dim3(32 * UPD_RL_WARPS), st, w->dworlds, s, R, (int)w->links.size());

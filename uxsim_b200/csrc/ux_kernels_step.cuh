@@ -1427,7 +1427,9 @@ __global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *w
 // per-lane pointer reads are bank-conflict free), so every helper (route_choice, log_run_record, dev_error) is shared with
 // k_update.  Bit-identical to k_update: the arithmetic per link is the same and links do not interact within this kernel.
 // ---------------------------------------------------------------------------------------------------
+#ifndef UPD_RL_WARPS
 #define UPD_RL_WARPS 8
+#endif
 // 4 blocks per SM (64 registers, 32 warps resident): the kernel is bound by load latency, not by registers -- B200, Chicago sketch x1024:
 // 649 us (95 registers, 2 blocks) -> 506 (80, 3 blocks) -> 488 (64, 4 blocks) -> 554 (5 blocks: spills)
 #ifndef UPD_RL_MINB

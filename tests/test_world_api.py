@@ -208,3 +208,43 @@ def test_link_and_vehicle_measures_match_reference_wrapper_formulas(emu_api, mon
     assert l1.average_flow(300) == l1.average_density(300) * l1.average_speed(300)
     assert l2.average_travel_time_between(0, 10) >= l2.length / l2.u - 1e-9
     assert set(W.ROUTECHOICE.dist_record) == set(range(0, W.TSIZE, W.DELTAT_ROUTE))
+
+
+def _override_signal_pair(wmod):
+    """test_verification_node.py::test_override_signal with an array-aware final comparison (the reference's `cum1 == cum2` is
+    ambiguous on numpy arrays, in its own C++ mode too): signal plan + groups given at construction == given through override_signal."""
+    out = []
+    for override in (False, True):
+        W = wmod.CudaWorld(name="", deltan=1, tmax=1200, print_mode=0, save_mode=0, random_seed=0)
+        for name, x, y in (("orig1", 0, 0), ("orig2", 0, 2), ("orig3", 0, 3), ("dest", 2, 1)):
+            W.addNode(name, x, y)
+        merge = W.addNode("merge", 1, 1) if override else W.addNode("merge", 1, 1, signal=[30, 60])
+        grp = {"link1": [0], "link2": [0, 1], "link2b": [1]}
+        for name, o, mp in (("link1", "orig1", 1), ("link2", "orig2", 1), ("link2b", "orig3", 0.5)):
+            kw = {} if override else {"signal_group": grp[name]}
+            W.addLink(name, o, "merge", length=1000, free_flow_speed=20, jam_density=0.2, merge_priority=mp, **kw)
+        W.addLink("link3", "merge", "dest", length=1000, free_flow_speed=20, jam_density=0.2, capacity_in=1)
+        W.adddemand("orig1", "dest", 0, 1000, 0.2); W.adddemand("orig2", "dest", 500, 1000, 0.3); W.adddemand("orig3", "dest", 500, 1000, 0.3)
+        if override:
+            merge.override_signal(signal=[30, 60], groups=[["link1", "link2"], ["link2", "link2b"]])
+        W.exec_simulation()
+        W.analyzer.basic_analysis()
+        out.append((W.analyzer.total_travel_time, [np.array(l.cum_arrival) for l in W.LINKS], list(W.get_node("merge").signal_log)))
+    return out
+
+
+def test_override_signal_equals_construction_time_plan_emulated(emu_api, monkeypatch):
+    import uxsim_b200.world as wmod
+
+    monkeypatch.setattr(wmod.C, "load_product", lambda: emu_api)
+    a, b = _override_signal_pair(wmod)
+    assert a[0] == b[0] and a[2] == b[2] and all(np.array_equal(x, y) for x, y in zip(a[1], b[1]))
+    assert len(set(a[2])) == 2  # the signal did switch phases
+
+
+@pytest.mark.gpu
+def test_override_signal_equals_construction_time_plan(cuda_api):
+    import uxsim_b200.world as wmod
+
+    a, b = _override_signal_pair(wmod)
+    assert a[0] == b[0] and a[2] == b[2] and all(np.array_equal(x, y) for x, y in zip(a[1], b[1]))

@@ -285,7 +285,11 @@ UX_API int64_t ux_ensemble_link_stats_device(ux_world *w, void **dptr) {
     if (!w->d_ens) w->d_ens = dalloc<double>(w, (size_t)L * 4);
     if (L > 0) {
         int rc = ensure_scratch(w, 8 * (size_t)L * 4 * w->R + 16); if (rc) return rc;
-        UX_LAUNCH(k_ensemble_partial, dim3((L + 63) / 64, w->R), dim3(64), w->stream, w->dworlds, w->d_scratch);
+#ifdef UX_EMU
+        UX_LAUNCH(k_ensemble_partial, dim3((L + 63) / 64, w->R), dim3(64), w->stream, w->dworlds, w->d_scratch, w->R);
+#else
+        UX_LAUNCH(k_ensemble_partial, dim3((unsigned)(((size_t)L * 32 + 255) / 256), (w->R + 31) / 32), dim3(256), w->stream, w->dworlds, w->d_scratch, w->R);
+#endif
         UX_LAUNCH(k_ensemble_stats, dim3((L * 4 + 127) / 128), dim3(128), w->stream, w->dworlds, w->R, (const double *)w->d_scratch, w->d_ens);
     }
     CUDA_OK(cudaStreamSynchronize(w->stream));

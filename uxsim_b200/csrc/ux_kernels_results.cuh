@@ -96,23 +96,32 @@ __global__ void k_veh_snapshot(const DevWorld *worlds, int replica, double *vx, 
 // per-link ensemble statistics over this world's replicas: {volume, sum tt_actual, sum tt_actual^2, platoons on link}.
 // Stage 1: thread per (link, replica) walks that replica's travel-time event table; stage 2: thread per link adds the
 // replicas in index order (deterministic sums).
-__global__ void k_ensemble_partial(const DevWorld *worlds, double *part) {
-    const DevWorld &W = worlds[blockIdx.y];
-    int l = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+// Lanes = the 32 replicas of ONE link (grid y = lane groups): the event tables and curves are replica-minor, so every load of a warp is one
+// contiguous row (a lane per link of one replica read a 4-byte word per 32-byte sector: 40 ms at 2 048 replicas of the Chicago sketch; this form: 4 ms).
+__global__ void k_ensemble_partial(const DevWorld *worlds, double *part, int R) {
+    const int idx = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+#ifdef UX_EMU
+    const int l = idx, ln = 0, r = (int)blockIdx.y;  // (the emulation runs one replica per grid row)
+    const DevWorld &W = worlds[r];
+#else
+    const int l = idx >> 5, ln = idx & 31, r = (int)blockIdx.y * 32 + ln;
+    const DevWorld &W = worlds[(int)blockIdx.y * 32];  // the group's first replica; the lanes add their offsets
+#endif
     int T = W.T, L = W.L;
-    if (l >= L) return;
+    if (l >= L || r >= R) return;
     double cur = W.l_tt0[l], s1 = 0, s2 = 0;
     int best = 0;
 #pragma unroll 8
     for (int i = 0; i < T; i++) {
-        int ord = W.ev_ord[TLI(W, i, l)];
-        double v = W.ev_tt[TLI(W, i, l)];
+        int ord = W.ev_ord[TLI(W, i, l) + ln];
+        double v = W.ev_tt[TLI(W, i, l) + ln];
         if (ord > best) { best = ord; cur = v; }
         s1 += cur; s2 += cur * cur;
     }
-    double *o = part + ((size_t)blockIdx.y * L + l) * 4;
-    o[0] = T > 0 ? W.cum_arr[TLI(W, (T - 1), l)] : 0.0; o[1] = s1; o[2] = s2;
-    o[3] = (double)(LQ(W, l).tail - LQ(W, l).head[*W.t_base & 1]);
+    double *o = part + ((size_t)r * L + l) * 4;
+    const LinkQ *lq = &LQ(W, l) + ln;
+    o[0] = T > 0 ? W.cum_arr[TLI(W, (T - 1), l) + ln] : 0.0; o[1] = s1; o[2] = s2;
+    o[3] = (double)(lq->tail - lq->head[*W.t_base & 1]);
 }
 __global__ void k_ensemble_stats(const DevWorld *worlds, int R, const double *part, double *out) {
     int L = worlds[0].L;

@@ -337,15 +337,16 @@ def test_bench_shape_chicago_128_replicas(cuda_api, oracle_api):
     Eg.close()
 
 
-def test_bench_shape_chicago_1024_replicas(cuda_api, oracle_api):
-    """bench.py's default since round 2: 1024 replicas in one world -- the node step with a thread per (node, replica), picked by
-    the engine itself.  Replicas 0, 511 and 1023 equal the single-seed oracle runs bit for bit; conservation over all replicas."""
+def test_bench_shape_chicago_2048_replicas(cuda_api, oracle_api):
+    """bench.py's default since round 2: 2048 replicas in one world (68 GB of state) -- the node step with a thread per (node,
+    replica), the link update without helper blocks, the warp-per-destination route search, all picked by the engine itself.
+    Replicas 0, 1023 and 2047 equal the single-seed oracle runs bit for bit; the replicas are genuinely different runs."""
     sc = S.chicago_sketch()
     tab = sc.tables()
-    R, seed0 = 1024, 300000
+    R, seed0 = 2048, 300000
     Eg = sc.engine_from_tables(cuda_api, tab, vehicle_logging_timestep_interval=-1, num_replicas=R, random_seed=seed0)
     Eg.main_loop()
-    for r in (0, 511, 1023):
+    for r in (0, 1023, 2047):
         Eo = sc.engine_from_tables(oracle_api, tab, vehicle_logging_timestep_interval=-1, random_seed=seed0 + r)
         Eo.main_loop()
         assert compare_engines(Eg, Eo, replica_a=r) == [], f"replica {r}"

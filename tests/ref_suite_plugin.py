@@ -39,3 +39,15 @@ def pytest_configure(config):
 
     mod.World.__new__ = _cuda_new
     ux.World = mod.World
+    # the day-to-day solvers: the reference hands `SolverDUE(func_World, cpp=True)` to its C++ adapter (DTAsolvers.py:21-26, 378-383);
+    # here every SolverDUE / SolverDSO_D2D is this package's counterpart of that adapter
+    import uxsim.DTAsolvers.DTAsolvers as dta_mod
+    import uxsim_b200.dta as cuda_dta
+
+    def _solver_new(cuda_cls):
+        def _new(cls, func_World, cpp=False):
+            return cuda_cls(func_World)
+        return _new
+
+    dta_mod.SolverDUE.__new__ = _solver_new(cuda_dta.CudaSolverDUE)
+    dta_mod.SolverDSO_D2D.__new__ = _solver_new(cuda_dta.CudaSolverDSO_D2D)

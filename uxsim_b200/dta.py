@@ -220,6 +220,44 @@ class _CudaSolverBase:
         return s.W_sol
 
 
+    # ---- the three convergence plots of the reference's solvers (DTAsolvers.py:267-372); drawing is outside the loop (out of
+    #      scope), so they are thin: without matplotlib they warn and return, like the reference's catch_exceptions_and_warn helpers
+    def _plot(self, draw):
+        try:
+            import matplotlib.pyplot as plt
+
+            draw(plt)
+            plt.show()
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"{type(self).__name__}: plotting skipped ({type(e).__name__}: {e})")
+
+    def plot_convergence(self):
+        def draw(plt):
+            for title, ys in (("total travel time", self.ttts), ("number of route change", self.n_swaps),
+                              ("travel cost difference between chosen route and minimum cost route", self.t_gaps)):
+                plt.figure(figsize=(6, 2)); plt.title(title); plt.plot(ys); plt.xlabel("iter")
+        self._plot(draw)
+
+    def plot_link_stats(self):
+        def draw(plt):
+            for title, col, ylabel in (("traffic volume", "traffic_volume", "volume (veh)"), ("average travel time", "average_travel_time", "time (s)")):
+                plt.figure(); plt.title(title)
+                for i, name in enumerate(self.dfs_link[0]["link"]):
+                    plt.plot([df[col][i] for df in self.dfs_link], label=name)
+                plt.xlabel("iteration"); plt.ylabel(ylabel); plt.legend(loc="center left", bbox_to_anchor=(1, 0.5))
+        self._plot(draw)
+
+    def plot_vehicle_stats(self, orig=None, dest=None):
+        def draw(plt):
+            half = range(len(self.cost_log) // 2, len(self.cost_log))
+            sel = [v for v in self.W_sol.VEHICLES.values() if orig in (None, v.orig.name) and dest in (None, v.dest.name)]
+            costs = np.array([[self.cost_log[day][v.id] for day in half] for v in sel])
+            plt.figure(); plt.title(f"orig: {orig or 'any'}, dest: {dest or 'any'}")
+            plt.errorbar(x=[v.departure_time_in_second for v in sel], y=costs.mean(axis=1), yerr=costs.std(axis=1), fmt="bx", ecolor="#aaaaff", capsize=0)
+            plt.xlabel("departure time of vehicle"); plt.ylabel("travel time")
+        self._plot(draw)
+
+
 class CudaSolverDUE(_CudaSolverBase):
     """Dynamic user equilibrium by day-to-day route swapping on the GPU (CppSolverDUE, DTAsolvers_cpp_adapter.py:249-366)."""
 

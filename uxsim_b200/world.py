@@ -703,6 +703,7 @@ class CudaWorld:
         self.VEHICLES, self.VEHICLES_LIVING, self.VEHICLES_RUNNING = _VehicleDict(self._veh_by_index), _VehicleDict(self._veh_by_index), _VehicleDict(self._veh_by_index, [])
         self.NODES, self.LINKS, self.NODES_NAME_DICT, self.LINKS_NAME_DICT = [], [], {}, {}
         self.vehicle_logging_timestep_interval = vehicle_logging_timestep_interval
+        self._log_mode = vehicle_logging_timestep_interval > 0
         self.route_choice_principle = route_choice_principle
         self.route_choice_update_gradual = route_choice_update_gradual
         self.instantaneous_TT_timestep_interval = min(int(instantaneous_TT_timestep_interval), self.DELTAT_ROUTE)
@@ -751,7 +752,7 @@ class CudaWorld:
 
     def _vehicle_log(self, vid):
         """Per-platoon view of the flat SoA logs (uxsim_cpp_wrapper.py:1309-1367), fetched once per state of the run."""
-        if self.vehicle_logging_timestep_interval <= 0:
+        if not self._log_mode:  # what the engine was created with: a caller may lower the attribute afterwards (the reference's Python solvers do), the records are still kept
             raise RuntimeError("vehicle logging is off (vehicle_logging_timestep_interval=-1)")
         if "logs" not in self._cache:
             E = self._E

@@ -46,7 +46,7 @@ def stage() -> bool:
         shutil.rmtree(tdir)
     os.makedirs(tdir)
     for n in sorted(os.listdir(os.path.join(SRC, "tests"))):
-        if n == "conftest.py" or (n.startswith("test_verification_") and n.endswith(".py")):
+        if n in ("conftest.py", "test_cpp_mode.py") or (n.startswith("test_verification_") and n.endswith(".py")):
             shutil.copy2(os.path.join(SRC, "tests", n), os.path.join(tdir, n))
     ddir = os.path.join(DST, "dat")
     os.makedirs(ddir, exist_ok=True)

@@ -220,6 +220,11 @@ enum {
     UX_OPT_RECORD_TRAVERSALS = 3, /* 1 (before the first main_loop): record every link entry (platoon, link, step) on the device so that
                                    dta_route_swap can read the traversed routes without the per-step vehicle logs (CUDA build; the CPU
                                    engines read their logs, as dta_get_traveled_route does, dta_solver.cpp:30-57) */
+    UX_OPT_ABORT_VEHICLE = 5,   /* value = platoon id (before the first main_loop): the platoon never departs and reports state ABORT -- what setting
+                                   Vehicle.state = "abort" before the run does in the reference (uxsim_cpp_wrapper.py:517-519, traffi.cpp:833-881) */
+    UX_OPT_ROUTE_TABLES_AT = 4, /* timestep >= 0: the next UX_A_ROUTE_DIST / UX_A_ROUTE_NEXT reads return the tables of the route update that was
+                                   current at that timestep (World::route_dist_record, traffi.cpp:1840-1851; the engine keeps the edge costs of every
+                                   update -- 8 B per node pair -- and searches on demand); -1: the latest update (default) */
     UX_OPT_ALL_DESTINATIONS = 2 /* 1 (before the first main_loop): keep route preferences for every node, as the reference does,
                                    instead of only for the destinations present in the demand.  Needed only if demand towards
                                    NEW destinations will be added between main_loop calls. */

@@ -1092,8 +1092,18 @@ UX_API int64_t uxo_get_array(ux_world *w, int what, int replica, void *dst, int6
     case UX_A_LINK_TRIPS_COMPLETED: for (int64_t l = 0; l < L; l++) d[l] = w->links[l].trips_completed; break;
     case UX_A_LINK_AVE_V_SUM: for (int64_t l = 0; l < L; l++) d[l] = w->links[l].ave_v_sum; break;
     case UX_A_ROUTE_PREF: memcpy(d, w->pref, sizeof(double) * N * L); break;
-    case UX_A_ROUTE_DIST: memcpy(d, w->rdist, sizeof(double) * N * N); break;
-    case UX_A_ROUTE_NEXT: memcpy(ii, w->rnext, sizeof(int) * N * N); break;
+    case UX_A_ROUTE_DIST: case UX_A_ROUTE_NEXT: {
+        /* RouteChoice.dist / .next are all-pairs tables in the reference (traffi.cpp:1317-1385); the loop only needs -- and only
+           searches -- the destinations that occur in the demand.  The getter completes the other columns on the edge costs of the
+           last route update (the loop never reads them). */
+        if (w->timestep > 0 && N > 0) {
+            int *queue = (int *)xrealloc(NULL, sizeof(int) * N);
+            unsigned char *inq = (unsigned char *)xrealloc(NULL, N);
+            for (int k = 0; k < N; k++) if (!w->dest_active[k]) route_search_dest(w, k, queue, inq);
+            free(queue); free(inq);
+        }
+        if (what == UX_A_ROUTE_DIST) memcpy(d, w->rdist, sizeof(double) * N * N); else memcpy(ii, w->rnext, sizeof(int) * N * N);
+        break; }
     case UX_A_LOG_OFFSETS: { int64_t s = 0; for (int64_t i = 0; i < P; i++) { ll[i] = s; s += w->vehs[i].log_size; } ll[P] = s; break; }
     case UX_A_LOG_N_MISSING: for (int64_t i = 0; i < P; i++) { const OVeh *v = &w->vehs[i]; ii[i] = (v->log_size > 0 && log_t_at(w, v, 0) > 0) ? (int)(log_t_at(w, v, 0) / w->delta_t) : 0; } break;
     case UX_A_LOG_T: case UX_A_LOG_X: case UX_A_LOG_V: case UX_A_LOG_S: case UX_A_LOG_STATE: case UX_A_LOG_LANE: case UX_A_LOG_LINK: {

@@ -23,13 +23,24 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILES = ["test_verification_straight_road.py", "test_verification_node.py", "test_verification_multilane.py",
          "test_verification_route_choice.py", "test_verification_exceptional.py", "test_verification_sioux_falls.py",
-         "test_verification_dta_solvers.py"]  # (the plugin serves SolverDUE / SolverDSO_D2D by uxsim_b200.dta, as `cpp=True` selects the C++ adapter)
+         "test_verification_dta_solvers.py",  # (the plugin serves SolverDUE / SolverDSO_D2D by uxsim_b200.dta, as `cpp=True` selects the C++ adapter)
+         "test_cpp_mode.py"]  # the reference's own C++-mode suite: every test of the files above once more with World(cpp=True), plus C++-mode specifics
+# tests of a file that cannot apply here: they start NEW python processes that `import uxsim` and run example scripts / notebooks
+DESELECT = {"test_cpp_mode.py": "not test_cpp_example_runs and not notebook"}
 EXPECTED_FAIL = {
     # `["log_t"] + veh.log_t`: list concatenation with a per-vehicle log; CppVehicle.log_t is a numpy array as well
     "test_verification_straight_road.py": {"test_iterative_exec_rigorous", "test_iterative_exec_rigorous_random_size_old",
                                            "test_iterative_exec_rigorous_random_size_duration_t2"},
     # `assert cum1 == cum2` on two cumulative curves: ambiguous truth value of an array; CppLink.cum_arrival is a numpy array as well
     "test_verification_node.py": {"test_override_signal"},
+    "test_cpp_mode.py": {
+        # expects save_scenario / load_scenario / copy / save to raise NotImplementedError as in C++ mode; load_scenario IS implemented here
+        # (SURVEY.md 8f-3), so the call goes on to open the file "dummy"
+        "test_coverage_misc_world_methods",
+        # expects addNode(existing name, auto_rename=True) to raise: the C++ wrapper renames on the Python side but registers the ORIGINAL name
+        # with the C++ world, which rejects it (uxsim_cpp_wrapper.py:62-75); here auto_rename renames, as in Python mode
+        "test_coverage_node_signal_and_rename",
+    },
 }
 
 
@@ -37,7 +48,8 @@ EXPECTED_FAIL = {
 # to pass here either.  test_DTA_dynamic_congestion_pricing_on_highway_bottleneck asserts `average_travel_time_between(500, 3000) > 300`
 # and `... (4000, 6000) < 200` after 40 day-to-day iterations; four runs of the reference's Python engine and solver in the dev container
 # gave 285 / 292 / 301 / 341 and 199 / 175 / 190 / 221, six runs of this backend 273 ... 385 and 164 ... 174.
-UNSTABLE_IN_REFERENCE = {"test_verification_dta_solvers.py": {"test_DTA_dynamic_congestion_pricing_on_highway_bottleneck"}}
+UNSTABLE_IN_REFERENCE = {"test_verification_dta_solvers.py": {"test_DTA_dynamic_congestion_pricing_on_highway_bottleneck"},
+                         "test_cpp_mode.py": {"test_DTA_dynamic_congestion_pricing_on_highway_bottleneck"}}
 
 
 def _reference_root():
@@ -50,6 +62,8 @@ def _reference_root():
 def _run(ref_root, fname, lib, extra=()):
     env = dict(os.environ, UXSIM_B200_SUITE_LIB=lib, UXSIM_REFERENCE_ROOT=ref_root,
                PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), ROOT, os.environ.get("PYTHONPATH", "")]))
+    if fname in DESELECT and not extra:
+        extra = ("-k", DESELECT[fname])
     cmd = [sys.executable, "-m", "pytest", "-p", "ref_suite_plugin", "-p", "no:cacheprovider", "-q", "-rfEp", "--tb=line",
            os.path.join("tests", fname), *extra]
     out = subprocess.run(cmd, cwd=ref_root, env=env, capture_output=True, text=True, timeout=3000).stdout  # cwd: the tests read "dat/..."
@@ -65,7 +79,7 @@ def _check(ref_root, fname, lib):
     expected = EXPECTED_FAIL.get(fname, set())
     unstable = UNSTABLE_IN_REFERENCE.get(fname, set())
     bad = sorted(t for t, r in res.items() if r != "PASSED" and t not in expected and t not in unstable)
-    for _ in range(3):  # the reference marks its stochastic tests `flaky(reruns=...)`
+    for _ in range(5):  # the reference marks its stochastic tests `flaky(reruns=...)`, up to 10
         if not bad:
             break
         again, out = _run(ref_root, fname, lib, ("-k", " or ".join(bad)))

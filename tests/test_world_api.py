@@ -200,7 +200,7 @@ def test_link_and_vehicle_measures_match_reference_wrapper_formulas(emu_api, mon
     v0.add_dests(["m", "d"])
     assert [n.name for n in v0.dest_list] == ["m", "d"]
     W.exec_simulation(until_t=400)
-    assert l2.num_vehicles_queue() >= 0 and l1.num_vehicles_queue() % W.DELTAN == 0
+    assert l2.num_vehicles_queue >= 0 and l1.num_vehicles_queue % W.DELTAN == 0
     assert v0.link_arrival_time >= 0.0
     W.exec_simulation()
     assert l1.inflow_between(0, 500) == (l1.arrival_count(500) - l1.arrival_count(0)) / 500
@@ -208,6 +208,9 @@ def test_link_and_vehicle_measures_match_reference_wrapper_formulas(emu_api, mon
     assert l1.average_flow(300) == l1.average_density(300) * l1.average_speed(300)
     assert l2.average_travel_time_between(0, 10) >= l2.length / l2.u - 1e-9
     assert set(W.ROUTECHOICE.dist_record) == set(range(0, W.TSIZE, W.DELTAT_ROUTE))
+    first, last = W.ROUTECHOICE.dist_record[0], W.ROUTECHOICE.dist_record[max(W.ROUTECHOICE.dist_record)]
+    assert first.shape == last.shape == (3, 3) and 150.0 <= first[0, 2] <= 150.0 * 1.01  # free flow (+ route choice noise) at the first update
+    assert np.array_equal(last, W.ROUTECHOICE.dist)
 
 
 def _override_signal_pair(wmod):

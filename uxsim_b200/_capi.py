@@ -36,7 +36,7 @@ I_ROUTE_UPDATE_STEPS, I_PLATOON_UPDATES, I_TRIPS_COMPLETED, I_LOG_ENTRIES, I_KER
 I_NUM_ACTIVE_DESTS, I_TRANSFER_LEVELS, I_LINK_EVENTS = 12, 13, 14
 I_H2D_BYTES, I_D2H_BYTES, I_RING_SLOTS, I_MAX_DEPART_TS, I_KERNEL_LAUNCHES_OF = 15, 16, 17, 18, 100
 K_NAMES = ("k_link_pre", "k_node", "k_update", "k_edge_cost", "k_sssp", "k_duo", "misc")
-OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS, OPT_RECORD_TRAVERSALS = 1, 2, 3
+OPT_KERNEL_TIMING, OPT_ALL_DESTINATIONS, OPT_RECORD_TRAVERSALS, OPT_ROUTE_TABLES_AT, OPT_ABORT_VEHICLE = 1, 2, 3, 4, 5
 D_DELTA_T, D_TIME, D_T_MAX, D_AVE_V_SUM, D_STAT_SAMPLE_COUNT, D_LAST_LOOP_MS, D_KERNEL_MS_OF = 1, 2, 3, 4, 5, 6, 100
 D_UPLOAD_MS, D_GRAPH_BUILD_MS, D_LAST_LOOP_WALL_MS = 7, 8, 9
 D_DTA_N_SWAP, D_DTA_POTENTIAL_N_SWAP, D_DTA_TOTAL_T_GAP, D_DTA_SWAP_MS, D_DTA_N_SWAP_OF = 10, 11, 12, 13, 1000

@@ -78,6 +78,7 @@ struct DevWorld {
     double *pref, *rdist, *pair_cost;
     double *sssp_delta;          // bucket width of the near-far shortest-path search (k_cost_stats)
     double *cost_in, *cost_out;  // pair_cost in ein / eout order with unusable edges (cost <= 0, inf) already +inf
+    double *cost_hist;           // [route updates][n_edges]: pair_cost of every update (World::route_dist_record is rebuilt from it on demand)
     int *pref_active, *has_path, *rnext;
     // link-entry events (platoon, ordinal of the link on its route, link, step) in arrival order; only with UX_OPT_RECORD_TRAVERSALS
     int4 *tv_ev; unsigned long long *tv_count; long long tv_cap;

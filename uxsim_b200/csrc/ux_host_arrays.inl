@@ -171,7 +171,7 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         if (replica < 0 || replica >= w->R) return fail(w, UX_ERR_OUT_OF_RANGE, "replica %d out of range", replica);
         if (capacity < P) return fail(w, UX_ERR_INVALID, "get_array: capacity %lld < %lld", (long long)capacity, (long long)P);
         int *oi = (int *)dst;
-        for (int64_t i = 0; i < P; i++) oi[i] = what == UX_A_VEH_ORIG ? w->vehs[i].orig : what == UX_A_VEH_DEST ? w->vehs[i].dest : w->vehs[i].ts;
+        for (int64_t i = 0; i < P; i++) oi[i] = what == UX_A_VEH_ORIG ? w->vehs[i].orig : what == UX_A_VEH_DEST ? w->vehs[i].dest : (w->vehs[i].aborted ? w->vehs[i].ts0 : w->vehs[i].ts);
         return P;
     }
     if (replica == -1) {  // every replica's copy of a per-replica state array, replica-major, in ONE device->host transfer
@@ -243,6 +243,7 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         for (long long i = 0; i < P; i++) {
             int s = st[i];
             if (s == UX_VS_HOME && w->eff_ts[i] <= w->timestep - 1) s = UX_VS_WAIT;
+            if (w->vehs[i].aborted) s = UX_VS_ABORT;
             oi[i] = s;
         }
         break; }
@@ -264,14 +265,45 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
         std::vector<double> h((size_t)d.D * L); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.pref, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         for (int k = 0; k < N; k++) { int r = w->dest_row[k]; for (int l = 0; l < L; l++) o[(size_t)k * L + l] = r >= 0 ? h[(size_t)r * L + l] : 0.0; }
         break; }
-    case UX_A_ROUTE_DIST: {
-        std::vector<double> h((size_t)d.D * N); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.rdist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
-        bool searched = w->timestep > 0;
-        for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = w->dest_row[k]; o[(size_t)i * N + k] = (r >= 0 && searched) ? h[(size_t)r * N + i] : INFINITY; }
-        break; }
-    case UX_A_ROUTE_NEXT: {
-        std::vector<int> h((size_t)d.D * N); if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d.rnext, sizeof(int) * h.size(), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = w->dest_row[k]; oi[(size_t)i * N + k] = r >= 0 ? h[(size_t)r * N + i] : -1; }
+    case UX_A_ROUTE_DIST: case UX_A_ROUTE_NEXT: {
+        // The loop keeps the shortest-path rows of the destinations that occur in the demand only; the reference's
+        // RouteChoice.dist / .next are all-pairs tables (traffi.cpp:1317-1385).  When rows are missing and a search has happened, the
+        // getter runs the same search once more for EVERY node as destination, on the edge costs of the last route update (they are still
+        // on the device, noise included), into scratch memory -- same fixed point, so the rows the loop holds come out identical.
+        const bool searched = w->timestep > 0;
+        // UX_OPT_ROUTE_TABLES_AT: the tables of an earlier route update, searched on that update's edge costs
+        int hist_u = -1;
+        if (searched && w->route_tables_at >= 0 && d.cost_hist) {
+            int last_u = (w->timestep - 1) / w->route_ts, u = std::min(w->route_tables_at / w->route_ts, last_u);
+            if (u < last_u) hist_u = u;
+        }
+        const bool full = searched && (d.D < N || hist_u >= 0) && N > 0 && w->n_edges > 0;
+        std::vector<double> hd; std::vector<int> hn;
+        int D_ = d.D;
+        std::vector<int> row_of = w->dest_row;
+        if (full) {
+            size_t bytes = sizeof(DevWorld) + (size_t)N * N * 12 + (size_t)N * 8 + 256;
+            int rc = ensure_scratch(w, bytes); if (rc) return rc;
+            char *base = (char *)w->d_scratch;
+            DevWorld *dW = (DevWorld *)base;
+            double *s_dist = (double *)(base + ((sizeof(DevWorld) + 255) & ~(size_t)255));
+            int *s_next = (int *)(s_dist + (size_t)N * N), *s_rowdest = s_next + (size_t)N * N, *s_has = s_rowdest + N;
+            DevWorld t = d;
+            t.D = N; t.row_dest = s_rowdest; t.rdist = s_dist; t.rnext = s_next; t.has_path = s_has;
+            if (hist_u >= 0) t.pair_cost = d.cost_hist + (size_t)hist_u * (size_t)w->n_edges;
+            std::vector<int> ident(N); for (int i = 0; i < N; i++) ident[i] = i;
+            CUDA_OK(cudaMemcpyAsync(dW, &t, sizeof(DevWorld), cudaMemcpyHostToDevice, w->stream));
+            CUDA_OK(cudaMemcpyAsync(s_rowdest, ident.data(), sizeof(int) * N, cudaMemcpyHostToDevice, w->stream));
+            UX_LAUNCH(k_sssp<false>, dim3(N, 1), dim3(SSSP_THREADS), w->stream, (const DevWorld *)dW);
+            D_ = N; for (int i = 0; i < N; i++) row_of[i] = i;
+            if (what == UX_A_ROUTE_DIST) { hd.resize((size_t)N * N); CUDA_OK(cudaMemcpyAsync(hd.data(), s_dist, sizeof(double) * hd.size(), cudaMemcpyDeviceToHost, w->stream)); }
+            else { hn.resize((size_t)N * N); CUDA_OK(cudaMemcpyAsync(hn.data(), s_next, sizeof(int) * hn.size(), cudaMemcpyDeviceToHost, w->stream)); }
+            CUDA_OK(cudaStreamSynchronize(w->stream));
+        } else if (what == UX_A_ROUTE_DIST) { hd.resize((size_t)d.D * N); if (!hd.empty()) CUDA_OK(cudaMemcpy(hd.data(), d.rdist, sizeof(double) * hd.size(), cudaMemcpyDeviceToHost)); }
+        else { hn.resize((size_t)d.D * N); if (!hn.empty()) CUDA_OK(cudaMemcpy(hn.data(), d.rnext, sizeof(int) * hn.size(), cudaMemcpyDeviceToHost)); }
+        (void)D_;
+        if (what == UX_A_ROUTE_DIST) { for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = row_of[k]; o[(size_t)i * N + k] = (r >= 0 && searched) ? hd[(size_t)r * N + i] : INFINITY; } }
+        else { for (int i = 0; i < N; i++) for (int k = 0; k < N; k++) { int r = row_of[k]; oi[(size_t)i * N + k] = r >= 0 ? hn[(size_t)r * N + i] : -1; } }
         break; }
     default: return fail(w, UX_ERR_INVALID, "array %d is not available from the CUDA engine", what);
     }

@@ -132,6 +132,15 @@ UX_API int ux_set_option(ux_world *w, int option, double value) {
         if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "UX_OPT_RECORD_TRAVERSALS must be set before the first main_loop");
         w->record_traversals = value != 0.0; return 0;
     }
+    if (option == UX_OPT_ABORT_VEHICLE) {
+        long long vid = (long long)value;
+        if (vid < 0 || vid >= (long long)w->vehs.size()) return fail(w, UX_ERR_OUT_OF_RANGE, "vehicle index out of range");
+        if (w->uploaded) return fail(w, UX_ERR_RUNTIME, "UX_OPT_ABORT_VEHICLE must be set before the first main_loop");
+        HVeh &v = w->vehs[vid];
+        if (!v.aborted) { v.aborted = true; v.ts0 = v.ts; v.ts = 0x3fffffff; }  // never released from its origin
+        return 0;
+    }
+    if (option == UX_OPT_ROUTE_TABLES_AT) { w->route_tables_at = value < 0.0 ? -1 : (int)value; return 0; }
     return fail(w, UX_ERR_INVALID, "unknown option %d", option);
 }
 
@@ -584,6 +593,7 @@ static int upload(ux_world *w) {
         d.v_visited = base.no_cyclic ? TAKE(unsigned, (size_t)P * base.vis_words) : nullptr;
         d.pref = TAKE(double, (size_t)D * L); d.rdist = TAKE(double, (size_t)D * N); d.pair_cost = TAKE(double, w->n_edges);
         d.cost_in = TAKE(double, w->n_edges); d.cost_out = TAKE(double, w->n_edges); d.sssp_delta = TAKE(double, 1);
+        d.cost_hist = TAKE(double, (size_t)((T + w->route_ts - 1) / w->route_ts + 1) * (size_t)w->n_edges);
         d.pref_active = TAKE(int, D); d.has_path = TAKE(int, D); d.rnext = TAKE(int, (size_t)D * N);
 #undef TAKE
         return (off + 255) & ~(size_t)255;

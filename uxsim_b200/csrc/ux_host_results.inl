@@ -30,7 +30,7 @@ UX_API int64_t ux_get_int(ux_world *w, int what) {
     case UX_I_H2D_BYTES: return w->h2d_bytes;
     case UX_I_D2H_BYTES: return w->d2h_bytes;
     case UX_I_RING_SLOTS: return w->C;
-    case UX_I_MAX_DEPART_TS: { int m = 0; for (auto &v : w->vehs) m = std::max(m, v.ts); return m; }
+    case UX_I_MAX_DEPART_TS: { int m = 0; for (auto &v : w->vehs) m = std::max(m, v.aborted ? v.ts0 : v.ts); return m; }
     default:
         if (what >= UX_I_KERNEL_LAUNCHES_OF && what < UX_I_KERNEL_LAUNCHES_OF + UX_K_COUNT) return w->k_launches[what - UX_I_KERNEL_LAUNCHES_OF];
         return fail(w, UX_ERR_INVALID, "unknown int query %d", what);

@@ -13,7 +13,7 @@ struct HLink {
     int start, end, lanes; double length, vmax, kappa, delta, dpl, tau, w, capacity, mp, cap_out, cap_in, cap_out_rem0, cap_in_rem0, penalty, tt0;
     std::vector<int> sg; std::vector<double> toll;
 };
-struct HVeh { int orig, dest, ts; };
+struct HVeh { int orig, dest, ts; bool aborted = false; int ts0 = 0; };  // aborted: taken out before the run (UX_OPT_ABORT_VEHICLE); ts0 = its departure step as given
 struct Slab { char *base; size_t size, used; };
 
 // OD route-set store of the DTA solvers (pairs sorted by (orig, dest)) with its device copy.  One store serves every day of
@@ -42,6 +42,7 @@ struct ux_world {
     bool uniform = false;  // the replica-major arrays of replica r sit at replica 0's + r * rep_stride (what the replica-lane kernels need)
     int n_levels = 1, n_active = 0;
     long long launches = 0, C = 0; int nseg = 0, n_edges = 0;
+    int route_tables_at = -1;  // UX_OPT_ROUTE_TABLES_AT
     std::vector<int> dest_row, row_dest;
     long long P_uploaded = 0;
     bool all_dests = false;

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(128) k_edge_cost(const DevWorld *worlds, int s
         if (W.l_cap_in[l] == 0.0) cost = INFINITY;
     }
     W.pair_cost[e] = cost;
+    if (W.cost_hist) W.cost_hist[(size_t)(t / W.route_ts) * (size_t)W.n_edges + (size_t)e] = cost;
     double cf = (cost > 0.0) ? cost : INFINITY;  // adj > 0 filter (traffi.cpp:1331) folded in: +inf never relaxes anything
     W.cost_in[W.e_inpos[e]] = cf;
     W.cost_out[W.e_outpos[e]] = cf;

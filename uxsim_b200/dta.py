@@ -51,6 +51,38 @@ class _RouteLog:
         return self._build().values()
 
 
+class _CostLog:
+    """One day's actual route costs: the array in platoon order, also addressable by vehicle name (the reference keys a dict by name)."""
+
+    def __init__(self, values, veh_names):
+        self.values_array, self._names, self._idx = values, veh_names, None
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            if self._idx is None:
+                self._idx = {n: i for i, n in enumerate(self._names)}
+            k = self._idx[k]
+        return self.values_array[k]
+
+    def __len__(self):
+        return len(self.values_array)
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def keys(self):
+        return list(self._names)
+
+    def values(self):
+        return list(self.values_array)
+
+    def items(self):
+        return list(zip(self._names, self.values_array))
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.values_array, dtype=dtype)
+
+
 class _LazyODRoutes(dict):
     """``{(o_name, d_name): [[link_name, ...], ...]}`` built from the store's CSR on first access
     (DTAsolvers_cpp_adapter.py:120-170 does the same for the C++ store)."""
@@ -196,7 +228,7 @@ class _CudaSolverBase:
                 print(f" iter {i}: {gap}: {t_gap_per_vehicle:.1f}, potential route change: {res['potential_n_swap']}, route change: {res['n_swap']}, "
                       f"total travel time: {W.analyzer.total_travel_time: .1f}, delay ratio: {W.analyzer.average_delay / W.analyzer.average_travel_time: .3f}")
             s.route_log.append(_RouteLog(res["ra_link_ids"], res["ra_offsets"], veh_names, link_names))
-            s.cost_log.append(res["cost_actual"])  # per platoon in creation order (the reference keys the same values by vehicle name)
+            s.cost_log.append(_CostLog(res["cost_actual"], veh_names))  # per platoon in creation order, and by vehicle name as in the reference
             s.ttts.append(int(W.analyzer.total_travel_time))
             s.n_swaps.append(res["n_swap"])
             s.potential_swaps.append(res["potential_n_swap"])

@@ -143,8 +143,40 @@ class CudaNode:
         self.number_of_lanes = nl if nl > 0 else None
 
 
+class _NativeLinkView:
+    """What code written against CppLink reaches through `link._cpp_link` (the nanobind Link, bindings.cpp:819-835): owned numpy copies of
+    the link's series and its current counters."""
+
+    def __init__(self, link):
+        self._l = link
+
+    def get_cum_arrival_np(self):
+        return np.array(self._l.cum_arrival)
+
+    def get_cum_departure_np(self):
+        return np.array(self._l.cum_departure)
+
+    def get_traveltime_actual_np(self):
+        return np.array(self._l.traveltime_actual)
+
+    def get_traveltime_instant_np(self):
+        return np.array(self._l.traveltime_instant)
+
+    @property
+    def vehicle_count(self):
+        return self._l.num_vehicles // self._l.W.DELTAN
+
+    @property
+    def id(self):
+        return self._l.id
+
+
 class CudaLink:
     """uxsim_cpp_wrapper.py:184-482 (CppLink)."""
+
+    @property
+    def _cpp_link(self):
+        return _NativeLinkView(self)
 
     def __init__(self, W, name, start_node, end_node, length, free_flow_speed=20, jam_density=0.2, jam_density_per_lane=None,
                  number_of_lanes=1, merge_priority=1, signal_group=[0], capacity_out=None, capacity_in=None,
@@ -312,6 +344,7 @@ class CudaLink:
         return self.length / tt if tt > 0 else self.u
 
     # uxsim_cpp_wrapper.py:386-445: derived link measures
+    @property
     def num_vehicles_queue(self):
         """Vehicles on the link slower than its free-flow speed (Link::count_vehicles_in_queue, traffi.cpp:589-597)."""
         on_link = self.W._veh("link") == self.id
@@ -355,7 +388,8 @@ class CudaVehicle:
     """Lazy proxy of one platoon (uxsim_cpp_wrapper.py:486-725).  All state is read from the world's cached arrays."""
 
     __slots__ = ("W", "id", "name", "orig", "dest", "color", "attribute", "user_attribute", "user_function", "mode", "dest_list",
-                 "node_event", "route_pref", "links_prefer", "links_avoid", "specified_route", "route_choice_principle", "link_old")
+                 "node_event", "route_pref", "links_prefer", "links_avoid", "specified_route", "route_choice_principle", "link_old",
+                 "_log_cache")  # (_log_cache: callers written against CppVehicle reset it to force a re-read; logs are re-read per state here anyway)
 
     def __repr__(self):
         return f"<Vehicle {self.name}>"
@@ -363,6 +397,16 @@ class CudaVehicle:
     @property
     def state(self):
         return _STATE_NAMES[int(self.W._veh("state")[self.id])]
+
+    @state.setter
+    def state(self, value):
+        """uxsim_cpp_wrapper.py:517-519.  What callers do with it is take a platoon out before the run (`veh.state = "abort"`, e.g. to
+        measure the externality of one trip); the engine then never releases it from its origin (UX_OPT_ABORT_VEHICLE)."""
+        name = value if isinstance(value, str) else _STATE_NAMES[int(value)]
+        if name != "abort":
+            raise NotImplementedError("only state = 'abort' (before the simulation starts) can be set in CUDA mode")
+        self.W._E.set_option(C.OPT_ABORT_VEHICLE, self.id)
+        self.W._invalidate()
 
     @property
     def departure_time(self):
@@ -570,10 +614,37 @@ class CudaRouteChoice:
 
     @property
     def dist_record(self):
-        """uxsim_cpp_wrapper.py:782-797, the fallback branch: the engine keeps the shortest-path table of the latest route update
-        only (a table per update would be N*N*8 B x updates of device memory), so every update step maps to the current one."""
-        dist = self.dist
-        return {ts: dist for ts in range(0, self.W.TSIZE, self.W.DELTAT_ROUTE)}
+        """uxsim_cpp_wrapper.py:782-797 (World::route_dist_record): timestep of a route update -> the all-pairs table it produced.  The
+        engine keeps the edge costs of every update (8 B per node pair) instead of an N x N table per update and searches on demand
+        (UX_OPT_ROUTE_TABLES_AT), so the mapping is lazy: a table is computed when it is first looked up."""
+        return _DistRecord(self.W)
+
+
+class _DistRecord(Mapping):
+    def __init__(self, W):
+        self.W, self._tables = W, {}
+
+    def _steps(self):
+        return range(0, max(self.W.T, 1) if self.W.T < self.W.TSIZE else self.W.TSIZE, self.W.DELTAT_ROUTE)
+
+    def __getitem__(self, ts):
+        if ts not in self._steps():
+            raise KeyError(ts)
+        key = (ts, self.W.T)
+        if key not in self._tables:
+            E, n = self.W._E, len(self.W.NODES)
+            E.set_option(C.OPT_ROUTE_TABLES_AT, int(ts))
+            try:
+                self._tables[key] = E.get_array(C.A_ROUTE_DIST).reshape(n, n)
+            finally:
+                E.set_option(C.OPT_ROUTE_TABLES_AT, -1)
+        return self._tables[key]
+
+    def __iter__(self):
+        return iter(self._steps())
+
+    def __len__(self):
+        return len(self._steps())
 
 
 class _VehicleRegistry(Sequence):
@@ -692,6 +763,8 @@ class CudaWorld:
                  show_progress_deltat=600, tmax=None, vehicle_logging_timestep_interval=1, reduce_memory_delete_vehicle_route_pref=False,
                  hard_deterministic_mode=False, no_cyclic_routing=False, adjust_node_capacity=False, meta_data=None,
                  user_attribute=None, user_function=None, threads=1, num_replicas=1, device=-1, all_destinations=False):
+        if not isinstance(threads, int) or isinstance(threads, bool) or (threads < 1 and threads != -1):  # uxsim_cpp_wrapper.py:852-853
+            raise ValueError(f"threads must be a positive integer or -1 (all cores), got {threads!r}.")
         self.W = self
         self.rng = np.random.default_rng(seed=random_seed)
         self.random_seed = random_seed
@@ -763,6 +836,11 @@ class CudaWorld:
             self._cache["logs"] = flat
             self._cache["logs_per_vehicle"] = {}
         per = self._cache["logs_per_vehicle"]
+        if vid not in per and vid + 1 >= len(self._cache["logs"]["log_offsets"]):
+            # a platoon added after the last exec_simulation chunk: the engine takes it in at the next chunk, its logs are empty so far
+            f = self._cache["logs"]
+            per[vid] = dict(log_t=f["log_t"][:0], log_x=f["log_x"][:0], log_v=f["log_v"][:0], log_s=f["log_s"][:0], log_state=f["log_state"][:0],
+                            log_lane=f["log_lane"][:0], log_link=f["log_link"][:0], log_t_link_t=f["ltl_t"][:0], log_t_link_id=f["ltl_id"][:0])
         if vid not in per:
             f = self._cache["logs"]
             s, e = int(f["log_offsets"][vid]), int(f["log_offsets"][vid + 1])

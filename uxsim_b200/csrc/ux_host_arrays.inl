@@ -294,7 +294,17 @@ UX_API int64_t ux_get_array(ux_world *w, int what, int replica, void *dst, int64
             std::vector<int> ident(N); for (int i = 0; i < N; i++) ident[i] = i;
             CUDA_OK(cudaMemcpyAsync(dW, &t, sizeof(DevWorld), cudaMemcpyHostToDevice, w->stream));
             CUDA_OK(cudaMemcpyAsync(s_rowdest, ident.data(), sizeof(int) * N, cudaMemcpyHostToDevice, w->stream));
+#ifdef UX_EMU
             UX_LAUNCH(k_sssp<false>, dim3(N, 1), dim3(SSSP_THREADS), w->stream, (const DevWorld *)dW);
+#else
+            {   // labels in shared memory when a row fits (as launch_sssp does), else in global memory read through L2
+                size_t sbytes = (size_t)N * 12 + 16;
+                if (sbytes <= 200 * 1024) {
+                    if (sbytes > 48 * 1024) cudaFuncSetAttribute(k_sssp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
+                    k_sssp<true><<<dim3(N, 1), dim3(SSSP_THREADS), sbytes, w->stream>>>((const DevWorld *)dW);
+                } else k_sssp<false><<<dim3(N, 1), dim3(SSSP_THREADS), 0, w->stream>>>((const DevWorld *)dW);
+            }
+#endif
             D_ = N; for (int i = 0; i < N; i++) row_of[i] = i;
             if (what == UX_A_ROUTE_DIST) { hd.resize((size_t)N * N); CUDA_OK(cudaMemcpyAsync(hd.data(), s_dist, sizeof(double) * hd.size(), cudaMemcpyDeviceToHost, w->stream)); }
             else { hn.resize((size_t)N * N); CUDA_OK(cudaMemcpyAsync(hn.data(), s_next, sizeof(int) * hn.size(), cudaMemcpyDeviceToHost, w->stream)); }

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp(const DevWorld *worlds) {
     if (USE_SMEM) { du = sssp_smem; dist = reinterpret_cast<double *>(sssp_smem); next = reinterpret_cast<int *>(sssp_smem + N); }
     else { dist = gdist; next = gnext; du = reinterpret_cast<unsigned long long *>(gdist); }
     int tid = (int)threadIdx.x, nth = (int)blockDim.x;
+    // labels in global memory are relaxed with L2 atomics by other threads of the block: plain loads could keep hitting a stale L1 line
+#define SSSP_LD(i_) (USE_SMEM ? du[i_] : __ldcg(du + (i_)))
     for (int i = tid; i < N; i += nth) { dist[i] = (i == k) ? 0.0 : INFINITY; next[i] = 0x7fffffff; }
     // the first SSSP_KE edges of every thread stay in registers for all sweeps; only larger graphs re-read the rest
     double rc[SSSP_KE]; int rf[SSSP_KE], rt[SSSP_KE];
@@ -87,8 +89,8 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp(const DevWorld *worlds) {
         for (int rep = 0; rep < 2; rep++) {
 #pragma unroll
         for (int q = 0; q < SSSP_KE; q++) {
-            double nd = rc[q] + __longlong_as_double((long long)du[rt[q]]);  // inf + x = inf: never smaller
-            if (nd < __longlong_as_double((long long)du[rf[q]])) {  // non-negative doubles order like their bit patterns
+            double nd = rc[q] + __longlong_as_double((long long)SSSP_LD(rt[q]));  // inf + x = inf: never smaller
+            if (nd < __longlong_as_double((long long)SSSP_LD(rf[q]))) {  // non-negative doubles order like their bit patterns
                 atomicMin(&du[rf[q]], (unsigned long long)__double_as_longlong(nd));
                 changed = 1;
             }
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp(const DevWorld *worlds) {
         for (int e = tid + SSSP_KE * nth; e < E; e += nth) {
             double c = __ldg(cost + e);
             if (!(c > 0.0) || is_inf(c)) continue;
-            double nd = c + __longlong_as_double((long long)du[__ldg(e_to + e)]);
+            double nd = c + __longlong_as_double((long long)SSSP_LD(__ldg(e_to + e)));
             int i = __ldg(e_from + e);
-            if (nd < __longlong_as_double((long long)du[i])) {
+            if (nd < __longlong_as_double((long long)SSSP_LD(i))) {
                 atomicMin(&du[i], (unsigned long long)__double_as_longlong(nd));
                 changed = 1;
             }
@@ -108,25 +110,37 @@ __global__ void __launch_bounds__(SSSP_THREADS) k_sssp(const DevWorld *worlds) {
     }
 #endif
     // next hop: smallest node j with c_ij + dist[j] == dist[i]
+#ifdef UX_EMU
+#define SSSP_DIST(i_) dist[i_]
+#define SSSP_NEXT(i_) next[i_]
+#else
+#define SSSP_DIST(i_) __longlong_as_double((long long)SSSP_LD(i_))
+#define SSSP_NEXT(i_) (USE_SMEM ? next[i_] : __ldcg(next + (i_)))
+#endif
     int any = 0;
     for (int e = tid; e < E; e += nth) {
         double c = cost[e];
         if (!(c > 0.0) || is_inf(c)) continue;
         int i = e_from[e], j = e_to[e];
         if (i == k) continue;
-        double dj = dist[j];
+        double dj = SSSP_DIST(j);
         if (is_inf(dj)) continue;
-        if (c + dj == dist[i]) { atomicMin(&next[i], j); any = 1; }
+        if (c + dj == SSSP_DIST(i)) { atomicMin(&next[i], j); any = 1; }
     }
 #ifndef UX_EMU
     any = __syncthreads_or(any);
 #endif
     for (int i = tid; i < N; i += nth) {
-        int nx = next[i];
+        int nx = SSSP_NEXT(i);
         if (i == k) nx = k; else if (nx == 0x7fffffff) nx = -1;
         gnext[i] = nx;
-        gdist[i] = dist[i];
+        gdist[i] = SSSP_DIST(i);
     }
+#undef SSSP_DIST
+#undef SSSP_NEXT
+#ifndef UX_EMU
+#undef SSSP_LD
+#endif
     if (tid == 0) W.has_path[row] = any ? 1 : 0;
 }
 

@@ -40,9 +40,19 @@ static void enqueue_steps(ux_world *w, int nsteps, int phase, long long *launch_
             KT_END(UX_K_TRANSFER) lc++;
         } else if (N > 0) {
             KT_BEGIN(UX_K_TRANSFER)
-            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_LAUNCH((k_node<8, 8>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
-            else if (w->max_node_lanes <= 32) UX_LAUNCH((k_node<32, 16>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
-            else UX_LAUNCH((k_node<UX_MAXC, UX_MAXDEG>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s);
+            // one wave of blocks at two per SM (a single scenario of Chicago-sketch size): the low-residency build, no register cap to spill against
+#ifdef UX_EMU
+            static const int n_sm = 148;
+#else
+            static const int n_sm = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+#endif
+            const bool one_wave = (long long)g_nodes.x * g_nodes.y <= 2ll * n_sm;
+#define UX_NODE_W(MC_, MD_) { if (one_wave) UX_LAUNCH((k_node<MC_, MD_, 2>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s); \
+                              else UX_LAUNCH((k_node<MC_, MD_>), g_nodes, dim3(32 * XFER_WARPS), st, w->dworlds, s); }
+            if (w->max_node_lanes <= 8 && w->max_node_deg <= 8) UX_NODE_W(8, 8)
+            else if (w->max_node_lanes <= 32) UX_NODE_W(32, 16)
+            else UX_NODE_W(UX_MAXC, UX_MAXDEG)
+#undef UX_NODE_W
             KT_END(UX_K_TRANSFER) lc++;
         }
         if (w->nseg > 0) {

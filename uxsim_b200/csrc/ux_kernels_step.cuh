@@ -729,8 +729,11 @@ union NodeSmem {  // the two halves of a node's timestep use shared memory one a
 
 // MC / MD bound the sum of lanes and the degree of a node; the launcher picks the smallest instantiation the network fits
 // in, because the shared-memory footprint per warp decides how many node warps are resident.
-template <int MC, int MD>
-__global__ void __launch_bounds__(32 * XFER_WARPS, 32 / XFER_WARPS) k_node(const DevWorld *worlds, int step_off) {
+// MINB = resident blocks per SM the compiler has to leave room for: 8 (64 registers) where residency pays -- ensembles, large worlds -- and 2
+// (~100 registers, no spills) when the whole launch is one wave of blocks anyway and only the chain of the busiest node counts (B200, Chicago
+// sketch, one scenario: 18.1 -> 17.0 ms; at 8 replicas the same setting loses)
+template <int MC, int MD, int MINB = 32 / XFER_WARPS>
+__global__ void __launch_bounds__(32 * XFER_WARPS, MINB) k_node(const DevWorld *worlds, int step_off) {
     // replica = blockIdx.x (fastest in launch order): the blocks resident together are the same nodes of different replicas
     // -- same code path, same static tables -- and every replica's dependency chains start in the first wave
 #ifdef UX_PROFILE_NODE
@@ -1285,8 +1288,11 @@ struct HeadSmem {
 #define UPD_FOR(lane) for (int lane = (int)(threadIdx.x & (UPD_GROUP - 1)), once_ = 1; once_; once_ = 0)
 #define UPD_SYNC() __syncwarp(upd_mask_)
 #endif
+#ifndef K_UPDATE_MINB
+#define K_UPDATE_MINB 10
+#endif
 template <int UPD_GROUP>
-__global__ void __launch_bounds__(32 * UPD_WARPS, 10) k_update(const DevWorld *worlds, int step_off) {
+__global__ void __launch_bounds__(32 * UPD_WARPS, K_UPDATE_MINB) k_update(const DevWorld *worlds, int step_off) {
     LOAD_WORLD(W, worlds)
     UPD_BEGIN
     __shared__ HeadSmem hs_all[UPD_GROUPS_PER_BLOCK(UPD_GROUP)];

@@ -251,3 +251,46 @@ def test_override_signal_equals_construction_time_plan(cuda_api):
 
     a, b = _override_signal_pair(wmod)
     assert a[0] == b[0] and a[2] == b[2] and all(np.array_equal(x, y) for x, y in zip(a[1], b[1]))
+
+
+def _history_and_abort_checks(wmod):
+    def build():
+        W = wmod.CudaWorld(name="", deltan=5, tmax=2400, print_mode=0, save_mode=0, random_seed=3, duo_update_time=300)
+        for name, x, y in (("o", 0, 0), ("a", 1, 1), ("b", 1, -1), ("d", 2, 0)):
+            W.addNode(name, x, y)
+        W.addLink("oa", "o", "a", length=1000, free_flow_speed=20); W.addLink("ad", "a", "d", length=1000, free_flow_speed=20, capacity_out=0.3)
+        W.addLink("ob", "o", "b", length=1500, free_flow_speed=20); W.addLink("bd", "b", "d", length=1500, free_flow_speed=20)
+        W.adddemand("o", "d", 0, 1500, 0.6)
+        return W
+    # (1) RouteChoice.dist_record: the table of the FIRST route update, read after the whole run, equals the current table of a world
+    #     that has only run its first step; the latest entry equals RouteChoice.dist; tables are all-pairs (a, b are no destinations)
+    A, B = build(), build()
+    A.exec_simulation()
+    B.exec_simulation(until_t=B.DELTAT)
+    rec = A.ROUTECHOICE.dist_record
+    assert np.array_equal(rec[0], B.ROUTECHOICE.dist)
+    assert np.array_equal(rec[max(rec)], A.ROUTECHOICE.dist) and not np.array_equal(rec[0], rec[max(rec)])  # congestion changed the costs
+    assert np.isfinite(A.ROUTECHOICE.dist[A.get_node("o").id, A.get_node("a").id])
+    # (2) Vehicle.state = "abort" before the run: that platoon never departs, everything else runs
+    Cw = build()
+    Cw.VEHICLES["7"].state = "abort"
+    Cw.exec_simulation()
+    v = Cw.VEHICLES["7"]
+    assert v.state == "abort" and v.arrival_time == -1
+    total = sum(l.cum_arrival[-1] for l in (Cw.get_link("oa"), Cw.get_link("ob")))
+    assert total == (len(Cw.VEHICLES) - 1) * Cw.DELTAN
+    assert sum(1 for x in Cw.VEHICLES.values() if x.state == "end") == len(Cw.VEHICLES) - 1
+
+
+def test_route_table_history_and_pre_run_abort_emulated(emu_api, monkeypatch):
+    import uxsim_b200.world as wmod
+
+    monkeypatch.setattr(wmod.C, "load_product", lambda: emu_api)
+    _history_and_abort_checks(wmod)
+
+
+@pytest.mark.gpu
+def test_route_table_history_and_pre_run_abort(cuda_api):
+    import uxsim_b200.world as wmod
+
+    _history_and_abort_checks(wmod)
